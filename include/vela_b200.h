@@ -1,0 +1,278 @@
+/*
+ * vela_b200.h — C ABI of libvela_b200.so: the B200 (sm_100a) implementation of
+ * Vela.jl's batched posterior hot path.
+ *
+ * The reference (Vela.jl v0.1.6) has no FFI layer for this path; the seam it
+ * replaces is Julia multiple dispatch on (TimingModel, Vector{TOA}|Vector{WidebandTOA},
+ * params).  Every entry point below names the reference function(s) whose
+ * result it reproduces (paths relative to the reference tree):
+ *
+ *   vela_b200_lnlike_batch   <- calc_lnlike_vectorized   src/likelihood/gls_likelihood.jl:298-309
+ *                               calc_lnlike_serial       src/likelihood/wls_likelihood.jl:49-56,
+ *                                                        src/likelihood/gls_likelihood.jl:249-262
+ *                               calc_lnlike              src/likelihood/wls_likelihood.jl:24-47,
+ *                                                        src/likelihood/gls_likelihood.jl:264-296
+ *   vela_b200_lnpost_batch   <- calc_lnpost_vectorized   src/likelihood/posterior.jl:14-25
+ *                               calc_lnpost(_serial)     src/likelihood/posterior.jl:4-12
+ *   vela_b200_chi2_batch     <- calc_chi2_serial         src/likelihood/wls_chi2.jl:44-51
+ *   vela_b200_residuals      <- form_residuals           src/residuals/residuals.jl:19-26,
+ *                                                        src/residuals/wideband_residuals.jl:24-27
+ *                               _calc_resids_and_Ninvdiag src/likelihood/gls_likelihood.jl:9-79
+ *   vela_b200_noise_weights_inv <- calc_noise_weights_inv src/likelihood/gls_likelihood.jl:3-7
+ *   vela_b200_create/destroy <- Pulsar(model, toas)      src/pulsar/pulsar.jl:9-12
+ *                               (deep copy of the constant model/TOA data to the GPU(s))
+ *
+ * Conventions
+ *  - plain C types only; all pointers are HOST pointers owned by the caller and
+ *    only need to stay valid for the duration of the call (create deep-copies).
+ *  - all quantities are in Vela's internal units (seconds^n; docs/src/quantities.md).
+ *  - return value 0 = success, negative = VelaStatus error; message through
+ *    vela_b200_last_error() (thread-local).  No exceptions, no aborts, no signal
+ *    handlers.  Per-sample numerical failure (non positive-definite Sigma^-1,
+ *    src/likelihood/gls_likelihood.jl:211-213; invalid eccentricity,
+ *    src/model/binary/orbit.jl:26; NaN anywhere) yields -Inf for that sample
+ *    and the call still returns 0.
+ *  - there is NO CPU fallback: every compute entry point fails with
+ *    VELA_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef VELA_B200_H
+#define VELA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VELA_B200_ABI_VERSION 1
+#define VELA_MAX_PAR 24
+
+typedef enum VelaStatus {
+    VELA_OK = 0,
+    VELA_ERR_INVALID_ARG = -1,   /* bad descriptor / shape mismatch (cf. parameter.jl:162) */
+    VELA_ERR_NO_DEVICE = -2,     /* no usable CUDA device: the library has no CPU path */
+    VELA_ERR_CUDA = -3,          /* CUDA runtime error; see vela_b200_last_error() */
+    VELA_ERR_UNSUPPORTED = -4,   /* component / kernel outside the implemented hot path */
+    VELA_ERR_OOM = -5
+} VelaStatus;
+
+/* Timing-model components, in the order-dependent chain of
+ * correct_toa(components::Tuple, ...)  src/model/timing_model.jl:85-98. */
+typedef enum VelaComponentKind {
+    VELA_COMP_SOLAR_SYSTEM = 1,        /* src/model/solarsystem.jl:67-134 */
+    VELA_COMP_SOLAR_WIND = 2,          /* SolarWindDispersion, src/model/solarwind.jl:37-51 */
+    VELA_COMP_DISPERSION_TAYLOR = 3,   /* src/model/dispersion.jl:15-26 */
+    VELA_COMP_DISPERSION_PIECEWISE = 4,/* DMX, src/model/dispersion.jl:43-54 */
+    VELA_COMP_CHROMATIC_TAYLOR = 5,    /* src/model/chromatic.jl:23-34 */
+    VELA_COMP_CHROMATIC_PIECEWISE = 6, /* CMX, src/model/chromatic.jl:46-57 */
+    VELA_COMP_BINARY_ELL1 = 7,         /* src/model/binary/binary_ell1_base.jl:159-180 */
+    VELA_COMP_BINARY_DD = 8,           /* src/model/binary/binary_dd_base.jl:134-162 */
+    VELA_COMP_GLITCH = 9,              /* src/model/glitch.jl:14-38 */
+    VELA_COMP_EXP_DIP = 10,            /* ChromaticExponentialDip, src/model/expdip.jl:11-31 */
+    VELA_COMP_SPINDOWN = 11,           /* src/model/spindown.jl:15-33 */
+    VELA_COMP_PHASE_OFFSET = 12,       /* src/model/phase_offset.jl:12-13 */
+    VELA_COMP_PHASE_JUMP_EXCLUSIVE = 13, /* ExclusivePhaseJump, src/model/jump.jl:31-45 */
+    VELA_COMP_PHASE_JUMP = 14,         /* PhaseJump (BitMatrix), src/model/jump.jl:14-22 */
+    VELA_COMP_MEASUREMENT_NOISE = 15,  /* EFAC/EQUAD, src/model/measurement_noise.jl:20-38 */
+    VELA_COMP_DM_JUMP_EXCLUSIVE = 16,  /* ExclusiveDispersionJump, src/model/dmjump.jl:62-86 */
+    VELA_COMP_DM_JUMP = 17,            /* DispersionJump (BitMatrix), src/model/dmjump.jl:28-47 */
+    VELA_COMP_DM_MEASUREMENT_NOISE = 18 /* DMEFAC/DMEQUAD, src/model/dispersion_measurement_noise.jl:19-46 */
+} VelaComponentKind;
+
+/* VelaComponentDesc.flags */
+#define VELA_FLAG_ECLIPTIC        1   /* SolarSystem.ecliptic_coordinates */
+#define VELA_FLAG_PLANET_SHAPIRO  2   /* SolarSystem.planet_shapiro */
+#define VELA_FLAG_USE_FBX         4   /* BinaryELL1/BinaryDD.use_fbx */
+
+/*
+ * One timing-model component.  `par[]` holds 0-based offsets into the FULL
+ * parameter vector (the flattened `_default_params_tuple`,
+ * src/parameter/parameter.jl:87-92,151-153: non-noise singles, non-noise multis,
+ * noise singles, noise multis); -1 = unused.  For tuple-valued parameters the
+ * offset is that of the first element, the length is in `len[]`.
+ *
+ * Slot meaning per kind (par / len / mask):
+ *  SOLAR_SYSTEM   par: 0 LONG(RAJ|ELONG) 1 LAT(DECJ|ELAT) 2 PMLONG 3 PMLAT 4 PX 5 POSEPOCH
+ *  SOLAR_WIND     par: 0 SWEPOCH 1 NE_SW[0]            len: 0 #NE_SW
+ *  DISPERSION_TAYLOR par: 0 DMEPOCH 1 DM[0]            len: 0 #DM
+ *  DISPERSION_PIECEWISE par: 0 DMX_[0]                 len: 0 #DMX_   mask: 0 dmx index mask
+ *  CHROMATIC_TAYLOR par: 0 CMEPOCH 1 CM[0] 2 TNCHROMIDX len: 0 #CM
+ *  CHROMATIC_PIECEWISE par: 0 CMX_[0] 2 TNCHROMIDX      len: 0 #CMX_   mask: 0 cmx index mask
+ *  BINARY_ELL1    par: 0 TASC 1 PB 2 PBDOT 3 FB[0] 4 A1 5 A1DOT 6 EPS1 7 EPS2 8 EPS1DOT
+ *                      9 EPS2DOT 10 M2 11 SINI          len: 0 #FB
+ *  BINARY_DD      par: 0 T0 1 PB 2 PBDOT 3 FB[0] 4 A1 5 A1DOT 6 ECC 7 EDOT 8 OM 9 OMDOT
+ *                      10 DR 11 DTH 12 GAMMA 13 M2 14 SINI  len: 0 #FB
+ *  GLITCH         par: 0 GLEP_[0] 1 GLPH_[0] 2 GLF0_[0] 3 GLF1_[0] 4 GLF2_[0] 5 GLF0D_[0]
+ *                      6 GLTD_[0]                       len: 0 #glitches
+ *  EXP_DIP        par: 0 EXPDIPFREF 1 EXPDIPEPS 2 EXPDIPEP_[0] 3 EXPDIPAMP_[0] 4 EXPDIPIDX_[0]
+ *                      5 EXPDIPTAU_[0]                  len: 0 #dips
+ *  SPINDOWN       par: 0 F_ 1 F[0]                      len: 0 #F
+ *  PHASE_OFFSET   par: 0 PHOFF
+ *  PHASE_JUMP_EXCLUSIVE par: 0 JUMP[0] 1 F_ 2 F[0]      len: 0 #JUMP  mask: 0 jump index mask
+ *  PHASE_JUMP     par: 0 JUMP[0] 1 F_ 2 F[0]            len: 0 #JUMP  mask: 0 first bit-mask row
+ *  MEASUREMENT_NOISE par: 0 EFAC[0] 1 EQUAD[0]          len: 0 #EFAC 1 #EQUAD
+ *                                                       mask: 0 efac index mask 1 equad index mask
+ *  DM_JUMP_EXCLUSIVE par: 0 DMJUMP[0]                   len: 0 #DMJUMP mask: 0 index mask
+ *  DM_JUMP        par: 0 DMJUMP[0]                      len: 0 #DMJUMP mask: 0 first bit-mask row
+ *  DM_MEASUREMENT_NOISE par: 0 DMEFAC[0] 1 DMEQUAD[0]   len: 0 #DMEFAC 1 #DMEQUAD
+ *                                                       mask: 0 dmefac mask 1 dmequad mask
+ */
+typedef struct VelaComponentDesc {
+    int32_t kind;
+    int32_t flags;
+    int32_t par[VELA_MAX_PAR];
+    int32_t len[4];
+    int32_t mask[2];
+} VelaComponentDesc;
+
+/* Likelihood kernels, src/model/kernel.jl:20,74-92. */
+typedef enum VelaKernelKind {
+    VELA_KERNEL_WHITE = 0,            /* WhiteNoiseKernel */
+    VELA_KERNEL_WOODBURY_WHITE = 2    /* WoodburyKernel{WhiteNoiseKernel} */
+} VelaKernelKind;
+
+/* Amplitude-marginalised Gaussian-process components of a WoodburyKernel. */
+typedef enum VelaGPKind {
+    VELA_GP_POWERLAW_RED = 1,    /* PowerlawRedNoiseGP, ln_js are Float32: src/model/gp_noise.jl:110-115 */
+    VELA_GP_POWERLAW_DM = 2,     /* PowerlawDispersionNoiseGP, src/model/gp_noise.jl:155-160 */
+    VELA_GP_POWERLAW_CHROM = 3,  /* PowerlawChromaticNoiseGP, src/model/gp_noise.jl:207-212 */
+    VELA_GP_MARGINALIZED_TM = 4  /* MarginalizedTimingModel, src/model/marginalized_timing_model.jl:13-26 */
+} VelaGPKind;
+
+typedef struct VelaGPDesc {
+    int32_t kind;
+    int32_t n;               /* power-law GPs: number of harmonics (2n basis columns, [SIN x n, COS x n]);
+                                MARGINALIZED_TM: number of columns */
+    int32_t par_log10_amp;   /* TNREDAMP | TNDMAMP | TNCHROMAMP */
+    int32_t par_gamma;       /* TNREDGAM | TNDMGAM | TNCHROMGAM */
+    int32_t par_f1;          /* PLREDFREQ | PLDMFREQ | PLCHROMFREQ */
+    int32_t _pad;
+    const double* ln_js;        /* n values; RED: the Float32 tuple widened to double (exact) */
+    const double* weights_inv;  /* MARGINALIZED_TM: prior_weights_inv[n] */
+} VelaGPDesc;
+
+/*
+ * TOA records are passed in the memory layout of the reference's isbits structs
+ * so that a Julia caller hands over `pointer(toas)` unchanged:
+ *   TOA (248 bytes, src/toa/toa.jl:39-50 + src/toa/ephemeris.jl:14-23), 31 little-endian 8-byte words:
+ *     0 value.hi 1 value.lo 2 error 3 observing_frequency 4 pulse_number.hi 5 pulse_number.lo
+ *     6-8 ssb_obs_pos 9-11 ssb_obs_vel 12-14 obs_sun_pos 15-17 obs_jupiter_pos 18-20 obs_saturn_pos
+ *     21-23 obs_venus_pos 24-26 obs_uranus_pos 27-29 obs_neptune_pos 30 index (UInt64; 0 = TZR TOA)
+ *   WidebandTOA (264 bytes, src/toa/wideband_toa.jl:18-21,85-88): the TOA record followed by
+ *     31 dminfo.value 32 dminfo.error
+ * The TZR TOA is always a narrowband TOA record (src/model/timing_model.jl:24).
+ */
+#define VELA_TOA_WORDS 31
+#define VELA_WTOA_WORDS 33
+
+typedef struct VelaModelDesc {
+    int32_t abi_version;          /* VELA_B200_ABI_VERSION */
+    int32_t n_components;
+    const VelaComponentDesc* components;
+
+    int32_t n_params;             /* length of the full parameter vector */
+    int32_t n_free;               /* number of free parameters (ndim of the sampler) */
+    const double* default_values; /* ParamHandler._default_values, parameter.jl:130 */
+    const int32_t* free_indices;  /* ParamHandler._free_indices converted to 0-based */
+
+    int64_t n_toas;
+    int32_t wideband;             /* 0: Vector{TOA}; 1: Vector{WidebandTOA} */
+    int32_t toa_stride_bytes;     /* 248 or 264 */
+    const void* toas;             /* n_toas records */
+    const void* tzr_toa;          /* one 248-byte TOA record, index == 0 */
+
+    int32_t n_index_masks;        /* exclusive ("index") masks, each n_toas long */
+    int32_t n_bit_mask_rows;      /* rows of all BitMatrix masks, each n_toas long */
+    const uint32_t* index_masks;  /* [n_index_masks][n_toas]; entry = 1-based group, 0 = none */
+    const uint8_t* bit_masks;     /* [n_bit_mask_rows][n_toas]; entry = 0/1 */
+
+    int32_t kernel_kind;          /* VelaKernelKind */
+    int32_t n_gp;
+    const VelaGPDesc* gp;         /* WoodburyKernel.gp_components, in order */
+    int64_t basis_rows;           /* n_toas (narrowband) or 2*n_toas (wideband) */
+    int64_t basis_cols;           /* p = sum of GP columns */
+    int64_t basis_ld;             /* leading dimension (column-major, Julia Matrix{Float64}) */
+    const double* noise_basis;    /* WoodburyKernel.noise_basis, kernel.jl:77 */
+
+    int32_t n_devices;            /* 0: use the current CUDA device */
+    int32_t _pad;
+    const int32_t* devices;       /* CUDA device ordinals; walkers are split evenly across them */
+} VelaModelDesc;
+
+typedef struct VelaPulsar* VelaHandle;
+
+/* Number of usable CUDA devices (0 if none / no driver). */
+int vela_b200_device_count(void);
+
+/* Thread-local description of the last error returned on this thread. */
+const char* vela_b200_last_error(void);
+
+/* Deep-copies the model and TOA data onto the device(s). */
+int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out);
+int vela_b200_destroy(VelaHandle h);
+
+/* Model shape queries. */
+int vela_b200_n_free(VelaHandle h);
+int64_t vela_b200_n_rows(VelaHandle h);   /* rows of y: n_toas or 2*n_toas */
+int64_t vela_b200_n_basis(VelaHandle h);  /* p */
+
+/*
+ * ln L for a matrix of parameter samples.  Element (b, k) of the (B x n_free)
+ * matrix is params[b*row_stride + k*col_stride] (strides in elements): a
+ * row-major numpy array uses (n_free, 1); a Julia Matrix uses (1, B).
+ * out_lnlike[B].
+ */
+int vela_b200_lnlike_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
+                           int64_t row_stride, int64_t col_stride, double* out_lnlike);
+
+/*
+ * ln posterior = lnprior[b] + ln L_b, with the reference's short-circuit: when
+ * lnprior[b] is not finite the result is lnprior[b] itself (posterior.jl:9-12).
+ * lnprior == NULL means a flat (zero) prior.
+ */
+int vela_b200_lnpost_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
+                           int64_t row_stride, int64_t col_stride, const double* lnprior,
+                           double* out_lnpost);
+
+/* chi^2 = sum r^2/sigma^2 (+ DM term for wideband); white-noise kernels only. */
+int vela_b200_chi2_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
+                         int64_t row_stride, int64_t col_stride, double* out_chi2);
+
+/*
+ * Residuals y[n_rows] (seconds; wideband: [time residuals; DM residuals]) and
+ * N^-1 diagonal w[n_rows] = 1/sigma^2 for ONE parameter vector.
+ * Either output may be NULL.
+ */
+int vela_b200_residuals(VelaHandle h, const double* params, int64_t n_free, double* y, double* w);
+
+/* Phi^-1 (p values) for ONE parameter vector; Woodbury kernels only. */
+int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int64_t n_free, double* phiinv);
+
+/*
+ * Device-resident variant used by benchmarks and by callers that already hold
+ * the samples on the GPU: `d_params` is a row-major (B x n_free) DEVICE buffer on
+ * device `devices[0]`, `d_out` a DEVICE buffer of B doubles.  Work is enqueued on
+ * `stream` (a cudaStream_t passed as void*; NULL = the handle's own stream) and
+ * the call returns without synchronising.
+ */
+int vela_b200_lnlike_batch_device(VelaHandle h, const double* d_params, int64_t B,
+                                  double* d_out, void* stream);
+
+/* Number of kernel launches the handle has issued so far (all devices). */
+int64_t vela_b200_launch_count(VelaHandle h);
+
+/* Wall-free timing hooks: device-time (ms) of the stages of the last batch on device 0,
+ * measured with CUDA events on the handle's stream.  stage: 0 prologue, 1 chain,
+ * 2 sigma contraction, 3 cholesky/finish, 4 total (H2D..D2H).  Returns <0 if
+ * stage timing was not enabled. */
+int vela_b200_set_stage_timing(VelaHandle h, int enabled);
+double vela_b200_last_stage_ms(VelaHandle h, int stage);
+
+/* FP64 micro-benchmarks used for the roofline denominators (TFLOP/s):
+ * kind 0 = register-resident DFMA loop, kind 1 = mma.sync m8n8k4 f64 (DMMA) loop. */
+double vela_b200_fp64_peak_tflops(int device, int kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELA_B200_H */
