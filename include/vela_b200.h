@@ -44,6 +44,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define VELA_API __attribute__((visibility("default")))
+#else
+#define VELA_API
+#endif
+
 #define VELA_B200_ABI_VERSION 1
 #define VELA_MAX_PAR 24
 
@@ -202,19 +208,19 @@ typedef struct VelaModelDesc {
 typedef struct VelaPulsar* VelaHandle;
 
 /* Number of usable CUDA devices (0 if none / no driver). */
-int vela_b200_device_count(void);
+VELA_API int vela_b200_device_count(void);
 
 /* Thread-local description of the last error returned on this thread. */
-const char* vela_b200_last_error(void);
+VELA_API const char* vela_b200_last_error(void);
 
 /* Deep-copies the model and TOA data onto the device(s). */
-int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out);
-int vela_b200_destroy(VelaHandle h);
+VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out);
+VELA_API int vela_b200_destroy(VelaHandle h);
 
 /* Model shape queries. */
-int vela_b200_n_free(VelaHandle h);
-int64_t vela_b200_n_rows(VelaHandle h);   /* rows of y: n_toas or 2*n_toas */
-int64_t vela_b200_n_basis(VelaHandle h);  /* p */
+VELA_API int vela_b200_n_free(VelaHandle h);
+VELA_API int64_t vela_b200_n_rows(VelaHandle h);   /* rows of y: n_toas or 2*n_toas */
+VELA_API int64_t vela_b200_n_basis(VelaHandle h);  /* p */
 
 /*
  * ln L for a matrix of parameter samples.  Element (b, k) of the (B x n_free)
@@ -222,7 +228,7 @@ int64_t vela_b200_n_basis(VelaHandle h);  /* p */
  * row-major numpy array uses (n_free, 1); a Julia Matrix uses (1, B).
  * out_lnlike[B].
  */
-int vela_b200_lnlike_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
+VELA_API int vela_b200_lnlike_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
                            int64_t row_stride, int64_t col_stride, double* out_lnlike);
 
 /*
@@ -230,12 +236,12 @@ int vela_b200_lnlike_batch(VelaHandle h, const double* params, int64_t B, int64_
  * lnprior[b] is not finite the result is lnprior[b] itself (posterior.jl:9-12).
  * lnprior == NULL means a flat (zero) prior.
  */
-int vela_b200_lnpost_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
+VELA_API int vela_b200_lnpost_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
                            int64_t row_stride, int64_t col_stride, const double* lnprior,
                            double* out_lnpost);
 
 /* chi^2 = sum r^2/sigma^2 (+ DM term for wideband); white-noise kernels only. */
-int vela_b200_chi2_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
+VELA_API int vela_b200_chi2_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
                          int64_t row_stride, int64_t col_stride, double* out_chi2);
 
 /*
@@ -243,10 +249,10 @@ int vela_b200_chi2_batch(VelaHandle h, const double* params, int64_t B, int64_t 
  * N^-1 diagonal w[n_rows] = 1/sigma^2 for ONE parameter vector.
  * Either output may be NULL.
  */
-int vela_b200_residuals(VelaHandle h, const double* params, int64_t n_free, double* y, double* w);
+VELA_API int vela_b200_residuals(VelaHandle h, const double* params, int64_t n_free, double* y, double* w);
 
 /* Phi^-1 (p values) for ONE parameter vector; Woodbury kernels only. */
-int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int64_t n_free, double* phiinv);
+VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int64_t n_free, double* phiinv);
 
 /*
  * Device-resident variant used by benchmarks and by callers that already hold
@@ -255,22 +261,22 @@ int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int64_t n_fr
  * `stream` (a cudaStream_t passed as void*; NULL = the handle's own stream) and
  * the call returns without synchronising.
  */
-int vela_b200_lnlike_batch_device(VelaHandle h, const double* d_params, int64_t B,
+VELA_API int vela_b200_lnlike_batch_device(VelaHandle h, const double* d_params, int64_t B,
                                   double* d_out, void* stream);
 
 /* Number of kernel launches the handle has issued so far (all devices). */
-int64_t vela_b200_launch_count(VelaHandle h);
+VELA_API int64_t vela_b200_launch_count(VelaHandle h);
 
 /* Wall-free timing hooks: device-time (ms) of the stages of the last batch on device 0,
  * measured with CUDA events on the handle's stream.  stage: 0 prologue, 1 chain,
  * 2 sigma contraction, 3 cholesky/finish, 4 total (H2D..D2H).  Returns <0 if
  * stage timing was not enabled. */
-int vela_b200_set_stage_timing(VelaHandle h, int enabled);
-double vela_b200_last_stage_ms(VelaHandle h, int stage);
+VELA_API int vela_b200_set_stage_timing(VelaHandle h, int enabled);
+VELA_API double vela_b200_last_stage_ms(VelaHandle h, int stage);
 
 /* FP64 micro-benchmarks used for the roofline denominators (TFLOP/s):
  * kind 0 = register-resident DFMA loop, kind 1 = mma.sync m8n8k4 f64 (DMMA) loop. */
-double vela_b200_fp64_peak_tflops(int device, int kind);
+VELA_API double vela_b200_fp64_peak_tflops(int device, int kind);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,257 @@
+"""The drop-in surface: Vela.jl's public names for the posterior hot path, backed by libvela_b200.so.
+
+Reference names mirrored (paths relative to the reference tree):
+  Pulsar                                      src/pulsar/pulsar.jl:9-25
+  calc_lnlike / calc_lnlike_serial            src/likelihood/wls_likelihood.jl:24-56, gls_likelihood.jl:249-296
+  calc_lnlike_vectorized                      src/likelihood/gls_likelihood.jl:298-309
+  calc_lnprior / prior_transform              src/prior/prior.jl:13-37
+  calc_lnpost / _serial / _vectorized         src/likelihood/posterior.jl:4-25
+  get_lnlike_{serial,parallel}_func, get_lnlike_func   src/likelihood/wls_likelihood.jl:75-104
+  get_lnpost_func                             src/likelihood/posterior.jl:34-46
+  get_lnprior_func / get_prior_transform_func src/prior/prior.jl:26,37
+  calc_chi2(_serial), get_chi2_*func, degrees_of_freedom, calc_chi2_reduced   src/likelihood/wls_chi2.jl
+  form_residuals / _calc_resids_and_Ninvdiag  src/residuals/residuals.jl:19-26, gls_likelihood.jl:9-79
+  calc_noise_weights_inv                      src/likelihood/gls_likelihood.jl:3-7
+Every entry point accepts either (model, toas, params) or (pulsar, params), and `params` may be the
+free-value vector or the full parameter vector returned by `read_params` (the NamedTuple in Julia).
+Serial, parallel and vectorised flavours all map onto the same GPU kernels (B = 1 is a TOA-parallel
+launch); there is no CPU path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import lib as _lib
+from . import priors as _priors
+from .descriptor import ModelDescriptor
+from .model import TimingModel, TOAs, WhiteNoiseKernel
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Pulsar:
+    """`Pulsar(model, toas)`: the object `pyvela.SPNTA` holds; owns the GPU-resident replica."""
+
+    def __init__(self, model: TimingModel, toas: TOAs, devices=None):
+        self.model = model
+        self.toas = toas
+        self.descriptor = ModelDescriptor(model, toas, devices=devices)
+        self._lib = _lib.lib()
+        if self._lib.vela_b200_device_count() <= 0:
+            raise _lib.VelaB200Error("no CUDA device: vela.jl_b200 has no CPU fallback")
+        h = C.c_void_p()
+        _lib.check(self._lib.vela_b200_create(self.descriptor.byref(), C.byref(h)), "vela_b200_create")
+        self._h = h
+        self._finalizer = weakref.finalize(self, self._lib.vela_b200_destroy, h)
+        self.ndim = model.param_handler._nfree
+
+    # -- helpers
+    def _free(self, params) -> np.ndarray:
+        """Accept the free vector or the full parameter vector (NamedTuple analogue)."""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        ph = self.model.param_handler
+        if p.ndim == 1 and p.shape[0] == len(ph._default_values) and p.shape[0] != ph._nfree:
+            p = ph.read_param_values_to_vector(p)
+        return p
+
+    def _batch(self, fn, paramss, *extra) -> np.ndarray:
+        a = np.asarray(paramss, dtype=np.float64)
+        if a.ndim != 2:
+            raise ValueError("paramss must be a (nsamples, ndim) matrix")
+        B, nd = a.shape
+        out = np.empty(B, dtype=np.float64)
+        rs, cs = (s // 8 for s in a.strides) if B > 0 and nd > 0 else (nd, 1)
+        if B > 0 and (a.strides[0] % 8 or a.strides[1] % 8 or rs < 0 or cs < 0):
+            a = np.ascontiguousarray(a)
+            rs, cs = nd, 1
+        _lib.check(fn(self._h, _dp(a), B, nd, rs, cs, *extra, _dp(out)), fn.__name__)
+        return out
+
+    # -- likelihood
+    def lnlike_vectorized(self, paramss) -> np.ndarray:
+        return self._batch(self._lib.vela_b200_lnlike_batch, paramss)
+
+    def lnlike(self, params) -> float:
+        return float(self.lnlike_vectorized(self._free(params)[None, :])[0])
+
+    def chi2_vectorized(self, paramss) -> np.ndarray:
+        return self._batch(self._lib.vela_b200_chi2_batch, paramss)
+
+    def chi2(self, params) -> float:
+        return float(self.chi2_vectorized(self._free(params)[None, :])[0])
+
+    # -- prior / posterior
+    def lnprior(self, params):
+        return _priors.lnprior(self.model.priors, self._free(params) if np.ndim(params) == 1 else params)
+
+    def prior_transform(self, cube):
+        return _priors.prior_transform(self.model.priors, cube)
+
+    def lnpost_vectorized(self, paramss) -> np.ndarray:
+        a = np.asarray(paramss, dtype=np.float64)
+        lnpr = np.ascontiguousarray(_priors.lnprior(self.model.priors, a), dtype=np.float64)
+        return self._batch(self._lib.vela_b200_lnpost_batch, a, _dp(lnpr))
+
+    def lnpost(self, params) -> float:
+        return float(self.lnpost_vectorized(self._free(params)[None, :])[0])
+
+    # -- residuals
+    def resids_and_Ninvdiag(self, params):
+        p = self._free(params)
+        n = int(self._lib.vela_b200_n_rows(self._h))
+        y = np.empty(n)
+        w = np.empty(n)
+        _lib.check(self._lib.vela_b200_residuals(self._h, _dp(p), len(p), _dp(y), _dp(w)), "vela_b200_residuals")
+        return y, w
+
+    def noise_weights_inv(self, params) -> np.ndarray:
+        p = self._free(params)
+        out = np.empty(int(self._lib.vela_b200_n_basis(self._h)))
+        _lib.check(self._lib.vela_b200_noise_weights_inv(self._h, _dp(p), len(p), _dp(out)),
+                   "vela_b200_noise_weights_inv")
+        return out
+
+    # -- benchmarking hooks
+    def lnlike_device(self, d_params_ptr: int, B: int, d_out_ptr: int, stream: int = 0):
+        _lib.check(self._lib.vela_b200_lnlike_batch_device(self._h, C.c_void_p(d_params_ptr), B,
+                                                           C.c_void_p(d_out_ptr), C.c_void_p(stream)),
+                   "vela_b200_lnlike_batch_device")
+
+    def launch_count(self) -> int:
+        return int(self._lib.vela_b200_launch_count(self._h))
+
+    def set_stage_timing(self, on: bool):
+        self._lib.vela_b200_set_stage_timing(self._h, int(on))
+
+    def last_stage_ms(self):
+        return [float(self._lib.vela_b200_last_stage_ms(self._h, s)) for s in range(5)]
+
+
+_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _pulsar(*args):
+    """(pulsar, params) | (model, toas, params) -> (Pulsar, params)"""
+    if isinstance(args[0], Pulsar):
+        return args[0], args[1]
+    model, toas, params = args
+    per_model = _CACHE.setdefault(model, {})
+    psr = per_model.get(id(toas))
+    if psr is None or psr.toas is not toas:
+        psr = Pulsar(model, toas)
+        per_model[id(toas)] = psr
+    return psr, params
+
+
+def calc_lnlike(*args) -> float:
+    psr, params = _pulsar(*args)
+    return psr.lnlike(params)
+
+
+calc_lnlike_serial = calc_lnlike
+
+
+def calc_lnlike_vectorized(*args) -> np.ndarray:
+    psr, paramss = _pulsar(*args)
+    return psr.lnlike_vectorized(paramss)
+
+
+def calc_lnprior(obj, params):
+    model = obj.model if isinstance(obj, Pulsar) else obj
+    p = np.asarray(params, dtype=np.float64)
+    ph = model.param_handler
+    if p.ndim == 1 and p.shape[0] == len(ph._default_values) and p.shape[0] != ph._nfree:
+        p = ph.read_param_values_to_vector(p)
+    return _priors.lnprior(model.priors, p)
+
+
+def prior_transform(obj, cube):
+    model = obj.model if isinstance(obj, Pulsar) else obj
+    return _priors.prior_transform(model.priors, cube)
+
+
+def calc_lnpost(*args) -> float:
+    psr, params = _pulsar(*args)
+    return psr.lnpost(params)
+
+
+calc_lnpost_serial = calc_lnpost
+
+
+def calc_lnpost_vectorized(*args) -> np.ndarray:
+    psr, paramss = _pulsar(*args)
+    return psr.lnpost_vectorized(paramss)
+
+
+def calc_chi2(*args) -> float:
+    psr, params = _pulsar(*args)
+    return psr.chi2(params)
+
+
+calc_chi2_serial = calc_chi2
+
+
+def degrees_of_freedom(model: TimingModel, toas: TOAs) -> int:
+    """wls_chi2.jl:85-88"""
+    return (2 if toas.wideband else 1) * len(toas) - model.param_handler._nfree
+
+
+def calc_chi2_reduced(model, toas, params) -> float:
+    return calc_chi2(model, toas, params) / degrees_of_freedom(model, toas)
+
+
+def form_residuals(*args):
+    """residuals.jl:19-26 (narrowband: time residuals) / wideband_residuals.jl:24-27 ((time, DM) pairs)."""
+    psr, params = _pulsar(*args)
+    y, _ = psr.resids_and_Ninvdiag(params)
+    n = len(psr.toas)
+    return (y[:n], y[n:]) if psr.toas.wideband else y
+
+
+def _calc_resids_and_Ninvdiag(*args):
+    psr, params = _pulsar(*args)
+    return psr.resids_and_Ninvdiag(params)
+
+
+def calc_noise_weights_inv(*args):
+    psr, params = _pulsar(*args)
+    return psr.noise_weights_inv(params)
+
+
+def get_lnlike_serial_func(model, toas) -> Callable:
+    psr, _ = _pulsar(model, toas, None)
+    return psr.lnlike
+
+
+get_lnlike_parallel_func = get_lnlike_serial_func
+get_lnlike_func = get_lnlike_serial_func
+
+
+def get_chi2_serial_func(model, toas) -> Callable:
+    psr, _ = _pulsar(model, toas, None)
+    return psr.chi2
+
+
+get_chi2_parallel_func = get_chi2_serial_func
+get_chi2_func = get_chi2_serial_func
+
+
+def get_lnprior_func(model) -> Callable:
+    return lambda params: calc_lnprior(model, params)
+
+
+def get_prior_transform_func(model) -> Callable:
+    return lambda cube: prior_transform(model, cube)
+
+
+def get_lnpost_func(model, toas, vectorize: bool = False) -> Callable:
+    """posterior.jl:34-46"""
+    psr, _ = _pulsar(model, toas, None)
+    return psr.lnpost_vectorized if vectorize else psr.lnpost

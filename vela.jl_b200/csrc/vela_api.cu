@@ -1,0 +1,649 @@
+// vela_api.cu — host side of libvela_b200.so: handle lifetime, per-device model replicas, batch
+// orchestration (streams, pinned staging, walker sharding across devices) and the C ABI of
+// include/vela_b200.h.  There is no CPU compute path in this library.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "vela_kernels.cuh"
+
+using namespace vela;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? VELA_ERR_OOM : VELA_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                                     \
+    } while (0)
+
+template <class T>
+int upload(T** dst, const T* src, size_t n) {
+    *dst = nullptr;
+    if (n == 0) n = 1;
+    CU(cudaMalloc((void**)dst, n * sizeof(T)));
+    CU(cudaMemset(*dst, 0, n * sizeof(T)));
+    if (src) CU(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
+
+struct Buffers {  // per-device, per-batch scratch (grown on demand)
+    long cap_B = 0;
+    double *params = nullptr, *Pext = nullptr, *tzr = nullptr, *partial = nullptr, *Y = nullptr, *W = nullptr;
+    double *Sig = nullptr, *U = nullptr, *out = nullptr, *lnprior = nullptr;
+    double *h_params = nullptr, *h_out = nullptr, *h_lnprior = nullptr;  // pinned
+    long h_cap = 0;
+};
+
+struct DeviceModel {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    double* toa = nullptr;
+    long toa_stride = 0;
+    double* tzr_block = nullptr;
+    uint32_t* index_masks = nullptr;
+    uint8_t* bit_masks = nullptr;
+    double* defaults = nullptr;
+    int* free_idx = nullptr;
+    double* M = nullptr;
+    long ldM = 0;
+    int2* units = nullptr;
+    GPDev* gp = nullptr;
+    double* gp_data = nullptr;
+    Buffers buf;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+};
+
+}  // namespace
+
+struct VelaPulsar {
+    ProgramDev prog;
+    int kernel_kind = 0;
+    long n_toas = 0, n_rows = 0, n_rows_pad = 0;
+    int p = 0, pp = 0, n_blocks = 0, n_units = 0, n_gp = 0;
+    int chain_threads = 256, chain_group = 32, n_tiles = 0;
+    bool chol_smem = true;
+    size_t chol_smem_bytes = 0;
+    std::vector<DeviceModel> devs;
+    std::mutex mtx;
+    int64_t launches = 0;
+    bool stage_timing = false;
+    long max_chunk = 0;  // walkers per device per pass
+};
+
+namespace {
+
+void free_buffers(Buffers& b) {
+    cudaFree(b.params); cudaFree(b.Pext); cudaFree(b.tzr); cudaFree(b.partial); cudaFree(b.Y); cudaFree(b.W);
+    cudaFree(b.Sig); cudaFree(b.U); cudaFree(b.out); cudaFree(b.lnprior);
+    b.params = b.Pext = b.tzr = b.partial = b.Y = b.W = b.Sig = b.U = b.out = b.lnprior = nullptr;
+    b.cap_B = 0;
+}
+
+int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
+    Buffers& b = d.buf;
+    if (B <= b.cap_B) return 0;
+    free_buffers(b);
+    long cap = std::max<long>(round_up(B, kSigSamples), 64);
+    const ProgramDev& pg = h->prog;
+    CU(cudaMalloc((void**)&b.params, (size_t)cap * std::max(pg.n_free, 1) * sizeof(double)));
+    CU(cudaMalloc((void**)&b.Pext, (size_t)cap * pg.row * sizeof(double)));
+    CU(cudaMalloc((void**)&b.tzr, (size_t)cap * 2 * sizeof(double)));
+    CU(cudaMalloc((void**)&b.partial, (size_t)h->n_tiles * cap * 2 * sizeof(double)));
+    CU(cudaMalloc((void**)&b.out, (size_t)cap * sizeof(double)));
+    CU(cudaMalloc((void**)&b.lnprior, (size_t)cap * sizeof(double)));
+    if (h->kernel_kind != VELA_KERNEL_WHITE) {
+        size_t yw = (size_t)cap * h->n_rows_pad * sizeof(double);
+        CU(cudaMalloc((void**)&b.Y, yw));
+        CU(cudaMalloc((void**)&b.W, yw));
+        CU(cudaMemsetAsync(b.Y, 0, yw, d.stream));
+        CU(cudaMemsetAsync(b.W, 0, yw, d.stream));
+        CU(cudaMalloc((void**)&b.Sig, (size_t)cap * h->pp * h->pp * sizeof(double)));
+        CU(cudaMalloc((void**)&b.U, (size_t)cap * h->pp * sizeof(double)));
+        CU(cudaMemsetAsync(b.Sig, 0, (size_t)cap * h->pp * h->pp * sizeof(double), d.stream));
+        CU(cudaMemsetAsync(b.U, 0, (size_t)cap * h->pp * sizeof(double), d.stream));
+    }
+    b.cap_B = cap;
+    return 0;
+}
+
+int ensure_host_buffers(VelaPulsar* h, DeviceModel& d, long B) {
+    Buffers& b = d.buf;
+    if (B <= b.h_cap) return 0;
+    if (b.h_params) cudaFreeHost(b.h_params);
+    if (b.h_out) cudaFreeHost(b.h_out);
+    if (b.h_lnprior) cudaFreeHost(b.h_lnprior);
+    long cap = std::max<long>(B, 64);
+    CU(cudaMallocHost((void**)&b.h_params, (size_t)cap * std::max(h->prog.n_free, 1) * sizeof(double)));
+    CU(cudaMallocHost((void**)&b.h_out, (size_t)cap * sizeof(double)));
+    CU(cudaMallocHost((void**)&b.h_lnprior, (size_t)cap * sizeof(double)));
+    b.h_cap = cap;
+    return 0;
+}
+
+// Enqueue the whole pipeline for B walkers whose parameters already sit in d_params (row-major B x n_free).
+// mode: 0 ln L, 1 chi^2 (white kernels only).  with_prior: combine with d_lnprior (may be null = 0).
+int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B, int mode, int with_prior,
+                  const double* d_lnprior, double* d_out, cudaStream_t st) {
+    const ProgramDev& pg = h->prog;
+    Buffers& b = d.buf;
+    const bool timing = h->stage_timing && (&d == &h->devs[0]);
+    if (timing) cudaEventRecord(d.ev[0], st);
+    sample_prologue_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(pg, d.defaults, d.free_idx, d_params, B,
+                                                                         d.tzr_block, d.index_masks, d.bit_masks,
+                                                                         h->n_toas, b.Pext, b.tzr);
+    if (timing) cudaEventRecord(d.ev[1], st);
+    const bool woodbury = h->kernel_kind != VELA_KERNEL_WHITE && mode == 0;
+    ChainArgs ca;
+    ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
+    ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = B; ca.group = h->chain_group;
+    ca.emit = woodbury ? 1 : 0; ca.Y = b.Y; ca.W = b.W; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
+    const int warps = h->chain_threads / 32;
+    size_t chain_smem = ((size_t)h->chain_group * pg.row + 2 * h->chain_group + (size_t)warps * h->chain_group * 2) * sizeof(double);
+    dim3 cgrid((unsigned)h->n_tiles, (unsigned)((B + h->chain_group - 1) / h->chain_group));
+    toa_chain_kernel<<<cgrid, h->chain_threads, chain_smem, st>>>(pg, ca);
+    if (timing) cudaEventRecord(d.ev[2], st);
+    h->launches += 2;
+    if (!woodbury) {
+        finish_white_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(b.partial, h->n_tiles, B, mode, d_lnprior,
+                                                                         with_prior, d_out);
+        h->launches += 1;
+        if (timing) { cudaEventRecord(d.ev[3], st); cudaEventRecord(d.ev[4], st); }
+    } else {
+        SigmaArgs sa;
+        sa.M = d.M; sa.ldM = d.ldM; sa.n_blocks = h->n_blocks; sa.n_rows_pad = h->n_rows_pad; sa.W = b.W; sa.Y = b.Y;
+        sa.ld_yw = h->n_rows_pad; sa.B = B; sa.units = d.units; sa.n_units = h->n_units; sa.Sig = b.Sig; sa.U = b.U;
+        dim3 sgrid((unsigned)((h->n_units + kSigWarps - 1) / kSigWarps), (unsigned)((B + kSigSamples - 1) / kSigSamples));
+        sigma_contract_kernel<<<sgrid, kSigThreads, sigma_smem_bytes(), st>>>(sa);
+        if (timing) cudaEventRecord(d.ev[3], st);
+        CholArgs ch;
+        ch.Sig = b.Sig; ch.U = b.U; ch.Pext = b.Pext; ch.row = pg.row; ch.p = h->p; ch.pp = h->pp; ch.n_gp = h->n_gp;
+        ch.gp = d.gp; ch.gp_data = d.gp_data; ch.partial = b.partial; ch.n_tiles = h->n_tiles; ch.B = B;
+        ch.lnprior = d_lnprior; ch.with_prior = with_prior; ch.out = d_out; ch.use_smem = h->chol_smem ? 1 : 0;
+        chol_finish_kernel<<<(unsigned)B, kCholThreads, h->chol_smem_bytes, st>>>(ch);
+        if (timing) cudaEventRecord(d.ev[4], st);
+        h->launches += 2;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const std::vector<double>& toa_soa,
+                 const std::vector<double>& tzr_block, const std::vector<int2>& units, const std::vector<GPDev>& gps,
+                 const std::vector<double>& gp_data) {
+    CU(cudaSetDevice(d.dev));
+    CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    for (auto& e : d.ev) CU(cudaEventCreate(&e));
+    if (upload(&d.toa, toa_soa.data(), toa_soa.size())) return VELA_ERR_CUDA;
+    if (upload(&d.tzr_block, tzr_block.data(), tzr_block.size())) return VELA_ERR_CUDA;
+    if (upload(&d.index_masks, desc->index_masks, (size_t)desc->n_index_masks * desc->n_toas)) return VELA_ERR_CUDA;
+    if (upload(&d.bit_masks, desc->bit_masks, (size_t)desc->n_bit_mask_rows * desc->n_toas)) return VELA_ERR_CUDA;
+    if (upload(&d.defaults, desc->default_values, (size_t)desc->n_params)) return VELA_ERR_CUDA;
+    if (upload(&d.free_idx, desc->free_indices, (size_t)desc->n_free)) return VELA_ERR_CUDA;
+    if (h->kernel_kind != VELA_KERNEL_WHITE) {
+        // M: column-major with the leading dimension padded (zero rows) to n_rows_pad, columns padded to pp
+        d.ldM = h->n_rows_pad;
+        std::vector<double> Mp((size_t)d.ldM * h->pp, 0.0);
+        for (long c = 0; c < h->p; ++c)
+            memcpy(&Mp[(size_t)c * d.ldM], desc->noise_basis + (size_t)c * desc->basis_ld, sizeof(double) * h->n_rows);
+        if (upload(&d.M, Mp.data(), Mp.size())) return VELA_ERR_CUDA;
+        if (upload(&d.units, units.data(), units.size())) return VELA_ERR_CUDA;
+        if (upload(&d.gp, gps.data(), gps.size())) return VELA_ERR_CUDA;
+        if (upload(&d.gp_data, gp_data.data(), gp_data.size())) return VELA_ERR_CUDA;
+        CU(cudaFuncSetAttribute(sigma_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sigma_smem_bytes()));
+        if (h->chol_smem_bytes > 48 * 1024)
+            CU(cudaFuncSetAttribute(chol_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->chol_smem_bytes));
+    }
+    size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
+    if (chain_smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(toa_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem));
+    return 0;
+}
+
+void destroy_device(DeviceModel& d) {
+    cudaSetDevice(d.dev);
+    if (d.stream) cudaStreamSynchronize(d.stream);
+    free_buffers(d.buf);
+    if (d.buf.h_params) cudaFreeHost(d.buf.h_params);
+    if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
+    if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
+    cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
+    cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.units); cudaFree(d.gp); cudaFree(d.gp_data);
+    for (auto& e : d.ev) if (e) cudaEventDestroy(e);
+    if (d.stream) cudaStreamDestroy(d.stream);
+}
+
+// TOA record (Julia isbits layout) -> SoA columns with the TOA-only hoists
+void fill_toa_columns(const double* rec, int wideband, double* cols, long stride, long j) {
+    auto put = [&](int c, double v) { cols[(size_t)c * stride + j] = v; };
+    put(C_T_HI, rec[0]); put(C_T_LO, rec[1]);
+    put(C_ERR2, rec[2] * rec[2]);  // toa.error * toa.error, toa.jl:123
+    put(C_FREQ, rec[3]); put(C_PN_HI, rec[4]); put(C_PN_LO, rec[5]);
+    for (int i = 0; i < 3; ++i) { put(C_POS + i, rec[6 + i]); put(C_VEL + i, rec[9 + i]); put(C_SUN + i, rec[12 + i]); }
+    const double* s = rec + 12;
+    const double* R = rec + 6;
+    put(C_RSUN, std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]));
+    put(C_R2, R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
+    put(C_DM, wideband ? rec[31] : 0.0);
+    put(C_DMERR2, wideband ? rec[32] * rec[32] : 0.0);
+    for (int b = 0; b < 5; ++b) {
+        const double* r = rec + 15 + 3 * b;
+        for (int i = 0; i < 3; ++i) put(C_PLANET + 3 * b + i, r[i]);
+        put(C_RPLANET + b, std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]));
+    }
+}
+
+int validate(const VelaModelDesc* d) {
+    if (!d) return fail(VELA_ERR_INVALID_ARG, "null descriptor");
+    if (d->abi_version != VELA_B200_ABI_VERSION) return fail(VELA_ERR_INVALID_ARG, "ABI version %d, expected %d", d->abi_version, VELA_B200_ABI_VERSION);
+    if (d->n_components <= 0 || d->n_components > kMaxComponents) return fail(VELA_ERR_INVALID_ARG, "n_components %d outside 1..%d", d->n_components, kMaxComponents);
+    if (d->n_toas <= 0 || !d->toas || !d->tzr_toa) return fail(VELA_ERR_INVALID_ARG, "missing TOAs / TZR TOA");
+    if (d->toa_stride_bytes != (d->wideband ? VELA_WTOA_WORDS : VELA_TOA_WORDS) * 8) return fail(VELA_ERR_INVALID_ARG, "toa_stride_bytes %d does not match the %s record", d->toa_stride_bytes, d->wideband ? "WidebandTOA" : "TOA");
+    if (d->n_params <= 0 || d->n_free < 0 || d->n_free > d->n_params || !d->default_values) return fail(VELA_ERR_INVALID_ARG, "bad parameter counts");
+    for (int i = 0; i < d->n_free; ++i)
+        if (d->free_indices[i] < 0 || d->free_indices[i] >= d->n_params) return fail(VELA_ERR_INVALID_ARG, "free index %d out of range", d->free_indices[i]);
+    uint64_t tzr_index;
+    memcpy(&tzr_index, (const double*)d->tzr_toa + 30, 8);
+    if (tzr_index != 0) return fail(VELA_ERR_INVALID_ARG, "Invalid TZR TOA (index != 0), timing_model.jl:37");
+    for (int ic = 0; ic < d->n_components; ++ic) {
+        const VelaComponentDesc& c = d->components[ic];
+        if (c.kind < VELA_COMP_SOLAR_SYSTEM || c.kind > VELA_COMP_DM_MEASUREMENT_NOISE) return fail(VELA_ERR_UNSUPPORTED, "component kind %d is outside the implemented hot path", c.kind);
+        for (int k = 0; k < VELA_MAX_PAR; ++k)
+            if (c.par[k] >= d->n_params) return fail(VELA_ERR_INVALID_ARG, "component %d: parameter offset %d out of range", ic, c.par[k]);
+        const bool bits = c.kind == VELA_COMP_PHASE_JUMP || c.kind == VELA_COMP_DM_JUMP;
+        for (int m = 0; m < 2; ++m) {
+            if (c.mask[m] < 0) continue;
+            if (bits ? (c.mask[m] + c.len[0] > d->n_bit_mask_rows) : (c.mask[m] >= d->n_index_masks)) return fail(VELA_ERR_INVALID_ARG, "component %d: mask %d out of range", ic, c.mask[m]);
+        }
+    }
+    if (d->kernel_kind != VELA_KERNEL_WHITE && d->kernel_kind != VELA_KERNEL_WOODBURY_WHITE) return fail(VELA_ERR_UNSUPPORTED, "kernel kind %d is outside the implemented hot path", d->kernel_kind);
+    if (d->kernel_kind == VELA_KERNEL_WOODBURY_WHITE) {
+        long nr = d->wideband ? 2 * d->n_toas : d->n_toas;
+        if (d->basis_rows != nr || d->basis_cols <= 0 || d->basis_ld < nr || !d->noise_basis) return fail(VELA_ERR_INVALID_ARG, "noise_basis shape (%ld x %ld, ld %ld) does not match %ld rows", (long)d->basis_rows, (long)d->basis_cols, (long)d->basis_ld, nr);
+        if (d->basis_cols > kSigMaxBlocks * 8) return fail(VELA_ERR_UNSUPPORTED, "basis rank %ld > %d", (long)d->basis_cols, kSigMaxBlocks * 8);
+        long cols = 0;
+        for (int g = 0; g < d->n_gp; ++g) cols += d->gp[g].kind == VELA_GP_MARGINALIZED_TM ? d->gp[g].n : 2 * d->gp[g].n;
+        if (cols != d->basis_cols) return fail(VELA_ERR_INVALID_ARG, "GP components describe %ld columns, basis has %ld (kernel.jl:85)", cols, (long)d->basis_cols);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+VELA_API int vela_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+VELA_API const char* vela_b200_last_error(void) { return g_last_error.c_str(); }
+
+VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
+    if (!out) return fail(VELA_ERR_INVALID_ARG, "null output handle");
+    *out = nullptr;
+    if (int rc = validate(desc)) return rc;
+    int ndev_avail = vela_b200_device_count();
+    if (ndev_avail <= 0) return fail(VELA_ERR_NO_DEVICE, "no CUDA device available; libvela_b200 has no CPU path");
+
+    VelaPulsar* h = new VelaPulsar();
+    ProgramDev& pg = h->prog;
+    memset(&pg, 0, sizeof pg);
+    pg.n_comp = desc->n_components;
+    pg.n_params = desc->n_params;
+    pg.n_free = desc->n_free;
+    pg.wideband = desc->wideband;
+    int nder = 0;
+    for (int ic = 0; ic < desc->n_components; ++ic) {
+        const VelaComponentDesc& c = desc->components[ic];
+        CompDev& cd = pg.comp[ic];
+        cd.kind = c.kind; cd.flags = c.flags;
+        memcpy(cd.par, c.par, sizeof cd.par);
+        memcpy(cd.len, c.len, sizeof cd.len);
+        memcpy(cd.mask, c.mask, sizeof cd.mask);
+        cd.der = nder;
+        nder += derived_count(c.kind, c.len);
+    }
+    pg.n_derived = nder;
+    pg.row = pg.n_params + nder;
+    if ((pg.row & 1) == 0) pg.row += 1;  // odd pitch: conflict-free column reads across rows
+
+    h->kernel_kind = desc->kernel_kind;
+    h->n_toas = desc->n_toas;
+    h->n_rows = desc->wideband ? 2 * desc->n_toas : desc->n_toas;
+    h->n_rows_pad = round_up(h->n_rows, kSigBK);
+    h->chain_threads = desc->n_toas <= 64 ? 64 : (desc->n_toas <= 2048 ? 128 : 256);
+    h->n_tiles = (int)((desc->n_toas + h->chain_threads - 1) / h->chain_threads);
+    h->chain_group = 32;
+
+    std::vector<int2> units;
+    std::vector<GPDev> gps;
+    std::vector<double> gp_data;
+    if (desc->kernel_kind != VELA_KERNEL_WHITE) {
+        h->p = (int)desc->basis_cols;
+        h->n_blocks = (h->p + 7) / 8;
+        h->pp = h->n_blocks * 8;
+        h->n_gp = desc->n_gp;
+        for (int I = 0; I < h->n_blocks; ++I)
+            for (int J = 0; J <= I; ++J) units.push_back(make_int2(I, J));
+        while (units.size() % kSigWarps) units.push_back(make_int2(-2, 0));  // keep u units in their own CTAs
+        for (int t = 0; t < h->n_blocks; t += 8) units.push_back(make_int2(-1, t));
+        h->n_units = (int)units.size();
+        int col = 0;
+        for (int g = 0; g < desc->n_gp; ++g) {
+            const VelaGPDesc& s = desc->gp[g];
+            GPDev gd;
+            gd.kind = s.kind; gd.n = s.n; gd.par_log10_amp = s.par_log10_amp; gd.par_gamma = s.par_gamma; gd.par_f1 = s.par_f1;
+            gd.col0 = col; gd.data0 = (int)gp_data.size();
+            const double* src = s.kind == VELA_GP_MARGINALIZED_TM ? s.weights_inv : s.ln_js;
+            if (!src || s.n <= 0) { delete h; return fail(VELA_ERR_INVALID_ARG, "GP component %d has no data", g); }
+            if (s.kind != VELA_GP_MARGINALIZED_TM && (s.par_log10_amp < 0 || s.par_gamma < 0 || s.par_f1 < 0 ||
+                                                      s.par_log10_amp >= desc->n_params || s.par_gamma >= desc->n_params || s.par_f1 >= desc->n_params)) {
+                delete h;
+                return fail(VELA_ERR_INVALID_ARG, "GP component %d: bad parameter offsets", g);
+            }
+            gp_data.insert(gp_data.end(), src, src + s.n);
+            col += s.kind == VELA_GP_MARGINALIZED_TM ? s.n : 2 * s.n;
+            gps.push_back(gd);
+        }
+        size_t need = ((size_t)2 * h->pp + (size_t)h->p * (h->pp + 1)) * sizeof(double);
+        h->chol_smem = need <= 200 * 1024;
+        h->chol_smem_bytes = h->chol_smem ? need : (size_t)2 * h->pp * sizeof(double);
+    }
+
+    // SoA TOA table (+ TOA-only hoists) and the TZR block
+    long stride = round_up(desc->n_toas, 32);
+    std::vector<double> soa((size_t)C_NCOL * stride, 0.0);
+    for (long j = 0; j < desc->n_toas; ++j)
+        fill_toa_columns((const double*)((const char*)desc->toas + j * (long)desc->toa_stride_bytes), desc->wideband, soa.data(), stride, j);
+    std::vector<double> tzr(C_NCOL, 0.0);
+    fill_toa_columns((const double*)desc->tzr_toa, 0, tzr.data(), 1, 0);
+
+    std::vector<int> devices;
+    if (desc->n_devices > 0 && desc->devices) devices.assign(desc->devices, desc->devices + desc->n_devices);
+    else {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        devices.push_back(cur);
+    }
+    for (int dv : devices)
+        if (dv < 0 || dv >= ndev_avail) { delete h; return fail(VELA_ERR_INVALID_ARG, "device %d not available (%d devices)", dv, ndev_avail); }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    h->devs.resize(devices.size());
+    for (size_t i = 0; i < devices.size(); ++i) {
+        h->devs[i].dev = devices[i];
+        h->devs[i].toa_stride = stride;
+        int rc = build_device(h, h->devs[i], desc, soa, tzr, units, gps, gp_data);
+        if (rc) {
+            for (auto& d : h->devs) destroy_device(d);
+            delete h;
+            cudaSetDevice(prev);
+            return rc;
+        }
+    }
+    cudaSetDevice(prev);
+
+    // walkers per device per pass: bound the y/w/Sigma scratch to ~1/4 of the device memory
+    if (h->kernel_kind != VELA_KERNEL_WHITE) {
+        size_t per = (size_t)2 * h->n_rows_pad * 8 + (size_t)h->pp * h->pp * 8 + (size_t)h->pp * 8;
+        size_t free_b = 0, total_b = 0;
+        cudaSetDevice(devices[0]);
+        cudaMemGetInfo(&free_b, &total_b);
+        cudaSetDevice(prev);
+        size_t budget = std::min<size_t>(free_b / 2, (size_t)48 << 30);
+        long mc = (long)(budget / std::max<size_t>(per, 1));
+        h->max_chunk = std::max<long>(kSigSamples, mc / kSigSamples * kSigSamples);
+    } else {
+        h->max_chunk = 1 << 20;
+    }
+    *out = h;
+    return VELA_OK;
+}
+
+VELA_API int vela_b200_destroy(VelaHandle h) {
+    if (!h) return VELA_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto& d : h->devs) destroy_device(d);
+    cudaSetDevice(prev);
+    delete h;
+    return VELA_OK;
+}
+
+VELA_API int vela_b200_n_free(VelaHandle h) { return h ? h->prog.n_free : -1; }
+VELA_API int64_t vela_b200_n_rows(VelaHandle h) { return h ? h->n_rows : -1; }
+VELA_API int64_t vela_b200_n_basis(VelaHandle h) { return h ? h->p : -1; }
+VELA_API int64_t vela_b200_launch_count(VelaHandle h) { return h ? h->launches : -1; }
+
+static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free, int64_t rs, int64_t cs,
+                          const double* lnprior, int with_prior, int mode, double* out) {
+    if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
+    if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d free parameters, got %ld (parameter.jl:162)", h->prog.n_free, (long)n_free);
+    if (B < 0 || (B > 0 && (!params || !out))) return fail(VELA_ERR_INVALID_ARG, "null params/out");
+    if (mode == 1 && h->kernel_kind != VELA_KERNEL_WHITE) return fail(VELA_ERR_UNSUPPORTED, "chi2 is defined for white-noise kernels only (wls_chi2.jl:44)");
+    if (B == 0) return VELA_OK;
+    std::lock_guard<std::mutex> lock(h->mtx);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    const int nd = (int)h->devs.size();
+    const long nf = h->prog.n_free;
+    // contiguous walker blocks per device, processed in passes of at most max_chunk
+    long done = 0;
+    int rc = 0;
+    while (done < B && !rc) {
+        long pass = std::min<long>(B - done, h->max_chunk * nd);
+        long per = (pass + nd - 1) / nd;
+        std::vector<long> r0(nd), r1(nd);
+        for (int i = 0; i < nd; ++i) { r0[i] = done + std::min<long>(pass, i * per); r1[i] = done + std::min<long>(pass, (i + 1) * per); }
+        for (int i = 0; i < nd && !rc; ++i) {
+            DeviceModel& d = h->devs[i];
+            long n = r1[i] - r0[i];
+            if (n <= 0) continue;
+            cudaSetDevice(d.dev);
+            if ((rc = ensure_host_buffers(h, d, n))) break;
+            if ((rc = ensure_device_buffers(h, d, n))) break;
+            Buffers& b = d.buf;
+            if (rs == nf && cs == 1) memcpy(b.h_params, params + r0[i] * rs, sizeof(double) * n * nf);
+            else
+                for (long r = 0; r < n; ++r)
+                    for (long k = 0; k < nf; ++k) b.h_params[r * nf + k] = params[(r0[i] + r) * rs + k * cs];
+            const bool timing = h->stage_timing && i == 0;
+            if (timing) cudaEventRecord(d.ev[5], d.stream);
+            cudaMemcpyAsync(b.params, b.h_params, sizeof(double) * n * std::max<long>(nf, 1), cudaMemcpyHostToDevice, d.stream);
+            const double* d_lp = nullptr;
+            if (with_prior && lnprior) {
+                memcpy(b.h_lnprior, lnprior + r0[i], sizeof(double) * n);
+                cudaMemcpyAsync(b.lnprior, b.h_lnprior, sizeof(double) * n, cudaMemcpyHostToDevice, d.stream);
+                d_lp = b.lnprior;
+            }
+            rc = enqueue_batch(h, d, b.params, n, mode, with_prior, d_lp, b.out, d.stream);
+            cudaMemcpyAsync(b.h_out, b.out, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
+        }
+        for (int i = 0; i < nd; ++i) {
+            DeviceModel& d = h->devs[i];
+            long n = r1[i] - r0[i];
+            if (n <= 0) continue;
+            cudaSetDevice(d.dev);
+            cudaError_t e = cudaStreamSynchronize(d.stream);
+            if (e != cudaSuccess && !rc) rc = fail(VELA_ERR_CUDA, "device %d: %s", d.dev, cudaGetErrorString(e));
+            if (!rc) memcpy(out + r0[i], d.buf.h_out, sizeof(double) * n);
+            if (!rc && h->stage_timing && i == 0) {
+                for (int s = 0; s < 4; ++s) cudaEventElapsedTime(&d.stage_ms[s], d.ev[s], d.ev[s + 1]);
+                cudaEventElapsedTime(&d.stage_ms[4], d.ev[0], d.ev[4]);
+            }
+        }
+        done += pass;
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+VELA_API int vela_b200_lnlike_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free, int64_t row_stride,
+                           int64_t col_stride, double* out_lnlike) {
+    return run_host_batch(h, params, B, n_free, row_stride, col_stride, nullptr, 0, 0, out_lnlike);
+}
+
+VELA_API int vela_b200_lnpost_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free, int64_t row_stride,
+                           int64_t col_stride, const double* lnprior, double* out_lnpost) {
+    return run_host_batch(h, params, B, n_free, row_stride, col_stride, lnprior, 1, 0, out_lnpost);
+}
+
+VELA_API int vela_b200_chi2_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free, int64_t row_stride,
+                         int64_t col_stride, double* out_chi2) {
+    return run_host_batch(h, params, B, n_free, row_stride, col_stride, nullptr, 0, 1, out_chi2);
+}
+
+VELA_API int vela_b200_lnlike_batch_device(VelaHandle h, const double* d_params, int64_t B, double* d_out, void* stream) {
+    if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
+    if (B <= 0) return VELA_OK;
+    std::lock_guard<std::mutex> lock(h->mtx);
+    DeviceModel& d = h->devs[0];
+    if (B > h->max_chunk) return fail(VELA_ERR_INVALID_ARG, "device-resident batch of %ld exceeds the per-pass limit %ld", (long)B, h->max_chunk);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d.dev);
+    int rc = ensure_device_buffers(h, d, B);
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+    if (!rc && st != d.stream) cudaStreamSynchronize(d.stream);  // scratch zero-fills were queued on the handle's stream
+    if (!rc) rc = enqueue_batch(h, d, d_params, B, 0, 0, nullptr, d_out, st);
+    cudaSetDevice(prev);
+    return rc;
+}
+
+// _calc_resids_and_Ninvdiag for ONE parameter vector (runs the emit path with B = 1 on device 0)
+VELA_API int vela_b200_residuals(VelaHandle h, const double* params, int64_t n_free, double* y, double* w) {
+    if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
+    if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d free parameters, got %ld", h->prog.n_free, (long)n_free);
+    std::lock_guard<std::mutex> lock(h->mtx);
+    DeviceModel& d = h->devs[0];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d.dev);
+    int rc = ensure_device_buffers(h, d, 1);
+    if (rc) { cudaSetDevice(prev); return rc; }
+    Buffers& b = d.buf;
+    double *dY = b.Y, *dW = b.W;
+    bool tmp = false;
+    if (!dY) {  // white kernel: no resident y/w scratch
+        tmp = true;
+        cudaMalloc((void**)&dY, sizeof(double) * h->n_rows_pad);
+        cudaMalloc((void**)&dW, sizeof(double) * h->n_rows_pad);
+    }
+    cudaMemcpyAsync(b.params, params, sizeof(double) * std::max<long>(n_free, 1), cudaMemcpyHostToDevice, d.stream);
+    sample_prologue_kernel<<<1, 128, 0, d.stream>>>(h->prog, d.defaults, d.free_idx, b.params, 1, d.tzr_block,
+                                                    d.index_masks, d.bit_masks, h->n_toas, b.Pext, b.tzr);
+    ChainArgs ca;
+    ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
+    ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = 1;
+    ca.Y = dY; ca.W = dW; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
+    size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
+    toa_chain_kernel<<<dim3((unsigned)h->n_tiles, 1), h->chain_threads, chain_smem, d.stream>>>(h->prog, ca);
+    h->launches += 2;
+    if (y) cudaMemcpyAsync(y, dY, sizeof(double) * h->n_rows, cudaMemcpyDeviceToHost, d.stream);
+    if (w) cudaMemcpyAsync(w, dW, sizeof(double) * h->n_rows, cudaMemcpyDeviceToHost, d.stream);
+    cudaError_t e = cudaStreamSynchronize(d.stream);
+    if (tmp) { cudaFree(dY); cudaFree(dW); }
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "residuals: %s", cudaGetErrorString(e));
+    return VELA_OK;
+}
+
+VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int64_t n_free, double* phiinv) {
+    if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
+    if (h->kernel_kind == VELA_KERNEL_WHITE) return fail(VELA_ERR_UNSUPPORTED, "white-noise kernel has no Phi");
+    if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d free parameters, got %ld", h->prog.n_free, (long)n_free);
+    std::lock_guard<std::mutex> lock(h->mtx);
+    DeviceModel& d = h->devs[0];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d.dev);
+    int rc = ensure_device_buffers(h, d, 1);
+    if (rc) { cudaSetDevice(prev); return rc; }
+    Buffers& b = d.buf;
+    cudaMemcpyAsync(b.params, params, sizeof(double) * std::max<long>(n_free, 1), cudaMemcpyHostToDevice, d.stream);
+    sample_prologue_kernel<<<1, 128, 0, d.stream>>>(h->prog, d.defaults, d.free_idx, b.params, 1, d.tzr_block,
+                                                    d.index_masks, d.bit_masks, h->n_toas, b.Pext, b.tzr);
+    CholArgs ch;
+    memset(&ch, 0, sizeof ch);
+    ch.Pext = b.Pext; ch.row = h->prog.row; ch.p = h->p; ch.pp = h->pp; ch.n_gp = h->n_gp; ch.gp = d.gp; ch.gp_data = d.gp_data;
+    double* dphi = nullptr;
+    cudaMalloc((void**)&dphi, sizeof(double) * h->pp);
+    phiinv_kernel<<<1, 128, 0, d.stream>>>(ch, dphi);
+    h->launches += 2;
+    cudaMemcpyAsync(phiinv, dphi, sizeof(double) * h->p, cudaMemcpyDeviceToHost, d.stream);
+    cudaError_t e = cudaStreamSynchronize(d.stream);
+    cudaFree(dphi);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "noise_weights_inv: %s", cudaGetErrorString(e));
+    return VELA_OK;
+}
+
+VELA_API int vela_b200_set_stage_timing(VelaHandle h, int enabled) {
+    if (!h) return VELA_ERR_INVALID_ARG;
+    h->stage_timing = enabled != 0;
+    return VELA_OK;
+}
+
+VELA_API double vela_b200_last_stage_ms(VelaHandle h, int stage) {
+    if (!h || !h->stage_timing || stage < 0 || stage > 4) return -1.0;
+    return h->devs[0].stage_ms[stage];
+}
+
+VELA_API double vela_b200_fp64_peak_tflops(int device, int kind) {
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess) return -1.0;
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double* dout = nullptr;
+    cudaMalloc((void**)&dout, sizeof(double) * blocks * threads);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        if (kind == 0) dfma_peak_kernel<<<blocks, threads>>>(dout, iters);
+        else dmma_peak_kernel<<<blocks, threads>>>(dout, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flops = kind == 0 ? (double)blocks * threads * iters * 16 * 2
+                                 : (double)blocks * (threads / 32) * iters * 16 * (8.0 * 8 * 4 * 2);
+        if (ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(dout);
+    cudaSetDevice(prev);
+    return best;
+}
+
+}  // extern "C"

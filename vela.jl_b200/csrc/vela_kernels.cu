@@ -1,0 +1,542 @@
+// vela_kernels.cu — the CUDA kernels of the batched posterior hot path (sm_100a).
+//
+//   K0 sample_prologue   read_params scatter + per-sample hoists + TZR phase        (1 thread / walker)
+//   K1 toa_chain         per (walker, TOA): component chain -> r, sigma^2; block-reduced
+//                        chi^2 / log-det partials; optional emit of y, w           (1 thread / TOA,
+//                        loops over a group of walkers whose parameter rows sit in shared memory)
+//   K1b finish_white     sums the per-tile partials, assembles ln L / chi^2 (+ ln prior)
+//   K3 sigma_contract    Sigma^-1 blocks = M^T diag(w) M (lower block triangle) and u = M^T (w.y)
+//                        as an FP64 tensor-core (DMMA m8n8k4) contraction over the TOA axis
+//   K4 chol_finish       + diag(Phi^-1); batched in-place Cholesky, log-det, forward solve,
+//                        Woodbury ln L assembly (+ ln prior)
+//
+// Host-side orchestration and the C ABI are in vela_api.cu.
+#include "vela_kernels.cuh"
+
+#include <cstdio>
+
+namespace vela {
+
+// ------------------------------------------------------------------------------------------
+// K0  sample prologue
+// ------------------------------------------------------------------------------------------
+// read_params (parameter.jl:158-169) + hoists + calc_tzr_phase (residuals.jl:29-32)
+__global__ void __launch_bounds__(128) sample_prologue_kernel(const __grid_constant__ ProgramDev prog,
+                                                             const double* __restrict__ defaults,
+                                                             const int* __restrict__ free_idx,
+                                                             const double* __restrict__ params, long B,
+                                                             const double* __restrict__ tzr_block,
+                                                             const uint32_t* __restrict__ index_masks,
+                                                             const uint8_t* __restrict__ bit_masks, long n_toas,
+                                                             double* __restrict__ Pext, double* __restrict__ tzr_phase) {
+    long b = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double* P = Pext + b * prog.row;
+    for (int i = 0; i < prog.n_params; ++i) P[i] = defaults[i];
+    for (int i = 0; i < prog.n_free; ++i) P[free_idx[i]] = params[b * prog.n_free + i];
+    double* D = P + prog.n_params;
+    for (int ic = 0; ic < prog.n_comp; ++ic) fill_derived(prog.comp[ic], P, D + prog.comp[ic].der);
+
+    ChainEnv e;
+    e.toa_base = tzr_block; e.stride = 1; e.j = 0;
+    e.index_masks = index_masks; e.bit_masks = bit_masks; e.n_toas = n_toas;
+    e.tzr = true; e.wide = false;
+    // the TZR block is laid out column-after-column with stride 1 (C_NCOL doubles)
+    ToaRegs t = load_toa(tzr_block, 1, 0, false);
+    Corr k = run_chain(prog, P, t, e);
+    tzr_phase[2 * b] = k.bad ? CUDART_NAN : k.phase.hi;
+    tzr_phase[2 * b + 1] = k.phase.lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1  per-(walker, TOA) chain
+// ------------------------------------------------------------------------------------------
+// _wls_lnlike_term (wls_likelihood.jl:7-14, wideband_wls_likelihood.jl:1-21) and
+// _calc_resids_and_Ninvdiag (gls_likelihood.jl:9-79).
+//
+// grid = (TOA tiles, walker groups); one thread owns one TOA (its record lives in registers for the
+// whole kernel) and loops over the walkers of the group, whose extended parameter rows are staged in
+// shared memory once per block (uniform-address LDS = broadcast).  For each walker the block reduces
+// chi^2 and log-det terms over its TOAs with warp shuffles; per-tile partials go to `partial`
+// [tile][walker][2] and are summed in a fixed order later (deterministic, no atomics).
+__global__ void __launch_bounds__(kChainThreads) toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a) {
+    extern __shared__ double smem[];
+    const int row = prog.row;
+    double* sP = smem;                                  // [group][row]
+    double* sTzr = sP + (size_t)a.group * row;          // [group][2]
+    double* sRed = sTzr + 2 * a.group;                  // [warps][group][2]
+
+    const long b0 = (long)blockIdx.y * a.group;
+    const int nb = (int)min((long)a.group, a.B - b0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < nb * row; i += blockDim.x) sP[i] = a.Pext[b0 * row + i];
+    for (int i = tid; i < 2 * nb; i += blockDim.x) sTzr[i] = a.tzr_phase[2 * b0 + i];
+
+    const long j = (long)blockIdx.x * blockDim.x + tid;
+    const bool active = j < a.n_toas;
+    const long jj = active ? j : a.n_toas - 1;
+    ToaRegs t = load_toa(a.toa, a.toa_stride, jj, false);
+    ChainEnv e;
+    e.toa_base = a.toa; e.stride = a.toa_stride; e.j = jj;
+    e.index_masks = a.index_masks; e.bit_masks = a.bit_masks; e.n_toas = a.n_toas;
+    e.tzr = false; e.wide = prog.wideband != 0;
+    __syncthreads();
+
+    for (int s = 0; s < nb; ++s) {
+        const double* P = sP + (size_t)s * row;
+        Corr k = run_chain(prog, P, t, e);
+        // form_residual residuals.jl:8-12: Float64((phase - pulse_number) - tzrphase) / (f (1 + doppler))
+        dd dphase = dd_sub(dd_sub(k.phase, dd{t.pn_hi, t.pn_lo}), dd{sTzr[2 * s], sTzr[2 * s + 1]});
+        double f = k.spin_frequency * (1 + k.doppler);
+        double tres = dphase.hi / f;
+        double err2 = (t.err2 + k.equad2) * k.efac * k.efac;  // scaled_toa_error_sqr toa.jl:122-123
+        double chi, lg, w = 0.0;
+        if (a.emit) {  // Woodbury: y^T N^-1 y and log det N from Ninvdiag, gls_likelihood.jl:81-99
+            w = 1.0 / err2;
+            chi = tres * tres * w;
+            lg = -log(w);
+        } else {
+            chi = tres * tres / err2;
+            lg = log(err2);
+        }
+        double dmres = 0.0, wdm = 0.0;
+        if (e.wide) {  // wideband_residuals.jl:6-17, wideband_toa.jl:68-69
+            dmres = t.dm - k.model_dm;
+            double dmerr2 = (t.dmerr2 + k.dmequad2) * k.dmefac * k.dmefac;
+            if (a.emit) {
+                wdm = 1.0 / dmerr2;
+                chi += dmres * dmres * wdm;
+                lg += -log(wdm);
+            } else {
+                chi += dmres * dmres / dmerr2;
+                lg += log(dmerr2);
+            }
+        }
+        if (k.bad || k.spin_frequency == 0.0) chi = CUDART_NAN;
+        if (!active) { chi = 0.0; lg = 0.0; }
+        if (a.emit && active) {
+            const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
+            a.Y[o] = tres;
+            a.W[o] = w;
+            if (e.wide) {
+                a.Y[o + a.n_toas] = dmres;
+                a.W[o + a.n_toas] = wdm;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            chi += __shfl_xor_sync(0xffffffffu, chi, off);
+            lg += __shfl_xor_sync(0xffffffffu, lg, off);
+        }
+        if (lane == 0) {
+            sRed[((size_t)warp * a.group + s) * 2] = chi;
+            sRed[((size_t)warp * a.group + s) * 2 + 1] = lg;
+        }
+    }
+    __syncthreads();
+    const int nwarps = blockDim.x >> 5;
+    for (int i = tid; i < 2 * nb; i += blockDim.x) {
+        double acc = 0.0;
+        for (int w = 0; w < nwarps; ++w) acc += sRed[(size_t)w * a.group * 2 + i];
+        a.partial[((size_t)blockIdx.x * a.B + b0) * 2 + i] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1b  white-noise finish: -sum/2 (wls_likelihood.jl:49-56) or chi^2 (wls_chi2.jl:44-51), + prior
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double combine_prior(double lnl, const double* lnprior, long b, int with_prior) {
+    if (isnan(lnl)) lnl = -CUDART_INF;
+    if (!with_prior) return lnl;
+    double lp = lnprior ? lnprior[b] : 0.0;
+    return isfinite(lp) ? lp + lnl : lp;  // posterior.jl:9-12
+}
+
+__global__ void finish_white_kernel(const double* __restrict__ partial, int n_tiles, long B, int mode,
+                                    const double* __restrict__ lnprior, int with_prior, double* __restrict__ out) {
+    long b = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double chi = 0.0, lg = 0.0;
+    for (int t = 0; t < n_tiles; ++t) {
+        chi += partial[((size_t)t * B + b) * 2];
+        lg += partial[((size_t)t * B + b) * 2 + 1];
+    }
+    if (mode == 1) { out[b] = chi; return; }
+    out[b] = combine_prior(-(chi + lg) / 2, lnprior, b, with_prior);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3  Sigma^-1 contraction on the FP64 tensor cores
+// ------------------------------------------------------------------------------------------
+// _calc_Ninv_M + _calc_Sigmainv__and__MT_Ninv_y (gls_likelihood.jl:101-199), restructured as one
+// GEMM over the TOA axis:   C[(p,q), b] = sum_j (M[j,p] M[j,q]) * w[b,j],   u[p, b] = sum_j M[j,p] (w y)[b,j].
+//
+// The p x p matrix is cut into 8 x 8 blocks; a work "unit" is either a block pair (I, J<=I) — eight
+// m8n8k4 A-tiles, tile i = row p = 8I+i against the eight q = 8J..8J+7, formed ON THE FLY as
+// M[j,p] * M[j,q] from the shared-memory M tile — or a "u" unit (eight p-blocks of M^T against w.y).
+// A warp owns one unit x 32 walkers (4 n-tiles): 8 x 4 accumulator tiles = 64 FP64 registers, so each
+// k4 step issues 32 independent DMMAs for 13 LDS.64 + 8 DMUL.  A CTA is 8 warps = 8 consecutive
+// units over the same 32 walkers; only the column blocks those units touch are staged (cp.async,
+// kSigStages-deep ring), K-contiguous with a 20-double row pitch (conflict-free fragment reads).
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int sSlotBlock[kSigMaxSlots];   // slot -> column block
+    __shared__ int sNSlots;
+    __shared__ short sBlockSlot[kSigMaxBlocks];  // column block -> slot (-1)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int unit0 = blockIdx.x * kSigWarps;
+    const long b0 = (long)blockIdx.y * kSigSamples;
+
+    // ---- which column blocks does this CTA need?
+    if (tid == 0) {
+        for (int i = 0; i < a.n_blocks; ++i) sBlockSlot[i] = -1;
+        int ns = 0;
+        auto want = [&](int blk) {
+            if (sBlockSlot[blk] < 0 && ns < kSigMaxSlots) { sBlockSlot[blk] = (short)ns; sSlotBlock[ns++] = blk; }
+        };
+        for (int w = 0; w < kSigWarps; ++w) {
+            int u = unit0 + w;
+            if (u >= a.n_units) break;
+            int2 un = a.units[u];
+            if (un.x >= 0) { want(un.x); want(un.y); }
+            else if (un.x == -1) {
+                int count = min(8, a.n_blocks - un.y);
+                for (int t = 0; t < count; ++t) want(un.y + t);
+            }
+        }
+        sNSlots = ns;
+    }
+    __syncthreads();
+    const int nslots = sNSlots;
+
+    // stage layout: [nslots*8 columns of M][kSigSamples rows of W][kSigSamples rows of Y], pitch kSigPitch
+    const int stage_rows = kSigMaxSlots * 8 + 2 * kSigSamples;
+    const size_t stage_doubles = (size_t)stage_rows * kSigPitch;
+    auto stage_ptr = [&](int s) { return smem + (size_t)s * stage_doubles; };
+
+    // each row is kSigBK doubles = kSigBK/2 16-byte chunks
+    constexpr int kChunks = kSigBK / 2;
+    const int m_rows = nslots * 8;
+    const int total_chunks = (m_rows + 2 * kSigSamples) * kChunks;
+    auto issue = [&](int kt, int s) {
+        double* base = stage_ptr(s);
+        const long j0 = (long)kt * kSigBK;
+        for (int c = tid; c < total_chunks; c += kSigThreads) {
+            int r = c / kChunks, ch = c - r * kChunks;
+            const double* src;
+            double* dst;
+            if (r < m_rows) {
+                int col = sSlotBlock[r >> 3] * 8 + (r & 7);
+                src = a.M + (size_t)col * a.ldM + j0 + ch * 2;
+                dst = base + (size_t)r * kSigPitch + ch * 2;
+            } else if (r < m_rows + kSigSamples) {
+                int n = r - m_rows;
+                src = a.W + (size_t)(b0 + n) * a.ld_yw + j0 + ch * 2;
+                dst = base + (size_t)(kSigMaxSlots * 8 + n) * kSigPitch + ch * 2;
+            } else {
+                int n = r - m_rows - kSigSamples;
+                src = a.Y + (size_t)(b0 + n) * a.ld_yw + j0 + ch * 2;
+                dst = base + (size_t)(kSigMaxSlots * 8 + kSigSamples + n) * kSigPitch + ch * 2;
+            }
+            cp_async16(dst, src);
+        }
+    };
+
+    const int n_ktiles = (int)(a.n_rows_pad / kSigBK);
+    // ---- this warp's unit
+    const int u = unit0 + warp;
+    int2 un = (u < a.n_units) ? a.units[u] : make_int2(-2, 0);
+    const bool have_unit = un.x >= -1;
+    const bool is_pair = un.x >= 0;
+    int slotI = 0, slotJ = 0, u_first = 0, u_count = 0;
+    if (have_unit) {
+        if (is_pair) { slotI = sBlockSlot[un.x]; slotJ = sBlockSlot[un.y]; }
+        else { u_first = un.y; u_count = min(8, a.n_blocks - u_first); }
+    }
+    int uslot[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) uslot[i] = (!is_pair && i < u_count) ? sBlockSlot[u_first + i] : 0;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
+
+    // ---- prologue of the ring
+#pragma unroll
+    for (int s = 0; s < kSigStages - 1; ++s) {
+        if (s < n_ktiles) issue(s, s);
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < n_ktiles; ++kt) {
+        cp_async_wait<kSigStages - 2>();
+        __syncthreads();
+        {   // refill the slot freed by the previous iteration
+            int nk = kt + kSigStages - 1;
+            if (nk < n_ktiles) issue(nk, nk % kSigStages);
+            cp_async_commit();
+        }
+        if (have_unit) {
+            const double* sM = stage_ptr(kt % kSigStages);
+            const double* sW = sM + (size_t)kSigMaxSlots * 8 * kSigPitch;
+            const double* sY = sW + (size_t)kSigSamples * kSigPitch;
+#pragma unroll
+            for (int kk = 0; kk < kSigBK / 4; ++kk) {
+                const int k = kk * 4 + tig;
+                double bw[4];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) bw[n] = sW[(size_t)(n * 8 + gid) * kSigPitch + k];
+                if (is_pair) {
+                    const double qf = sM[(size_t)(slotJ * 8 + gid) * kSigPitch + k];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const double af = sM[(size_t)(slotI * 8 + i) * kSigPitch + k] * qf;
+#pragma unroll
+                        for (int n = 0; n < 4; ++n) dmma8x8x4(acc[i][n][0], acc[i][n][1], af, bw[n]);
+                    }
+                } else {
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) bw[n] *= sY[(size_t)(n * 8 + gid) * kSigPitch + k];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < u_count) {
+                            const double af = sM[(size_t)(uslot[i] * 8 + gid) * kSigPitch + k];
+#pragma unroll
+                            for (int n = 0; n < 4; ++n) dmma8x8x4(acc[i][n][0], acc[i][n][1], af, bw[n]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue: accumulator (row = gid, col = 2*tig + {0,1}) of tile (i, n)
+    if (!have_unit) return;
+    const int pp = a.n_blocks * 8;
+    if (is_pair) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int prow = un.x * 8 + i, q = un.y * 8 + gid;
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    long b = b0 + n * 8 + 2 * tig + r;
+                    if (b < a.B) a.Sig[(size_t)b * pp * pp + (size_t)prow * pp + q] = acc[i][n][r];
+                }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < u_count) {
+                const int prow = (u_first + i) * 8 + gid;
+#pragma unroll
+                for (int n = 0; n < 4; ++n)
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        long b = b0 + n * 8 + 2 * tig + r;
+                        if (b < a.B) a.U[(size_t)b * pp + prow] = acc[i][n][r];
+                    }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4  + Phi^-1, Cholesky, log-det, solve, ln L
+// ------------------------------------------------------------------------------------------
+// calc_noise_weights_inv (gls_likelihood.jl:3-7, gp_noise.jl:12-16,64-78, marginalized_timing_model.jl:24)
+// and _gls_lnlike_serial (gls_likelihood.jl:201-226).  One CTA per walker.  The lower triangle of
+// Sigma^-1 (row p, col q<=p) is factorised in place as L L^T (right-looking, one column per step),
+// in shared memory when it fits, else directly in the L2-resident global buffer.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += scratch[w];
+    return s;
+}
+
+__global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double scratch[kCholThreads / 32];
+    __shared__ int sFail;
+    const long b = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int p = a.p, pp = a.pp;
+
+    double* phi = smem;            // [pp]
+    double* z = phi + pp;          // [pp]
+    double* A;                     // lower triangle, row pitch lda
+    int lda;
+    double* gA = a.Sig + (size_t)b * pp * pp;
+    if (a.use_smem) {
+        lda = pp + 1;
+        A = z + pp;
+        for (int i = tid; i < p * pp; i += nt) {
+            int r = i / pp, c = i - r * pp;
+            if (c <= r) A[r * lda + c] = gA[(size_t)r * pp + c];
+        }
+    } else {
+        lda = pp;
+        A = gA;
+    }
+    if (tid == 0) sFail = 0;
+
+    // ---- Phi^-1 for this walker
+    const double* P = a.Pext + (size_t)b * a.row;
+    for (int g = 0; g < a.n_gp; ++g) {
+        GPDev gp = a.gp[g];
+        if (gp.kind == VELA_GP_MARGINALIZED_TM) {
+            for (int i = tid; i < gp.n; i += nt) phi[gp.col0 + i] = a.gp_data[gp.data0 + i];
+        } else {
+            // powerlaw(A, gamma, f1, f1) gp_noise.jl:12-16 with A = exp10(log10_A)
+            const double fyr = 1.0 / 3600 / 24 / 365.25;
+            const double denom = 12 * (CUDART_PI * CUDART_PI) * fyr * fyr * fyr;
+            double amp = exp10(P[gp.par_log10_amp]), gamma = P[gp.par_gamma], f1 = P[gp.par_f1];
+            double P1 = amp * amp / denom * pow(fyr / f1, gamma) * f1;
+            for (int i = tid; i < gp.n; i += nt) {
+                double v = 1 / (P1 * exp(-gamma * a.gp_data[gp.data0 + i]));
+                phi[gp.col0 + i] = v;
+                phi[gp.col0 + gp.n + i] = v;
+            }
+        }
+    }
+    for (int i = tid; i < p; i += nt) z[i] = a.U[(size_t)b * pp + i];
+    __syncthreads();
+    double lphi = 0.0;
+    for (int i = tid; i < p; i += nt) {
+        lphi += log(phi[i]);
+        A[i * lda + i] += phi[i];
+    }
+    const double logdetPhi = -block_sum(lphi, scratch);
+    __syncthreads();
+
+    // ---- Cholesky A = L L^T (isposdef + cholesky!, gls_likelihood.jl:211-217)
+    for (int k = 0; k < p; ++k) {
+        if (tid == 0) {
+            double d = A[k * lda + k];
+            if (!(d > 0.0) || !isfinite(d)) { sFail = 1; d = 1.0; }
+            A[k * lda + k] = sqrt(d);
+        }
+        __syncthreads();
+        const double dk = A[k * lda + k];
+        for (int i = k + 1 + tid; i < p; i += nt) A[i * lda + k] /= dk;
+        __syncthreads();
+        // trailing update, lower triangle: A[i][j] -= A[i][k] A[j][k], k < j <= i (16 x 16 thread grid)
+        {
+            const int tx = tid & 15, ty = tid >> 4, sy = nt >> 4;
+            for (int i = k + 1 + ty; i < p; i += sy) {
+                const double aik = A[i * lda + k];
+                for (int j = k + 1 + tx; j <= i; j += 16) A[i * lda + j] -= aik * A[j * lda + k];
+            }
+        }
+        __syncthreads();
+    }
+    double ld = 0.0;
+    for (int i = tid; i < p; i += nt) ld += log(A[i * lda + i]);
+    const double logdetSig = 2 * block_sum(ld, scratch);
+    // ---- forward solve L z = u (ldiv!, gls_likelihood.jl:220)
+    for (int k = 0; k < p; ++k) {
+        __syncthreads();
+        if (tid == 0) z[k] /= A[k * lda + k];
+        __syncthreads();
+        const double zk = z[k];
+        for (int i = k + 1 + tid; i < p; i += nt) z[i] -= A[i * lda + k] * zk;
+    }
+    __syncthreads();
+    double zz = 0.0;
+    for (int i = tid; i < p; i += nt) zz += z[i] * z[i];
+    zz = block_sum(zz, scratch);
+
+    if (tid == 0) {
+        double yNy = 0.0, logdetN = 0.0;
+        for (int t = 0; t < a.n_tiles; ++t) {
+            yNy += a.partial[((size_t)t * a.B + b) * 2];
+            logdetN += a.partial[((size_t)t * a.B + b) * 2 + 1];
+        }
+        double lnl = -0.5 * (yNy - zz + logdetN + logdetPhi + logdetSig);
+        if (sFail) lnl = -CUDART_INF;
+        a.out[b] = combine_prior(lnl, a.lnprior, b, a.with_prior);
+    }
+}
+
+// Phi^-1 only (vela_b200_noise_weights_inv): one block, walker 0
+__global__ void phiinv_kernel(CholArgs a, double* __restrict__ out) {
+    const double* P = a.Pext;
+    for (int g = 0; g < a.n_gp; ++g) {
+        GPDev gp = a.gp[g];
+        if (gp.kind == VELA_GP_MARGINALIZED_TM) {
+            for (int i = threadIdx.x; i < gp.n; i += blockDim.x) out[gp.col0 + i] = a.gp_data[gp.data0 + i];
+        } else {
+            const double fyr = 1.0 / 3600 / 24 / 365.25;
+            const double denom = 12 * (CUDART_PI * CUDART_PI) * fyr * fyr * fyr;
+            double amp = exp10(P[gp.par_log10_amp]), gamma = P[gp.par_gamma], f1 = P[gp.par_f1];
+            double P1 = amp * amp / denom * pow(fyr / f1, gamma) * f1;
+            for (int i = threadIdx.x; i < gp.n; i += blockDim.x) {
+                double v = 1 / (P1 * exp(-gamma * a.gp_data[gp.data0 + i]));
+                out[gp.col0 + i] = v;
+                out[gp.col0 + gp.n + i] = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 peak micro-benchmarks (roofline denominators)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double a = 1.0000001, c = 1e-7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = fma(x[i], a, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double acc[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+    double af = 1.0 + 1e-9 * threadIdx.x, bf = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma8x8x4(acc[i][0], acc[i][1], af, bf);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace vela

@@ -1,0 +1,94 @@
+// vela_kernels.cuh — launch-argument structs and tile constants shared by vela_kernels.cu and vela_api.cu
+#pragma once
+#include "vela_device.cuh"
+
+namespace vela {
+
+constexpr int kChainThreads = 256;  // max threads per block of the chain kernel (one TOA each)
+
+// K3 tiling
+constexpr int kSigThreads = 256;
+constexpr int kSigWarps = 8;        // units per CTA
+constexpr int kSigSamples = 32;     // walkers per CTA (4 n-tiles of 8)
+constexpr int kSigBK = 16;          // TOA rows per pipeline stage
+constexpr int kSigPitch = 20;       // shared-memory row pitch in doubles (conflict-free fragment reads)
+constexpr int kSigStages = 4;
+constexpr int kSigMaxSlots = 16;    // distinct 8-column blocks a CTA can stage
+constexpr int kSigMaxBlocks = 128;  // p <= 1024
+
+constexpr int kCholThreads = 256;
+
+struct ChainArgs {
+    const double* Pext;        // [B][row]
+    const double* tzr_phase;   // [B][2]
+    const double* toa;         // SoA table
+    long toa_stride;
+    long n_toas;
+    const uint32_t* index_masks;
+    const uint8_t* bit_masks;
+    long B;
+    int group;                 // walkers per block
+    int emit;                  // 1: write y, w (Woodbury path)
+    double* Y;                 // [B_pad][ld_yw]
+    double* W;
+    long ld_yw;
+    double* partial;           // [tiles][B][2]
+};
+
+struct SigmaArgs {
+    const double* M;           // column-major, leading dimension ldM (rows zero-padded to n_rows_pad)
+    long ldM;
+    int n_blocks;              // ceil(p / 8)
+    long n_rows_pad;
+    const double* W;
+    const double* Y;
+    long ld_yw;
+    long B;
+    const int2* units;         // (I, J) block pair, (-1, first block) u unit, (-2, *) padding
+    int n_units;
+    double* Sig;               // [B][pp][pp], row p / col q, lower block triangle written
+    double* U;                 // [B][pp]
+};
+
+struct GPDev {
+    int kind, n, par_log10_amp, par_gamma, par_f1;
+    int col0;                  // first basis column of this GP component
+    int data0;                 // offset into gp_data (ln_js or prior_weights_inv)
+};
+
+struct CholArgs {
+    double* Sig;
+    const double* U;
+    const double* Pext;
+    int row;
+    int p, pp;
+    int n_gp;
+    const GPDev* gp;
+    const double* gp_data;
+    const double* partial;
+    int n_tiles;
+    long B;
+    const double* lnprior;
+    int with_prior;
+    double* out;
+    int use_smem;
+};
+
+__global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, const double* defaults, const int* free_idx,
+                                       const double* params, long B, const double* tzr_block,
+                                       const uint32_t* index_masks, const uint8_t* bit_masks, long n_toas,
+                                       double* Pext, double* tzr_phase);
+__global__ void toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a);
+__global__ void finish_white_kernel(const double* partial, int n_tiles, long B, int mode, const double* lnprior,
+                                    int with_prior, double* out);
+__global__ void sigma_contract_kernel(SigmaArgs a);
+__global__ void chol_finish_kernel(CholArgs a);
+__global__ void phiinv_kernel(CholArgs a, double* out);
+__global__ void dfma_peak_kernel(double* out, int iters);
+__global__ void dmma_peak_kernel(double* out, int iters);
+
+inline size_t sigma_smem_bytes() {
+    return (size_t)kSigStages * (kSigMaxSlots * 8 + 2 * kSigSamples) * kSigPitch * sizeof(double);
+}
+
+}  // namespace vela

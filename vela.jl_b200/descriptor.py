@@ -1,0 +1,297 @@
+"""Flatten a (TimingModel, TOAs) pair into the C-ABI `VelaModelDesc` of include/vela_b200.h.
+
+This is the Python twin of the Julia shim's `_describe(model, toas)` (vela.jl_b200/julia/VelaB200.jl):
+it walks the ordered component tuple, looks every named parameter up in the ParamHandler's
+flattened ordering (src/parameter/parameter.jl:87-92) and records 0-based offsets.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, List
+
+import numpy as np
+
+from . import model as M
+
+VELA_B200_ABI_VERSION = 1
+VELA_MAX_PAR = 24
+
+# VelaComponentKind
+(COMP_SOLAR_SYSTEM, COMP_SOLAR_WIND, COMP_DISPERSION_TAYLOR, COMP_DISPERSION_PIECEWISE,
+ COMP_CHROMATIC_TAYLOR, COMP_CHROMATIC_PIECEWISE, COMP_BINARY_ELL1, COMP_BINARY_DD, COMP_GLITCH,
+ COMP_EXP_DIP, COMP_SPINDOWN, COMP_PHASE_OFFSET, COMP_PHASE_JUMP_EXCLUSIVE, COMP_PHASE_JUMP,
+ COMP_MEASUREMENT_NOISE, COMP_DM_JUMP_EXCLUSIVE, COMP_DM_JUMP, COMP_DM_MEASUREMENT_NOISE) = range(1, 19)
+FLAG_ECLIPTIC, FLAG_PLANET_SHAPIRO, FLAG_USE_FBX = 1, 2, 4
+KERNEL_WHITE, KERNEL_WOODBURY_WHITE = 0, 2
+GP_POWERLAW_RED, GP_POWERLAW_DM, GP_POWERLAW_CHROM, GP_MARGINALIZED_TM = 1, 2, 3, 4
+
+
+class VelaComponentDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("flags", C.c_int32), ("par", C.c_int32 * VELA_MAX_PAR),
+                ("len", C.c_int32 * 4), ("mask", C.c_int32 * 2)]
+
+
+class VelaGPDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("par_log10_amp", C.c_int32),
+                ("par_gamma", C.c_int32), ("par_f1", C.c_int32), ("_pad", C.c_int32),
+                ("ln_js", C.POINTER(C.c_double)), ("weights_inv", C.POINTER(C.c_double))]
+
+
+class VelaModelDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("n_components", C.c_int32),
+        ("components", C.POINTER(VelaComponentDesc)),
+        ("n_params", C.c_int32), ("n_free", C.c_int32),
+        ("default_values", C.POINTER(C.c_double)), ("free_indices", C.POINTER(C.c_int32)),
+        ("n_toas", C.c_int64), ("wideband", C.c_int32), ("toa_stride_bytes", C.c_int32),
+        ("toas", C.c_void_p), ("tzr_toa", C.c_void_p),
+        ("n_index_masks", C.c_int32), ("n_bit_mask_rows", C.c_int32),
+        ("index_masks", C.POINTER(C.c_uint32)), ("bit_masks", C.POINTER(C.c_uint8)),
+        ("kernel_kind", C.c_int32), ("n_gp", C.c_int32), ("gp", C.POINTER(VelaGPDesc)),
+        ("basis_rows", C.c_int64), ("basis_cols", C.c_int64), ("basis_ld", C.c_int64),
+        ("noise_basis", C.POINTER(C.c_double)),
+        ("n_devices", C.c_int32), ("_pad", C.c_int32), ("devices", C.POINTER(C.c_int32)),
+    ]
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class ModelDescriptor:
+    """Owns the numpy buffers a `VelaModelDesc` points into."""
+
+    def __init__(self, model: M.TimingModel, toas: M.TOAs, devices=None):
+        self.model = model
+        self.toas = toas
+        self._keep: List[Any] = []
+        ph = model.param_handler
+        ntoa = len(toas)
+        if ntoa == 0:
+            raise ValueError("empty TOA set")
+
+        index_masks: List[np.ndarray] = []
+        bit_rows: List[np.ndarray] = []
+
+        def add_index_mask(mask) -> int:
+            mask = np.asarray(mask).astype(np.uint32)
+            if mask.shape != (ntoa,):
+                raise ValueError(f"index mask has shape {mask.shape}, expected ({ntoa},)")
+            index_masks.append(mask)
+            return len(index_masks) - 1
+
+        def add_bit_mask(mask) -> int:
+            mask = np.asarray(mask).astype(np.uint8)
+            if mask.ndim != 2 or mask.shape[1] != ntoa:
+                raise ValueError(f"bit mask has shape {mask.shape}, expected (njump, {ntoa})")
+            first = len(bit_rows)
+            bit_rows.extend(list(mask))
+            return first
+
+        comps: List[VelaComponentDesc] = []
+
+        def new(kind, flags=0):
+            c = VelaComponentDesc()
+            c.kind, c.flags = kind, flags
+            for i in range(VELA_MAX_PAR):
+                c.par[i] = -1
+            c.mask[0] = c.mask[1] = -1
+            return c
+
+        def setp(c, slot, name, len_slot=None, required=True):
+            if not ph.has(name):
+                if required:
+                    raise KeyError(f"component needs parameter {name}, absent from the ParamHandler")
+                return False
+            c.par[slot] = ph.offset(name)
+            if len_slot is not None:
+                c.len[len_slot] = ph.length(name)
+            return True
+
+        for comp in model.components:
+            if isinstance(comp, M.SolarSystem):
+                ecl = comp.ecliptic_coordinates
+                c = new(COMP_SOLAR_SYSTEM, (FLAG_ECLIPTIC if ecl else 0) |
+                        (FLAG_PLANET_SHAPIRO if comp.planet_shapiro else 0))
+                names = ("ELONG", "ELAT", "PMELONG", "PMELAT") if ecl else ("RAJ", "DECJ", "PMRA", "PMDEC")
+                for s, nme in enumerate(names + ("PX", "POSEPOCH")):
+                    setp(c, s, nme)
+            elif isinstance(comp, M.SolarWindDispersion):
+                c = new(COMP_SOLAR_WIND)
+                setp(c, 0, "SWEPOCH")
+                setp(c, 1, "NE_SW", 0)
+            elif isinstance(comp, M.DispersionTaylor):
+                c = new(COMP_DISPERSION_TAYLOR)
+                setp(c, 0, "DMEPOCH")
+                setp(c, 1, "DM", 0)
+            elif isinstance(comp, M.DispersionPiecewise):
+                c = new(COMP_DISPERSION_PIECEWISE)
+                setp(c, 0, "DMX_", 0)
+                c.mask[0] = add_index_mask(comp.dmx_mask)
+            elif isinstance(comp, M.ChromaticTaylor):
+                c = new(COMP_CHROMATIC_TAYLOR)
+                setp(c, 0, "CMEPOCH")
+                setp(c, 1, "CM", 0)
+                setp(c, 2, "TNCHROMIDX")
+            elif isinstance(comp, M.ChromaticPiecewise):
+                c = new(COMP_CHROMATIC_PIECEWISE)
+                setp(c, 0, "CMX_", 0)
+                setp(c, 2, "TNCHROMIDX")
+                c.mask[0] = add_index_mask(comp.cmx_mask)
+            elif isinstance(comp, M.BinaryELL1):
+                c = new(COMP_BINARY_ELL1, FLAG_USE_FBX if comp.use_fbx else 0)
+                setp(c, 0, "TASC")
+                if comp.use_fbx:
+                    setp(c, 3, "FB", 0)
+                else:
+                    setp(c, 1, "PB")
+                    setp(c, 2, "PBDOT")
+                for s, nme in enumerate(("A1", "A1DOT", "EPS1", "EPS2", "EPS1DOT", "EPS2DOT", "M2", "SINI"), 4):
+                    setp(c, s, nme)
+            elif isinstance(comp, M.BinaryDD):
+                c = new(COMP_BINARY_DD, FLAG_USE_FBX if comp.use_fbx else 0)
+                setp(c, 0, "T0")
+                if comp.use_fbx:
+                    setp(c, 3, "FB", 0)
+                else:
+                    setp(c, 1, "PB")
+                    setp(c, 2, "PBDOT")
+                for s, nme in enumerate(("A1", "A1DOT", "ECC", "EDOT", "OM", "OMDOT", "DR", "DTH", "GAMMA",
+                                         "M2", "SINI"), 4):
+                    setp(c, s, nme)
+            elif isinstance(comp, M.Glitch):
+                c = new(COMP_GLITCH)
+                for s, nme in enumerate(("GLEP_", "GLPH_", "GLF0_", "GLF1_", "GLF2_", "GLF0D_", "GLTD_")):
+                    setp(c, s, nme, 0)
+            elif isinstance(comp, M.ChromaticExponentialDip):
+                c = new(COMP_EXP_DIP)
+                setp(c, 0, "EXPDIPFREF")
+                setp(c, 1, "EXPDIPEPS")
+                for s, nme in enumerate(("EXPDIPEP_", "EXPDIPAMP_", "EXPDIPIDX_", "EXPDIPTAU_"), 2):
+                    setp(c, s, nme, 0)
+            elif isinstance(comp, M.Spindown):
+                c = new(COMP_SPINDOWN)
+                setp(c, 0, "F_")
+                setp(c, 1, "F", 0)
+            elif isinstance(comp, M.PhaseOffset):
+                c = new(COMP_PHASE_OFFSET)
+                setp(c, 0, "PHOFF")
+            elif isinstance(comp, (M.ExclusivePhaseJump, M.PhaseJump)):
+                excl = isinstance(comp, M.ExclusivePhaseJump)
+                c = new(COMP_PHASE_JUMP_EXCLUSIVE if excl else COMP_PHASE_JUMP)
+                setp(c, 0, "JUMP", 0)
+                setp(c, 1, "F_")
+                setp(c, 2, "F")
+                c.mask[0] = add_index_mask(comp.jump_mask) if excl else add_bit_mask(comp.jump_mask)
+            elif isinstance(comp, M.MeasurementNoise):
+                c = new(COMP_MEASUREMENT_NOISE)
+                setp(c, 0, "EFAC", 0, required=False)
+                setp(c, 1, "EQUAD", 1, required=False)
+                c.mask[0] = add_index_mask(comp.efac_index_mask)
+                c.mask[1] = add_index_mask(comp.equad_index_mask)
+            elif isinstance(comp, (M.ExclusiveDispersionJump, M.DispersionJump)):
+                excl = isinstance(comp, M.ExclusiveDispersionJump)
+                c = new(COMP_DM_JUMP_EXCLUSIVE if excl else COMP_DM_JUMP)
+                setp(c, 0, "DMJUMP", 0)
+                c.mask[0] = add_index_mask(comp.jump_mask) if excl else add_bit_mask(comp.jump_mask)
+            elif isinstance(comp, M.DispersionMeasurementNoise):
+                c = new(COMP_DM_MEASUREMENT_NOISE)
+                setp(c, 0, "DMEFAC", 0, required=False)
+                setp(c, 1, "DMEQUAD", 1, required=False)
+                c.mask[0] = add_index_mask(comp.dmefac_index_mask)
+                c.mask[1] = add_index_mask(comp.dmequad_index_mask)
+            else:
+                raise NotImplementedError(f"component {type(comp).__name__} is outside the implemented hot path")
+            comps.append(c)
+
+        d = VelaModelDesc()
+        d.abi_version = VELA_B200_ABI_VERSION
+        self._comps = (VelaComponentDesc * len(comps))(*comps)
+        d.n_components = len(comps)
+        d.components = self._comps
+
+        self._defaults = np.ascontiguousarray(ph._default_values, dtype=np.float64)
+        self._free = np.ascontiguousarray(ph._free_indices0, dtype=np.int32)
+        d.n_params = len(self._defaults)
+        d.n_free = len(self._free)
+        d.default_values = _dptr(self._defaults)
+        d.free_indices = self._free.ctypes.data_as(C.POINTER(C.c_int32))
+
+        self._records = np.ascontiguousarray(toas.records, dtype=np.float64)
+        self._tzr = np.ascontiguousarray(model.tzr_toa.record(), dtype=np.float64)
+        d.n_toas = ntoa
+        d.wideband = 1 if toas.wideband else 0
+        d.toa_stride_bytes = self._records.shape[1] * 8
+        d.toas = self._records.ctypes.data
+        d.tzr_toa = self._tzr.ctypes.data
+
+        self._index_masks = (np.ascontiguousarray(np.stack(index_masks), dtype=np.uint32)
+                             if index_masks else np.zeros((0, ntoa), dtype=np.uint32))
+        self._bit_masks = (np.ascontiguousarray(np.stack(bit_rows), dtype=np.uint8)
+                           if bit_rows else np.zeros((0, ntoa), dtype=np.uint8))
+        d.n_index_masks = self._index_masks.shape[0]
+        d.n_bit_mask_rows = self._bit_masks.shape[0]
+        d.index_masks = self._index_masks.ctypes.data_as(C.POINTER(C.c_uint32))
+        d.bit_masks = self._bit_masks.ctypes.data_as(C.POINTER(C.c_uint8))
+
+        kernel = model.kernel
+        if isinstance(kernel, M.WhiteNoiseKernel):
+            d.kernel_kind = KERNEL_WHITE
+            d.n_gp = 0
+        elif isinstance(kernel, M.WoodburyKernel) and isinstance(kernel.inner_kernel, M.WhiteNoiseKernel):
+            d.kernel_kind = KERNEL_WOODBURY_WHITE
+            gps = []
+            for gp in kernel.gp_components:
+                g = VelaGPDesc()
+                g.par_log10_amp = g.par_gamma = g.par_f1 = -1
+                if isinstance(gp, M.MarginalizedTimingModel):
+                    g.kind = GP_MARGINALIZED_TM
+                    w = np.ascontiguousarray(gp.prior_weights_inv, dtype=np.float64)
+                    self._keep.append(w)
+                    g.n = len(w)
+                    g.weights_inv = _dptr(w)
+                else:
+                    g.kind = {M.PowerlawRedNoiseGP: GP_POWERLAW_RED, M.PowerlawDispersionNoiseGP: GP_POWERLAW_DM,
+                              M.PowerlawChromaticNoiseGP: GP_POWERLAW_CHROM}[type(gp)]
+                    lj = np.ascontiguousarray(gp.ln_js, dtype=np.float64)
+                    self._keep.append(lj)
+                    g.n = len(lj)
+                    g.ln_js = _dptr(lj)
+                    g.par_log10_amp = ph.offset(gp.amp)
+                    g.par_gamma = ph.offset(gp.gam)
+                    g.par_f1 = ph.offset(gp.freq)
+                gps.append(g)
+            self._gps = (VelaGPDesc * len(gps))(*gps)
+            d.n_gp = len(gps)
+            d.gp = self._gps
+            self._basis = np.asfortranarray(kernel.noise_basis, dtype=np.float64)
+            nrows = 2 * ntoa if toas.wideband else ntoa
+            if self._basis.shape[0] != nrows:
+                raise ValueError(f"noise_basis has {self._basis.shape[0]} rows, expected {nrows}")
+            d.basis_rows, d.basis_cols = self._basis.shape
+            d.basis_ld = self._basis.shape[0]
+            d.noise_basis = _dptr(self._basis)
+        else:
+            raise NotImplementedError(
+                f"kernel {kernel!r}: only WhiteNoiseKernel and WoodburyKernel{{WhiteNoiseKernel}} are on the "
+                "implemented hot path (ECORR kernels are a 'next' row)")
+
+        if devices:
+            self._devices = np.ascontiguousarray(devices, dtype=np.int32)
+            d.n_devices = len(self._devices)
+            d.devices = self._devices.ctypes.data_as(C.POINTER(C.c_int32))
+        else:
+            d.n_devices = 0
+        self.desc = d
+
+    @property
+    def n_rows(self) -> int:
+        return (2 if self.toas.wideband else 1) * len(self.toas)
+
+    @property
+    def n_basis(self) -> int:
+        return int(self.desc.basis_cols) if self.desc.kernel_kind != KERNEL_WHITE else 0
+
+    def byref(self):
+        return C.byref(self.desc)
