@@ -255,6 +255,13 @@ VELA_API int vela_b200_residuals(VelaHandle h, const double* params, int64_t n_f
 VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int64_t n_free, double* phiinv);
 
 /*
+ * Sigma^-1 = diag(Phi^-1) + M^T N^-1 M (full symmetric, column-major p x p) and u = M^T N^-1 y
+ * for ONE parameter vector: _calc_Sigmainv__and__MT_Ninv_y, src/likelihood/gls_likelihood.jl:101-169
+ * (pyvela reads the same quantities in spnta.py:376-394).  Woodbury kernels only.
+ */
+VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n_free, double* Sigma, double* u);
+
+/*
  * Device-resident variant used by benchmarks and by callers that already hold
  * the samples on the GPU: `d_params` is a row-major (B x n_free) DEVICE buffer on
  * device `devices[0]`, `d_out` a DEVICE buffer of B doubles.  Work is enqueued on
@@ -277,6 +284,9 @@ VELA_API double vela_b200_last_stage_ms(VelaHandle h, int stage);
 /* FP64 micro-benchmarks used for the roofline denominators (TFLOP/s):
  * kind 0 = register-resident DFMA loop, kind 1 = mma.sync m8n8k4 f64 (DMMA) loop. */
 VELA_API double vela_b200_fp64_peak_tflops(int device, int kind);
+
+/* Test hook: the correctly rounded sin/cos (double-double Taylor) used for the sky-position unit vector. */
+VELA_API int vela_b200_debug_sincos(const double* x, int n, double* s, double* c);
 
 #ifdef __cplusplus
 }

@@ -118,6 +118,15 @@ class Pulsar:
                    "vela_b200_noise_weights_inv")
         return out
 
+    def sigma_and_u(self, params):
+        """(Sigma^-1 (p, p) symmetric, u (p,)) — _calc_Σinv__and__MT_Ninv_y, gls_likelihood.jl:101-169."""
+        p = self._free(params)
+        n = int(self._lib.vela_b200_n_basis(self._h))
+        S = np.empty((n, n))
+        u = np.empty(n)
+        _lib.check(self._lib.vela_b200_sigma_and_u(self._h, _dp(p), len(p), _dp(S), _dp(u)), "vela_b200_sigma_and_u")
+        return S, u
+
     # -- benchmarking hooks
     def lnlike_device(self, d_params_ptr: int, B: int, d_out_ptr: int, stream: int = 0):
         _lib.check(self._lib.vela_b200_lnlike_batch_device(self._h, C.c_void_p(d_params_ptr), B,

@@ -350,8 +350,13 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         h->n_gp = desc->n_gp;
         for (int I = 0; I < h->n_blocks; ++I)
             for (int J = 0; J <= I; ++J) units.push_back(make_int2(I, J));
-        while (units.size() % kSigWarps) units.push_back(make_int2(-2, 0));  // keep u units in their own CTAs
-        for (int t = 0; t < h->n_blocks; t += 8) units.push_back(make_int2(-1, t));
+        // u units go into CTAs of their own, two per CTA (2 x 8 column blocks = the kSigMaxSlots a CTA can stage)
+        int n_u = 0;
+        for (int t = 0; t < h->n_blocks; t += 8, ++n_u) {
+            if (n_u % 2 == 0)
+                while (units.size() % kSigWarps) units.push_back(make_int2(-2, 0));
+            units.push_back(make_int2(-1, t));
+        }
         h->n_units = (int)units.size();
         int col = 0;
         for (int g = 0; g < desc->n_gp; ++g) {
@@ -603,6 +608,53 @@ VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int
     return VELA_OK;
 }
 
+// _calc_Sigmainv__and__MT_Ninv_y (gls_likelihood.jl:101-169) for ONE parameter vector:
+// Sigma^-1 = diag(Phi^-1) + M^T N^-1 M as a full symmetric column-major p x p matrix, u = M^T N^-1 y.
+VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n_free, double* Sigma, double* u) {
+    if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
+    if (h->kernel_kind == VELA_KERNEL_WHITE) return fail(VELA_ERR_UNSUPPORTED, "white-noise kernel has no Sigma");
+    if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d free parameters, got %ld", h->prog.n_free, (long)n_free);
+    std::vector<double> phi(h->p);
+    if (int rc = vela_b200_noise_weights_inv(h, params, n_free, phi.data())) return rc;
+    std::lock_guard<std::mutex> lock(h->mtx);
+    DeviceModel& d = h->devs[0];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d.dev);
+    int rc = ensure_device_buffers(h, d, 1);
+    if (rc) { cudaSetDevice(prev); return rc; }
+    Buffers& b = d.buf;
+    cudaMemcpyAsync(b.params, params, sizeof(double) * std::max<long>(n_free, 1), cudaMemcpyHostToDevice, d.stream);
+    sample_prologue_kernel<<<1, 128, 0, d.stream>>>(h->prog, d.defaults, d.free_idx, b.params, 1, d.tzr_block,
+                                                    d.index_masks, d.bit_masks, h->n_toas, b.Pext, b.tzr);
+    ChainArgs ca;
+    ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
+    ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = 1;
+    ca.Y = b.Y; ca.W = b.W; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
+    size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
+    toa_chain_kernel<<<dim3((unsigned)h->n_tiles, 1), h->chain_threads, chain_smem, d.stream>>>(h->prog, ca);
+    SigmaArgs sa;
+    sa.M = d.M; sa.ldM = d.ldM; sa.n_blocks = h->n_blocks; sa.n_rows_pad = h->n_rows_pad; sa.W = b.W; sa.Y = b.Y;
+    sa.ld_yw = h->n_rows_pad; sa.B = 1; sa.units = d.units; sa.n_units = h->n_units; sa.Sig = b.Sig; sa.U = b.U;
+    sigma_contract_kernel<<<dim3((unsigned)((h->n_units + kSigWarps - 1) / kSigWarps), 1), kSigThreads, sigma_smem_bytes(), d.stream>>>(sa);
+    h->launches += 3;
+    std::vector<double> S((size_t)h->pp * h->pp), U(h->pp);
+    cudaMemcpyAsync(S.data(), b.Sig, sizeof(double) * S.size(), cudaMemcpyDeviceToHost, d.stream);
+    cudaMemcpyAsync(U.data(), b.U, sizeof(double) * U.size(), cudaMemcpyDeviceToHost, d.stream);
+    cudaError_t e = cudaStreamSynchronize(d.stream);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "sigma_and_u: %s", cudaGetErrorString(e));
+    const int p = h->p, pp = h->pp;
+    for (int r = 0; r < p; ++r)
+        for (int c = 0; c <= r; ++c) {
+            double v = S[(size_t)r * pp + c] + (r == c ? phi[r] : 0.0);
+            Sigma[(size_t)c * p + r] = v;
+            Sigma[(size_t)r * p + c] = v;
+        }
+    if (u) memcpy(u, U.data(), sizeof(double) * p);
+    return VELA_OK;
+}
+
 VELA_API int vela_b200_set_stage_timing(VelaHandle h, int enabled) {
     if (!h) return VELA_ERR_INVALID_ARG;
     h->stage_timing = enabled != 0;
@@ -612,6 +664,21 @@ VELA_API int vela_b200_set_stage_timing(VelaHandle h, int enabled) {
 VELA_API double vela_b200_last_stage_ms(VelaHandle h, int stage) {
     if (!h || !h->stage_timing || stage < 0 || stage > 4) return -1.0;
     return h->devs[0].stage_ms[stage];
+}
+
+// test hook: the correctly-rounded sin/cos used for the sky position (n host values in, n out)
+VELA_API int vela_b200_debug_sincos(const double* x, int n, double* s, double* c) {
+    if (vela_b200_device_count() <= 0) return fail(VELA_ERR_NO_DEVICE, "no CUDA device");
+    double *dx = nullptr, *ds = nullptr, *dc = nullptr;
+    CU(cudaMalloc((void**)&dx, sizeof(double) * n));
+    CU(cudaMalloc((void**)&ds, sizeof(double) * n));
+    CU(cudaMalloc((void**)&dc, sizeof(double) * n));
+    CU(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    sincos_cr_kernel<<<(n + 127) / 128, 128>>>(dx, n, ds, dc);
+    CU(cudaMemcpy(s, ds, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(c, dc, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(ds); cudaFree(dc);
+    return VELA_OK;
 }
 
 VELA_API double vela_b200_fp64_peak_tflops(int device, int kind) {

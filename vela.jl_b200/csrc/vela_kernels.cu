@@ -506,6 +506,12 @@ __global__ void phiinv_kernel(CholArgs a, double* __restrict__ out) {
     }
 }
 
+// test hook for sincos_cr
+__global__ void sincos_cr_kernel(const double* x, int n, double* s, double* c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sincos_cr(x[i], s + i, c + i);
+}
+
 // ------------------------------------------------------------------------------------------
 // FP64 peak micro-benchmarks (roofline denominators)
 // ------------------------------------------------------------------------------------------

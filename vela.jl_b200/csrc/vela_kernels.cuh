@@ -84,6 +84,7 @@ __global__ void finish_white_kernel(const double* partial, int n_tiles, long B, 
 __global__ void sigma_contract_kernel(SigmaArgs a);
 __global__ void chol_finish_kernel(CholArgs a);
 __global__ void phiinv_kernel(CholArgs a, double* out);
+__global__ void sincos_cr_kernel(const double* x, int n, double* s, double* c);
 __global__ void dfma_peak_kernel(double* out, int iters);
 __global__ void dmma_peak_kernel(double* out, int iters);
 
