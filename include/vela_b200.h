@@ -251,6 +251,15 @@ VELA_API int vela_b200_chi2_batch(VelaHandle h, const double* params, int64_t B,
  */
 VELA_API int vela_b200_residuals(VelaHandle h, const double* params, int64_t n_free, double* y, double* w);
 
+/*
+ * Phase residuals before rounding to Float64, for ONE parameter vector: the Double64
+ * `phase_residual(toa, ctoa) - tzrphase` (src/toa/toa.jl:151, src/residuals/residuals.jl:10) as (hi, lo)
+ * and `doppler_shifted_spin_frequency(ctoa)` (src/toa/toa.jl:131-134), n_toas values each.
+ * This is what pulse-number assignment needs (pyvela/pyvela/model.py:699-700 asks PINT for it).
+ */
+VELA_API int vela_b200_phases(VelaHandle h, const double* params, int64_t n_free, double* phase_hi,
+                              double* phase_lo, double* spin_frequency);
+
 /* Phi^-1 (p values) for ONE parameter vector; Woodbury kernels only. */
 VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int64_t n_free, double* phiinv);
 
@@ -271,13 +280,17 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
 VELA_API int vela_b200_lnlike_batch_device(VelaHandle h, const double* d_params, int64_t B,
                                   double* d_out, void* stream);
 
+/* Same, for the log-posterior: d_lnprior is a DEVICE buffer of B doubles (NULL = flat prior). */
+VELA_API int vela_b200_lnpost_batch_device(VelaHandle h, const double* d_params, int64_t B, const double* d_lnprior,
+                                           int with_prior, double* d_out, void* stream);
+
 /* Number of kernel launches the handle has issued so far (all devices). */
 VELA_API int64_t vela_b200_launch_count(VelaHandle h);
 
-/* Wall-free timing hooks: device-time (ms) of the stages of the last batch on device 0,
- * measured with CUDA events on the handle's stream.  stage: 0 prologue, 1 chain,
- * 2 sigma contraction, 3 cholesky/finish, 4 total (H2D..D2H).  Returns <0 if
- * stage timing was not enabled. */
+/* Timing hooks: device time (ms) of the stages of the last batch on device 0, measured with CUDA
+ * events on the stream the kernels were launched on.  stage: 0 sample prologue, 1 TOA chain,
+ * 2 Sigma contraction (white kernels: finish), 3 Cholesky/finish, 4 all kernels.  Returns <0 if stage
+ * timing is not enabled. */
 VELA_API int vela_b200_set_stage_timing(VelaHandle h, int enabled);
 VELA_API double vela_b200_last_stage_ms(VelaHandle h, int stage);
 

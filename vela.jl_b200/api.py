@@ -111,6 +111,14 @@ class Pulsar:
         _lib.check(self._lib.vela_b200_residuals(self._h, _dp(p), len(p), _dp(y), _dp(w)), "vela_b200_residuals")
         return y, w
 
+    def phases(self, params):
+        """(phase_hi, phase_lo, doppler-shifted spin frequency) per TOA; phase = phase_residual - tzrphase."""
+        p = self._free(params)
+        n = len(self.toas)
+        hi, lo, f = np.empty(n), np.empty(n), np.empty(n)
+        _lib.check(self._lib.vela_b200_phases(self._h, _dp(p), len(p), _dp(hi), _dp(lo), _dp(f)), "vela_b200_phases")
+        return hi, lo, f
+
     def noise_weights_inv(self, params) -> np.ndarray:
         p = self._free(params)
         out = np.empty(int(self._lib.vela_b200_n_basis(self._h)))
@@ -132,6 +140,11 @@ class Pulsar:
         _lib.check(self._lib.vela_b200_lnlike_batch_device(self._h, C.c_void_p(d_params_ptr), B,
                                                            C.c_void_p(d_out_ptr), C.c_void_p(stream)),
                    "vela_b200_lnlike_batch_device")
+
+    def lnpost_device(self, d_params_ptr: int, B: int, d_lnprior_ptr: int, d_out_ptr: int, stream: int = 0):
+        _lib.check(self._lib.vela_b200_lnpost_batch_device(self._h, C.c_void_p(d_params_ptr), B,
+                                                           C.c_void_p(d_lnprior_ptr), 1, C.c_void_p(d_out_ptr),
+                                                           C.c_void_p(stream)), "vela_b200_lnpost_batch_device")
 
     def launch_count(self) -> int:
         return int(self._lib.vela_b200_launch_count(self._h))

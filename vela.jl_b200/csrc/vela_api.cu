@@ -159,7 +159,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
     ChainArgs ca;
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = B; ca.group = h->chain_group;
-    ca.emit = woodbury ? 1 : 0; ca.Y = b.Y; ca.W = b.W; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
+    ca.emit = woodbury ? 1 : 0; ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     const int warps = h->chain_threads / 32;
     size_t chain_smem = ((size_t)h->chain_group * pg.row + 2 * h->chain_group + (size_t)warps * h->chain_group * 2) * sizeof(double);
     dim3 cgrid((unsigned)h->n_tiles, (unsigned)((B + h->chain_group - 1) / h->chain_group));
@@ -523,7 +523,8 @@ VELA_API int vela_b200_chi2_batch(VelaHandle h, const double* params, int64_t B,
     return run_host_batch(h, params, B, n_free, row_stride, col_stride, nullptr, 0, 1, out_chi2);
 }
 
-VELA_API int vela_b200_lnlike_batch_device(VelaHandle h, const double* d_params, int64_t B, double* d_out, void* stream) {
+VELA_API int vela_b200_lnpost_batch_device(VelaHandle h, const double* d_params, int64_t B, const double* d_lnprior,
+                                           int with_prior, double* d_out, void* stream) {
     if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
     if (B <= 0) return VELA_OK;
     std::lock_guard<std::mutex> lock(h->mtx);
@@ -532,16 +533,22 @@ VELA_API int vela_b200_lnlike_batch_device(VelaHandle h, const double* d_params,
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(d.dev);
+    long cap_before = d.buf.cap_B;
     int rc = ensure_device_buffers(h, d, B);
     cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
-    if (!rc && st != d.stream) cudaStreamSynchronize(d.stream);  // scratch zero-fills were queued on the handle's stream
-    if (!rc) rc = enqueue_batch(h, d, d_params, B, 0, 0, nullptr, d_out, st);
+    if (!rc && st != d.stream && d.buf.cap_B != cap_before) cudaStreamSynchronize(d.stream);  // scratch zero-fills ran on the handle's stream
+    if (!rc) rc = enqueue_batch(h, d, d_params, B, 0, with_prior, d_lnprior, d_out, st);
     cudaSetDevice(prev);
     return rc;
 }
 
-// _calc_resids_and_Ninvdiag for ONE parameter vector (runs the emit path with B = 1 on device 0)
-VELA_API int vela_b200_residuals(VelaHandle h, const double* params, int64_t n_free, double* y, double* w) {
+VELA_API int vela_b200_lnlike_batch_device(VelaHandle h, const double* d_params, int64_t B, double* d_out, void* stream) {
+    return vela_b200_lnpost_batch_device(h, d_params, B, nullptr, 0, d_out, stream);
+}
+
+// Runs prologue + chain for ONE parameter vector on device 0 and copies per-TOA outputs back.
+// mode 1: y, w (n_rows each); mode 2: phase hi, lo and spin frequency (n_toas each).
+static int run_single(VelaHandle h, const double* params, int64_t n_free, int mode, double* o0, double* o1, double* o2) {
     if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
     if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d free parameters, got %ld", h->prog.n_free, (long)n_free);
     std::lock_guard<std::mutex> lock(h->mtx);
@@ -552,30 +559,40 @@ VELA_API int vela_b200_residuals(VelaHandle h, const double* params, int64_t n_f
     int rc = ensure_device_buffers(h, d, 1);
     if (rc) { cudaSetDevice(prev); return rc; }
     Buffers& b = d.buf;
-    double *dY = b.Y, *dW = b.W;
-    bool tmp = false;
-    if (!dY) {  // white kernel: no resident y/w scratch
-        tmp = true;
-        cudaMalloc((void**)&dY, sizeof(double) * h->n_rows_pad);
-        cudaMalloc((void**)&dW, sizeof(double) * h->n_rows_pad);
-    }
+    double *dY = nullptr, *dW = nullptr, *dF = nullptr;
+    cudaMalloc((void**)&dY, sizeof(double) * h->n_rows_pad);
+    cudaMalloc((void**)&dW, sizeof(double) * h->n_rows_pad);
+    cudaMalloc((void**)&dF, sizeof(double) * h->n_rows_pad);
     cudaMemcpyAsync(b.params, params, sizeof(double) * std::max<long>(n_free, 1), cudaMemcpyHostToDevice, d.stream);
     sample_prologue_kernel<<<1, 128, 0, d.stream>>>(h->prog, d.defaults, d.free_idx, b.params, 1, d.tzr_block,
                                                     d.index_masks, d.bit_masks, h->n_toas, b.Pext, b.tzr);
     ChainArgs ca;
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
-    ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = 1;
-    ca.Y = dY; ca.W = dW; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
+    ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = mode;
+    ca.Y = dY; ca.W = dW; ca.F = dF; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
     toa_chain_kernel<<<dim3((unsigned)h->n_tiles, 1), h->chain_threads, chain_smem, d.stream>>>(h->prog, ca);
     h->launches += 2;
-    if (y) cudaMemcpyAsync(y, dY, sizeof(double) * h->n_rows, cudaMemcpyDeviceToHost, d.stream);
-    if (w) cudaMemcpyAsync(w, dW, sizeof(double) * h->n_rows, cudaMemcpyDeviceToHost, d.stream);
+    const long n = mode == 1 ? h->n_rows : h->n_toas;
+    if (o0) cudaMemcpyAsync(o0, dY, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
+    if (o1) cudaMemcpyAsync(o1, dW, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
+    if (o2) cudaMemcpyAsync(o2, dF, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
     cudaError_t e = cudaStreamSynchronize(d.stream);
-    if (tmp) { cudaFree(dY); cudaFree(dW); }
+    cudaFree(dY); cudaFree(dW); cudaFree(dF);
     cudaSetDevice(prev);
-    if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "residuals: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "single-sample run: %s", cudaGetErrorString(e));
     return VELA_OK;
+}
+
+// _calc_resids_and_Ninvdiag for ONE parameter vector
+VELA_API int vela_b200_residuals(VelaHandle h, const double* params, int64_t n_free, double* y, double* w) {
+    return run_single(h, params, n_free, 1, y, w, nullptr);
+}
+
+// phase_residual(toa, ctoa) - tzrphase as a Double64 (hi, lo) and doppler_shifted_spin_frequency per TOA
+VELA_API int vela_b200_phases(VelaHandle h, const double* params, int64_t n_free, double* phase_hi, double* phase_lo,
+                              double* spin_frequency) {
+    return run_single(h, params, n_free, 2, phase_hi, phase_lo, spin_frequency);
 }
 
 VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int64_t n_free, double* phiinv) {
@@ -630,7 +647,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     ChainArgs ca;
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = 1;
-    ca.Y = b.Y; ca.W = b.W; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
+    ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
     toa_chain_kernel<<<dim3((unsigned)h->n_tiles, 1), h->chain_threads, chain_smem, d.stream>>>(h->prog, ca);
     SigmaArgs sa;
@@ -663,7 +680,16 @@ VELA_API int vela_b200_set_stage_timing(VelaHandle h, int enabled) {
 
 VELA_API double vela_b200_last_stage_ms(VelaHandle h, int stage) {
     if (!h || !h->stage_timing || stage < 0 || stage > 4) return -1.0;
-    return h->devs[0].stage_ms[stage];
+    DeviceModel& d = h->devs[0];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d.dev);
+    float ms = -1.0f;
+    cudaError_t e = cudaEventSynchronize(d.ev[4]);
+    if (e == cudaSuccess) e = stage < 4 ? cudaEventElapsedTime(&ms, d.ev[stage], d.ev[stage + 1]) : cudaEventElapsedTime(&ms, d.ev[0], d.ev[4]);
+    if (e != cudaSuccess) { cudaGetLastError(); ms = -1.0f; }
+    cudaSetDevice(prev);
+    return ms;
 }
 
 // test hook: the correctly-rounded sin/cos used for the sky position (n host values in, n out)

@@ -115,7 +115,12 @@ __global__ void __launch_bounds__(kChainThreads) toa_chain_kernel(const __grid_c
         }
         if (k.bad || k.spin_frequency == 0.0) chi = CUDART_NAN;
         if (!active) { chi = 0.0; lg = 0.0; }
-        if (a.emit && active) {
+        if (a.emit == 2 && active) {  // phase mode: Double64 phase residual and doppler-shifted spin frequency
+            const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
+            a.Y[o] = dphase.hi;
+            a.W[o] = dphase.lo;
+            a.F[o] = f;
+        } else if (a.emit && active) {
             const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
             a.Y[o] = tres;
             a.W[o] = w;

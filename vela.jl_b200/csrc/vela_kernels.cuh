@@ -28,9 +28,10 @@ struct ChainArgs {
     const uint8_t* bit_masks;
     long B;
     int group;                 // walkers per block
-    int emit;                  // 1: write y, w (Woodbury path)
+    int emit;                  // 1: write y, w (Woodbury path); 2: write phase (hi, lo) and spin frequency
     double* Y;                 // [B_pad][ld_yw]
     double* W;
+    double* F;                 // emit == 2 only
     long ld_yw;
     double* partial;           // [tiles][B][2]
 };

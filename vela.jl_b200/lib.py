@@ -17,8 +17,8 @@ _LIB = None
 EXPORTS = [
     "vela_b200_device_count", "vela_b200_last_error", "vela_b200_create", "vela_b200_destroy",
     "vela_b200_n_free", "vela_b200_n_rows", "vela_b200_n_basis", "vela_b200_lnlike_batch",
-    "vela_b200_lnpost_batch", "vela_b200_chi2_batch", "vela_b200_residuals",
-    "vela_b200_noise_weights_inv", "vela_b200_sigma_and_u", "vela_b200_lnlike_batch_device", "vela_b200_launch_count",
+    "vela_b200_lnpost_batch", "vela_b200_chi2_batch", "vela_b200_residuals", "vela_b200_phases",
+    "vela_b200_noise_weights_inv", "vela_b200_sigma_and_u", "vela_b200_lnlike_batch_device", "vela_b200_lnpost_batch_device", "vela_b200_launch_count",
     "vela_b200_set_stage_timing", "vela_b200_last_stage_ms", "vela_b200_fp64_peak_tflops",
     "vela_b200_debug_sincos",
 ]
@@ -63,9 +63,11 @@ def lib():
     L.vela_b200_lnpost_batch.argtypes = [vp, dp, i64, i64, i64, i64, dp, dp]
     L.vela_b200_chi2_batch.argtypes = [vp, dp, i64, i64, i64, i64, dp]
     L.vela_b200_residuals.argtypes = [vp, dp, i64, dp, dp]
+    L.vela_b200_phases.argtypes = [vp, dp, i64, dp, dp, dp]
     L.vela_b200_noise_weights_inv.argtypes = [vp, dp, i64, dp]
     L.vela_b200_sigma_and_u.argtypes = [vp, dp, i64, dp, dp]
     L.vela_b200_lnlike_batch_device.argtypes = [vp, vp, i64, vp, vp]
+    L.vela_b200_lnpost_batch_device.argtypes = [vp, vp, i64, vp, C.c_int, vp, vp]
     L.vela_b200_launch_count.argtypes = [vp]
     L.vela_b200_launch_count.restype = i64
     L.vela_b200_set_stage_timing.argtypes = [vp, C.c_int]

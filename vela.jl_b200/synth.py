@@ -1,0 +1,378 @@
+"""Synthetic phase-connected pulsar datasets of the shapes named in BASELINE.json `configs`.
+
+No PINT here: TOAs are built directly in Vela's internal representation (seconds from PEPOCH as a
+double-double, light-second ephemeris vectors — pyvela/pyvela/toas.py:11-109 defines that contract).
+
+Phase connection needs the model phase at each trial TOA in double-double precision.  The generator
+does not compute it itself: it is handed an *evaluator factory* — `make_eval(model, toas)` returning
+an object with `.phases(params) -> (hi, lo, f)` and `.resids_and_Ninvdiag(params) -> (y, w)`.
+`bench.py` passes `vela_jl_b200.Pulsar` (the CUDA library evaluates its own inputs); the CPU tests
+pass a wrapper around the oracle.  Either way the dataset is deterministic given (config, seed).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from . import model as M
+from . import priors as P
+
+DAY = 86400.0
+AU = 499.00478383615643           # light-seconds (src/model/solarsystem.jl:5)
+OBL = 0.4090926006005829
+YEAR = 365.25 * DAY
+DMCONST = 4.148808e15             # Hz^2 pc^-1 cm^3 s: DM [pc cm^-3] -> Vela units [Hz] (parameters.py:42-46)
+F_YR = 1.0 / YEAR
+
+
+@dataclass
+class SynthDataset:
+    name: str
+    model: M.TimingModel
+    toas: M.TOAs
+    truth: np.ndarray                 # free-parameter vector the data were generated at
+    sigma_par: np.ndarray             # per-parameter scatter used for walker batches
+    noise_draw: Dict[int, tuple]      # free index -> ("lognormal"|"loguniform"|"normal", a, b)
+    info: dict
+
+    def walkers(self, n: int, seed: int = 0) -> np.ndarray:
+        """Row b = truth + sigma_par * z_b (posterior-width scatter); noise
+        hyper-parameters are drawn from narrow priors around the truth."""
+        rng = np.random.default_rng(seed)
+        out = self.truth[None, :] + self.sigma_par[None, :] * rng.standard_normal((n, len(self.truth)))
+        for k, (kind, a, b) in self.noise_draw.items():
+            if kind == "lognormal":
+                out[:, k] = a * np.exp(b * rng.standard_normal(n))
+            elif kind == "loguniform":
+                out[:, k] = np.exp(rng.uniform(np.log(a), np.log(b), n))
+            else:
+                out[:, k] = a + b * rng.standard_normal(n)
+        return np.ascontiguousarray(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# toy solar-system ephemeris: circular, coplanar orbits in the ecliptic, rotated to equatorial axes
+# ---------------------------------------------------------------------------------------------
+_PLANETS = [("jupiter", 5.2044, 11.862), ("saturn", 9.5826, 29.4571), ("venus", 0.7233, 0.61519),
+            ("uranus", 19.2184, 84.0205), ("neptune", 30.07, 164.8)]
+
+
+def _orbit(t, radius_au, period_yr, phase0):
+    ang = 2 * np.pi * t / (period_yr * YEAR) + phase0
+    x, y = radius_au * AU * np.cos(ang), radius_au * AU * np.sin(ang)
+    w = 2 * np.pi / (period_yr * YEAR)
+    vx, vy = -radius_au * AU * w * np.sin(ang), radius_au * AU * w * np.cos(ang)
+    ce, se = np.cos(OBL), np.sin(OBL)
+    pos = np.stack([x, ce * y, se * y], axis=1)
+    vel = np.stack([vx, ce * vy, se * vy], axis=1)
+    return pos, vel
+
+
+def ephemeris_words(t: np.ndarray, rng) -> np.ndarray:
+    """24 ephemeris words per TOA (ssb_obs_pos, ssb_obs_vel, obs_sun_pos, 5 planets)."""
+    earth, vel = _orbit(t, 1.0, 1.0, rng.uniform(0, 2 * np.pi))
+    sun = 0.0 * earth
+    sun[:, 0] += 1.5 * np.cos(2 * np.pi * t / (11.86 * YEAR))      # a couple of light-seconds of solar wobble
+    sun[:, 1] += 1.5 * np.sin(2 * np.pi * t / (11.86 * YEAR))
+    cols = [earth, vel, sun - earth]
+    for _, r, per in _PLANETS:
+        pos, _ = _orbit(t, r, per, rng.uniform(0, 2 * np.pi))
+        cols.append(pos - earth)
+    return np.concatenate(cols, axis=1)
+
+
+def _records(t_hi, t_lo, err, freq, eph, wide_dm=None) -> np.ndarray:
+    n = len(t_hi)
+    rec = np.zeros((n, M.WTOA_WORDS if wide_dm is not None else M.TOA_WORDS))
+    rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3] = t_hi, t_lo, err, freq
+    rec[:, 6:30] = eph
+    rec[:, 30] = np.arange(1, n + 1, dtype=np.uint64).view(np.float64)
+    if wide_dm is not None:
+        rec[:, 31], rec[:, 32] = wide_dm
+    return rec
+
+
+def _two_sum(a, b):
+    s = a + b
+    v = s - a
+    return s, (a - (s - v)) + (b - v)
+
+
+def _shift(t_hi, t_lo, delta):
+    """(t_hi, t_lo) + delta in double-double (delta: float64 array)."""
+    s, e = _two_sum(t_hi, delta)
+    e = e + t_lo
+    hi = s + e
+    return hi, e - (hi - s)
+
+
+def _fourier_basis(t, nharm, tspan):
+    """PINT create_fourier_design_matrix convention: columns [sin x nharm, cos x nharm] (model.py:566-567)."""
+    k = np.arange(1, nharm + 1)
+    arg = 2 * np.pi * np.outer(t - t.min(), k) / tspan
+    return np.sin(arg), np.cos(arg)
+
+
+def _powerlaw_weights(log10A, gamma, f1, nharm):
+    """gp_noise.jl:12-16,64-78 (weights, not inverse) for linear harmonics."""
+    A = 10.0 ** log10A
+    fyr = 1.0 / 3600 / 24 / 365.25
+    P1 = A * A / (12 * np.pi**2 * fyr**3) * (fyr / f1) ** gamma * f1
+    return P1 * np.exp(-gamma * np.log(np.arange(1, nharm + 1)))
+
+
+# ---------------------------------------------------------------------------------------------
+# configuration table
+# ---------------------------------------------------------------------------------------------
+CONFIGS = {
+    # BASELINE.json configs[1]: "sim2 synthetic ELL1 binary pulsar, 5k TOAs, EFAC/EQUAD white noise, 4096-walker batch"
+    "config2_ell1": dict(ntoa=5000, span_d=4000.0, binary="ELL1", nback=4, walkers=4096, seed=2),
+    # configs[2]: "sim3_gp: PowerlawRedNoiseGP Woodbury likelihood, 10k TOAs, 30 Fourier harmonics, 8192 walkers"
+    "config3_gp": dict(ntoa=10000, span_d=4000.0, red=30, nback=4, walkers=8192, seed=3),
+    # configs[3]: "BinaryDD + DMGP + SolarWind wideband TOAs with MarginalizedTimingModel, 20k TOAs, 8192 walkers"
+    "config4_dd_wb": dict(ntoa=20000, span_d=5000.0, binary="DD", wideband=True, dmgp=30, solarwind=True,
+                          ecliptic=True, mtm=True, nback=1, walkers=8192, seed=4),
+    # configs[4]: "100k TOAs, red+DM+chromatic GP (rank ~300), 65536 walkers sharded over 8 GPUs"
+    "config5_array": dict(ntoa=100000, span_d=6000.0, red=50, dmgp=50, chromgp=50, nback=8, walkers=65536, seed=5),
+}
+
+
+def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, seed: Optional[int] = None) -> SynthDataset:
+    cfg = dict(CONFIGS[name])
+    if ntoa is not None:
+        cfg["ntoa"] = ntoa
+    if seed is not None:
+        cfg["seed"] = seed
+    rng = np.random.default_rng(cfg["seed"])
+    n = cfg["ntoa"]
+    span = cfg["span_d"] * DAY
+    wide = bool(cfg.get("wideband"))
+    ecl = bool(cfg.get("ecliptic"))
+    nback = cfg["nback"]
+
+    # ---- TOA skeleton
+    t = np.sort(rng.uniform(-span / 2, span / 2, n))
+    freqs = np.array([500e6, 643e6, 786e6, 929e6, 1071e6, 1214e6, 1357e6, 1500e6])
+    freq = 1400e6 * np.ones(n) if wide else freqs[np.arange(n) % 8]
+    err = rng.uniform(0.5e-6, 2e-6, n)
+    backend = (np.arange(n) // 8) % nback + 1          # all 8 frequencies of an epoch share a backend
+    eph = ephemeris_words(t, rng)
+    dm_err = DMCONST * 1e-4 * np.ones(n)
+
+    # ---- parameters (Vela units)
+    single: List[M.Parameter] = []
+    multi: List[M.MultiParameter] = []
+    sigma: Dict[str, float] = {}
+    noise_draw_names: Dict[str, tuple] = {}
+
+    def sp(name, val, free=False, dim=0, noise=False, sig=0.0):
+        single.append(M.Parameter(name, float(val), dim, not free, "", 1.0, noise))
+        if free:
+            sigma[name] = sig
+
+    def mp(name, vals, free, dim=0, noise=False, sig=None, prefix=None):
+        ps = []
+        for i, (v, fr) in enumerate(zip(vals, free)):
+            pname = f"{prefix or name}{i + 1}" if len(vals) > 1 or prefix else name
+            ps.append(M.Parameter(pname, float(v), dim, not fr, "", 1.0, noise))
+            if fr:
+                sigma[pname] = sig[i] if sig is not None else 0.0
+        multi.append(M.MultiParameter(name, ps))
+
+    F0 = 218.8118437960826 if name != "config2_ell1" else 173.6879458121843
+    F_hi = float(F0)
+    lon, lat = (1.2, 0.3) if ecl else (4.51, -0.21)
+    sp("POSEPOCH", 0.0, dim=1)
+    sp("PX", 1.2 * 9.715611890180196e-12 if ecl else 0.0, dim=-1)
+    sp("ELONG" if ecl else "RAJ", lon, free=True)
+    sp("ELAT" if ecl else "DECJ", lat, free=True)
+    sp("PMELONG" if ecl else "PMRA", 3.0 * 1.5362818500441604e-16, free=True, dim=-1)
+    sp("PMELAT" if ecl else "PMDEC", -2.0 * 1.5362818500441604e-16, free=True, dim=-1)
+    mtm = bool(cfg.get("mtm"))
+    sp("PHOFF", 0.0, free=not mtm)
+    if cfg.get("solarwind"):
+        sp("SWEPOCH", 0.0, dim=1)
+    sp("DMEPOCH", 0.0, dim=1)
+    if cfg.get("chromgp"):
+        sp("CMEPOCH", 0.0, dim=1)
+        sp("TNCHROMIDX", 4.0)
+    binary = cfg.get("binary")
+    if binary == "ELL1":
+        sp("TASC", 0.3 * DAY, free=True, dim=1)
+        sp("PB", 4.0742 * DAY, free=True, dim=1)
+        sp("PBDOT", 0.0)
+        sp("A1", 3.3667, free=True, dim=1)
+        sp("A1DOT", 0.0)
+        sp("EPS1", 1.2e-5, free=True)
+        sp("EPS2", -0.8e-5, free=True)
+        sp("EPS1DOT", 0.0, dim=-1)
+        sp("EPS2DOT", 0.0, dim=-1)
+        sp("M2", 0.25 * 4.92549094830932e-06, free=True, dim=1)
+        sp("SINI", 0.95, free=True)
+    elif binary == "DD":
+        sp("T0", 1.7 * DAY, free=True, dim=1)
+        sp("PB", 25.3 * DAY, free=True, dim=1)
+        sp("PBDOT", 0.0)
+        sp("A1", 21.3, free=True, dim=1)
+        sp("A1DOT", 0.0)
+        sp("ECC", 0.1072, free=True)
+        sp("EDOT", 0.0, dim=-1)
+        sp("OM", 1.1, free=True)
+        sp("OMDOT", 2.0e-10, free=True, dim=-1)
+        sp("DR", 0.0)
+        sp("DTH", 0.0)
+        sp("GAMMA", 1.0e-3, dim=1)
+        sp("M2", 0.3 * 4.92549094830932e-06, free=True, dim=1)
+        sp("SINI", 0.9, free=True)
+    for key, amp, gam in (("RED", -13.6, 3.8), ("DM", -13.4, 3.2), ("CHROM", -13.8, 3.5)):
+        flag = {"RED": "red", "DM": "dmgp", "CHROM": "chromgp"}[key]
+        if cfg.get(flag):
+            sp(f"PL{key}FREQ", 1.0 / span, dim=-1)
+    sp("F_", F_hi, dim=-1)
+    dm0 = 15.0 * DMCONST
+    if cfg.get("solarwind"):
+        mp("NE_SW", [1.7e8], [True], dim=-2, sig=[0.0])   # ~7.9 cm^-3 in Vela units (cf. sim_sw.wb fixture)
+    mp("DM", [dm0, 1e-4 * DMCONST / YEAR], [not mtm, True], dim=-1, prefix="DM", sig=[0.0, 0.0])
+    if cfg.get("chromgp"):
+        mp("CM", [0.0], [False], dim=-1, prefix="CM")
+    mp("F", [0.0, -1.0e-15], [not mtm, not mtm], dim=-1, prefix="F", sig=[0.0, 0.0])
+    # noise parameters
+    for key, amp, gam in (("RED", -13.6, 3.8), ("DM", -13.4, 3.2), ("CHROM", -13.8, 3.5)):
+        flag = {"RED": "red", "DM": "dmgp", "CHROM": "chromgp"}[key]
+        if cfg.get(flag):
+            sp(f"TN{key}AMP", amp, free=True, noise=True)
+            sp(f"TN{key}GAM", gam, free=True, noise=True)
+            noise_draw_names[f"TN{key}AMP"] = ("normal", amp, 0.3)
+            noise_draw_names[f"TN{key}GAM"] = ("normal", gam, 0.4)
+    efac_true = 1.0 + 0.05 * rng.standard_normal(nback)
+    equad_true = np.exp(rng.uniform(np.log(1e-7), np.log(5e-7), nback))
+    mp("EFAC", efac_true, [True] * nback, noise=True, prefix="EFAC", sig=[0.0] * nback)
+    mp("EQUAD", equad_true, [True] * nback, dim=1, noise=True, prefix="EQUAD", sig=[0.0] * nback)
+    for i in range(nback):
+        noise_draw_names[f"EFAC{i + 1}"] = ("lognormal", efac_true[i], 0.05)
+        noise_draw_names[f"EQUAD{i + 1}"] = ("loguniform", 0.5 * equad_true[i], 2.0 * equad_true[i])
+    if wide:
+        mp("DMEFAC", [1.05], [True], noise=True, prefix="DMEFAC", sig=[0.0])
+        mp("DMEQUAD", [0.5e-4 * DMCONST], [True], dim=-1, noise=True, prefix="DMEQUAD", sig=[0.0])
+        noise_draw_names["DMEFAC1"] = ("lognormal", 1.05, 0.05)
+        noise_draw_names["DMEQUAD1"] = ("loguniform", 0.25e-4 * DMCONST, 1e-4 * DMCONST)
+    handler = M.ParamHandler(single, multi)
+
+    # ---- components in pyvela's authoritative order (model.py:85-351)
+    comps: List[M.Component] = [M.SolarSystem(ecl, planet_shapiro=bool(cfg.get("solarwind")))]
+    if cfg.get("solarwind"):
+        comps.append(M.SolarWindDispersion())
+    comps.append(M.DispersionTaylor())
+    if cfg.get("chromgp"):
+        comps.append(M.ChromaticTaylor())
+    if binary == "ELL1":
+        comps.append(M.BinaryELL1(False))
+    elif binary == "DD":
+        comps.append(M.BinaryDD(False))
+    comps += [M.Spindown(), M.PhaseOffset(), M.MeasurementNoise(backend.astype(np.uint32), backend.astype(np.uint32))]
+    if wide:
+        ones = np.ones(n, dtype=np.uint32)
+        comps.append(M.DispersionMeasurementNoise(ones, ones))
+
+    tzr_eph = ephemeris_words(np.array([0.0]), np.random.default_rng(cfg["seed"] + 1000))[0]
+    tzr = M.make_tzr_toa((0.0, 0.0), 1400e6, M.SolarSystemEphemeris(*[tuple(tzr_eph[3 * i: 3 * i + 3]) for i in range(8)]))
+
+    def build(t_hi, t_lo, pn, kernel, dm=None):
+        rec = _records(t_hi, t_lo, err, freq, eph, (dm, dm_err) if wide else None)
+        rec[:, 4] = pn
+        model = M.TimingModel("SYNTH_" + name, "toy-circular", "none", "TDB", 0.0, tuple(comps), kernel, handler, tzr, ())
+        return model, M.TOAs(rec)
+
+    x0 = handler.read_param_values_to_vector()
+
+    # ---- phase connection: pulse numbers from the model phase, then Newton steps on the TOA
+    t_hi, t_lo = t.copy(), np.zeros(n)
+    pn = np.zeros(n)
+    for it in range(4):
+        model, toas = build(t_hi, t_lo, pn, M.WhiteNoiseKernel(), dm=np.zeros(n) if wide else None)
+        ev = make_eval(model, toas)
+        hi, lo, f = ev.phases(x0)
+        if it == 0:
+            pn = np.rint(hi)
+            hi = hi - pn
+        t_hi, t_lo = _shift(t_hi, t_lo, -(hi + lo) / f)
+    model, toas = build(t_hi, t_lo, pn, M.WhiteNoiseKernel(), dm=np.zeros(n) if wide else None)
+    ev = make_eval(model, toas)
+    hi, lo, f = ev.phases(x0)
+    connect_rms = float(np.sqrt(np.mean(((hi + lo) / f) ** 2)))
+
+    # ---- noise realisation: white + GP, added to the TOAs; wideband DMs around the model DM
+    efac_j = efac_true[backend - 1]
+    equad_j = equad_true[backend - 1]
+    noise = efac_j * np.sqrt(err**2 + equad_j**2) * rng.standard_normal(n)
+    tspan = t.max() - t.min()
+    nu_ratio2 = (1400e6 / freq) ** 2
+    blocks, gps = [], []
+    toa_rows_extra: Dict[str, np.ndarray] = {}
+    for key, cls, amp, gam, scale in (("red", M.PowerlawRedNoiseGP, -13.6, 3.8, np.ones(n)),
+                                      ("dmgp", M.PowerlawDispersionNoiseGP, -13.4, 3.2, nu_ratio2),
+                                      ("chromgp", M.PowerlawChromaticNoiseGP, -13.8, 3.5, nu_ratio2**2)):
+        nh = cfg.get(key)
+        if not nh:
+            continue
+        s, c = _fourier_basis(t, nh, tspan)
+        s, c = s * scale[:, None], c * scale[:, None]
+        wts = _powerlaw_weights(amp, gam, 1.0 / span, nh)
+        coef = rng.standard_normal(2 * nh) * np.sqrt(np.concatenate([wts, wts]))
+        noise = noise + np.concatenate([s, c], axis=1) @ coef
+        if wide:   # DM-row block: toa block x nu^2 for the DM GP, zero otherwise (model.py:556-564)
+            fac = freq[:, None] ** 2 if key == "dmgp" else 0.0
+            s, c = np.vstack([s, s * fac]), np.vstack([c, c * fac])
+            if key == "dmgp":
+                toa_rows_extra["dm_gp"] = (np.concatenate([s[n:], c[n:]], axis=1) @ coef)
+        blocks += [s, c]
+        gps.append(cls(nh, 0, 2.0))
+    t_hi, t_lo = _shift(t_hi, t_lo, noise)
+
+    dm_meas = None
+    if wide:
+        model, toas = build(t_hi, t_lo, pn, M.WhiteNoiseKernel(), dm=np.zeros(n))
+        y, _ = make_eval(model, toas).resids_and_Ninvdiag(x0)
+        model_dm = -y[n:]
+        dm_sig = 1.05 * np.sqrt(dm_err**2 + (0.5e-4 * DMCONST) ** 2)
+        dm_meas = model_dm + toa_rows_extra.get("dm_gp", 0.0) + dm_sig * rng.standard_normal(n)
+
+    if mtm:   # linearised timing parameters PHOFF, F0, F1, DM as design-matrix columns (model.py:585-619)
+        cols = [np.full(n, 1.0 / F0), -t / F0, -0.5 * t**2 / F0, 1.0 / freq**2]
+        dmrows = [np.zeros(n), np.zeros(n), np.zeros(n), np.ones(n)]
+        blocks.append(np.stack([np.concatenate([c, d]) if wide else c for c, d in zip(cols, dmrows)], axis=1))
+        gps.append(M.MarginalizedTimingModel(weights=np.full(4, 1e40), pnames=["PHOFF", "F0", "F1", "DM"]))
+
+    kernel = M.WoodburyKernel(M.WhiteNoiseKernel(), gps, np.concatenate(blocks, axis=1)) if gps else M.WhiteNoiseKernel()
+    model, toas = build(t_hi, t_lo, pn, kernel, dm=dm_meas)
+    ev = make_eval(model, toas)
+
+    # ---- walker scatter: diagonal Fisher widths from finite-difference residual derivatives
+    names = handler.get_free_param_names()
+    y0, w0 = ev.resids_and_Ninvdiag(x0)
+    sig = np.zeros(len(names))
+    noise_draw: Dict[int, tuple] = {}
+    for k, nme in enumerate(names):
+        if nme in noise_draw_names:
+            noise_draw[k] = noise_draw_names[nme]
+            continue
+        h = max(abs(x0[k]) * 1e-9, 1e-30)
+        for _ in range(6):
+            xp = x0.copy()
+            xp[k] += h
+            yk, _ = ev.resids_and_Ninvdiag(xp)
+            d = (yk - y0)
+            chi = np.sqrt(np.sum(d * d * w0))
+            if not np.isfinite(chi) or chi == 0.0:
+                h *= 100.0
+                continue
+            if 0.05 < chi < 20.0:
+                break
+            h *= 1.0 / chi
+        sig[k] = h / chi if (np.isfinite(chi) and chi > 0) else 0.0
+    info = dict(config=name, ntoa=n, wideband=wide, nfree=len(names), rank=int(kernel.noise_basis.shape[1]) if gps else 0,
+                connect_rms_s=connect_rms, free_names=names)
+    return SynthDataset(name, model, toas, x0, sig, noise_draw, info)
