@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(parts)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         if not self.rows:
@@ -129,11 +129,14 @@ def cpu_reference_arm(args, rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--walkers", type=int, default=8192, help="walkers per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="after warm-up run ONE device-resident step between cudaProfilerStart/Stop and exit "
+                         "(use with `ncu --profile-from-start off`)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -187,7 +190,12 @@ def main():
     dev_lnpr = [torch.from_numpy(lp).cuda() for lp in host_lnpr]
     d_out = torch.empty(B, dtype=torch.float64, device="cuda")
     gathered = torch.empty(B * world, dtype=torch.float64, device="cuda") if world > 1 else None
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated non-default stream: the library launches on the stream it is given, and torch's events
+    # (recorded on the current stream) must see those launches
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step_device(i):
         psr.lnpost_device(dev_sets[i % n_sets].data_ptr(), B, dev_lnpr[i % n_sets].data_ptr(), d_out.data_ptr(), stream)
@@ -204,6 +212,13 @@ def main():
     for i in range(args.warmup):
         step_device(i)
     barrier()
+    if args.profile:
+        torch.cuda.cudart().cudaProfilerStart()
+        step_device(0)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        log("profiled one step")
+        return
     psr.set_stage_timing(True)
     sampler = ClockSampler(local_rank)
     sampler.start()

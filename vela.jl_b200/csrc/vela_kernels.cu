@@ -175,15 +175,16 @@ __global__ void finish_white_kernel(const double* __restrict__ partial, int n_ti
 // K3  Sigma^-1 contraction on the FP64 tensor cores
 // ------------------------------------------------------------------------------------------
 // _calc_Ninv_M + _calc_Sigmainv__and__MT_Ninv_y (gls_likelihood.jl:101-199), restructured as one
-// GEMM over the TOA axis:   C[(p,q), b] = sum_j (M[j,p] M[j,q]) * w[b,j],   u[p, b] = sum_j M[j,p] (w y)[b,j].
+// GEMM over the TOA axis:   C[t(p,q), b] = sum_j (M[j,p] M[j,q]) * w[b,j],   u[p, b] = sum_j M[j,p] (w y)[b,j].
 //
-// The p x p matrix is cut into 8 x 8 blocks; a work "unit" is either a block pair (I, J<=I) — eight
-// m8n8k4 A-tiles, tile i = row p = 8I+i against the eight q = 8J..8J+7, formed ON THE FLY as
-// M[j,p] * M[j,q] from the shared-memory M tile — or a "u" unit (eight p-blocks of M^T against w.y).
-// A warp owns one unit x 32 walkers (4 n-tiles): 8 x 4 accumulator tiles = 64 FP64 registers, so each
-// k4 step issues 32 independent DMMAs for 13 LDS.64 + 8 DMUL.  A CTA is 8 warps = 8 consecutive
-// units over the same 32 walkers; only the column blocks those units touch are staged (cp.async,
-// kSigStages-deep ring), K-contiguous with a 20-double row pitch (conflict-free fragment reads).
+// GEMM rows are the PACKED lower triangle t = p(p+1)/2 + q (q <= p < rank): no padding of the rank and
+// no redundant upper/diagonal-block work.  Rows are cut into m8 tiles; a warp owns a "unit" of 8
+// consecutive m-tiles x 32 walkers (4 n-tiles): 8 x 4 m8n8k4 accumulators = 64 FP64 registers, so each
+// k4 step issues 32 independent DMMAs for 20 LDS.64 + 8 DMUL.  The A operand is never materialised: every
+// A element is the product of two entries of the shared-memory M tile (row gid of m-tile i <-> its (p,q)).
+// "u" units use M rows directly against the w.y product.  A CTA is 8 warps = 8 consecutive units over
+// the same 32 walkers; all `rank` columns of M plus the W and Y rows of the 32 walkers are staged with
+// cp.async in a STAGES-deep ring, K-contiguous with a (BK+4)-double row pitch (conflict-free fragment reads).
 __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
@@ -198,86 +199,58 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+template <int BK, int STAGES>
 __global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArgs a) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ int sSlotBlock[kSigMaxSlots];   // slot -> column block
-    __shared__ int sNSlots;
-    __shared__ short sBlockSlot[kSigMaxBlocks];  // column block -> slot (-1)
-
+    constexpr int PITCH = BK + 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const int unit0 = blockIdx.x * kSigWarps;
     const long b0 = (long)blockIdx.y * kSigSamples;
+    const int P = a.rank;
 
-    // ---- which column blocks does this CTA need?
-    if (tid == 0) {
-        for (int i = 0; i < a.n_blocks; ++i) sBlockSlot[i] = -1;
-        int ns = 0;
-        auto want = [&](int blk) {
-            if (sBlockSlot[blk] < 0 && ns < kSigMaxSlots) { sBlockSlot[blk] = (short)ns; sSlotBlock[ns++] = blk; }
-        };
-        for (int w = 0; w < kSigWarps; ++w) {
-            int u = unit0 + w;
-            if (u >= a.n_units) break;
-            int2 un = a.units[u];
-            if (un.x >= 0) { want(un.x); want(un.y); }
-            else if (un.x == -1) {
-                int count = min(8, a.n_blocks - un.y);
-                for (int t = 0; t < count; ++t) want(un.y + t);
-            }
-        }
-        sNSlots = ns;
-    }
-    __syncthreads();
-    const int nslots = sNSlots;
-
-    // stage layout: [nslots*8 columns of M][kSigSamples rows of W][kSigSamples rows of Y], pitch kSigPitch
-    const int stage_rows = kSigMaxSlots * 8 + 2 * kSigSamples;
-    const size_t stage_doubles = (size_t)stage_rows * kSigPitch;
-    auto stage_ptr = [&](int s) { return smem + (size_t)s * stage_doubles; };
-
-    // each row is kSigBK doubles = kSigBK/2 16-byte chunks
-    constexpr int kChunks = kSigBK / 2;
-    const int m_rows = nslots * 8;
-    const int total_chunks = (m_rows + 2 * kSigSamples) * kChunks;
+    // stage layout: [P columns of M][kSigSamples rows of W][kSigSamples rows of Y]
+    const int stage_rows = P + 2 * kSigSamples;
+    const size_t stage_doubles = (size_t)stage_rows * PITCH;
+    constexpr int kChunks = BK / 2;   // 16-byte chunks per row
+    const int total_chunks = stage_rows * kChunks;
     auto issue = [&](int kt, int s) {
-        double* base = stage_ptr(s);
-        const long j0 = (long)kt * kSigBK;
+        double* base = smem + (size_t)s * stage_doubles;
+        const long j0 = (long)kt * BK;
         for (int c = tid; c < total_chunks; c += kSigThreads) {
             int r = c / kChunks, ch = c - r * kChunks;
             const double* src;
-            double* dst;
-            if (r < m_rows) {
-                int col = sSlotBlock[r >> 3] * 8 + (r & 7);
-                src = a.M + (size_t)col * a.ldM + j0 + ch * 2;
-                dst = base + (size_t)r * kSigPitch + ch * 2;
-            } else if (r < m_rows + kSigSamples) {
-                int n = r - m_rows;
-                src = a.W + (size_t)(b0 + n) * a.ld_yw + j0 + ch * 2;
-                dst = base + (size_t)(kSigMaxSlots * 8 + n) * kSigPitch + ch * 2;
-            } else {
-                int n = r - m_rows - kSigSamples;
-                src = a.Y + (size_t)(b0 + n) * a.ld_yw + j0 + ch * 2;
-                dst = base + (size_t)(kSigMaxSlots * 8 + kSigSamples + n) * kSigPitch + ch * 2;
-            }
-            cp_async16(dst, src);
+            if (r < P) src = a.M + (size_t)r * a.ldM + j0 + ch * 2;
+            else if (r < P + kSigSamples) src = a.W + (size_t)(b0 + (r - P)) * a.ld_yw + j0 + ch * 2;
+            else src = a.Y + (size_t)(b0 + (r - P - kSigSamples)) * a.ld_yw + j0 + ch * 2;
+            cp_async16(base + (size_t)r * PITCH + ch * 2, src);
         }
     };
 
-    const int n_ktiles = (int)(a.n_rows_pad / kSigBK);
-    // ---- this warp's unit
-    const int u = unit0 + warp;
-    int2 un = (u < a.n_units) ? a.units[u] : make_int2(-2, 0);
-    const bool have_unit = un.x >= -1;
-    const bool is_pair = un.x >= 0;
-    int slotI = 0, slotJ = 0, u_first = 0, u_count = 0;
-    if (have_unit) {
-        if (is_pair) { slotI = sBlockSlot[un.x]; slotJ = sBlockSlot[un.y]; }
-        else { u_first = un.y; u_count = min(8, a.n_blocks - u_first); }
-    }
-    int uslot[8];
+    // ---- this warp's unit: 8 m-tiles; row gid of m-tile i is packed pair t -> (p, q), or M row p for u units
+    const int u = blockIdx.x * kSigWarps + warp;
+    const bool have_unit = u < a.n_units;
+    const bool is_pair = u < a.n_pair_units;
+    const int tile0 = is_pair ? u * 8 : (u - a.n_pair_units) * 8;
+    int offp[8], offq[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) uslot[i] = (!is_pair && i < u_count) ? sBlockSlot[u_first + i] : 0;
+    for (int i = 0; i < 8; ++i) {
+        int p = 0, q = 0;
+        if (have_unit) {
+            long t = (long)(tile0 + i) * 8 + gid;
+            if (is_pair) {
+                if (t < a.n_pairs) {
+                    p = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+                    while ((long)(p + 1) * (p + 2) / 2 <= t) ++p;
+                    while ((long)p * (p + 1) / 2 > t) --p;
+                    q = (int)(t - (long)p * (p + 1) / 2);
+                }
+            } else if (t < P) {
+                p = (int)t;
+            }
+        }
+        offp[i] = p * PITCH;
+        offq[i] = q * PITCH;
+    }
 
     double acc[8][4][2];
 #pragma unroll
@@ -285,49 +258,46 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArg
 #pragma unroll
         for (int n = 0; n < 4; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
 
-    // ---- prologue of the ring
+    const int n_ktiles = (int)(a.n_rows_pad / BK);
 #pragma unroll
-    for (int s = 0; s < kSigStages - 1; ++s) {
+    for (int s = 0; s < STAGES - 1; ++s) {
         if (s < n_ktiles) issue(s, s);
         cp_async_commit();
     }
 
     for (int kt = 0; kt < n_ktiles; ++kt) {
-        cp_async_wait<kSigStages - 2>();
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
         {   // refill the slot freed by the previous iteration
-            int nk = kt + kSigStages - 1;
-            if (nk < n_ktiles) issue(nk, nk % kSigStages);
+            int nk = kt + STAGES - 1;
+            if (nk < n_ktiles) issue(nk, nk % STAGES);
             cp_async_commit();
         }
         if (have_unit) {
-            const double* sM = stage_ptr(kt % kSigStages);
-            const double* sW = sM + (size_t)kSigMaxSlots * 8 * kSigPitch;
-            const double* sY = sW + (size_t)kSigSamples * kSigPitch;
+            const double* sM = smem + (size_t)(kt % STAGES) * stage_doubles;
+            const double* sW = sM + (size_t)P * PITCH;
+            const double* sY = sW + (size_t)kSigSamples * PITCH;
 #pragma unroll
-            for (int kk = 0; kk < kSigBK / 4; ++kk) {
+            for (int kk = 0; kk < BK / 4; ++kk) {
                 const int k = kk * 4 + tig;
                 double bw[4];
 #pragma unroll
-                for (int n = 0; n < 4; ++n) bw[n] = sW[(size_t)(n * 8 + gid) * kSigPitch + k];
+                for (int n = 0; n < 4; ++n) bw[n] = sW[(n * 8 + gid) * PITCH + k];
                 if (is_pair) {
-                    const double qf = sM[(size_t)(slotJ * 8 + gid) * kSigPitch + k];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const double af = sM[(size_t)(slotI * 8 + i) * kSigPitch + k] * qf;
+                        const double af = sM[offp[i] + k] * sM[offq[i] + k];
 #pragma unroll
                         for (int n = 0; n < 4; ++n) dmma8x8x4(acc[i][n][0], acc[i][n][1], af, bw[n]);
                     }
                 } else {
 #pragma unroll
-                    for (int n = 0; n < 4; ++n) bw[n] *= sY[(size_t)(n * 8 + gid) * kSigPitch + k];
+                    for (int n = 0; n < 4; ++n) bw[n] *= sY[(n * 8 + gid) * PITCH + k];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        if (i < u_count) {
-                            const double af = sM[(size_t)(uslot[i] * 8 + gid) * kSigPitch + k];
+                        const double af = sM[offp[i] + k];
 #pragma unroll
-                            for (int n = 0; n < 4; ++n) dmma8x8x4(acc[i][n][0], acc[i][n][1], af, bw[n]);
-                        }
+                        for (int n = 0; n < 4; ++n) dmma8x8x4(acc[i][n][0], acc[i][n][1], af, bw[n]);
                     }
                 }
             }
@@ -337,35 +307,29 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArg
 
     // ---- epilogue: accumulator (row = gid, col = 2*tig + {0,1}) of tile (i, n)
     if (!have_unit) return;
-    const int pp = a.n_blocks * 8;
-    if (is_pair) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int prow = un.x * 8 + i, q = un.y * 8 + gid;
+    for (int i = 0; i < 8; ++i) {
+        const long t = (long)(tile0 + i) * 8 + gid;
+        const bool ok = is_pair ? (t < a.n_pairs) : (t < P);
+        if (!ok) continue;
 #pragma unroll
-            for (int n = 0; n < 4; ++n)
+        for (int n = 0; n < 4; ++n)
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    long b = b0 + n * 8 + 2 * tig + r;
-                    if (b < a.B) a.Sig[(size_t)b * pp * pp + (size_t)prow * pp + q] = acc[i][n][r];
+            for (int r = 0; r < 2; ++r) {
+                long b = b0 + n * 8 + 2 * tig + r;
+                if (b < a.B) {
+                    if (is_pair) a.Sig[(size_t)b * a.ld_sig + t] = acc[i][n][r];
+                    else a.U[(size_t)b * a.ld_u + t] = acc[i][n][r];
                 }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (i < u_count) {
-                const int prow = (u_first + i) * 8 + gid;
-#pragma unroll
-                for (int n = 0; n < 4; ++n)
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        long b = b0 + n * 8 + 2 * tig + r;
-                        if (b < a.B) a.U[(size_t)b * pp + prow] = acc[i][n][r];
-                    }
             }
-        }
     }
 }
+
+template __global__ void sigma_contract_kernel<32, 4>(SigmaArgs);
+template __global__ void sigma_contract_kernel<16, 4>(SigmaArgs);
+template __global__ void sigma_contract_kernel<16, 3>(SigmaArgs);
+template __global__ void sigma_contract_kernel<16, 2>(SigmaArgs);
+template __global__ void sigma_contract_kernel<8, 2>(SigmaArgs);
 
 // ------------------------------------------------------------------------------------------
 // K4  + Phi^-1, Cholesky, log-det, solve, ln L
@@ -398,17 +362,22 @@ __global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
     double* z = phi + pp;          // [pp]
     double* A;                     // lower triangle, row pitch lda
     int lda;
-    double* gA = a.Sig + (size_t)b * pp * pp;
+    double* gA = a.Sig + (size_t)b * a.ld_sig;   // packed lower triangle t = r(r+1)/2 + c
     if (a.use_smem) {
         lda = pp + 1;
         A = z + pp;
-        for (int i = tid; i < p * pp; i += nt) {
-            int r = i / pp, c = i - r * pp;
-            if (c <= r) A[r * lda + c] = gA[(size_t)r * pp + c];
+        for (int r = 0; r < p; ++r) {
+            const double* src = gA + (size_t)r * (r + 1) / 2;
+            for (int c = tid; c <= r; c += nt) A[r * lda + c] = src[c];
         }
     } else {
+        // large rank: unpack into the square scratch of this walker and factorise there (L2-resident)
         lda = pp;
-        A = gA;
+        A = a.Sq + (size_t)b * pp * pp;
+        for (int r = 0; r < p; ++r) {
+            const double* src = gA + (size_t)r * (r + 1) / 2;
+            for (int c = tid; c <= r; c += nt) A[r * lda + c] = src[c];
+        }
     }
     if (tid == 0) sFail = 0;
 
@@ -431,7 +400,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
             }
         }
     }
-    for (int i = tid; i < p; i += nt) z[i] = a.U[(size_t)b * pp + i];
+    for (int i = tid; i < p; i += nt) z[i] = a.U[(size_t)b * a.ld_u + i];
     __syncthreads();
     double lphi = 0.0;
     for (int i = tid; i < p; i += nt) {

@@ -10,11 +10,7 @@ constexpr int kChainThreads = 256;  // max threads per block of the chain kernel
 constexpr int kSigThreads = 256;
 constexpr int kSigWarps = 8;        // units per CTA
 constexpr int kSigSamples = 32;     // walkers per CTA (4 n-tiles of 8)
-constexpr int kSigBK = 16;          // TOA rows per pipeline stage
-constexpr int kSigPitch = 20;       // shared-memory row pitch in doubles (conflict-free fragment reads)
-constexpr int kSigStages = 4;
-constexpr int kSigMaxSlots = 16;    // distinct 8-column blocks a CTA can stage
-constexpr int kSigMaxBlocks = 128;  // p <= 1024
+constexpr int kSigMaxRank = 1024;
 
 constexpr int kCholThreads = 256;
 
@@ -39,16 +35,19 @@ struct ChainArgs {
 struct SigmaArgs {
     const double* M;           // column-major, leading dimension ldM (rows zero-padded to n_rows_pad)
     long ldM;
-    int n_blocks;              // ceil(p / 8)
+    int rank;                  // p
+    long n_pairs;              // p (p + 1) / 2 packed lower-triangle rows
+    int n_pair_units;          // units of 8 m-tiles covering the pairs
+    int n_units;               // pair units + u units
     long n_rows_pad;
     const double* W;
     const double* Y;
     long ld_yw;
     long B;
-    const int2* units;         // (I, J) block pair, (-1, first block) u unit, (-2, *) padding
-    int n_units;
-    double* Sig;               // [B][pp][pp], row p / col q, lower block triangle written
-    double* U;                 // [B][pp]
+    double* Sig;               // [B][ld_sig], packed lower triangle t = p(p+1)/2 + q
+    long ld_sig;
+    double* U;                 // [B][ld_u]
+    long ld_u;
 };
 
 struct GPDev {
@@ -58,7 +57,10 @@ struct GPDev {
 };
 
 struct CholArgs {
-    double* Sig;
+    double* Sig;               // packed lower triangle per walker
+    long ld_sig;
+    long ld_u;
+    double* Sq;                // [B][pp][pp] square scratch, only when the matrix does not fit shared memory
     const double* U;
     const double* Pext;
     int row;
@@ -82,6 +84,7 @@ __global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, 
 __global__ void toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a);
 __global__ void finish_white_kernel(const double* partial, int n_tiles, long B, int mode, const double* lnprior,
                                     int with_prior, double* out);
+template <int BK, int STAGES>
 __global__ void sigma_contract_kernel(SigmaArgs a);
 __global__ void chol_finish_kernel(CholArgs a);
 __global__ void phiinv_kernel(CholArgs a, double* out);
@@ -89,8 +92,8 @@ __global__ void sincos_cr_kernel(const double* x, int n, double* s, double* c);
 __global__ void dfma_peak_kernel(double* out, int iters);
 __global__ void dmma_peak_kernel(double* out, int iters);
 
-inline size_t sigma_smem_bytes() {
-    return (size_t)kSigStages * (kSigMaxSlots * 8 + 2 * kSigSamples) * kSigPitch * sizeof(double);
+inline size_t sigma_smem_bytes(int rank, int bk, int stages) {
+    return (size_t)stages * (rank + 2 * kSigSamples) * (bk + 4) * sizeof(double);
 }
 
 }  // namespace vela
