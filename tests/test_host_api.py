@@ -1,0 +1,153 @@
+"""Host-side logic and the C-ABI surface (`-m "not gpu"`: no compute calls, no GPU needed)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+
+
+def test_library_loads_and_exports_every_declared_symbol(vb):
+    hdr = open(os.path.join(ROOT, "include", "vela_b200.h")).read()
+    declared = sorted(set(re.findall(r"VELA_API[^;(]*?\b(vela_b200_\w+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(vb.lib.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/vela_b200.h but not exported"
+    assert sorted(vb.lib.EXPORTS) == declared
+
+
+def test_no_cpu_fallback_fails_loudly(vb, golden):
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    g = golden("NGC6440E")
+    with pytest.raises(vb.VelaB200Error, match="no CPU fallback"):
+        vb.Pulsar(g.model, g.toas)
+    h = ctypes.c_void_p()
+    rc = vb.lib.lib().vela_b200_create(g.md.byref(), ctypes.byref(h))
+    assert rc == -2 and b"no CPU path" in vb.lib.lib().vela_b200_last_error()      # VELA_ERR_NO_DEVICE
+
+
+def test_create_rejects_bad_descriptors(vb, golden):
+    g = golden("NGC6440E")
+    L = vb.lib.lib()
+    h = ctypes.c_void_p()
+    md = vb.ModelDescriptor(g.model, g.toas)
+    md.desc.abi_version = 99
+    assert L.vela_b200_create(md.byref(), ctypes.byref(h)) == -1
+    assert b"ABI version" in L.vela_b200_last_error()
+    md = vb.ModelDescriptor(g.model, g.toas)
+    md.desc.toa_stride_bytes = 100
+    assert L.vela_b200_create(md.byref(), ctypes.byref(h)) == -1
+    md = vb.ModelDescriptor(g.model, g.toas)
+    md._tzr[30:31].view(np.uint64)[0] = 7        # not a TZR TOA (timing_model.jl:37)
+    assert L.vela_b200_create(md.byref(), ctypes.byref(h)) == -1
+    assert L.vela_b200_create(None, ctypes.byref(h)) == -1
+
+
+def test_param_handler_ordering(vb):
+    """parameter.jl:87-119: non-noise singles, non-noise multis, noise singles, noise multis."""
+    M = vb.model
+    P = M.Parameter
+    ph = M.ParamHandler(
+        [P("A", 1.0, 0, True), P("NZ", 9.0, 0, False, noise=True), P("B", 2.0, 0, False)],
+        [M.MultiParameter("E", [P("E1", 7.0, 0, False, noise=True), P("E2", 8.0, 0, True, noise=True)]),
+         M.MultiParameter("F", [P("F0", 3.0, 0, False), P("F1", 4.0, 0, True)])])
+    np.testing.assert_array_equal(ph._default_values, [1.0, 2.0, 3.0, 4.0, 9.0, 7.0, 8.0])
+    np.testing.assert_array_equal(ph._free_indices, [2, 3, 5, 6])            # 1-based, as in Julia
+    assert ph.get_free_param_names() == ["B", "F0", "NZ", "E1"]
+    assert ph.get_free_param_prefixes() == ["B", "F", "NZ", "E"]
+    assert ph.get_num_timing_params() == 2
+    full = ph.read_params([20.0, 30.0, 90.0, 70.0])
+    np.testing.assert_array_equal(full, [1.0, 20.0, 30.0, 4.0, 90.0, 70.0, 8.0])
+    np.testing.assert_array_equal(ph.read_param_values_to_vector(full), [20.0, 30.0, 90.0, 70.0])
+    with pytest.raises(AssertionError):
+        ph.read_params([1.0])                                                 # parameter.jl:162
+
+
+def test_fixture_param_handler_matches_reference(golden):
+    """_default_values of NGC6440E as decoded from the reference file."""
+    g = golden("NGC6440E")
+    ph = g.model.param_handler
+    assert len(ph._default_values) == 16 and ph._nfree == 8
+    np.testing.assert_array_equal(ph._free_indices, [3, 4, 7, 10, 12, 13, 15, 16])
+    assert ph.offset("F_") == 8 and ph.offset("DM") == 9 and ph.offset("F") == 11
+    assert ph.offset("EFAC") == 14 and ph.offset("EQUAD") == 15
+
+
+def test_descriptor_offsets(vb, golden):
+    g = golden("sim_sw_wb")
+    d = g.md.desc
+    assert d.n_components == 7 and d.wideband == 1 and d.toa_stride_bytes == 264 and d.n_toas == 500
+    kinds = [d.components[i].kind for i in range(d.n_components)]
+    D = vb.descriptor
+    assert kinds == [D.COMP_SOLAR_SYSTEM, D.COMP_SOLAR_WIND, D.COMP_DISPERSION_TAYLOR, D.COMP_DM_JUMP_EXCLUSIVE,
+                     D.COMP_SPINDOWN, D.COMP_PHASE_OFFSET, D.COMP_DM_MEASUREMENT_NOISE]
+    ss = d.components[0]
+    assert ss.flags == (D.FLAG_ECLIPTIC | D.FLAG_PLANET_SHAPIRO)
+    ph = g.model.param_handler
+    assert [ss.par[i] for i in range(6)] == [ph.offset(n) for n in ("ELONG", "ELAT", "PMELONG", "PMELAT", "PX", "POSEPOCH")]
+    sp = d.components[4]
+    assert sp.par[0] == ph.offset("F_") and sp.par[1] == ph.offset("F") and sp.len[0] == 3
+    assert d.n_index_masks == 3
+    g3 = golden("sim3_gp").md.desc
+    assert g3.kernel_kind == D.KERNEL_WOODBURY_WHITE and g3.n_gp == 3 and g3.basis_cols == 180 and g3.basis_rows == 2000
+    assert [g3.gp[i].kind for i in range(3)] == [D.GP_POWERLAW_RED, D.GP_POWERLAW_DM, D.GP_POWERLAW_CHROM]
+
+
+def test_ecorr_kernel_is_rejected_not_silently_ignored(vb, golden):
+    g = golden("NGC6440E")
+    M = vb.model
+    m2 = M.TimingModel(g.model.pulsar_name, g.model.ephem, g.model.clock, g.model.units, g.model.epoch,
+                       g.model.components, M.EcorrKernel(np.zeros((0, 3), dtype=np.uint64)), g.model.param_handler,
+                       g.model.tzr_toa, g.model.priors)
+    with pytest.raises(NotImplementedError, match="ECORR"):
+        vb.ModelDescriptor(m2, g.toas)
+
+
+def test_priors_host_side(vb, golden):
+    g = golden("NGC6440E")
+    pri = vb.priors
+    assert np.isfinite(pri.lnprior(g.model.priors, g.x0))                       # test_NGC6440E.jl:172
+    x = g.x0.copy()
+    x[0] += 1.0                                                                # outside the RAJ box
+    assert pri.lnprior(g.model.priors, x) == -np.inf
+    batch = np.stack([g.x0, x])
+    np.testing.assert_array_equal(np.isfinite(pri.lnprior(g.model.priors, batch)), [True, False])
+    cube = pri.prior_transform(g.model.priors, np.full(len(g.x0), 0.5))
+    assert np.all(np.isfinite(cube)) and np.isfinite(pri.lnprior(g.model.priors, cube))   # :177-179,198
+    # quantile/logpdf consistency of the default families and the custom ones (known_priors.jl)
+    from scipy import integrate
+    for d in (pri.Uniform(-1, 3), pri.Normal(0.5, 2.0), pri.LogNormal(0.0, 0.25), pri.LogUniform(1e-3, 10.0),
+              pri.KINPriorDistribution(), pri.SINIPriorDistribution(),
+              pri.LatitudePriorDistribution(), pri.PXPriorDistribution(2.0)):
+        lo, hi = float(d.quantile(0.1)), float(d.quantile(0.7))
+        mass, _ = integrate.quad(lambda t: float(np.exp(d.logpdf(t))), lo, hi)
+        assert mass == pytest.approx(0.6, abs=1e-6), type(d).__name__
+    # STIGMA: the mirror keeps the reference's quantile q/(2-q) verbatim (known_priors.jl:61) although it is not the
+    # inverse of its cdf 2s^2/(1+s^2) (:60) — drop-in behaviour over self-consistency
+    assert float(pri.STIGMAPriorDistribution().quantile(0.5)) == pytest.approx(0.5 / 1.5)
+    assert float(np.exp(pri.STIGMAPriorDistribution().logpdf(0.5))) == pytest.approx(4 * 0.5 / 1.25**2)
+
+
+def test_npz_round_trip(vb, golden, tmp_path):
+    g = golden("sim_dmgp_wb")
+    path = str(tmp_path / "x.npz")
+    vb.readwrite.save_pulsar_npz(path, g.model, g.toas)
+    m2, t2, _ = vb.readwrite.load_pulsar_npz(path)
+    np.testing.assert_array_equal(t2.records, g.toas.records)
+    np.testing.assert_array_equal(m2.param_handler._default_values, g.model.param_handler._default_values)
+    np.testing.assert_array_equal(np.asarray(m2.kernel.noise_basis), np.asarray(g.model.kernel.noise_basis))
+    assert [type(c).__name__ for c in m2.components] == [type(c).__name__ for c in g.model.components]
+    assert m2.get_marginalized_param_names()[:2] == ["PLREDSIN_0001", "PLREDSIN_0002"]   # gp_noise.jl:87-97
+
+
+def test_shard_range(vb):
+    sr = vb.parallel.shard_range
+    for n in (0, 1, 7, 8192, 8193):
+        for world in (1, 2, 3, 8):
+            blocks = [sr(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))

@@ -4,7 +4,7 @@ The directory name contains a dot, so it is loaded under the module name `vela_j
 (see `__graft_entry__.load_package()`).
 """
 
-from . import model, priors, readwrite, descriptor, jlso, lib, api, synth  # noqa: F401
+from . import model, priors, readwrite, descriptor, jlso, lib, api, synth, parallel  # noqa: F401
 from .model import *  # noqa: F401,F403
 from .readwrite import load_pulsar_data  # noqa: F401
 from .descriptor import ModelDescriptor  # noqa: F401

@@ -137,6 +137,13 @@ CONFIGS = {
                           ecliptic=True, mtm=True, nback=1, walkers=8192, seed=4),
     # configs[4]: "100k TOAs, red+DM+chromatic GP (rank ~300), 65536 walkers sharded over 8 GPUs"
     "config5_array": dict(ntoa=100000, span_d=6000.0, red=50, dmgp=50, chromgp=50, nback=8, walkers=65536, seed=5),
+    # component-coverage cases for the parity tests (not benchmark lines)
+    "extra_ell1_fbx": dict(ntoa=1500, span_d=3000.0, binary="ELL1", fbx=True, glitch=2, expdip=2, dmx=6, cmx=4,
+                           jump="exclusive", nback=3, walkers=256, seed=11),
+    "extra_dd_fbx_wb": dict(ntoa=1200, span_d=3000.0, binary="DD", fbx=True, wideband=True, dmjump="exclusive",
+                            jump="bits", solarwind=True, ecliptic=True, glitch=1, nback=2, walkers=256, seed=12),
+    "extra_dmjump_bits_wb": dict(ntoa=800, span_d=2000.0, wideband=True, dmjump="bits", ecliptic=False, nback=2,
+                                 red=10, walkers=128, seed=13),
 }
 
 
@@ -202,8 +209,9 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
     binary = cfg.get("binary")
     if binary == "ELL1":
         sp("TASC", 0.3 * DAY, free=True, dim=1)
-        sp("PB", 4.0742 * DAY, free=True, dim=1)
-        sp("PBDOT", 0.0)
+        if not cfg.get("fbx"):
+            sp("PB", 4.0742 * DAY, free=True, dim=1)
+            sp("PBDOT", 0.0)
         sp("A1", 3.3667, free=True, dim=1)
         sp("A1DOT", 0.0)
         sp("EPS1", 1.2e-5, free=True)
@@ -214,8 +222,9 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         sp("SINI", 0.95, free=True)
     elif binary == "DD":
         sp("T0", 1.7 * DAY, free=True, dim=1)
-        sp("PB", 25.3 * DAY, free=True, dim=1)
-        sp("PBDOT", 0.0)
+        if not cfg.get("fbx"):
+            sp("PB", 25.3 * DAY, free=True, dim=1)
+            sp("PBDOT", 0.0)
         sp("A1", 21.3, free=True, dim=1)
         sp("A1DOT", 0.0)
         sp("ECC", 0.1072, free=True)
@@ -238,6 +247,40 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
     mp("DM", [dm0, 1e-4 * DMCONST / YEAR], [not mtm, True], dim=-1, prefix="DM", sig=[0.0, 0.0])
     if cfg.get("chromgp"):
         mp("CM", [0.0], [False], dim=-1, prefix="CM")
+    if cfg.get("fbx"):
+        pb = (4.0742 if binary == "ELL1" else 25.3) * DAY
+        mp("FB", [1.0 / pb, -2.0e-20], [True, True], dim=-1, prefix="FB", sig=[0.0, 0.0])
+    ng = cfg.get("glitch", 0)
+    if ng:
+        gl_ep = np.linspace(-0.3, 0.25, ng) * span
+        mp("GLEP_", gl_ep, [False] * ng, dim=1, prefix="GLEP_")
+        mp("GLPH_", 0.1 + 0.05 * np.arange(ng), [True] * ng, prefix="GLPH_", sig=[0.0] * ng)
+        mp("GLF0_", 2e-8 * (1 + np.arange(ng)), [True] * ng, dim=-1, prefix="GLF0_", sig=[0.0] * ng)
+        mp("GLF1_", -1e-16 * np.ones(ng), [True] * ng, dim=-2, prefix="GLF1_", sig=[0.0] * ng)
+        mp("GLF2_", np.zeros(ng), [False] * ng, dim=-3, prefix="GLF2_")
+        mp("GLF0D_", 1e-8 * np.ones(ng), [True] * ng, dim=-1, prefix="GLF0D_", sig=[0.0] * ng)
+        mp("GLTD_", 50.0 * DAY * np.ones(ng), [False] * ng, dim=1, prefix="GLTD_")
+    ne = cfg.get("expdip", 0)
+    if ne:
+        sp("EXPDIPFREF", 1.4e9, dim=-1)
+        sp("EXPDIPEPS", 0.1 * DAY, dim=1)
+        mp("EXPDIPEP_", np.linspace(-0.2, 0.3, ne) * span, [False] * ne, dim=1, prefix="EXPDIPEP_")
+        mp("EXPDIPAMP_", 2e-6 * np.ones(ne), [True] * ne, dim=1, prefix="EXPDIPAMP_", sig=[0.0] * ne)
+        mp("EXPDIPIDX_", -2.0 * np.ones(ne), [True] * ne, prefix="EXPDIPIDX_", sig=[0.0] * ne)
+        mp("EXPDIPTAU_", 30.0 * DAY * np.ones(ne), [True] * ne, dim=1, prefix="EXPDIPTAU_", sig=[0.0] * ne)
+    ndmx = cfg.get("dmx", 0)
+    if ndmx:
+        mp("DMX_", 1e-3 * DMCONST * rng.standard_normal(ndmx), [True] * ndmx, dim=-1, prefix="DMX_", sig=[0.0] * ndmx)
+    ncmx = cfg.get("cmx", 0)
+    if ncmx:
+        if not cfg.get("chromgp"):
+            sp("TNCHROMIDX", 4.0)
+        mp("CMX_", 1e-3 * DMCONST * rng.standard_normal(ncmx), [True] * ncmx, dim=-1, prefix="CMX_", sig=[0.0] * ncmx)
+    njump = 2 if cfg.get("jump") else 0
+    if njump:
+        mp("JUMP", [3e-6, -2e-6], [True, True], dim=1, prefix="JUMP", sig=[0.0, 0.0])
+    if cfg.get("dmjump"):
+        mp("DMJUMP", [2e-4 * DMCONST, -1e-4 * DMCONST], [True, True], dim=-1, prefix="DMJUMP", sig=[0.0, 0.0])
     mp("F", [0.0, -1.0e-15], [not mtm, not mtm], dim=-1, prefix="F", sig=[0.0, 0.0])
     # noise parameters
     for key, amp, gam in (("RED", -13.6, 3.8), ("DM", -13.4, 3.2), ("CHROM", -13.8, 3.5)):
@@ -266,13 +309,32 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
     if cfg.get("solarwind"):
         comps.append(M.SolarWindDispersion())
     comps.append(M.DispersionTaylor())
+    seg = lambda k: (np.minimum((np.arange(n) * (k + 1)) // n, k)).astype(np.uint32)   # 0 = none, 1..k  # noqa: E731
+    if ndmx:
+        comps.append(M.DispersionPiecewise(seg(ndmx)))
+    if cfg.get("dmjump") == "exclusive":
+        comps.append(M.ExclusiveDispersionJump(((np.arange(n) // 5) % 3).astype(np.uint32)))
+    elif cfg.get("dmjump") == "bits":
+        comps.append(M.DispersionJump(np.stack([(np.arange(n) % 3) == 0, (np.arange(n) % 4) == 1])))
     if cfg.get("chromgp"):
         comps.append(M.ChromaticTaylor())
+    if ncmx:
+        comps.append(M.ChromaticPiecewise(seg(ncmx)[::-1].copy()))
     if binary == "ELL1":
-        comps.append(M.BinaryELL1(False))
+        comps.append(M.BinaryELL1(bool(cfg.get("fbx"))))
     elif binary == "DD":
-        comps.append(M.BinaryDD(False))
-    comps += [M.Spindown(), M.PhaseOffset(), M.MeasurementNoise(backend.astype(np.uint32), backend.astype(np.uint32))]
+        comps.append(M.BinaryDD(bool(cfg.get("fbx"))))
+    if ne:
+        comps.append(M.ChromaticExponentialDip())
+    comps.append(M.Spindown())
+    if ng:
+        comps.append(M.Glitch())
+    comps.append(M.PhaseOffset())
+    if cfg.get("jump") == "exclusive":
+        comps.append(M.ExclusivePhaseJump(((np.arange(n) // 3) % 3).astype(np.uint32)))
+    elif cfg.get("jump") == "bits":
+        comps.append(M.PhaseJump(np.stack([(np.arange(n) % 5) < 2, (np.arange(n) % 7) == 3])))
+    comps.append(M.MeasurementNoise(backend.astype(np.uint32), backend.astype(np.uint32)))
     if wide:
         ones = np.ones(n, dtype=np.uint32)
         comps.append(M.DispersionMeasurementNoise(ones, ones))
