@@ -1,0 +1,28 @@
+"""Full BASELINE.json sizes on the GPU: size-independent properties + an oracle check on a walker subset."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,nsub", [("config2_ell1", 64), ("config3_gp", 64), ("config4_dd_wb", 32)])
+def test_full_size_config(name, nsub, vb, oracle):
+    cfg = vb.synth.CONFIGS[name]
+    ds = vb.synth.make_dataset(name, lambda m, t: vb.Pulsar(m, t))
+    assert len(ds.toas) == cfg["ntoa"]
+    psr = vb.Pulsar(ds.model, ds.toas)
+    B = cfg["walkers"]
+    W = ds.walkers(B, seed=5)
+    out = psr.lnlike_vectorized(W)
+    assert out.shape == (B,) and np.all(np.isfinite(out))
+    # property: any sub-batch reproduces the same numbers bit for bit (row independence, determinism)
+    idx = np.random.default_rng(1).choice(B, size=100, replace=False)
+    np.testing.assert_array_equal(psr.lnlike_vectorized(W[idx]), out[idx])
+    # property: lnpost = lnprior + lnlike with a flat prior
+    np.testing.assert_array_equal(psr._batch(psr._lib.vela_b200_lnpost_batch, W[:256], None), out[:256])
+    # oracle on a subset
+    md = vb.ModelDescriptor(ds.model, ds.toas)
+    np.testing.assert_allclose(out[:nsub], oracle.lnlike_batch(md, W[:nsub]), rtol=1e-9)
+    y, _ = psr.resids_and_Ninvdiag(ds.truth)
+    yo, _ = oracle.residuals(md, ds.truth)
+    assert np.max(np.abs(y - yo)[: len(ds.toas)]) < 1e-9

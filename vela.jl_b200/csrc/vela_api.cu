@@ -163,13 +163,18 @@ void launch_sigma(VelaPulsar* h, const SigmaArgs& sa, long B, cudaStream_t st) {
     else sigma_contract_kernel<8, 2><<<grid, kSigThreads, sm, st>>>(sa);
 }
 
-int set_sigma_smem_attr(VelaPulsar* h) {
-    const int sm = (int)h->sig_smem;
-    if (h->sig_bk == 32) CU(cudaFuncSetAttribute(sigma_contract_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    else if (h->sig_bk == 16 && h->sig_stages == 4) CU(cudaFuncSetAttribute(sigma_contract_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    else if (h->sig_bk == 16 && h->sig_stages == 3) CU(cudaFuncSetAttribute(sigma_contract_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    else if (h->sig_bk == 16) CU(cudaFuncSetAttribute(sigma_contract_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    else CU(cudaFuncSetAttribute(sigma_contract_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+// Dynamic shared-memory ceilings are per FUNCTION, not per handle: raise every kernel to the device opt-in
+// maximum once, so handles with different ranks cannot shrink each other's limit.
+int set_smem_attrs(int dev) {
+    int max_optin = 0;
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CU(cudaFuncSetAttribute(sigma_contract_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(sigma_contract_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(sigma_contract_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(sigma_contract_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(sigma_contract_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(chol_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
+    CU(cudaFuncSetAttribute(toa_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     return 0;
 }
 
@@ -240,13 +245,8 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
         if (upload(&d.M, Mp.data(), Mp.size())) return VELA_ERR_CUDA;
         if (upload(&d.gp, gps.data(), gps.size())) return VELA_ERR_CUDA;
         if (upload(&d.gp_data, gp_data.data(), gp_data.size())) return VELA_ERR_CUDA;
-        if (set_sigma_smem_attr(h)) return VELA_ERR_CUDA;
-        if (h->chol_smem_bytes > 48 * 1024)
-            CU(cudaFuncSetAttribute(chol_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->chol_smem_bytes));
     }
-    size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
-    if (chain_smem > 48 * 1024)
-        CU(cudaFuncSetAttribute(toa_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem));
+    if (set_smem_attrs(d.dev)) return VELA_ERR_CUDA;
     return 0;
 }
 
@@ -603,7 +603,9 @@ static int run_single(VelaHandle h, const double* params, int64_t n_free, int mo
     if (o0) cudaMemcpyAsync(o0, dY, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
     if (o1) cudaMemcpyAsync(o1, dW, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
     if (o2) cudaMemcpyAsync(o2, dF, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
-    cudaError_t e = cudaStreamSynchronize(d.stream);
+    cudaError_t e = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(d.stream);
+    if (e == cudaSuccess) e = e2;
     cudaFree(dY); cudaFree(dW); cudaFree(dF);
     cudaSetDevice(prev);
     if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "single-sample run: %s", cudaGetErrorString(e));
@@ -644,7 +646,9 @@ VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int
     phiinv_kernel<<<1, 128, 0, d.stream>>>(ch, dphi);
     h->launches += 2;
     cudaMemcpyAsync(phiinv, dphi, sizeof(double) * h->p, cudaMemcpyDeviceToHost, d.stream);
-    cudaError_t e = cudaStreamSynchronize(d.stream);
+    cudaError_t e = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(d.stream);
+    if (e == cudaSuccess) e = e2;
     cudaFree(dphi);
     cudaSetDevice(prev);
     if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "noise_weights_inv: %s", cudaGetErrorString(e));
@@ -683,7 +687,9 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     std::vector<double> S((size_t)h->ld_sig), U(h->pp);
     cudaMemcpyAsync(S.data(), b.Sig, sizeof(double) * S.size(), cudaMemcpyDeviceToHost, d.stream);
     cudaMemcpyAsync(U.data(), b.U, sizeof(double) * U.size(), cudaMemcpyDeviceToHost, d.stream);
-    cudaError_t e = cudaStreamSynchronize(d.stream);
+    cudaError_t e = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(d.stream);
+    if (e == cudaSuccess) e = e2;
     cudaSetDevice(prev);
     if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "sigma_and_u: %s", cudaGetErrorString(e));
     const int p = h->p;

@@ -440,7 +440,7 @@ class WoodburyKernel(Kernel):
 # ---------------------------------------------------------------------------------------------
 # TimingModel
 # ---------------------------------------------------------------------------------------------
-@dataclass
+@dataclass(eq=False)
 class TimingModel:
     pulsar_name: str
     ephem: str
