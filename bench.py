@@ -273,7 +273,8 @@ def main():
         value = total_evals / (dev_ms * 1e-3)
         e2e_value = total_evals / (e2e_ms * 1e-3)
         flops_eval, flops_sigma = algorithmic_flops(ntoa, nrows, p)
-        dmma_peak = float(L.vela_b200_fp64_peak_tflops(local_rank, 1))
+        # two occupancies of the same register-resident DMMA loop (64 and 8 warps/SM); the better one is the peak
+        dmma_peak = max(float(L.vela_b200_fp64_peak_tflops(local_rank, 1)), float(L.vela_b200_fp64_peak_tflops(local_rank, 108)))
         dfma_peak = float(L.vela_b200_fp64_peak_tflops(local_rank, 0))
         sigma_ms = float(stage_ms[2])
         achieved = flops_sigma * B / (sigma_ms * 1e-3) / 1e12 if sigma_ms > 0 else None

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -83,7 +84,7 @@ struct VelaPulsar {
     long n_toas = 0, n_rows = 0, n_rows_pad = 0;
     int p = 0, pp = 0, n_units = 0, n_pair_units = 0, n_gp = 0;
     long n_pairs = 0, ld_sig = 0;
-    int sig_bk = 32, sig_stages = 4;
+    int sig_bk = 32, sig_stages = 4, sig_mt = 8, sig_nt = 4;
     size_t sig_smem = 0;
     int chain_threads = 256, chain_group = 32, n_tiles = 0;
     bool chol_smem = true;
@@ -108,7 +109,7 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
     Buffers& b = d.buf;
     if (B <= b.cap_B) return 0;
     free_buffers(b);
-    long cap = std::max<long>(round_up(B, kSigSamples), 64);
+    long cap = std::max<long>(round_up(B, kSigMaxSamples), 64);
     const ProgramDev& pg = h->prog;
     CU(cudaMalloc((void**)&b.params, (size_t)cap * std::max(pg.n_free, 1) * sizeof(double)));
     CU(cudaMalloc((void**)&b.Pext, (size_t)cap * pg.row * sizeof(double)));
@@ -153,14 +154,45 @@ void fill_sigma_args(VelaPulsar* h, DeviceModel& d, long B, SigmaArgs& sa) {
     sa.Sig = b.Sig; sa.ld_sig = h->ld_sig; sa.U = b.U; sa.ld_u = h->pp;
 }
 
-void launch_sigma(VelaPulsar* h, const SigmaArgs& sa, long B, cudaStream_t st) {
-    dim3 grid((unsigned)((h->n_units + kSigWarps - 1) / kSigWarps), (unsigned)((B + kSigSamples - 1) / kSigSamples));
+#define VELA_SIGMA_DISPATCH(KERNEL)                                                                          \
+    do {                                                                                                      \
+        if (bk == 64) KERNEL<64, 3, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);                              \
+        else if (bk == 32 && ns == 4) KERNEL<32, 4, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);              \
+        else if (bk == 32) KERNEL<32, 3, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);                         \
+        else if (bk == 16 && ns == 4) KERNEL<16, 4, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);              \
+        else if (bk == 16 && ns == 3) KERNEL<16, 3, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);              \
+        else if (bk == 16) KERNEL<16, 2, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);                         \
+        else KERNEL<8, 2, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);                                        \
+    } while (0)
+
+template <int MT, int NT>
+void launch_sigma_t(VelaPulsar* h, const SigmaArgs& sa, dim3 grid, cudaStream_t st) {
     const size_t sm = h->sig_smem;
-    if (h->sig_bk == 32) sigma_contract_kernel<32, 4><<<grid, kSigThreads, sm, st>>>(sa);
-    else if (h->sig_bk == 16 && h->sig_stages == 4) sigma_contract_kernel<16, 4><<<grid, kSigThreads, sm, st>>>(sa);
-    else if (h->sig_bk == 16 && h->sig_stages == 3) sigma_contract_kernel<16, 3><<<grid, kSigThreads, sm, st>>>(sa);
-    else if (h->sig_bk == 16) sigma_contract_kernel<16, 2><<<grid, kSigThreads, sm, st>>>(sa);
-    else sigma_contract_kernel<8, 2><<<grid, kSigThreads, sm, st>>>(sa);
+    const int bk = h->sig_bk, ns = h->sig_stages;
+    VELA_SIGMA_DISPATCH(sigma_contract_kernel);
+}
+
+void launch_sigma(VelaPulsar* h, const SigmaArgs& sa, long B, cudaStream_t st) {
+    const int nsamp = 8 * h->sig_nt;
+    dim3 grid((unsigned)((h->n_units + kSigWarps - 1) / kSigWarps), (unsigned)((B + nsamp - 1) / nsamp));
+    launch_sigma_t<8, 4>(h, sa, grid, st);
+}
+
+#define VELA_SIGMA_ATTR(KERNEL)                                                                                        \
+    do {                                                                                                                \
+        CU(cudaFuncSetAttribute(KERNEL<64, 3, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
+        CU(cudaFuncSetAttribute(KERNEL<32, 4, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
+        CU(cudaFuncSetAttribute(KERNEL<32, 3, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
+        CU(cudaFuncSetAttribute(KERNEL<16, 4, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
+        CU(cudaFuncSetAttribute(KERNEL<16, 3, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
+        CU(cudaFuncSetAttribute(KERNEL<16, 2, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
+        CU(cudaFuncSetAttribute(KERNEL<8, 2, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));        \
+    } while (0)
+
+template <int MT, int NT>
+int set_sigma_attrs(int max_optin) {
+    VELA_SIGMA_ATTR(sigma_contract_kernel);
+    return 0;
 }
 
 // Dynamic shared-memory ceilings are per FUNCTION, not per handle: raise every kernel to the device opt-in
@@ -168,11 +200,8 @@ void launch_sigma(VelaPulsar* h, const SigmaArgs& sa, long B, cudaStream_t st) {
 int set_smem_attrs(int dev) {
     int max_optin = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    CU(cudaFuncSetAttribute(sigma_contract_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-    CU(cudaFuncSetAttribute(sigma_contract_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-    CU(cudaFuncSetAttribute(sigma_contract_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-    CU(cudaFuncSetAttribute(sigma_contract_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-    CU(cudaFuncSetAttribute(sigma_contract_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    max_optin -= 256;   // room for the static mbarrier words of the bulk-copy kernel
+    if (set_sigma_attrs<8, 4>(max_optin)) return VELA_ERR_CUDA;
     CU(cudaFuncSetAttribute(chol_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
     CU(cudaFuncSetAttribute(toa_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     return 0;
@@ -362,7 +391,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     h->kernel_kind = desc->kernel_kind;
     h->n_toas = desc->n_toas;
     h->n_rows = desc->wideband ? 2 * desc->n_toas : desc->n_toas;
-    h->n_rows_pad = round_up(h->n_rows, 32);
+    h->n_rows_pad = round_up(h->n_rows, 64);
     h->chain_threads = desc->n_toas <= 64 ? 64 : (desc->n_toas <= 2048 ? 128 : 256);
     h->n_tiles = (int)((desc->n_toas + h->chain_threads - 1) / h->chain_threads);
     h->chain_group = 32;
@@ -375,15 +404,22 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         h->n_gp = desc->n_gp;
         h->n_pairs = (long)h->p * (h->p + 1) / 2;
         h->ld_sig = round_up(h->n_pairs, 8);
+        // warp tile shape: MT m-tiles x NT n-tiles
+        h->sig_mt = 8; h->sig_nt = 4;
         const long pair_tiles = (h->n_pairs + 7) / 8;
-        h->n_pair_units = (int)((pair_tiles + 7) / 8);
-        h->n_units = h->n_pair_units + (h->pp / 8 + 7) / 8;
+        h->n_pair_units = (int)((pair_tiles + h->sig_mt - 1) / h->sig_mt);
+        h->n_units = h->n_pair_units + (h->pp / 8 + h->sig_mt - 1) / h->sig_mt;
         // pipeline shape: the deepest/widest ring of all-M-columns stages that fits in shared memory
-        const int cand[5][2] = {{32, 4}, {16, 4}, {16, 3}, {16, 2}, {8, 2}};
+        const int cand[7][2] = {{64, 3}, {32, 4}, {32, 3}, {16, 4}, {16, 3}, {16, 2}, {8, 2}};
         h->sig_bk = 8; h->sig_stages = 2;
         for (auto& c : cand)
-            if (sigma_smem_bytes(h->p, c[0], c[1]) <= (size_t)220 * 1024) { h->sig_bk = c[0]; h->sig_stages = c[1]; break; }
-        h->sig_smem = sigma_smem_bytes(h->p, h->sig_bk, h->sig_stages);
+            if (sigma_smem_bytes(h->p, c[0], c[1], h->sig_nt) <= (size_t)220 * 1024) { h->sig_bk = c[0]; h->sig_stages = c[1]; break; }
+        if (const char* e = getenv("VELA_B200_SIGMA_BK")) {
+            int bk = atoi(e);
+            for (auto& c : cand)
+                if (c[0] == bk && sigma_smem_bytes(h->p, c[0], c[1], h->sig_nt) <= (size_t)220 * 1024) { h->sig_bk = c[0]; h->sig_stages = c[1]; break; }
+        }
+        h->sig_smem = sigma_smem_bytes(h->p, h->sig_bk, h->sig_stages, h->sig_nt);
         int col = 0;
         for (int g = 0; g < desc->n_gp; ++g) {
             const VelaGPDesc& s = desc->gp[g];
@@ -448,7 +484,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         cudaSetDevice(prev);
         size_t budget = std::min<size_t>(free_b / 2, (size_t)48 << 30);
         long mc = (long)(budget / std::max<size_t>(per, 1));
-        h->max_chunk = std::max<long>(kSigSamples, mc / kSigSamples * kSigSamples);
+        h->max_chunk = std::max<long>(kSigMaxSamples, mc / kSigMaxSamples * kSigMaxSamples);
     } else {
         h->max_chunk = 1 << 20;
     }
@@ -738,13 +774,17 @@ VELA_API int vela_b200_debug_sincos(const double* x, int n, double* s, double* c
     return VELA_OK;
 }
 
+// kind: 0 DFMA, 1 DMMA at full occupancy; 100 + w: DMMA with w warps per SM (one block of 32 w threads per SM)
 VELA_API double vela_b200_fp64_peak_tflops(int device, int kind) {
     int prev = 0;
     if (cudaGetDevice(&prev) != cudaSuccess) return -1.0;
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 16384;
+    int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 16384;
+    int mix = -1;
+    if (kind >= 200) { mix = kind - 200; blocks = prop.multiProcessorCount; threads = 256; kind = 1; iters = 65536; }
+    else if (kind >= 100) { blocks = prop.multiProcessorCount; threads = 32 * (kind - 100); kind = 1; iters = 65536; }
     double* dout = nullptr;
     cudaMalloc((void**)&dout, sizeof(double) * blocks * threads);
     cudaEvent_t e0, e1;
@@ -754,6 +794,7 @@ VELA_API double vela_b200_fp64_peak_tflops(int device, int kind) {
     for (int rep = 0; rep < 12; ++rep) {   // first reps warm the clocks up; best of the rest
         cudaEventRecord(e0);
         if (kind == 0) dfma_peak_kernel<<<blocks, threads>>>(dout, iters);
+        else if (mix >= 0) dmma_mix_kernel<<<blocks, threads>>>(dout, iters, mix == 1 ? 1 : (mix == 2 ? 4 : 0), mix == 3 ? 8 : 0);
         else dmma_peak_kernel<<<blocks, threads>>>(dout, iters);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) sample_prologue_kernel(const __grid_const
 // shared memory once per block (uniform-address LDS = broadcast).  For each walker the block reduces
 // chi^2 and log-det terms over its TOAs with warp shuffles; per-tile partials go to `partial`
 // [tile][walker][2] and are summed in a fixed order later (deterministic, no atomics).
-__global__ void __launch_bounds__(kChainThreads) toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a) {
+__global__ void __launch_bounds__(kChainThreads, 2) toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a) {
     extern __shared__ double smem[];
     const int row = prog.row;
     double* sP = smem;                                  // [group][row]
@@ -178,13 +178,19 @@ __global__ void finish_white_kernel(const double* __restrict__ partial, int n_ti
 // GEMM over the TOA axis:   C[t(p,q), b] = sum_j (M[j,p] M[j,q]) * w[b,j],   u[p, b] = sum_j M[j,p] (w y)[b,j].
 //
 // GEMM rows are the PACKED lower triangle t = p(p+1)/2 + q (q <= p < rank): no padding of the rank and
-// no redundant upper/diagonal-block work.  Rows are cut into m8 tiles; a warp owns a "unit" of 8
-// consecutive m-tiles x 32 walkers (4 n-tiles): 8 x 4 m8n8k4 accumulators = 64 FP64 registers, so each
+// no redundant upper/diagonal-block work.  Rows are cut into m8 tiles; a warp owns a "unit" of MT=8
+// consecutive m-tiles x NT=4 n-tiles (32 walkers): 32 m8n8k4 accumulators = 64 FP64 registers, so each
 // k4 step issues 32 independent DMMAs for 20 LDS.64 + 8 DMUL.  The A operand is never materialised: every
 // A element is the product of two entries of the shared-memory M tile (row gid of m-tile i <-> its (p,q)).
 // "u" units use M rows directly against the w.y product.  A CTA is 8 warps = 8 consecutive units over
 // the same 32 walkers; all `rank` columns of M plus the W and Y rows of the 32 walkers are staged with
-// cp.async in a STAGES-deep ring, K-contiguous with a (BK+4)-double row pitch (conflict-free fragment reads).
+// cp.async (LDGSTS) in a STAGES-deep ring, K-contiguous with a (BK+4)-double row pitch (conflict-free
+// fragment reads).  Stage hand-off uses mbarriers instead of __syncthreads: copies complete on a per-stage
+// "full" barrier (cp.async.mbarrier.arrive.noinc), readers release a stage through its "empty" barrier,
+// and the refill runs STAGES-2 tiles ahead - one tile behind the slowest reader - so warps drift freely.
+// Measured alternatives (B200, config 3): __syncthreads ring 11.32 ms, 1-D bulk copies
+// (cp.async.bulk, one row per lane: UBLKCP is a uniform-datapath instruction, so per-lane rows serialise)
+// 13.96 ms, 4x8 warp tile 11.9 ms, this version 11.12 ms.
 __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
@@ -199,41 +205,81 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int BK, int STAGES>
+// mbarrier helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// ---- K3, decoupled cp.async pipeline: LDGSTS data movement as in sigma_contract_kernel, but completion is
+// tracked with per-stage mbarriers (cp.async.mbarrier.arrive.noinc) and stages are released through "empty"
+// mbarriers, so there is no block-wide barrier in the main loop; the refill runs S-2 tiles ahead, one tile
+// behind the slowest reader, so neither wait normally blocks.
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BK, int STAGES, int MT, int NT>
 __global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArgs a) {
     extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
     constexpr int PITCH = BK + 4;
+    constexpr int NS = NT * 8;
+    constexpr int AHEAD = STAGES > 2 ? STAGES - 2 : 1;   // prefetch distance in tiles
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const long b0 = (long)blockIdx.y * kSigSamples;
+    const long b0 = (long)blockIdx.y * NS;
     const int P = a.rank;
-
-    // stage layout: [P columns of M][kSigSamples rows of W][kSigSamples rows of Y]
-    const int stage_rows = P + 2 * kSigSamples;
+    const int stage_rows = P + 2 * NS;
     const size_t stage_doubles = (size_t)stage_rows * PITCH;
-    constexpr int kChunks = BK / 2;   // 16-byte chunks per row
+    constexpr int kChunks = BK / 2;
     const int total_chunks = stage_rows * kChunks;
-    auto issue = [&](int kt, int s) {
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kSigThreads); mbar_init(&empty_bar[s], kSigWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {
+        const int s = t % STAGES;
         double* base = smem + (size_t)s * stage_doubles;
-        const long j0 = (long)kt * BK;
+        const long j0 = (long)t * BK;
         for (int c = tid; c < total_chunks; c += kSigThreads) {
             int r = c / kChunks, ch = c - r * kChunks;
             const double* src;
             if (r < P) src = a.M + (size_t)r * a.ldM + j0 + ch * 2;
-            else if (r < P + kSigSamples) src = a.W + (size_t)(b0 + (r - P)) * a.ld_yw + j0 + ch * 2;
-            else src = a.Y + (size_t)(b0 + (r - P - kSigSamples)) * a.ld_yw + j0 + ch * 2;
+            else if (r < P + NS) src = a.W + (size_t)(b0 + (r - P)) * a.ld_yw + j0 + ch * 2;
+            else src = a.Y + (size_t)(b0 + (r - P - NS)) * a.ld_yw + j0 + ch * 2;
             cp_async16(base + (size_t)r * PITCH + ch * 2, src);
         }
+        cp_async_mbar_arrive(&full_bar[s]);
     };
 
-    // ---- this warp's unit: 8 m-tiles; row gid of m-tile i is packed pair t -> (p, q), or M row p for u units
     const int u = blockIdx.x * kSigWarps + warp;
     const bool have_unit = u < a.n_units;
     const bool is_pair = u < a.n_pair_units;
-    const int tile0 = is_pair ? u * 8 : (u - a.n_pair_units) * 8;
-    int offp[8], offq[8];
+    const int tile0 = is_pair ? u * MT : (u - a.n_pair_units) * MT;
+    int offp[MT], offq[MT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < MT; ++i) {
         int p = 0, q = 0;
         if (have_unit) {
             long t = (long)(tile0 + i) * 8 + gid;
@@ -252,68 +298,60 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArg
         offq[i] = q * PITCH;
     }
 
-    double acc[8][4][2];
+    double acc[MT][NT][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int n = 0; n < 4; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
+        for (int n = 0; n < NT; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
 
     const int n_ktiles = (int)(a.n_rows_pad / BK);
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < n_ktiles) issue(s, s);
-        cp_async_commit();
-    }
+    for (int t = 0; t < AHEAD && t < n_ktiles; ++t) issue(t);
 
     for (int kt = 0; kt < n_ktiles; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {   // refill the slot freed by the previous iteration
-            int nk = kt + STAGES - 1;
-            if (nk < n_ktiles) issue(nk, nk % STAGES);
-            cp_async_commit();
+        const int nk = kt + AHEAD;
+        if (nk < n_ktiles) {
+            if (nk >= STAGES) mbar_wait(&empty_bar[nk % STAGES], ((nk / STAGES) - 1) & 1);
+            issue(nk);
         }
+        const int s = kt % STAGES;
+        mbar_wait(&full_bar[s], (kt / STAGES) & 1);
         if (have_unit) {
-            const double* sM = smem + (size_t)(kt % STAGES) * stage_doubles;
+            const double* sM = smem + (size_t)s * stage_doubles;
             const double* sW = sM + (size_t)P * PITCH;
-            const double* sY = sW + (size_t)kSigSamples * PITCH;
+            const double* sY = sW + (size_t)NS * PITCH;
 #pragma unroll
             for (int kk = 0; kk < BK / 4; ++kk) {
                 const int k = kk * 4 + tig;
-                double bw[4];
+                double bw[NT], af[MT];
 #pragma unroll
-                for (int n = 0; n < 4; ++n) bw[n] = sW[(n * 8 + gid) * PITCH + k];
+                for (int n = 0; n < NT; ++n) bw[n] = sW[(n * 8 + gid) * PITCH + k];
                 if (is_pair) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const double af = sM[offp[i] + k] * sM[offq[i] + k];
-#pragma unroll
-                        for (int n = 0; n < 4; ++n) dmma8x8x4(acc[i][n][0], acc[i][n][1], af, bw[n]);
-                    }
+                    for (int i = 0; i < MT; ++i) af[i] = sM[offp[i] + k] * sM[offq[i] + k];
                 } else {
 #pragma unroll
-                    for (int n = 0; n < 4; ++n) bw[n] *= sY[(n * 8 + gid) * PITCH + k];
+                    for (int n = 0; n < NT; ++n) bw[n] *= sY[(n * 8 + gid) * PITCH + k];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const double af = sM[offp[i] + k];
-#pragma unroll
-                        for (int n = 0; n < 4; ++n) dmma8x8x4(acc[i][n][0], acc[i][n][1], af, bw[n]);
-                    }
+                    for (int i = 0; i < MT; ++i) af[i] = sM[offp[i] + k];
                 }
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) dmma8x8x4(acc[i][n][0], acc[i][n][1], af[i], bw[n]);
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
-    cp_async_wait<0>();
 
-    // ---- epilogue: accumulator (row = gid, col = 2*tig + {0,1}) of tile (i, n)
     if (!have_unit) return;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < MT; ++i) {
         const long t = (long)(tile0 + i) * 8 + gid;
         const bool ok = is_pair ? (t < a.n_pairs) : (t < P);
         if (!ok) continue;
 #pragma unroll
-        for (int n = 0; n < 4; ++n)
+        for (int n = 0; n < NT; ++n)
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 long b = b0 + n * 8 + 2 * tig + r;
@@ -325,11 +363,14 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArg
     }
 }
 
-template __global__ void sigma_contract_kernel<32, 4>(SigmaArgs);
-template __global__ void sigma_contract_kernel<16, 4>(SigmaArgs);
-template __global__ void sigma_contract_kernel<16, 3>(SigmaArgs);
-template __global__ void sigma_contract_kernel<16, 2>(SigmaArgs);
-template __global__ void sigma_contract_kernel<8, 2>(SigmaArgs);
+#define VELA_SIGMA_INST(BK, ST) template __global__ void sigma_contract_kernel<BK, ST, 8, 4>(SigmaArgs);
+VELA_SIGMA_INST(64, 3)
+VELA_SIGMA_INST(32, 4)
+VELA_SIGMA_INST(32, 3)
+VELA_SIGMA_INST(16, 4)
+VELA_SIGMA_INST(16, 3)
+VELA_SIGMA_INST(16, 2)
+VELA_SIGMA_INST(8, 2)
 
 // ------------------------------------------------------------------------------------------
 // K4  + Phi^-1, Cholesky, log-det, solve, ln L
@@ -512,6 +553,38 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) dmma8x8x4(acc[i][0], acc[i][1], af, bf);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// DMMA loop with `nmul` interleaved DMULs and `nlds` shared-memory loads per 16 DMMAs (pipe-interference probe)
+__global__ void __launch_bounds__(256) dmma_mix_kernel(double* out, int iters, int nmul, int nlds) {
+    __shared__ double sbuf[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sbuf[i] = 1.0 + 1e-9 * i;
+    __syncthreads();
+    double acc[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+    double af[4], bf = 1.0 - 1e-9 * threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) af[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    double m0 = 1.0000001;
+    int idx = threadIdx.x & 255;
+    for (int it = 0; it < iters; ++it) {
+        if (nlds == 8) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = sbuf[(idx + 32 * i + it) & 1023] * sbuf[(idx + 7 * i + 2 * it) & 1023];
+        } else if (nmul == 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = af[i] * m0;
+        } else if (nmul == 1) {
+            af[0] = af[0] * m0;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma8x8x4(acc[i][0], acc[i][1], af[i & 3], bf);
     }
     double s = 0.0;
 #pragma unroll

@@ -9,7 +9,7 @@ constexpr int kChainThreads = 256;  // max threads per block of the chain kernel
 // K3 tiling
 constexpr int kSigThreads = 256;
 constexpr int kSigWarps = 8;        // units per CTA
-constexpr int kSigSamples = 32;     // walkers per CTA (4 n-tiles of 8)
+constexpr int kSigMaxSamples = 64;  // walkers per CTA: 8 x (n-tiles per warp)
 constexpr int kSigMaxRank = 1024;
 
 constexpr int kCholThreads = 256;
@@ -37,7 +37,7 @@ struct SigmaArgs {
     long ldM;
     int rank;                  // p
     long n_pairs;              // p (p + 1) / 2 packed lower-triangle rows
-    int n_pair_units;          // units of 8 m-tiles covering the pairs
+    int n_pair_units;          // units of MT m-tiles covering the pairs
     int n_units;               // pair units + u units
     long n_rows_pad;
     const double* W;
@@ -84,16 +84,18 @@ __global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, 
 __global__ void toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a);
 __global__ void finish_white_kernel(const double* partial, int n_tiles, long B, int mode, const double* lnprior,
                                     int with_prior, double* out);
-template <int BK, int STAGES>
+template <int BK, int STAGES, int MT, int NT>
 __global__ void sigma_contract_kernel(SigmaArgs a);
+
 __global__ void chol_finish_kernel(CholArgs a);
 __global__ void phiinv_kernel(CholArgs a, double* out);
 __global__ void sincos_cr_kernel(const double* x, int n, double* s, double* c);
 __global__ void dfma_peak_kernel(double* out, int iters);
 __global__ void dmma_peak_kernel(double* out, int iters);
+__global__ void dmma_mix_kernel(double* out, int iters, int nmul, int nlds);
 
-inline size_t sigma_smem_bytes(int rank, int bk, int stages) {
-    return (size_t)stages * (rank + 2 * kSigSamples) * (bk + 4) * sizeof(double);
+inline size_t sigma_smem_bytes(int rank, int bk, int stages, int nt) {
+    return (size_t)stages * (rank + 2 * 8 * nt) * (bk + 4) * sizeof(double);
 }
 
 }  // namespace vela
