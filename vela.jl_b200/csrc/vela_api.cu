@@ -84,7 +84,7 @@ struct VelaPulsar {
     long n_toas = 0, n_rows = 0, n_rows_pad = 0;
     int p = 0, pp = 0, n_units = 0, n_pair_units = 0, n_gp = 0;
     long n_pairs = 0, ld_sig = 0;
-    int sig_bk = 32, sig_stages = 4, sig_mt = 8, sig_nt = 4;
+    int sig_shape = 0;
     size_t sig_smem = 0;
     int chain_threads = 256, chain_group = 32, n_tiles = 0;
     bool chol_smem = true;
@@ -154,45 +154,19 @@ void fill_sigma_args(VelaPulsar* h, DeviceModel& d, long B, SigmaArgs& sa) {
     sa.Sig = b.Sig; sa.ld_sig = h->ld_sig; sa.U = b.U; sa.ld_u = h->pp;
 }
 
-#define VELA_SIGMA_DISPATCH(KERNEL)                                                                          \
-    do {                                                                                                      \
-        if (bk == 64) KERNEL<64, 3, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);                              \
-        else if (bk == 32 && ns == 4) KERNEL<32, 4, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);              \
-        else if (bk == 32) KERNEL<32, 3, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);                         \
-        else if (bk == 16 && ns == 4) KERNEL<16, 4, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);              \
-        else if (bk == 16 && ns == 3) KERNEL<16, 3, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);              \
-        else if (bk == 16) KERNEL<16, 2, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);                         \
-        else KERNEL<8, 2, MT, NT><<<grid, kSigThreads, sm, st>>>(sa);                                        \
-    } while (0)
-
-template <int MT, int NT>
-void launch_sigma_t(VelaPulsar* h, const SigmaArgs& sa, dim3 grid, cudaStream_t st) {
-    const size_t sm = h->sig_smem;
-    const int bk = h->sig_bk, ns = h->sig_stages;
-    VELA_SIGMA_DISPATCH(sigma_contract_kernel);
-}
+// K3 launch shapes: (BK, stages, m-tiles, n-tiles, warps); see DESIGN.md section 5
+struct SigmaShape { int bk, stages, mt, nt, warps, ctas_per_sm; void (*kernel)(SigmaArgs); };
+#define VELA_SHAPE(BK, ST, MT, NT, W, C) SigmaShape{BK, ST, MT, NT, W, C, sigma_contract_kernel<BK, ST, MT, NT, W>}
+const SigmaShape kSigmaShapes[] = {
+    VELA_SHAPE(64, 3, 4, 4, 16, 1), VELA_SHAPE(32, 4, 4, 4, 16, 1), VELA_SHAPE(32, 3, 4, 4, 16, 1), VELA_SHAPE(16, 4, 4, 4, 16, 1),
+    VELA_SHAPE(16, 3, 4, 4, 16, 1), VELA_SHAPE(16, 2, 4, 4, 16, 1), VELA_SHAPE(8, 2, 4, 4, 16, 1),
+};
 
 void launch_sigma(VelaPulsar* h, const SigmaArgs& sa, long B, cudaStream_t st) {
-    const int nsamp = 8 * h->sig_nt;
-    dim3 grid((unsigned)((h->n_units + kSigWarps - 1) / kSigWarps), (unsigned)((B + nsamp - 1) / nsamp));
-    launch_sigma_t<8, 4>(h, sa, grid, st);
-}
-
-#define VELA_SIGMA_ATTR(KERNEL)                                                                                        \
-    do {                                                                                                                \
-        CU(cudaFuncSetAttribute(KERNEL<64, 3, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
-        CU(cudaFuncSetAttribute(KERNEL<32, 4, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
-        CU(cudaFuncSetAttribute(KERNEL<32, 3, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
-        CU(cudaFuncSetAttribute(KERNEL<16, 4, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
-        CU(cudaFuncSetAttribute(KERNEL<16, 3, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
-        CU(cudaFuncSetAttribute(KERNEL<16, 2, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));       \
-        CU(cudaFuncSetAttribute(KERNEL<8, 2, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));        \
-    } while (0)
-
-template <int MT, int NT>
-int set_sigma_attrs(int max_optin) {
-    VELA_SIGMA_ATTR(sigma_contract_kernel);
-    return 0;
+    const SigmaShape& sh = kSigmaShapes[h->sig_shape];
+    const int nsamp = 8 * sh.nt;
+    dim3 grid((unsigned)((h->n_units + sh.warps - 1) / sh.warps), (unsigned)((B + nsamp - 1) / nsamp));
+    sh.kernel<<<grid, sh.warps * 32, h->sig_smem, st>>>(sa);
 }
 
 // Dynamic shared-memory ceilings are per FUNCTION, not per handle: raise every kernel to the device opt-in
@@ -200,8 +174,9 @@ int set_sigma_attrs(int max_optin) {
 int set_smem_attrs(int dev) {
     int max_optin = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    max_optin -= 256;   // room for the static mbarrier words of the bulk-copy kernel
-    if (set_sigma_attrs<8, 4>(max_optin)) return VELA_ERR_CUDA;
+    max_optin -= 256;   // room for the static mbarrier words
+    for (const SigmaShape& sh : kSigmaShapes)
+        CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(chol_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
     CU(cudaFuncSetAttribute(toa_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     return 0;
@@ -404,22 +379,26 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         h->n_gp = desc->n_gp;
         h->n_pairs = (long)h->p * (h->p + 1) / 2;
         h->ld_sig = round_up(h->n_pairs, 8);
-        // warp tile shape: MT m-tiles x NT n-tiles
-        h->sig_mt = 8; h->sig_nt = 4;
-        const long pair_tiles = (h->n_pairs + 7) / 8;
-        h->n_pair_units = (int)((pair_tiles + h->sig_mt - 1) / h->sig_mt);
-        h->n_units = h->n_pair_units + (h->pp / 8 + h->sig_mt - 1) / h->sig_mt;
-        // pipeline shape: the deepest/widest ring of all-M-columns stages that fits in shared memory
-        const int cand[7][2] = {{64, 3}, {32, 4}, {32, 3}, {16, 4}, {16, 3}, {16, 2}, {8, 2}};
-        h->sig_bk = 8; h->sig_stages = 2;
-        for (auto& c : cand)
-            if (sigma_smem_bytes(h->p, c[0], c[1], h->sig_nt) <= (size_t)220 * 1024) { h->sig_bk = c[0]; h->sig_stages = c[1]; break; }
-        if (const char* e = getenv("VELA_B200_SIGMA_BK")) {
-            int bk = atoi(e);
-            for (auto& c : cand)
-                if (c[0] == bk && sigma_smem_bytes(h->p, c[0], c[1], h->sig_nt) <= (size_t)220 * 1024) { h->sig_bk = c[0]; h->sig_stages = c[1]; break; }
+        // pick the first launch shape whose ring fits (two CTAs per SM need <= 110 KB each); the environment
+        // variable VELA_B200_SIGMA_SHAPE=<index into kSigmaShapes> overrides for A/B measurements
+        const int n_shapes = (int)(sizeof(kSigmaShapes) / sizeof(kSigmaShapes[0]));
+        h->sig_shape = -1;
+        for (int i = 0; i < n_shapes; ++i) {
+            const SigmaShape& sh = kSigmaShapes[i];
+            size_t need = sigma_smem_bytes(h->p, sh.bk, sh.stages, sh.nt);
+            if (need <= (size_t)(sh.ctas_per_sm == 2 ? 110 : 220) * 1024) { h->sig_shape = i; break; }
         }
-        h->sig_smem = sigma_smem_bytes(h->p, h->sig_bk, h->sig_stages, h->sig_nt);
+        if (const char* e = getenv("VELA_B200_SIGMA_SHAPE")) {
+            int i = atoi(e);
+            if (i >= 0 && i < n_shapes && sigma_smem_bytes(h->p, kSigmaShapes[i].bk, kSigmaShapes[i].stages, kSigmaShapes[i].nt) <= (size_t)220 * 1024)
+                h->sig_shape = i;
+        }
+        if (h->sig_shape < 0) { delete h; return fail(VELA_ERR_UNSUPPORTED, "basis rank %d does not fit any Sigma-contraction shape", h->p); }
+        const SigmaShape& shp = kSigmaShapes[h->sig_shape];
+        const long pair_tiles = (h->n_pairs + 7) / 8;
+        h->n_pair_units = (int)((pair_tiles + shp.mt - 1) / shp.mt);
+        h->n_units = h->n_pair_units + (h->pp / 8 + shp.mt - 1) / shp.mt;
+        h->sig_smem = sigma_smem_bytes(h->p, shp.bk, shp.stages, shp.nt);
         int col = 0;
         for (int g = 0; g < desc->n_gp; ++g) {
             const VelaGPDesc& s = desc->gp[g];

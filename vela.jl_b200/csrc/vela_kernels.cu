@@ -178,19 +178,21 @@ __global__ void finish_white_kernel(const double* __restrict__ partial, int n_ti
 // GEMM over the TOA axis:   C[t(p,q), b] = sum_j (M[j,p] M[j,q]) * w[b,j],   u[p, b] = sum_j M[j,p] (w y)[b,j].
 //
 // GEMM rows are the PACKED lower triangle t = p(p+1)/2 + q (q <= p < rank): no padding of the rank and
-// no redundant upper/diagonal-block work.  Rows are cut into m8 tiles; a warp owns a "unit" of MT=8
-// consecutive m-tiles x NT=4 n-tiles (32 walkers): 32 m8n8k4 accumulators = 64 FP64 registers, so each
-// k4 step issues 32 independent DMMAs for 20 LDS.64 + 8 DMUL.  The A operand is never materialised: every
+// no redundant upper/diagonal-block work.  Rows are cut into m8 tiles; a warp owns a "unit" of MT=4
+// consecutive m-tiles x NT=4 n-tiles (32 walkers): 16 m8n8k4 accumulators = 32 FP64 registers, and each
+// k4 step issues 16 independent DMMAs for 12 LDS.64 + 4 DMUL.  The A operand is never materialised: every
 // A element is the product of two entries of the shared-memory M tile (row gid of m-tile i <-> its (p,q)).
-// "u" units use M rows directly against the w.y product.  A CTA is 8 warps = 8 consecutive units over
-// the same 32 walkers; all `rank` columns of M plus the W and Y rows of the 32 walkers are staged with
-// cp.async (LDGSTS) in a STAGES-deep ring, K-contiguous with a (BK+4)-double row pitch (conflict-free
-// fragment reads).  Stage hand-off uses mbarriers instead of __syncthreads: copies complete on a per-stage
-// "full" barrier (cp.async.mbarrier.arrive.noinc), readers release a stage through its "empty" barrier,
-// and the refill runs STAGES-2 tiles ahead - one tile behind the slowest reader - so warps drift freely.
-// Measured alternatives (B200, config 3): __syncthreads ring 11.32 ms, 1-D bulk copies
-// (cp.async.bulk, one row per lane: UBLKCP is a uniform-datapath instruction, so per-lane rows serialise)
-// 13.96 ms, 4x8 warp tile 11.9 ms, this version 11.12 ms.
+// "u" units use M rows directly against the w.y product.  A CTA is 16 warps = 16 consecutive units over
+// the same 32 walkers (one CTA per SM, 4 warps per scheduler); all `rank` columns of M plus the W and Y
+// rows of the 32 walkers are staged with cp.async (LDGSTS) in a STAGES-deep ring, K-contiguous with a
+// (BK+4)-double row pitch (conflict-free fragment reads).  Stage hand-off uses mbarriers instead of
+// __syncthreads: copies complete on a per-stage "full" barrier (cp.async.mbarrier.arrive.noinc), readers
+// release a stage through its "empty" barrier, and the refill runs STAGES-2 tiles ahead - one tile behind
+// the slowest reader - so warps drift freely.
+// Measured alternatives (B200, config 3, ms per launch): 8x8-block tiling 16.3;
+// packed rows, 8x4 warp tile x 8 warps: __syncthreads ring 11.32, mbarrier ring 11.10, 1-D bulk copies
+// (cp.async.bulk; UBLKCP is a uniform-datapath instruction, so per-lane rows serialise) 13.96;
+// 4x4 warp tile: 8 warps x 2 CTAs/SM 10.61, 16 warps x 1 CTA/SM (this kernel) 10.50.
 __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
@@ -235,8 +237,9 @@ __device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BK, int STAGES, int MT, int NT>
-__global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArgs a) {
+template <int BK, int STAGES, int MT, int NT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (MT * NT * WARPS <= 128) ? 2 : 1) sigma_contract_kernel(SigmaArgs a) {
+    constexpr int kThreads = WARPS * 32;
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
     constexpr int PITCH = BK + 4;
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArg
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kSigThreads); mbar_init(&empty_bar[s], kSigWarps); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kThreads); mbar_init(&empty_bar[s], WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArg
         const int s = t % STAGES;
         double* base = smem + (size_t)s * stage_doubles;
         const long j0 = (long)t * BK;
-        for (int c = tid; c < total_chunks; c += kSigThreads) {
+        for (int c = tid; c < total_chunks; c += kThreads) {
             int r = c / kChunks, ch = c - r * kChunks;
             const double* src;
             if (r < P) src = a.M + (size_t)r * a.ldM + j0 + ch * 2;
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArg
         cp_async_mbar_arrive(&full_bar[s]);
     };
 
-    const int u = blockIdx.x * kSigWarps + warp;
+    const int u = blockIdx.x * WARPS + warp;
     const bool have_unit = u < a.n_units;
     const bool is_pair = u < a.n_pair_units;
     const int tile0 = is_pair ? u * MT : (u - a.n_pair_units) * MT;
@@ -363,14 +366,15 @@ __global__ void __launch_bounds__(kSigThreads, 1) sigma_contract_kernel(SigmaArg
     }
 }
 
-#define VELA_SIGMA_INST(BK, ST) template __global__ void sigma_contract_kernel<BK, ST, 8, 4>(SigmaArgs);
-VELA_SIGMA_INST(64, 3)
-VELA_SIGMA_INST(32, 4)
-VELA_SIGMA_INST(32, 3)
-VELA_SIGMA_INST(16, 4)
-VELA_SIGMA_INST(16, 3)
-VELA_SIGMA_INST(16, 2)
-VELA_SIGMA_INST(8, 2)
+#define VELA_SIGMA_INST(BK, ST, MT, NT, W) template __global__ void sigma_contract_kernel<BK, ST, MT, NT, W>(SigmaArgs);
+// 4x4 warp tiles, 16 warps sharing one ring, one CTA per SM
+VELA_SIGMA_INST(64, 3, 4, 4, 16)
+VELA_SIGMA_INST(32, 4, 4, 4, 16)
+VELA_SIGMA_INST(32, 3, 4, 4, 16)
+VELA_SIGMA_INST(16, 4, 4, 4, 16)
+VELA_SIGMA_INST(16, 3, 4, 4, 16)
+VELA_SIGMA_INST(16, 2, 4, 4, 16)
+VELA_SIGMA_INST(8, 2, 4, 4, 16)
 
 // ------------------------------------------------------------------------------------------
 // K4  + Phi^-1, Cholesky, log-det, solve, ln L

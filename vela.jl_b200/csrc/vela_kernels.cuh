@@ -7,8 +7,6 @@ namespace vela {
 constexpr int kChainThreads = 256;  // max threads per block of the chain kernel (one TOA each)
 
 // K3 tiling
-constexpr int kSigThreads = 256;
-constexpr int kSigWarps = 8;        // units per CTA
 constexpr int kSigMaxSamples = 64;  // walkers per CTA: 8 x (n-tiles per warp)
 constexpr int kSigMaxRank = 1024;
 
@@ -84,7 +82,7 @@ __global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, 
 __global__ void toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a);
 __global__ void finish_white_kernel(const double* partial, int n_tiles, long B, int mode, const double* lnprior,
                                     int with_prior, double* out);
-template <int BK, int STAGES, int MT, int NT>
+template <int BK, int STAGES, int MT, int NT, int WARPS>
 __global__ void sigma_contract_kernel(SigmaArgs a);
 
 __global__ void chol_finish_kernel(CholArgs a);
