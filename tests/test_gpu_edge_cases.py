@@ -38,8 +38,12 @@ def test_batch_is_independent_of_order_and_neighbours(gp):
     a = psr.lnlike_vectorized(W)
     perm = np.random.default_rng(0).permutation(len(W))
     np.testing.assert_array_equal(psr.lnlike_vectorized(W[perm]), a[perm])
-    np.testing.assert_array_equal(psr.lnlike_vectorized(W[:7]), a[:7])
     np.testing.assert_array_equal(psr.lnlike_vectorized(W), a)            # deterministic: no atomics
+    # a different batch SIZE may pick a different split-K factor for the Sigma contraction, i.e. a different
+    # (still fixed) summation order over TOAs: equal to rounding, not bit for bit
+    np.testing.assert_allclose(psr.lnlike_vectorized(W[:7]), a[:7], rtol=1e-13)
+    sub = psr.lnlike_vectorized(W[:7])
+    np.testing.assert_array_equal(psr.lnlike_vectorized(W[6::-1]), sub[::-1])
 
 
 def test_column_major_and_strided_inputs(ngc):

@@ -49,8 +49,8 @@ def test_lnlike_batch_matches_oracle(name, golden, pulsars, oracle):
     assert np.all(np.isfinite(want))
     np.testing.assert_allclose(got, want, rtol=LNLIKE_RTOL)
     np.testing.assert_allclose(got, g.lnlike, rtol=LNLIKE_RTOL)
-    # serial == vectorised (test_NGC6440E.jl:211-214)
-    assert psr.lnlike(g.x0) == got[0]
+    # serial ≈ vectorised (test_NGC6440E.jl:211-214 uses ≈; a single walker may use another split-K factor)
+    assert psr.lnlike(g.x0) == pytest.approx(got[0], rel=1e-10)
 
 
 @pytest.mark.parametrize("name", ["sim3_gp", "sim_dmgp_wb"])

@@ -14,8 +14,9 @@ def test_two_devices_in_one_handle(vb, golden):
         one = vb.Pulsar(g.model, g.toas, devices=[0])
         two = vb.Pulsar(g.model, g.toas, devices=[0, 1])
         W = np.resize(g.walkers, (101, g.walkers.shape[1]))            # ragged split: 51 + 50
-        np.testing.assert_array_equal(two.lnlike_vectorized(W), one.lnlike_vectorized(W))
-        np.testing.assert_array_equal(two.lnpost_vectorized(W[:3]), one.lnpost_vectorized(W[:3]))
+        # each device sees a smaller block than the single-device run (possibly another split-K factor): equal to rounding
+        np.testing.assert_allclose(two.lnlike_vectorized(W), one.lnlike_vectorized(W), rtol=1e-13)
+        np.testing.assert_allclose(two.lnpost_vectorized(W[:3]), one.lnpost_vectorized(W[:3]), rtol=1e-13)
         np.testing.assert_array_equal(two.lnlike_vectorized(W[:1]), one.lnlike_vectorized(W[:1]))
 
 

@@ -48,9 +48,11 @@ int upload(T** dst, const T* src, size_t n) {
 }
 
 inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
+constexpr long kSplitRows = 2048;   // walker rows reserved for split-K slabs of small batches
 
 struct Buffers {  // per-device, per-batch scratch (grown on demand)
     long cap_B = 0;
+    long sig_rows = 0;   // walker rows of the Sigma / U scratch (>= cap_B; larger so small batches can split K)
     double *params = nullptr, *Pext = nullptr, *tzr = nullptr, *partial = nullptr, *Y = nullptr, *W = nullptr;
     double *Sig = nullptr, *U = nullptr, *Sq = nullptr, *out = nullptr, *lnprior = nullptr;
     double *h_params = nullptr, *h_out = nullptr, *h_lnprior = nullptr;  // pinned
@@ -103,6 +105,7 @@ void free_buffers(Buffers& b) {
     cudaFree(b.Sig); cudaFree(b.U); cudaFree(b.Sq); cudaFree(b.out); cudaFree(b.lnprior);
     b.params = b.Pext = b.tzr = b.partial = b.Y = b.W = b.Sig = b.U = b.Sq = b.out = b.lnprior = nullptr;
     b.cap_B = 0;
+    b.sig_rows = 0;
 }
 
 int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
@@ -123,10 +126,13 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
         CU(cudaMalloc((void**)&b.W, yw));
         CU(cudaMemsetAsync(b.Y, 0, yw, d.stream));
         CU(cudaMemsetAsync(b.W, 0, yw, d.stream));
-        CU(cudaMalloc((void**)&b.Sig, (size_t)cap * h->ld_sig * sizeof(double)));
-        CU(cudaMalloc((void**)&b.U, (size_t)cap * h->pp * sizeof(double)));
-        CU(cudaMemsetAsync(b.Sig, 0, (size_t)cap * h->ld_sig * sizeof(double), d.stream));
-        CU(cudaMemsetAsync(b.U, 0, (size_t)cap * h->pp * sizeof(double), d.stream));
+        // Sigma / U scratch: at least `cap` walker rows, and never fewer than kSplitRows so that small batches can
+        // hold several split-K slabs
+        b.sig_rows = std::max<long>(cap, kSplitRows);
+        CU(cudaMalloc((void**)&b.Sig, (size_t)b.sig_rows * h->ld_sig * sizeof(double)));
+        CU(cudaMalloc((void**)&b.U, (size_t)b.sig_rows * h->pp * sizeof(double)));
+        CU(cudaMemsetAsync(b.Sig, 0, (size_t)b.sig_rows * h->ld_sig * sizeof(double), d.stream));
+        CU(cudaMemsetAsync(b.U, 0, (size_t)b.sig_rows * h->pp * sizeof(double), d.stream));
         if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * h->pp * h->pp * sizeof(double)));
     }
     b.cap_B = cap;
@@ -147,11 +153,15 @@ int ensure_host_buffers(VelaPulsar* h, DeviceModel& d, long B) {
     return 0;
 }
 
-void fill_sigma_args(VelaPulsar* h, DeviceModel& d, long B, SigmaArgs& sa) {
-    Buffers& b = d.buf;
-    sa.M = d.M; sa.ldM = d.ldM; sa.rank = h->p; sa.n_pairs = h->n_pairs; sa.n_pair_units = h->n_pair_units;
-    sa.n_units = h->n_units; sa.n_rows_pad = h->n_rows_pad; sa.W = b.W; sa.Y = b.Y; sa.ld_yw = h->n_rows_pad; sa.B = B;
-    sa.Sig = b.Sig; sa.ld_sig = h->ld_sig; sa.U = b.U; sa.ld_u = h->pp;
+// Small batches do not fill the GPU with (units x walker groups) CTAs; split the TOA axis over gridDim.z and let
+// K4 sum the slabs (deterministic).  Returns the number of slices for a batch of B walkers.
+int choose_ksplit(VelaPulsar* h, long sig_rows, long B, int bk, int warps, int nsamp) {
+    const long ctas = (long)((h->n_units + warps - 1) / warps) * ((B + nsamp - 1) / nsamp);
+    const long n_ktiles = h->n_rows_pad / bk;
+    long want = (2 * 148 + ctas - 1) / ctas;
+    want = std::min<long>(want, std::max<long>(1, n_ktiles / 4));
+    want = std::min<long>(want, std::max<long>(1, sig_rows / std::max<long>(round_up(B, kSigMaxSamples), 1)));
+    return (int)std::max<long>(1, std::min<long>(want, 64));
 }
 
 // K3 launch shapes: (BK, stages, m-tiles, n-tiles, warps); see DESIGN.md section 5
@@ -162,11 +172,26 @@ const SigmaShape kSigmaShapes[] = {
     VELA_SHAPE(16, 3, 4, 4, 16, 1), VELA_SHAPE(16, 2, 4, 4, 16, 1), VELA_SHAPE(8, 2, 4, 4, 16, 1),
 };
 
-void launch_sigma(VelaPulsar* h, const SigmaArgs& sa, long B, cudaStream_t st) {
+// Fills the launch arguments, picks split-K and launches K3; returns the split count K4 has to sum.
+int launch_sigma(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, SigmaArgs* out_args = nullptr) {
     const SigmaShape& sh = kSigmaShapes[h->sig_shape];
+    Buffers& b = d.buf;
     const int nsamp = 8 * sh.nt;
-    dim3 grid((unsigned)((h->n_units + sh.warps - 1) / sh.warps), (unsigned)((B + nsamp - 1) / nsamp));
+    SigmaArgs sa;
+    sa.M = d.M; sa.ldM = d.ldM; sa.rank = h->p; sa.n_pairs = h->n_pairs; sa.n_pair_units = h->n_pair_units;
+    sa.n_units = h->n_units; sa.n_rows_pad = h->n_rows_pad; sa.W = b.W; sa.Y = b.Y; sa.ld_yw = h->n_rows_pad; sa.B = B;
+    sa.Sig = b.Sig; sa.ld_sig = h->ld_sig; sa.U = b.U; sa.ld_u = h->pp;
+    const int ksplit = choose_ksplit(h, b.sig_rows, B, sh.bk, sh.warps, nsamp);
+    const long n_ktiles = h->n_rows_pad / sh.bk;
+    sa.kt_per_split = (int)((n_ktiles + ksplit - 1) / ksplit);
+    const int nz = (int)((n_ktiles + sa.kt_per_split - 1) / sa.kt_per_split);
+    const long rows = round_up(B, kSigMaxSamples);
+    sa.split_stride_sig = rows * h->ld_sig;
+    sa.split_stride_u = rows * h->pp;
+    dim3 grid((unsigned)((h->n_units + sh.warps - 1) / sh.warps), (unsigned)((B + nsamp - 1) / nsamp), (unsigned)nz);
     sh.kernel<<<grid, sh.warps * 32, h->sig_smem, st>>>(sa);
+    if (out_args) *out_args = sa;
+    return nz;
 }
 
 // Dynamic shared-memory ceilings are per FUNCTION, not per handle: raise every kernel to the device opt-in
@@ -212,13 +237,13 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         if (timing) { cudaEventRecord(d.ev[3], st); cudaEventRecord(d.ev[4], st); }
     } else {
         SigmaArgs sa;
-        fill_sigma_args(h, d, B, sa);
-        launch_sigma(h, sa, B, st);
+        const int ksplit = launch_sigma(h, d, B, st, &sa);
         if (timing) cudaEventRecord(d.ev[3], st);
         CholArgs ch;
         ch.Sig = b.Sig; ch.ld_sig = h->ld_sig; ch.ld_u = h->pp; ch.Sq = b.Sq; ch.U = b.U; ch.Pext = b.Pext; ch.row = pg.row; ch.p = h->p; ch.pp = h->pp; ch.n_gp = h->n_gp;
         ch.gp = d.gp; ch.gp_data = d.gp_data; ch.partial = b.partial; ch.n_tiles = h->n_tiles; ch.B = B;
         ch.lnprior = d_lnprior; ch.with_prior = with_prior; ch.out = d_out; ch.use_smem = h->chol_smem ? 1 : 0;
+        ch.ksplit = ksplit; ch.split_stride_sig = sa.split_stride_sig; ch.split_stride_u = sa.split_stride_u;
         chol_finish_kernel<<<(unsigned)B, kCholThreads, h->chol_smem_bytes, st>>>(ch);
         if (timing) cudaEventRecord(d.ev[4], st);
         h->launches += 2;
@@ -696,12 +721,16 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
     toa_chain_kernel<<<dim3((unsigned)h->n_tiles, 1), h->chain_threads, chain_smem, d.stream>>>(h->prog, ca);
     SigmaArgs sa;
-    fill_sigma_args(h, d, 1, sa);
-    launch_sigma(h, sa, 1, d.stream);
+    const int ksplit = launch_sigma(h, d, 1, d.stream, &sa);
     h->launches += 3;
-    std::vector<double> S((size_t)h->ld_sig), U(h->pp);
-    cudaMemcpyAsync(S.data(), b.Sig, sizeof(double) * S.size(), cudaMemcpyDeviceToHost, d.stream);
-    cudaMemcpyAsync(U.data(), b.U, sizeof(double) * U.size(), cudaMemcpyDeviceToHost, d.stream);
+    std::vector<double> S((size_t)h->ld_sig, 0.0), U(h->pp, 0.0), tS((size_t)h->ld_sig), tU(h->pp);
+    for (int z = 0; z < ksplit; ++z) {   // sum the split-K slabs in slice order, as K4 does
+        cudaMemcpyAsync(tS.data(), b.Sig + (size_t)z * sa.split_stride_sig, sizeof(double) * tS.size(), cudaMemcpyDeviceToHost, d.stream);
+        cudaMemcpyAsync(tU.data(), b.U + (size_t)z * sa.split_stride_u, sizeof(double) * tU.size(), cudaMemcpyDeviceToHost, d.stream);
+        cudaStreamSynchronize(d.stream);
+        for (size_t i = 0; i < S.size(); ++i) S[i] = z == 0 ? tS[i] : S[i] + tS[i];
+        for (size_t i = 0; i < U.size(); ++i) U[i] = z == 0 ? tU[i] : U[i] + tU[i];
+    }
     cudaError_t e = cudaGetLastError();
     cudaError_t e2 = cudaStreamSynchronize(d.stream);
     if (e == cudaSuccess) e = e2;

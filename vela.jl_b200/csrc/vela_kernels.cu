@@ -261,10 +261,13 @@ __global__ void __launch_bounds__(WARPS * 32, (MT * NT * WARPS <= 128) ? 2 : 1) 
     }
     __syncthreads();
 
-    auto issue = [&](int t) {
+    // split-K: this CTA covers k-tiles [kt0, kt0 + n_ktiles) and writes its own partial Sigma slab
+    const int kt0 = blockIdx.z * a.kt_per_split;
+    const int n_ktiles = min(a.kt_per_split, (int)(a.n_rows_pad / BK) - kt0);
+    auto issue = [&](int t) {   // t: local tile index
         const int s = t % STAGES;
         double* base = smem + (size_t)s * stage_doubles;
-        const long j0 = (long)t * BK;
+        const long j0 = (long)(kt0 + t) * BK;
         for (int c = tid; c < total_chunks; c += kThreads) {
             int r = c / kChunks, ch = c - r * kChunks;
             const double* src;
@@ -307,7 +310,6 @@ __global__ void __launch_bounds__(WARPS * 32, (MT * NT * WARPS <= 128) ? 2 : 1) 
 #pragma unroll
         for (int n = 0; n < NT; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
 
-    const int n_ktiles = (int)(a.n_rows_pad / BK);
     for (int t = 0; t < AHEAD && t < n_ktiles; ++t) issue(t);
 
     for (int kt = 0; kt < n_ktiles; ++kt) {
@@ -359,8 +361,8 @@ __global__ void __launch_bounds__(WARPS * 32, (MT * NT * WARPS <= 128) ? 2 : 1) 
             for (int r = 0; r < 2; ++r) {
                 long b = b0 + n * 8 + 2 * tig + r;
                 if (b < a.B) {
-                    if (is_pair) a.Sig[(size_t)b * a.ld_sig + t] = acc[i][n][r];
-                    else a.U[(size_t)b * a.ld_u + t] = acc[i][n][r];
+                    if (is_pair) a.Sig[(size_t)blockIdx.z * a.split_stride_sig + (size_t)b * a.ld_sig + t] = acc[i][n][r];
+                    else a.U[(size_t)blockIdx.z * a.split_stride_u + (size_t)b * a.ld_u + t] = acc[i][n][r];
                 }
             }
     }
@@ -413,7 +415,11 @@ __global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
         A = z + pp;
         for (int r = 0; r < p; ++r) {
             const double* src = gA + (size_t)r * (r + 1) / 2;
-            for (int c = tid; c <= r; c += nt) A[r * lda + c] = src[c];
+            for (int c = tid; c <= r; c += nt) {
+                double v = src[c];
+                for (int z = 1; z < a.ksplit; ++z) v += src[(size_t)z * a.split_stride_sig + c];
+                A[r * lda + c] = v;
+            }
         }
     } else {
         // large rank: unpack into the square scratch of this walker and factorise there (L2-resident)
@@ -421,7 +427,11 @@ __global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
         A = a.Sq + (size_t)b * pp * pp;
         for (int r = 0; r < p; ++r) {
             const double* src = gA + (size_t)r * (r + 1) / 2;
-            for (int c = tid; c <= r; c += nt) A[r * lda + c] = src[c];
+            for (int c = tid; c <= r; c += nt) {
+                double v = src[c];
+                for (int z = 1; z < a.ksplit; ++z) v += src[(size_t)z * a.split_stride_sig + c];
+                A[r * lda + c] = v;
+            }
         }
     }
     if (tid == 0) sFail = 0;
@@ -445,7 +455,11 @@ __global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
             }
         }
     }
-    for (int i = tid; i < p; i += nt) z[i] = a.U[(size_t)b * a.ld_u + i];
+    for (int i = tid; i < p; i += nt) {
+        double v = a.U[(size_t)b * a.ld_u + i];
+        for (int zz = 1; zz < a.ksplit; ++zz) v += a.U[(size_t)zz * a.split_stride_u + (size_t)b * a.ld_u + i];
+        z[i] = v;
+    }
     __syncthreads();
     double lphi = 0.0;
     for (int i = tid; i < p; i += nt) {

@@ -46,6 +46,9 @@ struct SigmaArgs {
     long ld_sig;
     double* U;                 // [B][ld_u]
     long ld_u;
+    int kt_per_split;          // k-tiles per split-K slice (gridDim.z slices)
+    long split_stride_sig;     // doubles between the Sigma slabs of consecutive slices
+    long split_stride_u;
 };
 
 struct GPDev {
@@ -59,6 +62,9 @@ struct CholArgs {
     long ld_sig;
     long ld_u;
     double* Sq;                // [B][pp][pp] square scratch, only when the matrix does not fit shared memory
+    int ksplit;                // number of split-K slabs to sum
+    long split_stride_sig;
+    long split_stride_u;
     const double* U;
     const double* Pext;
     int row;
