@@ -50,7 +50,7 @@ extern "C" {
 #define VELA_API
 #endif
 
-#define VELA_B200_ABI_VERSION 1
+#define VELA_B200_ABI_VERSION 2
 #define VELA_MAX_PAR 24
 
 typedef enum VelaStatus {
@@ -131,10 +131,13 @@ typedef struct VelaComponentDesc {
     int32_t mask[2];
 } VelaComponentDesc;
 
-/* Likelihood kernels, src/model/kernel.jl:20,74-92. */
+/* Likelihood kernels, src/model/kernel.jl:20-92. */
 typedef enum VelaKernelKind {
     VELA_KERNEL_WHITE = 0,            /* WhiteNoiseKernel */
-    VELA_KERNEL_WOODBURY_WHITE = 2    /* WoodburyKernel{WhiteNoiseKernel} */
+    VELA_KERNEL_ECORR = 1,            /* EcorrKernel: white noise + ECORR, block-diagonal covariance
+                                         (src/likelihood/ecorr_likelihood.jl, ecorr_chi2.jl); narrowband only */
+    VELA_KERNEL_WOODBURY_WHITE = 2,   /* WoodburyKernel{WhiteNoiseKernel} */
+    VELA_KERNEL_WOODBURY_ECORR = 3    /* WoodburyKernel{EcorrKernel} (src/likelihood/gls_ecorr_likelihood.jl) */
 } VelaKernelKind;
 
 /* Amplitude-marginalised Gaussian-process components of a WoodburyKernel. */
@@ -200,6 +203,13 @@ typedef struct VelaModelDesc {
     int64_t basis_ld;             /* leading dimension (column-major, Julia Matrix{Float64}) */
     const double* noise_basis;    /* WoodburyKernel.noise_basis, kernel.jl:77 */
 
+    /* ECORR groups of an EcorrKernel (kernel kinds 1 and 3): the reference's isbits EcorrGroup records
+     * {start, stop, index} as 3 x UInt64 each (src/model/kernel.jl:25-29), 1-based inclusive TOA ranges that
+     * partition the (ECORR-sorted, pyvela/pyvela/ecorr.py:31-75) TOAs; index 0 = no ECORR, else 1-based into ECORR. */
+    int32_t n_ecorr_groups;
+    int32_t par_ecorr;            /* offset of ECORR[1] in the full parameter vector (-1 if none) */
+    const uint64_t* ecorr_groups; /* [n_ecorr_groups][3] */
+
     int32_t n_devices;            /* 0: use the current CUDA device */
     int32_t _pad;
     const int32_t* devices;       /* CUDA device ordinals; walkers are split evenly across them */
@@ -240,7 +250,8 @@ VELA_API int vela_b200_lnpost_batch(VelaHandle h, const double* params, int64_t 
                            int64_t row_stride, int64_t col_stride, const double* lnprior,
                            double* out_lnpost);
 
-/* chi^2 = sum r^2/sigma^2 (+ DM term for wideband); white-noise kernels only. */
+/* chi^2 = sum r^2/sigma^2 (+ DM term for wideband) for white-noise kernels (wls_chi2.jl:44-51), the
+ * ECORR-corrected chi^2 for EcorrKernel (ecorr_chi2.jl:6-72); not defined for Woodbury kernels. */
 VELA_API int vela_b200_chi2_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
                          int64_t row_stride, int64_t col_stride, double* out_chi2);
 

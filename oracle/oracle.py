@@ -39,7 +39,7 @@ def lib():
         L.oracle_phases.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, dp]
         L.oracle_noise_weights_inv.argtypes = [C.c_void_p, dp, dp]
         L.oracle_sigma.argtypes = [C.c_void_p, dp, dp, dp]
-        L.oracle_gls_lnlike_raw.argtypes = [dp, C.c_int64, C.c_int64, dp, dp, dp]
+        L.oracle_gls_lnlike_raw.argtypes = [dp, C.c_int64, C.c_int64, dp, dp, dp, C.POINTER(C.c_uint64), C.c_int, dp]
         L.oracle_gls_lnlike_raw.restype = C.c_double
         L.oracle_mikkola.argtypes = [C.c_double, C.c_double]
         L.oracle_mikkola.restype = C.c_double
@@ -116,10 +116,18 @@ def sigma(md, params):
     return L + np.tril(S, -1).T, u
 
 
-def gls_lnlike_raw(Mmat, Ninvdiag, Phiinv, y) -> float:
+def gls_lnlike_raw(Mmat, Ninvdiag, Phiinv, y, ecorr_groups=None, ecorr=None) -> float:
+    """_gls_lnlike_serial for a WhiteNoiseKernel, or an EcorrKernel given as (start, stop, index) rows + ECORR values."""
     Mf = np.asfortranarray(Mmat, dtype=np.float64)
     n, p = Mf.shape
-    return float(lib().oracle_gls_lnlike_raw(_dp(Mf), n, p, _dp(_vec(Ninvdiag)), _dp(_vec(Phiinv)), _dp(_vec(y))))
+    if ecorr_groups is None:
+        grp, ng, ec = None, 0, None
+    else:
+        g = np.ascontiguousarray(ecorr_groups, dtype=np.uint64).reshape(-1, 3)
+        grp, ng = g.ctypes.data_as(C.POINTER(C.c_uint64)), len(g)
+        e = _vec(ecorr)
+        ec = _dp(e)
+    return float(lib().oracle_gls_lnlike_raw(_dp(Mf), n, p, _dp(_vec(Ninvdiag)), _dp(_vec(Phiinv)), _dp(_vec(y)), grp, ng, ec))
 
 
 def mikkola(l: float, e: float) -> float:

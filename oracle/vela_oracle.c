@@ -602,6 +602,20 @@ static int resids_and_ninvdiag(const Ctx* ctx, double* y, double* w) {
     return bad;
 }
 
+/* EcorrGroup {start, stop, index}, kernel.jl:25-29 (1-based, inclusive) */
+typedef struct { int64_t start, stop, index; } EGroup;
+static EGroup egroup(const VelaModelDesc* d, int g) {
+    EGroup e = { (int64_t)d->ecorr_groups[3 * g], (int64_t)d->ecorr_groups[3 * g + 1], (int64_t)d->ecorr_groups[3 * g + 2] };
+    return e;
+}
+static double ecorr_weight(const VelaModelDesc* d, const double* P, const EGroup* e) {
+    double ecorr = (e->index == 0) ? 0.0 : P[d->par_ecorr + e->index - 1];
+    return ecorr * ecorr;
+}
+static int has_ecorr(const VelaModelDesc* d) {
+    return d->kernel_kind == VELA_KERNEL_ECORR || d->kernel_kind == VELA_KERNEL_WOODBURY_ECORR;
+}
+
 /* powerlaw gp_noise.jl:12-16 */
 static double powerlaw(double A, double gamma, double f, double f1) {
     double fyr = 1.0 / 3600 / 24 / 365.25;
@@ -634,12 +648,29 @@ static void noise_weights_inv(const Ctx* ctx, double* phiinv) {
 
 /* _calc_Ninv_M gls_likelihood.jl:171-199 + _calc_Sigmainv__and__MT_Ninv_y gls_likelihood.jl:101-169.
  * Sigma is returned as a full column-major p x p with only the upper triangle (q <= p) meaningful. */
-static void sigma_and_u(const VelaModelDesc* d, const double* w, const double* phiinv, const double* y,
+static void sigma_and_u(const VelaModelDesc* d, const double* Pfull, const double* w, const double* phiinv, const double* y,
                         double* NinvM, double* Sig, double* u) {
     int64_t n = d->basis_rows, p = d->basis_cols, ld = d->basis_ld;
     const double* M = d->noise_basis;
-    for (int64_t c = 0; c < p; ++c)
-        for (int64_t j = 0; j < n; ++j) NinvM[c * n + j] = M[c * ld + j] * w[j];
+    if (!has_ecorr(d)) {
+        for (int64_t c = 0; c < p; ++c)
+            for (int64_t j = 0; j < n; ++j) NinvM[c * n + j] = M[c * ld + j] * w[j];
+    } else {
+        /* _calc_Ninv_M(::EcorrKernel, ...) gls_ecorr_likelihood.jl:66-137: per-group Sherman-Morrison */
+        for (int g = 0; g < d->n_ecorr_groups; ++g) {
+            EGroup e = egroup(d, g);
+            double wt = ecorr_weight(d, Pfull, &e);
+            double Q = 0.0;
+            for (int64_t i = e.start - 1; i < e.stop; ++i) Q += w[i];
+            double alpha = wt / (1 + wt * Q);
+            for (int64_t c = 0; c < p; ++c) {
+                double Pp = 0.0;
+                for (int64_t i = e.start - 1; i < e.stop; ++i) Pp += M[c * ld + i] * w[i];
+                double R = Pp * alpha;
+                for (int64_t i = e.start - 1; i < e.stop; ++i) NinvM[c * n + i] = (M[c * ld + i] - R) * w[i];
+            }
+        }
+    }
     for (int64_t c = 0; c < p; ++c)
         for (int64_t q = 0; q <= c; ++q) {
             double s = (c == q) ? phiinv[c] : 0.0;
@@ -675,15 +706,35 @@ static int chol_upper(double* A, int64_t p) {
 }
 
 /* _gls_lnlike_serial gls_likelihood.jl:201-226 */
-static double gls_lnlike(const VelaModelDesc* d, const double* w, const double* phiinv, const double* y,
+static double gls_lnlike(const VelaModelDesc* d, const double* Pfull, const double* w, const double* phiinv, const double* y,
                          double* NinvM, double* Sig, double* u) {
     int64_t n = d->basis_rows, p = d->basis_cols;
-    sigma_and_u(d, w, phiinv, y, NinvM, Sig, u);
-    /* _calc_y_Ninv_y__and__logdet_N gls_likelihood.jl:81-99 */
+    sigma_and_u(d, Pfull, w, phiinv, y, NinvM, Sig, u);
     double yNy = 0.0, logdetN = 0.0;
-    for (int64_t j = 0; j < n; ++j) yNy += y[j] * y[j] * w[j];
-    for (int64_t j = 0; j < n; ++j) logdetN += log(w[j]);
-    logdetN = -logdetN;
+    if (!has_ecorr(d)) {
+        /* _calc_y_Ninv_y__and__logdet_N gls_likelihood.jl:81-99 */
+        for (int64_t j = 0; j < n; ++j) yNy += y[j] * y[j] * w[j];
+        for (int64_t j = 0; j < n; ++j) logdetN += log(w[j]);
+        logdetN = -logdetN;
+    } else {
+        /* _calc_y_Ninv_y__and__logdet_N(::EcorrKernel, ...) gls_ecorr_likelihood.jl:1-64 (serial branch) */
+        for (int g = 0; g < d->n_ecorr_groups; ++g) {
+            EGroup e = egroup(d, g);
+            double wt = ecorr_weight(d, Pfull, &e);
+            double r_r = 0.0, r_u = 0.0, u_u = 0.0, ldn = 0.0;
+            for (int64_t ii = e.start - 1; ii < e.stop; ++ii) {
+                double Ninv_ii = w[ii];
+                double r_u_ii = y[ii] * Ninv_ii;
+                r_r += y[ii] * r_u_ii;
+                r_u += r_u_ii;
+                u_u += Ninv_ii;
+                ldn -= log(w[ii]);
+            }
+            double denom = 1 + wt * u_u;
+            yNy += r_r - wt * r_u * r_u / denom;
+            logdetN += ldn + log(denom);
+        }
+    }
     if (!chol_upper(Sig, p)) return -INFINITY;
     double logdetS = 0.0;
     for (int64_t j = 0; j < p; ++j) logdetS += log(Sig[j * p + j]);
@@ -702,10 +753,37 @@ static double gls_lnlike(const VelaModelDesc* d, const double* w, const double* 
     return -0.5 * (yNy - zz + logdetN + logdetPhi + logdetS);
 }
 
+/* _ecorr_lnlike_group ecorr_likelihood.jl:8-38 / _ecorr_chi2_group ecorr_chi2.jl:6-30, summed over groups
+ * (calc_lnlike_serial ecorr_likelihood.jl:62-76, calc_chi2_serial ecorr_chi2.jl:58-72) */
+static double ecorr_white_sum(const Ctx* ctx, int chi2_only, int* bad) {
+    const VelaModelDesc* d = ctx->d;
+    dd tzr = calc_tzr_phase(ctx, bad);
+    double total = 0.0;
+    for (int g = 0; g < d->n_ecorr_groups; ++g) {
+        EGroup e = egroup(d, g);
+        double w = ecorr_weight(d, ctx->P, &e);
+        double r_r = 0.0, r_u = 0.0, u_u = 0.0, norm = 0.0;
+        for (int64_t ii = e.start; ii <= e.stop; ++ii) {
+            Toa toa = toa_view(toa_rec(d, ii - 1), 0);
+            Resid r = form_residual(ctx, &toa, tzr);
+            *bad |= r.bad;
+            r_r += r.tres * r.tres / r.err2;
+            r_u += r.tres / r.err2;
+            u_u += 1 / r.err2;
+            norm += log(r.err2);
+        }
+        double term = r_r - w * r_u * r_u / (1 + w * u_u);
+        if (!chi2_only) term += norm + log(1 + w * u_u);
+        total += term;
+    }
+    return total;
+}
+
 typedef struct { double *P, *y, *w, *phiinv, *NinvM, *Sig, *u; } Work;
 
 static int work_alloc(const VelaModelDesc* d, Work* k) {
-    int64_t n = d->wideband ? 2 * d->n_toas : d->n_toas, p = d->kernel_kind == VELA_KERNEL_WHITE ? 0 : d->basis_cols;
+    int64_t n = d->wideband ? 2 * d->n_toas : d->n_toas;
+    int64_t p = (d->kernel_kind == VELA_KERNEL_WOODBURY_WHITE || d->kernel_kind == VELA_KERNEL_WOODBURY_ECORR) ? d->basis_cols : 0;
     memset(k, 0, sizeof *k);
     k->P = malloc(sizeof(double) * (d->n_params + 1));
     k->y = malloc(sizeof(double) * (n + 1));
@@ -724,6 +802,13 @@ static void work_free(Work* k) {
 static double lnlike_one(const VelaModelDesc* d, Work* k, int chi2_only) {
     Ctx ctx = { d, k->P };
     int64_t n = d->n_toas;
+    if (d->kernel_kind == VELA_KERNEL_ECORR) {
+        int bad = 0;
+        double sum = ecorr_white_sum(&ctx, chi2_only, &bad);
+        double res = chi2_only ? sum : -sum / 2;
+        if (bad || isnan(res)) return chi2_only ? NAN : -INFINITY;
+        return res;
+    }
     if (d->kernel_kind == VELA_KERNEL_WHITE || chi2_only) {
         int bad = 0;
         dd tzr = calc_tzr_phase(&ctx, &bad);
@@ -742,7 +827,7 @@ static double lnlike_one(const VelaModelDesc* d, Work* k, int chi2_only) {
     }
     int bad = resids_and_ninvdiag(&ctx, k->y, k->w);
     noise_weights_inv(&ctx, k->phiinv);
-    double res = gls_lnlike(d, k->w, k->phiinv, k->y, k->NinvM, k->Sig, k->u);
+    double res = gls_lnlike(d, k->P, k->w, k->phiinv, k->y, k->NinvM, k->Sig, k->u);
     if (bad || isnan(res)) return -INFINITY;
     return res;
 }
@@ -832,7 +917,7 @@ ORACLE_API int oracle_sigma(const VelaModelDesc* d, const double* params, double
     Ctx ctx = { d, k.P };
     int bad = resids_and_ninvdiag(&ctx, k.y, k.w);
     noise_weights_inv(&ctx, k.phiinv);
-    sigma_and_u(d, k.w, k.phiinv, k.y, k.NinvM, k.Sig, k.u);
+    sigma_and_u(d, k.P, k.w, k.phiinv, k.y, k.NinvM, k.Sig, k.u);
     int64_t p = d->basis_cols;
     memcpy(Sig, k.Sig, sizeof(double) * p * p);
     memcpy(u, k.u, sizeof(double) * p);
@@ -840,16 +925,19 @@ ORACLE_API int oracle_sigma(const VelaModelDesc* d, const double* params, double
     return bad ? 1 : 0;
 }
 
-/* _gls_lnlike_serial on caller-supplied (M, Ninvdiag, Phiinv, y): test_woodbury_kernel.jl:37-92 */
+/* _gls_lnlike_serial on caller-supplied (M, Ninvdiag, Phiinv, y), optionally with an EcorrKernel given as
+ * groups[ngroups][3] and the ECORR values: test_woodbury_kernel.jl:37-92 (white) and :96-160 (ECORR) */
 ORACLE_API double oracle_gls_lnlike_raw(const double* M, int64_t n, int64_t p, const double* w, const double* phiinv,
-                                        const double* y) {
+                                        const double* y, const uint64_t* groups, int ngroups, const double* ecorr) {
     VelaModelDesc d;
     memset(&d, 0, sizeof d);
     d.basis_rows = n; d.basis_cols = p; d.basis_ld = n; d.noise_basis = M;
+    d.kernel_kind = ngroups > 0 ? VELA_KERNEL_WOODBURY_ECORR : VELA_KERNEL_WOODBURY_WHITE;
+    d.n_ecorr_groups = ngroups; d.ecorr_groups = groups; d.par_ecorr = 0;
     double* NinvM = malloc(sizeof(double) * (n * p + 1));
     double* Sig = malloc(sizeof(double) * (p * p + 1));
     double* u = malloc(sizeof(double) * (p + 1));
-    double r = gls_lnlike(&d, w, phiinv, y, NinvM, Sig, u);
+    double r = gls_lnlike(&d, ecorr, w, phiinv, y, NinvM, Sig, u);
     free(NinvM); free(Sig); free(u);
     return r;
 }

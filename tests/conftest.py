@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from __graft_entry__ import load_package  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GOLDEN_NAMES = ["NGC6440E", "sim_sw_wb", "sim3_gp", "sim_dmgp_wb"]
+GOLDEN_NAMES = ["NGC6440E", "sim_sw_wb", "sim3_gp", "sim_dmgp_wb", "sim2"]
 
 
 def pytest_configure(config):

@@ -22,7 +22,7 @@ vb = load_package()
 import oracle as O  # noqa: E402
 
 REF = "/root/reference/test/datafiles"
-FIXTURES = ["NGC6440E", "sim_sw.wb", "sim3.gp", "sim_dmgp_wb"]
+FIXTURES = ["NGC6440E", "sim_sw.wb", "sim3.gp", "sim_dmgp_wb", "sim2"]
 
 
 def walkers(model, n, seed):
@@ -53,7 +53,7 @@ def main():
         extra = {
             "source": f"test/datafiles/{name}.jlso",
             "lnlike_default": O.lnlike(md, x0),
-            "chi2_default": O.chi2(md, x0) if md.desc.kernel_kind == 0 else None,
+            "chi2_default": O.chi2(md, x0) if md.desc.kernel_kind in (0, 1) else None,
         }
         out = os.path.join(ROOT, "tests", "golden", name.replace(".", "_") + ".npz")
         vb.readwrite.save_pulsar_npz(out, model, toas, extra)

@@ -59,10 +59,16 @@ def test_noise_weights_inv(name, golden, pulsars, oracle):
     np.testing.assert_allclose(psr.noise_weights_inv(g.x0), oracle.noise_weights_inv(g.md, g.x0), rtol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["NGC6440E", "sim_sw_wb"])
+@pytest.mark.parametrize("name", ["NGC6440E", "sim_sw_wb", "sim2"])
 def test_chi2(name, golden, pulsars, oracle):
     g, psr = golden(name), pulsars(name)
     np.testing.assert_allclose(psr.chi2(g.x0), oracle.chi2(g.md, g.x0), rtol=1e-9)
+
+
+def test_sim2_pint_chi2_with_ecorr(golden, pulsars):
+    """PINT's GLS chi^2 for the ECORR dataset: CHI2 1999.9595 (pyvela/examples/sim2.par:17)."""
+    g, psr = golden("sim2"), pulsars("sim2")
+    assert abs(psr.chi2(g.x0) - 1999.9595338710205) < 0.02
 
 
 def test_ngc6440e_pint_chi2(golden, pulsars):

@@ -97,13 +97,34 @@ def test_descriptor_offsets(vb, golden):
     assert [g3.gp[i].kind for i in range(3)] == [D.GP_POWERLAW_RED, D.GP_POWERLAW_DM, D.GP_POWERLAW_CHROM]
 
 
-def test_ecorr_kernel_is_rejected_not_silently_ignored(vb, golden):
-    g = golden("NGC6440E")
+def test_unsupported_kernels_are_rejected_not_silently_ignored(vb, golden):
+    """WoodburyKernel{EcorrKernel} is a 'next' row: create() must refuse it (VELA_ERR_UNSUPPORTED), never ignore ECORR."""
+    g = golden("sim2")
+    M = vb.model
+    basis = np.ones((len(g.toas), 2))
+    kernel = M.WoodburyKernel(g.model.kernel, [M.MarginalizedTimingModel(weights=[1e40, 1e40], pnames=["PHOFF", "F0"])], basis)
+    m2 = M.TimingModel(g.model.pulsar_name, g.model.ephem, g.model.clock, g.model.units, g.model.epoch,
+                       g.model.components, kernel, g.model.param_handler, g.model.tzr_toa, g.model.priors)
+    md = vb.ModelDescriptor(m2, g.toas)
+    assert md.desc.kernel_kind == vb.descriptor.KERNEL_WOODBURY_ECORR
+    h = ctypes.c_void_p()
+    L = vb.lib.lib()
+    assert L.vela_b200_create(md.byref(), ctypes.byref(h)) == -4
+    assert b"EcorrKernel" in L.vela_b200_last_error()
+
+
+def test_ecorr_descriptor(vb, golden):
+    g = golden("sim2")
+    d = g.md.desc
+    assert d.kernel_kind == vb.descriptor.KERNEL_ECORR and d.n_ecorr_groups == 250
+    assert [d.ecorr_groups[i] for i in range(6)] == [1, 8, 1, 9, 16, 1]
+    assert d.par_ecorr == g.model.param_handler.offset("ECORR")
+    bad = g.model.kernel.ecorr_groups.copy()
+    bad[3, 0] += 1                     # hole in the TOA partition
     M = vb.model
     m2 = M.TimingModel(g.model.pulsar_name, g.model.ephem, g.model.clock, g.model.units, g.model.epoch,
-                       g.model.components, M.EcorrKernel(np.zeros((0, 3), dtype=np.uint64)), g.model.param_handler,
-                       g.model.tzr_toa, g.model.priors)
-    with pytest.raises(NotImplementedError, match="ECORR"):
+                       g.model.components, M.EcorrKernel(bad), g.model.param_handler, g.model.tzr_toa, g.model.priors)
+    with pytest.raises(ValueError, match="partition"):
         vb.ModelDescriptor(m2, g.toas)
 
 

@@ -21,6 +21,7 @@ def test_load_pulsar_data(name, ntoa, words, kernel, vb):
     assert model.tzr_toa.index == 0
     assert len(model.priors) == model.param_handler._nfree           # timing_model.jl:40
     assert np.isfinite(vb.priors.lnprior(model.priors, model.read_param_values_to_vector()))
+    vb.ModelDescriptor(model, toas)      # every reference fixture maps onto the C-ABI descriptor
 
 
 def test_golden_npz_is_the_jlso_content(vb, golden):

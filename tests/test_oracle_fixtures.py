@@ -101,6 +101,46 @@ def test_woodbury_equals_dense_gaussian(golden, oracle):
     np.testing.assert_allclose(oracle.lnlike(g.md, g.x0), dense, rtol=1e-8)
 
 
+def test_sim2_ecorr_bounds(golden, oracle):
+    """EcorrKernel dataset: test/test_sim2.jl:87-136 and PINT's CHI2 1999.9595 (pyvela/examples/sim2.par:17-18)."""
+    g = golden("sim2")
+    assert len(g.toas) == 2000 and type(g.model.kernel).__name__ == "EcorrKernel"
+    assert set(g.model.get_free_param_names()) == {"RAJ", "DECJ", "PHOFF", "F0", "F1", "EFAC1", "ECORR1"}
+    y, w = oracle.residuals(g.md, g.x0)
+    assert np.all(np.abs(y) < 7 * g.toas.error)                           # test_sim2.jl:106-110
+    chi2 = oracle.chi2(g.md, g.x0)
+    assert chi2 / (len(g.toas) - len(g.x0)) < 1.2                         # test_sim2.jl:119
+    assert abs(chi2 - 1999.9595338710205) < 0.02                          # PINT's GLS chi^2 incl. ECORR
+    p1 = g.x0.copy()
+    p1[-1] *= 2                                                           # test_sim2.jl:133-135
+    assert oracle.lnlike(g.md, p1) < oracle.lnlike(g.md, g.x0)
+
+
+def test_ecorr_likelihood_equals_dense_gaussian(golden, oracle):
+    """White + ECORR ln L = -1/2 (r^T C^-1 r + log det C), C = N + U diag(ECORR^2) U^T (Johnson+ 2024), on sim2."""
+    g = golden("sim2")
+    y, w = oracle.residuals(g.md, g.x0)
+    ecorr = g.model.read_params(g.x0)[g.model.param_handler.offset("ECORR")]
+    total = 0.0
+    for start, stop, idx in g.model.kernel.ecorr_groups:
+        sl = slice(int(start) - 1, int(stop))
+        n = sl.stop - sl.start
+        C = np.diag(1 / w[sl]) + (ecorr**2 if idx else 0.0) * np.ones((n, n))
+        total += y[sl] @ np.linalg.solve(C, y[sl]) + np.linalg.slogdet(C)[1]
+    np.testing.assert_allclose(oracle.lnlike(g.md, g.x0), -0.5 * total, rtol=1e-10)
+
+
+def test_gls_ecorr_identity(oracle):
+    """test/test_woodbury_kernel.jl:96-160: WoodburyKernel{EcorrKernel} == dense Gaussian with C = Nc + M Phi M^T."""
+    rng = np.random.default_rng(3)
+    y, Nd, M, Ph = rng.standard_normal(9), 1 + rng.random(9), rng.standard_normal((9, 5)), 1 + rng.random(5)
+    groups, ec = [[1, 3, 1], [4, 6, 2], [7, 9, 3]], np.array([0.5, 1.1, 0.9])
+    U = np.kron(np.eye(3), np.ones((1, 3)))
+    C = np.diag(Nd) + U.T @ np.diag(ec**2) @ U + M @ np.diag(1 / Ph) @ M.T
+    want = -0.5 * (y @ np.linalg.solve(C, y) + np.linalg.slogdet(C)[1])
+    assert oracle.gls_lnlike_raw(M, 1 / Nd, Ph, y, groups, ec) == pytest.approx(want, rel=1e-12)
+
+
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_oracle_matches_recorded_numbers(name, golden, oracle):
     """Regression pin: the numbers stored in the fixture by make_golden.py."""

@@ -73,6 +73,8 @@ struct DeviceModel {
     long ldM = 0;
     GPDev* gp = nullptr;
     double* gp_data = nullptr;
+    int3* ecorr_groups = nullptr;
+    int* ecorr_chunks = nullptr;
     Buffers buf;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[5] = {0, 0, 0, 0, 0};
@@ -89,6 +91,7 @@ struct VelaPulsar {
     int sig_shape = 0;
     size_t sig_smem = 0;
     int chain_threads = 256, chain_group = 32, n_tiles = 0;
+    int n_ecorr_groups = 0, n_ecorr_chunks = 0, par_ecorr = -1;   // EcorrKernel: group corrections occupy partial rows n_tiles..
     bool chol_smem = true;
     size_t chol_smem_bytes = 0;
     std::vector<DeviceModel> devs;
@@ -117,15 +120,17 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
     CU(cudaMalloc((void**)&b.params, (size_t)cap * std::max(pg.n_free, 1) * sizeof(double)));
     CU(cudaMalloc((void**)&b.Pext, (size_t)cap * pg.row * sizeof(double)));
     CU(cudaMalloc((void**)&b.tzr, (size_t)cap * 2 * sizeof(double)));
-    CU(cudaMalloc((void**)&b.partial, (size_t)h->n_tiles * cap * 2 * sizeof(double)));
+    CU(cudaMalloc((void**)&b.partial, (size_t)(h->n_tiles + h->n_ecorr_chunks) * cap * 2 * sizeof(double)));
     CU(cudaMalloc((void**)&b.out, (size_t)cap * sizeof(double)));
     CU(cudaMalloc((void**)&b.lnprior, (size_t)cap * sizeof(double)));
-    if (h->kernel_kind != VELA_KERNEL_WHITE) {
+    if (h->kernel_kind != VELA_KERNEL_WHITE) {   // every kernel but the plain white one needs y, w
         size_t yw = (size_t)cap * h->n_rows_pad * sizeof(double);
         CU(cudaMalloc((void**)&b.Y, yw));
         CU(cudaMalloc((void**)&b.W, yw));
         CU(cudaMemsetAsync(b.Y, 0, yw, d.stream));
         CU(cudaMemsetAsync(b.W, 0, yw, d.stream));
+    }
+    if (h->p > 0) {
         // Sigma / U scratch: at least `cap` walker rows, and never fewer than kSplitRows so that small batches can
         // hold several split-K slabs
         b.sig_rows = std::max<long>(cap, kSplitRows);
@@ -219,19 +224,29 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
                                                                          d.tzr_block, d.index_masks, d.bit_masks,
                                                                          h->n_toas, b.Pext, b.tzr);
     if (timing) cudaEventRecord(d.ev[1], st);
-    const bool woodbury = h->kernel_kind != VELA_KERNEL_WHITE && mode == 0;
+    const bool woodbury = h->p > 0 && mode == 0;
+    const bool ecorr = h->n_ecorr_groups > 0;
     ChainArgs ca;
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = B; ca.group = h->chain_group;
-    ca.emit = woodbury ? 1 : 0; ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
+    ca.emit = (woodbury || ecorr) ? 1 : 0; ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     const int warps = h->chain_threads / 32;
     size_t chain_smem = ((size_t)h->chain_group * pg.row + 2 * h->chain_group + (size_t)warps * h->chain_group * 2) * sizeof(double);
     dim3 cgrid((unsigned)h->n_tiles, (unsigned)((B + h->chain_group - 1) / h->chain_group));
     toa_chain_kernel<<<cgrid, h->chain_threads, chain_smem, st>>>(pg, ca);
-    if (timing) cudaEventRecord(d.ev[2], st);
     h->launches += 2;
+    if (ecorr) {
+        EcorrArgs ea;
+        ea.Pext = b.Pext; ea.row = pg.row; ea.Y = b.Y; ea.W = b.W; ea.ld_yw = h->n_rows_pad; ea.B = B;
+        ea.groups = d.ecorr_groups; ea.chunk_start = d.ecorr_chunks; ea.par_ecorr = h->par_ecorr;
+        ea.first_row = h->n_tiles; ea.partial = b.partial;
+        ecorr_group_kernel<<<dim3((unsigned)((B + 127) / 128), (unsigned)h->n_ecorr_chunks), 128, 0, st>>>(ea);
+        h->launches += 1;
+    }
+    if (timing) cudaEventRecord(d.ev[2], st);
+    const int n_rows_partial = h->n_tiles + h->n_ecorr_chunks;
     if (!woodbury) {
-        finish_white_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(b.partial, h->n_tiles, B, mode, d_lnprior,
+        finish_white_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(b.partial, n_rows_partial, B, mode, d_lnprior,
                                                                          with_prior, d_out);
         h->launches += 1;
         if (timing) { cudaEventRecord(d.ev[3], st); cudaEventRecord(d.ev[4], st); }
@@ -241,7 +256,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         if (timing) cudaEventRecord(d.ev[3], st);
         CholArgs ch;
         ch.Sig = b.Sig; ch.ld_sig = h->ld_sig; ch.ld_u = h->pp; ch.Sq = b.Sq; ch.U = b.U; ch.Pext = b.Pext; ch.row = pg.row; ch.p = h->p; ch.pp = h->pp; ch.n_gp = h->n_gp;
-        ch.gp = d.gp; ch.gp_data = d.gp_data; ch.partial = b.partial; ch.n_tiles = h->n_tiles; ch.B = B;
+        ch.gp = d.gp; ch.gp_data = d.gp_data; ch.partial = b.partial; ch.n_tiles = n_rows_partial; ch.B = B;
         ch.lnprior = d_lnprior; ch.with_prior = with_prior; ch.out = d_out; ch.use_smem = h->chol_smem ? 1 : 0;
         ch.ksplit = ksplit; ch.split_stride_sig = sa.split_stride_sig; ch.split_stride_u = sa.split_stride_u;
         chol_finish_kernel<<<(unsigned)B, kCholThreads, h->chol_smem_bytes, st>>>(ch);
@@ -255,7 +270,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
 
 int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const std::vector<double>& toa_soa,
                  const std::vector<double>& tzr_block, const std::vector<GPDev>& gps,
-                 const std::vector<double>& gp_data) {
+                 const std::vector<double>& gp_data, const std::vector<int3>& egroups, const std::vector<int>& echunks) {
     CU(cudaSetDevice(d.dev));
     CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     for (auto& e : d.ev) CU(cudaEventCreate(&e));
@@ -265,7 +280,11 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
     if (upload(&d.bit_masks, desc->bit_masks, (size_t)desc->n_bit_mask_rows * desc->n_toas)) return VELA_ERR_CUDA;
     if (upload(&d.defaults, desc->default_values, (size_t)desc->n_params)) return VELA_ERR_CUDA;
     if (upload(&d.free_idx, desc->free_indices, (size_t)desc->n_free)) return VELA_ERR_CUDA;
-    if (h->kernel_kind != VELA_KERNEL_WHITE) {
+    if (!egroups.empty()) {
+        if (upload(&d.ecorr_groups, egroups.data(), egroups.size())) return VELA_ERR_CUDA;
+        if (upload(&d.ecorr_chunks, echunks.data(), echunks.size())) return VELA_ERR_CUDA;
+    }
+    if (h->p > 0) {
         // M: column-major with the leading dimension padded (zero rows) to n_rows_pad, columns padded to pp
         d.ldM = h->n_rows_pad;
         std::vector<double> Mp((size_t)d.ldM * h->p, 0.0);
@@ -287,7 +306,7 @@ void destroy_device(DeviceModel& d) {
     if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
     if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
-    cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data);
+    cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
 }
@@ -335,7 +354,20 @@ int validate(const VelaModelDesc* d) {
             if (bits ? (c.mask[m] + c.len[0] > d->n_bit_mask_rows) : (c.mask[m] >= d->n_index_masks)) return fail(VELA_ERR_INVALID_ARG, "component %d: mask %d out of range", ic, c.mask[m]);
         }
     }
-    if (d->kernel_kind != VELA_KERNEL_WHITE && d->kernel_kind != VELA_KERNEL_WOODBURY_WHITE) return fail(VELA_ERR_UNSUPPORTED, "kernel kind %d is outside the implemented hot path", d->kernel_kind);
+    if (d->kernel_kind == VELA_KERNEL_WOODBURY_ECORR) return fail(VELA_ERR_UNSUPPORTED, "WoodburyKernel{EcorrKernel} is not on the GPU path yet (next row, DESIGN.md section 8)");
+    if (d->kernel_kind != VELA_KERNEL_WHITE && d->kernel_kind != VELA_KERNEL_WOODBURY_WHITE && d->kernel_kind != VELA_KERNEL_ECORR) return fail(VELA_ERR_UNSUPPORTED, "kernel kind %d is outside the implemented hot path", d->kernel_kind);
+    if (d->kernel_kind == VELA_KERNEL_ECORR) {
+        if (d->wideband) return fail(VELA_ERR_INVALID_ARG, "ECORR kernels are narrowband only");
+        if (d->n_ecorr_groups <= 0 || !d->ecorr_groups) return fail(VELA_ERR_INVALID_ARG, "EcorrKernel without groups");
+        uint64_t next = 1;
+        for (int g = 0; g < d->n_ecorr_groups; ++g) {
+            const uint64_t* e = d->ecorr_groups + 3 * g;
+            if (e[0] != next || e[1] < e[0] || e[1] > (uint64_t)d->n_toas) return fail(VELA_ERR_INVALID_ARG, "ECORR group %d does not continue the TOA partition", g);
+            if (e[2] != 0 && (d->par_ecorr < 0 || d->par_ecorr + (int64_t)e[2] > d->n_params)) return fail(VELA_ERR_INVALID_ARG, "ECORR group %d: bad ECORR index", g);
+            next = e[1] + 1;
+        }
+        if (next != (uint64_t)d->n_toas + 1) return fail(VELA_ERR_INVALID_ARG, "ECORR groups do not cover all TOAs");
+    }
     if (d->kernel_kind == VELA_KERNEL_WOODBURY_WHITE) {
         long nr = d->wideband ? 2 * d->n_toas : d->n_toas;
         if (d->basis_rows != nr || d->basis_cols <= 0 || d->basis_ld < nr || !d->noise_basis) return fail(VELA_ERR_INVALID_ARG, "noise_basis shape (%ld x %ld, ld %ld) does not match %ld rows", (long)d->basis_rows, (long)d->basis_cols, (long)d->basis_ld, nr);
@@ -396,9 +428,26 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     h->n_tiles = (int)((desc->n_toas + h->chain_threads - 1) / h->chain_threads);
     h->chain_group = 32;
 
+    std::vector<int3> egroups;
+    std::vector<int> echunks;
+    if (desc->kernel_kind == VELA_KERNEL_ECORR) {
+        // groups without ECORR (index 0) need no correction; the others are packed into chunks of ~64 TOAs per thread
+        h->par_ecorr = desc->par_ecorr;
+        echunks.push_back(0);
+        long in_chunk = 0;
+        for (int g = 0; g < desc->n_ecorr_groups; ++g) {
+            const uint64_t* e = desc->ecorr_groups + 3 * g;
+            egroups.push_back(make_int3((int)(e[0] - 1), (int)e[1], (int)e[2]));
+            in_chunk += e[2] ? (long)(e[1] - e[0] + 1) : 0;
+            if (in_chunk >= 64) { echunks.push_back(g + 1); in_chunk = 0; }
+        }
+        if (echunks.back() != desc->n_ecorr_groups) echunks.push_back(desc->n_ecorr_groups);
+        h->n_ecorr_groups = desc->n_ecorr_groups;
+        h->n_ecorr_chunks = (int)echunks.size() - 1;
+    }
     std::vector<GPDev> gps;
     std::vector<double> gp_data;
-    if (desc->kernel_kind != VELA_KERNEL_WHITE) {
+    if (desc->kernel_kind == VELA_KERNEL_WOODBURY_WHITE) {
         h->p = (int)desc->basis_cols;
         h->pp = (h->p + 7) / 8 * 8;
         h->n_gp = desc->n_gp;
@@ -469,7 +518,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     for (size_t i = 0; i < devices.size(); ++i) {
         h->devs[i].dev = devices[i];
         h->devs[i].toa_stride = stride;
-        int rc = build_device(h, h->devs[i], desc, soa, tzr, gps, gp_data);
+        int rc = build_device(h, h->devs[i], desc, soa, tzr, gps, gp_data, egroups, echunks);
         if (rc) {
             for (auto& d : h->devs) destroy_device(d);
             delete h;
@@ -516,7 +565,7 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
     if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
     if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d free parameters, got %ld (parameter.jl:162)", h->prog.n_free, (long)n_free);
     if (B < 0 || (B > 0 && (!params || !out))) return fail(VELA_ERR_INVALID_ARG, "null params/out");
-    if (mode == 1 && h->kernel_kind != VELA_KERNEL_WHITE) return fail(VELA_ERR_UNSUPPORTED, "chi2 is defined for white-noise kernels only (wls_chi2.jl:44)");
+    if (mode == 1 && h->p > 0) return fail(VELA_ERR_UNSUPPORTED, "chi2 is defined for white-noise and ECORR kernels only (wls_chi2.jl:44, ecorr_chi2.jl:58)");
     if (B == 0) return VELA_OK;
     std::lock_guard<std::mutex> lock(h->mtx);
     int prev = 0;
@@ -665,7 +714,7 @@ VELA_API int vela_b200_phases(VelaHandle h, const double* params, int64_t n_free
 
 VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int64_t n_free, double* phiinv) {
     if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
-    if (h->kernel_kind == VELA_KERNEL_WHITE) return fail(VELA_ERR_UNSUPPORTED, "white-noise kernel has no Phi");
+    if (h->p == 0) return fail(VELA_ERR_UNSUPPORTED, "this kernel has no Phi");
     if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d free parameters, got %ld", h->prog.n_free, (long)n_free);
     std::lock_guard<std::mutex> lock(h->mtx);
     DeviceModel& d = h->devs[0];
@@ -699,7 +748,7 @@ VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int
 // Sigma^-1 = diag(Phi^-1) + M^T N^-1 M as a full symmetric column-major p x p matrix, u = M^T N^-1 y.
 VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n_free, double* Sigma, double* u) {
     if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
-    if (h->kernel_kind == VELA_KERNEL_WHITE) return fail(VELA_ERR_UNSUPPORTED, "white-noise kernel has no Sigma");
+    if (h->p == 0) return fail(VELA_ERR_UNSUPPORTED, "this kernel has no Sigma");
     if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d free parameters, got %ld", h->prog.n_free, (long)n_free);
     std::vector<double> phi(h->p);
     if (int rc = vela_b200_noise_weights_inv(h, params, n_free, phi.data())) return rc;

@@ -172,6 +172,41 @@ __global__ void finish_white_kernel(const double* __restrict__ partial, int n_ti
 }
 
 // ------------------------------------------------------------------------------------------
+// K2  ECORR group corrections (EcorrKernel)
+// ------------------------------------------------------------------------------------------
+// _ecorr_lnlike_group / _ecorr_chi2_group (ecorr_likelihood.jl:8-38, ecorr_chi2.jl:6-30): with r_u = sum_g y w,
+// u_u = sum_g w over the TOAs of an ECORR group and W = ECORR^2, the block-diagonal covariance adds
+//   chi^2   -= W r_u^2 / (1 + W u_u),      log det += log(1 + W u_u)
+// to the white-noise sums the chain kernel already produced.  One thread = one walker x one chunk of consecutive
+// groups; the two corrections are written as extra rows of `partial`, so the finishing kernels need no change.
+__global__ void __launch_bounds__(128) ecorr_group_kernel(EcorrArgs a) {
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int c = blockIdx.y;
+    const double* P = a.Pext + (size_t)b * a.row;
+    const double* y = a.Y + (size_t)b * a.ld_yw;
+    const double* w = a.W + (size_t)b * a.ld_yw;
+    double dchi = 0.0, dlg = 0.0;
+    for (int g = a.chunk_start[c]; g < a.chunk_start[c + 1]; ++g) {
+        const int3 grp = a.groups[g];          // first TOA (0-based), one-past-last TOA, ECORR index (0 = none)
+        if (grp.z == 0) continue;
+        const double ecorr = P[a.par_ecorr + grp.z - 1];
+        const double wt = ecorr * ecorr;
+        double r_u = 0.0, u_u = 0.0;
+        for (int j = grp.x; j < grp.y; ++j) {
+            const double wj = w[j];
+            r_u += y[j] * wj;
+            u_u += wj;
+        }
+        const double denom = 1 + wt * u_u;
+        dchi -= wt * r_u * r_u / denom;
+        dlg += log(denom);
+    }
+    a.partial[((size_t)(a.first_row + c) * a.B + b) * 2] = dchi;
+    a.partial[((size_t)(a.first_row + c) * a.B + b) * 2 + 1] = dlg;
+}
+
+// ------------------------------------------------------------------------------------------
 // K3  Sigma^-1 contraction on the FP64 tensor cores
 // ------------------------------------------------------------------------------------------
 // _calc_Ninv_M + _calc_Sigmainv__and__MT_Ninv_y (gls_likelihood.jl:101-199), restructured as one

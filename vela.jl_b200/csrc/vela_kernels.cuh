@@ -51,6 +51,20 @@ struct SigmaArgs {
     long split_stride_u;
 };
 
+struct EcorrArgs {
+    const double* Pext;
+    int row;
+    const double* Y;
+    const double* W;
+    long ld_yw;
+    long B;
+    const int3* groups;        // [n_groups] (first TOA 0-based, one past last, ECORR index)
+    const int* chunk_start;    // [n_chunks + 1] group ranges handled by one thread
+    int par_ecorr;
+    int first_row;             // first `partial` row owned by the ECORR corrections (= number of TOA tiles)
+    double* partial;
+};
+
 struct GPDev {
     int kind, n, par_log10_amp, par_gamma, par_f1;
     int col0;                  // first basis column of this GP component
@@ -86,6 +100,7 @@ __global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, 
                                        const uint32_t* index_masks, const uint8_t* bit_masks, long n_toas,
                                        double* Pext, double* tzr_phase);
 __global__ void toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a);
+__global__ void ecorr_group_kernel(EcorrArgs a);
 __global__ void finish_white_kernel(const double* partial, int n_tiles, long B, int mode, const double* lnprior,
                                     int with_prior, double* out);
 template <int BK, int STAGES, int MT, int NT, int WARPS>

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import model as M
 
-VELA_B200_ABI_VERSION = 1
+VELA_B200_ABI_VERSION = 2
 VELA_MAX_PAR = 24
 
 # VelaComponentKind
@@ -23,7 +23,7 @@ VELA_MAX_PAR = 24
  COMP_EXP_DIP, COMP_SPINDOWN, COMP_PHASE_OFFSET, COMP_PHASE_JUMP_EXCLUSIVE, COMP_PHASE_JUMP,
  COMP_MEASUREMENT_NOISE, COMP_DM_JUMP_EXCLUSIVE, COMP_DM_JUMP, COMP_DM_MEASUREMENT_NOISE) = range(1, 19)
 FLAG_ECLIPTIC, FLAG_PLANET_SHAPIRO, FLAG_USE_FBX = 1, 2, 4
-KERNEL_WHITE, KERNEL_WOODBURY_WHITE = 0, 2
+KERNEL_WHITE, KERNEL_ECORR, KERNEL_WOODBURY_WHITE, KERNEL_WOODBURY_ECORR = 0, 1, 2, 3
 GP_POWERLAW_RED, GP_POWERLAW_DM, GP_POWERLAW_CHROM, GP_MARGINALIZED_TM = 1, 2, 3, 4
 
 
@@ -51,6 +51,7 @@ class VelaModelDesc(C.Structure):
         ("kernel_kind", C.c_int32), ("n_gp", C.c_int32), ("gp", C.POINTER(VelaGPDesc)),
         ("basis_rows", C.c_int64), ("basis_cols", C.c_int64), ("basis_ld", C.c_int64),
         ("noise_basis", C.POINTER(C.c_double)),
+        ("n_ecorr_groups", C.c_int32), ("par_ecorr", C.c_int32), ("ecorr_groups", C.POINTER(C.c_uint64)),
         ("n_devices", C.c_int32), ("_pad", C.c_int32), ("devices", C.POINTER(C.c_int32)),
     ]
 
@@ -236,11 +237,29 @@ class ModelDescriptor:
         d.bit_masks = self._bit_masks.ctypes.data_as(C.POINTER(C.c_uint8))
 
         kernel = model.kernel
-        if isinstance(kernel, M.WhiteNoiseKernel):
-            d.kernel_kind = KERNEL_WHITE
+        inner = kernel.inner_kernel if isinstance(kernel, M.WoodburyKernel) else kernel
+        d.n_ecorr_groups, d.par_ecorr = 0, -1
+        if isinstance(inner, M.EcorrKernel):
+            if toas.wideband:
+                raise ValueError("ECORR kernel is not supported for wideband TOAs (pyvela/pyvela/model.py:470)")
+            grp = np.ascontiguousarray(inner.ecorr_groups, dtype=np.uint64).reshape(-1, 3)
+            if len(grp) == 0 or grp[0, 0] != 1 or grp[-1, 1] != ntoa or np.any(grp[1:, 0] != grp[:-1, 1] + 1):
+                raise ValueError("ECORR groups must partition the TOAs into contiguous 1-based ranges")
+            self._ecorr_groups = grp
+            d.n_ecorr_groups = len(grp)
+            d.ecorr_groups = grp.ctypes.data_as(C.POINTER(C.c_uint64))
+            if grp[:, 2].max() > 0:
+                d.par_ecorr = ph.offset("ECORR")
+                if grp[:, 2].max() > ph.length("ECORR"):
+                    raise ValueError("ECORR group index exceeds the number of ECORR parameters")
+        elif not isinstance(inner, M.WhiteNoiseKernel):
+            raise NotImplementedError(f"kernel {kernel!r} is outside the implemented hot path")
+        ecorr = isinstance(inner, M.EcorrKernel)
+        if not isinstance(kernel, M.WoodburyKernel):
+            d.kernel_kind = KERNEL_ECORR if ecorr else KERNEL_WHITE
             d.n_gp = 0
-        elif isinstance(kernel, M.WoodburyKernel) and isinstance(kernel.inner_kernel, M.WhiteNoiseKernel):
-            d.kernel_kind = KERNEL_WOODBURY_WHITE
+        else:
+            d.kernel_kind = KERNEL_WOODBURY_ECORR if ecorr else KERNEL_WOODBURY_WHITE
             gps = []
             for gp in kernel.gp_components:
                 g = VelaGPDesc()
@@ -272,10 +291,6 @@ class ModelDescriptor:
             d.basis_rows, d.basis_cols = self._basis.shape
             d.basis_ld = self._basis.shape[0]
             d.noise_basis = _dptr(self._basis)
-        else:
-            raise NotImplementedError(
-                f"kernel {kernel!r}: only WhiteNoiseKernel and WoodburyKernel{{WhiteNoiseKernel}} are on the "
-                "implemented hot path (ECORR kernels are a 'next' row)")
 
         if devices:
             self._devices = np.ascontiguousarray(devices, dtype=np.int32)
@@ -291,7 +306,7 @@ class ModelDescriptor:
 
     @property
     def n_basis(self) -> int:
-        return int(self.desc.basis_cols) if self.desc.kernel_kind != KERNEL_WHITE else 0
+        return int(self.desc.basis_cols) if self.desc.kernel_kind in (KERNEL_WOODBURY_WHITE, KERNEL_WOODBURY_ECORR) else 0
 
     def byref(self):
         return C.byref(self.desc)

@@ -13,7 +13,8 @@
 module VelaB200
 
 using ..Vela
-using ..Vela: TimingModel, TOA, WidebandTOA, TOABase, Pulsar, ParamHandler, WhiteNoiseKernel, WoodburyKernel,
+using ..Vela: TimingModel, TOA, WidebandTOA, TOABase, Pulsar, ParamHandler, WhiteNoiseKernel, EcorrKernel, EcorrGroup,
+    WoodburyKernel,
     SolarSystem, SolarWindDispersion, DispersionTaylor, DispersionPiecewise, ChromaticTaylor, ChromaticPiecewise,
     BinaryELL1, BinaryDD, Glitch, ChromaticExponentialDip, Spindown, PhaseOffset, PhaseJump, ExclusivePhaseJump,
     MeasurementNoise, DispersionJump, ExclusiveDispersionJump, DispersionMeasurementNoise, PowerlawRedNoiseGP,
@@ -69,6 +70,9 @@ struct VelaModelDesc
     basis_cols::Int64
     basis_ld::Int64
     noise_basis::Ptr{Float64}
+    n_ecorr_groups::Int32
+    par_ecorr::Int32
+    ecorr_groups::Ptr{UInt64}      # Vector{EcorrGroup} is isbits: 3 x UInt64 per group (kernel.jl:25-29)
     n_devices::Int32
     _pad::Int32
     devices::Ptr{Int32}
@@ -213,10 +217,18 @@ function B200Pulsar(model::TimingModel, toas::Vector{T}; devices::Vector{Int32} 
     gps = VelaGPDesc[]
     keep = Any[]            # arrays the descriptor points into
     basis = Matrix{Float64}(undef, 0, 0)
+    egroups = EcorrGroup[]
+    par_ecorr = Int32(-1)
     kernel_kind = 0
+    inner = kernel isa WoodburyKernel ? kernel.inner_kernel : kernel
+    if inner isa EcorrKernel
+        egroups = inner.ecorr_groups
+        has(b, :ECORR) && (par_ecorr = off(b, :ECORR))
+    elseif !(inner isa WhiteNoiseKernel)
+        error("VelaB200: kernel $(typeof(kernel)) is not on the GPU path yet")
+    end
     if kernel isa WoodburyKernel
-        kernel.inner_kernel isa WhiteNoiseKernel || error("VelaB200: ECORR inner kernels are not on the GPU path yet")
-        kernel_kind = 2
+        kernel_kind = inner isa EcorrKernel ? 3 : 2     # 3 is refused by the library for now (VELA_ERR_UNSUPPORTED)
         basis = kernel.noise_basis
         for gp in kernel.gp_components
             if gp isa MarginalizedTimingModel
@@ -230,17 +242,17 @@ function B200Pulsar(model::TimingModel, toas::Vector{T}; devices::Vector{Int32} 
                 push!(gps, VelaGPDesc(kind, length(lj), off(b, amp), off(b, gam), off(b, frq), 0, pointer(lj), C_NULL))
             end
         end
-    elseif !(kernel isa WhiteNoiseKernel)
-        error("VelaB200: kernel $(typeof(kernel)) is not on the GPU path yet")
+    else
+        kernel_kind = inner isa EcorrKernel ? 1 : 0
     end
 
     handle = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve comps defaults free0 toas tzr index_masks bit_masks gps keep basis devices begin
-        desc = VelaModelDesc(1, length(comps), pointer(comps), length(defaults), length(free0), pointer(defaults),
+    GC.@preserve comps defaults free0 toas tzr index_masks bit_masks gps keep basis egroups devices begin
+        desc = VelaModelDesc(2, length(comps), pointer(comps), length(defaults), length(free0), pointer(defaults),
             pointer(free0), length(toas), wide ? 1 : 0, sizeof(T), pointer(toas), pointer(tzr),
             length(b.index_masks), length(b.bit_rows), pointer(index_masks), pointer(bit_masks), kernel_kind,
             length(gps), pointer(gps), size(basis, 1), size(basis, 2), max(size(basis, 1), 1), pointer(basis),
-            length(devices), 0, pointer(devices))
+            length(egroups), par_ecorr, Ptr{UInt64}(pointer(egroups)), length(devices), 0, pointer(devices))
         check(ccall((:vela_b200_create, LIB), Cint, (Ref{VelaModelDesc}, Ref{Ptr{Cvoid}}), desc, handle), "vela_b200_create")
     end
     psr = B200Pulsar{typeof(model),T}(model, toas, handle[])
