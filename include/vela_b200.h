@@ -82,8 +82,22 @@ typedef enum VelaComponentKind {
     VELA_COMP_MEASUREMENT_NOISE = 15,  /* EFAC/EQUAD, src/model/measurement_noise.jl:20-38 */
     VELA_COMP_DM_JUMP_EXCLUSIVE = 16,  /* ExclusiveDispersionJump, src/model/dmjump.jl:62-86 */
     VELA_COMP_DM_JUMP = 17,            /* DispersionJump (BitMatrix), src/model/dmjump.jl:28-47 */
-    VELA_COMP_DM_MEASUREMENT_NOISE = 18 /* DMEFAC/DMEQUAD, src/model/dispersion_measurement_noise.jl:19-46 */
+    VELA_COMP_DM_MEASUREMENT_NOISE = 18, /* DMEFAC/DMEQUAD, src/model/dispersion_measurement_noise.jl:19-46 */
+    VELA_COMP_BINARY_ELL1H = 19,       /* src/model/binary/binary_ell1h.jl:18-46 */
+    VELA_COMP_BINARY_ELL1K = 20,       /* src/model/binary/binary_ell1k.jl:13-49 */
+    VELA_COMP_BINARY_DDH = 21,         /* src/model/binary/binary_ddh.jl:14-24 */
+    VELA_COMP_BINARY_DDS = 22,         /* src/model/binary/binary_dds.jl:14-23 */
+    VELA_COMP_BINARY_DDK = 23,         /* src/model/binary/binary_ddk.jl:15-120 (Kopeikin corrections) */
+    VELA_COMP_FD = 24,                 /* FrequencyDependent, src/model/frequency_dependent.jl:22-34 */
+    VELA_COMP_FD_JUMP = 25,            /* FrequencyDependentJump, src/model/frequency_dependent.jl:46-81 */
+    VELA_COMP_WAVEX = 26,              /* src/model/wavex.jl:23-62 */
+    VELA_COMP_DM_WAVEX = 27,           /* src/model/wavex.jl:78-87 */
+    VELA_COMP_CM_WAVEX = 28,           /* src/model/wavex.jl:97-106 */
+    VELA_COMP_SOLAR_WIND_PIECEWISE = 29, /* SolarWindDispersionPiecewise (SWX), src/model/solarwind.jl:64-91 */
+    VELA_COMP_DM_OFFSET_EXCLUSIVE = 30,  /* ExclusiveDispersionOffset (FDJUMPDM), src/model/fdjumpdm.jl:44-66 */
+    VELA_COMP_DM_OFFSET = 31           /* DispersionOffset (FDJUMPDM, BitMatrix), src/model/fdjumpdm.jl:14-37 */
 } VelaComponentKind;
+#define VELA_COMP_KIND_MAX 31
 
 /* VelaComponentDesc.flags */
 #define VELA_FLAG_ECLIPTIC        1   /* SolarSystem.ecliptic_coordinates */
@@ -122,6 +136,22 @@ typedef enum VelaComponentKind {
  *  DM_JUMP        par: 0 DMJUMP[0]                      len: 0 #DMJUMP mask: 0 first bit-mask row
  *  DM_MEASUREMENT_NOISE par: 0 DMEFAC[0] 1 DMEQUAD[0]   len: 0 #DMEFAC 1 #DMEQUAD
  *                                                       mask: 0 dmefac mask 1 dmequad mask
+ *  BINARY_ELL1H   as BINARY_ELL1 with par: 10 H3 11 STIGMA
+ *  BINARY_ELL1K   as BINARY_ELL1 with par: 8 OMDOT 9 LNEDOT (instead of EPS1DOT/EPS2DOT)
+ *  BINARY_DDH     as BINARY_DD with par: 13 H3 14 STIGMA
+ *  BINARY_DDS     as BINARY_DD with par: 13 M2 14 SHAPMAX
+ *  BINARY_DDK     as BINARY_DD with par: 13 M2 14 KIN 15 KOM 16 PMLONG(PMRA|PMELONG) 17 PMLAT(PMDEC|PMELAT) 18 PX;
+ *                 flags also carry VELA_FLAG_ECLIPTIC
+ *  FD             par: 0 FD[0]                          len: 0 #FD
+ *  FD_JUMP        par: 0 FDJUMP[0]                      len: 0 #FDJUMP mask: 0 first bit-mask row,
+ *                                                       1 index-mask row whose first #FDJUMP entries are the exponents
+ *  WAVEX          par: 0 WXEPOCH 1 WXSIN_[0] 2 WXCOS_[0] 3 WXFREQ_[0]          len: 0 #harmonics
+ *  DM_WAVEX       par: 0 DMWXEPOCH 1 DMWXSIN_[0] 2 DMWXCOS_[0] 3 DMWXFREQ_[0]  len: 0 #harmonics
+ *  CM_WAVEX       par: 0 CMWXEPOCH 1 CMWXSIN_[0] 2 CMWXCOS_[0] 3 CMWXFREQ_[0] 4 TNCHROMIDX  len: 0 #harmonics
+ *  SOLAR_WIND_PIECEWISE par: 0 SWXDM_[0]                len: 0 #SWXDM_  mask: 0 swx index mask
+ *                                                       dval: 0 conjunction_geometry 1 opposition_geometry
+ *  DM_OFFSET_EXCLUSIVE par: 0 FDJUMPDM[0]               len: 0 #FDJUMPDM mask: 0 index mask
+ *  DM_OFFSET      par: 0 FDJUMPDM[0]                    len: 0 #FDJUMPDM mask: 0 first bit-mask row
  */
 typedef struct VelaComponentDesc {
     int32_t kind;
@@ -129,6 +159,7 @@ typedef struct VelaComponentDesc {
     int32_t par[VELA_MAX_PAR];
     int32_t len[4];
     int32_t mask[2];
+    double dval[2];              /* per-component constants that are not parameters (struct fields in the reference) */
 } VelaComponentDesc;
 
 /* Likelihood kernels, src/model/kernel.jl:20-92. */

@@ -312,17 +312,34 @@ static double mean_motion(const Ctx* ctx, const VelaComponentDesc* c, double dt)
     return TWO_PI * (1 / (PAR(c, 1) + PAR(c, 2) * dt));
 }
 
-/* BinaryELL1 binary/binary_ell1_base.jl:36-180, shapiro params binary_ell1.jl:15 */
+/* shapiro_delay_params for the orthometric (H3, STIGMA) parametrisation: binary_ell1h.jl:22-28, binary_ddh.jl:18-24 */
+static void shapiro_from_h3_stigma(double h3, double stigma, double* m2, double* sini) {
+    *m2 = h3 / (stigma * stigma * stigma);
+    *sini = 2 * stigma / (1 + stigma * stigma);
+}
+
+/* BinaryELL1 / ELL1H / ELL1k: binary/binary_ell1_base.jl:36-180, binary_ell1.jl:15, binary_ell1h.jl:22-46,
+ * binary_ell1k.jl:17-49 */
 static void comp_ell1(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, Corr* k) {
     double dt = t64(toa, k) - PAR(c, 0);
     double a1 = PAR(c, 4) + dt * PAR(c, 5);
-    double e1 = PAR(c, 6) + dt * PAR(c, 8);
-    double e2 = PAR(c, 7) + dt * PAR(c, 9);
+    double e1, e2;
+    if (c->kind == VELA_COMP_BINARY_ELL1K) {
+        double omdot = PAR(c, 8), lnedot = PAR(c, 9), e10 = PAR(c, 6), e20 = PAR(c, 7);
+        double so = sin(omdot * dt), co = cos(omdot * dt);
+        e1 = (1 + lnedot * dt) * (e10 * co + e20 * so);
+        e2 = (1 + lnedot * dt) * (e20 * co - e10 * so);
+    } else {
+        e1 = PAR(c, 6) + dt * PAR(c, 8);
+        e2 = PAR(c, 7) + dt * PAR(c, 9);
+    }
     double Phi = mean_anomaly(ctx, c, dt);
     double s1 = sin(Phi), c1 = cos(Phi), s2 = sin(2 * Phi), c2 = cos(2 * Phi);
     double s3 = sin(3 * Phi), c3 = cos(3 * Phi), s4 = sin(4 * Phi), c4 = cos(4 * Phi);
     double n = mean_motion(ctx, c, dt);
-    double m2 = PAR(c, 10), sini = PAR(c, 11);
+    double m2, sini;
+    if (c->kind == VELA_COMP_BINARY_ELL1H) shapiro_from_h3_stigma(PAR(c, 10), PAR(c, 11), &m2, &sini);
+    else { m2 = PAR(c, 10); sini = PAR(c, 11); }
     double e1_2 = e1 * e1, e2_2 = e2 * e2, e1_3 = e1 * e1 * e1, e2_3 = e2 * e2 * e2;
 
     double dR = a1 * (s1 + 0.5 * (e2 * s2 - e1 * c2) -
@@ -330,6 +347,7 @@ static void comp_ell1(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa
                                    6 * e2 * e1 * c3) -
                       (1.0 / 12) * ((5 * e2_3 + 3 * e1_2 * e2) * s2 + (-6 * e1 * e2_2 - 4 * e1_3) * c2 +
                                     (-4 * e2_3 + 12 * e1_2 * e2) * s4 + (12 * e1 * e2_2 - 4 * e1_3) * c4));
+    if (c->kind == VELA_COMP_BINARY_ELL1K) dR = dR - 1.5 * a1 * e1;        /* binary_ell1k.jl:46-49 */
     double dRp = a1 * (c1 + e1 * s2 + e2 * c2 -
                        (1.0 / 8) * ((5 * e2_2 + 3 * e1_2) * c1 + 2 * e1 * e2 * s1 + (-9 * e2_2 + 9 * e1_2) * c3 -
                                     18 * e1 * e2 * s3) -
@@ -342,6 +360,13 @@ static void comp_ell1(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa
                                       (64 * e2_3 - 192 * e1_2 * e2) * s4 + (-192 * e1 * e2_2 + 64 * e1_3) * c4));
     double dR_inv = dR * (1 - n * dRp + n * n * dRp * dRp + 0.5 * n * n * dR * dRp2);
     double dS = -2 * m2 * log(1 - sini * s1);
+    if (c->kind == VELA_COMP_BINARY_ELL1H) {                              /* binary_ell1h.jl:30-46 */
+        double cbar = sqrt(1 - sini * sini);
+        double sg = sini / (1 + cbar);
+        double a0 = -log(1 + sg * sg), b1 = -2 * sg, a2 = sg * sg;
+        double dS012 = -2 * m2 * (a0 + b1 * s1 + a2 * c2);
+        dS = dS - dS012;
+    }
     k->delay += dR_inv + dS;
     k->doppler += -dRp * n;
 }
@@ -379,7 +404,29 @@ static double mikkola(double l, double e, int* bad) {
     return sgn * (sol + ncycles * TWO_PI);
 }
 
-/* BinaryDD binary/binary_dd_base.jl:36-162, shapiro params binary_dd.jl:15 */
+/* kopeikin_I0_J0 + kopeikin_corrections binary/binary_ddk.jl:72-120 */
+static void kopeikin_corrections(double dt, double x, double kin, double kom, double mua, double mud, double px,
+                                 const double* ssb_obs_pos, const double* L, double* dx, double* dom, double* dkin) {
+    double si = sin(kin), ci = cos(kin), sO = sin(kom), cO = cos(kom);
+    double cot = ci / si, csc = 1 / si;
+    double dkin_pm = (-mua * sO + mud * cO) * dt;
+    double dx_pm = x * cot * dkin_pm;
+    double dom_pm = csc * (mua * cO + mud * sO) * dt;
+    double sind = L[2];
+    double cosd = sqrt(1 - sind * sind);
+    double cosa = L[0] / cosd, sina = L[1] / cosd;
+    double I0[3] = { -sina, cosa, 0.0 };
+    double J0[3] = { -cosa * sind, -sina * sind, cosd };
+    double dI0 = dot3(ssb_obs_pos, I0), dJ0 = dot3(ssb_obs_pos, J0);
+    double dx_px = x * cot * px * (dI0 * sO - dJ0 * cO);
+    double dom_px = -csc * px * (dI0 * cO + dJ0 * sO);
+    *dx = dx_pm + dx_px;
+    *dom = dom_pm + dom_px;
+    *dkin = dkin_pm;
+}
+
+/* BinaryDD / DDH / DDS / DDK: binary/binary_dd_base.jl:36-162, binary_dd.jl:15, binary_ddh.jl:18-24,
+ * binary_dds.jl:18-23, binary_ddk.jl:20-66 */
 static void comp_dd(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, Corr* k) {
     double dt = t64(toa, k) - PAR(c, 0);
     double n = mean_motion(ctx, c, dt);
@@ -393,14 +440,25 @@ static void comp_dd(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, 
     double bphi = (1 - eta) / ephi;
     double v_u = 2 * atan2(bphi * sinu, 1 - bphi * cosu);
     double v = v_u + u;
-    double kk = PAR(c, 9) / n;
-    double om = PAR(c, 8) + kk * v;
-    double sinw = sin(om), cosw = cos(om);
     double a1 = PAR(c, 4) + dt * PAR(c, 5);
+    double m2, sini, dom = 0.0;
+    if (c->kind == VELA_COMP_BINARY_DDH) shapiro_from_h3_stigma(PAR(c, 13), PAR(c, 14), &m2, &sini);
+    else if (c->kind == VELA_COMP_BINARY_DDS) { m2 = PAR(c, 13); sini = 1 - exp(-PAR(c, 14)); }
+    else if (c->kind == VELA_COMP_BINARY_DDK) {
+        double dx, dkin, kin = PAR(c, 14);
+        kopeikin_corrections(dt, a1, kin, PAR(c, 15), PAR(c, 16), PAR(c, 17), PAR(c, 18), toa->eph, k->ssb_psr_pos,
+                             &dx, &dom, &dkin);
+        a1 += dx;
+        kin += dkin;
+        m2 = PAR(c, 13);
+        sini = sin(kin);
+    } else { m2 = PAR(c, 13); sini = PAR(c, 14); }
+    double kk = PAR(c, 9) / n;
+    double om = PAR(c, 8) + kk * v + dom;
+    double sinw = sin(om), cosw = cos(om);
     double alpha = a1 * sinw;
     double beta = a1 * eta * cosw;
     double gamma = PAR(c, 12);
-    double m2 = PAR(c, 13), sini = PAR(c, 14);
 
     double dRE = alpha * (cosu - er) + (beta + gamma) * sinu;
     double dREp = -alpha * sinu + (beta + gamma) * cosu;
@@ -411,6 +469,74 @@ static void comp_dd(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, 
     double dS = -2 * m2 * log(1 - et * cosu - (sini / a1) * (alpha * (cosu - er) + beta * sinu));
     k->delay += dRE_inv + dS;
     k->doppler += dREp * nhat;
+}
+
+/* FrequencyDependent frequency_dependent.jl:22-34 / FrequencyDependentJump :46-81 */
+static double int_pow(double x, unsigned p) { double r = 1.0; for (unsigned i = 0; i < p; ++i) r *= x; return r; }
+static void comp_fd(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, Corr* k) {
+    double lam = log(nu_c(toa, k) / 1e9);
+    double sum = 0.0;
+    for (int p = 1; p <= c->len[0]; ++p) sum += ctx->P[c->par[0] + p - 1] * int_pow(lam, (unsigned)p);
+    k->delay += sum;
+}
+static void comp_fdjump(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, Corr* k) {
+    if (toa_is_tzr(toa)) return;
+    double lam = log(nu_c(toa, k) / 1e9);
+    double delay = 0.0;
+    for (int g = 0; g < c->len[0]; ++g) {
+        if (ctx->d->bit_masks[(int64_t)(c->mask[0] + g) * ctx->d->n_toas + (int64_t)(toa->index - 1)]) {
+            unsigned p = ctx->d->index_masks[(int64_t)c->mask[1] * ctx->d->n_toas + g];
+            delay += ctx->P[c->par[0] + g] * int_pow(lam, p);
+        }
+    }
+    k->delay += delay;
+}
+
+/* evaluate_xwavex wavex.jl:28-42 */
+static double xwavex(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, const Corr* k) {
+    double t_t0 = t64(toa, k) - PAR(c, 0);
+    double kk = 2 * M_PI * t_t0;
+    double sum = 0.0;
+    for (int i = 0; i < c->len[0]; ++i) {
+        double phi = kk * ctx->P[c->par[3] + i];
+        sum += ctx->P[c->par[1] + i] * sin(phi) + ctx->P[c->par[2] + i] * cos(phi);
+    }
+    return sum;
+}
+
+/* SolarWindDispersionPiecewise solarwind.jl:72-91 */
+static void comp_swx(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, Corr* k) {
+    double dm = 0.0;
+    if (!toa_is_tzr(toa) && !toa_is_barycentered(toa)) {
+        uint32_t idx = mask_at(ctx, c->mask[0], toa);
+        if (idx != 0) {
+            if (!corr_is_barycentered(k)) { k->bad = 1; return; }
+            const double* rvec = toa->eph + 6;
+            double r = sqrt(dot3(rvec, rvec));
+            double rho = acos(-dot3(k->ssb_psr_pos, rvec) / r);
+            double geometry = AU * AU * rho / (r * sin(rho));
+            dm = ctx->P[c->par[0] + idx - 1] * (geometry - c->dval[1]) / (c->dval[0] - c->dval[1]);
+        }
+    }
+    apply_dispersion(toa, k, dm);
+}
+
+/* DispersionOffset / ExclusiveDispersionOffset (FDJUMPDM) fdjumpdm.jl:14-66: a full DispersionComponent */
+static void comp_dmoffset(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, Corr* k) {
+    double dm = 0.0;
+    if (!toa_is_tzr(toa)) {
+        if (c->kind == VELA_COMP_DM_OFFSET_EXCLUSIVE) {
+            uint32_t idx = mask_at(ctx, c->mask[0], toa);
+            if (idx != 0) dm = -ctx->P[c->par[0] + idx - 1];
+        } else {
+            double dot = 0.0;
+            for (int g = 0; g < c->len[0]; ++g)
+                dot += ctx->P[c->par[0] + g] *
+                       (double)ctx->d->bit_masks[(int64_t)(c->mask[0] + g) * ctx->d->n_toas + (int64_t)(toa->index - 1)];
+            dm = -dot;
+        }
+    }
+    apply_dispersion(toa, k, dm);
 }
 
 /* Glitch glitch.jl:14-38 */
@@ -531,8 +657,17 @@ static Corr correct_toa(const Ctx* ctx, const Toa* toa) {
             case VELA_COMP_DISPERSION_PIECEWISE: comp_dmx(ctx, c, toa, &k); break;
             case VELA_COMP_CHROMATIC_TAYLOR: comp_chromatic_taylor(ctx, c, toa, &k); break;
             case VELA_COMP_CHROMATIC_PIECEWISE: comp_cmx(ctx, c, toa, &k); break;
-            case VELA_COMP_BINARY_ELL1: comp_ell1(ctx, c, toa, &k); break;
-            case VELA_COMP_BINARY_DD: comp_dd(ctx, c, toa, &k); break;
+            case VELA_COMP_BINARY_ELL1: case VELA_COMP_BINARY_ELL1H: case VELA_COMP_BINARY_ELL1K:
+                comp_ell1(ctx, c, toa, &k); break;
+            case VELA_COMP_BINARY_DD: case VELA_COMP_BINARY_DDH: case VELA_COMP_BINARY_DDS: case VELA_COMP_BINARY_DDK:
+                comp_dd(ctx, c, toa, &k); break;
+            case VELA_COMP_FD: comp_fd(ctx, c, toa, &k); break;
+            case VELA_COMP_FD_JUMP: comp_fdjump(ctx, c, toa, &k); break;
+            case VELA_COMP_WAVEX: k.delay += xwavex(ctx, c, toa, &k); break;
+            case VELA_COMP_DM_WAVEX: apply_dispersion(toa, &k, xwavex(ctx, c, toa, &k)); break;
+            case VELA_COMP_CM_WAVEX: apply_chromatic(toa, &k, xwavex(ctx, c, toa, &k), PAR(c, 4)); break;
+            case VELA_COMP_SOLAR_WIND_PIECEWISE: comp_swx(ctx, c, toa, &k); break;
+            case VELA_COMP_DM_OFFSET_EXCLUSIVE: case VELA_COMP_DM_OFFSET: comp_dmoffset(ctx, c, toa, &k); break;
             case VELA_COMP_GLITCH: comp_glitch(ctx, c, toa, &k); break;
             case VELA_COMP_EXP_DIP: comp_expdip(ctx, c, toa, &k); break;
             case VELA_COMP_SPINDOWN: comp_spindown(ctx, c, toa, &k); break;

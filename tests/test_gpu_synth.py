@@ -10,7 +10,9 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 CASES = [("config2_ell1", 1500, 96), ("config3_gp", 1200, 96), ("config4_dd_wb", 700, 64), ("config5_array", 900, 40),
-         ("extra_ell1_fbx", None, 64), ("extra_dd_fbx_wb", None, 64), ("extra_dmjump_bits_wb", None, 64)]
+         ("extra_ell1_fbx", None, 64), ("extra_dd_fbx_wb", None, 64), ("extra_dmjump_bits_wb", None, 64),
+         ("extra_ell1h_fd_wavex", None, 48), ("extra_ell1k_swx", None, 48), ("extra_ddk_wb", None, 48),
+         ("extra_ddh", None, 48), ("extra_dds", None, 48)]
 
 
 @pytest.fixture(scope="module")

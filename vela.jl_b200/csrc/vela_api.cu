@@ -345,13 +345,13 @@ int validate(const VelaModelDesc* d) {
     if (tzr_index != 0) return fail(VELA_ERR_INVALID_ARG, "Invalid TZR TOA (index != 0), timing_model.jl:37");
     for (int ic = 0; ic < d->n_components; ++ic) {
         const VelaComponentDesc& c = d->components[ic];
-        if (c.kind < VELA_COMP_SOLAR_SYSTEM || c.kind > VELA_COMP_DM_MEASUREMENT_NOISE) return fail(VELA_ERR_UNSUPPORTED, "component kind %d is outside the implemented hot path", c.kind);
+        if (c.kind < VELA_COMP_SOLAR_SYSTEM || c.kind > VELA_COMP_KIND_MAX) return fail(VELA_ERR_UNSUPPORTED, "component kind %d is outside the implemented hot path", c.kind);
         for (int k = 0; k < VELA_MAX_PAR; ++k)
             if (c.par[k] >= d->n_params) return fail(VELA_ERR_INVALID_ARG, "component %d: parameter offset %d out of range", ic, c.par[k]);
-        const bool bits = c.kind == VELA_COMP_PHASE_JUMP || c.kind == VELA_COMP_DM_JUMP;
+        const bool bits = c.kind == VELA_COMP_PHASE_JUMP || c.kind == VELA_COMP_DM_JUMP || c.kind == VELA_COMP_DM_OFFSET || c.kind == VELA_COMP_FD_JUMP;
         for (int m = 0; m < 2; ++m) {
             if (c.mask[m] < 0) continue;
-            if (bits ? (c.mask[m] + c.len[0] > d->n_bit_mask_rows) : (c.mask[m] >= d->n_index_masks)) return fail(VELA_ERR_INVALID_ARG, "component %d: mask %d out of range", ic, c.mask[m]);
+            if ((bits && m == 0) ? (c.mask[m] + c.len[0] > d->n_bit_mask_rows) : (c.mask[m] >= d->n_index_masks)) return fail(VELA_ERR_INVALID_ARG, "component %d: mask %d out of range", ic, c.mask[m]);
         }
     }
     if (d->kernel_kind == VELA_KERNEL_WOODBURY_ECORR) return fail(VELA_ERR_UNSUPPORTED, "WoodburyKernel{EcorrKernel} is not on the GPU path yet (next row, DESIGN.md section 8)");
@@ -413,6 +413,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         memcpy(cd.par, c.par, sizeof cd.par);
         memcpy(cd.len, c.len, sizeof cd.len);
         memcpy(cd.mask, c.mask, sizeof cd.mask);
+        memcpy(cd.dval, c.dval, sizeof cd.dval);
         cd.der = nder;
         nder += derived_count(c.kind, c.len);
     }

@@ -21,7 +21,9 @@ VELA_MAX_PAR = 24
 (COMP_SOLAR_SYSTEM, COMP_SOLAR_WIND, COMP_DISPERSION_TAYLOR, COMP_DISPERSION_PIECEWISE,
  COMP_CHROMATIC_TAYLOR, COMP_CHROMATIC_PIECEWISE, COMP_BINARY_ELL1, COMP_BINARY_DD, COMP_GLITCH,
  COMP_EXP_DIP, COMP_SPINDOWN, COMP_PHASE_OFFSET, COMP_PHASE_JUMP_EXCLUSIVE, COMP_PHASE_JUMP,
- COMP_MEASUREMENT_NOISE, COMP_DM_JUMP_EXCLUSIVE, COMP_DM_JUMP, COMP_DM_MEASUREMENT_NOISE) = range(1, 19)
+ COMP_MEASUREMENT_NOISE, COMP_DM_JUMP_EXCLUSIVE, COMP_DM_JUMP, COMP_DM_MEASUREMENT_NOISE, COMP_BINARY_ELL1H,
+ COMP_BINARY_ELL1K, COMP_BINARY_DDH, COMP_BINARY_DDS, COMP_BINARY_DDK, COMP_FD, COMP_FD_JUMP, COMP_WAVEX, COMP_DM_WAVEX,
+ COMP_CM_WAVEX, COMP_SOLAR_WIND_PIECEWISE, COMP_DM_OFFSET_EXCLUSIVE, COMP_DM_OFFSET) = range(1, 32)
 FLAG_ECLIPTIC, FLAG_PLANET_SHAPIRO, FLAG_USE_FBX = 1, 2, 4
 KERNEL_WHITE, KERNEL_ECORR, KERNEL_WOODBURY_WHITE, KERNEL_WOODBURY_ECORR = 0, 1, 2, 3
 GP_POWERLAW_RED, GP_POWERLAW_DM, GP_POWERLAW_CHROM, GP_MARGINALIZED_TM = 1, 2, 3, 4
@@ -29,7 +31,7 @@ GP_POWERLAW_RED, GP_POWERLAW_DM, GP_POWERLAW_CHROM, GP_MARGINALIZED_TM = 1, 2, 3
 
 class VelaComponentDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("flags", C.c_int32), ("par", C.c_int32 * VELA_MAX_PAR),
-                ("len", C.c_int32 * 4), ("mask", C.c_int32 * 2)]
+                ("len", C.c_int32 * 4), ("mask", C.c_int32 * 2), ("dval", C.c_double * 2)]
 
 
 class VelaGPDesc(C.Structure):
@@ -140,27 +142,70 @@ class ModelDescriptor:
                 setp(c, 0, "CMX_", 0)
                 setp(c, 2, "TNCHROMIDX")
                 c.mask[0] = add_index_mask(comp.cmx_mask)
-            elif isinstance(comp, M.BinaryELL1):
-                c = new(COMP_BINARY_ELL1, FLAG_USE_FBX if comp.use_fbx else 0)
+            elif isinstance(comp, (M.BinaryELL1, M.BinaryELL1H, M.BinaryELL1k)):
+                kind = {M.BinaryELL1: COMP_BINARY_ELL1, M.BinaryELL1H: COMP_BINARY_ELL1H,
+                        M.BinaryELL1k: COMP_BINARY_ELL1K}[type(comp)]
+                c = new(kind, FLAG_USE_FBX if comp.use_fbx else 0)
                 setp(c, 0, "TASC")
                 if comp.use_fbx:
                     setp(c, 3, "FB", 0)
                 else:
                     setp(c, 1, "PB")
                     setp(c, 2, "PBDOT")
-                for s, nme in enumerate(("A1", "A1DOT", "EPS1", "EPS2", "EPS1DOT", "EPS2DOT", "M2", "SINI"), 4):
+                rates = ("OMDOT", "LNEDOT") if kind == COMP_BINARY_ELL1K else ("EPS1DOT", "EPS2DOT")
+                shap = ("H3", "STIGMA") if kind == COMP_BINARY_ELL1H else ("M2", "SINI")
+                for s, nme in enumerate(("A1", "A1DOT", "EPS1", "EPS2") + rates + shap, 4):
                     setp(c, s, nme)
-            elif isinstance(comp, M.BinaryDD):
-                c = new(COMP_BINARY_DD, FLAG_USE_FBX if comp.use_fbx else 0)
+            elif isinstance(comp, (M.BinaryDD, M.BinaryDDH, M.BinaryDDS, M.BinaryDDK)):
+                kind = {M.BinaryDD: COMP_BINARY_DD, M.BinaryDDH: COMP_BINARY_DDH, M.BinaryDDS: COMP_BINARY_DDS,
+                        M.BinaryDDK: COMP_BINARY_DDK}[type(comp)]
+                flags = FLAG_USE_FBX if comp.use_fbx else 0
+                if kind == COMP_BINARY_DDK and comp.ecliptic_coordinates:
+                    flags |= FLAG_ECLIPTIC
+                c = new(kind, flags)
                 setp(c, 0, "T0")
                 if comp.use_fbx:
                     setp(c, 3, "FB", 0)
                 else:
                     setp(c, 1, "PB")
                     setp(c, 2, "PBDOT")
-                for s, nme in enumerate(("A1", "A1DOT", "ECC", "EDOT", "OM", "OMDOT", "DR", "DTH", "GAMMA",
-                                         "M2", "SINI"), 4):
+                shap = {COMP_BINARY_DD: ("M2", "SINI"), COMP_BINARY_DDH: ("H3", "STIGMA"), COMP_BINARY_DDS: ("M2", "SHAPMAX"),
+                        COMP_BINARY_DDK: ("M2", "KIN", "KOM") + (("PMELONG", "PMELAT") if flags & FLAG_ECLIPTIC
+                                                               else ("PMRA", "PMDEC")) + ("PX",)}[kind]
+                for s, nme in enumerate(("A1", "A1DOT", "ECC", "EDOT", "OM", "OMDOT", "DR", "DTH", "GAMMA") + shap, 4):
                     setp(c, s, nme)
+            elif isinstance(comp, M.FrequencyDependent):
+                c = new(COMP_FD)
+                setp(c, 0, "FD", 0)
+            elif isinstance(comp, M.FrequencyDependentJump):
+                c = new(COMP_FD_JUMP)
+                setp(c, 0, "FDJUMP", 0)
+                c.mask[0] = add_bit_mask(comp.jump_mask)
+                exps = np.zeros(ntoa, dtype=np.uint32)
+                if len(comp.exponents) > ntoa or len(comp.exponents) != np.asarray(comp.jump_mask).shape[0]:
+                    raise ValueError("FDJUMP exponents must match the mask rows")
+                exps[: len(comp.exponents)] = comp.exponents
+                c.mask[1] = add_index_mask(exps)
+            elif isinstance(comp, (M.WaveX, M.DMWaveX, M.CMWaveX)):
+                pre, kind = {M.WaveX: ("WX", COMP_WAVEX), M.DMWaveX: ("DMWX", COMP_DM_WAVEX),
+                             M.CMWaveX: ("CMWX", COMP_CM_WAVEX)}[type(comp)]
+                c = new(kind)
+                setp(c, 0, pre + "EPOCH")
+                setp(c, 1, pre + "SIN_", 0)
+                setp(c, 2, pre + "COS_")
+                setp(c, 3, pre + "FREQ_")
+                if kind == COMP_CM_WAVEX:
+                    setp(c, 4, "TNCHROMIDX")
+            elif isinstance(comp, M.SolarWindDispersionPiecewise):
+                c = new(COMP_SOLAR_WIND_PIECEWISE)
+                setp(c, 0, "SWXDM_", 0)
+                c.mask[0] = add_index_mask(comp.swx_mask)
+                c.dval[0], c.dval[1] = comp.conjunction_geometry, comp.opposition_geometry
+            elif isinstance(comp, (M.ExclusiveDispersionOffset, M.DispersionOffset)):
+                excl = isinstance(comp, M.ExclusiveDispersionOffset)
+                c = new(COMP_DM_OFFSET_EXCLUSIVE if excl else COMP_DM_OFFSET)
+                setp(c, 0, "FDJUMPDM", 0)
+                c.mask[0] = add_index_mask(comp.jump_mask) if excl else add_bit_mask(comp.jump_mask)
             elif isinstance(comp, M.Glitch):
                 c = new(COMP_GLITCH)
                 for s, nme in enumerate(("GLEP_", "GLPH_", "GLF0_", "GLF1_", "GLF2_", "GLF0D_", "GLTD_")):

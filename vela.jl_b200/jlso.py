@@ -199,6 +199,12 @@ _FIELDS = {
     "DispersionPiecewise": ["dmx_mask"],                        # src/model/dispersion.jl:39-41
     "ChromaticPiecewise": ["cmx_mask"],                         # src/model/chromatic.jl:42-44
     "BinaryELL1": ["use_fbx"], "BinaryDD": ["use_fbx"],        # binary_ell1.jl:11-13, binary_dd.jl:11-13
+    "BinaryELL1H": ["use_fbx"], "BinaryELL1k": ["use_fbx"], "BinaryDDH": ["use_fbx"], "BinaryDDS": ["use_fbx"],
+    "BinaryDDK": ["use_fbx", "ecliptic_coordinates"],          # binary_ddk.jl:15-18
+    "FrequencyDependent": [], "WaveX": [], "DMWaveX": [], "CMWaveX": [],
+    "FrequencyDependentJump": ["jump_mask", "exponents"],      # frequency_dependent.jl:46-49
+    "SolarWindDispersionPiecewise": ["swx_mask", "conjunction_geometry", "opposition_geometry"],  # solarwind.jl:64-68
+    "DispersionOffset": ["jump_mask"], "ExclusiveDispersionOffset": ["jump_mask"],                # fdjumpdm.jl:14-16,44-46
     "PhaseJump": ["jump_mask"], "ExclusivePhaseJump": ["jump_mask"],   # src/model/jump.jl:14-16,31-33
     "DispersionJump": ["jump_mask"], "ExclusiveDispersionJump": ["jump_mask"],  # dmjump.jl:28-30,62-64
     "MeasurementNoise": ["efac_index_mask", "equad_index_mask"],        # measurement_noise.jl:14-17

@@ -16,7 +16,9 @@ using ..Vela
 using ..Vela: TimingModel, TOA, WidebandTOA, TOABase, Pulsar, ParamHandler, WhiteNoiseKernel, EcorrKernel, EcorrGroup,
     WoodburyKernel,
     SolarSystem, SolarWindDispersion, DispersionTaylor, DispersionPiecewise, ChromaticTaylor, ChromaticPiecewise,
-    BinaryELL1, BinaryDD, Glitch, ChromaticExponentialDip, Spindown, PhaseOffset, PhaseJump, ExclusivePhaseJump,
+    BinaryELL1, BinaryELL1H, BinaryELL1k, BinaryDD, BinaryDDH, BinaryDDS, BinaryDDK, FrequencyDependent,
+    FrequencyDependentJump, WaveX, DMWaveX, CMWaveX, SolarWindDispersionPiecewise, DispersionOffset,
+    ExclusiveDispersionOffset, Glitch, ChromaticExponentialDip, Spindown, PhaseOffset, PhaseJump, ExclusivePhaseJump,
     MeasurementNoise, DispersionJump, ExclusiveDispersionJump, DispersionMeasurementNoise, PowerlawRedNoiseGP,
     PowerlawDispersionNoiseGP, PowerlawChromaticNoiseGP, MarginalizedTimingModel, calc_lnprior,
     read_param_values_to_vector
@@ -33,6 +35,7 @@ struct VelaComponentDesc
     par::NTuple{VELA_MAX_PAR,Int32}
     len::NTuple{4,Int32}
     mask::NTuple{2,Int32}
+    dval::NTuple{2,Float64}
 end
 
 struct VelaGPDesc
@@ -97,7 +100,7 @@ mutable struct Builder
     bit_rows::Vector{Vector{UInt8}}
 end
 
-function comp(kind; flags = 0, par = (), len = (), mask = ())
+function comp(kind; flags = 0, par = (), len = (), mask = (), dval = (0.0, 0.0))
     p = fill(Int32(-1), VELA_MAX_PAR)
     for (slot, off) in par
         p[slot+1] = off
@@ -110,7 +113,7 @@ function comp(kind; flags = 0, par = (), len = (), mask = ())
     for (slot, i) in mask
         m[slot+1] = i
     end
-    return VelaComponentDesc(Int32(kind), Int32(flags), Tuple(p), Tuple(l), Tuple(m))
+    return VelaComponentDesc(Int32(kind), Int32(flags), Tuple(p), Tuple(l), Tuple(m), Float64.(dval))
 end
 
 off(b::Builder, s::Symbol) = b.offs[s][1]
@@ -160,6 +163,50 @@ describe(b::Builder, c::BinaryDD) =
             (:A1, :A1DOT, :ECC, :EDOT, :OM, :OMDOT, :DR, :DTH, :GAMMA, :M2, :SINI))
         comp(8; flags = c.use_fbx ? 4 : 0, par = par, len = l)
     end
+describe(b::Builder, c::BinaryELL1H) =
+    let (par, l) = binary_par(b, :TASC, c.use_fbx, (:A1, :A1DOT, :EPS1, :EPS2, :EPS1DOT, :EPS2DOT, :H3, :STIGMA))
+        comp(19; flags = c.use_fbx ? 4 : 0, par = par, len = l)
+    end
+describe(b::Builder, c::BinaryELL1k) =
+    let (par, l) = binary_par(b, :TASC, c.use_fbx, (:A1, :A1DOT, :EPS1, :EPS2, :OMDOT, :LNEDOT, :M2, :SINI))
+        comp(20; flags = c.use_fbx ? 4 : 0, par = par, len = l)
+    end
+const DD_COMMON = (:A1, :A1DOT, :ECC, :EDOT, :OM, :OMDOT, :DR, :DTH, :GAMMA)
+describe(b::Builder, c::BinaryDDH) =
+    let (par, l) = binary_par(b, :T0, c.use_fbx, (DD_COMMON..., :H3, :STIGMA))
+        comp(21; flags = c.use_fbx ? 4 : 0, par = par, len = l)
+    end
+describe(b::Builder, c::BinaryDDS) =
+    let (par, l) = binary_par(b, :T0, c.use_fbx, (DD_COMMON..., :M2, :SHAPMAX))
+        comp(22; flags = c.use_fbx ? 4 : 0, par = par, len = l)
+    end
+describe(b::Builder, c::BinaryDDK) =
+    let pm = c.ecliptic_coordinates ? (:PMELONG, :PMELAT) : (:PMRA, :PMDEC),
+        (par, l) = binary_par(b, :T0, c.use_fbx, (DD_COMMON..., :M2, :KIN, :KOM, pm..., :PX))
+
+        comp(23; flags = (c.use_fbx ? 4 : 0) | (c.ecliptic_coordinates ? 1 : 0), par = par, len = l)
+    end
+describe(b::Builder, ::FrequencyDependent) = comp(24; par = [(0, off(b, :FD))], len = [(0, len(b, :FD))])
+function describe(b::Builder, c::FrequencyDependentJump)
+    exps = zeros(UInt, b.ntoa)
+    exps[1:length(c.exponents)] .= c.exponents
+    bits = add_bit_mask!(b, c.jump_mask)
+    return comp(25; par = [(0, off(b, :FDJUMP))], len = [(0, len(b, :FDJUMP))], mask = [(0, bits), (1, add_index_mask!(b, exps))])
+end
+xwavex(b::Builder, kind, pre) =
+    comp(kind; par = vcat([(0, off(b, Symbol(pre, :EPOCH))), (1, off(b, Symbol(pre, :SIN_))), (2, off(b, Symbol(pre, :COS_))),
+                (3, off(b, Symbol(pre, :FREQ_)))], kind == 28 ? [(4, off(b, :TNCHROMIDX))] : []),
+        len = [(0, len(b, Symbol(pre, :SIN_)))])
+describe(b::Builder, ::WaveX) = xwavex(b, 26, :WX)
+describe(b::Builder, ::DMWaveX) = xwavex(b, 27, :DMWX)
+describe(b::Builder, ::CMWaveX) = xwavex(b, 28, :CMWX)
+describe(b::Builder, c::SolarWindDispersionPiecewise) =
+    comp(29; par = [(0, off(b, :SWXDM_))], len = [(0, len(b, :SWXDM_))], mask = [(0, add_index_mask!(b, c.swx_mask))],
+        dval = (c.conjunction_geometry.x, c.opposition_geometry.x))
+describe(b::Builder, c::ExclusiveDispersionOffset) =
+    comp(30; par = [(0, off(b, :FDJUMPDM))], len = [(0, len(b, :FDJUMPDM))], mask = [(0, add_index_mask!(b, c.jump_mask))])
+describe(b::Builder, c::DispersionOffset) =
+    comp(31; par = [(0, off(b, :FDJUMPDM))], len = [(0, len(b, :FDJUMPDM))], mask = [(0, add_bit_mask!(b, c.jump_mask))])
 describe(b::Builder, ::Glitch) =
     comp(9; par = [(i - 1, off(b, s)) for (i, s) in enumerate((:GLEP_, :GLPH_, :GLF0_, :GLF1_, :GLF2_, :GLF0D_, :GLTD_))],
         len = [(0, len(b, :GLEP_))])

@@ -290,6 +290,75 @@ class BinaryDD(Component):
 
 
 @dataclass
+class BinaryELL1H(Component):
+    use_fbx: bool
+
+
+@dataclass
+class BinaryELL1k(Component):
+    use_fbx: bool
+
+
+@dataclass
+class BinaryDDH(Component):
+    use_fbx: bool
+
+
+@dataclass
+class BinaryDDS(Component):
+    use_fbx: bool
+
+
+@dataclass
+class BinaryDDK(Component):
+    use_fbx: bool
+    ecliptic_coordinates: bool
+
+
+@dataclass
+class FrequencyDependent(Component):
+    pass
+
+
+@dataclass
+class FrequencyDependentJump(Component):
+    jump_mask: np.ndarray            # bool (njump, ntoa)
+    exponents: np.ndarray            # uint (njump,)
+
+
+@dataclass
+class WaveX(Component):
+    pass
+
+
+@dataclass
+class DMWaveX(Component):
+    pass
+
+
+@dataclass
+class CMWaveX(Component):
+    pass
+
+
+@dataclass
+class SolarWindDispersionPiecewise(Component):
+    swx_mask: np.ndarray
+    conjunction_geometry: float
+    opposition_geometry: float
+
+
+@dataclass
+class DispersionOffset(Component):
+    jump_mask: np.ndarray            # bool (njump, ntoa)
+
+
+@dataclass
+class ExclusiveDispersionOffset(Component):
+    jump_mask: np.ndarray            # uint (ntoa,)
+
+
+@dataclass
 class Glitch(Component):
     pass
 

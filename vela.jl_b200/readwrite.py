@@ -74,8 +74,20 @@ def _component(js: JLStruct):
         return M.DispersionPiecewise(_mask(js.dmx_mask))
     if n == "ChromaticPiecewise":
         return M.ChromaticPiecewise(_mask(js.cmx_mask))
-    if n in ("BinaryELL1", "BinaryDD"):
+    if n in ("BinaryELL1", "BinaryDD", "BinaryELL1H", "BinaryELL1k", "BinaryDDH", "BinaryDDS"):
         return getattr(M, n)(bool(js.use_fbx))
+    if n == "BinaryDDK":
+        return M.BinaryDDK(bool(js.use_fbx), bool(js.ecliptic_coordinates))
+    if n in ("FrequencyDependent", "WaveX", "DMWaveX", "CMWaveX"):
+        return getattr(M, n)()
+    if n == "FrequencyDependentJump":
+        return M.FrequencyDependentJump(_bitmatrix(js.jump_mask), _mask(js.exponents))
+    if n == "SolarWindDispersionPiecewise":
+        return M.SolarWindDispersionPiecewise(_mask(js.swx_mask), _gq(js.conjunction_geometry), _gq(js.opposition_geometry))
+    if n == "ExclusiveDispersionOffset":
+        return M.ExclusiveDispersionOffset(_mask(js.jump_mask))
+    if n == "DispersionOffset":
+        return M.DispersionOffset(_bitmatrix(js.jump_mask))
     if n == "ExclusivePhaseJump":
         return M.ExclusivePhaseJump(_mask(js.jump_mask))
     if n == "PhaseJump":
@@ -209,6 +221,9 @@ def save_pulsar_npz(path: str, model: M.TimingModel, toas: M.TOAs, extra: dict =
         for f in ("ecliptic_coordinates", "planet_shapiro", "use_fbx"):
             if hasattr(c, f):
                 spec[f] = bool(getattr(c, f))
+        for f in ("conjunction_geometry", "opposition_geometry"):
+            if hasattr(c, f):
+                spec[f] = float(getattr(c, f))
         comps.append(spec)
     k = model.kernel
     if isinstance(k, M.WoodburyKernel):
@@ -254,7 +269,7 @@ def load_pulsar_npz(path: str):
         kw = {}
         for f in _MASK_FIELDS.get(spec["type"], []):
             kw[f] = z[spec[f]]
-        for f in ("ecliptic_coordinates", "planet_shapiro", "use_fbx"):
+        for f in ("ecliptic_coordinates", "planet_shapiro", "use_fbx", "conjunction_geometry", "opposition_geometry"):
             if f in spec:
                 kw[f] = spec[f]
         comps.append(cls(**kw))

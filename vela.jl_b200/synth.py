@@ -144,6 +144,14 @@ CONFIGS = {
                             jump="bits", solarwind=True, ecliptic=True, glitch=1, nback=2, walkers=256, seed=12),
     "extra_dmjump_bits_wb": dict(ntoa=800, span_d=2000.0, wideband=True, dmjump="bits", ecliptic=False, nback=2,
                                  red=10, walkers=128, seed=13),
+    "extra_ell1h_fd_wavex": dict(ntoa=1000, span_d=2500.0, binary="ELL1H", fd=3, fdjump=2, wavex=4, dmwavex=3, cmwavex=2,
+                                 nback=2, walkers=128, seed=14),
+    "extra_ell1k_swx": dict(ntoa=900, span_d=2500.0, binary="ELL1k", swx=3, fdjumpdm="exclusive", ecliptic=True, nback=2,
+                            walkers=128, seed=15),
+    "extra_ddk_wb": dict(ntoa=800, span_d=2500.0, binary="DDK", wideband=True, fdjumpdm="bits", ecliptic=True, px=True,
+                         nback=1, walkers=128, seed=16),
+    "extra_ddh": dict(ntoa=700, span_d=2500.0, binary="DDH", fbx=True, nback=2, walkers=128, seed=17),
+    "extra_dds": dict(ntoa=700, span_d=2500.0, binary="DDS", nback=2, walkers=128, seed=18),
 }
 
 
@@ -193,7 +201,7 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
     F_hi = float(F0)
     lon, lat = (1.2, 0.3) if ecl else (4.51, -0.21)
     sp("POSEPOCH", 0.0, dim=1)
-    sp("PX", 1.2 * 9.715611890180196e-12 if ecl else 0.0, dim=-1)
+    sp("PX", 1.2 * 9.715611890180196e-12 if (ecl or cfg.get("px")) else 0.0, dim=-1)
     sp("ELONG" if ecl else "RAJ", lon, free=True)
     sp("ELAT" if ecl else "DECJ", lat, free=True)
     sp("PMELONG" if ecl else "PMRA", 3.0 * 1.5362818500441604e-16, free=True, dim=-1)
@@ -207,7 +215,9 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         sp("CMEPOCH", 0.0, dim=1)
         sp("TNCHROMIDX", 4.0)
     binary = cfg.get("binary")
-    if binary == "ELL1":
+    ell1_like = binary in ("ELL1", "ELL1H", "ELL1k")
+    dd_like = binary in ("DD", "DDH", "DDS", "DDK")
+    if ell1_like:
         sp("TASC", 0.3 * DAY, free=True, dim=1)
         if not cfg.get("fbx"):
             sp("PB", 4.0742 * DAY, free=True, dim=1)
@@ -216,11 +226,19 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         sp("A1DOT", 0.0)
         sp("EPS1", 1.2e-5, free=True)
         sp("EPS2", -0.8e-5, free=True)
-        sp("EPS1DOT", 0.0, dim=-1)
-        sp("EPS2DOT", 0.0, dim=-1)
-        sp("M2", 0.25 * 4.92549094830932e-06, free=True, dim=1)
-        sp("SINI", 0.95, free=True)
-    elif binary == "DD":
+        if binary == "ELL1k":
+            sp("OMDOT", 3.0e-9, free=True, dim=-1)
+            sp("LNEDOT", 1.0e-12, dim=-1)
+        else:
+            sp("EPS1DOT", 0.0, dim=-1)
+            sp("EPS2DOT", 0.0, dim=-1)
+        if binary == "ELL1H":
+            sp("H3", 2.0e-7, free=True, dim=1)
+            sp("STIGMA", 0.55, free=True)
+        else:
+            sp("M2", 0.25 * 4.92549094830932e-06, free=True, dim=1)
+            sp("SINI", 0.95, free=True)
+    elif dd_like:
         sp("T0", 1.7 * DAY, free=True, dim=1)
         if not cfg.get("fbx"):
             sp("PB", 25.3 * DAY, free=True, dim=1)
@@ -234,8 +252,19 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         sp("DR", 0.0)
         sp("DTH", 0.0)
         sp("GAMMA", 1.0e-3, dim=1)
-        sp("M2", 0.3 * 4.92549094830932e-06, free=True, dim=1)
-        sp("SINI", 0.9, free=True)
+        if binary == "DDH":
+            sp("H3", 3.0e-7, free=True, dim=1)
+            sp("STIGMA", 0.6, free=True)
+        elif binary == "DDS":
+            sp("M2", 0.3 * 4.92549094830932e-06, free=True, dim=1)
+            sp("SHAPMAX", 2.5, free=True)
+        elif binary == "DDK":
+            sp("M2", 0.3 * 4.92549094830932e-06, free=True, dim=1)
+            sp("KIN", 1.1, free=True)
+            sp("KOM", 0.7, free=True)
+        else:
+            sp("M2", 0.3 * 4.92549094830932e-06, free=True, dim=1)
+            sp("SINI", 0.9, free=True)
     for key, amp, gam in (("RED", -13.6, 3.8), ("DM", -13.4, 3.2), ("CHROM", -13.8, 3.5)):
         flag = {"RED": "red", "DM": "dmgp", "CHROM": "chromgp"}[key]
         if cfg.get(flag):
@@ -248,7 +277,7 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
     if cfg.get("chromgp"):
         mp("CM", [0.0], [False], dim=-1, prefix="CM")
     if cfg.get("fbx"):
-        pb = (4.0742 if binary == "ELL1" else 25.3) * DAY
+        pb = (4.0742 if ell1_like else 25.3) * DAY
         mp("FB", [1.0 / pb, -2.0e-20], [True, True], dim=-1, prefix="FB", sig=[0.0, 0.0])
     ng = cfg.get("glitch", 0)
     if ng:
@@ -281,6 +310,26 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         mp("JUMP", [3e-6, -2e-6], [True, True], dim=1, prefix="JUMP", sig=[0.0, 0.0])
     if cfg.get("dmjump"):
         mp("DMJUMP", [2e-4 * DMCONST, -1e-4 * DMCONST], [True, True], dim=-1, prefix="DMJUMP", sig=[0.0, 0.0])
+    nfd = cfg.get("fd", 0)
+    if nfd:
+        mp("FD", 1e-6 * np.array([1.0, -0.4, 0.2])[:nfd], [True] * nfd, dim=1, prefix="FD", sig=[0.0] * nfd)
+    nfdj = cfg.get("fdjump", 0)
+    if nfdj:
+        mp("FDJUMP", 5e-7 * np.array([1.0, -0.6])[:nfdj], [True] * nfdj, dim=1, prefix="FDJUMP", sig=[0.0] * nfdj)
+    for pre, key, amp, dim in (("WX", "wavex", 2e-7, 1), ("DMWX", "dmwavex", 2e-4 * DMCONST, -1), ("CMWX", "cmwavex", 1e-4 * DMCONST, -1)):
+        nw = cfg.get(key, 0)
+        if nw:
+            sp(pre + "EPOCH", 0.0, dim=1)
+            if pre == "CMWX" and not (cfg.get("chromgp") or cfg.get("cmx")):
+                sp("TNCHROMIDX", 4.0)
+            mp(pre + "SIN_", amp * rng.standard_normal(nw), [True] * nw, dim=dim, prefix=pre + "SIN_", sig=[0.0] * nw)
+            mp(pre + "COS_", amp * rng.standard_normal(nw), [True] * nw, dim=dim, prefix=pre + "COS_", sig=[0.0] * nw)
+            mp(pre + "FREQ_", np.arange(1, nw + 1) / span, [False] * nw, dim=-1, prefix=pre + "FREQ_")
+    nswx = cfg.get("swx", 0)
+    if nswx:
+        mp("SWXDM_", 3e-4 * DMCONST * (1 + 0.2 * np.arange(nswx)), [True] * nswx, dim=-1, prefix="SWXDM_", sig=[0.0] * nswx)
+    if cfg.get("fdjumpdm"):
+        mp("FDJUMPDM", [1e-4 * DMCONST, -2e-4 * DMCONST], [True, True], dim=-1, prefix="FDJUMPDM", sig=[0.0, 0.0])
     mp("F", [0.0, -1.0e-15], [not mtm, not mtm], dim=-1, prefix="F", sig=[0.0, 0.0])
     # noise parameters
     for key, amp, gam in (("RED", -13.6, 3.8), ("DM", -13.4, 3.2), ("CHROM", -13.8, 3.5)):
@@ -306,12 +355,20 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
 
     # ---- components in pyvela's authoritative order (model.py:85-351)
     comps: List[M.Component] = [M.SolarSystem(ecl, planet_shapiro=bool(cfg.get("solarwind")))]
+    seg = lambda k: (np.minimum((np.arange(n) * (k + 1)) // n, k)).astype(np.uint32)   # 0 = none, 1..k  # noqa: E731
     if cfg.get("solarwind"):
         comps.append(M.SolarWindDispersion())
+    elif nswx:
+        comps.append(M.SolarWindDispersionPiecewise(seg(nswx), 5000.0, 500.0))
     comps.append(M.DispersionTaylor())
-    seg = lambda k: (np.minimum((np.arange(n) * (k + 1)) // n, k)).astype(np.uint32)   # 0 = none, 1..k  # noqa: E731
     if ndmx:
         comps.append(M.DispersionPiecewise(seg(ndmx)))
+    if cfg.get("dmwavex"):
+        comps.append(M.DMWaveX())
+    if cfg.get("fdjumpdm") == "exclusive":
+        comps.append(M.ExclusiveDispersionOffset(((np.arange(n) // 4) % 3).astype(np.uint32)))
+    elif cfg.get("fdjumpdm") == "bits":
+        comps.append(M.DispersionOffset(np.stack([(np.arange(n) % 3) == 1, (np.arange(n) % 5) == 2])))
     if cfg.get("dmjump") == "exclusive":
         comps.append(M.ExclusiveDispersionJump(((np.arange(n) // 5) % 3).astype(np.uint32)))
     elif cfg.get("dmjump") == "bits":
@@ -320,12 +377,21 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         comps.append(M.ChromaticTaylor())
     if ncmx:
         comps.append(M.ChromaticPiecewise(seg(ncmx)[::-1].copy()))
-    if binary == "ELL1":
-        comps.append(M.BinaryELL1(bool(cfg.get("fbx"))))
-    elif binary == "DD":
-        comps.append(M.BinaryDD(bool(cfg.get("fbx"))))
+    if cfg.get("cmwavex"):
+        comps.append(M.CMWaveX())
+    if binary == "DDK":
+        comps.append(M.BinaryDDK(bool(cfg.get("fbx")), ecl))
+    elif binary:
+        comps.append(getattr(M, "Binary" + binary)(bool(cfg.get("fbx"))))
+    if nfd:
+        comps.append(M.FrequencyDependent())
+    if nfdj:
+        comps.append(M.FrequencyDependentJump(np.stack([(np.arange(n) % 3) == 0, (np.arange(n) % 4) == 1])[:nfdj],
+                                              np.array([1, 2], dtype=np.uint32)[:nfdj]))
     if ne:
         comps.append(M.ChromaticExponentialDip())
+    if cfg.get("wavex"):
+        comps.append(M.WaveX())
     comps.append(M.Spindown())
     if ng:
         comps.append(M.Glitch())
