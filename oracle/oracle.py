@@ -41,6 +41,7 @@ def lib():
         L.oracle_sigma.argtypes = [C.c_void_p, dp, dp, dp]
         L.oracle_gls_lnlike_raw.argtypes = [dp, C.c_int64, C.c_int64, dp, dp, dp, C.POINTER(C.c_uint64), C.c_int, dp]
         L.oracle_gls_lnlike_raw.restype = C.c_double
+        L.oracle_sincos_cr.argtypes = [C.c_double, dp, dp]
         L.oracle_mikkola.argtypes = [C.c_double, C.c_double]
         L.oracle_mikkola.restype = C.c_double
         L.oracle_powerlaw.argtypes = [C.c_double] * 4
@@ -128,6 +129,12 @@ def gls_lnlike_raw(Mmat, Ninvdiag, Phiinv, y, ecorr_groups=None, ecorr=None) -> 
         e = _vec(ecorr)
         ec = _dp(e)
     return float(lib().oracle_gls_lnlike_raw(_dp(Mf), n, p, _dp(_vec(Ninvdiag)), _dp(_vec(Phiinv)), _dp(_vec(y)), grp, ng, ec))
+
+
+def sincos_cr(x: float):
+    s, c = C.c_double(), C.c_double()
+    lib().oracle_sincos_cr(x, C.byref(s), C.byref(c))
+    return s.value, c.value
 
 
 def mikkola(l: float, e: float) -> float:

@@ -191,9 +191,36 @@ static double ss_shapiro(double M, const double* obs_obj_pos, const double* Lhat
     return -2 * M * log((r - Ldotr) / AU);
 }
 
+/* Correctly rounded sin/cos (double-double Taylor series after reduction by pi/2).  The sky-position unit vector
+ * multiplies the ~500 s Roemer delay of EVERY TOA, so a 1-ulp library difference in these four values is a coherent
+ * ~1e-13 s term in all residuals; libm (like Julia's own sincos) is faithful to < 1 ulp but not always correctly
+ * rounded (glibc: ~0.3 % of arguments), which would make the oracle itself platform dependent at the 1e-9 level of
+ * ln L for walkers far from the maximum.  Rounding the exact value removes that ambiguity. */
+static void sincos_cr(double x, double* s_out, double* c_out) {
+    if (!isfinite(x) || fabs(x) > 1e6) { *s_out = sin(x); *c_out = cos(x); return; }
+    const dd pio2 = { 1.5707963267948966, 6.123233995736766e-17 };
+    double k = rint(x * 0.6366197723675814);
+    dd r = dd_sub(dd_from(x), dd_mul_d(pio2, k));
+    r = dd_add_d(r, -k * -1.4973849048591698e-33);
+    dd r2 = dd_mul(r, r);
+    dd st = r, ct = { 1.0, 0.0 }, ssum = r, csum = { 1.0, 0.0 };
+    for (int n = 1; n <= 15; ++n) {
+        ct = dd_div_d(dd_mul(ct, r2), -(double)((2 * n - 1) * (2 * n)));
+        st = dd_div_d(dd_mul(st, r2), -(double)((2 * n) * (2 * n + 1)));
+        csum = dd_add(csum, ct);
+        ssum = dd_add(ssum, st);
+    }
+    int q = ((int)(long long)k) & 3;
+    double sv = ssum.hi, cv = csum.hi;
+    *s_out = (q == 0) ? sv : (q == 1) ? cv : (q == 2) ? -sv : -cv;
+    *c_out = (q == 0) ? cv : (q == 1) ? -sv : (q == 2) ? -cv : sv;
+}
+
 /* evaluate_proper_motion solarsystem.jl:45-64 */
 static void evaluate_proper_motion(double a0, double d0, double pma, double pmd, double dt, double* out) {
-    double sa = sin(a0), ca = cos(a0), sd = sin(d0), cd = cos(d0);
+    double sa, ca, sd, cd;
+    sincos_cr(a0, &sa, &ca);
+    sincos_cr(d0, &sd, &cd);
     double x0[3] = { ca * cd, sa * cd, sd };
     if (pma == 0.0 && pmd == 0.0) { out[0] = x0[0]; out[1] = x0[1]; out[2] = x0[2]; return; }
     double xa[3] = { -sa * pma, ca * pma, 0.0 };
@@ -1077,6 +1104,7 @@ ORACLE_API double oracle_gls_lnlike_raw(const double* M, int64_t n, int64_t p, c
     return r;
 }
 
+ORACLE_API void oracle_sincos_cr(double x, double* s, double* c) { sincos_cr(x, s, c); }
 ORACLE_API double oracle_mikkola(double l, double e) { int bad = 0; return mikkola(l, e, &bad); }
 ORACLE_API double oracle_powerlaw(double A, double gamma, double f, double f1) { return powerlaw(A, gamma, f, f1); }
 ORACLE_API int oracle_max_threads(void) {

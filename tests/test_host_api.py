@@ -97,22 +97,6 @@ def test_descriptor_offsets(vb, golden):
     assert [g3.gp[i].kind for i in range(3)] == [D.GP_POWERLAW_RED, D.GP_POWERLAW_DM, D.GP_POWERLAW_CHROM]
 
 
-def test_unsupported_kernels_are_rejected_not_silently_ignored(vb, golden):
-    """WoodburyKernel{EcorrKernel} is a 'next' row: create() must refuse it (VELA_ERR_UNSUPPORTED), never ignore ECORR."""
-    g = golden("sim2")
-    M = vb.model
-    basis = np.ones((len(g.toas), 2))
-    kernel = M.WoodburyKernel(g.model.kernel, [M.MarginalizedTimingModel(weights=[1e40, 1e40], pnames=["PHOFF", "F0"])], basis)
-    m2 = M.TimingModel(g.model.pulsar_name, g.model.ephem, g.model.clock, g.model.units, g.model.epoch,
-                       g.model.components, kernel, g.model.param_handler, g.model.tzr_toa, g.model.priors)
-    md = vb.ModelDescriptor(m2, g.toas)
-    assert md.desc.kernel_kind == vb.descriptor.KERNEL_WOODBURY_ECORR
-    h = ctypes.c_void_p()
-    L = vb.lib.lib()
-    assert L.vela_b200_create(md.byref(), ctypes.byref(h)) == -4
-    assert b"EcorrKernel" in L.vela_b200_last_error()
-
-
 def test_ecorr_descriptor(vb, golden):
     g = golden("sim2")
     d = g.md.desc

@@ -11,6 +11,16 @@ def test_mikkola_round_trip(oracle):
             assert oracle.mikkola(u - e * np.sin(u), e) == pytest.approx(u, rel=1e-8, abs=1e-12)
 
 
+def test_sincos_correctly_rounded(oracle):
+    """The oracle's sky-position sin/cos equals the exactly rounded value (mpmath, 200 bits)."""
+    import mpmath
+    mpmath.mp.prec = 200
+    rng = np.random.default_rng(11)
+    for x in np.concatenate([rng.uniform(-7, 7, 400), rng.uniform(-500, 500, 50), [0.0, 4.663868852922854, -0.3553169573849282]]):
+        s, c = oracle.sincos_cr(float(x))
+        assert s == float(mpmath.sin(mpmath.mpf(float(x)))) and c == float(mpmath.cos(mpmath.mpf(float(x))))
+
+
 def test_gls_lnlike_identities(oracle):
     """test/test_woodbury_kernel.jl:37-92 with the same shapes (100 x 5, random)."""
     rng = np.random.default_rng(5)

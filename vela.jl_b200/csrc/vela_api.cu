@@ -54,7 +54,7 @@ struct Buffers {  // per-device, per-batch scratch (grown on demand)
     long cap_B = 0;
     long sig_rows = 0;   // walker rows of the Sigma / U scratch (>= cap_B; larger so small batches can split K)
     double *params = nullptr, *Pext = nullptr, *tzr = nullptr, *partial = nullptr, *Y = nullptr, *W = nullptr;
-    double *Sig = nullptr, *U = nullptr, *Sq = nullptr, *out = nullptr, *lnprior = nullptr;
+    double *Sig = nullptr, *U = nullptr, *Sq = nullptr, *V = nullptr, *out = nullptr, *lnprior = nullptr;
     double *h_params = nullptr, *h_out = nullptr, *h_lnprior = nullptr;  // pinned
     long h_cap = 0;
 };
@@ -75,6 +75,7 @@ struct DeviceModel {
     double* gp_data = nullptr;
     int3* ecorr_groups = nullptr;
     int* ecorr_chunks = nullptr;
+    int3* ecorr_active = nullptr;   // groups with an ECORR parameter (index >= 1), for the Woodbury correction
     Buffers buf;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[5] = {0, 0, 0, 0, 0};
@@ -92,6 +93,8 @@ struct VelaPulsar {
     size_t sig_smem = 0;
     int chain_threads = 256, chain_group = 32, n_tiles = 0;
     int n_ecorr_groups = 0, n_ecorr_chunks = 0, par_ecorr = -1;   // EcorrKernel: group corrections occupy partial rows n_tiles..
+    int n_eg = 0, n_rect = 0;        // WoodburyKernel{EcorrKernel}: active groups, 32x32 rectangles of the (p+1) triangle
+    long eg_pad = 0, ldv = 0;
     bool chol_smem = true;
     size_t chol_smem_bytes = 0;
     std::vector<DeviceModel> devs;
@@ -105,8 +108,8 @@ namespace {
 
 void free_buffers(Buffers& b) {
     cudaFree(b.params); cudaFree(b.Pext); cudaFree(b.tzr); cudaFree(b.partial); cudaFree(b.Y); cudaFree(b.W);
-    cudaFree(b.Sig); cudaFree(b.U); cudaFree(b.Sq); cudaFree(b.out); cudaFree(b.lnprior);
-    b.params = b.Pext = b.tzr = b.partial = b.Y = b.W = b.Sig = b.U = b.Sq = b.out = b.lnprior = nullptr;
+    cudaFree(b.Sig); cudaFree(b.U); cudaFree(b.Sq); cudaFree(b.V); cudaFree(b.out); cudaFree(b.lnprior);
+    b.params = b.Pext = b.tzr = b.partial = b.Y = b.W = b.Sig = b.U = b.Sq = b.V = b.out = b.lnprior = nullptr;
     b.cap_B = 0;
     b.sig_rows = 0;
 }
@@ -139,6 +142,11 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
         CU(cudaMemsetAsync(b.Sig, 0, (size_t)b.sig_rows * h->ld_sig * sizeof(double), d.stream));
         CU(cudaMemsetAsync(b.U, 0, (size_t)b.sig_rows * h->pp * sizeof(double), d.stream));
         if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * h->pp * h->pp * sizeof(double)));
+        if (h->n_eg > 0) {
+            size_t vb = (size_t)cap * h->eg_pad * h->ldv * sizeof(double);
+            CU(cudaMalloc((void**)&b.V, vb));
+            CU(cudaMemsetAsync(b.V, 0, vb, d.stream));   // padding rows / columns stay zero
+        }
     }
     b.cap_B = cap;
     return 0;
@@ -177,6 +185,28 @@ const SigmaShape kSigmaShapes[] = {
     VELA_SHAPE(16, 3, 4, 4, 16, 1), VELA_SHAPE(16, 2, 4, 4, 16, 1), VELA_SHAPE(8, 2, 4, 4, 16, 1),
 };
 
+// WoodburyKernel{EcorrKernel}: subtract the per-group Sherman-Morrison terms from slab 0 of Sigma / U (K2b + K2c).
+void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st) {
+    Buffers& b = d.buf;
+    EcorrBasisArgs ba;
+    ba.M = d.M; ba.ldM = d.ldM; ba.rank = h->p; ba.Pext = b.Pext; ba.row = h->prog.row; ba.par_ecorr = h->par_ecorr;
+    ba.Y = b.Y; ba.W = b.W; ba.ld_yw = h->n_rows_pad; ba.B = B; ba.groups = d.ecorr_active; ba.n_groups = h->n_eg;
+    ba.groups_per_block = 16; ba.V = b.V; ba.g_pad = h->eg_pad; ba.ldv = h->ldv;
+    dim3 grid((unsigned)((h->n_eg + ba.groups_per_block - 1) / ba.groups_per_block), (unsigned)((B + 31) / 32));
+    const size_t sm = ((size_t)32 * (h->p + 1) + 2 * 32 * 33) * sizeof(double);
+    const int nacc = (h->p + 7) / 8;
+    if (nacc <= 8) ecorr_basis_kernel<8><<<grid, 256, sm, st>>>(ba);
+    else if (nacc <= 16) ecorr_basis_kernel<16><<<grid, 256, sm, st>>>(ba);
+    else if (nacc <= 40) ecorr_basis_kernel<40><<<grid, 256, sm, st>>>(ba);
+    else ecorr_basis_kernel<128><<<grid, 256, sm, st>>>(ba);
+    EcorrSyrkArgs sa;
+    sa.V = b.V; sa.g_pad = h->eg_pad; sa.ldv = h->ldv; sa.rank = h->p; sa.n_rect = h->n_rect; sa.B = B;
+    sa.Sig = b.Sig; sa.ld_sig = h->ld_sig; sa.U = b.U; sa.ld_u = h->pp;
+    const long warps = B * h->n_rect;
+    ecorr_syrk_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(sa);
+    h->launches += 2;
+}
+
 // Fills the launch arguments, picks split-K and launches K3; returns the split count K4 has to sum.
 int launch_sigma(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, SigmaArgs* out_args = nullptr) {
     const SigmaShape& sh = kSigmaShapes[h->sig_shape];
@@ -208,6 +238,10 @@ int set_smem_attrs(int dev) {
     for (const SigmaShape& sh : kSigmaShapes)
         CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(chol_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
+    CU(cudaFuncSetAttribute(ecorr_basis_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(ecorr_basis_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(ecorr_basis_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(ecorr_basis_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(toa_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     return 0;
 }
@@ -253,6 +287,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
     } else {
         SigmaArgs sa;
         const int ksplit = launch_sigma(h, d, B, st, &sa);
+        if (h->n_eg > 0) launch_ecorr_correction(h, d, B, st);
         if (timing) cudaEventRecord(d.ev[3], st);
         CholArgs ch;
         ch.Sig = b.Sig; ch.ld_sig = h->ld_sig; ch.ld_u = h->pp; ch.Sq = b.Sq; ch.U = b.U; ch.Pext = b.Pext; ch.row = pg.row; ch.p = h->p; ch.pp = h->pp; ch.n_gp = h->n_gp;
@@ -270,7 +305,8 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
 
 int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const std::vector<double>& toa_soa,
                  const std::vector<double>& tzr_block, const std::vector<GPDev>& gps,
-                 const std::vector<double>& gp_data, const std::vector<int3>& egroups, const std::vector<int>& echunks) {
+                 const std::vector<double>& gp_data, const std::vector<int3>& egroups, const std::vector<int>& echunks,
+                 const std::vector<int3>& eactive) {
     CU(cudaSetDevice(d.dev));
     CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     for (auto& e : d.ev) CU(cudaEventCreate(&e));
@@ -283,6 +319,7 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
     if (!egroups.empty()) {
         if (upload(&d.ecorr_groups, egroups.data(), egroups.size())) return VELA_ERR_CUDA;
         if (upload(&d.ecorr_chunks, echunks.data(), echunks.size())) return VELA_ERR_CUDA;
+        if (upload(&d.ecorr_active, eactive.data(), eactive.size())) return VELA_ERR_CUDA;
     }
     if (h->p > 0) {
         // M: column-major with the leading dimension padded (zero rows) to n_rows_pad, columns padded to pp
@@ -306,7 +343,7 @@ void destroy_device(DeviceModel& d) {
     if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
     if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
-    cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks);
+    cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
 }
@@ -354,9 +391,8 @@ int validate(const VelaModelDesc* d) {
             if ((bits && m == 0) ? (c.mask[m] + c.len[0] > d->n_bit_mask_rows) : (c.mask[m] >= d->n_index_masks)) return fail(VELA_ERR_INVALID_ARG, "component %d: mask %d out of range", ic, c.mask[m]);
         }
     }
-    if (d->kernel_kind == VELA_KERNEL_WOODBURY_ECORR) return fail(VELA_ERR_UNSUPPORTED, "WoodburyKernel{EcorrKernel} is not on the GPU path yet (next row, DESIGN.md section 8)");
-    if (d->kernel_kind != VELA_KERNEL_WHITE && d->kernel_kind != VELA_KERNEL_WOODBURY_WHITE && d->kernel_kind != VELA_KERNEL_ECORR) return fail(VELA_ERR_UNSUPPORTED, "kernel kind %d is outside the implemented hot path", d->kernel_kind);
-    if (d->kernel_kind == VELA_KERNEL_ECORR) {
+    if (d->kernel_kind < VELA_KERNEL_WHITE || d->kernel_kind > VELA_KERNEL_WOODBURY_ECORR) return fail(VELA_ERR_UNSUPPORTED, "kernel kind %d is outside the implemented hot path", d->kernel_kind);
+    if (d->kernel_kind == VELA_KERNEL_ECORR || d->kernel_kind == VELA_KERNEL_WOODBURY_ECORR) {
         if (d->wideband) return fail(VELA_ERR_INVALID_ARG, "ECORR kernels are narrowband only");
         if (d->n_ecorr_groups <= 0 || !d->ecorr_groups) return fail(VELA_ERR_INVALID_ARG, "EcorrKernel without groups");
         uint64_t next = 1;
@@ -368,7 +404,7 @@ int validate(const VelaModelDesc* d) {
         }
         if (next != (uint64_t)d->n_toas + 1) return fail(VELA_ERR_INVALID_ARG, "ECORR groups do not cover all TOAs");
     }
-    if (d->kernel_kind == VELA_KERNEL_WOODBURY_WHITE) {
+    if (d->kernel_kind == VELA_KERNEL_WOODBURY_WHITE || d->kernel_kind == VELA_KERNEL_WOODBURY_ECORR) {
         long nr = d->wideband ? 2 * d->n_toas : d->n_toas;
         if (d->basis_rows != nr || d->basis_cols <= 0 || d->basis_ld < nr || !d->noise_basis) return fail(VELA_ERR_INVALID_ARG, "noise_basis shape (%ld x %ld, ld %ld) does not match %ld rows", (long)d->basis_rows, (long)d->basis_cols, (long)d->basis_ld, nr);
         if (d->basis_cols > kSigMaxRank) return fail(VELA_ERR_UNSUPPORTED, "basis rank %ld > %d", (long)d->basis_cols, kSigMaxRank);
@@ -431,7 +467,8 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
 
     std::vector<int3> egroups;
     std::vector<int> echunks;
-    if (desc->kernel_kind == VELA_KERNEL_ECORR) {
+    std::vector<int3> eactive;
+    if (desc->kernel_kind == VELA_KERNEL_ECORR || desc->kernel_kind == VELA_KERNEL_WOODBURY_ECORR) {
         // groups without ECORR (index 0) need no correction; the others are packed into chunks of ~64 TOAs per thread
         h->par_ecorr = desc->par_ecorr;
         echunks.push_back(0);
@@ -439,6 +476,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         for (int g = 0; g < desc->n_ecorr_groups; ++g) {
             const uint64_t* e = desc->ecorr_groups + 3 * g;
             egroups.push_back(make_int3((int)(e[0] - 1), (int)e[1], (int)e[2]));
+            if (e[2]) eactive.push_back(egroups.back());
             in_chunk += e[2] ? (long)(e[1] - e[0] + 1) : 0;
             if (in_chunk >= 64) { echunks.push_back(g + 1); in_chunk = 0; }
         }
@@ -448,8 +486,15 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     }
     std::vector<GPDev> gps;
     std::vector<double> gp_data;
-    if (desc->kernel_kind == VELA_KERNEL_WOODBURY_WHITE) {
+    if (desc->kernel_kind == VELA_KERNEL_WOODBURY_WHITE || desc->kernel_kind == VELA_KERNEL_WOODBURY_ECORR) {
         h->p = (int)desc->basis_cols;
+        if (desc->kernel_kind == VELA_KERNEL_WOODBURY_ECORR && !eactive.empty()) {
+            h->n_eg = (int)eactive.size();
+            h->eg_pad = round_up(h->n_eg, 4);
+            const int nr = (h->p + 1 + 31) / 32;      // 32-column rectangles over [M | r]
+            h->ldv = (long)nr * 32;
+            h->n_rect = nr * (nr + 1) / 2;
+        }
         h->pp = (h->p + 7) / 8 * 8;
         h->n_gp = desc->n_gp;
         h->n_pairs = (long)h->p * (h->p + 1) / 2;
@@ -519,7 +564,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     for (size_t i = 0; i < devices.size(); ++i) {
         h->devs[i].dev = devices[i];
         h->devs[i].toa_stride = stride;
-        int rc = build_device(h, h->devs[i], desc, soa, tzr, gps, gp_data, egroups, echunks);
+        int rc = build_device(h, h->devs[i], desc, soa, tzr, gps, gp_data, egroups, echunks, eactive);
         if (rc) {
             for (auto& d : h->devs) destroy_device(d);
             delete h;
@@ -531,7 +576,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
 
     // walkers per device per pass: bound the y/w/Sigma scratch to ~1/4 of the device memory
     if (h->kernel_kind != VELA_KERNEL_WHITE) {
-        size_t per = (size_t)2 * h->n_rows_pad * 8 + (size_t)h->ld_sig * 8 + (size_t)h->pp * 8 + (h->chol_smem ? 0 : (size_t)h->pp * h->pp * 8);
+        size_t per = (size_t)2 * h->n_rows_pad * 8 + (size_t)h->ld_sig * 8 + (size_t)h->pp * 8 + (h->chol_smem ? 0 : (size_t)h->pp * h->pp * 8) + (size_t)h->eg_pad * h->ldv * 8;
         size_t free_b = 0, total_b = 0;
         cudaSetDevice(devices[0]);
         cudaMemGetInfo(&free_b, &total_b);
@@ -772,6 +817,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     toa_chain_kernel<<<dim3((unsigned)h->n_tiles, 1), h->chain_threads, chain_smem, d.stream>>>(h->prog, ca);
     SigmaArgs sa;
     const int ksplit = launch_sigma(h, d, 1, d.stream, &sa);
+    if (h->n_eg > 0) launch_ecorr_correction(h, d, 1, d.stream);
     h->launches += 3;
     std::vector<double> S((size_t)h->ld_sig, 0.0), U(h->pp, 0.0), tS((size_t)h->ld_sig), tU(h->pp);
     for (int z = 0; z < ksplit; ++z) {   // sum the split-K slabs in slice order, as K4 does

@@ -206,6 +206,131 @@ __global__ void __launch_bounds__(128) ecorr_group_kernel(EcorrArgs a) {
     a.partial[((size_t)(a.first_row + c) * a.B + b) * 2 + 1] = dlg;
 }
 
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- WoodburyKernel{EcorrKernel}: per-group Sherman-Morrison (_calc_Ninv_M, gls_ecorr_likelihood.jl:66-137).
+// With P_g = sum_{i in g} w_i M_i (a p-vector), Q_g = sum w_i, r_g = sum w_i y_i and alpha_g = W/(1 + W Q_g):
+//   M^T Nc^-1 M = M^T N^-1 M - sum_g alpha_g P_g P_g^T,      M^T Nc^-1 y = M^T N^-1 y - sum_g alpha_g r_g P_g.
+// K2b builds V_b[g] = sqrt(alpha_g) [P_g | r_g] for every walker b; K2c subtracts V_b^T V_b (a per-walker SYRK on the
+// FP64 tensor cores) from the Sigma / u that K3 produced for the white part.
+//
+// K2b: block = 32 walkers x 8 column slices; one pass = the TOAs of one ECORR group (<= 32 at a time) staged in
+// shared memory (M rows, w, y), accumulators in registers, NACC = ceil(columns / 8) per thread.
+template <int NACC>
+__global__ void __launch_bounds__(256) ecorr_basis_kernel(EcorrBasisArgs a) {
+    extern __shared__ double smem[];
+    const int p = a.rank, pc = p + 1;            // smem row pitch (odd -> conflict-free)
+    double* sM = smem;                            // [32 TOAs][pc]
+    double* sW = sM + 32 * pc;                    // [32 walkers][33]
+    double* sY = sW + 32 * 33;
+    const int tid = threadIdx.x, s = tid >> 3, c = tid & 7;
+    const long b0 = (long)blockIdx.y * 32;
+    const long b = b0 + s;
+    const bool live = b < a.B;
+    const int g_begin = blockIdx.x * a.groups_per_block, g_end = min(g_begin + a.groups_per_block, a.n_groups);
+    for (int g = g_begin; g < g_end; ++g) {
+        const int3 grp = a.groups[g];             // [first, last) TOA, ECORR index >= 1
+        double acc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+        double Q = 0.0, ru = 0.0;
+        for (int j0 = grp.x; j0 < grp.y; j0 += 32) {
+            const int nj = min(32, grp.y - j0);
+            __syncthreads();
+            for (int e = tid; e < p * 32; e += 256) {
+                int col = e >> 5, i = e & 31;
+                sM[i * pc + col] = i < nj ? a.M[(size_t)col * a.ldM + j0 + i] : 0.0;
+            }
+            for (int e = tid; e < 32 * 32; e += 256) {
+                int ss = e >> 5, i = e & 31;
+                bool ok = i < nj && b0 + ss < a.B;
+                sW[ss * 33 + i] = ok ? a.W[(size_t)(b0 + ss) * a.ld_yw + j0 + i] : 0.0;
+                sY[ss * 33 + i] = ok ? a.Y[(size_t)(b0 + ss) * a.ld_yw + j0 + i] : 0.0;
+            }
+            __syncthreads();
+            for (int i = 0; i < nj; ++i) {
+                const double w = sW[s * 33 + i];
+                Q += w;
+                ru += w * sY[s * 33 + i];
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) {
+                    int col = c + 8 * k;
+                    if (col < p) acc[k] += sM[i * pc + col] * w;
+                }
+            }
+        }
+        if (live) {
+            const double ecorr = a.Pext[(size_t)b * a.row + a.par_ecorr + grp.z - 1];
+            const double wt = ecorr * ecorr;
+            const double sa = sqrt(wt / (1 + wt * Q));
+            double* v = a.V + ((size_t)b * a.g_pad + g) * a.ldv;
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) {
+                int col = c + 8 * k;
+                if (col < p) v[col] = sa * acc[k];
+            }
+            if (c == 0) v[p] = sa * ru;
+        }
+    }
+}
+template __global__ void ecorr_basis_kernel<8>(EcorrBasisArgs);
+template __global__ void ecorr_basis_kernel<16>(EcorrBasisArgs);
+template __global__ void ecorr_basis_kernel<40>(EcorrBasisArgs);
+template __global__ void ecorr_basis_kernel<128>(EcorrBasisArgs);
+
+// K2c: C_b = V_b^T V_b over the ECORR groups, one warp = one walker x one 32 x 32 rectangle (4 x 4 m8n8k4 tiles) of
+// the lower block triangle; fragments come straight from global/L2 (V_b rows are 64-byte segments per lane group).
+// Row p of V (the r_g column) yields the correction to u.  The result is subtracted from slab 0 of Sigma / U.
+__global__ void __launch_bounds__(256) ecorr_syrk_kernel(EcorrSyrkArgs a) {
+    const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= a.B * a.n_rect) return;
+    const long b = wid / a.n_rect;
+    int rect = (int)(wid - b * a.n_rect);
+    int ri = 0;
+    while ((ri + 1) * (ri + 2) / 2 <= rect) ++ri;
+    const int cj = rect - ri * (ri + 1) / 2;
+    const double* V = a.V + (size_t)b * a.g_pad * a.ldv;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double* pa = V + (size_t)tig * a.ldv + ri * 32 + gid;
+    const double* pb = V + (size_t)tig * a.ldv + cj * 32 + gid;
+    for (int g0 = 0; g0 < a.g_pad; g0 += 4) {
+        double fa[4], fb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            fa[i] = pa[i * 8];
+            fb[i] = pb[i * 8];
+        }
+        pa += 4 * a.ldv;
+        pb += 4 * a.ldv;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+    }
+    const int p = a.rank;
+    double* sig = a.Sig + (size_t)b * a.ld_sig;
+    double* u = a.U + (size_t)b * a.ld_u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int pp = (ri * 4 + i) * 8 + gid, qq = (cj * 4 + j) * 8 + 2 * tig + r;
+                if (pp < p && qq <= pp) sig[(size_t)pp * (pp + 1) / 2 + qq] -= acc[i][j][r];
+                else if (pp == p && qq < p) u[qq] -= acc[i][j][r];
+            }
+}
+
 // ------------------------------------------------------------------------------------------
 // K3  Sigma^-1 contraction on the FP64 tensor cores
 // ------------------------------------------------------------------------------------------
@@ -228,11 +353,6 @@ __global__ void __launch_bounds__(128) ecorr_group_kernel(EcorrArgs a) {
 // packed rows, 8x4 warp tile x 8 warps: __syncthreads ring 11.32, mbarrier ring 11.10, 1-D bulk copies
 // (cp.async.bulk; UBLKCP is a uniform-datapath instruction, so per-lane rows serialise) 13.96;
 // 4x4 warp tile: 8 warps x 2 CTAs/SM 10.61, 16 warps x 1 CTA/SM (this kernel) 10.50.
-__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -65,6 +65,38 @@ struct EcorrArgs {
     double* partial;
 };
 
+struct EcorrBasisArgs {
+    const double* M;           // column-major noise basis
+    long ldM;
+    int rank;
+    const double* Pext;
+    int row;
+    int par_ecorr;
+    const double* Y;
+    const double* W;
+    long ld_yw;
+    long B;
+    const int3* groups;        // ECORR-active groups only (index >= 1)
+    int n_groups;
+    int groups_per_block;
+    double* V;                 // [B][g_pad][ldv]: sqrt(alpha_g) [P_g | r_g | 0...]
+    long g_pad;
+    long ldv;
+};
+
+struct EcorrSyrkArgs {
+    const double* V;
+    long g_pad;
+    long ldv;
+    int rank;
+    int n_rect;                // 32 x 32 rectangles of the lower block triangle of (rank + 1)
+    long B;
+    double* Sig;
+    long ld_sig;
+    double* U;
+    long ld_u;
+};
+
 struct GPDev {
     int kind, n, par_log10_amp, par_gamma, par_f1;
     int col0;                  // first basis column of this GP component
@@ -101,6 +133,9 @@ __global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, 
                                        double* Pext, double* tzr_phase);
 __global__ void toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a);
 __global__ void ecorr_group_kernel(EcorrArgs a);
+template <int NACC>
+__global__ void ecorr_basis_kernel(EcorrBasisArgs a);
+__global__ void ecorr_syrk_kernel(EcorrSyrkArgs a);
 __global__ void finish_white_kernel(const double* partial, int n_tiles, long B, int mode, const double* lnprior,
                                     int with_prior, double* out);
 template <int BK, int STAGES, int MT, int NT, int WARPS>

@@ -152,6 +152,10 @@ CONFIGS = {
                          nback=1, walkers=128, seed=16),
     "extra_ddh": dict(ntoa=700, span_d=2500.0, binary="DDH", fbx=True, nback=2, walkers=128, seed=17),
     "extra_dds": dict(ntoa=700, span_d=2500.0, binary="DDS", nback=2, walkers=128, seed=18),
+    # ECORR kernels: epochs of 8 TOAs (one per observing frequency) form the ECORR groups
+    "extra_ecorr": dict(ntoa=1600, span_d=3000.0, ecorr=True, nback=3, walkers=256, seed=19),
+    "extra_ecorr_gp": dict(ntoa=1600, span_d=3000.0, ecorr=True, red=12, dmgp=10, nback=3, walkers=256, seed=20),
+    "config3_gp_ecorr": dict(ntoa=10000, span_d=4000.0, red=30, ecorr=True, nback=4, walkers=8192, seed=21),
 }
 
 
@@ -346,6 +350,11 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
     for i in range(nback):
         noise_draw_names[f"EFAC{i + 1}"] = ("lognormal", efac_true[i], 0.05)
         noise_draw_names[f"EQUAD{i + 1}"] = ("loguniform", 0.5 * equad_true[i], 2.0 * equad_true[i])
+    ecorr_true = np.exp(rng.uniform(np.log(2e-7), np.log(8e-7), nback))
+    if cfg.get("ecorr"):
+        mp("ECORR", ecorr_true, [True] * nback, dim=1, noise=True, prefix="ECORR", sig=[0.0] * nback)
+        for i in range(nback):
+            noise_draw_names[f"ECORR{i + 1}"] = ("loguniform", 0.5 * ecorr_true[i], 2.0 * ecorr_true[i])
     if wide:
         mp("DMEFAC", [1.05], [True], noise=True, prefix="DMEFAC", sig=[0.0])
         mp("DMEQUAD", [0.5e-4 * DMCONST], [True], dim=-1, noise=True, prefix="DMEQUAD", sig=[0.0])
@@ -436,6 +445,16 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
     efac_j = efac_true[backend - 1]
     equad_j = equad_true[backend - 1]
     noise = efac_j * np.sqrt(err**2 + equad_j**2) * rng.standard_normal(n)
+    inner_kernel: M.Kernel = M.WhiteNoiseKernel()
+    if cfg.get("ecorr"):
+        # one ECORR group per epoch of 8 TOAs; the first 16 TOAs carry no ECORR (index 0), as pyvela's ecorr_sort
+        # puts un-grouped TOAs first (pyvela/pyvela/ecorr.py:52-57)
+        starts = list(range(16, n, 8))
+        groups = [(1, 16, 0)] + [(a + 1, min(a + 8, n), int(backend[a])) for a in starts]
+        inner_kernel = M.EcorrKernel(np.array(groups, dtype=np.uint64))
+        for a0, a1, idx in groups:
+            if idx:
+                noise[a0 - 1:a1] += ecorr_true[idx - 1] * rng.standard_normal()
     tspan = t.max() - t.min()
     nu_ratio2 = (1400e6 / freq) ** 2
     blocks, gps = [], []
@@ -474,7 +493,7 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         blocks.append(np.stack([np.concatenate([c, d]) if wide else c for c, d in zip(cols, dmrows)], axis=1))
         gps.append(M.MarginalizedTimingModel(weights=np.full(4, 1e40), pnames=["PHOFF", "F0", "F1", "DM"]))
 
-    kernel = M.WoodburyKernel(M.WhiteNoiseKernel(), gps, np.concatenate(blocks, axis=1)) if gps else M.WhiteNoiseKernel()
+    kernel = M.WoodburyKernel(inner_kernel, gps, np.concatenate(blocks, axis=1)) if gps else inner_kernel
     model, toas = build(t_hi, t_lo, pn, kernel, dm=dm_meas)
     ev = make_eval(model, toas)
 
@@ -487,20 +506,24 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         if nme in noise_draw_names:
             noise_draw[k] = noise_draw_names[nme]
             continue
+        # geometric search for a step that moves the residuals by ~1 sigma in total (chi ~ 1)
         h = max(abs(x0[k]) * 1e-9, 1e-30)
-        for _ in range(6):
+        chi = 0.0
+        for _ in range(60):
             xp = x0.copy()
             xp[k] += h
             yk, _ = ev.resids_and_Ninvdiag(xp)
             d = (yk - y0)
-            chi = np.sqrt(np.sum(d * d * w0))
-            if not np.isfinite(chi) or chi == 0.0:
-                h *= 100.0
-                continue
-            if 0.05 < chi < 20.0:
+            chi = float(np.sqrt(np.sum(d * d * w0)))
+            if np.isfinite(chi) and 0.05 < chi < 20.0:
                 break
-            h *= 1.0 / chi
-        sig[k] = h / chi if (np.isfinite(chi) and chi > 0) else 0.0
+            if not np.isfinite(chi):
+                h /= 1024.0
+            elif chi < 1e-3:          # below the rounding noise of the residuals: no usable slope information yet
+                h *= 1024.0
+            else:
+                h *= min(max(1.0 / chi, 1.0 / 1024), 1024.0)
+        sig[k] = h / chi if (np.isfinite(chi) and 0.05 < chi < 20.0) else 0.0
     info = dict(config=name, ntoa=n, wideband=wide, nfree=len(names), rank=int(kernel.noise_basis.shape[1]) if gps else 0,
                 connect_rms_s=connect_rms, free_names=names)
     return SynthDataset(name, model, toas, x0, sig, noise_draw, info)
