@@ -181,7 +181,7 @@ def main():
         else:
             w = 50 * max(ds.sigma_par[k], 1e-300)
             priors.append(vb.priors.SimplePrior(f"p{k}", vb.priors.Uniform(ds.truth[k] - w, ds.truth[k] + w)))
-    ds.model.priors = tuple(priors)
+    psr.set_priors(priors)          # uploads them to the device as well (all families have device twins)
 
     n_sets = 4   # rotate distinct walker batches so no step sees the previous step's inputs
     host_sets = [ds.walkers(B, seed=1000 * (rank + 1) + i) for i in range(n_sets)]

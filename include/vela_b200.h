@@ -294,6 +294,43 @@ VELA_API int vela_b200_chi2_batch(VelaHandle h, const double* params, int64_t B,
 VELA_API int vela_b200_residuals(VelaHandle h, const double* params, int64_t n_free, double* y, double* w);
 
 /*
+ * Device-side priors (optional).  The reference evaluates one univariate prior per free parameter on the host
+ * (lnprior, src/prior/prior.jl:13-19; SimplePrior / SimplePriorMulti, src/prior/simple_prior.jl:17-55; custom
+ * distributions, src/prior/known_priors.jl:33-100; defaults pyvela/pyvela/priors.py:30-76).  After
+ * vela_b200_set_priors the library evaluates them itself: vela_b200_lnpost_batch with lnprior == NULL then returns
+ * lnprior + lnlike with the reference's -Inf short-circuit (posterior.jl:9-12) instead of assuming a flat prior.
+ * One descriptor per free parameter, in free-parameter order.
+ */
+typedef enum VelaPriorKind {
+    VELA_PRIOR_UNIFORM = 1,        /* Uniform(a, b) */
+    VELA_PRIOR_NORMAL = 2,         /* Normal(mu = a, sigma = b) */
+    VELA_PRIOR_LOGNORMAL = 3,      /* LogNormal(mu = a, sigma = b) */
+    VELA_PRIOR_LOGUNIFORM = 4,     /* LogUniform(a, b) */
+    VELA_PRIOR_KIN = 5,            /* KINPriorDistribution, known_priors.jl:33-37 */
+    VELA_PRIOR_SINI = 6,           /* SINIPriorDistribution, known_priors.jl:45-49 */
+    VELA_PRIOR_STIGMA = 7,         /* STIGMAPriorDistribution, known_priors.jl:57-61 */
+    VELA_PRIOR_SHAPMAX = 8,        /* SHAPMAXPriorDistribution, known_priors.jl:69-73 */
+    VELA_PRIOR_PX = 9,             /* PXPriorDistribution(Rmax = a), known_priors.jl:82-88 */
+    VELA_PRIOR_LATITUDE = 10,      /* LatitudePriorDistribution, known_priors.jl:96-100 */
+    VELA_PRIOR_TRUNCATED_NORMAL = 11 /* truncated(Normal(a, b), lo, hi) */
+} VelaPriorKind;
+
+typedef struct VelaPriorDesc {
+    int32_t kind;
+    int32_t _pad;
+    double a, b;                  /* distribution arguments, see VelaPriorKind */
+    double lo, hi;                /* truncation bounds (TRUNCATED_NORMAL only) */
+} VelaPriorDesc;
+
+VELA_API int vela_b200_set_priors(VelaHandle h, const VelaPriorDesc* priors, int32_t n_free);
+/* sum of logpdf over the free parameters for each row of params (calc_lnprior, prior.jl:18-19) */
+VELA_API int vela_b200_lnprior_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
+                                     int64_t row_stride, int64_t col_stride, double* out_lnprior);
+/* quantile of each prior at each unit-cube coordinate (prior_transform, prior.jl:31-32); cube and out are
+ * row-major (B x n_free) */
+VELA_API int vela_b200_prior_transform_batch(VelaHandle h, const double* cube, int64_t B, int64_t n_free, double* out);
+
+/*
  * Phase residuals before rounding to Float64, for ONE parameter vector: the Double64
  * `phase_residual(toa, ctoa) - tzrphase` (src/toa/toa.jl:151, src/residuals/residuals.jl:10) as (hi, lo)
  * and `doppler_shifted_spin_frequency(ctoa)` (src/toa/toa.jl:131-134), n_toas values each.

@@ -28,7 +28,7 @@ import numpy as np
 
 from . import lib as _lib
 from . import priors as _priors
-from .descriptor import ModelDescriptor
+from .descriptor import ModelDescriptor, prior_descriptors
 from .model import TimingModel, TOAs, WhiteNoiseKernel
 
 
@@ -51,6 +51,20 @@ class Pulsar:
         self._h = h
         self._finalizer = weakref.finalize(self, self._lib.vela_b200_destroy, h)
         self.ndim = model.param_handler._nfree
+        self.device_priors = False
+        self.set_priors(model.priors)
+
+    def set_priors(self, priors) -> bool:
+        """Upload the per-parameter priors to the device when every family has a device twin (§8f rank 3);
+        otherwise lnprior stays on the host, exactly as in the reference (posterior.jl:9-12)."""
+        self.model.priors = tuple(priors)
+        self.device_priors = False
+        if len(self.model.priors) == self.ndim and self.ndim > 0:
+            descs = prior_descriptors(self.model.priors)
+            if descs is not None:
+                _lib.check(self._lib.vela_b200_set_priors(self._h, descs, self.ndim), "vela_b200_set_priors")
+                self.device_priors = True
+        return self.device_priors
 
     # -- helpers
     def _free(self, params) -> np.ndarray:
@@ -94,8 +108,25 @@ class Pulsar:
     def prior_transform(self, cube):
         return _priors.prior_transform(self.model.priors, cube)
 
+    def lnprior_vectorized(self, paramss) -> np.ndarray:
+        a = np.asarray(paramss, dtype=np.float64)
+        if self.device_priors:
+            return self._batch(self._lib.vela_b200_lnprior_batch, a)
+        return np.asarray(_priors.lnprior(self.model.priors, a), dtype=np.float64)
+
+    def prior_transform_vectorized(self, cubes) -> np.ndarray:
+        q = np.ascontiguousarray(np.atleast_2d(cubes), dtype=np.float64)
+        if not self.device_priors:
+            return _priors.prior_transform(self.model.priors, q)
+        out = np.empty_like(q)
+        _lib.check(self._lib.vela_b200_prior_transform_batch(self._h, _dp(q), q.shape[0], q.shape[1], _dp(out)),
+                   "vela_b200_prior_transform_batch")
+        return out
+
     def lnpost_vectorized(self, paramss) -> np.ndarray:
         a = np.asarray(paramss, dtype=np.float64)
+        if self.device_priors:          # priors evaluated on the GPU inside the same call
+            return self._batch(self._lib.vela_b200_lnpost_batch, a, None)
         lnpr = np.ascontiguousarray(_priors.lnprior(self.model.priors, a), dtype=np.float64)
         return self._batch(self._lib.vela_b200_lnpost_batch, a, _dp(lnpr))
 

@@ -76,6 +76,7 @@ struct DeviceModel {
     int3* ecorr_groups = nullptr;
     int* ecorr_chunks = nullptr;
     int3* ecorr_active = nullptr;   // groups with an ECORR parameter (index >= 1), for the Woodbury correction
+    PriorDev* priors = nullptr;     // device-side priors (vela_b200_set_priors)
     Buffers buf;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[5] = {0, 0, 0, 0, 0};
@@ -101,6 +102,7 @@ struct VelaPulsar {
     std::mutex mtx;
     int64_t launches = 0;
     bool stage_timing = false;
+    bool have_priors = false;
     long max_chunk = 0;  // walkers per device per pass
 };
 
@@ -343,7 +345,7 @@ void destroy_device(DeviceModel& d) {
     if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
     if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
-    cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active);
+    cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active); cudaFree(d.priors);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
 }
@@ -642,7 +644,11 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
             if (timing) cudaEventRecord(d.ev[5], d.stream);
             cudaMemcpyAsync(b.params, b.h_params, sizeof(double) * n * std::max<long>(nf, 1), cudaMemcpyHostToDevice, d.stream);
             const double* d_lp = nullptr;
-            if (with_prior && lnprior) {
+            if (with_prior && !lnprior && h->have_priors) {
+                prior_kernel<<<(unsigned)((n + 127) / 128), 128, 0, d.stream>>>(d.priors, (int)nf, b.params, n, 0, b.lnprior);
+                h->launches += 1;
+                d_lp = b.lnprior;
+            } else if (with_prior && lnprior) {
                 memcpy(b.h_lnprior, lnprior + r0[i], sizeof(double) * n);
                 cudaMemcpyAsync(b.lnprior, b.h_lnprior, sizeof(double) * n, cudaMemcpyHostToDevice, d.stream);
                 d_lp = b.lnprior;
@@ -698,6 +704,11 @@ VELA_API int vela_b200_lnpost_batch_device(VelaHandle h, const double* d_params,
     int rc = ensure_device_buffers(h, d, B);
     cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
     if (!rc && st != d.stream && d.buf.cap_B != cap_before) cudaStreamSynchronize(d.stream);  // scratch zero-fills ran on the handle's stream
+    if (!rc && with_prior && !d_lnprior && h->have_priors) {   // device-side priors
+        prior_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(d.priors, h->prog.n_free, d_params, B, 0, d.buf.lnprior);
+        h->launches += 1;
+        d_lnprior = d.buf.lnprior;
+    }
     if (!rc) rc = enqueue_batch(h, d, d_params, B, 0, with_prior, d_lnprior, d_out, st);
     cudaSetDevice(prev);
     return rc;
@@ -788,6 +799,87 @@ VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int
     cudaSetDevice(prev);
     if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "noise_weights_inv: %s", cudaGetErrorString(e));
     return VELA_OK;
+}
+
+VELA_API int vela_b200_set_priors(VelaHandle h, const VelaPriorDesc* priors, int32_t n_free) {
+    if (!h || !priors) return fail(VELA_ERR_INVALID_ARG, "null handle / priors");
+    if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d priors, got %d (timing_model.jl:40)", h->prog.n_free, n_free);
+    std::vector<PriorDev> pd(std::max(n_free, 1));
+    for (int k = 0; k < n_free; ++k) {
+        const VelaPriorDesc& s = priors[k];
+        PriorDev& p = pd[k];
+        p.kind = s.kind; p.a = s.a; p.b = s.b; p.lo = s.lo; p.hi = s.hi; p.norm = 0.0;
+        switch (s.kind) {
+            case VELA_PRIOR_UNIFORM: if (!(s.b > s.a)) return fail(VELA_ERR_INVALID_ARG, "prior %d: Uniform needs a < b", k); p.norm = -std::log(s.b - s.a); break;
+            case VELA_PRIOR_NORMAL: case VELA_PRIOR_LOGNORMAL: if (!(s.b > 0)) return fail(VELA_ERR_INVALID_ARG, "prior %d: sigma must be positive", k); p.norm = std::log(s.b); break;
+            case VELA_PRIOR_LOGUNIFORM: if (!(s.a > 0 && s.b > s.a)) return fail(VELA_ERR_INVALID_ARG, "prior %d: LogUniform needs 0 < a < b", k); p.norm = std::log(std::log(s.b / s.a)); break;
+            case VELA_PRIOR_PX: if (!(s.a > 0)) return fail(VELA_ERR_INVALID_ARG, "prior %d: PX prior needs Rmax > 0", k); break;
+            case VELA_PRIOR_TRUNCATED_NORMAL: {
+                if (!(s.b > 0 && s.hi > s.lo)) return fail(VELA_ERR_INVALID_ARG, "prior %d: bad truncated normal", k);
+                double c0 = 0.5 * std::erfc(-(s.lo - s.a) / s.b / std::sqrt(2.0)), c1 = 0.5 * std::erfc(-(s.hi - s.a) / s.b / std::sqrt(2.0));
+                p.norm = std::log(s.b) + std::log(c1 - c0);
+                break;
+            }
+            case VELA_PRIOR_KIN: case VELA_PRIOR_SINI: case VELA_PRIOR_STIGMA: case VELA_PRIOR_SHAPMAX: case VELA_PRIOR_LATITUDE: break;
+            default: return fail(VELA_ERR_UNSUPPORTED, "prior %d: unknown kind %d", k, s.kind);
+        }
+    }
+    std::lock_guard<std::mutex> lock(h->mtx);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto& d : h->devs) {
+        cudaSetDevice(d.dev);
+        cudaFree(d.priors);
+        if (upload(&d.priors, pd.data(), pd.size())) { cudaSetDevice(prev); return VELA_ERR_CUDA; }
+    }
+    cudaSetDevice(prev);
+    h->have_priors = true;
+    return VELA_OK;
+}
+
+// mode 0: lnprior per row; mode 1: prior transform per element (device 0)
+static int run_prior(VelaHandle h, const double* in, int64_t B, int64_t n_free, int64_t rs, int64_t cs, int mode, double* out) {
+    if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
+    if (!h->have_priors) return fail(VELA_ERR_INVALID_ARG, "no priors set (vela_b200_set_priors)");
+    if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d free parameters, got %ld", h->prog.n_free, (long)n_free);
+    if (B <= 0) return VELA_OK;
+    std::lock_guard<std::mutex> lock(h->mtx);
+    DeviceModel& d = h->devs[0];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d.dev);
+    const size_t nin = (size_t)B * n_free, nout = mode == 0 ? (size_t)B : nin;
+    std::vector<double> tmp;
+    if (!(rs == n_free && cs == 1)) {
+        tmp.resize(nin);
+        for (int64_t r = 0; r < B; ++r)
+            for (int64_t k = 0; k < n_free; ++k) tmp[r * n_free + k] = in[r * rs + k * cs];
+        in = tmp.data();
+    }
+    double *din = nullptr, *dout = nullptr;
+    cudaError_t e = cudaMalloc((void**)&din, std::max<size_t>(nin, 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dout, nout * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(din, in, nin * sizeof(double), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) {
+        prior_kernel<<<(unsigned)((B + 127) / 128), 128, 0, d.stream>>>(d.priors, (int)n_free, din, B, mode, dout);
+        h->launches += 1;
+        e = cudaMemcpyAsync(out, dout, nout * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(d.stream);
+    if (e == cudaSuccess) e = e2;
+    cudaFree(din); cudaFree(dout);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "prior evaluation: %s", cudaGetErrorString(e));
+    return VELA_OK;
+}
+
+VELA_API int vela_b200_lnprior_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free, int64_t row_stride,
+                                     int64_t col_stride, double* out_lnprior) {
+    return run_prior(h, params, B, n_free, row_stride, col_stride, 0, out_lnprior);
+}
+
+VELA_API int vela_b200_prior_transform_batch(VelaHandle h, const double* cube, int64_t B, int64_t n_free, double* out) {
+    return run_prior(h, cube, B, n_free, n_free, 1, 1, out);
 }
 
 // _calc_Sigmainv__and__MT_Ninv_y (gls_likelihood.jl:101-169) for ONE parameter vector:

@@ -49,6 +49,69 @@ __global__ void __launch_bounds__(128) sample_prologue_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------
+// Kp  device-side priors: lnprior (prior.jl:13-19) and prior_transform (prior.jl:31-32)
+// ------------------------------------------------------------------------------------------
+__device__ inline double prior_logpdf(const PriorDev& pr, double x) {
+    const double kLog2Pi = 1.8378770664093453;
+    switch (pr.kind) {
+        case VELA_PRIOR_UNIFORM: return (x >= pr.a && x <= pr.b) ? pr.norm : -CUDART_INF;
+        case VELA_PRIOR_NORMAL: { double z = (x - pr.a) / pr.b; return -(z * z + kLog2Pi) / 2 - pr.norm; }
+        case VELA_PRIOR_LOGNORMAL: {
+            if (!(x > 0)) return -CUDART_INF;
+            double lx = log(x), z = (lx - pr.a) / pr.b;
+            return -(z * z + kLog2Pi) / 2 - pr.norm - lx;
+        }
+        case VELA_PRIOR_LOGUNIFORM: return (x >= pr.a && x <= pr.b) ? -log(x) - pr.norm : -CUDART_INF;
+        case VELA_PRIOR_KIN: return (x >= 0 && x <= CUDART_PI) ? log(sin(x) / 2) : -CUDART_INF;
+        case VELA_PRIOR_SINI: return (x >= 0 && x <= 1) ? log(x / sqrt(1 - x * x)) : -CUDART_INF;
+        case VELA_PRIOR_STIGMA: { double t = 1 + x * x; return (x >= 0 && x <= 1) ? log(4 * x / (t * t)) : -CUDART_INF; }
+        case VELA_PRIOR_SHAPMAX: return (x >= 0) ? log((1 - exp(-x)) / sqrt(2 * exp(x) - 1)) : -CUDART_INF;
+        case VELA_PRIOR_PX: { double x2 = x * x; return (x >= 1 / pr.a) ? log(3 / (pr.a * pr.a * pr.a * x2 * x2)) : -CUDART_INF; }
+        case VELA_PRIOR_LATITUDE: return (x >= -CUDART_PI / 2 && x <= CUDART_PI / 2) ? log(cos(x) / 2) : -CUDART_INF;
+        case VELA_PRIOR_TRUNCATED_NORMAL: {
+            if (!(x >= pr.lo && x <= pr.hi)) return -CUDART_INF;
+            double z = (x - pr.a) / pr.b;
+            return -(z * z + kLog2Pi) / 2 - pr.norm;
+        }
+    }
+    return CUDART_NAN;
+}
+
+__device__ inline double prior_quantile(const PriorDev& pr, double q) {
+    switch (pr.kind) {
+        case VELA_PRIOR_UNIFORM: return pr.a + q * (pr.b - pr.a);
+        case VELA_PRIOR_NORMAL: return pr.a + pr.b * normcdfinv(q);
+        case VELA_PRIOR_LOGNORMAL: return exp(pr.a + pr.b * normcdfinv(q));
+        case VELA_PRIOR_LOGUNIFORM: return exp(log(pr.a) + q * log(pr.b / pr.a));
+        case VELA_PRIOR_KIN: return acos(1 - 2 * q);
+        case VELA_PRIOR_SINI: return sqrt((2 - q) * q);
+        case VELA_PRIOR_STIGMA: return q / (2 - q);                  // as in known_priors.jl:61
+        case VELA_PRIOR_SHAPMAX: return log((sqrt(2 * q - q * q) + 1) / ((q - 1) * (q - 1)));
+        case VELA_PRIOR_PX: return 1 / (pr.a * cbrt(1 - q));
+        case VELA_PRIOR_LATITUDE: return asin(2 * q - 1);
+        case VELA_PRIOR_TRUNCATED_NORMAL: {
+            double c0 = normcdf((pr.lo - pr.a) / pr.b), c1 = normcdf((pr.hi - pr.a) / pr.b);
+            return pr.a + pr.b * normcdfinv(c0 + q * (c1 - c0));
+        }
+    }
+    return CUDART_NAN;
+}
+
+// mode 0: out[b] = sum_k logpdf_k(params[b][k]);  mode 1: out[b][k] = quantile_k(params[b][k])
+__global__ void prior_kernel(const PriorDev* __restrict__ priors, int nd, const double* __restrict__ params, long B,
+                             int mode, double* __restrict__ out) {
+    long b = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (mode == 0) {
+        double lp = 0.0;
+        for (int k = 0; k < nd; ++k) lp += prior_logpdf(priors[k], params[b * nd + k]);
+        out[b] = lp;
+    } else {
+        for (int k = 0; k < nd; ++k) out[b * nd + k] = prior_quantile(priors[k], params[b * nd + k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K1  per-(walker, TOA) chain
 // ------------------------------------------------------------------------------------------
 // _wls_lnlike_term (wls_likelihood.jl:7-14, wideband_wls_likelihood.jl:1-21) and

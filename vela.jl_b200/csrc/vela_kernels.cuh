@@ -12,6 +12,12 @@ constexpr int kSigMaxRank = 1024;
 
 constexpr int kCholThreads = 256;
 
+struct PriorDev {
+    int kind;
+    double a, b, lo, hi;
+    double norm;               // kind-dependent precomputed constant (log normalisation)
+};
+
 struct ChainArgs {
     const double* Pext;        // [B][row]
     const double* tzr_phase;   // [B][2]
@@ -132,6 +138,7 @@ __global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, 
                                        const uint32_t* index_masks, const uint8_t* bit_masks, long n_toas,
                                        double* Pext, double* tzr_phase);
 __global__ void toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a);
+__global__ void prior_kernel(const PriorDev* priors, int nd, const double* params, long B, int mode, double* out);
 __global__ void ecorr_group_kernel(EcorrArgs a);
 template <int NACC>
 __global__ void ecorr_basis_kernel(EcorrBasisArgs a);

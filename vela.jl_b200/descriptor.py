@@ -58,6 +58,49 @@ class VelaModelDesc(C.Structure):
     ]
 
 
+class VelaPriorDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("a", C.c_double), ("b", C.c_double),
+                ("lo", C.c_double), ("hi", C.c_double)]
+
+
+(PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_LOGNORMAL, PRIOR_LOGUNIFORM, PRIOR_KIN, PRIOR_SINI, PRIOR_STIGMA, PRIOR_SHAPMAX,
+ PRIOR_PX, PRIOR_LATITUDE, PRIOR_TRUNCATED_NORMAL) = range(1, 12)
+
+
+def prior_descriptors(priors):
+    """One `VelaPriorDesc` per free parameter from the host-side prior objects, or None if a family has no device twin."""
+    from . import priors as P
+    out = (VelaPriorDesc * max(len(priors), 1))()
+    for k, pr in enumerate(priors):
+        d = pr.distribution
+        e = out[k]
+        if isinstance(d, P.Uniform):
+            e.kind, e.a, e.b = PRIOR_UNIFORM, d.a, d.b
+        elif isinstance(d, P.Normal):
+            e.kind, e.a, e.b = PRIOR_NORMAL, d.mu, d.sigma
+        elif isinstance(d, P.LogNormal):
+            e.kind, e.a, e.b = PRIOR_LOGNORMAL, d.mu, d.sigma
+        elif isinstance(d, P.LogUniform):
+            e.kind, e.a, e.b = PRIOR_LOGUNIFORM, d.a, d.b
+        elif isinstance(d, P.TruncatedNormal):
+            e.kind, e.a, e.b, e.lo, e.hi = PRIOR_TRUNCATED_NORMAL, d.mu, d.sigma, d.lower, d.upper
+        elif isinstance(d, P.PXPriorDistribution):
+            e.kind, e.a = PRIOR_PX, d.Rmax
+        elif isinstance(d, P.KINPriorDistribution):
+            e.kind = PRIOR_KIN
+        elif isinstance(d, P.SINIPriorDistribution):
+            e.kind = PRIOR_SINI
+        elif isinstance(d, P.STIGMAPriorDistribution):
+            e.kind = PRIOR_STIGMA
+        elif isinstance(d, P.SHAPMAXPriorDistribution):
+            e.kind = PRIOR_SHAPMAX
+        elif isinstance(d, P.LatitudePriorDistribution):
+            e.kind = PRIOR_LATITUDE
+        else:
+            return None
+    return out
+
+
 def _dptr(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 

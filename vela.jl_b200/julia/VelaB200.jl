@@ -239,11 +239,35 @@ gp_kind(::PowerlawRedNoiseGP) = (1, :TNREDAMP, :TNREDGAM, :PLREDFREQ)
 gp_kind(::PowerlawDispersionNoiseGP) = (2, :TNDMAMP, :TNDMGAM, :PLDMFREQ)
 gp_kind(::PowerlawChromaticNoiseGP) = (3, :TNCHROMAMP, :TNCHROMGAM, :PLCHROMFREQ)
 
+# ---- device-side priors (include/vela_b200.h: VelaPriorDesc); families of pyvela/pyvela/priors.py:30-76 -----------
+struct VelaPriorDesc
+    kind::Int32
+    _pad::Int32
+    a::Float64
+    b::Float64
+    lo::Float64
+    hi::Float64
+end
+using Distributions: Uniform, Normal, LogNormal, LogUniform, Truncated
+prior_desc(d::Uniform) = VelaPriorDesc(1, 0, d.a, d.b, 0.0, 0.0)
+prior_desc(d::Normal) = VelaPriorDesc(2, 0, d.μ, d.σ, 0.0, 0.0)
+prior_desc(d::LogNormal) = VelaPriorDesc(3, 0, d.μ, d.σ, 0.0, 0.0)
+prior_desc(d::LogUniform) = VelaPriorDesc(4, 0, d.a, d.b, 0.0, 0.0)
+prior_desc(::Vela.KINPriorDistribution) = VelaPriorDesc(5, 0, 0.0, 0.0, 0.0, 0.0)
+prior_desc(::Vela.SINIPriorDistribution) = VelaPriorDesc(6, 0, 0.0, 0.0, 0.0, 0.0)
+prior_desc(::Vela.STIGMAPriorDistribution) = VelaPriorDesc(7, 0, 0.0, 0.0, 0.0, 0.0)
+prior_desc(::Vela.SHAPMAXPriorDistribution) = VelaPriorDesc(8, 0, 0.0, 0.0, 0.0, 0.0)
+prior_desc(d::Vela.PXPriorDistribution) = VelaPriorDesc(9, 0, d.Rmax, 0.0, 0.0, 0.0)
+prior_desc(::Vela.LatitudePriorDistribution) = VelaPriorDesc(10, 0, 0.0, 0.0, 0.0, 0.0)
+prior_desc(d::Truncated{<:Normal}) = VelaPriorDesc(11, 0, d.untruncated.μ, d.untruncated.σ, d.lower, d.upper)
+prior_desc(::Any) = nothing     # no device twin: lnprior stays on the host for this model
+
 # ---- the wrapped pulsar --------------------------------------------------------------------------------
 mutable struct B200Pulsar{M<:TimingModel,T<:TOABase}
     model::M
     toas::Vector{T}
     handle::Ptr{Cvoid}
+    device_priors::Bool
 end
 
 last_error() = unsafe_string(ccall((:vela_b200_last_error, LIB), Cstring, ()))
@@ -302,8 +326,15 @@ function B200Pulsar(model::TimingModel, toas::Vector{T}; devices::Vector{Int32} 
             length(egroups), par_ecorr, Ptr{UInt64}(pointer(egroups)), length(devices), 0, pointer(devices))
         check(ccall((:vela_b200_create, LIB), Cint, (Ref{VelaModelDesc}, Ref{Ptr{Cvoid}}), desc, handle), "vela_b200_create")
     end
-    psr = B200Pulsar{typeof(model),T}(model, toas, handle[])
+    psr = B200Pulsar{typeof(model),T}(model, toas, handle[], false)
     finalizer(p -> ccall((:vela_b200_destroy, LIB), Cint, (Ptr{Cvoid},), p.handle), psr)
+    descs = [prior_desc(p.distribution) for p in model.priors]
+    if !isempty(descs) && all(!isnothing, descs)
+        pd = VelaPriorDesc[descs...]
+        check(ccall((:vela_b200_set_priors, LIB), Cint, (Ptr{Cvoid}, Ptr{VelaPriorDesc}, Int32), psr.handle, pd, length(pd)),
+            "vela_b200_set_priors")
+        psr.device_priors = true
+    end
     return psr
 end
 
@@ -322,7 +353,7 @@ function batch(sym::Symbol, psr::B200Pulsar, paramss::AbstractMatrix, extra...)
         rc = if sym === :lnpost
             ccall((:vela_b200_lnpost_batch, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
-                psr.handle, pointer(A), B, nd, rs, cs, pointer(extra[1]), pointer(out))
+                psr.handle, pointer(A), B, nd, rs, cs, extra[1] isa Ptr ? extra[1] : pointer(extra[1]), pointer(out))
         else
             ccall((:vela_b200_lnlike_batch, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}),
@@ -341,7 +372,9 @@ Vela.calc_lnprior(psr::B200Pulsar, params) = calc_lnprior(psr.model, params)
 Vela.prior_transform(psr::B200Pulsar, cube) = Vela.prior_transform(psr.model, cube)
 
 function Vela.calc_lnpost_vectorized(psr::B200Pulsar, paramss)
-    # priors stay on the host, exactly as in posterior.jl:9-12; the library applies the -Inf short-circuit
+    # device-side priors when every family has a device twin (lnprior == C_NULL); otherwise priors stay on the
+    # host exactly as in posterior.jl:9-12.  Either way the library applies the -Inf short-circuit.
+    psr.device_priors && return batch(:lnpost, psr, paramss, Ptr{Float64}(C_NULL))
     lnpr = Float64[calc_lnprior(psr.model, view(paramss, ii, :)) for ii = 1:size(paramss, 1)]
     return batch(:lnpost, psr, paramss, lnpr)
 end

@@ -85,6 +85,29 @@ class LogUniform(Distribution):
         return np.exp(math.log(self.a) + np.asarray(q) * math.log(self.b / self.a))
 
 
+@dataclass
+class TruncatedNormal(Distribution):
+    """Distributions.truncated(Normal(mu, sigma), lower, upper) — what pyvela builds for bounded custom priors
+    (pyvela/pyvela/priors.py:245-256)."""
+    mu: float
+    sigma: float
+    lower: float
+    upper: float
+
+    def _mass(self):
+        return special.ndtr((self.upper - self.mu) / self.sigma) - special.ndtr((self.lower - self.mu) / self.sigma)
+
+    def logpdf(self, x):
+        x = np.asarray(x, dtype=float)
+        z = (x - self.mu) / self.sigma
+        out = -0.5 * z * z - math.log(self.sigma) - 0.5 * math.log(2 * math.pi) - math.log(self._mass())
+        return np.where((x >= self.lower) & (x <= self.upper), out, -np.inf)
+
+    def quantile(self, q):
+        c0 = special.ndtr((self.lower - self.mu) / self.sigma)
+        return self.mu + self.sigma * special.ndtri(c0 + np.asarray(q) * self._mass())
+
+
 class _Custom(Distribution):
     lb, ub = 0.0, 1.0
 
