@@ -50,7 +50,7 @@ extern "C" {
 #define VELA_API
 #endif
 
-#define VELA_B200_ABI_VERSION 2
+#define VELA_B200_ABI_VERSION 3
 #define VELA_MAX_PAR 24
 
 typedef enum VelaStatus {
@@ -95,9 +95,14 @@ typedef enum VelaComponentKind {
     VELA_COMP_CM_WAVEX = 28,           /* src/model/wavex.jl:97-106 */
     VELA_COMP_SOLAR_WIND_PIECEWISE = 29, /* SolarWindDispersionPiecewise (SWX), src/model/solarwind.jl:64-91 */
     VELA_COMP_DM_OFFSET_EXCLUSIVE = 30,  /* ExclusiveDispersionOffset (FDJUMPDM), src/model/fdjumpdm.jl:44-66 */
-    VELA_COMP_DM_OFFSET = 31           /* DispersionOffset (FDJUMPDM, BitMatrix), src/model/fdjumpdm.jl:14-37 */
+    VELA_COMP_DM_OFFSET = 31,          /* DispersionOffset (FDJUMPDM, BitMatrix), src/model/fdjumpdm.jl:14-37 */
+    /* Power-law Fourier GPs with FREE (un-marginalised) amplitudes, used as ordinary delay components when
+     * pyvela is run with marginalize_gp_noise=False (pyvela/pyvela/model.py:693-700): */
+    VELA_COMP_POWERLAW_RED_GP = 32,    /* PowerlawRedNoiseGP delay, src/model/gp_noise.jl:110-130 */
+    VELA_COMP_POWERLAW_DM_GP = 33,     /* PowerlawDispersionNoiseGP dispersion_slope, src/model/gp_noise.jl:155-183 */
+    VELA_COMP_POWERLAW_CHROM_GP = 34   /* PowerlawChromaticNoiseGP chromatic_slope, src/model/gp_noise.jl:207-235 */
 } VelaComponentKind;
-#define VELA_COMP_KIND_MAX 31
+#define VELA_COMP_KIND_MAX 34
 
 /* VelaComponentDesc.flags */
 #define VELA_FLAG_ECLIPTIC        1   /* SolarSystem.ecliptic_coordinates */
@@ -152,6 +157,14 @@ typedef enum VelaComponentKind {
  *                                                       dval: 0 conjunction_geometry 1 opposition_geometry
  *  DM_OFFSET_EXCLUSIVE par: 0 FDJUMPDM[0]               len: 0 #FDJUMPDM mask: 0 index mask
  *  DM_OFFSET      par: 0 FDJUMPDM[0]                    len: 0 #FDJUMPDM mask: 0 first bit-mask row
+ *  POWERLAW_RED_GP   par: 0 TNREDAMP 1 TNREDGAM 2 PLREDSIN_[0] 3 PLREDCOS_[0] 4 PLREDFREQ 5 PLREDEPOCH
+ *  POWERLAW_DM_GP    par: 0 TNDMAMP 1 TNDMGAM 2 PLDMSIN_[0] 3 PLDMCOS_[0] 4 PLDMFREQ 5 PLDMEPOCH
+ *  POWERLAW_CHROM_GP par: 0 TNCHROMAMP 1 TNCHROMGAM 2 PLCHROMSIN_[0] 3 PLCHROMCOS_[0] 4 PLCHROMFREQ 5 PLCHROMEPOCH
+ *                         6 TNCHROMIDX
+ *                    all three: len: 0 #harmonics N, 1 number of leading log-spaced harmonics
+ *                    (findfirst(iszero, ln_js) - 1, gp_noise.jl:37), 2 offset into VelaModelDesc.aux_values of
+ *                    2N doubles: ln_js[0..N) (the struct field, widened from its storage type) followed by
+ *                    js[0..N) = exp(ln_js[i]) evaluated IN THE STORAGE TYPE (Float32 for the red-noise GP).
  */
 typedef struct VelaComponentDesc {
     int32_t kind;
@@ -244,6 +257,11 @@ typedef struct VelaModelDesc {
     int32_t n_devices;            /* 0: use the current CUDA device */
     int32_t _pad;
     const int32_t* devices;       /* CUDA device ordinals; walkers are split evenly across them */
+
+    /* Per-component constant tables that are struct fields in the reference (ln_js of the un-marginalised
+     * power-law GPs); components index into it through len[2].  May be NULL when n_aux == 0. */
+    int64_t n_aux;
+    const double* aux_values;
 } VelaModelDesc;
 
 typedef struct VelaPulsar* VelaHandle;
@@ -348,6 +366,22 @@ VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int
  * (pyvela reads the same quantities in spnta.py:376-394).  Woodbury kernels only.
  */
 VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n_free, double* Sigma, double* u);
+
+/*
+ * Conditional Gaussian of the analytically marginalised amplitudes for a batch of samples, computed from
+ * the same Sigma^-1 / u / Cholesky factor as ln L (no second factorisation):
+ *   ahat[b, :]   = Sigma u                        (B x p, row-major)   conditional mean offsets
+ *   cf[b, :, :]  = upper factor R, Sigma^-1 = R^T R (B x p x p, row-major; NULL to skip)
+ *   lnlike[b]    = ln L of the same sample          (NULL to skip)
+ * Replaces SPNTA.get_marginalized_param_offset_mean_and_covinvcf, pyvela/pyvela/spnta.py:376-394
+ * (scipy cholesky(lower=False) + cho_solve on the host); the draws in spnta.py:419-437 need only
+ * R and ahat.  Rows whose Sigma^-1 is not positive definite are NaN.  With an ECORR inner kernel
+ * Sigma^-1 carries the exact N^-1 (the reference helper keeps only its diagonal there).
+ * Woodbury kernels only; runs on devices[0].
+ */
+VELA_API int vela_b200_marginalized_mean_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
+                                               int64_t row_stride, int64_t col_stride, double* ahat, double* cf,
+                                               double* lnlike);
 
 /*
  * Device-resident variant used by benchmarks and by callers that already hold

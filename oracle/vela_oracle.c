@@ -531,6 +531,37 @@ static double xwavex(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa,
     return sum;
 }
 
+static double powerlaw(double A, double gamma, double f, double f1);
+
+/* evaluate_powerlaw_red_noise_gp gp_noise.jl:23-58 with the free (un-marginalised) amplitudes.
+ * aux holds ln_js[0..N) then js[0..N) = exp(ln_j) evaluated in the field's storage type (include/vela_b200.h). */
+static double powerlaw_gp(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, const Corr* k) {
+    const int N = c->len[0], nlog = c->len[1];
+    const double* ln_js = ctx->d->aux_values + c->len[2];
+    const double* js = ln_js + N;
+    const double* alpha = ctx->P + c->par[2];
+    const double* beta = ctx->P + c->par[3];
+    double A = pow(10.0, PAR(c, 0)), gamma = PAR(c, 1), f1 = PAR(c, 4);
+    double dt = t64(toa, k) - PAR(c, 5);
+    double phi1 = 2 * M_PI * f1 * dt;
+    double e_re = cos(phi1), e_im = sin(phi1);      /* exp(im * phi1) */
+    double sigma1 = sqrt(powerlaw(A, gamma, f1, f1));
+    double result = 0.0;
+    for (int i = 0; i < nlog; ++i) {
+        double jfac = exp(-(gamma / 2) * ln_js[i]);
+        double ph = js[i] * phi1;
+        result += jfac * (alpha[i] * sin(ph) + beta[i] * cos(ph));
+    }
+    double re = e_re, im = e_im;
+    for (int i = nlog; i < N; ++i) {
+        double jfac = exp(-(gamma / 2) * ln_js[i]);
+        result += jfac * (alpha[i] * im + beta[i] * re);
+        double nre = re * e_re - im * e_im, nim = re * e_im + im * e_re;   /* Complex * Complex */
+        re = nre; im = nim;
+    }
+    return sigma1 * result;
+}
+
 /* SolarWindDispersionPiecewise solarwind.jl:72-91 */
 static void comp_swx(const Ctx* ctx, const VelaComponentDesc* c, const Toa* toa, Corr* k) {
     double dm = 0.0;
@@ -693,6 +724,11 @@ static Corr correct_toa(const Ctx* ctx, const Toa* toa) {
             case VELA_COMP_WAVEX: k.delay += xwavex(ctx, c, toa, &k); break;
             case VELA_COMP_DM_WAVEX: apply_dispersion(toa, &k, xwavex(ctx, c, toa, &k)); break;
             case VELA_COMP_CM_WAVEX: apply_chromatic(toa, &k, xwavex(ctx, c, toa, &k), PAR(c, 4)); break;
+            case VELA_COMP_POWERLAW_RED_GP: k.delay += powerlaw_gp(ctx, c, toa, &k); break;               /* gp_noise.jl:120-130 */
+            case VELA_COMP_POWERLAW_DM_GP:                                                                /* gp_noise.jl:165-183 */
+                apply_dispersion(toa, &k, (1.4e9 * 1.4e9) * powerlaw_gp(ctx, c, toa, &k)); break;
+            case VELA_COMP_POWERLAW_CHROM_GP:                                                             /* gp_noise.jl:219-235 */
+                apply_chromatic(toa, &k, pow(1400.0, PAR(c, 6)) * powerlaw_gp(ctx, c, toa, &k), PAR(c, 6)); break;
             case VELA_COMP_SOLAR_WIND_PIECEWISE: comp_swx(ctx, c, toa, &k); break;
             case VELA_COMP_DM_OFFSET_EXCLUSIVE: case VELA_COMP_DM_OFFSET: comp_dmoffset(ctx, c, toa, &k); break;
             case VELA_COMP_GLITCH: comp_glitch(ctx, c, toa, &k); break;

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 CASES = [("config2_ell1", 1500, 96), ("config3_gp", 1200, 96), ("config4_dd_wb", 700, 64), ("config5_array", 900, 40),
          ("extra_ell1_fbx", None, 64), ("extra_dd_fbx_wb", None, 64), ("extra_dmjump_bits_wb", None, 64),
          ("extra_ell1h_fd_wavex", None, 48), ("extra_ell1k_swx", None, 48), ("extra_ddk_wb", None, 48),
-         ("extra_ddh", None, 48), ("extra_dds", None, 48), ("extra_ecorr", None, 64), ("extra_ecorr_gp", None, 64)]
+         ("extra_ddh", None, 48), ("extra_dds", None, 48), ("extra_ecorr", None, 64), ("extra_ecorr_gp", None, 64),
+         ("extra_free_gp", None, 48), ("extra_free_gp_wb", None, 48)]
 
 
 @pytest.fixture(scope="module")
@@ -65,3 +66,41 @@ def test_phases_api_matches_oracle(datasets, oracle):
     ho, lo_o, fo, _, _ = oracle.phases(md, ds.truth)
     assert np.max(np.abs((hi - ho) + (lo - lo_o))) < 1e-9            # cycles
     np.testing.assert_allclose(f, fo, rtol=1e-14)
+
+
+@pytest.mark.parametrize("name,ntoa", [("config3_gp", 1200), ("config4_dd_wb", 700), ("extra_ecorr_gp", None)])
+def test_marginalized_mean_and_factor(name, ntoa, datasets, oracle):
+    """ahat = Sigma u and the upper factor of Sigma^-1 (pyvela spnta.py:376-394) against scipy on the oracle's
+    Sigma^-1, u; compared in the Sigma^-1 energy norm because Sigma^-1 is ill-conditioned by construction."""
+    from scipy.linalg import cho_factor, cho_solve
+    ds, psr, md = datasets(name, ntoa)
+    W = ds.walkers(5, seed=3)
+    ahat, cf, lnl = psr.marginalized_offset_mean_vectorized(W, with_cf=True, with_lnlike=True)
+    np.testing.assert_array_equal(lnl, psr.lnlike_vectorized(W))
+    for b in range(len(W)):
+        So, uo = oracle.sigma(md, W[b])
+        scale = np.sqrt(np.outer(np.diag(So), np.diag(So)))
+        R = cf[b]
+        assert np.all(np.tril(R, -1) == 0) and np.all(np.diag(R) > 0)
+        assert np.max(np.abs(R.T @ R - So) / scale) < 1e-12
+        want = cho_solve(cho_factor(So), uo)
+        d = ahat[b] - want
+        assert d @ So @ d < 1e-16 * (want @ So @ want)
+    # single-sample mirrors of the SPNTA helpers
+    a1, R1 = psr.get_marginalized_param_offset_mean_and_covinvcf(W[0])
+    np.testing.assert_array_equal(a1, ahat[0])
+    std = psr.get_marginalized_param_std(W[0])
+    So, _ = oracle.sigma(md, W[0])
+    np.testing.assert_allclose(std, np.sqrt(np.diag(np.linalg.inv(So))), rtol=1e-6)
+    a, lnp = psr.get_marginalized_param_offset_sample(W[0], np.random.default_rng(0))
+    z = R1 @ (a - a1)
+    assert abs(lnp - (-0.5 * z @ z + np.log(np.diag(R1)).sum() - 0.5 * len(a) * np.log(2 * np.pi))) < 1e-8 * abs(lnp)
+    assert psr.get_marginalized_gp_noise_realization(W[0], np.random.default_rng(0)).shape == (psr.n_rows,)
+
+
+def test_marginalized_mean_refused_for_white_kernels(vb, datasets):
+    ds, psr, md = datasets("config2_ell1", 1500)
+    assert not psr.has_marginalized_gp_noise
+    with pytest.raises(vb.VelaB200Error):
+        psr.marginalized_offset_mean_vectorized(ds.walkers(2, seed=1))
+    assert psr.get_marginalized_param_offset_mean(ds.truth).size == 0

@@ -123,3 +123,43 @@ def test_component_identities(vb, oracle):
           ("GLF0D_", [0.0]), ("GLTD_", [0.0]), ("F", [0.0, 0.0])]
     e = _single_toa_model(vb, [M.Spindown(), M.Glitch()], [("F_", 100.0)], gl)
     assert oracle.phases(e, np.zeros(0))[0][0] == pytest.approx(pa[0][0] + 0.0, abs=1e-3)
+
+
+def test_free_amplitude_powerlaw_gp_delay(vb, oracle):
+    """Un-marginalised power-law GPs as delay components with the parameters of test/test_gp_noise.jl:5-12,41-48,
+    75-83 (the reference asserts only `isfinite(delay)`); here the delay is checked against a direct mpmath
+    evaluation of gp_noise.jl:23-58 with exact trigonometry instead of the complex recurrence."""
+    import mpmath
+    mpmath.mp.prec = 120
+    M = vb.model
+    amp, gam, f1, epoch, t = -13.5, 3.5, 1e-8, -1.2e8, 3.3e7
+    sins = {"PLRED": (1.3, 2.0, 1.1, 0.12, -0.23), "PLDM": (3.0, 2.0, 1.1, 0.12, -0.23), "PLCHROM": (1.3, 2.0, 1.1, 0.12, -0.23)}
+    coss = {"PLRED": (-1.6, 2.3, 1.5, -1.11, -0.8), "PLDM": (3.0, 2.0, 1.5, -1.11, -0.8), "PLCHROM": (1.3, -2.0, 1.5, -1.11, -0.8)}
+    nu = 2.5e9
+    for cls, tn, pre in ((M.PowerlawRedNoiseGP, "TNRED", "PLRED"), (M.PowerlawDispersionNoiseGP, "TNDM", "PLDM"),
+                         (M.PowerlawChromaticNoiseGP, "TNCHROM", "PLCHROM")):
+        gp = cls(3, 2, 2.0)
+        single = [(tn + "AMP", amp), (tn + "GAM", gam), (pre + "FREQ", f1), (pre + "EPOCH", epoch), ("F_", 100.0)]
+        if pre == "PLCHROM":
+            single.append(("TNCHROMIDX", 4.0))
+        md = _single_toa_model(vb, [gp, M.Spindown()], single,
+                               [(pre + "SIN_", sins[pre]), (pre + "COS_", coss[pre]), ("F", [0.0, 0.0])], toa_value=t, freq=nu)
+        assert md.desc.components[0].len[1] == 2          # two log-spaced harmonics precede ln(1) == 0
+        delay = oracle.phases(md, np.zeros(0))[3][0]
+        fyr = mpmath.mpf(1) / 3600 / 24 / mpmath.mpf("365.25")
+        P1 = mpmath.mpf(10) ** (2 * amp) / (12 * mpmath.pi**2 * fyr**3) * (fyr / f1) ** gam * f1
+        phi1 = 2 * mpmath.pi * f1 * (mpmath.mpf(t) - epoch)
+        tot = mpmath.mpf(0)
+        for i, (lnj, j) in enumerate(zip(gp.ln_js, gp.js())):
+            jj = mpmath.mpf(float(j)) if i < 2 else mpmath.mpf(i - 1)
+            tot += mpmath.exp(-mpmath.mpf(gam) / 2 * float(lnj)) * (sins[pre][i] * mpmath.sin(jj * phi1) + coss[pre][i] * mpmath.cos(jj * phi1))
+        want = mpmath.sqrt(P1) * tot
+        if pre == "PLDM":
+            want = want * mpmath.mpf(1.4e9) ** 2 / mpmath.mpf(nu) ** 2
+        elif pre == "PLCHROM":
+            want = want * mpmath.mpf(1400.0) ** 4 * (mpmath.mpf(1e6) / nu) ** 4
+        assert np.isfinite(delay) and delay == pytest.approx(float(want), rel=1e-12)
+    # the free-amplitude variance matches the marginalised prior weight: (sigma1 jfac)^2 == 1 / weights_inv
+    red = M.PowerlawRedNoiseGP(3, 2, 2.0)
+    P1 = oracle.powerlaw(10.0**amp, gam, f1, f1)
+    np.testing.assert_allclose(P1 * np.exp(-(gam / 2) * red.ln_js) ** 2, P1 * np.exp(-gam * red.ln_js), rtol=1e-14)

@@ -51,6 +51,7 @@ class Pulsar:
         self._h = h
         self._finalizer = weakref.finalize(self, self._lib.vela_b200_destroy, h)
         self.ndim = model.param_handler._nfree
+        self.n_rows = int(self._lib.vela_b200_n_rows(h))
         self.device_priors = False
         self.set_priors(model.priors)
 
@@ -165,6 +166,64 @@ class Pulsar:
         u = np.empty(n)
         _lib.check(self._lib.vela_b200_sigma_and_u(self._h, _dp(p), len(p), _dp(S), _dp(u)), "vela_b200_sigma_and_u")
         return S, u
+
+    # -- conditional distribution of the marginalised amplitudes (pyvela/pyvela/spnta.py:376-465)
+    def marginalized_offset_mean_vectorized(self, paramss, with_cf: bool = False, with_lnlike: bool = False):
+        """ahat (B, p) [, upper factor R of Sigma^-1 (B, p, p)] [, ln L (B,)] for a batch, from the same
+        device factorisation the likelihood uses."""
+        a = np.ascontiguousarray(paramss, dtype=np.float64)
+        if a.ndim != 2:
+            raise ValueError("paramss must be (nwalkers, ndim)")
+        B, nd = a.shape
+        p = int(self._lib.vela_b200_n_basis(self._h))
+        ahat = np.empty((B, p))
+        cf = np.empty((B, p, p)) if with_cf else None
+        lnl = np.empty(B) if with_lnlike else None
+        _lib.check(self._lib.vela_b200_marginalized_mean_batch(
+            self._h, _dp(a), B, nd, nd, 1, _dp(ahat), _dp(cf) if with_cf else None,
+            _dp(lnl) if with_lnlike else None), "vela_b200_marginalized_mean_batch")
+        out = (ahat,) + ((cf,) if with_cf else ()) + ((lnl,) if with_lnlike else ())
+        return out[0] if len(out) == 1 else out
+
+    @property
+    def has_marginalized_gp_noise(self) -> bool:
+        return int(self._lib.vela_b200_n_basis(self._h)) > 0
+
+    def get_marginalized_param_offset_mean_and_covinvcf(self, params):
+        """spnta.py:376-394 — (ahat, Sigmainv_cf) for one sample; empty arrays without marginalised GPs."""
+        if not self.has_marginalized_gp_noise:
+            return np.array([]), np.array([[]])
+        ahat, cf = self.marginalized_offset_mean_vectorized(self._free(params)[None, :], with_cf=True)
+        return ahat[0], cf[0]
+
+    def get_marginalized_param_offset_mean(self, params):
+        return self.get_marginalized_param_offset_mean_and_covinvcf(params)[0]
+
+    def get_marginalized_param_std(self, params):
+        """spnta.py:407-417 — sqrt(diag(Sigma)) from the triangular inverse of the factor."""
+        if not self.has_marginalized_gp_noise:
+            return np.array([])
+        from scipy.linalg import solve_triangular
+        cf = self.get_marginalized_param_offset_mean_and_covinvcf(params)[1]
+        inv = solve_triangular(cf, np.eye(cf.shape[0]), lower=False)
+        return np.sqrt(np.sum(inv * inv, axis=1))
+
+    def get_marginalized_param_offset_sample(self, params, rng=None):
+        """spnta.py:419-437 — one draw a ~ N(ahat, Sigma) and its log density."""
+        if not self.has_marginalized_gp_noise:
+            return np.array([]), 0.0
+        from scipy.linalg import solve_triangular
+        ahat, cf = self.get_marginalized_param_offset_mean_and_covinvcf(params)
+        z = (rng if rng is not None else np.random.default_rng()).standard_normal(len(ahat))
+        a = ahat + solve_triangular(cf, z, lower=False)
+        lnp = -0.5 * (z @ z) + np.sum(np.log(np.diag(cf))) - 0.5 * len(ahat) * np.log(2 * np.pi)
+        return a, float(lnp)
+
+    def get_marginalized_gp_noise_realization(self, params, rng=None):
+        """spnta.py:456-465 — M a for one draw of the marginalised amplitudes (zeros without GPs)."""
+        if not self.has_marginalized_gp_noise:
+            return np.zeros(len(self.toas))
+        return np.asarray(self.model.kernel.noise_basis) @ self.get_marginalized_param_offset_sample(params, rng)[0]
 
     # -- benchmarking hooks
     def lnlike_device(self, d_params_ptr: int, B: int, d_out_ptr: int, stream: int = 0):

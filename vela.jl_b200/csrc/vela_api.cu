@@ -251,7 +251,8 @@ int set_smem_attrs(int dev) {
 // Enqueue the whole pipeline for B walkers whose parameters already sit in d_params (row-major B x n_free).
 // mode: 0 ln L, 1 chi^2 (white kernels only).  with_prior: combine with d_lnprior (may be null = 0).
 int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B, int mode, int with_prior,
-                  const double* d_lnprior, double* d_out, cudaStream_t st) {
+                  const double* d_lnprior, double* d_out, cudaStream_t st, double* d_ahat = nullptr,
+                  double* d_cf = nullptr) {
     const ProgramDev& pg = h->prog;
     Buffers& b = d.buf;
     const bool timing = h->stage_timing && (&d == &h->devs[0]);
@@ -296,6 +297,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         ch.gp = d.gp; ch.gp_data = d.gp_data; ch.partial = b.partial; ch.n_tiles = n_rows_partial; ch.B = B;
         ch.lnprior = d_lnprior; ch.with_prior = with_prior; ch.out = d_out; ch.use_smem = h->chol_smem ? 1 : 0;
         ch.ksplit = ksplit; ch.split_stride_sig = sa.split_stride_sig; ch.split_stride_u = sa.split_stride_u;
+        ch.ahat = d_ahat; ch.cf = d_cf;
         chol_finish_kernel<<<(unsigned)B, kCholThreads, h->chol_smem_bytes, st>>>(ch);
         if (timing) cudaEventRecord(d.ev[4], st);
         h->launches += 2;
@@ -316,7 +318,11 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
     if (upload(&d.tzr_block, tzr_block.data(), tzr_block.size())) return VELA_ERR_CUDA;
     if (upload(&d.index_masks, desc->index_masks, (size_t)desc->n_index_masks * desc->n_toas)) return VELA_ERR_CUDA;
     if (upload(&d.bit_masks, desc->bit_masks, (size_t)desc->n_bit_mask_rows * desc->n_toas)) return VELA_ERR_CUDA;
-    if (upload(&d.defaults, desc->default_values, (size_t)desc->n_params)) return VELA_ERR_CUDA;
+    {   // default values followed by the aux table (read by the prologue only)
+        std::vector<double> dv(desc->default_values, desc->default_values + desc->n_params);
+        if (desc->n_aux > 0) dv.insert(dv.end(), desc->aux_values, desc->aux_values + desc->n_aux);
+        if (upload(&d.defaults, dv.data(), dv.size())) return VELA_ERR_CUDA;
+    }
     if (upload(&d.free_idx, desc->free_indices, (size_t)desc->n_free)) return VELA_ERR_CUDA;
     if (!egroups.empty()) {
         if (upload(&d.ecorr_groups, egroups.data(), egroups.size())) return VELA_ERR_CUDA;
@@ -387,6 +393,13 @@ int validate(const VelaModelDesc* d) {
         if (c.kind < VELA_COMP_SOLAR_SYSTEM || c.kind > VELA_COMP_KIND_MAX) return fail(VELA_ERR_UNSUPPORTED, "component kind %d is outside the implemented hot path", c.kind);
         for (int k = 0; k < VELA_MAX_PAR; ++k)
             if (c.par[k] >= d->n_params) return fail(VELA_ERR_INVALID_ARG, "component %d: parameter offset %d out of range", ic, c.par[k]);
+        if (c.kind >= VELA_COMP_POWERLAW_RED_GP && c.kind <= VELA_COMP_POWERLAW_CHROM_GP) {
+            if (c.len[0] <= 0 || c.len[1] < 0 || c.len[1] > c.len[0] || c.len[2] < 0 || !d->aux_values ||
+                (int64_t)c.len[2] + 2 * (int64_t)c.len[0] > d->n_aux)
+                return fail(VELA_ERR_INVALID_ARG, "component %d: power-law GP needs 2N aux values (ln_js, js)", ic);
+            for (int k = 0; k < (c.kind == VELA_COMP_POWERLAW_CHROM_GP ? 7 : 6); ++k)
+                if (c.par[k] < 0) return fail(VELA_ERR_INVALID_ARG, "component %d: power-law GP parameter slot %d unset", ic, k);
+        }
         const bool bits = c.kind == VELA_COMP_PHASE_JUMP || c.kind == VELA_COMP_DM_JUMP || c.kind == VELA_COMP_DM_OFFSET || c.kind == VELA_COMP_FD_JUMP;
         for (int m = 0; m < 2; ++m) {
             if (c.mask[m] < 0) continue;
@@ -933,6 +946,49 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
         }
     if (u) memcpy(u, U.data(), sizeof(double) * p);
     return VELA_OK;
+}
+
+// Conditional Gaussian of the analytically marginalised amplitudes for a batch (device 0):
+// ahat = Sigma u and the upper Cholesky factor of Sigma^-1, from the same K3/K4 results as ln L
+// (pyvela/pyvela/spnta.py:376-394).
+VELA_API int vela_b200_marginalized_mean_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
+                                               int64_t rs, int64_t cs, double* ahat, double* cf, double* lnlike) {
+    if (!h) return fail(VELA_ERR_INVALID_ARG, "null handle");
+    if (h->p == 0) return fail(VELA_ERR_UNSUPPORTED, "this kernel has no marginalised amplitudes");
+    if (n_free != h->prog.n_free) return fail(VELA_ERR_INVALID_ARG, "expected %d free parameters, got %ld (parameter.jl:162)", h->prog.n_free, (long)n_free);
+    if (B < 0 || (B > 0 && (!params || !ahat))) return fail(VELA_ERR_INVALID_ARG, "null params/ahat");
+    if (B == 0) return VELA_OK;
+    std::lock_guard<std::mutex> lock(h->mtx);
+    DeviceModel& d = h->devs[0];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d.dev);
+    const long p = h->p, nf = h->prog.n_free;
+    const long chunk = std::min<long>(h->max_chunk, 1024);
+    double *d_ahat = nullptr, *d_cf = nullptr;
+    int rc = 0;
+    cudaError_t e = cudaMalloc((void**)&d_ahat, sizeof(double) * chunk * p);
+    if (e == cudaSuccess && cf) e = cudaMalloc((void**)&d_cf, sizeof(double) * chunk * p * p);
+    if (e != cudaSuccess) rc = fail(VELA_ERR_CUDA, "marginalized_mean: %s", cudaGetErrorString(e));
+    std::vector<double> stage;
+    for (long done = 0; done < B && !rc; done += chunk) {
+        const long n = std::min<long>(chunk, B - done);
+        if ((rc = ensure_host_buffers(h, d, n))) break;
+        if ((rc = ensure_device_buffers(h, d, n))) break;
+        Buffers& b = d.buf;
+        for (long r = 0; r < n; ++r)
+            for (long k = 0; k < nf; ++k) b.h_params[r * nf + k] = params[(done + r) * rs + k * cs];
+        cudaMemcpyAsync(b.params, b.h_params, sizeof(double) * n * std::max<long>(nf, 1), cudaMemcpyHostToDevice, d.stream);
+        rc = enqueue_batch(h, d, b.params, n, 0, 0, nullptr, b.out, d.stream, d_ahat, d_cf);
+        cudaMemcpyAsync(ahat + done * p, d_ahat, sizeof(double) * n * p, cudaMemcpyDeviceToHost, d.stream);
+        if (cf) cudaMemcpyAsync(cf + done * p * p, d_cf, sizeof(double) * n * p * p, cudaMemcpyDeviceToHost, d.stream);
+        if (lnlike) cudaMemcpyAsync(lnlike + done, b.out, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
+        e = cudaStreamSynchronize(d.stream);
+        if (e != cudaSuccess && !rc) rc = fail(VELA_ERR_CUDA, "marginalized_mean: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_ahat); cudaFree(d_cf);
+    cudaSetDevice(prev);
+    return rc;
 }
 
 VELA_API int vela_b200_set_stage_timing(VelaHandle h, int enabled) {

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(128) sample_prologue_kernel(const __grid_const
     for (int i = 0; i < prog.n_params; ++i) P[i] = defaults[i];
     for (int i = 0; i < prog.n_free; ++i) P[free_idx[i]] = params[b * prog.n_free + i];
     double* D = P + prog.n_params;
-    for (int ic = 0; ic < prog.n_comp; ++ic) fill_derived(prog.comp[ic], P, D + prog.comp[ic].der);
+    for (int ic = 0; ic < prog.n_comp; ++ic) fill_derived(prog.comp[ic], P, D + prog.comp[ic].der, defaults + prog.n_params);
 
     ChainEnv e;
     e.toa_base = tzr_block; e.stride = 1; e.j = 0;
@@ -733,6 +733,26 @@ __global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
         double lnl = -0.5 * (yNy - zz + logdetN + logdetPhi + logdetSig);
         if (sFail) lnl = -CUDART_INF;
         a.out[b] = combine_prior(lnl, a.lnprior, b, a.with_prior);
+    }
+    if (!a.ahat) return;
+    // ---- conditional mean of the marginalised amplitudes: L^T ahat = z, i.e. ahat = Sigma u
+    // (pyvela/pyvela/spnta.py:376-394: cho_solve((Sigmainv_cf, False), MT_Ninv_y)) and the upper factor L^T
+    for (int k = p - 1; k >= 0; --k) {
+        __syncthreads();
+        if (tid == 0) z[k] /= A[k * lda + k];
+        __syncthreads();
+        const double zk = z[k];
+        for (int i = tid; i < k; i += nt) z[i] -= A[k * lda + i] * zk;
+    }
+    __syncthreads();
+    const double bad = sFail ? CUDART_NAN : 0.0;
+    for (int i = tid; i < p; i += nt) a.ahat[(size_t)b * p + i] = z[i] + bad;
+    if (a.cf) {
+        double* dst = a.cf + (size_t)b * p * p;
+        for (int idx = tid; idx < p * p; idx += nt) {
+            const int i = idx / p, j = idx - i * p;
+            dst[idx] = j >= i ? A[j * lda + i] + bad : 0.0;
+        }
     }
 }
 

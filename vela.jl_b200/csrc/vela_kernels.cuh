@@ -131,6 +131,8 @@ struct CholArgs {
     int with_prior;
     double* out;
     int use_smem;
+    double* ahat;              // optional [B][p]: conditional mean of the marginalised amplitudes, Sigma u
+    double* cf;                // optional [B][p][p] row-major upper Cholesky factor of Sigma^-1 (L^T)
 };
 
 __global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, const double* defaults, const int* free_idx,

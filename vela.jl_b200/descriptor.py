@@ -14,7 +14,7 @@ import numpy as np
 
 from . import model as M
 
-VELA_B200_ABI_VERSION = 2
+VELA_B200_ABI_VERSION = 3
 VELA_MAX_PAR = 24
 
 # VelaComponentKind
@@ -23,7 +23,8 @@ VELA_MAX_PAR = 24
  COMP_EXP_DIP, COMP_SPINDOWN, COMP_PHASE_OFFSET, COMP_PHASE_JUMP_EXCLUSIVE, COMP_PHASE_JUMP,
  COMP_MEASUREMENT_NOISE, COMP_DM_JUMP_EXCLUSIVE, COMP_DM_JUMP, COMP_DM_MEASUREMENT_NOISE, COMP_BINARY_ELL1H,
  COMP_BINARY_ELL1K, COMP_BINARY_DDH, COMP_BINARY_DDS, COMP_BINARY_DDK, COMP_FD, COMP_FD_JUMP, COMP_WAVEX, COMP_DM_WAVEX,
- COMP_CM_WAVEX, COMP_SOLAR_WIND_PIECEWISE, COMP_DM_OFFSET_EXCLUSIVE, COMP_DM_OFFSET) = range(1, 32)
+ COMP_CM_WAVEX, COMP_SOLAR_WIND_PIECEWISE, COMP_DM_OFFSET_EXCLUSIVE, COMP_DM_OFFSET, COMP_POWERLAW_RED_GP,
+ COMP_POWERLAW_DM_GP, COMP_POWERLAW_CHROM_GP) = range(1, 35)
 FLAG_ECLIPTIC, FLAG_PLANET_SHAPIRO, FLAG_USE_FBX = 1, 2, 4
 KERNEL_WHITE, KERNEL_ECORR, KERNEL_WOODBURY_WHITE, KERNEL_WOODBURY_ECORR = 0, 1, 2, 3
 GP_POWERLAW_RED, GP_POWERLAW_DM, GP_POWERLAW_CHROM, GP_MARGINALIZED_TM = 1, 2, 3, 4
@@ -55,6 +56,7 @@ class VelaModelDesc(C.Structure):
         ("noise_basis", C.POINTER(C.c_double)),
         ("n_ecorr_groups", C.c_int32), ("par_ecorr", C.c_int32), ("ecorr_groups", C.POINTER(C.c_uint64)),
         ("n_devices", C.c_int32), ("_pad", C.c_int32), ("devices", C.POINTER(C.c_int32)),
+        ("n_aux", C.c_int64), ("aux_values", C.POINTER(C.c_double)),
     ]
 
 
@@ -136,6 +138,7 @@ class ModelDescriptor:
             return first
 
         comps: List[VelaComponentDesc] = []
+        aux: List[float] = []
 
         def new(kind, flags=0):
             c = VelaComponentDesc()
@@ -239,6 +242,28 @@ class ModelDescriptor:
                 setp(c, 3, pre + "FREQ_")
                 if kind == COMP_CM_WAVEX:
                     setp(c, 4, "TNCHROMIDX")
+            elif isinstance(comp, M._PowerlawGP):
+                # the same structs double as delay components when their amplitudes are free parameters
+                kind = {M.PowerlawRedNoiseGP: COMP_POWERLAW_RED_GP, M.PowerlawDispersionNoiseGP: COMP_POWERLAW_DM_GP,
+                        M.PowerlawChromaticNoiseGP: COMP_POWERLAW_CHROM_GP}[type(comp)]
+                c = new(kind)
+                setp(c, 0, comp.amp)
+                setp(c, 1, comp.gam)
+                setp(c, 2, comp.prefix + "SIN_", 0)
+                setp(c, 3, comp.prefix + "COS_")
+                setp(c, 4, comp.freq)
+                setp(c, 5, comp.prefix + "EPOCH")
+                if kind == COMP_POWERLAW_CHROM_GP:
+                    setp(c, 6, "TNCHROMIDX")
+                if c.len[0] != len(comp.ln_js) or ph.length(comp.prefix + "COS_") != len(comp.ln_js):
+                    raise ValueError("length(alphas) == length(betas) == length(ln_js) (gp_noise.jl:24)")
+                zeros = np.flatnonzero(comp.ln_js == 0)
+                if len(zeros) == 0:
+                    raise ValueError("ln_js has no zero entry (findfirst(iszero, ln_js), gp_noise.jl:37)")
+                c.len[1] = int(zeros[0])
+                c.len[2] = len(aux)
+                aux.extend(comp.ln_js.tolist())
+                aux.extend(comp.js().tolist())
             elif isinstance(comp, M.SolarWindDispersionPiecewise):
                 c = new(COMP_SOLAR_WIND_PIECEWISE)
                 setp(c, 0, "SWXDM_", 0)
@@ -300,6 +325,10 @@ class ModelDescriptor:
         d.n_components = len(comps)
         d.components = self._comps
 
+        self._aux = np.ascontiguousarray(aux, dtype=np.float64)
+        d.n_aux = len(self._aux)
+        if len(self._aux):
+            d.aux_values = _dptr(self._aux)
         self._defaults = np.ascontiguousarray(ph._default_values, dtype=np.float64)
         self._free = np.ascontiguousarray(ph._free_indices0, dtype=np.int32)
         d.n_params = len(self._defaults)

@@ -79,6 +79,8 @@ struct VelaModelDesc
     n_devices::Int32
     _pad::Int32
     devices::Ptr{Int32}
+    n_aux::Int64
+    aux_values::Ptr{Float64}
 end
 
 # ---- parameter offsets: the flattened `_default_params_tuple` (src/parameter/parameter.jl:87-92,151-153) ----
@@ -98,6 +100,7 @@ mutable struct Builder
     ntoa::Int
     index_masks::Vector{Vector{UInt32}}
     bit_rows::Vector{Vector{UInt8}}
+    aux::Vector{Float64}
 end
 
 function comp(kind; flags = 0, par = (), len = (), mask = (), dval = (0.0, 0.0))
@@ -200,6 +203,21 @@ xwavex(b::Builder, kind, pre) =
 describe(b::Builder, ::WaveX) = xwavex(b, 26, :WX)
 describe(b::Builder, ::DMWaveX) = xwavex(b, 27, :DMWX)
 describe(b::Builder, ::CMWaveX) = xwavex(b, 28, :CMWX)
+# power-law GPs with free amplitudes used as delay components (gp_noise.jl:120-130,165-183,219-235): the aux table
+# carries ln_js widened to Float64 and js = exp(ln_j) evaluated in the field's own type (Float32 for the red GP)
+function free_gp(b::Builder, kind, tn, pre, ln_js; idx = false)
+    nlog = findfirst(iszero, ln_js) - 1
+    aux0 = length(b.aux)
+    append!(b.aux, Float64.(collect(ln_js)))
+    append!(b.aux, Float64.(map(exp, collect(ln_js))))
+    par = [(0, off(b, Symbol(tn, :AMP))), (1, off(b, Symbol(tn, :GAM))), (2, off(b, Symbol(pre, :SIN_))),
+        (3, off(b, Symbol(pre, :COS_))), (4, off(b, Symbol(pre, :FREQ))), (5, off(b, Symbol(pre, :EPOCH)))]
+    idx && push!(par, (6, off(b, :TNCHROMIDX)))
+    return comp(kind; par = par, len = [(0, length(ln_js)), (1, nlog), (2, aux0)])
+end
+describe(b::Builder, c::PowerlawRedNoiseGP) = free_gp(b, 32, :TNRED, :PLRED, c.ln_js)
+describe(b::Builder, c::PowerlawDispersionNoiseGP) = free_gp(b, 33, :TNDM, :PLDM, c.ln_js)
+describe(b::Builder, c::PowerlawChromaticNoiseGP) = free_gp(b, 34, :TNCHROM, :PLCHROM, c.ln_js; idx = true)
 describe(b::Builder, c::SolarWindDispersionPiecewise) =
     comp(29; par = [(0, off(b, :SWXDM_))], len = [(0, len(b, :SWXDM_))], mask = [(0, add_index_mask!(b, c.swx_mask))],
         dval = (c.conjunction_geometry.x, c.opposition_geometry.x))
@@ -275,7 +293,7 @@ check(rc, what) = rc == 0 ? nothing : error("$what failed ($rc): $(last_error())
 
 function B200Pulsar(model::TimingModel, toas::Vector{T}; devices::Vector{Int32} = Int32[]) where {T<:TOABase}
     ph = model.param_handler
-    b = Builder(param_offsets(ph), length(toas), Vector{UInt32}[], Vector{UInt8}[])
+    b = Builder(param_offsets(ph), length(toas), Vector{UInt32}[], Vector{UInt8}[], Float64[])
     comps = VelaComponentDesc[describe(b, c) for c in model.components]
     defaults = copy(ph._default_values)
     free0 = Int32.(ph._free_indices .- 1)
@@ -283,6 +301,7 @@ function B200Pulsar(model::TimingModel, toas::Vector{T}; devices::Vector{Int32} 
     bit_masks = isempty(b.bit_rows) ? UInt8[] : reduce(vcat, b.bit_rows)
     wide = T <: WidebandTOA
     tzr = [model.tzr_toa]
+    aux = b.aux
 
     kernel = model.kernel
     gps = VelaGPDesc[]
@@ -299,7 +318,7 @@ function B200Pulsar(model::TimingModel, toas::Vector{T}; devices::Vector{Int32} 
         error("VelaB200: kernel $(typeof(kernel)) is not on the GPU path yet")
     end
     if kernel isa WoodburyKernel
-        kernel_kind = inner isa EcorrKernel ? 3 : 2     # 3 is refused by the library for now (VELA_ERR_UNSUPPORTED)
+        kernel_kind = inner isa EcorrKernel ? 3 : 2
         basis = kernel.noise_basis
         for gp in kernel.gp_components
             if gp isa MarginalizedTimingModel
@@ -318,12 +337,13 @@ function B200Pulsar(model::TimingModel, toas::Vector{T}; devices::Vector{Int32} 
     end
 
     handle = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve comps defaults free0 toas tzr index_masks bit_masks gps keep basis egroups devices begin
-        desc = VelaModelDesc(2, length(comps), pointer(comps), length(defaults), length(free0), pointer(defaults),
+    GC.@preserve comps defaults free0 toas tzr index_masks bit_masks gps keep basis egroups devices aux begin
+        desc = VelaModelDesc(3, length(comps), pointer(comps), length(defaults), length(free0), pointer(defaults),
             pointer(free0), length(toas), wide ? 1 : 0, sizeof(T), pointer(toas), pointer(tzr),
             length(b.index_masks), length(b.bit_rows), pointer(index_masks), pointer(bit_masks), kernel_kind,
             length(gps), pointer(gps), size(basis, 1), size(basis, 2), max(size(basis, 1), 1), pointer(basis),
-            length(egroups), par_ecorr, Ptr{UInt64}(pointer(egroups)), length(devices), 0, pointer(devices))
+            length(egroups), par_ecorr, Ptr{UInt64}(pointer(egroups)), length(devices), 0, pointer(devices),
+            length(aux), pointer(aux))
         check(ccall((:vela_b200_create, LIB), Cint, (Ref{VelaModelDesc}, Ref{Ptr{Cvoid}}), desc, handle), "vela_b200_create")
     end
     psr = B200Pulsar{typeof(model),T}(model, toas, handle[], false)
@@ -397,6 +417,27 @@ function Vela._calc_resids_and_Ninvdiag(psr::B200Pulsar, params)
     check(ccall((:vela_b200_residuals, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
             psr.handle, v, length(v), y, w), "vela_b200_residuals")
     return y, w
+end
+
+"""
+    marginalized_offset_mean_and_covinvcf(psr, paramss) -> (ahat::Matrix (p x B), cf::Array (p x p x B))
+
+Conditional mean of the analytically marginalised amplitudes and the Cholesky factor of Sigma^-1 for a batch, from the
+factorisation the likelihood already computed (what pyvela derives on the host with scipy in spnta.py:376-394).
+`cf[:, :, b]` is the row-major upper factor of the C ABI read column-major, i.e. the LOWER factor L with
+Sigma^-1 = L L'; `UpperTriangular(cf[:, :, b]')` is scipy's `cholesky(lower=False)`.
+"""
+function marginalized_offset_mean_and_covinvcf(psr::B200Pulsar, paramss::AbstractMatrix)
+    B, nd = size(paramss)
+    A = paramss isa StridedMatrix{Float64} ? paramss : Matrix{Float64}(paramss)
+    rs, cs = strides(A)
+    p = ccall((:vela_b200_n_basis, LIB), Int64, (Ptr{Cvoid},), psr.handle)
+    ahat = Matrix{Float64}(undef, p, B)
+    cf = Array{Float64,3}(undef, p, p, B)
+    GC.@preserve A check(ccall((:vela_b200_marginalized_mean_batch, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            psr.handle, pointer(A), B, nd, rs, cs, ahat, cf, C_NULL), "vela_b200_marginalized_mean_batch")
+    return ahat, cf
 end
 
 end # module

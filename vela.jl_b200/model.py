@@ -449,6 +449,12 @@ class _PowerlawGP(Component):
     def get_gp_npars(self) -> int:
         return 2 * len(self.ln_js)
 
+    def js(self) -> np.ndarray:
+        """exp(ln_j) as the reference evaluates it: in the storage type of the field (gp_noise.jl:41)."""
+        if self.float32_ln_js:
+            return np.exp(self.ln_js.astype(np.float32)).astype(np.float64)
+        return np.exp(self.ln_js)
+
     def __repr__(self):
         return f"{type(self).__name__}({len(self.ln_js)} harmonics)"
 

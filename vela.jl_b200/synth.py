@@ -155,6 +155,10 @@ CONFIGS = {
     # ECORR kernels: epochs of 8 TOAs (one per observing frequency) form the ECORR groups
     "extra_ecorr": dict(ntoa=1600, span_d=3000.0, ecorr=True, nback=3, walkers=256, seed=19),
     "extra_ecorr_gp": dict(ntoa=1600, span_d=3000.0, ecorr=True, red=12, dmgp=10, nback=3, walkers=256, seed=20),
+    # power-law GPs with free amplitudes as delay components (marginalize_gp_noise=False): (Nlin, Nlog) per GP
+    "extra_free_gp": dict(ntoa=900, span_d=3000.0, ured=(6, 2), udm=(5, 0), uchrom=(4, 1), nback=2, walkers=128, seed=22),
+    "extra_free_gp_wb": dict(ntoa=700, span_d=2500.0, wideband=True, udm=(6, 1), ured=(4, 0), binary="ELL1", nback=2,
+                             walkers=128, seed=23),
     "config3_gp_ecorr": dict(ntoa=10000, span_d=4000.0, red=30, ecorr=True, nback=4, walkers=8192, seed=21),
 }
 
@@ -218,6 +222,13 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
     if cfg.get("chromgp"):
         sp("CMEPOCH", 0.0, dim=1)
         sp("TNCHROMIDX", 4.0)
+    free_gps = [(key, pre, tn, cfg[key]) for key, pre, tn in (("ured", "PLRED", "TNRED"), ("udm", "PLDM", "TNDM"),
+                                                              ("uchrom", "PLCHROM", "TNCHROM")) if cfg.get(key)]
+    for key, pre, tn, (nlin, nlog) in free_gps:
+        sp(pre + "EPOCH", -0.37 * span, dim=1)
+        sp(pre + "FREQ", 1.0 / span, dim=-1)
+        if key == "uchrom" and not cfg.get("chromgp"):
+            sp("TNCHROMIDX", 4.0)
     binary = cfg.get("binary")
     ell1_like = binary in ("ELL1", "ELL1H", "ELL1k")
     dd_like = binary in ("DD", "DDH", "DDS", "DDK")
@@ -334,8 +345,19 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         mp("SWXDM_", 3e-4 * DMCONST * (1 + 0.2 * np.arange(nswx)), [True] * nswx, dim=-1, prefix="SWXDM_", sig=[0.0] * nswx)
     if cfg.get("fdjumpdm"):
         mp("FDJUMPDM", [1e-4 * DMCONST, -2e-4 * DMCONST], [True, True], dim=-1, prefix="FDJUMPDM", sig=[0.0, 0.0])
+    for key, pre, tn, (nlin, nlog) in free_gps:
+        nh = nlin + nlog
+        mp(pre + "SIN_", rng.standard_normal(nh), [True] * nh, prefix=pre + "SIN_", sig=[0.0] * nh)
+        mp(pre + "COS_", rng.standard_normal(nh), [True] * nh, prefix=pre + "COS_", sig=[0.0] * nh)
     mp("F", [0.0, -1.0e-15], [not mtm, not mtm], dim=-1, prefix="F", sig=[0.0, 0.0])
     # noise parameters
+    for (key, pre, tn, _), (amp, gam) in zip(free_gps, ((-13.6, 3.8), (-13.4, 3.2), (-13.8, 3.5))):
+        amp, gam = {"ured": (-13.6, 3.8), "udm": (-13.4, 3.2), "uchrom": (-13.8, 3.5)}[key]
+        sp(tn + "AMP", amp, free=True, noise=True)
+        sp(tn + "GAM", gam, free=True, noise=True)
+        # with fixed amplitudes the hyper-parameters scale the delay itself: keep the scatter at the few-sigma level
+        noise_draw_names[tn + "AMP"] = ("normal", amp, 0.002)
+        noise_draw_names[tn + "GAM"] = ("normal", gam, 0.002)
     for key, amp, gam in (("RED", -13.6, 3.8), ("DM", -13.4, 3.2), ("CHROM", -13.8, 3.5)):
         flag = {"RED": "red", "DM": "dmgp", "CHROM": "chromgp"}[key]
         if cfg.get(flag):
@@ -374,6 +396,8 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         comps.append(M.DispersionPiecewise(seg(ndmx)))
     if cfg.get("dmwavex"):
         comps.append(M.DMWaveX())
+    elif cfg.get("udm"):
+        comps.append(M.PowerlawDispersionNoiseGP(*cfg["udm"], 2.0))
     if cfg.get("fdjumpdm") == "exclusive":
         comps.append(M.ExclusiveDispersionOffset(((np.arange(n) // 4) % 3).astype(np.uint32)))
     elif cfg.get("fdjumpdm") == "bits":
@@ -388,6 +412,8 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         comps.append(M.ChromaticPiecewise(seg(ncmx)[::-1].copy()))
     if cfg.get("cmwavex"):
         comps.append(M.CMWaveX())
+    elif cfg.get("uchrom"):
+        comps.append(M.PowerlawChromaticNoiseGP(*cfg["uchrom"], 2.0))
     if binary == "DDK":
         comps.append(M.BinaryDDK(bool(cfg.get("fbx")), ecl))
     elif binary:
@@ -401,6 +427,8 @@ def make_dataset(name: str, make_eval: Callable, ntoa: Optional[int] = None, see
         comps.append(M.ChromaticExponentialDip())
     if cfg.get("wavex"):
         comps.append(M.WaveX())
+    elif cfg.get("ured"):
+        comps.append(M.PowerlawRedNoiseGP(*cfg["ured"], 2.0))
     comps.append(M.Spindown())
     if ng:
         comps.append(M.Glitch())
