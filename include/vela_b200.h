@@ -38,7 +38,9 @@
 #ifndef VELA_B200_H
 #define VELA_B200_H
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -266,6 +268,8 @@ typedef struct VelaModelDesc {
 
 typedef struct VelaPulsar* VelaHandle;
 
+#ifndef __CUDACC_RTC__   /* the entry points are host functions: hidden from the device-only NVRTC pass */
+
 /* Number of usable CUDA devices (0 if none / no driver). */
 VELA_API int vela_b200_device_count(void);
 
@@ -379,6 +383,20 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
  * Sigma^-1 carries the exact N^-1 (the reference helper keeps only its diagonal there).
  * Woodbury kernels only; runs on devices[0].
  */
+/*
+ * Per-model specialisation of the chain kernel.  `create` compiles the component chain of THIS model with NVRTC
+ * (program baked in as constants; same source and flags as the generic kernel, bit-identical results) unless
+ * VELA_B200_JIT=0 or libnvrtc cannot be loaded, in which case the generic interpreting kernel is used.
+ *   vela_b200_chain_specialized(h, -1) -> 1 / 0: which kernel is in use;  (h, 0 | 1) switches (A/B tests).
+ *   vela_b200_jit_log(h): compiler log, or why there is no specialised kernel.
+ *   vela_b200_debug_spec_source / _compile: the generated translation unit and a device-free compile of it
+ *   (returns the cubin size), for tests and tooling.
+ */
+VELA_API int vela_b200_chain_specialized(VelaHandle h, int on);
+VELA_API const char* vela_b200_jit_log(VelaHandle h);
+VELA_API int64_t vela_b200_debug_spec_source(const VelaModelDesc* desc, char* buf, int64_t cap);
+VELA_API int64_t vela_b200_debug_spec_compile(const VelaModelDesc* desc);
+
 VELA_API int vela_b200_marginalized_mean_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
                                                int64_t row_stride, int64_t col_stride, double* ahat, double* cf,
                                                double* lnlike);
@@ -413,6 +431,8 @@ VELA_API double vela_b200_fp64_peak_tflops(int device, int kind);
 
 /* Test hook: the correctly rounded sin/cos (double-double Taylor) used for the sky-position unit vector. */
 VELA_API int vela_b200_debug_sincos(const double* x, int n, double* s, double* c);
+
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -104,3 +104,32 @@ def test_marginalized_mean_refused_for_white_kernels(vb, datasets):
     with pytest.raises(vb.VelaB200Error):
         psr.marginalized_offset_mean_vectorized(ds.walkers(2, seed=1))
     assert psr.get_marginalized_param_offset_mean(ds.truth).size == 0
+
+
+def test_whitened_residuals(datasets, oracle):
+    """spnta.py:523-556: the per-group closed form equals the reference's dense ECORR normal equations."""
+    from scipy.linalg import cho_factor, cho_solve
+    ds, psr, md = datasets("extra_ecorr", None)
+    x = ds.walkers(1, seed=9)[0]
+    y, w = psr.resids_and_Ninvdiag(x)
+    groups = [g for g in np.asarray(ds.model.kernel.ecorr_groups, dtype=np.int64).reshape(-1, 3) if g[2] > 0]
+    ph = ds.model.param_handler
+    full = np.array(ph._default_values)
+    full[np.asarray(ph._free_indices0)] = x
+    U = np.zeros((len(y), len(groups)))
+    phi = np.empty(len(groups))
+    for k, (a0, a1, idx) in enumerate(groups):
+        U[a0 - 1:a1, k] = 1.0
+        phi[k] = full[ph.offset("ECORR") + idx - 1] ** 2
+    NinvU = U * w[:, None]
+    ahat = cho_solve(cho_factor(np.diag(1 / phi) + U.T @ NinvU), NinvU.T @ y)
+    np.testing.assert_allclose(psr.whitened_time_residuals(x), y - U @ ahat, rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(psr.scaled_toa_uncertainties(x), 1 / np.sqrt(w), rtol=1e-15)
+    # wideband + GP: the whitened residuals remove exactly M a for the draw made with the same generator
+    ds4, psr4, _ = datasets("config4_dd_wb", 700)
+    n = len(ds4.toas)
+    real = psr4.get_marginalized_gp_noise_realization(ds4.truth, np.random.default_rng(5))
+    np.testing.assert_array_equal(psr4.whitened_time_residuals(ds4.truth, np.random.default_rng(5)),
+                                  psr4.time_residuals(ds4.truth) - real[:n])
+    np.testing.assert_array_equal(psr4.whitened_dm_residuals(ds4.truth, np.random.default_rng(5)),
+                                  psr4.dm_residuals(ds4.truth) - real[n:])

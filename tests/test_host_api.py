@@ -156,3 +156,21 @@ def test_shard_range(vb):
             blocks = [sr(n, world, r) for r in range(world)]
             assert blocks[0][0] == 0 and blocks[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+
+
+def test_chain_specialisation_source_and_nvrtc_compile(vb, oracle):
+    """The per-model translation unit names every component once and compiles with NVRTC without a GPU."""
+    import ctypes as C
+    from helpers import oracle_eval_factory
+    L = vb.lib.lib()
+    ds = vb.synth.make_dataset("extra_ell1_fbx", oracle_eval_factory(vb, oracle), ntoa=120)
+    md = vb.ModelDescriptor(ds.model, ds.toas)
+    buf = C.create_string_buffer(1 << 16)
+    n = L.vela_b200_debug_spec_source(md.byref(), buf, len(buf))
+    src = buf.value.decode()
+    assert n == len(src) and src.count("VELA_APPLY(") == len(ds.model.components)
+    assert "vela_chain_spec" in src and "kSpecProg" in src
+    size = L.vela_b200_debug_spec_compile(md.byref())
+    if size < 0 and b"libnvrtc not available" in L.vela_b200_last_error():
+        pytest.skip("libnvrtc not installed")
+    assert size > 10000, L.vela_b200_last_error()

@@ -225,6 +225,47 @@ class Pulsar:
             return np.zeros(len(self.toas))
         return np.asarray(self.model.kernel.noise_basis) @ self.get_marginalized_param_offset_sample(params, rng)[0]
 
+    # -- residual post-processing (pyvela/pyvela/spnta.py:506-556); y, N^-1 come from the device chain
+    def time_residuals(self, params) -> np.ndarray:
+        return self.resids_and_Ninvdiag(params)[0][: len(self.toas)]
+
+    def dm_residuals(self, params) -> np.ndarray:
+        if not self.toas.wideband:
+            raise AssertionError("This method is only defined for wideband datasets.")
+        return self.resids_and_Ninvdiag(params)[0][len(self.toas):]
+
+    def scaled_toa_uncertainties(self, params) -> np.ndarray:
+        return 1.0 / np.sqrt(self.resids_and_Ninvdiag(params)[1][: len(self.toas)])
+
+    def whitened_time_residuals(self, params, rng=None) -> np.ndarray:
+        """spnta.py:523-556: subtract one GP realisation, then the conditional mean of the ECORR jitter.  The
+        ECORR design matrix is block-orthogonal, so its normal equations decouple into one scalar per group."""
+        y, w = self.resids_and_Ninvdiag(params)
+        n = len(self.toas)
+        r = y[:n].copy()
+        if self.has_marginalized_gp_noise:
+            r -= self.get_marginalized_gp_noise_realization(params, rng)[:n]
+        kernel = self.model.kernel
+        inner = getattr(kernel, "inner_kernel", kernel)
+        groups = getattr(inner, "ecorr_groups", None)
+        if groups is not None:
+            ph = self.model.param_handler
+            full = np.array(ph._default_values, dtype=np.float64)
+            full[np.asarray(ph._free_indices0)] = self._free(params)
+            ecorr0 = ph.offset("ECORR") if ph.has("ECORR") else 0
+            for a0, a1, idx in np.asarray(groups, dtype=np.int64).reshape(-1, 3):
+                if idx > 0:
+                    sl = slice(a0 - 1, a1)
+                    c2 = full[ecorr0 + idx - 1] ** 2
+                    r[sl] -= np.sum(r[sl] * w[sl]) / (1.0 / c2 + np.sum(w[sl]))
+        return r
+
+    def whitened_dm_residuals(self, params, rng=None) -> np.ndarray:
+        d = self.dm_residuals(params)
+        if self.has_marginalized_gp_noise:
+            d = d - self.get_marginalized_gp_noise_realization(params, rng)[len(self.toas):]
+        return d
+
     # -- benchmarking hooks
     def lnlike_device(self, d_params_ptr: int, B: int, d_out_ptr: int, stream: int = 0):
         _lib.check(self._lib.vela_b200_lnlike_batch_device(self._h, C.c_void_p(d_params_ptr), B,
@@ -235,6 +276,13 @@ class Pulsar:
         _lib.check(self._lib.vela_b200_lnpost_batch_device(self._h, C.c_void_p(d_params_ptr), B,
                                                            C.c_void_p(d_lnprior_ptr), 1, C.c_void_p(d_out_ptr),
                                                            C.c_void_p(stream)), "vela_b200_lnpost_batch_device")
+
+    def chain_specialized(self, on=None) -> bool:
+        """Whether the per-model (NVRTC) chain kernel is in use; `on=True/False` switches kernels (A/B tests)."""
+        return bool(self._lib.vela_b200_chain_specialized(self._h, -1 if on is None else int(bool(on))))
+
+    def jit_log(self) -> str:
+        return (self._lib.vela_b200_jit_log(self._h) or b"").decode(errors="replace")
 
     def launch_count(self) -> int:
         return int(self._lib.vela_b200_launch_count(self._h))

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "vela_jit.h"
 #include "vela_kernels.cuh"
 
 using namespace vela;
@@ -49,6 +50,7 @@ int upload(T** dst, const T* src, size_t n) {
 
 inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
 constexpr long kSplitRows = 2048;   // walker rows reserved for split-K slabs of small batches
+constexpr long kMaxBigSplit = 4;    // split-K slabs kept for full-size batches (wave quantisation), memory permitting
 
 struct Buffers {  // per-device, per-batch scratch (grown on demand)
     long cap_B = 0;
@@ -61,6 +63,7 @@ struct Buffers {  // per-device, per-batch scratch (grown on demand)
 
 struct DeviceModel {
     int dev = 0;
+    int n_sm = 148;
     cudaStream_t stream = nullptr;
     double* toa = nullptr;
     long toa_stride = 0;
@@ -88,7 +91,7 @@ struct VelaPulsar {
     ProgramDev prog;
     int kernel_kind = 0;
     long n_toas = 0, n_rows = 0, n_rows_pad = 0;
-    int p = 0, pp = 0, n_units = 0, n_pair_units = 0, n_gp = 0;
+    int p = 0, pp = 0, n_gp = 0;
     long n_pairs = 0, ld_sig = 0;
     int sig_shape = 0;
     size_t sig_smem = 0;
@@ -104,6 +107,9 @@ struct VelaPulsar {
     bool stage_timing = false;
     bool have_priors = false;
     long max_chunk = 0;  // walkers per device per pass
+    cudaKernel_t spec_chain = nullptr;   // NVRTC-specialised chain kernel (vela_jit.cu); null = generic kernel only
+    bool use_spec = false;
+    std::string jit_log;
 };
 
 namespace {
@@ -138,12 +144,13 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
     if (h->p > 0) {
         // Sigma / U scratch: at least `cap` walker rows, and never fewer than kSplitRows so that small batches can
         // hold several split-K slabs
-        b.sig_rows = std::max<long>(cap, kSplitRows);
+        const long slabs = std::max<long>(1, std::min<long>(kMaxBigSplit, (long)(((size_t)6 << 30) / ((size_t)cap * h->ld_sig * sizeof(double)))));
+        b.sig_rows = std::max<long>(cap * slabs, kSplitRows);
         CU(cudaMalloc((void**)&b.Sig, (size_t)b.sig_rows * h->ld_sig * sizeof(double)));
         CU(cudaMalloc((void**)&b.U, (size_t)b.sig_rows * h->pp * sizeof(double)));
         CU(cudaMemsetAsync(b.Sig, 0, (size_t)b.sig_rows * h->ld_sig * sizeof(double), d.stream));
         CU(cudaMemsetAsync(b.U, 0, (size_t)b.sig_rows * h->pp * sizeof(double), d.stream));
-        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * h->pp * h->pp * sizeof(double)));
+        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * (h->p + 1) * (h->pp + 1) * sizeof(double)));
         if (h->n_eg > 0) {
             size_t vb = (size_t)cap * h->eg_pad * h->ldv * sizeof(double);
             CU(cudaMalloc((void**)&b.V, vb));
@@ -168,24 +175,53 @@ int ensure_host_buffers(VelaPulsar* h, DeviceModel& d, long B) {
     return 0;
 }
 
-// Small batches do not fill the GPU with (units x walker groups) CTAs; split the TOA axis over gridDim.z and let
-// K4 sum the slabs (deterministic).  Returns the number of slices for a batch of B walkers.
-int choose_ksplit(VelaPulsar* h, long sig_rows, long B, int bk, int warps, int nsamp) {
-    const long ctas = (long)((h->n_units + warps - 1) / warps) * ((B + nsamp - 1) / nsamp);
-    const long n_ktiles = h->n_rows_pad / bk;
-    long want = (2 * 148 + ctas - 1) / ctas;
-    want = std::min<long>(want, std::max<long>(1, n_ktiles / 4));
-    want = std::min<long>(want, std::max<long>(1, sig_rows / std::max<long>(round_up(B, kSigMaxSamples), 1)));
-    return (int)std::max<long>(1, std::min<long>(want, 64));
-}
-
-// K3 launch shapes: (BK, stages, m-tiles, n-tiles, warps); see DESIGN.md section 5
-struct SigmaShape { int bk, stages, mt, nt, warps, ctas_per_sm; void (*kernel)(SigmaArgs); };
-#define VELA_SHAPE(BK, ST, MT, NT, W, C) SigmaShape{BK, ST, MT, NT, W, C, sigma_contract_kernel<BK, ST, MT, NT, W>}
+// K3 launch shapes: (BK, stages, n-tiles, warps) with two row-tile heights per shape; see DESIGN.md section 5
+struct SigmaShape { int bk, stages, nt, warps, ctas_per_sm; void (*kernel4)(SigmaArgs); void (*kernel3)(SigmaArgs); };
+#define VELA_SHAPE(BK, ST, NT, W, C) \
+    SigmaShape{BK, ST, NT, W, C, sigma_contract_kernel<BK, ST, 4, NT, W>, sigma_contract_kernel<BK, ST, 3, NT, W>}
 const SigmaShape kSigmaShapes[] = {
-    VELA_SHAPE(64, 3, 4, 4, 16, 1), VELA_SHAPE(32, 4, 4, 4, 16, 1), VELA_SHAPE(32, 3, 4, 4, 16, 1), VELA_SHAPE(16, 4, 4, 4, 16, 1),
-    VELA_SHAPE(16, 3, 4, 4, 16, 1), VELA_SHAPE(16, 2, 4, 4, 16, 1), VELA_SHAPE(8, 2, 4, 4, 16, 1),
+    VELA_SHAPE(64, 3, 4, 16, 1), VELA_SHAPE(32, 4, 4, 16, 1), VELA_SHAPE(32, 3, 4, 16, 1), VELA_SHAPE(16, 4, 4, 16, 1),
+    VELA_SHAPE(16, 3, 4, 16, 1), VELA_SHAPE(16, 2, 4, 16, 1), VELA_SHAPE(8, 2, 4, 16, 1),
 };
+
+// K3 work quantisation.  A CTA is `warps` units of MT m8-tiles over 32 walkers and one CTA is resident per SM, so a
+// launch costs about  CTAs x t_cta / SMs + 0.8 t_cta  (throughput term + tail; the tail factor is fitted to the
+// measurements in tests/gpu_plan_probe.py).  Two knobs trade padding against the tail: the row-tile height MT (4 or 3
+// m8-tiles per warp) and split-K over gridDim.z (K4 sums the slabs in slice order, so the result stays deterministic
+// for a given batch size).  Small batches use the same model: few CTAs -> deep split.
+struct SigmaPlan { int mt, ksplit, n_pair_units, n_units; };
+SigmaPlan plan_sigma(const VelaPulsar* h, const SigmaShape& sh, long sig_rows, long B, int n_sm) {
+    const int nsamp = 8 * sh.nt;
+    const long n_ktiles = h->n_rows_pad / sh.bk;
+    const long pair_tiles = (h->n_pairs + 7) / 8, u_tiles = h->pp / 8;
+    const long max_split = std::max<long>(1, std::min<long>({64, std::max<long>(1, n_ktiles / 4),
+                                                              sig_rows / std::max<long>(round_up(B, kSigMaxSamples), 1)}));
+    // Units: one k-tile of 64 TOAs for one m8 tile row of a CTA (2.4 us on a B200).  Measured at config 3 / 4
+    // (tests/gpu_plan_probe.py): the MT = 3 kernel runs ~12 % slower per DMMA (10 LDS per 12 DMMAs instead of 12 per
+    // 16), and every extra split-K slab costs K4 one more pass over the walkers' packed triangles.
+    const double kFixed = 6.0;                         // pipeline fill + epilogue of one CTA
+    const double tile = sh.bk / 64.0;
+    const double slab = 1.3e-6 * (double)B * (double)h->n_pairs;
+    SigmaPlan best{4, 1, 0, 0};
+    double best_cost = 1e300;
+    const int force_mt = getenv("VELA_B200_SIGMA_MT") ? atoi(getenv("VELA_B200_SIGMA_MT")) : 0;
+    const int force_ks = getenv("VELA_B200_SIGMA_KSPLIT") ? atoi(getenv("VELA_B200_SIGMA_KSPLIT")) : 0;
+    for (int mt = 4; mt >= 3; --mt) {
+        if (force_mt && mt != force_mt) continue;
+        const long pu = (pair_tiles + mt - 1) / mt, units = pu + (u_tiles + mt - 1) / mt;
+        const long ctas_xy = ((units + sh.warps - 1) / sh.warps) * ((B + nsamp - 1) / nsamp);
+        for (long ks = 1; ks <= max_split; ++ks) {
+            if (force_ks && ks != std::min<long>(force_ks, max_split)) continue;
+            const long kt = (n_ktiles + ks - 1) / ks, nz = (n_ktiles + kt - 1) / kt;
+            if (nz != ks) continue;   // same slicing as a smaller ks
+            const double t_cta = (double)kt * tile * mt * (mt == 3 ? 1.12 : 1.0) + kFixed;
+            const double n_cta = (double)(ctas_xy * nz);
+            const double cost = std::max(n_cta / n_sm, 1.0) * t_cta + 0.8 * t_cta + slab * (double)(ks - 1);
+            if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = SigmaPlan{mt, (int)ks, (int)pu, (int)units}; }
+        }
+    }
+    return best;
+}
 
 // WoodburyKernel{EcorrKernel}: subtract the per-group Sherman-Morrison terms from slab 0 of Sigma / U (K2b + K2c).
 void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st) {
@@ -209,24 +245,24 @@ void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t
     h->launches += 2;
 }
 
-// Fills the launch arguments, picks split-K and launches K3; returns the split count K4 has to sum.
+// Fills the launch arguments, plans (row-tile height, split-K) and launches K3; returns the split count K4 has to sum.
 int launch_sigma(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, SigmaArgs* out_args = nullptr) {
     const SigmaShape& sh = kSigmaShapes[h->sig_shape];
     Buffers& b = d.buf;
     const int nsamp = 8 * sh.nt;
+    const SigmaPlan pl = plan_sigma(h, sh, b.sig_rows, B, d.n_sm);
     SigmaArgs sa;
-    sa.M = d.M; sa.ldM = d.ldM; sa.rank = h->p; sa.n_pairs = h->n_pairs; sa.n_pair_units = h->n_pair_units;
-    sa.n_units = h->n_units; sa.n_rows_pad = h->n_rows_pad; sa.W = b.W; sa.Y = b.Y; sa.ld_yw = h->n_rows_pad; sa.B = B;
+    sa.M = d.M; sa.ldM = d.ldM; sa.rank = h->p; sa.n_pairs = h->n_pairs; sa.n_pair_units = pl.n_pair_units;
+    sa.n_units = pl.n_units; sa.n_rows_pad = h->n_rows_pad; sa.W = b.W; sa.Y = b.Y; sa.ld_yw = h->n_rows_pad; sa.B = B;
     sa.Sig = b.Sig; sa.ld_sig = h->ld_sig; sa.U = b.U; sa.ld_u = h->pp;
-    const int ksplit = choose_ksplit(h, b.sig_rows, B, sh.bk, sh.warps, nsamp);
     const long n_ktiles = h->n_rows_pad / sh.bk;
-    sa.kt_per_split = (int)((n_ktiles + ksplit - 1) / ksplit);
+    sa.kt_per_split = (int)((n_ktiles + pl.ksplit - 1) / pl.ksplit);
     const int nz = (int)((n_ktiles + sa.kt_per_split - 1) / sa.kt_per_split);
     const long rows = round_up(B, kSigMaxSamples);
     sa.split_stride_sig = rows * h->ld_sig;
     sa.split_stride_u = rows * h->pp;
-    dim3 grid((unsigned)((h->n_units + sh.warps - 1) / sh.warps), (unsigned)((B + nsamp - 1) / nsamp), (unsigned)nz);
-    sh.kernel<<<grid, sh.warps * 32, h->sig_smem, st>>>(sa);
+    dim3 grid((unsigned)((pl.n_units + sh.warps - 1) / sh.warps), (unsigned)((B + nsamp - 1) / nsamp), (unsigned)nz);
+    (pl.mt == 4 ? sh.kernel4 : sh.kernel3)<<<grid, sh.warps * 32, h->sig_smem, st>>>(sa);
     if (out_args) *out_args = sa;
     return nz;
 }
@@ -237,15 +273,28 @@ int set_smem_attrs(int dev) {
     int max_optin = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     max_optin -= 256;   // room for the static mbarrier words
-    for (const SigmaShape& sh : kSigmaShapes)
-        CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-    CU(cudaFuncSetAttribute(chol_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
+    for (const SigmaShape& sh : kSigmaShapes) {
+        CU(cudaFuncSetAttribute(sh.kernel4, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+        CU(cudaFuncSetAttribute(sh.kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    }
+    CU(cudaFuncSetAttribute(chol_finish_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
+    CU(cudaFuncSetAttribute(chol_finish_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(toa_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     return 0;
+}
+
+// K1 launch: the NVRTC-specialised kernel of this model when it exists and is enabled, else the generic interpreter
+void launch_chain(VelaPulsar* h, dim3 grid, size_t smem, cudaStream_t st, ChainArgs& ca) {
+    if (h->use_spec && h->spec_chain) {
+        void* args[] = {&ca};
+        cudaLaunchKernel((const void*)h->spec_chain, grid, dim3((unsigned)h->chain_threads), args, smem, st);
+    } else {
+        toa_chain_kernel<<<grid, h->chain_threads, smem, st>>>(h->prog, ca);
+    }
 }
 
 // Enqueue the whole pipeline for B walkers whose parameters already sit in d_params (row-major B x n_free).
@@ -270,7 +319,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
     const int warps = h->chain_threads / 32;
     size_t chain_smem = ((size_t)h->chain_group * pg.row + 2 * h->chain_group + (size_t)warps * h->chain_group * 2) * sizeof(double);
     dim3 cgrid((unsigned)h->n_tiles, (unsigned)((B + h->chain_group - 1) / h->chain_group));
-    toa_chain_kernel<<<cgrid, h->chain_threads, chain_smem, st>>>(pg, ca);
+    launch_chain(h, cgrid, chain_smem, st, ca);
     h->launches += 2;
     if (ecorr) {
         EcorrArgs ea;
@@ -298,7 +347,9 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         ch.lnprior = d_lnprior; ch.with_prior = with_prior; ch.out = d_out; ch.use_smem = h->chol_smem ? 1 : 0;
         ch.ksplit = ksplit; ch.split_stride_sig = sa.split_stride_sig; ch.split_stride_u = sa.split_stride_u;
         ch.ahat = d_ahat; ch.cf = d_cf;
-        chol_finish_kernel<<<(unsigned)B, kCholThreads, h->chol_smem_bytes, st>>>(ch);
+        int chol_threads = 128;     // measured best across ranks 60..300 (tests/gpu_chol_probe.py)
+        if (const char* e = getenv("VELA_B200_CHOL_THREADS")) chol_threads = std::max(32, std::min(kCholThreads, atoi(e) / 32 * 32));
+        (h->p <= kCholSmallRank ? chol_finish_kernel<8> : chol_finish_kernel<16>)<<<(unsigned)B, chol_threads, h->chol_smem_bytes, st>>>(ch);
         if (timing) cudaEventRecord(d.ev[4], st);
         h->launches += 2;
     }
@@ -312,6 +363,7 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
                  const std::vector<double>& gp_data, const std::vector<int3>& egroups, const std::vector<int>& echunks,
                  const std::vector<int3>& eactive) {
     CU(cudaSetDevice(d.dev));
+    CU(cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, d.dev));
     CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     for (auto& e : d.ev) CU(cudaEventCreate(&e));
     if (upload(&d.toa, toa_soa.data(), toa_soa.size())) return VELA_ERR_CUDA;
@@ -374,6 +426,57 @@ void fill_toa_columns(const double* rec, int wideband, double* cols, long stride
         for (int i = 0; i < 3; ++i) put(C_PLANET + 3 * b + i, r[i]);
         put(C_RPLANET + b, std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]));
     }
+}
+
+// Component program of a validated descriptor (offsets of the hoisted per-sample values included).
+void build_program(const VelaModelDesc* desc, ProgramDev& pg) {
+    memset(&pg, 0, sizeof pg);
+    pg.n_comp = desc->n_components;
+    pg.n_params = desc->n_params;
+    pg.n_free = desc->n_free;
+    pg.wideband = desc->wideband;
+    int nder = 0;
+    for (int ic = 0; ic < desc->n_components; ++ic) {
+        const VelaComponentDesc& c = desc->components[ic];
+        CompDev& cd = pg.comp[ic];
+        cd.kind = c.kind; cd.flags = c.flags;
+        memcpy(cd.par, c.par, sizeof cd.par);
+        memcpy(cd.len, c.len, sizeof cd.len);
+        memcpy(cd.mask, c.mask, sizeof cd.mask);
+        memcpy(cd.dval, c.dval, sizeof cd.dval);
+        cd.der = nder;
+        nder += derived_count(c.kind, c.len);
+    }
+    pg.n_derived = nder;
+    pg.row = pg.n_params + nder;
+    if ((pg.row & 1) == 0) pg.row += 1;  // odd pitch: conflict-free column reads across rows
+}
+
+// Translation unit of the per-model chain kernel: the program as a constant object + the shared kernel body.
+std::string spec_source(const ProgramDev& pg) {
+    std::string src;
+    char buf[256];
+    src += "#define VELA_SPEC_CALLS";
+    for (int ic = 0; ic < pg.n_comp; ++ic) { snprintf(buf, sizeof buf, " VELA_APPLY(%d)", ic); src += buf; }
+    src += "\n#include \"vela_chain.cuh\"\nnamespace vela {\n";
+    snprintf(buf, sizeof buf, "__device__ const ProgramDev kSpecProg = {%d, %d, %d, %d, %d, %d, {\n", pg.n_comp, pg.n_params,
+             pg.n_derived, pg.row, pg.wideband, pg.n_free);
+    src += buf;
+    for (int ic = 0; ic < pg.n_comp; ++ic) {
+        const CompDev& c = pg.comp[ic];
+        snprintf(buf, sizeof buf, "  {%d, %d, {", c.kind, c.flags);
+        src += buf;
+        for (int k = 0; k < VELA_MAX_PAR; ++k) { snprintf(buf, sizeof buf, "%d%s", c.par[k], k + 1 < VELA_MAX_PAR ? "," : ""); src += buf; }
+        snprintf(buf, sizeof buf, "}, {%d,%d,%d,%d}, {%d,%d}, %d, {", c.len[0], c.len[1], c.len[2], c.len[3], c.mask[0], c.mask[1], c.der);
+        src += buf;
+        // hexadecimal floating literals: the struct constants round-trip bit for bit
+        snprintf(buf, sizeof buf, "%a, %a}},\n", c.dval[0], c.dval[1]);
+        src += buf;
+    }
+    src += "}};\n}  // namespace vela\n"
+           "extern \"C\" __global__ void __launch_bounds__(vela::kChainThreads, 2) vela_chain_spec(vela::ChainArgs a) {\n"
+           "    vela::chain_body(vela::kSpecProg, a);\n}\n";
+    return src;
 }
 
 int validate(const VelaModelDesc* d) {
@@ -451,26 +554,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
 
     VelaPulsar* h = new VelaPulsar();
     ProgramDev& pg = h->prog;
-    memset(&pg, 0, sizeof pg);
-    pg.n_comp = desc->n_components;
-    pg.n_params = desc->n_params;
-    pg.n_free = desc->n_free;
-    pg.wideband = desc->wideband;
-    int nder = 0;
-    for (int ic = 0; ic < desc->n_components; ++ic) {
-        const VelaComponentDesc& c = desc->components[ic];
-        CompDev& cd = pg.comp[ic];
-        cd.kind = c.kind; cd.flags = c.flags;
-        memcpy(cd.par, c.par, sizeof cd.par);
-        memcpy(cd.len, c.len, sizeof cd.len);
-        memcpy(cd.mask, c.mask, sizeof cd.mask);
-        memcpy(cd.dval, c.dval, sizeof cd.dval);
-        cd.der = nder;
-        nder += derived_count(c.kind, c.len);
-    }
-    pg.n_derived = nder;
-    pg.row = pg.n_params + nder;
-    if ((pg.row & 1) == 0) pg.row += 1;  // odd pitch: conflict-free column reads across rows
+    build_program(desc, pg);
 
     h->kernel_kind = desc->kernel_kind;
     h->n_toas = desc->n_toas;
@@ -530,9 +614,6 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         }
         if (h->sig_shape < 0) { delete h; return fail(VELA_ERR_UNSUPPORTED, "basis rank %d does not fit any Sigma-contraction shape", h->p); }
         const SigmaShape& shp = kSigmaShapes[h->sig_shape];
-        const long pair_tiles = (h->n_pairs + 7) / 8;
-        h->n_pair_units = (int)((pair_tiles + shp.mt - 1) / shp.mt);
-        h->n_units = h->n_pair_units + (h->pp / 8 + shp.mt - 1) / shp.mt;
         h->sig_smem = sigma_smem_bytes(h->p, shp.bk, shp.stages, shp.nt);
         int col = 0;
         for (int g = 0; g < desc->n_gp; ++g) {
@@ -551,9 +632,10 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
             col += s.kind == VELA_GP_MARGINALIZED_TM ? s.n : 2 * s.n;
             gps.push_back(gd);
         }
-        size_t need = ((size_t)2 * h->pp + (size_t)h->p * (h->pp + 1)) * sizeof(double);
+        const int cnb = h->p <= kCholSmallRank ? 8 : 16;
+        size_t need = chol_smem_doubles(h->p, h->pp, cnb, true) * sizeof(double);
         h->chol_smem = need <= 200 * 1024;
-        h->chol_smem_bytes = h->chol_smem ? need : (size_t)2 * h->pp * sizeof(double);
+        h->chol_smem_bytes = h->chol_smem ? need : chol_smem_doubles(h->p, h->pp, cnb, false) * sizeof(double);
     }
 
     // SoA TOA table (+ TOA-only hoists) and the TZR block
@@ -589,9 +671,33 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     }
     cudaSetDevice(prev);
 
+    // per-model chain kernel (vela_jit.cu); any failure leaves the generic kernel in charge
+    {
+        const char* e = getenv("VELA_B200_JIT");
+        if (!(e && atoi(e) == 0)) {
+            cudaKernel_t k = nullptr;
+            if (jit_chain_kernel(spec_source(pg), &k, h->jit_log) == 0) {
+                bool ok = true;
+                for (auto& d : h->devs) {
+                    cudaSetDevice(d.dev);
+                    int max_optin = 0;
+                    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.dev);
+                    if (cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 256) != cudaSuccess) {
+                        h->jit_log = std::string("cudaFuncSetAttribute on the specialised kernel: ") + cudaGetErrorString(cudaGetLastError());
+                        ok = false;
+                    }
+                }
+                cudaSetDevice(prev);
+                if (ok) { h->spec_chain = k; h->use_spec = true; }
+            }
+        } else {
+            h->jit_log = "disabled by VELA_B200_JIT=0";
+        }
+    }
+
     // walkers per device per pass: bound the y/w/Sigma scratch to ~1/4 of the device memory
     if (h->kernel_kind != VELA_KERNEL_WHITE) {
-        size_t per = (size_t)2 * h->n_rows_pad * 8 + (size_t)h->ld_sig * 8 + (size_t)h->pp * 8 + (h->chol_smem ? 0 : (size_t)h->pp * h->pp * 8) + (size_t)h->eg_pad * h->ldv * 8;
+        size_t per = (size_t)2 * h->n_rows_pad * 8 + (size_t)h->ld_sig * 8 + (size_t)h->pp * 8 + (h->chol_smem ? 0 : (size_t)(h->p + 1) * (h->pp + 1) * 8) + (size_t)h->eg_pad * h->ldv * 8;
         size_t free_b = 0, total_b = 0;
         cudaSetDevice(devices[0]);
         cudaMemGetInfo(&free_b, &total_b);
@@ -756,7 +862,7 @@ static int run_single(VelaHandle h, const double* params, int64_t n_free, int mo
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = mode;
     ca.Y = dY; ca.W = dW; ca.F = dF; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
-    toa_chain_kernel<<<dim3((unsigned)h->n_tiles, 1), h->chain_threads, chain_smem, d.stream>>>(h->prog, ca);
+    launch_chain(h, dim3((unsigned)h->n_tiles, 1), chain_smem, d.stream, ca);
     h->launches += 2;
     const long n = mode == 1 ? h->n_rows : h->n_toas;
     if (o0) cudaMemcpyAsync(o0, dY, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
@@ -919,7 +1025,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = 1;
     ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
-    toa_chain_kernel<<<dim3((unsigned)h->n_tiles, 1), h->chain_threads, chain_smem, d.stream>>>(h->prog, ca);
+    launch_chain(h, dim3((unsigned)h->n_tiles, 1), chain_smem, d.stream, ca);
     SigmaArgs sa;
     const int ksplit = launch_sigma(h, d, 1, d.stream, &sa);
     if (h->n_eg > 0) launch_ecorr_correction(h, d, 1, d.stream);
@@ -989,6 +1095,42 @@ VELA_API int vela_b200_marginalized_mean_batch(VelaHandle h, const double* param
     cudaFree(d_ahat); cudaFree(d_cf);
     cudaSetDevice(prev);
     return rc;
+}
+
+// 1 if the per-model (NVRTC) chain kernel is in use, 0 if the generic one is; `on` = 0/1 switches, -1 only queries.
+VELA_API int vela_b200_chain_specialized(VelaHandle h, int on) {
+    if (!h) return VELA_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(h->mtx);
+    if (on >= 0) h->use_spec = (on != 0) && h->spec_chain != nullptr;
+    return h->use_spec ? 1 : 0;
+}
+
+// Compiler log / reason the specialised kernel is absent (empty when it compiled cleanly).
+VELA_API const char* vela_b200_jit_log(VelaHandle h) { return h ? h->jit_log.c_str() : ""; }
+
+// test / tooling hook: compile the translation unit below with NVRTC (no device needed); returns the cubin size
+VELA_API int64_t vela_b200_debug_spec_compile(const VelaModelDesc* desc) {
+    if (int rc = validate(desc)) return rc;
+    ProgramDev pg;
+    build_program(desc, pg);
+    std::vector<char> cubin;
+    std::string log;
+    if (jit_compile_cubin(spec_source(pg), cubin, log)) return fail(VELA_ERR_UNSUPPORTED, "%s", log.c_str());
+    return (int64_t)cubin.size();
+}
+
+// test / tooling hook: the NVRTC translation unit create() would compile for this descriptor (no device needed)
+VELA_API int64_t vela_b200_debug_spec_source(const VelaModelDesc* desc, char* buf, int64_t cap) {
+    if (int rc = validate(desc)) return rc;
+    ProgramDev pg;
+    build_program(desc, pg);
+    const std::string src = spec_source(pg);
+    if (buf && cap > 0) {
+        const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
+        memcpy(buf, src.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)src.size();
 }
 
 VELA_API int vela_b200_set_stage_timing(VelaHandle h, int enabled) {

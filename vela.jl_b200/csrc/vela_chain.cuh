@@ -1,0 +1,119 @@
+// vela_chain.cuh - body of the per-(TOA, walker) chain kernel (K1), shared by the generic kernel in
+// vela_kernels.cu (program passed as a __grid_constant__ parameter and interpreted) and by the per-model
+// specialised kernel that vela_api.cu compiles at create() time with NVRTC (program baked in as a constant, so
+// the component switch and every parameter offset fold away).  Same source, same flags, same arithmetic.
+#pragma once
+#include "vela_device.cuh"
+
+namespace vela {
+
+constexpr int kChainThreads = 256;  // max threads per block of the chain kernel (one TOA each)
+
+struct ChainArgs {
+    const double* Pext;        // [B][row]
+    const double* tzr_phase;   // [B][2]
+    const double* toa;         // SoA table
+    long toa_stride;
+    long n_toas;
+    const uint32_t* index_masks;
+    const uint8_t* bit_masks;
+    long B;
+    int group;                 // walkers per block
+    int emit;                  // 1: write y, w (Woodbury path); 2: write phase (hi, lo) and spin frequency
+    double* Y;                 // [B_pad][ld_yw]
+    double* W;
+    double* F;                 // emit == 2 only
+    long ld_yw;
+    double* partial;           // [tiles][B][2]
+};
+
+__device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainArgs& a) {
+    extern __shared__ double smem[];
+    const int row = prog.row;
+    double* sP = smem;                                  // [group][row]
+    double* sTzr = sP + (size_t)a.group * row;          // [group][2]
+    double* sRed = sTzr + 2 * a.group;                  // [warps][group][2]
+
+    const long b0 = (long)blockIdx.y * a.group;
+    const int nb = (int)min((long)a.group, a.B - b0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < nb * row; i += blockDim.x) sP[i] = a.Pext[b0 * row + i];
+    for (int i = tid; i < 2 * nb; i += blockDim.x) sTzr[i] = a.tzr_phase[2 * b0 + i];
+
+    const long j = (long)blockIdx.x * blockDim.x + tid;
+    const bool active = j < a.n_toas;
+    const long jj = active ? j : a.n_toas - 1;
+    ToaRegs t = load_toa(a.toa, a.toa_stride, jj, false);
+    ChainEnv e;
+    e.toa_base = a.toa; e.stride = a.toa_stride; e.j = jj;
+    e.index_masks = a.index_masks; e.bit_masks = a.bit_masks; e.n_toas = a.n_toas;
+    e.tzr = false; e.wide = prog.wideband != 0;
+    __syncthreads();
+
+    for (int s = 0; s < nb; ++s) {
+        const double* P = sP + (size_t)s * row;
+        Corr k = run_chain(prog, P, t, e);
+        // form_residual residuals.jl:8-12: Float64((phase - pulse_number) - tzrphase) / (f (1 + doppler))
+        dd dphase = dd_sub(dd_sub(k.phase, dd{t.pn_hi, t.pn_lo}), dd{sTzr[2 * s], sTzr[2 * s + 1]});
+        double f = k.spin_frequency * (1 + k.doppler);
+        double tres = dphase.hi / f;
+        double err2 = (t.err2 + k.equad2) * k.efac * k.efac;  // scaled_toa_error_sqr toa.jl:122-123
+        double chi, lg, w = 0.0;
+        if (a.emit) {  // Woodbury: y^T N^-1 y and log det N from Ninvdiag, gls_likelihood.jl:81-99
+            w = 1.0 / err2;
+            chi = tres * tres * w;
+            lg = -log(w);
+        } else {
+            chi = tres * tres / err2;
+            lg = log(err2);
+        }
+        double dmres = 0.0, wdm = 0.0;
+        if (e.wide) {  // wideband_residuals.jl:6-17, wideband_toa.jl:68-69
+            dmres = t.dm - k.model_dm;
+            double dmerr2 = (t.dmerr2 + k.dmequad2) * k.dmefac * k.dmefac;
+            if (a.emit) {
+                wdm = 1.0 / dmerr2;
+                chi += dmres * dmres * wdm;
+                lg += -log(wdm);
+            } else {
+                chi += dmres * dmres / dmerr2;
+                lg += log(dmerr2);
+            }
+        }
+        if (k.bad || k.spin_frequency == 0.0) chi = CUDART_NAN;
+        if (!active) { chi = 0.0; lg = 0.0; }
+        if (a.emit == 2 && active) {  // phase mode: Double64 phase residual and doppler-shifted spin frequency
+            const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
+            a.Y[o] = dphase.hi;
+            a.W[o] = dphase.lo;
+            a.F[o] = f;
+        } else if (a.emit && active) {
+            const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
+            a.Y[o] = tres;
+            a.W[o] = w;
+            if (e.wide) {
+                a.Y[o + a.n_toas] = dmres;
+                a.W[o + a.n_toas] = wdm;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            chi += __shfl_xor_sync(0xffffffffu, chi, off);
+            lg += __shfl_xor_sync(0xffffffffu, lg, off);
+        }
+        if (lane == 0) {
+            sRed[((size_t)warp * a.group + s) * 2] = chi;
+            sRed[((size_t)warp * a.group + s) * 2 + 1] = lg;
+        }
+    }
+    __syncthreads();
+    const int nwarps = blockDim.x >> 5;
+    for (int i = tid; i < 2 * nb; i += blockDim.x) {
+        double acc = 0.0;
+        for (int w = 0; w < nwarps; ++w) acc += sRed[(size_t)w * a.group * 2 + i];
+        a.partial[((size_t)blockIdx.x * a.B + b0) * 2 + i] = acc;
+    }
+}
+
+}  // namespace vela

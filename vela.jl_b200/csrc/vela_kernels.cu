@@ -123,92 +123,7 @@ __global__ void prior_kernel(const PriorDev* __restrict__ priors, int nd, const 
 // chi^2 and log-det terms over its TOAs with warp shuffles; per-tile partials go to `partial`
 // [tile][walker][2] and are summed in a fixed order later (deterministic, no atomics).
 __global__ void __launch_bounds__(kChainThreads, 2) toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a) {
-    extern __shared__ double smem[];
-    const int row = prog.row;
-    double* sP = smem;                                  // [group][row]
-    double* sTzr = sP + (size_t)a.group * row;          // [group][2]
-    double* sRed = sTzr + 2 * a.group;                  // [warps][group][2]
-
-    const long b0 = (long)blockIdx.y * a.group;
-    const int nb = (int)min((long)a.group, a.B - b0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    for (int i = tid; i < nb * row; i += blockDim.x) sP[i] = a.Pext[b0 * row + i];
-    for (int i = tid; i < 2 * nb; i += blockDim.x) sTzr[i] = a.tzr_phase[2 * b0 + i];
-
-    const long j = (long)blockIdx.x * blockDim.x + tid;
-    const bool active = j < a.n_toas;
-    const long jj = active ? j : a.n_toas - 1;
-    ToaRegs t = load_toa(a.toa, a.toa_stride, jj, false);
-    ChainEnv e;
-    e.toa_base = a.toa; e.stride = a.toa_stride; e.j = jj;
-    e.index_masks = a.index_masks; e.bit_masks = a.bit_masks; e.n_toas = a.n_toas;
-    e.tzr = false; e.wide = prog.wideband != 0;
-    __syncthreads();
-
-    for (int s = 0; s < nb; ++s) {
-        const double* P = sP + (size_t)s * row;
-        Corr k = run_chain(prog, P, t, e);
-        // form_residual residuals.jl:8-12: Float64((phase - pulse_number) - tzrphase) / (f (1 + doppler))
-        dd dphase = dd_sub(dd_sub(k.phase, dd{t.pn_hi, t.pn_lo}), dd{sTzr[2 * s], sTzr[2 * s + 1]});
-        double f = k.spin_frequency * (1 + k.doppler);
-        double tres = dphase.hi / f;
-        double err2 = (t.err2 + k.equad2) * k.efac * k.efac;  // scaled_toa_error_sqr toa.jl:122-123
-        double chi, lg, w = 0.0;
-        if (a.emit) {  // Woodbury: y^T N^-1 y and log det N from Ninvdiag, gls_likelihood.jl:81-99
-            w = 1.0 / err2;
-            chi = tres * tres * w;
-            lg = -log(w);
-        } else {
-            chi = tres * tres / err2;
-            lg = log(err2);
-        }
-        double dmres = 0.0, wdm = 0.0;
-        if (e.wide) {  // wideband_residuals.jl:6-17, wideband_toa.jl:68-69
-            dmres = t.dm - k.model_dm;
-            double dmerr2 = (t.dmerr2 + k.dmequad2) * k.dmefac * k.dmefac;
-            if (a.emit) {
-                wdm = 1.0 / dmerr2;
-                chi += dmres * dmres * wdm;
-                lg += -log(wdm);
-            } else {
-                chi += dmres * dmres / dmerr2;
-                lg += log(dmerr2);
-            }
-        }
-        if (k.bad || k.spin_frequency == 0.0) chi = CUDART_NAN;
-        if (!active) { chi = 0.0; lg = 0.0; }
-        if (a.emit == 2 && active) {  // phase mode: Double64 phase residual and doppler-shifted spin frequency
-            const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
-            a.Y[o] = dphase.hi;
-            a.W[o] = dphase.lo;
-            a.F[o] = f;
-        } else if (a.emit && active) {
-            const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
-            a.Y[o] = tres;
-            a.W[o] = w;
-            if (e.wide) {
-                a.Y[o + a.n_toas] = dmres;
-                a.W[o + a.n_toas] = wdm;
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            chi += __shfl_xor_sync(0xffffffffu, chi, off);
-            lg += __shfl_xor_sync(0xffffffffu, lg, off);
-        }
-        if (lane == 0) {
-            sRed[((size_t)warp * a.group + s) * 2] = chi;
-            sRed[((size_t)warp * a.group + s) * 2 + 1] = lg;
-        }
-    }
-    __syncthreads();
-    const int nwarps = blockDim.x >> 5;
-    for (int i = tid; i < 2 * nb; i += blockDim.x) {
-        double acc = 0.0;
-        for (int w = 0; w < nwarps; ++w) acc += sRed[(size_t)w * a.group * 2 + i];
-        a.partial[((size_t)blockIdx.x * a.B + b0) * 2 + i] = acc;
-    }
+    chain_body(prog, a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -595,6 +510,14 @@ VELA_SIGMA_INST(16, 4, 4, 4, 16)
 VELA_SIGMA_INST(16, 3, 4, 4, 16)
 VELA_SIGMA_INST(16, 2, 4, 4, 16)
 VELA_SIGMA_INST(8, 2, 4, 4, 16)
+// 3x4 warp tiles: same CTA shape, used when 24-row units quantise the packed rows better (plan_sigma)
+VELA_SIGMA_INST(64, 3, 3, 4, 16)
+VELA_SIGMA_INST(32, 4, 3, 4, 16)
+VELA_SIGMA_INST(32, 3, 3, 4, 16)
+VELA_SIGMA_INST(16, 4, 3, 4, 16)
+VELA_SIGMA_INST(16, 3, 3, 4, 16)
+VELA_SIGMA_INST(16, 2, 3, 4, 16)
+VELA_SIGMA_INST(8, 2, 3, 4, 16)
 
 // ------------------------------------------------------------------------------------------
 // K4  + Phi^-1, Cholesky, log-det, solve, ln L
@@ -615,44 +538,56 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     return s;
 }
 
-__global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
+// Blocked right-looking factorisation (block width NB): per block column (1) the NB x NB diagonal block is
+// factorised by one warp in a small shared tile, (2) one thread per row solves the panel below it against that
+// block, (3) all threads apply the rank-NB update to the trailing lower triangle in 2x2 register micro-tiles fed
+// from a shared copy of the panel.  u is carried as an extra matrix row p: the panel solve turns it into
+// z = L^-1 u and the trailing update leaves -z.z in entry (p, p), so there is no separate forward solve.
+// Four block barriers per block column instead of five per column.
+template <int NB>
+__global__ void __launch_bounds__(kCholThreads, NB <= 8 ? 2 : 1) chol_finish_kernel(CholArgs a) {
     extern __shared__ double smem[];
     __shared__ double scratch[kCholThreads / 32];
     __shared__ int sFail;
+    constexpr int PP = NB + 1;                    // pitch of the panel / diagonal tiles
     const long b = blockIdx.x;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int p = a.p, pp = a.pp;
 
-    double* phi = smem;            // [pp]
-    double* z = phi + pp;          // [pp]
-    double* A;                     // lower triangle, row pitch lda
+    double* phi = smem;                           // [pp]
+    double* z = phi + pp;                         // [pp]   (conditional-mean back substitution only)
+    double* dblk = z + pp;                        // [NB][PP] diagonal block
+    double* rdiag = dblk + NB * PP;               // [NB]   1 / L_cc of the current block
+    double* panel = rdiag + NB;                   // [p + 1][PP] rows below the diagonal block
+    double* A;                                    // lower triangle + row p = u^T, row pitch lda
     int lda;
-    double* gA = a.Sig + (size_t)b * a.ld_sig;   // packed lower triangle t = r(r+1)/2 + c
     if (a.use_smem) {
         lda = pp + 1;
-        A = z + pp;
-        for (int r = 0; r < p; ++r) {
-            const double* src = gA + (size_t)r * (r + 1) / 2;
-            for (int c = tid; c <= r; c += nt) {
-                double v = src[c];
-                for (int z = 1; z < a.ksplit; ++z) v += src[(size_t)z * a.split_stride_sig + c];
-                A[r * lda + c] = v;
-            }
+        A = panel + (size_t)(p + 1) * PP;
+    } else {                                      // large rank: factorise in the L2-resident global scratch
+        lda = pp + 1;                             // room for entry (p, p) when p == pp
+        A = a.Sq + (size_t)b * (p + 1) * (pp + 1);
+    }
+    // ---- unpack the packed lower triangle t = r(r+1)/2 + c, summing the split-K slabs in slice order
+    {
+        const double* gA = a.Sig + (size_t)b * a.ld_sig;
+        const long n_pairs = (long)p * (p + 1) / 2;
+        int r = 0, c = tid;
+        while (c > r) { c -= r + 1; ++r; }
+        for (long t = tid; t < n_pairs; t += nt) {
+            double v = gA[t];
+            for (int zz = 1; zz < a.ksplit; ++zz) v += gA[(size_t)zz * a.split_stride_sig + t];
+            A[(size_t)r * lda + c] = v;
+            c += nt;
+            while (c > r) { c -= r + 1; ++r; }
         }
-    } else {
-        // large rank: unpack into the square scratch of this walker and factorise there (L2-resident)
-        lda = pp;
-        A = a.Sq + (size_t)b * pp * pp;
-        for (int r = 0; r < p; ++r) {
-            const double* src = gA + (size_t)r * (r + 1) / 2;
-            for (int c = tid; c <= r; c += nt) {
-                double v = src[c];
-                for (int z = 1; z < a.ksplit; ++z) v += src[(size_t)z * a.split_stride_sig + c];
-                A[r * lda + c] = v;
-            }
+        for (int i = tid; i < p; i += nt) {
+            double v = a.U[(size_t)b * a.ld_u + i];
+            for (int zz = 1; zz < a.ksplit; ++zz) v += a.U[(size_t)zz * a.split_stride_u + (size_t)b * a.ld_u + i];
+            A[(size_t)p * lda + i] = v;
         }
     }
-    if (tid == 0) sFail = 0;
+    if (tid == 0) { sFail = 0; A[(size_t)p * lda + p] = 0.0; }
 
     // ---- Phi^-1 for this walker
     const double* P = a.Pext + (size_t)b * a.row;
@@ -673,58 +608,146 @@ __global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
             }
         }
     }
-    for (int i = tid; i < p; i += nt) {
-        double v = a.U[(size_t)b * a.ld_u + i];
-        for (int zz = 1; zz < a.ksplit; ++zz) v += a.U[(size_t)zz * a.split_stride_u + (size_t)b * a.ld_u + i];
-        z[i] = v;
-    }
     __syncthreads();
     double lphi = 0.0;
     for (int i = tid; i < p; i += nt) {
         lphi += log(phi[i]);
-        A[i * lda + i] += phi[i];
+        A[(size_t)i * lda + i] += phi[i];
     }
     const double logdetPhi = -block_sum(lphi, scratch);
     __syncthreads();
 
-    // ---- Cholesky A = L L^T (isposdef + cholesky!, gls_likelihood.jl:211-217)
-    for (int k = 0; k < p; ++k) {
-        if (tid == 0) {
-            double d = A[k * lda + k];
-            if (!(d > 0.0) || !isfinite(d)) { sFail = 1; d = 1.0; }
-            A[k * lda + k] = sqrt(d);
+    // ---- Cholesky A = L L^T (isposdef + cholesky!, gls_likelihood.jl:211-217) and z = L^-1 u (ldiv!, :220)
+    const int n1 = p + 1;                         // matrix rows including the u row
+    for (int k0 = 0; k0 < p; k0 += NB) {
+        const int nb = min(NB, p - k0), k1 = k0 + nb;
+        // (1) diagonal block
+        if constexpr (NB <= 8) {
+            // one thread factorises the NB x NB block entirely in registers (a dependent chain either way; this
+            // avoids NB rounds of warp barriers and shared-memory round trips); rows >= nb are identity padding
+            if (tid == 0) {
+                double L[NB][NB];
+#pragma unroll
+                for (int r = 0; r < NB; ++r)
+#pragma unroll
+                    for (int c = 0; c <= r; ++c)
+                        L[r][c] = (r < nb) ? A[(size_t)(k0 + r) * lda + k0 + c] : (r == c ? 1.0 : 0.0);
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    double d = L[c][c];
+                    if (!(d > 0.0) || !isfinite(d)) { sFail = 1; d = 1.0; }
+                    const double rd = rsqrt(d);
+                    L[c][c] = d * rd;
+                    rdiag[c] = rd;
+#pragma unroll
+                    for (int r = c + 1; r < NB; ++r) L[r][c] *= rd;
+#pragma unroll
+                    for (int r = c + 1; r < NB; ++r)
+#pragma unroll
+                        for (int q = c + 1; q <= r; ++q) L[r][q] -= L[r][c] * L[q][c];
+                }
+#pragma unroll
+                for (int r = 0; r < NB; ++r)
+#pragma unroll
+                    for (int c = 0; c <= r; ++c) {
+                        dblk[r * PP + c] = L[r][c];
+                        if (r < nb) A[(size_t)(k0 + r) * lda + k0 + c] = L[r][c];
+                    }
+            }
+        } else {
+            for (int e = tid; e < nb * nb; e += nt) {
+                const int r = e / nb, c = e - r * nb;
+                if (c <= r) dblk[r * PP + c] = A[(size_t)(k0 + r) * lda + k0 + c];
+            }
+            __syncthreads();
+            if (tid < 32) {
+                for (int c = 0; c < nb; ++c) {
+                    if (tid == 0) {
+                        double d = dblk[c * PP + c];
+                        if (!(d > 0.0) || !isfinite(d)) { sFail = 1; d = 1.0; }
+                        const double rd = rsqrt(d);
+                        dblk[c * PP + c] = d * rd;
+                        rdiag[c] = rd;
+                    }
+                    __syncwarp();
+                    const double rd = rdiag[c];
+                    for (int r = c + 1 + tid; r < nb; r += 32) dblk[r * PP + c] *= rd;
+                    __syncwarp();
+                    const int m = nb - c - 1;     // trailing block of the tile: entries (r, q), c < q <= r < nb
+                    for (int e = tid; e < m * m; e += 32) {
+                        const int r = c + 1 + e / m, q = c + 1 + e % m;
+                        if (q <= r) dblk[r * PP + q] -= dblk[r * PP + c] * dblk[q * PP + c];
+                    }
+                    __syncwarp();
+                }
+                for (int e = tid; e < nb * nb; e += 32) {
+                    const int r = e / nb, c = e - r * nb;
+                    if (c <= r) A[(size_t)(k0 + r) * lda + k0 + c] = dblk[r * PP + c];
+                }
+            }
         }
         __syncthreads();
-        const double dk = A[k * lda + k];
-        for (int i = k + 1 + tid; i < p; i += nt) A[i * lda + k] /= dk;
+        // (2) panel: rows k1 .. p (row p is u^T) times L_kk^-T, one thread per row
+        for (int i = k1 + tid; i < n1; i += nt) {
+            double x[NB];
+            double* row = A + (size_t)i * lda + k0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) x[c] = c < nb ? row[c] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c < nb) {
+                    double v = x[c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) v -= x[q] * dblk[c * PP + q];
+                    x[c] = v * rdiag[c];
+                }
+            }
+            double* prow = panel + (size_t)(i - k1) * PP;
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+                if (c < nb) { row[c] = x[c]; prow[c] = x[c]; }
+                else prow[c] = 0.0;
+        }
         __syncthreads();
-        // trailing update, lower triangle: A[i][j] -= A[i][k] A[j][k], k < j <= i (16 x 16 thread grid)
+        // (3) trailing update A[i][j] -= sum_c L[i][k0+c] L[j][k0+c] for k1 <= j <= i <= p, 2x2 micro-tiles
         {
-            const int tx = tid & 15, ty = tid >> 4, sy = nt >> 4;
-            for (int i = k + 1 + ty; i < p; i += sy) {
-                const double aik = A[i * lda + k];
-                for (int j = k + 1 + tx; j <= i; j += 16) A[i * lda + j] -= aik * A[j * lda + k];
+            const int tx = tid & 15, ty = tid >> 4, ny = nt >> 4;
+            const int m = n1 - k1;                // trailing size (rows k1..p)
+            for (int i0 = ty; i0 < m; i0 += 2 * ny) {
+                const int i1 = i0 + ny;
+                double li0[NB], li1[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    li0[c] = panel[(size_t)i0 * PP + c];
+                    li1[c] = i1 < m ? panel[(size_t)i1 * PP + c] : 0.0;
+                }
+                for (int j0 = tx; j0 <= min(i1, m - 1); j0 += 32) {
+                    const int j1 = j0 + 16;
+                    double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) {
+                        const double lj0 = panel[(size_t)j0 * PP + c];
+                        const double lj1 = j1 < m ? panel[(size_t)j1 * PP + c] : 0.0;
+                        s00 += li0[c] * lj0; s01 += li0[c] * lj1;
+                        s10 += li1[c] * lj0; s11 += li1[c] * lj1;
+                    }
+                    if (j0 <= i0) A[(size_t)(k1 + i0) * lda + k1 + j0] -= s00;
+                    if (j1 <= i0 && j1 < m) A[(size_t)(k1 + i0) * lda + k1 + j1] -= s01;
+                    if (i1 < m) {
+                        if (j0 <= i1) A[(size_t)(k1 + i1) * lda + k1 + j0] -= s10;
+                        if (j1 <= i1 && j1 < m) A[(size_t)(k1 + i1) * lda + k1 + j1] -= s11;
+                    }
+                }
             }
         }
         __syncthreads();
     }
-    double ld = 0.0;
-    for (int i = tid; i < p; i += nt) ld += log(A[i * lda + i]);
-    const double logdetSig = 2 * block_sum(ld, scratch);
-    // ---- forward solve L z = u (ldiv!, gls_likelihood.jl:220)
-    for (int k = 0; k < p; ++k) {
-        __syncthreads();
-        if (tid == 0) z[k] /= A[k * lda + k];
-        __syncthreads();
-        const double zk = z[k];
-        for (int i = k + 1 + tid; i < p; i += nt) z[i] -= A[i * lda + k] * zk;
-    }
-    __syncthreads();
-    double zz = 0.0;
-    for (int i = tid; i < p; i += nt) zz += z[i] * z[i];
-    zz = block_sum(zz, scratch);
 
+    double ld = 0.0;
+    for (int i = tid; i < p; i += nt) ld += log(A[(size_t)i * lda + i]);
+    const double logdetSig = 2 * block_sum(ld, scratch);
     if (tid == 0) {
+        const double zz = -A[(size_t)p * lda + p];
         double yNy = 0.0, logdetN = 0.0;
         for (int t = 0; t < a.n_tiles; ++t) {
             yNy += a.partial[((size_t)t * a.B + b) * 2];
@@ -737,6 +760,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
     if (!a.ahat) return;
     // ---- conditional mean of the marginalised amplitudes: L^T ahat = z, i.e. ahat = Sigma u
     // (pyvela/pyvela/spnta.py:376-394: cho_solve((Sigmainv_cf, False), MT_Ninv_y)) and the upper factor L^T
+    for (int i = tid; i < p; i += nt) z[i] = A[(size_t)p * lda + i];
     for (int k = p - 1; k >= 0; --k) {
         __syncthreads();
         if (tid == 0) z[k] /= A[k * lda + k];
@@ -755,6 +779,8 @@ __global__ void __launch_bounds__(kCholThreads) chol_finish_kernel(CholArgs a) {
         }
     }
 }
+template __global__ void chol_finish_kernel<8>(CholArgs);
+template __global__ void chol_finish_kernel<16>(CholArgs);
 
 // Phi^-1 only (vela_b200_noise_weights_inv): one block, walker 0
 __global__ void phiinv_kernel(CholArgs a, double* __restrict__ out) {

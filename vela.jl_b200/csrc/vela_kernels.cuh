@@ -1,10 +1,8 @@
 // vela_kernels.cuh — launch-argument structs and tile constants shared by vela_kernels.cu and vela_api.cu
 #pragma once
-#include "vela_device.cuh"
+#include "vela_chain.cuh"
 
 namespace vela {
-
-constexpr int kChainThreads = 256;  // max threads per block of the chain kernel (one TOA each)
 
 // K3 tiling
 constexpr int kSigMaxSamples = 64;  // walkers per CTA: 8 x (n-tiles per warp)
@@ -16,24 +14,6 @@ struct PriorDev {
     int kind;
     double a, b, lo, hi;
     double norm;               // kind-dependent precomputed constant (log normalisation)
-};
-
-struct ChainArgs {
-    const double* Pext;        // [B][row]
-    const double* tzr_phase;   // [B][2]
-    const double* toa;         // SoA table
-    long toa_stride;
-    long n_toas;
-    const uint32_t* index_masks;
-    const uint8_t* bit_masks;
-    long B;
-    int group;                 // walkers per block
-    int emit;                  // 1: write y, w (Woodbury path); 2: write phase (hi, lo) and spin frequency
-    double* Y;                 // [B_pad][ld_yw]
-    double* W;
-    double* F;                 // emit == 2 only
-    long ld_yw;
-    double* partial;           // [tiles][B][2]
 };
 
 struct SigmaArgs {
@@ -113,7 +93,7 @@ struct CholArgs {
     double* Sig;               // packed lower triangle per walker
     long ld_sig;
     long ld_u;
-    double* Sq;                // [B][pp][pp] square scratch, only when the matrix does not fit shared memory
+    double* Sq;                // [B][p + 1][pp + 1] scratch, only when the matrix does not fit shared memory
     int ksplit;                // number of split-K slabs to sum
     long split_stride_sig;
     long split_stride_u;
@@ -150,7 +130,12 @@ __global__ void finish_white_kernel(const double* partial, int n_tiles, long B, 
 template <int BK, int STAGES, int MT, int NT, int WARPS>
 __global__ void sigma_contract_kernel(SigmaArgs a);
 
+template <int NB>
 __global__ void chol_finish_kernel(CholArgs a);
+constexpr int kCholSmallRank = 96;   // block width 8 up to this rank, 16 above
+inline size_t chol_smem_doubles(int p, int pp, int nb, bool matrix_in_smem) {
+    return (size_t)2 * pp + (size_t)nb * (nb + 1) + nb + (size_t)(p + 1) * (nb + 1) + (matrix_in_smem ? (size_t)(p + 1) * (pp + 1) : 0);
+}
 __global__ void phiinv_kernel(CholArgs a, double* out);
 __global__ void sincos_cr_kernel(const double* x, int n, double* s, double* c);
 __global__ void dfma_peak_kernel(double* out, int iters);

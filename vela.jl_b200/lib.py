@@ -21,7 +21,8 @@ EXPORTS = [
     "vela_b200_noise_weights_inv", "vela_b200_sigma_and_u", "vela_b200_lnlike_batch_device", "vela_b200_lnpost_batch_device", "vela_b200_launch_count",
     "vela_b200_set_stage_timing", "vela_b200_last_stage_ms", "vela_b200_fp64_peak_tflops",
     "vela_b200_debug_sincos", "vela_b200_set_priors", "vela_b200_lnprior_batch", "vela_b200_prior_transform_batch",
-    "vela_b200_marginalized_mean_batch",
+    "vela_b200_marginalized_mean_batch", "vela_b200_chain_specialized", "vela_b200_jit_log",
+    "vela_b200_debug_spec_source", "vela_b200_debug_spec_compile",
 ]
 
 
@@ -78,6 +79,13 @@ def lib():
     L.vela_b200_lnprior_batch.argtypes = [vp, dp, i64, i64, i64, i64, dp]
     L.vela_b200_prior_transform_batch.argtypes = [vp, dp, i64, i64, dp]
     L.vela_b200_marginalized_mean_batch.argtypes = [vp, dp, i64, i64, i64, i64, dp, dp, dp]
+    L.vela_b200_chain_specialized.argtypes = [vp, C.c_int]
+    L.vela_b200_jit_log.argtypes = [vp]
+    L.vela_b200_jit_log.restype = C.c_char_p
+    L.vela_b200_debug_spec_source.argtypes = [vp, C.c_char_p, i64]
+    L.vela_b200_debug_spec_source.restype = i64
+    L.vela_b200_debug_spec_compile.argtypes = [vp]
+    L.vela_b200_debug_spec_compile.restype = i64
     L.vela_b200_debug_sincos.argtypes = [dp, C.c_int, dp, dp]
     L.vela_b200_fp64_peak_tflops.argtypes = [C.c_int, C.c_int]
     L.vela_b200_fp64_peak_tflops.restype = C.c_double
