@@ -393,6 +393,10 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
  *   (returns the cubin size), for tests and tooling.
  */
 VELA_API int vela_b200_chain_specialized(VelaHandle h, int on);
+/* Structured Sigma path (Fourier-harmonic bases): host-only evaluation for tests, see vela_api.cu. */
+VELA_API int64_t vela_b200_debug_structured_sigma(const VelaModelDesc* desc, const double* w, double* sigma_packed, int32_t* info);
+/* 1 if this handle assembles Sigma from column sums (structured path), 0 if it runs the dense pair contraction. */
+VELA_API int vela_b200_sigma_structured(VelaHandle h);
 VELA_API const char* vela_b200_jit_log(VelaHandle h);
 VELA_API int64_t vela_b200_debug_spec_source(const VelaModelDesc* desc, char* buf, int64_t cap);
 VELA_API int64_t vela_b200_debug_spec_compile(const VelaModelDesc* desc);

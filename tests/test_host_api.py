@@ -174,3 +174,45 @@ def test_chain_specialisation_source_and_nvrtc_compile(vb, oracle):
     if size < 0 and b"libnvrtc not available" in L.vela_b200_last_error():
         pytest.skip("libnvrtc not installed")
     assert size > 10000, L.vela_b200_last_error()
+
+
+@pytest.mark.parametrize("name,ntoa", [("config3_gp", 600), ("config4_dd_wb", 400), ("config5_array", 500),
+                                       ("extra_ecorr_gp", None), ("fixture:sim3_gp", None), ("fixture:sim_dmgp_wb", None)])
+def test_structured_sigma_analysis_matches_dense(name, ntoa, vb, oracle, golden):
+    """Host half of the structured Sigma path: the harmonic structure is detected on the numbers of the basis
+    (synthetic bases and the PINT-made bases of the reference fixtures) and the column-sum table reproduces
+    M^T N^-1 M to rounding."""
+    import ctypes as C
+    from helpers import oracle_eval_factory
+    if name.startswith("fixture:"):
+        g = golden(name.split(":")[1])
+        model, toas, x = g.model, g.toas, g.x0
+    else:
+        ds = vb.synth.make_dataset(name, oracle_eval_factory(vb, oracle), ntoa=ntoa)
+        model, toas, x = ds.model, ds.toas, ds.truth
+    md = vb.ModelDescriptor(model, toas)
+    M = np.asarray(model.kernel.noise_basis)
+    p = M.shape[1]
+    _, w = oracle.residuals(md, x)
+    out = np.zeros(p * (p + 1) // 2)
+    info = (C.c_int32 * 3)()
+    dp = C.POINTER(C.c_double)
+    n_r = vb.lib.lib().vela_b200_debug_structured_sigma(md.byref(), w.ctypes.data_as(dp), out.ctypes.data_as(dp), info)
+    assert 0 < n_r <= p * (p + 1) // 4 and info[2] >= 1          # at least 2x fewer rows than the packed triangle
+    dense = M.T @ (M * w[:, None])
+    il = np.tril_indices(p)
+    scale = np.sqrt(np.outer(np.diag(dense), np.diag(dense)))[il]
+    assert np.max(np.abs(out - dense[il]) / scale) < 1e-13
+
+
+def test_structured_sigma_rejects_unstructured_basis(vb, oracle):
+    """A basis that is not harmonic (random columns) stays on the dense path."""
+    from helpers import oracle_eval_factory
+    ds = vb.synth.make_dataset("config3_gp", oracle_eval_factory(vb, oracle), ntoa=300)
+    k = ds.model.kernel
+    rng = np.random.default_rng(0)
+    bad = vb.model.WoodburyKernel(k.inner_kernel, k.gp_components, rng.standard_normal(k.noise_basis.shape))
+    model = vb.model.TimingModel(ds.model.pulsar_name, ds.model.ephem, ds.model.clock, ds.model.units, ds.model.epoch,
+                                 ds.model.components, bad, ds.model.param_handler, ds.model.tzr_toa, ds.model.priors)
+    md = vb.ModelDescriptor(model, ds.toas)
+    assert vb.lib.lib().vela_b200_debug_structured_sigma(md.byref(), None, None, None) == 0

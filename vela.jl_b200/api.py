@@ -281,6 +281,10 @@ class Pulsar:
         """Whether the per-model (NVRTC) chain kernel is in use; `on=True/False` switches kernels (A/B tests)."""
         return bool(self._lib.vela_b200_chain_specialized(self._h, -1 if on is None else int(bool(on))))
 
+    def sigma_structured(self) -> bool:
+        """True when Sigma^-1 is assembled from trigonometric column sums (harmonic Fourier basis detected)."""
+        return bool(self._lib.vela_b200_sigma_structured(self._h))
+
     def jit_log(self) -> str:
         return (self._lib.vela_b200_jit_log(self._h) or b"").decode(errors="replace")
 

@@ -57,6 +57,8 @@ struct Buffers {  // per-device, per-batch scratch (grown on demand)
     long sig_rows = 0;   // walker rows of the Sigma / U scratch (>= cap_B; larger so small batches can split K)
     double *params = nullptr, *Pext = nullptr, *tzr = nullptr, *partial = nullptr, *Y = nullptr, *W = nullptr;
     double *Sig = nullptr, *U = nullptr, *Sq = nullptr, *V = nullptr, *out = nullptr, *lnprior = nullptr;
+    double* R = nullptr;   // structured path: column sums [r_rows][n_cols]
+    long r_rows = 0;
     double *h_params = nullptr, *h_out = nullptr, *h_lnprior = nullptr;  // pinned
     long h_cap = 0;
 };
@@ -74,6 +76,8 @@ struct DeviceModel {
     int* free_idx = nullptr;
     double* M = nullptr;
     long ldM = 0;
+    double* T = nullptr;            // structured path: [n_rows_pad x n_cols] table (device copy of StructPlan::T)
+    PairTerm* table = nullptr;
     GPDev* gp = nullptr;
     double* gp_data = nullptr;
     int3* ecorr_groups = nullptr;
@@ -87,8 +91,20 @@ struct DeviceModel {
 
 }  // namespace
 
+// Structured Sigma path (see colsum_kernel in vela_kernels.cu): the table of trigonometric / product columns T,
+// its M columns appended for u, and the per-pair recipe that rebuilds Sigma from the column sums.
+struct StructPlan {
+    bool active = false;
+    int n_r = 0;               // T columns (multiple of 32)
+    int n_cols = 0;            // n_r + round_up(p, 32)
+    int n_groups = 0;          // harmonic column groups found
+    std::vector<double> T;     // n_rows_pad x n_cols, column-major (host copy dropped after upload)
+    std::vector<PairTerm> table;
+};
+
 struct VelaPulsar {
     ProgramDev prog;
+    StructPlan sp;
     int kernel_kind = 0;
     long n_toas = 0, n_rows = 0, n_rows_pad = 0;
     int p = 0, pp = 0, n_gp = 0;
@@ -116,8 +132,9 @@ namespace {
 
 void free_buffers(Buffers& b) {
     cudaFree(b.params); cudaFree(b.Pext); cudaFree(b.tzr); cudaFree(b.partial); cudaFree(b.Y); cudaFree(b.W);
-    cudaFree(b.Sig); cudaFree(b.U); cudaFree(b.Sq); cudaFree(b.V); cudaFree(b.out); cudaFree(b.lnprior);
-    b.params = b.Pext = b.tzr = b.partial = b.Y = b.W = b.Sig = b.U = b.Sq = b.V = b.out = b.lnprior = nullptr;
+    cudaFree(b.Sig); cudaFree(b.U); cudaFree(b.Sq); cudaFree(b.V); cudaFree(b.out); cudaFree(b.lnprior); cudaFree(b.R);
+    b.params = b.Pext = b.tzr = b.partial = b.Y = b.W = b.Sig = b.U = b.Sq = b.V = b.out = b.lnprior = b.R = nullptr;
+    b.r_rows = 0;
     b.cap_B = 0;
     b.sig_rows = 0;
 }
@@ -141,7 +158,14 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
         CU(cudaMemsetAsync(b.Y, 0, yw, d.stream));
         CU(cudaMemsetAsync(b.W, 0, yw, d.stream));
     }
-    if (h->p > 0) {
+    if (h->p > 0 && h->sp.active) {
+        b.r_rows = std::max<long>(cap * 4, kSplitRows);
+        CU(cudaMalloc((void**)&b.R, (size_t)b.r_rows * h->sp.n_cols * sizeof(double)));
+        CU(cudaMemsetAsync(b.R, 0, (size_t)b.r_rows * h->sp.n_cols * sizeof(double), d.stream));
+    }
+    if (h->p > 0 && h->sp.active && h->n_eg == 0) {
+        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * (h->p + 1) * (h->pp + 1) * sizeof(double)));
+    } else if (h->p > 0) {
         // Sigma / U scratch: at least `cap` walker rows, and never fewer than kSplitRows so that small batches can
         // hold several split-K slabs
         const long slabs = std::max<long>(1, std::min<long>(kMaxBigSplit, (long)(((size_t)6 << 30) / ((size_t)cap * h->ld_sig * sizeof(double)))));
@@ -223,6 +247,193 @@ SigmaPlan plan_sigma(const VelaPulsar* h, const SigmaShape& sh, long sig_rows, l
     return best;
 }
 
+// ---- structured Sigma path: host-side analysis of the basis -----------------------------------------------------
+// Looks for column groups of the form  M[j, sin_k] = s_j sin(k x_j),  M[j, cos_k] = s_j cos(k x_j)  (the power-law
+// Fourier GPs; s_j is the per-row chromatic / DM-row scale, x_j one phase per row shared by all groups) and VERIFIES
+// the form on the numbers of M itself (relative 2e-13), so an arbitrary basis simply stays on the dense path.
+// Harmonic x harmonic products are then served by 2 (K_a + K_c) + 1 trigonometric columns per group pair, any
+// product with another column by an explicit product column.  Returns false when that is not at least ~2x fewer
+// rows than the packed triangle.
+bool analyse_basis(const VelaModelDesc* desc, long n_rows, long n_rows_pad, int p, StructPlan& sp) {
+    const char* env = getenv("VELA_B200_STRUCTURED");
+    if (env && atoi(env) == 0) return false;
+    const double* M = desc->noise_basis;
+    const long ld = desc->basis_ld;
+    auto Mc = [&](int c) { return M + (size_t)c * ld; };
+    std::vector<int> group(p, -1), kh(p, 0), is_cos(p, 0);
+    struct Grp { int sin1 = -1, cos1 = -1, kmax = 0; std::vector<int> cols; std::vector<double> s; bool ok = false; };
+    std::vector<Grp> groups;
+    int col = 0;
+    for (int g = 0; g < desc->n_gp; ++g) {
+        const VelaGPDesc& gp = desc->gp[g];
+        if (gp.kind == VELA_GP_MARGINALIZED_TM) { col += gp.n; continue; }
+        Grp G;
+        const int gi = (int)groups.size();
+        for (int i = 0; i < gp.n; ++i) {
+            const double j = std::exp(gp.ln_js[i]);
+            const long kk = std::lround(j);
+            if (kk >= 1 && std::fabs(j - (double)kk) <= 1e-6 * (double)kk) {
+                for (int t = 0; t < 2; ++t) {
+                    const int c = col + t * gp.n + i;
+                    group[c] = gi; kh[c] = (int)kk; is_cos[c] = t;
+                    G.cols.push_back(c);
+                }
+                if (kk == 1) { G.sin1 = col + i; G.cos1 = col + gp.n + i; }
+                G.kmax = std::max(G.kmax, (int)kk);
+            }
+        }
+        col += 2 * gp.n;
+        groups.push_back(std::move(G));
+    }
+    // one phase per row, from the first group whose fundamental is non-zero there
+    std::vector<double> x(n_rows, 0.0);
+    std::vector<char> have(n_rows, 0);
+    for (auto& G : groups) {
+        if (G.sin1 < 0) continue;
+        const double *sn = Mc(G.sin1), *cs = Mc(G.cos1);
+        for (long j = 0; j < n_rows; ++j)
+            if (!have[j] && (sn[j] != 0.0 || cs[j] != 0.0)) { x[j] = std::atan2(sn[j], cs[j]); have[j] = 1; }
+    }
+    int n_ok = 0;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        Grp& G = groups[gi];
+        if (G.sin1 < 0) continue;
+        const double *sn = Mc(G.sin1), *cs = Mc(G.cos1);
+        G.s.resize(n_rows);
+        for (long j = 0; j < n_rows; ++j) G.s[j] = sn[j] * std::sin(x[j]) + cs[j] * std::cos(x[j]);   // signed scale
+        bool ok = true;
+        for (int c : G.cols) {
+            const double* m = Mc(c);
+            for (long j = 0; j < n_rows && ok; ++j) {
+                const double arg = (double)kh[c] * x[j];
+                const double want = G.s[j] * (is_cos[c] ? std::cos(arg) : std::sin(arg));
+                if (!(std::fabs(m[j] - want) <= 2e-13 * std::fabs(G.s[j]) + 1e-300)) ok = false;
+            }
+            if (!ok) break;
+        }
+        G.ok = ok;
+        n_ok += ok;
+    }
+    for (int c = 0; c < p; ++c)
+        if (group[c] >= 0 && !groups[group[c]].ok) group[c] = -1;
+    if (n_ok == 0) return false;
+
+    // column layout of T: per unordered pair of good groups (a <= c): C(0..K), S(1..K), K = kmax_a + kmax_c
+    std::vector<int> good;
+    for (size_t gi = 0; gi < groups.size(); ++gi) if (groups[gi].ok) good.push_back((int)gi);
+    const int ng = (int)good.size();
+    std::vector<int> gslot(groups.size(), -1);
+    for (int i = 0; i < ng; ++i) gslot[good[i]] = i;
+    std::vector<int> baseC((size_t)ng * ng, -1), baseS((size_t)ng * ng, -1);
+    long n_r = 0;
+    for (int a = 0; a < ng; ++a)
+        for (int c = a; c < ng; ++c) {
+            const int K = groups[good[a]].kmax + groups[good[c]].kmax;
+            baseC[(size_t)a * ng + c] = baseC[(size_t)c * ng + a] = (int)n_r; n_r += K + 1;
+            baseS[(size_t)a * ng + c] = baseS[(size_t)c * ng + a] = (int)n_r - 1; n_r += K;   // S(m) at baseS + m, m >= 1
+        }
+    const long n_trig = n_r;
+    const long n_pairs = (long)p * (p + 1) / 2;
+    std::vector<std::pair<int, int>> products;
+    sp.table.assign(n_pairs, PairTerm{0, 0, 0.0, 0.0});
+    for (int r = 0; r < p; ++r)
+        for (int c = 0; c <= r; ++c) {
+            PairTerm& pt = sp.table[(size_t)r * (r + 1) / 2 + c];
+            if (group[r] >= 0 && group[c] >= 0) {
+                const int a = gslot[group[r]], b = gslot[group[c]];
+                const int bc = baseC[(size_t)a * ng + b], bs = baseS[(size_t)a * ng + b];
+                const int kr = kh[r], kc = kh[c], sum = kr + kc, dif = std::abs(kr - kc);
+                if (is_cos[r] == is_cos[c]) {        // sin sin = (C(|d|) - C(sum)) / 2,  cos cos = (C(|d|) + C(sum)) / 2
+                    pt = PairTerm{bc + dif, bc + sum, 0.5, is_cos[r] ? 0.5 : -0.5};
+                } else {                              // sin_k cos_l = (S(k + l) + S(k - l)) / 2, S(-m) = -S(m), S(0) = 0
+                    const int d = is_cos[r] ? (kc - kr) : (kr - kc);   // (harmonic of the sine) - (harmonic of the cosine)
+                    pt = PairTerm{bs + sum, d == 0 ? bs + sum : bs + std::abs(d), 0.5, d == 0 ? 0.0 : (d > 0 ? 0.5 : -0.5)};
+                }
+            } else {
+                pt = PairTerm{(int)(n_trig + (long)products.size()), 0, 1.0, 0.0};
+                products.emplace_back(r, c);
+            }
+        }
+    n_r = n_trig + (long)products.size();
+    if ((double)n_r > 0.5 * (double)n_pairs) { sp.table.clear(); return false; }
+    sp.n_r = (int)round_up(n_r, 32);
+    sp.n_cols = sp.n_r + (int)round_up(p, 32);
+    sp.n_groups = ng;
+    sp.T.assign((size_t)n_rows_pad * sp.n_cols, 0.0);
+    auto Tc = [&](long c) { return sp.T.data() + (size_t)c * n_rows_pad; };
+    for (int a = 0; a < ng; ++a)
+        for (int c = a; c < ng; ++c) {
+            const Grp &Ga = groups[good[a]], &Gc = groups[good[c]];
+            const int K = Ga.kmax + Gc.kmax, bc = baseC[(size_t)a * ng + c], bs = baseS[(size_t)a * ng + c];
+            for (long j = 0; j < n_rows; ++j) {
+                const double ss = Ga.s[j] * Gc.s[j];
+                if (ss == 0.0) continue;
+                for (int m = 0; m <= K; ++m) {
+                    const double arg = (double)m * x[j];
+                    Tc(bc + m)[j] = ss * std::cos(arg);
+                    if (m >= 1) Tc(bs + m)[j] = ss * std::sin(arg);
+                }
+            }
+        }
+    for (size_t i = 0; i < products.size(); ++i) {
+        const double *a = Mc(products[i].first), *b = Mc(products[i].second);
+        double* t = Tc(n_trig + (long)i);
+        for (long j = 0; j < n_rows; ++j) t[j] = a[j] * b[j];
+    }
+    for (int c = 0; c < p; ++c) memcpy(Tc(sp.n_r + c), Mc(c), sizeof(double) * n_rows);
+    sp.active = true;
+    return true;
+}
+
+// K3s launch shapes (BK, stages, column units, walker tiles per CTA)
+struct ColsumShape { int bk, stages, uc, wc; void (*kernel)(ColsumArgs); };
+const ColsumShape kColsumShapes[] = {
+    {16, 2, 16, 1, colsum_kernel<16, 2, 16, 1>}, {16, 3, 8, 2, colsum_kernel<16, 3, 8, 2>},
+    {16, 3, 4, 4, colsum_kernel<16, 3, 4, 4>}, {16, 2, 2, 8, colsum_kernel<16, 2, 2, 8>},
+};
+
+// Launches K3s for B walkers; returns the number of split-K slabs K4 has to sum.
+int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, ColsumArgs* out_args = nullptr) {
+    Buffers& b = d.buf;
+    const int n_units = h->sp.n_cols / 32;
+    // column units per CTA: everything in one CTA column when there are many units (W, Y are then staged once per
+    // walker tile), otherwise the shape that pads the unit count least
+    int si = 0;
+    if (n_units < 12) {
+        long best = 1 << 30;
+        for (int i = 1; i < 4; ++i) {
+            const long padded = round_up(n_units, kColsumShapes[i].uc);
+            if (padded < best) { best = padded; si = i; }
+        }
+    }
+    if (const char* e = getenv("VELA_B200_COLSUM_SHAPE")) si = std::max(0, std::min(3, atoi(e)));
+    const ColsumShape& sh = kColsumShapes[si];
+    const long n_ktiles = h->n_rows_pad / sh.bk;
+    const long ctas_xy = ((n_units + sh.uc - 1) / sh.uc) * ((B + 32 * sh.wc - 1) / (32 * sh.wc));
+    const long max_split = std::max<long>(1, std::min<long>({64, std::max<long>(1, n_ktiles / 8),
+                                                              b.r_rows / std::max<long>(round_up(B, kSigMaxSamples), 1)}));
+    long ks_best = 1;
+    double best_cost = 1e300;
+    for (long ks = 1; ks <= max_split; ++ks) {     // same cost model as plan_sigma
+        const long kt = (n_ktiles + ks - 1) / ks, nz = (n_ktiles + kt - 1) / kt;
+        if (nz != ks) continue;
+        const double t_cta = (double)kt * (sh.bk / 64.0) * 4 + 6.0;
+        const double cost = std::max((double)(ctas_xy * nz) / d.n_sm, 1.0) * t_cta + 0.8 * t_cta + 0.02 * t_cta * (double)(ks - 1) / ks;
+        if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; ks_best = ks; }
+    }
+    if (const char* e = getenv("VELA_B200_SIGMA_KSPLIT")) ks_best = std::max<long>(1, std::min<long>(atoi(e), max_split));
+    ColsumArgs ca;
+    ca.T = d.T; ca.ldT = h->n_rows_pad; ca.n_cols = h->sp.n_cols; ca.n_w_units = h->sp.n_r / 32; ca.n_rows_pad = h->n_rows_pad;
+    ca.W = b.W; ca.Y = b.Y; ca.ld_yw = h->n_rows_pad; ca.B = B; ca.R = b.R; ca.ld_r = h->sp.n_cols;
+    ca.kt_per_split = (int)((n_ktiles + ks_best - 1) / ks_best);
+    const int nz = (int)((n_ktiles + ca.kt_per_split - 1) / ca.kt_per_split);
+    ca.split_stride_r = round_up(B, kSigMaxSamples) * (long)h->sp.n_cols;
+    dim3 grid((unsigned)((n_units + sh.uc - 1) / sh.uc), (unsigned)((B + 32 * sh.wc - 1) / (32 * sh.wc)), (unsigned)nz);
+    sh.kernel<<<grid, 512, colsum_smem_bytes(sh.bk, sh.stages, sh.uc, sh.wc), st>>>(ca);
+    if (out_args) *out_args = ca;
+    return nz;
+}
+
 // WoodburyKernel{EcorrKernel}: subtract the per-group Sherman-Morrison terms from slab 0 of Sigma / U (K2b + K2c).
 void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st) {
     Buffers& b = d.buf;
@@ -240,6 +451,7 @@ void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t
     EcorrSyrkArgs sa;
     sa.V = b.V; sa.g_pad = h->eg_pad; sa.ldv = h->ldv; sa.rank = h->p; sa.n_rect = h->n_rect; sa.B = B;
     sa.Sig = b.Sig; sa.ld_sig = h->ld_sig; sa.U = b.U; sa.ld_u = h->pp;
+    if (h->sp.active) { sa.U = b.R + h->sp.n_r; sa.ld_u = h->sp.n_cols; }   // u lives behind the column sums
     const long warps = B * h->n_rect;
     ecorr_syrk_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(sa);
     h->launches += 2;
@@ -277,6 +489,8 @@ int set_smem_attrs(int dev) {
         CU(cudaFuncSetAttribute(sh.kernel4, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
         CU(cudaFuncSetAttribute(sh.kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     }
+    for (const ColsumShape& sh : kColsumShapes)
+        CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(chol_finish_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
     CU(cudaFuncSetAttribute(chol_finish_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
@@ -338,14 +552,32 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         if (timing) { cudaEventRecord(d.ev[3], st); cudaEventRecord(d.ev[4], st); }
     } else {
         SigmaArgs sa;
-        const int ksplit = launch_sigma(h, d, B, st, &sa);
-        if (h->n_eg > 0) launch_ecorr_correction(h, d, B, st);
+        ColsumArgs cs;
+        int ksplit;
+        if (h->sp.active) {
+            ksplit = launch_colsum(h, d, B, st, &cs);
+            if (h->n_eg > 0) {   // the ECORR correction is accumulated into a zeroed packed triangle that K4 adds
+                cudaMemsetAsync(b.Sig, 0, (size_t)B * h->ld_sig * sizeof(double), st);
+                launch_ecorr_correction(h, d, B, st);
+            }
+        } else {
+            ksplit = launch_sigma(h, d, B, st, &sa);
+            if (h->n_eg > 0) launch_ecorr_correction(h, d, B, st);
+        }
         if (timing) cudaEventRecord(d.ev[3], st);
         CholArgs ch;
         ch.Sig = b.Sig; ch.ld_sig = h->ld_sig; ch.ld_u = h->pp; ch.Sq = b.Sq; ch.U = b.U; ch.Pext = b.Pext; ch.row = pg.row; ch.p = h->p; ch.pp = h->pp; ch.n_gp = h->n_gp;
         ch.gp = d.gp; ch.gp_data = d.gp_data; ch.partial = b.partial; ch.n_tiles = n_rows_partial; ch.B = B;
         ch.lnprior = d_lnprior; ch.with_prior = with_prior; ch.out = d_out; ch.use_smem = h->chol_smem ? 1 : 0;
-        ch.ksplit = ksplit; ch.split_stride_sig = sa.split_stride_sig; ch.split_stride_u = sa.split_stride_u;
+        ch.ksplit = ksplit;
+        ch.table = nullptr; ch.R = nullptr; ch.ld_r = 0; ch.split_stride_r = 0; ch.n_r = 0; ch.u_off = 0; ch.add_sig = 0;
+        ch.split_stride_sig = ch.split_stride_u = 0;
+        if (h->sp.active) {
+            ch.table = d.table; ch.R = b.R; ch.ld_r = cs.ld_r; ch.split_stride_r = cs.split_stride_r;
+            ch.n_r = h->sp.n_r; ch.u_off = h->sp.n_r; ch.add_sig = h->n_eg > 0 ? 1 : 0;
+        } else {
+            ch.split_stride_sig = sa.split_stride_sig; ch.split_stride_u = sa.split_stride_u;
+        }
         ch.ahat = d_ahat; ch.cf = d_cf;
         int chol_threads = 128;     // measured best across ranks 60..300 (tests/gpu_chol_probe.py)
         if (const char* e = getenv("VELA_B200_CHOL_THREADS")) chol_threads = std::max(32, std::min(kCholThreads, atoi(e) / 32 * 32));
@@ -390,6 +622,10 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
         if (upload(&d.M, Mp.data(), Mp.size())) return VELA_ERR_CUDA;
         if (upload(&d.gp, gps.data(), gps.size())) return VELA_ERR_CUDA;
         if (upload(&d.gp_data, gp_data.data(), gp_data.size())) return VELA_ERR_CUDA;
+        if (h->sp.active) {
+            if (upload(&d.T, h->sp.T.data(), h->sp.T.size())) return VELA_ERR_CUDA;
+            if (upload(&d.table, h->sp.table.data(), h->sp.table.size())) return VELA_ERR_CUDA;
+        }
     }
     if (set_smem_attrs(d.dev)) return VELA_ERR_CUDA;
     return 0;
@@ -402,6 +638,7 @@ void destroy_device(DeviceModel& d) {
     if (d.buf.h_params) cudaFreeHost(d.buf.h_params);
     if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
     if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
+    cudaFree(d.T); cudaFree(d.table);
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
     cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active); cudaFree(d.priors);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -598,6 +835,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         h->n_gp = desc->n_gp;
         h->n_pairs = (long)h->p * (h->p + 1) / 2;
         h->ld_sig = round_up(h->n_pairs, 8);
+        analyse_basis(desc, h->n_rows, h->n_rows_pad, h->p, h->sp);
         // pick the first launch shape whose ring fits (two CTAs per SM need <= 110 KB each); the environment
         // variable VELA_B200_SIGMA_SHAPE=<index into kSigmaShapes> overrides for A/B measurements
         const int n_shapes = (int)(sizeof(kSigmaShapes) / sizeof(kSigmaShapes[0]));
@@ -633,9 +871,10 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
             gps.push_back(gd);
         }
         const int cnb = h->p <= kCholSmallRank ? 8 : 16;
-        size_t need = chol_smem_doubles(h->p, h->pp, cnb, true) * sizeof(double);
+        const int n_r = h->sp.active ? h->sp.n_r : 0;
+        size_t need = chol_smem_doubles(h->p, h->pp, cnb, true, n_r) * sizeof(double);
         h->chol_smem = need <= 200 * 1024;
-        h->chol_smem_bytes = h->chol_smem ? need : chol_smem_doubles(h->p, h->pp, cnb, false) * sizeof(double);
+        h->chol_smem_bytes = h->chol_smem ? need : chol_smem_doubles(h->p, h->pp, cnb, false, n_r) * sizeof(double);
     }
 
     // SoA TOA table (+ TOA-only hoists) and the TZR block
@@ -670,6 +909,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         }
     }
     cudaSetDevice(prev);
+    std::vector<double>().swap(h->sp.T);   // the device copies are authoritative from here on
 
     // per-model chain kernel (vela_jit.cu); any failure leaves the generic kernel in charge
     {
@@ -697,7 +937,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
 
     // walkers per device per pass: bound the y/w/Sigma scratch to ~1/4 of the device memory
     if (h->kernel_kind != VELA_KERNEL_WHITE) {
-        size_t per = (size_t)2 * h->n_rows_pad * 8 + (size_t)h->ld_sig * 8 + (size_t)h->pp * 8 + (h->chol_smem ? 0 : (size_t)(h->p + 1) * (h->pp + 1) * 8) + (size_t)h->eg_pad * h->ldv * 8;
+        size_t per = (size_t)2 * h->n_rows_pad * 8 + (h->sp.active ? (size_t)h->sp.n_cols * 32 + (h->n_eg ? (size_t)h->ld_sig * 8 : 0) : (size_t)h->ld_sig * 8) + (size_t)h->pp * 8 + (h->chol_smem ? 0 : (size_t)(h->p + 1) * (h->pp + 1) * 8) + (size_t)h->eg_pad * h->ldv * 8;
         size_t free_b = 0, total_b = 0;
         cudaSetDevice(devices[0]);
         cudaMemGetInfo(&free_b, &total_b);
@@ -1026,17 +1266,41 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
     launch_chain(h, dim3((unsigned)h->n_tiles, 1), chain_smem, d.stream, ca);
-    SigmaArgs sa;
-    const int ksplit = launch_sigma(h, d, 1, d.stream, &sa);
-    if (h->n_eg > 0) launch_ecorr_correction(h, d, 1, d.stream);
+    std::vector<double> S((size_t)h->ld_sig, 0.0), U(h->pp, 0.0);
     h->launches += 3;
-    std::vector<double> S((size_t)h->ld_sig, 0.0), U(h->pp, 0.0), tS((size_t)h->ld_sig), tU(h->pp);
-    for (int z = 0; z < ksplit; ++z) {   // sum the split-K slabs in slice order, as K4 does
-        cudaMemcpyAsync(tS.data(), b.Sig + (size_t)z * sa.split_stride_sig, sizeof(double) * tS.size(), cudaMemcpyDeviceToHost, d.stream);
-        cudaMemcpyAsync(tU.data(), b.U + (size_t)z * sa.split_stride_u, sizeof(double) * tU.size(), cudaMemcpyDeviceToHost, d.stream);
-        cudaStreamSynchronize(d.stream);
-        for (size_t i = 0; i < S.size(); ++i) S[i] = z == 0 ? tS[i] : S[i] + tS[i];
-        for (size_t i = 0; i < U.size(); ++i) U[i] = z == 0 ? tU[i] : U[i] + tU[i];
+    if (h->sp.active) {
+        ColsumArgs cs;
+        const int ksplit = launch_colsum(h, d, 1, d.stream, &cs);
+        if (h->n_eg > 0) {
+            cudaMemsetAsync(b.Sig, 0, (size_t)h->ld_sig * sizeof(double), d.stream);
+            launch_ecorr_correction(h, d, 1, d.stream);
+            cudaMemcpyAsync(S.data(), b.Sig, sizeof(double) * S.size(), cudaMemcpyDeviceToHost, d.stream);
+        }
+        std::vector<double> R(h->sp.n_cols, 0.0), tR(h->sp.n_cols);
+        for (int z = 0; z < ksplit; ++z) {   // sum the split-K slabs in slice order, as K4 does
+            cudaMemcpyAsync(tR.data(), b.R + (size_t)z * cs.split_stride_r, sizeof(double) * tR.size(), cudaMemcpyDeviceToHost, d.stream);
+            cudaStreamSynchronize(d.stream);
+            for (size_t i = 0; i < R.size(); ++i) R[i] = z == 0 ? tR[i] : R[i] + tR[i];
+        }
+        for (long t = 0; t < h->n_pairs; ++t) {
+            const PairTerm& pt = h->sp.table[t];
+            double v = pt.c1 * R[pt.i1];
+            if (pt.c2 != 0.0) v += pt.c2 * R[pt.i2];
+            S[t] = v + S[t];
+        }
+        for (int i = 0; i < h->p; ++i) U[i] = R[h->sp.n_r + i];
+    } else {
+        SigmaArgs sa;
+        const int ksplit = launch_sigma(h, d, 1, d.stream, &sa);
+        if (h->n_eg > 0) launch_ecorr_correction(h, d, 1, d.stream);
+        std::vector<double> tS((size_t)h->ld_sig), tU(h->pp);
+        for (int z = 0; z < ksplit; ++z) {   // sum the split-K slabs in slice order, as K4 does
+            cudaMemcpyAsync(tS.data(), b.Sig + (size_t)z * sa.split_stride_sig, sizeof(double) * tS.size(), cudaMemcpyDeviceToHost, d.stream);
+            cudaMemcpyAsync(tU.data(), b.U + (size_t)z * sa.split_stride_u, sizeof(double) * tU.size(), cudaMemcpyDeviceToHost, d.stream);
+            cudaStreamSynchronize(d.stream);
+            for (size_t i = 0; i < S.size(); ++i) S[i] = z == 0 ? tS[i] : S[i] + tS[i];
+            for (size_t i = 0; i < U.size(); ++i) U[i] = z == 0 ? tU[i] : U[i] + tU[i];
+        }
     }
     cudaError_t e = cudaGetLastError();
     cudaError_t e2 = cudaStreamSynchronize(d.stream);
@@ -1105,8 +1369,37 @@ VELA_API int vela_b200_chain_specialized(VelaHandle h, int on) {
     return h->use_spec ? 1 : 0;
 }
 
+VELA_API int vela_b200_sigma_structured(VelaHandle h) { return h ? (h->sp.active ? 1 : 0) : VELA_ERR_INVALID_ARG; }
+
 // Compiler log / reason the specialised kernel is absent (empty when it compiled cleanly).
 VELA_API const char* vela_b200_jit_log(VelaHandle h) { return h ? h->jit_log.c_str() : ""; }
+
+// test / tooling hook (no device needed): run the basis analysis of the structured Sigma path on the host and, when
+// `w` is given, evaluate M^T diag(w) M through the column-sum table (packed lower triangle, p(p+1)/2 doubles).
+// Returns the number of table columns (0 = the basis stays on the dense path); info = {n_r, n_cols, n_groups}.
+VELA_API int64_t vela_b200_debug_structured_sigma(const VelaModelDesc* desc, const double* w, double* sigma_packed, int32_t* info) {
+    if (int rc = validate(desc)) return rc;
+    if (desc->kernel_kind != VELA_KERNEL_WOODBURY_WHITE && desc->kernel_kind != VELA_KERNEL_WOODBURY_ECORR) return 0;
+    const long n_rows = desc->wideband ? 2 * desc->n_toas : desc->n_toas, n_rows_pad = round_up(n_rows, 64);
+    const int p = (int)desc->basis_cols;
+    StructPlan sp;
+    if (!analyse_basis(desc, n_rows, n_rows_pad, p, sp)) return 0;
+    if (info) { info[0] = sp.n_r; info[1] = sp.n_cols; info[2] = sp.n_groups; }
+    if (w && sigma_packed) {
+        std::vector<double> R(sp.n_r, 0.0);
+        for (int c = 0; c < sp.n_r; ++c) {
+            const double* t = sp.T.data() + (size_t)c * n_rows_pad;
+            double acc = 0.0;
+            for (long j = 0; j < n_rows; ++j) acc += t[j] * w[j];
+            R[c] = acc;
+        }
+        for (size_t t = 0; t < sp.table.size(); ++t) {
+            const PairTerm& pt = sp.table[t];
+            sigma_packed[t] = pt.c1 * R[pt.i1] + (pt.c2 != 0.0 ? pt.c2 * R[pt.i2] : 0.0);
+        }
+    }
+    return sp.n_r;
+}
 
 // test / tooling hook: compile the translation unit below with NVRTC (no device needed); returns the cubin size
 VELA_API int64_t vela_b200_debug_spec_compile(const VelaModelDesc* desc) {

@@ -520,6 +520,125 @@ VELA_SIGMA_INST(16, 2, 3, 4, 16)
 VELA_SIGMA_INST(8, 2, 3, 4, 16)
 
 // ------------------------------------------------------------------------------------------
+// K3s  column sums for the structured Sigma path
+// ------------------------------------------------------------------------------------------
+// When the basis columns are harmonics of one phase per row (Fourier GPs: M[j, sin_k] = s_j sin(k x_j), ...), every
+// product M[j,p] M[j,q] is half the sum / difference of two entries of a small trigonometric table
+// (sin a sin b = (cos(a-b) - cos(a+b)) / 2, ...), so Sigma^-1's p(p+1)/2 contractions over the TOAs collapse to
+// the 2 (K_a + K_c) + 1 sums  C(m) = sum_j w_j s_j cos(m x_j),  S(m) = sum_j w_j s_j sin(m x_j)  per pair of
+// column groups; products with non-harmonic columns are stored as explicit columns.  The host builds that table
+// T at create() (vela_api.cu: analyse_basis); this kernel is the remaining GEMM  R = T^T w  (and u = M^T (w y),
+// whose columns are appended to T), on the same DMMA tiling and mbarrier ring as the dense kernel: a warp owns
+// 32 columns x 32 walkers, a CTA is UC column units x WC walker tiles (16 warps) and stages only its own
+// 32 UC columns of T.
+template <int BK, int STAGES, int UC, int WC>
+__global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
+    constexpr int WARPS = UC * WC, kThreads = WARPS * 32, MT = 4, NT = 4;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
+    constexpr int PITCH = BK + 4;
+    constexpr int NCOL = UC * 32, NS = WC * 32;
+    constexpr int AHEAD = STAGES > 2 ? STAGES - 2 : 1;
+    constexpr int stage_rows = NCOL + 2 * NS;
+    constexpr size_t stage_doubles = (size_t)stage_rows * PITCH;
+    constexpr int kChunks = BK / 2;
+    constexpr int total_chunks = stage_rows * kChunks;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int uc = warp % UC, wc = warp / UC;
+    const long b0 = (long)blockIdx.y * NS;
+    const int c0 = blockIdx.x * NCOL;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kThreads); mbar_init(&empty_bar[s], WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int kt0 = blockIdx.z * a.kt_per_split;
+    const int n_ktiles = min(a.kt_per_split, (int)(a.n_rows_pad / BK) - kt0);
+    auto issue = [&](int t) {
+        const int s = t % STAGES;
+        double* base = smem + (size_t)s * stage_doubles;
+        const long j0 = (long)(kt0 + t) * BK;
+        for (int c = tid; c < total_chunks; c += kThreads) {
+            int r = c / kChunks, ch = c - r * kChunks;
+            const double* src;
+            if (r < NCOL) src = a.T + (size_t)min(c0 + r, a.n_cols - 1) * a.ldT + j0 + ch * 2;
+            else if (r < NCOL + NS) src = a.W + (size_t)min(b0 + (r - NCOL), a.B - 1) * a.ld_yw + j0 + ch * 2;
+            else src = a.Y + (size_t)min(b0 + (r - NCOL - NS), a.B - 1) * a.ld_yw + j0 + ch * 2;
+            cp_async16(base + (size_t)r * PITCH + ch * 2, src);
+        }
+        cp_async_mbar_arrive(&full_bar[s]);
+    };
+
+    const int u = blockIdx.x * UC + uc;
+    const bool have_unit = u * 32 < a.n_cols;
+    const bool use_y = u >= a.n_w_units;
+
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
+
+    for (int t = 0; t < AHEAD && t < n_ktiles; ++t) issue(t);
+
+    for (int kt = 0; kt < n_ktiles; ++kt) {
+        const int nk = kt + AHEAD;
+        if (nk < n_ktiles) {
+            if (nk >= STAGES) mbar_wait(&empty_bar[nk % STAGES], ((nk / STAGES) - 1) & 1);
+            issue(nk);
+        }
+        const int s = kt % STAGES;
+        mbar_wait(&full_bar[s], (kt / STAGES) & 1);
+        if (have_unit) {
+            const double* sT = smem + (size_t)s * stage_doubles + (size_t)(uc * 32) * PITCH;
+            const double* sW = smem + (size_t)s * stage_doubles + (size_t)(NCOL + wc * 32) * PITCH;
+            const double* sY = sW + (size_t)NS * PITCH;
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                const int k = kk * 4 + tig;
+                double bw[NT], af[MT];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) bw[n] = sW[(n * 8 + gid) * PITCH + k];
+                if (use_y) {
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) bw[n] *= sY[(n * 8 + gid) * PITCH + k];
+                }
+#pragma unroll
+                for (int i = 0; i < MT; ++i) af[i] = sT[(i * 8 + gid) * PITCH + k];
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) dmma8x8x4(acc[i][n][0], acc[i][n][1], af[i], bw[n]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+    if (!have_unit) return;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int col = u * 32 + i * 8 + gid;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                long b = b0 + wc * 32 + n * 8 + 2 * tig + r;
+                if (b < a.B) a.R[(size_t)blockIdx.z * a.split_stride_r + (size_t)b * a.ld_r + col] = acc[i][n][r];
+            }
+    }
+}
+
+template __global__ void colsum_kernel<16, 2, 16, 1>(ColsumArgs);
+template __global__ void colsum_kernel<16, 3, 8, 2>(ColsumArgs);
+template __global__ void colsum_kernel<16, 3, 4, 4>(ColsumArgs);
+template __global__ void colsum_kernel<16, 2, 2, 8>(ColsumArgs);
+
+// ------------------------------------------------------------------------------------------
 // K4  + Phi^-1, Cholesky, log-det, solve, ln L
 // ------------------------------------------------------------------------------------------
 // calc_noise_weights_inv (gls_likelihood.jl:3-7, gp_noise.jl:12-16,64-78, marginalized_timing_model.jl:24)
@@ -568,22 +687,44 @@ __global__ void __launch_bounds__(kCholThreads, NB <= 8 ? 2 : 1) chol_finish_ker
         lda = pp + 1;                             // room for entry (p, p) when p == pp
         A = a.Sq + (size_t)b * (p + 1) * (pp + 1);
     }
-    // ---- unpack the packed lower triangle t = r(r+1)/2 + c, summing the split-K slabs in slice order
+    // ---- Sigma: unpack the packed lower triangle t = r(r+1)/2 + c (dense path) or assemble it from the column sums
+    //      through the pair table (structured path); split-K slabs are summed in slice order
     {
         const double* gA = a.Sig + (size_t)b * a.ld_sig;
         const long n_pairs = (long)p * (p + 1) / 2;
+        double* sR = nullptr;
+        if (a.table) {
+            sR = panel + (size_t)(p + 1) * PP + (a.use_smem ? (size_t)(p + 1) * lda : 0);   // last shared slot
+            const double* gR = a.R + (size_t)b * a.ld_r;
+            for (int i = tid; i < a.n_r; i += nt) {
+                double v = gR[i];
+                for (int zz = 1; zz < a.ksplit; ++zz) v += gR[(size_t)zz * a.split_stride_r + i];
+                sR[i] = v;
+            }
+            __syncthreads();
+        }
         int r = 0, c = tid;
         while (c > r) { c -= r + 1; ++r; }
         for (long t = tid; t < n_pairs; t += nt) {
-            double v = gA[t];
-            for (int zz = 1; zz < a.ksplit; ++zz) v += gA[(size_t)zz * a.split_stride_sig + t];
+            double v;
+            if (a.table) {
+                const PairTerm pt = a.table[t];
+                v = pt.c1 * sR[pt.i1];
+                if (pt.c2 != 0.0) v += pt.c2 * sR[pt.i2];
+                if (a.add_sig) v += gA[t];
+            } else {
+                v = gA[t];
+                for (int zz = 1; zz < a.ksplit; ++zz) v += gA[(size_t)zz * a.split_stride_sig + t];
+            }
             A[(size_t)r * lda + c] = v;
             c += nt;
             while (c > r) { c -= r + 1; ++r; }
         }
+        const double* gU = a.table ? a.R + a.u_off : a.U;
+        const long ldu = a.table ? a.ld_r : a.ld_u, su = a.table ? a.split_stride_r : a.split_stride_u;
         for (int i = tid; i < p; i += nt) {
-            double v = a.U[(size_t)b * a.ld_u + i];
-            for (int zz = 1; zz < a.ksplit; ++zz) v += a.U[(size_t)zz * a.split_stride_u + (size_t)b * a.ld_u + i];
+            double v = gU[(size_t)b * ldu + i];
+            for (int zz = 1; zz < a.ksplit; ++zz) v += gU[(size_t)zz * su + (size_t)b * ldu + i];
             A[(size_t)p * lda + i] = v;
         }
     }

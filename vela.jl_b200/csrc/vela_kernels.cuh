@@ -37,6 +37,29 @@ struct SigmaArgs {
     long split_stride_u;
 };
 
+// K3s: column sums  R[b, c] = sum_j T[j, c] * (c < n_w_cols ? w[b, j] : w[b, j] y[b, j])  (structured Sigma path)
+struct ColsumArgs {
+    const double* T;           // column-major [n_rows_pad x n_cols], leading dimension ldT; n_cols multiple of 32
+    long ldT;
+    int n_cols;
+    int n_w_units;             // 32-column units that use w; the remaining units use w.y
+    long n_rows_pad;
+    const double* W;
+    const double* Y;
+    long ld_yw;
+    long B;
+    double* R;                 // [B][ld_r]
+    long ld_r;
+    int kt_per_split;
+    long split_stride_r;       // doubles between the slabs of consecutive split-K slices
+};
+
+// Sigma[p][q] = c1 R[i1] + c2 R[i2]  (c2 == 0: single term) for the packed pair t = p(p+1)/2 + q
+struct PairTerm {
+    int i1, i2;
+    double c1, c2;
+};
+
 struct EcorrArgs {
     const double* Pext;
     int row;
@@ -111,6 +134,14 @@ struct CholArgs {
     int with_prior;
     double* out;
     int use_smem;
+    // structured path: Sigma is assembled from the column sums R through the pair table (Sig then only carries the
+    // ECORR correction, or is unused)
+    const PairTerm* table;     // null = dense path (Sig holds the packed triangle)
+    const double* R;           // [B][ld_r]: n_r column sums, then u at column u_off
+    long ld_r;
+    long split_stride_r;
+    int n_r, u_off;
+    int add_sig;               // add Sig[t] (ECORR correction) to the assembled entry
     double* ahat;              // optional [B][p]: conditional mean of the marginalised amplitudes, Sigma u
     double* cf;                // optional [B][p][p] row-major upper Cholesky factor of Sigma^-1 (L^T)
 };
@@ -133,14 +164,21 @@ __global__ void sigma_contract_kernel(SigmaArgs a);
 template <int NB>
 __global__ void chol_finish_kernel(CholArgs a);
 constexpr int kCholSmallRank = 96;   // block width 8 up to this rank, 16 above
-inline size_t chol_smem_doubles(int p, int pp, int nb, bool matrix_in_smem) {
-    return (size_t)2 * pp + (size_t)nb * (nb + 1) + nb + (size_t)(p + 1) * (nb + 1) + (matrix_in_smem ? (size_t)(p + 1) * (pp + 1) : 0);
+inline size_t chol_smem_doubles(int p, int pp, int nb, bool matrix_in_smem, int n_r) {
+    return (size_t)2 * pp + (size_t)nb * (nb + 1) + nb + (size_t)(p + 1) * (nb + 1) +
+           (matrix_in_smem ? (size_t)(p + 1) * (pp + 1) : 0) + (size_t)n_r;   // n_r: column sums of the structured path
 }
 __global__ void phiinv_kernel(CholArgs a, double* out);
 __global__ void sincos_cr_kernel(const double* x, int n, double* s, double* c);
 __global__ void dfma_peak_kernel(double* out, int iters);
 __global__ void dmma_peak_kernel(double* out, int iters);
 __global__ void dmma_mix_kernel(double* out, int iters, int nmul, int nlds);
+
+template <int BK, int STAGES, int UC, int WC>
+__global__ void colsum_kernel(ColsumArgs a);
+inline size_t colsum_smem_bytes(int bk, int stages, int uc, int wc) {
+    return (size_t)stages * (uc * 32 + 2 * wc * 32) * (bk + 4) * sizeof(double);
+}
 
 inline size_t sigma_smem_bytes(int rank, int bk, int stages, int nt) {
     return (size_t)stages * (rank + 2 * 8 * nt) * (bk + 4) * sizeof(double);

@@ -22,7 +22,8 @@ EXPORTS = [
     "vela_b200_set_stage_timing", "vela_b200_last_stage_ms", "vela_b200_fp64_peak_tflops",
     "vela_b200_debug_sincos", "vela_b200_set_priors", "vela_b200_lnprior_batch", "vela_b200_prior_transform_batch",
     "vela_b200_marginalized_mean_batch", "vela_b200_chain_specialized", "vela_b200_jit_log",
-    "vela_b200_debug_spec_source", "vela_b200_debug_spec_compile",
+    "vela_b200_debug_spec_source", "vela_b200_debug_spec_compile", "vela_b200_debug_structured_sigma",
+    "vela_b200_sigma_structured",
 ]
 
 
@@ -86,6 +87,9 @@ def lib():
     L.vela_b200_debug_spec_source.restype = i64
     L.vela_b200_debug_spec_compile.argtypes = [vp]
     L.vela_b200_debug_spec_compile.restype = i64
+    L.vela_b200_debug_structured_sigma.argtypes = [vp, dp, dp, C.POINTER(C.c_int32)]
+    L.vela_b200_debug_structured_sigma.restype = i64
+    L.vela_b200_sigma_structured.argtypes = [vp]
     L.vela_b200_debug_sincos.argtypes = [dp, C.c_int, dp, dp]
     L.vela_b200_fp64_peak_tflops.argtypes = [C.c_int, C.c_int]
     L.vela_b200_fp64_peak_tflops.restype = C.c_double
