@@ -10,8 +10,8 @@ the per-walker lnpost vector is all-gathered over NCCL).  Workload = BASELINE.js
 ("sim3_gp: PowerlawRedNoiseGP Woodbury likelihood, 10k TOAs, 30 Fourier harmonics, 8192 walkers"),
 the configuration the headline metric is quoted on; data are synthetic (vela.jl_b200/synth.py).
 
-Keys beyond the base contract: `roofline` (dominant kernel = the FP64 tensor-core Sigma contraction,
-against the DMMA peak measured in this run), `cpu_baseline` (the CPU oracle — a C/OpenMP restatement of
+Keys beyond the base contract: `roofline` (the kernel with the largest share of the step, against the FP64
+peak of its pipe measured in this run; every kernel of the step is listed under `roofline.kernels`), `cpu_baseline` (the CPU oracle — a C/OpenMP restatement of
 the reference algorithm, NOT Julia — on a bounded sample of the same workload), `e2e` (host buffers
 through the public `Pulsar.lnpost_vectorized` call, H2D/D2H inside the timed region), `clocks`,
 `gpu_launches`, `parity` (max relative lnlike difference vs the oracle on the CPU sample).
@@ -277,26 +277,58 @@ def main():
         dmma_peak = max(float(L.vela_b200_fp64_peak_tflops(local_rank, 1)), float(L.vela_b200_fp64_peak_tflops(local_rank, 108)))
         dfma_peak = float(L.vela_b200_fp64_peak_tflops(local_rank, 0))
         sigma_ms = float(stage_ms[2])
-        achieved = flops_sigma * B / (sigma_ms * 1e-3) / 1e12 if sigma_ms > 0 else None
+        chain_ms, chol_ms = float(stage_ms[1]), float(stage_ms[3])
+        structured = psr.sigma_structured()
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         yw_bytes = 2 * B * nrows * 8   # y, w written by the chain kernel and read by the contraction
+        # Per-kernel roofline entries.  "algorithmic" flops are SURVEY 8(d)'s per-evaluation counts x walkers per
+        # launch; the structured Sigma path executes FEWER flops than the reference algorithm's contraction (it is an
+        # algebraic identity on harmonic bases), so its entry is rated on the flops it executes and the
+        # reference-equivalent rate is given separately.
+        n_cols = None
+        if structured:
+            import ctypes as C
+            info = (C.c_int32 * 3)()
+            md0 = vb.ModelDescriptor(ds.model, ds.toas)
+            L.vela_b200_debug_structured_sigma(md0.byref(), None, None, info)
+            n_cols = int(info[1])
+        nrows_pad = (nrows + 63) // 64 * 64
+        sigma_exec = 2.0 * n_cols * nrows_pad if structured else float(flops_sigma)
+        tf = lambda fl, ms: (fl * B / (ms * 1e-3) / 1e12) if ms > 0 else None   # noqa: E731
+        kernels = [
+            {"kernel": "toa_chain_kernel (per-model NVRTC build)" if psr.chain_specialized() else "toa_chain_kernel (generic)",
+             "bound": "fp64", "ms": chain_ms, "algorithmic_flops_per_launch": 330.0 * ntoa * B,
+             "achieved": tf(330.0 * ntoa, chain_ms), "peak": dfma_peak, "unit": "TFLOP/s"},
+            {"kernel": "colsum_kernel (structured Sigma, FP64 DMMA m8n8k4)" if structured else "sigma_contract_kernel (FP64 DMMA m8n8k4)",
+             "bound": "tensor", "ms": sigma_ms, "algorithmic_flops_per_launch": sigma_exec * B,
+             "achieved": tf(sigma_exec, sigma_ms), "peak": dmma_peak, "unit": "TFLOP/s",
+             "reference_equivalent_tflops": tf(float(flops_sigma), sigma_ms)},
+            {"kernel": "chol_finish_kernel", "bound": "fp64", "ms": chol_ms,
+             "algorithmic_flops_per_launch": (p**3 / 3 + p * p + 10 * p) * B,
+             "achieved": tf(p**3 / 3 + p * p + 10 * p, chol_ms), "peak": dfma_peak, "unit": "TFLOP/s"},
+        ]
+        for k in kernels:
+            k["frac"] = (k["achieved"] / k["peak"]) if k["achieved"] and k["peak"] > 0 else None
+            k["share_of_step"] = k["ms"] / float(stage_ms[4]) if stage_ms[4] > 0 else None
+        dom = max(kernels, key=lambda k: k["ms"])
         roofline = {
-            "bound": "tensor", "kernel": "sigma_contract_kernel (FP64 DMMA m8n8k4)", "achieved": achieved,
-            "peak": dmma_peak, "unit": "TFLOP/s", "frac": (achieved / dmma_peak) if achieved and dmma_peak > 0 else None,
-            "traffic": None,
-            "peak_source": "measured in this run: register-resident mma.sync.m8n8k4.f64 loop "
-                           "(vela_b200_fp64_peak_tflops); MEASURED_PEAKS.json holds only HBM and bf16 peaks",
-            "fp64_fma_peak_tflops": dfma_peak,
-            "algorithmic_flops_per_launch": flops_sigma * B,
-            "kernel_ms": sigma_ms,
-            "stage_ms": {"prologue": float(stage_ms[0]), "chain": float(stage_ms[1]), "sigma_contract": sigma_ms,
-                         "chol_finish": float(stage_ms[3]), "all_kernels": float(stage_ms[4])},
+            "bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
+            "unit": "TFLOP/s", "frac": dom["frac"], "traffic": None,
+            "peak_source": "measured in this run: register-resident FP64 loops (vela_b200_fp64_peak_tflops: DFMA for "
+                           "'fp64' kernels, mma.sync.m8n8k4.f64 for 'tensor' kernels); MEASURED_PEAKS.json holds only "
+                           "HBM and bf16 peaks",
+            "fp64_fma_peak_tflops": dfma_peak, "fp64_dmma_peak_tflops": dmma_peak,
+            "algorithmic_flops_per_launch": dom["algorithmic_flops_per_launch"],
+            "kernel_ms": dom["ms"], "sigma_path": "structured (column sums)" if structured else "dense (pair contraction)",
+            "kernels": kernels,
+            "stage_ms": {"prologue": float(stage_ms[0]), "chain": chain_ms, "sigma_contract": sigma_ms,
+                         "chol_finish": chol_ms, "all_kernels": float(stage_ms[4])},
             "hbm": {"algorithmic_bytes_per_step": yw_bytes * 2,
-                    "achieved_gbs_chain_write": (yw_bytes / (stage_ms[1] * 1e-3) / 1e9) if stage_ms[1] > 0 else None,
+                    "achieved_gbs_chain_write": (yw_bytes / (chain_ms * 1e-3) / 1e9) if chain_ms > 0 else None,
                     "peak_gbs": peaks.get("hbm_gbs"), "note": "path is FP64-compute bound, not HBM bound (SURVEY 8d)"},
         }
         line = {
@@ -310,7 +342,8 @@ def main():
                     "d2h_bytes_per_step": int(B * 8 * world), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary(),
             "finite_fraction": finite_frac,
-            "flops_per_eval": flops_eval, "achieved_tflops_whole_step": flops_eval * B * world / (dev_ms / args.steps * 1e-3) / 1e12,
+            "flops_per_eval": flops_eval,
+            "reference_equivalent_tflops_whole_step": flops_eval * B * world / (dev_ms / args.steps * 1e-3) / 1e12,
         }
         if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))

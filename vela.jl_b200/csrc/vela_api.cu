@@ -396,11 +396,11 @@ const ColsumShape kColsumShapes[] = {
 int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, ColsumArgs* out_args = nullptr) {
     Buffers& b = d.buf;
     const int n_units = h->sp.n_cols / 32;
-    // column units per CTA: everything in one CTA column when there are many units (W, Y are then staged once per
-    // walker tile), otherwise the shape that pads the unit count least
-    int si = 0;
-    if (n_units < 12) {
-        long best = 1 << 30;
+    // column units per CTA: the shape that pads the unit count least; ties go to the three-stage rings (measured
+    // 20-25 % faster than the two-stage ones, tests/gpu_colsum_probe.py), wide CTAs for many units
+    int si = n_units <= 8 ? 2 : 1;
+    {
+        long best = round_up(n_units, kColsumShapes[si].uc);
         for (int i = 1; i < 4; ++i) {
             const long padded = round_up(n_units, kColsumShapes[i].uc);
             if (padded < best) { best = padded; si = i; }
@@ -690,7 +690,7 @@ void build_program(const VelaModelDesc* desc, ProgramDev& pg) {
 }
 
 // Translation unit of the per-model chain kernel: the program as a constant object + the shared kernel body.
-std::string spec_source(const ProgramDev& pg) {
+std::string spec_source(const ProgramDev& pg, int min_blocks = 2) {
     std::string src;
     char buf[256];
     src += "#define VELA_SPEC_CALLS";
@@ -711,8 +711,9 @@ std::string spec_source(const ProgramDev& pg) {
         src += buf;
     }
     src += "}};\n}  // namespace vela\n"
-           "extern \"C\" __global__ void __launch_bounds__(vela::kChainThreads, 2) vela_chain_spec(vela::ChainArgs a) {\n"
-           "    vela::chain_body(vela::kSpecProg, a);\n}\n";
+           "extern \"C\" __global__ void __launch_bounds__(vela::kChainThreads, ";
+    src += std::to_string(min_blocks);
+    src += ") vela_chain_spec(vela::ChainArgs a) {\n    vela::chain_body(vela::kSpecProg, a);\n}\n";
     return src;
 }
 
@@ -916,7 +917,12 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         const char* e = getenv("VELA_B200_JIT");
         if (!(e && atoi(e) == 0)) {
             cudaKernel_t k = nullptr;
-            if (jit_chain_kernel(spec_source(pg), &k, h->jit_log) == 0) {
+            // three resident blocks per SM (80 registers): 3-8 % faster than two on every model probed, the few
+            // spilled bytes included (tests/gpu_chain_probe.py)
+            int mb = 3;
+            if (const char* force = getenv("VELA_B200_JIT_MINBLOCKS")) mb = std::max(1, std::min(4, atoi(force)));
+            int rc_jit = jit_chain_kernel(spec_source(pg, mb), &k, h->jit_log);
+            if (rc_jit == 0) {
                 bool ok = true;
                 for (auto& d : h->devs) {
                     cudaSetDevice(d.dev);
@@ -1408,7 +1414,10 @@ VELA_API int64_t vela_b200_debug_spec_compile(const VelaModelDesc* desc) {
     build_program(desc, pg);
     std::vector<char> cubin;
     std::string log;
-    if (jit_compile_cubin(spec_source(pg), cubin, log)) return fail(VELA_ERR_UNSUPPORTED, "%s", log.c_str());
+    int mb = 3;
+    if (const char* f = getenv("VELA_B200_JIT_MINBLOCKS")) mb = std::max(1, std::min(4, atoi(f)));
+    if (jit_compile_cubin(spec_source(pg, mb), cubin, log)) return fail(VELA_ERR_UNSUPPORTED, "%s", log.c_str());
+    g_last_error = log;   // ptxas statistics of the successful build, readable through vela_b200_last_error()
     return (int64_t)cubin.size();
 }
 

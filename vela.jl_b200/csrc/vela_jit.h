@@ -14,4 +14,7 @@ int jit_compile_cubin(const std::string& src, std::vector<char>& cubin, std::str
 // Compile (cached per process by source text), load and return the `vela_chain_spec` kernel.
 int jit_chain_kernel(const std::string& src, cudaKernel_t* out, std::string& log);
 
+// True when the ptxas statistics in `log` (compiled with -v) report register spills.
+bool jit_log_spills(const std::string& log);
+
 }  // namespace vela
