@@ -311,13 +311,22 @@ def main():
              "algorithmic_flops_per_launch": (p**3 / 3 + p * p + 10 * p) * B,
              "achieved": tf(p**3 / 3 + p * p + 10 * p, chol_ms), "peak": dfma_peak, "unit": "TFLOP/s"},
         ]
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+        # very step (profiles/r1_ncu_full_config3_v3.txt); only valid for the default workload and kernel variants
+        ncu_traffic = {"toa_chain_kernel (per-model NVRTC build)": 0.003848e9 + 1.257515e9,
+                       "colsum_kernel (structured Sigma, FP64 DMMA m8n8k4)": 1.360821e9 + 0.042892e9,
+                       "sigma_contract_kernel (FP64 DMMA m8n8k4)": 1.532375e9 + 0.116714e9,
+                       "chol_finish_kernel": 0.057261e9 + 0.000297e9}
         for k in kernels:
+            k["traffic"] = ncu_traffic.get(k["kernel"]) if (ntoa, p, B) == (10000, 60, 8192) else None
             k["frac"] = (k["achieved"] / k["peak"]) if k["achieved"] and k["peak"] > 0 else None
             k["share_of_step"] = k["ms"] / float(stage_ms[4]) if stage_ms[4] > 0 else None
         dom = max(kernels, key=lambda k: k["ms"])
         roofline = {
             "bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
-            "unit": "TFLOP/s", "frac": dom["frac"], "traffic": None,
+            "unit": "TFLOP/s", "frac": dom["frac"], "traffic": dom["traffic"],
+            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                              "(profiles/r1_ncu_full_config3_v3.txt)",
             "peak_source": "measured in this run: register-resident FP64 loops (vela_b200_fp64_peak_tflops: DFMA for "
                            "'fp64' kernels, mma.sync.m8n8k4.f64 for 'tensor' kernels); MEASURED_PEAKS.json holds only "
                            "HBM and bf16 peaks",
