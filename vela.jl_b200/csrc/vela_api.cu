@@ -385,31 +385,41 @@ bool analyse_basis(const VelaModelDesc* desc, long n_rows, long n_rows_pad, int 
     return true;
 }
 
-// K3s launch shapes (BK, stages, column units, walker tiles per CTA)
+// K3s launch shapes (BK, stages, column units, walker tiles per CTA); the second table is for batches whose Y buffer
+// holds w.y (homogeneous CTA columns, one walker operand per stage)
 struct ColsumShape { int bk, stages, uc, wc; void (*kernel)(ColsumArgs); };
 const ColsumShape kColsumShapes[] = {
-    {16, 2, 16, 1, colsum_kernel<16, 2, 16, 1>}, {16, 3, 8, 2, colsum_kernel<16, 3, 8, 2>},
-    {16, 3, 4, 4, colsum_kernel<16, 3, 4, 4>}, {16, 2, 2, 8, colsum_kernel<16, 2, 2, 8>},
+    {16, 2, 16, 1, colsum_kernel<16, 2, 16, 1, false>}, {16, 3, 8, 2, colsum_kernel<16, 3, 8, 2, false>},
+    {16, 3, 4, 4, colsum_kernel<16, 3, 4, 4, false>}, {16, 2, 2, 8, colsum_kernel<16, 2, 2, 8, false>},
+};
+const ColsumShape kColsumSplitShapes[] = {
+    {8, 4, 16, 1, colsum_kernel<8, 4, 16, 1, true>}, {16, 4, 8, 2, colsum_kernel<16, 4, 8, 2, true>},
+    {16, 4, 4, 4, colsum_kernel<16, 4, 4, 4, true>}, {16, 4, 2, 8, colsum_kernel<16, 4, 2, 8, true>},
 };
 
-// Launches K3s for B walkers; returns the number of split-K slabs K4 has to sum.
-int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, ColsumArgs* out_args = nullptr) {
+// Launches K3s for B walkers; `wy`: the chain kernel stored w.y in Y (emit 3).  Returns the number of split-K slabs.
+int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool wy, ColsumArgs* out_args = nullptr) {
     Buffers& b = d.buf;
-    const int n_units = h->sp.n_cols / 32;
-    // column units per CTA: the shape that pads the unit count least; ties go to the three-stage rings (measured
-    // 20-25 % faster than the two-stage ones, tests/gpu_colsum_probe.py), wide CTAs for many units
+    const int n_units = h->sp.n_cols / 32, n_t = h->sp.n_r / 32, n_u = n_units - n_t;
+    const ColsumShape* shapes = wy ? kColsumSplitShapes : kColsumShapes;
+    // CTA columns for a shape: homogeneous columns pad the two kinds of units separately
+    auto cta_cols = [&](const ColsumShape& sh) -> long {
+        return wy ? (n_t + sh.uc - 1) / sh.uc + (n_u + sh.uc - 1) / sh.uc : (n_units + sh.uc - 1) / sh.uc;
+    };
+    // the shape that pads the unit count least; ties go to the deeper rings and, for many units, to wide CTAs
+    // (tests/gpu_colsum_probe.py)
     int si = n_units <= 8 ? 2 : 1;
     {
-        long best = round_up(n_units, kColsumShapes[si].uc);
+        long best = cta_cols(shapes[si]) * shapes[si].uc;
         for (int i = 1; i < 4; ++i) {
-            const long padded = round_up(n_units, kColsumShapes[i].uc);
+            const long padded = cta_cols(shapes[i]) * shapes[i].uc;
             if (padded < best) { best = padded; si = i; }
         }
     }
     if (const char* e = getenv("VELA_B200_COLSUM_SHAPE")) si = std::max(0, std::min(3, atoi(e)));
-    const ColsumShape& sh = kColsumShapes[si];
+    const ColsumShape& sh = shapes[si];
     const long n_ktiles = h->n_rows_pad / sh.bk;
-    const long ctas_xy = ((n_units + sh.uc - 1) / sh.uc) * ((B + 32 * sh.wc - 1) / (32 * sh.wc));
+    const long ctas_xy = cta_cols(sh) * ((B + 32 * sh.wc - 1) / (32 * sh.wc));
     const long max_split = std::max<long>(1, std::min<long>({64, std::max<long>(1, n_ktiles / 8),
                                                               b.r_rows / std::max<long>(round_up(B, kSigMaxSamples), 1)}));
     long ks_best = 1;
@@ -423,13 +433,13 @@ int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, Colsum
     }
     if (const char* e = getenv("VELA_B200_SIGMA_KSPLIT")) ks_best = std::max<long>(1, std::min<long>(atoi(e), max_split));
     ColsumArgs ca;
-    ca.T = d.T; ca.ldT = h->n_rows_pad; ca.n_cols = h->sp.n_cols; ca.n_w_units = h->sp.n_r / 32; ca.n_rows_pad = h->n_rows_pad;
+    ca.T = d.T; ca.ldT = h->n_rows_pad; ca.n_cols = h->sp.n_cols; ca.n_w_units = n_t; ca.n_rows_pad = h->n_rows_pad;
     ca.W = b.W; ca.Y = b.Y; ca.ld_yw = h->n_rows_pad; ca.B = B; ca.R = b.R; ca.ld_r = h->sp.n_cols;
     ca.kt_per_split = (int)((n_ktiles + ks_best - 1) / ks_best);
     const int nz = (int)((n_ktiles + ca.kt_per_split - 1) / ca.kt_per_split);
     ca.split_stride_r = round_up(B, kSigMaxSamples) * (long)h->sp.n_cols;
-    dim3 grid((unsigned)((n_units + sh.uc - 1) / sh.uc), (unsigned)((B + 32 * sh.wc - 1) / (32 * sh.wc)), (unsigned)nz);
-    sh.kernel<<<grid, 512, colsum_smem_bytes(sh.bk, sh.stages, sh.uc, sh.wc), st>>>(ca);
+    dim3 grid((unsigned)cta_cols(sh), (unsigned)((B + 32 * sh.wc - 1) / (32 * sh.wc)), (unsigned)nz);
+    sh.kernel<<<grid, 512, colsum_smem_bytes(sh.bk, sh.stages, sh.uc, sh.wc, wy), st>>>(ca);
     if (out_args) *out_args = ca;
     return nz;
 }
@@ -491,6 +501,8 @@ int set_smem_attrs(int dev) {
     }
     for (const ColsumShape& sh : kColsumShapes)
         CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    for (const ColsumShape& sh : kColsumSplitShapes)
+        CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(chol_finish_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
     CU(cudaFuncSetAttribute(chol_finish_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
@@ -529,7 +541,8 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
     ChainArgs ca;
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = B; ca.group = h->chain_group;
-    ca.emit = (woodbury || ecorr) ? 1 : 0; ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
+    const bool wy = woodbury && h->sp.active && !ecorr;   // Y carries w.y for the structured contraction
+    ca.emit = wy ? 3 : ((woodbury || ecorr) ? 1 : 0); ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     const int warps = h->chain_threads / 32;
     size_t chain_smem = ((size_t)h->chain_group * pg.row + 2 * h->chain_group + (size_t)warps * h->chain_group * 2) * sizeof(double);
     dim3 cgrid((unsigned)h->n_tiles, (unsigned)((B + h->chain_group - 1) / h->chain_group));
@@ -555,7 +568,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         ColsumArgs cs;
         int ksplit;
         if (h->sp.active) {
-            ksplit = launch_colsum(h, d, B, st, &cs);
+            ksplit = launch_colsum(h, d, B, st, wy, &cs);
             if (h->n_eg > 0) {   // the ECORR correction is accumulated into a zeroed packed triangle that K4 adds
                 cudaMemsetAsync(b.Sig, 0, (size_t)B * h->ld_sig * sizeof(double), st);
                 launch_ecorr_correction(h, d, B, st);
@@ -1268,7 +1281,8 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
                                                     d.index_masks, d.bit_masks, h->n_toas, b.Pext, b.tzr);
     ChainArgs ca;
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
-    ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = 1;
+    const bool wy = h->sp.active && h->n_ecorr_groups == 0;
+    ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = wy ? 3 : 1;
     ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
     launch_chain(h, dim3((unsigned)h->n_tiles, 1), chain_smem, d.stream, ca);
@@ -1276,7 +1290,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     h->launches += 3;
     if (h->sp.active) {
         ColsumArgs cs;
-        const int ksplit = launch_colsum(h, d, 1, d.stream, &cs);
+        const int ksplit = launch_colsum(h, d, 1, d.stream, wy, &cs);
         if (h->n_eg > 0) {
             cudaMemsetAsync(b.Sig, 0, (size_t)h->ld_sig * sizeof(double), d.stream);
             launch_ecorr_correction(h, d, 1, d.stream);

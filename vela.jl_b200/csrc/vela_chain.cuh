@@ -19,7 +19,7 @@ struct ChainArgs {
     const uint8_t* bit_masks;
     long B;
     int group;                 // walkers per block
-    int emit;                  // 1: write y, w (Woodbury path); 2: write phase (hi, lo) and spin frequency
+    int emit;                  // 1: write y, w (Woodbury path); 2: write phase (hi, lo) and spin frequency; 3: write w.y, w
     double* Y;                 // [B_pad][ld_yw]
     double* W;
     double* F;                 // emit == 2 only
@@ -90,10 +90,10 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
             a.F[o] = f;
         } else if (a.emit && active) {
             const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
-            a.Y[o] = tres;
+            a.Y[o] = a.emit == 3 ? w * tres : tres;       // emit 3: the structured contraction wants w.y
             a.W[o] = w;
             if (e.wide) {
-                a.Y[o + a.n_toas] = dmres;
+                a.Y[o + a.n_toas] = a.emit == 3 ? wdm * dmres : dmres;
                 a.W[o + a.n_toas] = wdm;
             }
         }

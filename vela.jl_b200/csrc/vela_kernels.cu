@@ -531,7 +531,10 @@ VELA_SIGMA_INST(8, 2, 3, 4, 16)
 // whose columns are appended to T), on the same DMMA tiling and mbarrier ring as the dense kernel: a warp owns
 // 32 columns x 32 walkers, a CTA is UC column units x WC walker tiles (16 warps) and stages only its own
 // 32 UC columns of T.
-template <int BK, int STAGES, int UC, int WC>
+// SPLIT = true: the chain kernel stored w.y in the Y buffer (ChainArgs::emit == 3), and every CTA column is
+// homogeneous - either 32 UC table columns against W or 32 UC columns of M against w.y - so a stage holds one walker
+// operand instead of two and the two kinds of units pad separately.
+template <int BK, int STAGES, int UC, int WC, bool SPLIT>
 __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
     constexpr int WARPS = UC * WC, kThreads = WARPS * 32, MT = 4, NT = 4;
     extern __shared__ __align__(16) double smem[];
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
     constexpr int PITCH = BK + 4;
     constexpr int NCOL = UC * 32, NS = WC * 32;
     constexpr int AHEAD = STAGES > 2 ? STAGES - 2 : 1;
-    constexpr int stage_rows = NCOL + 2 * NS;
+    constexpr int stage_rows = NCOL + (SPLIT ? NS : 2 * NS);
     constexpr size_t stage_doubles = (size_t)stage_rows * PITCH;
     constexpr int kChunks = BK / 2;
     constexpr int total_chunks = stage_rows * kChunks;
@@ -547,7 +550,21 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
     const int gid = lane >> 2, tig = lane & 3;
     const int uc = warp % UC, wc = warp / UC;
     const long b0 = (long)blockIdx.y * NS;
-    const int c0 = blockIdx.x * NCOL;
+    const int n_units = a.n_cols / 32;
+    // first unit of this CTA column and whether its units multiply w or w.y
+    int u_first, u_end;
+    bool use_y;
+    if (SPLIT) {
+        const int n_t_ctas = (a.n_w_units + UC - 1) / UC;
+        use_y = (int)blockIdx.x >= n_t_ctas;
+        u_first = use_y ? a.n_w_units + ((int)blockIdx.x - n_t_ctas) * UC : (int)blockIdx.x * UC;
+        u_end = use_y ? n_units : a.n_w_units;
+    } else {
+        u_first = blockIdx.x * UC;
+        u_end = n_units;
+        use_y = false;
+    }
+    const int c0 = u_first * 32;
 
     if (tid == 0) {
 #pragma unroll
@@ -558,6 +575,7 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
 
     const int kt0 = blockIdx.z * a.kt_per_split;
     const int n_ktiles = min(a.kt_per_split, (int)(a.n_rows_pad / BK) - kt0);
+    const double* walker_src = (SPLIT && use_y) ? a.Y : a.W;
     auto issue = [&](int t) {
         const int s = t % STAGES;
         double* base = smem + (size_t)s * stage_doubles;
@@ -566,16 +584,16 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
             int r = c / kChunks, ch = c - r * kChunks;
             const double* src;
             if (r < NCOL) src = a.T + (size_t)min(c0 + r, a.n_cols - 1) * a.ldT + j0 + ch * 2;
-            else if (r < NCOL + NS) src = a.W + (size_t)min(b0 + (r - NCOL), a.B - 1) * a.ld_yw + j0 + ch * 2;
+            else if (r < NCOL + NS) src = walker_src + (size_t)min(b0 + (r - NCOL), a.B - 1) * a.ld_yw + j0 + ch * 2;
             else src = a.Y + (size_t)min(b0 + (r - NCOL - NS), a.B - 1) * a.ld_yw + j0 + ch * 2;
             cp_async16(base + (size_t)r * PITCH + ch * 2, src);
         }
         cp_async_mbar_arrive(&full_bar[s]);
     };
 
-    const int u = blockIdx.x * UC + uc;
-    const bool have_unit = u * 32 < a.n_cols;
-    const bool use_y = u >= a.n_w_units;
+    const int u = u_first + uc;
+    const bool have_unit = u < u_end;
+    const bool mul_y = !SPLIT && u >= a.n_w_units;
 
     double acc[MT][NT][2];
 #pragma unroll
@@ -603,7 +621,7 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
                 double bw[NT], af[MT];
 #pragma unroll
                 for (int n = 0; n < NT; ++n) bw[n] = sW[(n * 8 + gid) * PITCH + k];
-                if (use_y) {
+                if (mul_y) {
 #pragma unroll
                     for (int n = 0; n < NT; ++n) bw[n] *= sY[(n * 8 + gid) * PITCH + k];
                 }
@@ -633,10 +651,14 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
     }
 }
 
-template __global__ void colsum_kernel<16, 2, 16, 1>(ColsumArgs);
-template __global__ void colsum_kernel<16, 3, 8, 2>(ColsumArgs);
-template __global__ void colsum_kernel<16, 3, 4, 4>(ColsumArgs);
-template __global__ void colsum_kernel<16, 2, 2, 8>(ColsumArgs);
+template __global__ void colsum_kernel<16, 2, 16, 1, false>(ColsumArgs);
+template __global__ void colsum_kernel<16, 3, 8, 2, false>(ColsumArgs);
+template __global__ void colsum_kernel<16, 3, 4, 4, false>(ColsumArgs);
+template __global__ void colsum_kernel<16, 2, 2, 8, false>(ColsumArgs);
+template __global__ void colsum_kernel<8, 4, 16, 1, true>(ColsumArgs);
+template __global__ void colsum_kernel<16, 4, 8, 2, true>(ColsumArgs);
+template __global__ void colsum_kernel<16, 4, 4, 4, true>(ColsumArgs);
+template __global__ void colsum_kernel<16, 4, 2, 8, true>(ColsumArgs);
 
 // ------------------------------------------------------------------------------------------
 // K4  + Phi^-1, Cholesky, log-det, solve, ln L

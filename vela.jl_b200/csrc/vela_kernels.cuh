@@ -174,10 +174,10 @@ __global__ void dfma_peak_kernel(double* out, int iters);
 __global__ void dmma_peak_kernel(double* out, int iters);
 __global__ void dmma_mix_kernel(double* out, int iters, int nmul, int nlds);
 
-template <int BK, int STAGES, int UC, int WC>
+template <int BK, int STAGES, int UC, int WC, bool SPLIT>
 __global__ void colsum_kernel(ColsumArgs a);
-inline size_t colsum_smem_bytes(int bk, int stages, int uc, int wc) {
-    return (size_t)stages * (uc * 32 + 2 * wc * 32) * (bk + 4) * sizeof(double);
+inline size_t colsum_smem_bytes(int bk, int stages, int uc, int wc, bool split) {
+    return (size_t)stages * (uc * 32 + (split ? 1 : 2) * wc * 32) * (bk + 4) * sizeof(double);
 }
 
 inline size_t sigma_smem_bytes(int rank, int bk, int stages, int nt) {
