@@ -361,20 +361,35 @@ bool analyse_basis(const VelaModelDesc* desc, long n_rows, long n_rows_pad, int 
     sp.n_groups = ng;
     sp.T.assign((size_t)n_rows_pad * sp.n_cols, 0.0);
     auto Tc = [&](long c) { return sp.T.data() + (size_t)c * n_rows_pad; };
-    for (int a = 0; a < ng; ++a)
-        for (int c = a; c < ng; ++c) {
-            const Grp &Ga = groups[good[a]], &Gc = groups[good[c]];
-            const int K = Ga.kmax + Gc.kmax, bc = baseC[(size_t)a * ng + c], bs = baseS[(size_t)a * ng + c];
-            for (long j = 0; j < n_rows; ++j) {
-                const double ss = Ga.s[j] * Gc.s[j];
-                if (ss == 0.0) continue;
-                for (int m = 0; m <= K; ++m) {
-                    const double arg = (double)m * x[j];
-                    Tc(bc + m)[j] = ss * std::cos(arg);
-                    if (m >= 1) Tc(bs + m)[j] = ss * std::sin(arg);
+    {   // trigonometric columns: cos(m x_j), sin(m x_j) once per row block, reused by every group pair
+        int mmax = 0;
+        for (int a = 0; a < ng; ++a) mmax = std::max(mmax, 2 * groups[good[a]].kmax);
+        constexpr long JB = 128;
+        std::vector<double> cm((size_t)JB * (mmax + 1)), sm((size_t)JB * (mmax + 1));
+        for (long j0 = 0; j0 < n_rows; j0 += JB) {
+            const long nj = std::min<long>(JB, n_rows - j0);
+            for (long jj = 0; jj < nj; ++jj)
+                for (int m = 0; m <= mmax; ++m) {
+                    const double arg = (double)m * x[j0 + jj];
+                    cm[(size_t)m * JB + jj] = std::cos(arg);
+                    sm[(size_t)m * JB + jj] = std::sin(arg);
                 }
-            }
+            for (int a = 0; a < ng; ++a)
+                for (int c = a; c < ng; ++c) {
+                    const Grp &Ga = groups[good[a]], &Gc = groups[good[c]];
+                    const int K = Ga.kmax + Gc.kmax, bc = baseC[(size_t)a * ng + c], bs = baseS[(size_t)a * ng + c];
+                    for (int m = 0; m <= K; ++m) {
+                        double* tc = Tc(bc + m) + j0;
+                        double* ts = m >= 1 ? Tc(bs + m) + j0 : nullptr;
+                        for (long jj = 0; jj < nj; ++jj) {
+                            const double ss = Ga.s[j0 + jj] * Gc.s[j0 + jj];
+                            tc[jj] = ss * cm[(size_t)m * JB + jj];
+                            if (ts) ts[jj] = ss * sm[(size_t)m * JB + jj];
+                        }
+                    }
+                }
         }
+    }
     for (size_t i = 0; i < products.size(); ++i) {
         const double *a = Mc(products[i].first), *b = Mc(products[i].second);
         double* t = Tc(n_trig + (long)i);
