@@ -133,3 +133,29 @@ def test_whitened_residuals(datasets, oracle):
                                   psr4.time_residuals(ds4.truth) - real[:n])
     np.testing.assert_array_equal(psr4.whitened_dm_residuals(ds4.truth, np.random.default_rng(5)),
                                   psr4.dm_residuals(ds4.truth) - real[n:])
+
+
+@pytest.mark.parametrize("name,ntoa", [("config3_gp", 1200), ("config4_dd_wb", 700), ("config5_array", 900),
+                                       ("extra_ecorr_gp", None), ("extra_dmjump_bits_wb", None)])
+def test_structured_and_dense_sigma_paths_agree(name, ntoa, datasets, vb, oracle, monkeypatch):
+    """The column-sum (structured) contraction and the dense pair contraction are the same quantity: both run
+    here on the same walkers, and both are checked against the oracle."""
+    ds, psr, md = datasets(name, ntoa)
+    assert psr.sigma_structured()
+    monkeypatch.setenv("VELA_B200_STRUCTURED", "0")
+    dense = vb.Pulsar(ds.model, ds.toas)
+    monkeypatch.delenv("VELA_B200_STRUCTURED")
+    assert not dense.sigma_structured()
+    W = ds.walkers(150, seed=8)
+    a, b = psr.lnlike_vectorized(W), dense.lnlike_vectorized(W)
+    np.testing.assert_allclose(a, b, rtol=1e-11)
+    np.testing.assert_allclose(b, oracle.lnlike_batch(md, W), rtol=1e-9)
+    S1, u1 = psr.sigma_and_u(ds.truth)
+    S0, u0 = dense.sigma_and_u(ds.truth)
+    scale = np.sqrt(np.outer(np.diag(S0), np.diag(S0)))
+    assert np.max(np.abs(S1 - S0) / scale) < 1e-13
+    np.testing.assert_allclose(u1, u0, rtol=1e-10, atol=1e-10 * np.abs(u0).max())
+    # small and odd batch sizes go through the split-K planner of both paths
+    for B in (1, 3, 33):
+        np.testing.assert_allclose(psr.lnlike_vectorized(W[:B]), a[:B], rtol=1e-12)
+        np.testing.assert_allclose(dense.lnlike_vectorized(W[:B]), b[:B], rtol=1e-12)
