@@ -559,7 +559,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
     const bool wy = woodbury && h->sp.active && !ecorr;   // Y carries w.y for the structured contraction
     ca.emit = wy ? 3 : ((woodbury || ecorr) ? 1 : 0); ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     const int warps = h->chain_threads / 32;
-    size_t chain_smem = ((size_t)h->chain_group * pg.row + 2 * h->chain_group + (size_t)warps * h->chain_group * 2) * sizeof(double);
+    size_t chain_smem = ((size_t)h->chain_group * pg.row + 2 * h->chain_group + (size_t)warps * h->chain_group * 3) * sizeof(double);
     dim3 cgrid((unsigned)h->n_tiles, (unsigned)((B + h->chain_group - 1) / h->chain_group));
     launch_chain(h, cgrid, chain_smem, st, ca);
     h->launches += 2;
@@ -1135,7 +1135,7 @@ static int run_single(VelaHandle h, const double* params, int64_t n_free, int mo
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = mode;
     ca.Y = dY; ca.W = dW; ca.F = dF; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
-    size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
+    size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 3) * sizeof(double);
     launch_chain(h, dim3((unsigned)h->n_tiles, 1), chain_smem, d.stream, ca);
     h->launches += 2;
     const long n = mode == 1 ? h->n_rows : h->n_toas;
@@ -1299,7 +1299,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     const bool wy = h->sp.active && h->n_ecorr_groups == 0;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = wy ? 3 : 1;
     ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
-    size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 2) * sizeof(double);
+    size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 3) * sizeof(double);
     launch_chain(h, dim3((unsigned)h->n_tiles, 1), chain_smem, d.stream, ca);
     std::vector<double> S((size_t)h->ld_sig, 0.0), U(h->pp, 0.0);
     h->launches += 3;

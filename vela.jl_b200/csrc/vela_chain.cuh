@@ -32,7 +32,7 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
     const int row = prog.row;
     double* sP = smem;                                  // [group][row]
     double* sTzr = sP + (size_t)a.group * row;          // [group][2]
-    double* sRed = sTzr + 2 * a.group;                  // [warps][group][2]
+    double* sRed = sTzr + 2 * a.group;                  // [warps][group][3]: chi^2, mantissa product, exponent sum
 
     const long b0 = (long)blockIdx.y * a.group;
     const int nb = (int)min((long)a.group, a.B - b0);
@@ -59,30 +59,33 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
         double f = k.spin_frequency * (1 + k.doppler);
         double tres = dphase.hi / f;
         double err2 = (t.err2 + k.equad2) * k.efac * k.efac;  // scaled_toa_error_sqr toa.jl:122-123
-        double chi, lg, w = 0.0;
+        // log det N = sum_j log(err2_j) is accumulated as a PRODUCT of mantissas and a sum of binary exponents, so the
+        // logarithm is taken once per (tile, walker) in the block epilogue instead of once per (TOA, walker)
+        double chi, w = 0.0;
+        int lex;
+        double lman = frexp(err2, &lex);
         if (a.emit) {  // Woodbury: y^T N^-1 y and log det N from Ninvdiag, gls_likelihood.jl:81-99
             w = 1.0 / err2;
             chi = tres * tres * w;
-            lg = -log(w);
         } else {
             chi = tres * tres / err2;
-            lg = log(err2);
         }
         double dmres = 0.0, wdm = 0.0;
         if (e.wide) {  // wideband_residuals.jl:6-17, wideband_toa.jl:68-69
             dmres = t.dm - k.model_dm;
             double dmerr2 = (t.dmerr2 + k.dmequad2) * k.dmefac * k.dmefac;
+            int dex;
+            lman *= frexp(dmerr2, &dex);
+            lex += dex;
             if (a.emit) {
                 wdm = 1.0 / dmerr2;
                 chi += dmres * dmres * wdm;
-                lg += -log(wdm);
             } else {
                 chi += dmres * dmres / dmerr2;
-                lg += log(dmerr2);
             }
         }
         if (k.bad || k.spin_frequency == 0.0) chi = CUDART_NAN;
-        if (!active) { chi = 0.0; lg = 0.0; }
+        if (!active) { chi = 0.0; lman = 1.0; lex = 0; }
         if (a.emit == 2 && active) {  // phase mode: Double64 phase residual and doppler-shifted spin frequency
             const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
             a.Y[o] = dphase.hi;
@@ -100,19 +103,25 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             chi += __shfl_xor_sync(0xffffffffu, chi, off);
-            lg += __shfl_xor_sync(0xffffffffu, lg, off);
+            lman *= __shfl_xor_sync(0xffffffffu, lman, off);    // 32 mantissas in [1/4, 1): no underflow
+            lex += __shfl_xor_sync(0xffffffffu, lex, off);
         }
         if (lane == 0) {
-            sRed[((size_t)warp * a.group + s) * 2] = chi;
-            sRed[((size_t)warp * a.group + s) * 2 + 1] = lg;
+            double* r = sRed + ((size_t)warp * a.group + s) * 3;
+            r[0] = chi; r[1] = lman; r[2] = (double)lex;
         }
     }
     __syncthreads();
     const int nwarps = blockDim.x >> 5;
-    for (int i = tid; i < 2 * nb; i += blockDim.x) {
-        double acc = 0.0;
-        for (int w = 0; w < nwarps; ++w) acc += sRed[(size_t)w * a.group * 2 + i];
-        a.partial[((size_t)blockIdx.x * a.B + b0) * 2 + i] = acc;
+    for (int i = tid; i < nb; i += blockDim.x) {
+        double chi = 0.0, man = 1.0, ex = 0.0;
+        for (int w = 0; w < nwarps; ++w) {
+            const double* r = sRed + ((size_t)w * a.group + i) * 3;
+            chi += r[0]; man *= r[1]; ex += r[2];
+        }
+        double* out = a.partial + ((size_t)blockIdx.x * a.B + b0 + i) * 2;
+        out[0] = chi;
+        out[1] = log(man) + ex * 0.6931471805599453;   // ln 2
     }
 }
 
