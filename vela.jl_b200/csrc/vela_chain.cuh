@@ -55,7 +55,9 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
         const double* P = sP + (size_t)s * row;
         Corr k = run_chain(prog, P, t, e);
         // form_residual residuals.jl:8-12: Float64((phase - pulse_number) - tzrphase) / (f (1 + doppler))
-        dd dphase = dd_sub(dd_sub(k.phase, dd{t.pn_hi, t.pn_lo}), dd{sTzr[2 * s], sTzr[2 * s + 1]});
+        // (pulse numbers are integers below 2^53, so pn_lo is normally 0: dd - double is the same bits for 11 adds less)
+        dd dphase = t.pn_lo == 0.0 ? dd_add_d(k.phase, -t.pn_hi) : dd_sub(k.phase, dd{t.pn_hi, t.pn_lo});
+        dphase = dd_sub(dphase, dd{sTzr[2 * s], sTzr[2 * s + 1]});
         double f = k.spin_frequency * (1 + k.doppler);
         double tres = dphase.hi / f;
         double err2 = (t.err2 + k.equad2) * k.efac * k.efac;  // scaled_toa_error_sqr toa.jl:122-123

@@ -8,7 +8,8 @@ namespace vela {
 constexpr int kSigMaxSamples = 64;  // walkers per CTA: 8 x (n-tiles per warp)
 constexpr int kSigMaxRank = 1024;
 
-constexpr int kCholThreads = 256;
+constexpr int kCholThreads = 256;        // sizing of the per-warp scratch
+constexpr int kCholLaunchThreads = 128;  // threads per walker CTA (measured best across ranks 60..300)
 
 struct PriorDev {
     int kind;
@@ -116,7 +117,7 @@ struct CholArgs {
     double* Sig;               // packed lower triangle per walker
     long ld_sig;
     long ld_u;
-    double* Sq;                // [B][p + 1][pp + 1] scratch, only when the matrix does not fit shared memory
+    double* Sq;                // [B][(p + 1)(p + 2) / 2] row-packed scratch, only when the matrix does not fit shared memory
     int ksplit;                // number of split-K slabs to sum
     long split_stride_sig;
     long split_stride_u;
@@ -166,7 +167,7 @@ __global__ void chol_finish_kernel(CholArgs a);
 constexpr int kCholSmallRank = 96;   // block width 8 up to this rank, 16 above
 inline size_t chol_smem_doubles(int p, int pp, int nb, bool matrix_in_smem, int n_r) {
     return (size_t)2 * pp + (size_t)nb * (nb + 1) + nb + (size_t)(p + 1) * (nb + 1) +
-           (matrix_in_smem ? (size_t)(p + 1) * (pp + 1) : 0) + (size_t)n_r;   // n_r: column sums of the structured path
+           (matrix_in_smem ? (size_t)(p + 1) * (p + 2) / 2 : 0) + (size_t)n_r;   // n_r: column sums of the structured path
 }
 __global__ void phiinv_kernel(CholArgs a, double* out);
 __global__ void sincos_cr_kernel(const double* x, int n, double* s, double* c);
