@@ -164,7 +164,7 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
         CU(cudaMemsetAsync(b.R, 0, (size_t)b.r_rows * h->sp.n_cols * sizeof(double), d.stream));
     }
     if (h->p > 0 && h->sp.active && h->n_eg == 0) {
-        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * ((size_t)(h->p + 1) * (h->p + 2) / 2) * sizeof(double)));
+        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * (h->p + 1) * (h->pp + 1) * sizeof(double)));
     } else if (h->p > 0) {
         // Sigma / U scratch: at least `cap` walker rows, and never fewer than kSplitRows so that small batches can
         // hold several split-K slabs
@@ -174,7 +174,7 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
         CU(cudaMalloc((void**)&b.U, (size_t)b.sig_rows * h->pp * sizeof(double)));
         CU(cudaMemsetAsync(b.Sig, 0, (size_t)b.sig_rows * h->ld_sig * sizeof(double), d.stream));
         CU(cudaMemsetAsync(b.U, 0, (size_t)b.sig_rows * h->pp * sizeof(double), d.stream));
-        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * ((size_t)(h->p + 1) * (h->p + 2) / 2) * sizeof(double)));
+        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * (h->p + 1) * (h->pp + 1) * sizeof(double)));
         if (h->n_eg > 0) {
             size_t vb = (size_t)cap * h->eg_pad * h->ldv * sizeof(double);
             CU(cudaMalloc((void**)&b.V, vb));
@@ -518,8 +518,12 @@ int set_smem_attrs(int dev) {
         CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     for (const ColsumShape& sh : kColsumSplitShapes)
         CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-    CU(cudaFuncSetAttribute(chol_finish_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
-    CU(cudaFuncSetAttribute(chol_finish_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
+    for (auto k : {chol_finish_kernel<8, true>, chol_finish_kernel<16, true>, chol_finish_kernel<16, false>})
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
+    // shared-memory matrices: many small walker CTAs per SM, so ask for the largest shared carve-out; the global-scratch
+    // variant keeps the default split (its matrix traffic wants the L1)
+    for (auto k : {chol_finish_kernel<8, true>, chol_finish_kernel<16, true>})
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
@@ -609,7 +613,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         ch.ahat = d_ahat; ch.cf = d_cf;
         int chol_threads = kCholLaunchThreads;     // measured best across ranks 60..300 (tests/gpu_chol_probe.py)
         if (const char* e = getenv("VELA_B200_CHOL_THREADS")) chol_threads = std::max(32, std::min(kCholLaunchThreads, atoi(e) / 32 * 32));
-        (h->p <= kCholSmallRank ? chol_finish_kernel<8> : chol_finish_kernel<16>)<<<(unsigned)B, chol_threads, h->chol_smem_bytes, st>>>(ch);
+        (h->p <= kCholSmallRank ? chol_finish_kernel<8, true> : (h->chol_smem ? chol_finish_kernel<16, true> : chol_finish_kernel<16, false>))<<<(unsigned)B, chol_threads, h->chol_smem_bytes, st>>>(ch);
         if (timing) cudaEventRecord(d.ev[4], st);
         h->launches += 2;
     }
@@ -971,7 +975,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
 
     // walkers per device per pass: bound the y/w/Sigma scratch to ~1/4 of the device memory
     if (h->kernel_kind != VELA_KERNEL_WHITE) {
-        size_t per = (size_t)2 * h->n_rows_pad * 8 + (h->sp.active ? (size_t)h->sp.n_cols * 32 + (h->n_eg ? (size_t)h->ld_sig * 8 : 0) : (size_t)h->ld_sig * 8) + (size_t)h->pp * 8 + (h->chol_smem ? 0 : (size_t)(h->p + 1) * (h->p + 2) / 2 * 8) + (size_t)h->eg_pad * h->ldv * 8;
+        size_t per = (size_t)2 * h->n_rows_pad * 8 + (h->sp.active ? (size_t)h->sp.n_cols * 32 + (h->n_eg ? (size_t)h->ld_sig * 8 : 0) : (size_t)h->ld_sig * 8) + (size_t)h->pp * 8 + (h->chol_smem ? 0 : (size_t)(h->p + 1) * (h->pp + 1) * 8) + (size_t)h->eg_pad * h->ldv * 8;
         size_t free_b = 0, total_b = 0;
         cudaSetDevice(devices[0]);
         cudaMemGetInfo(&free_b, &total_b);

@@ -682,37 +682,41 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 // Row-packed lower triangle: entry (r, c <= r) of the walker's matrix (rows 0..p, row p = u^T and -z.z)
 __device__ __forceinline__ size_t tri(int r, int c) { return (size_t)r * (r + 1) / 2 + c; }
 
-// Cholesky of one NB x NB diagonal block by a single thread, entirely in registers; rows >= nb are identity padding.
-// Kept out of line so that its ~100 registers do not set the register count of the whole CTA.
-template <int NB>
-__device__ __noinline__ void factor_diag_block(double* A, int k0, int nb, double* dblk, double* rdiag, int* fail) {
+// matrix entry (r, c <= r): row-packed triangle or pitched rows
+#define AIDX(r, c) (PACKED ? tri((r), (c)) : (size_t)(r) * lda + (c))
+
+// Cholesky of one NB x NB (NB <= 8) diagonal block by one warp, in registers: lane r owns row r (statically indexed
+// after unrolling), columns travel by shuffle.  Rows >= nb are identity padding.  ~20 registers, no shared-memory
+// round trips inside the dependent chain.
+template <int NB, bool PACKED>
+__device__ __forceinline__ void factor_diag_block_warp(double* A, int lda, int k0, int nb, double* dblk, double* rdiag, int* fail) {
     constexpr int PP = NB + 1;
-    double L[NB][NB];
+    const int lane = threadIdx.x & 31;
+    double row[NB];
 #pragma unroll
-    for (int r = 0; r < NB; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) L[r][c] = (r < nb) ? A[tri(k0 + r, k0 + c)] : (r == c ? 1.0 : 0.0);
+    for (int c = 0; c < NB; ++c)
+        row[c] = (lane < nb && c <= lane) ? A[AIDX(k0 + lane, k0 + c)] : ((lane == c) ? 1.0 : 0.0);
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
-        double d = L[c][c];
-        if (!(d > 0.0) || !isfinite(d)) { *fail = 1; d = 1.0; }
+        double d = __shfl_sync(0xffffffffu, row[c], c);          // pivot, held by lane c
+        if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *fail = 1; d = 1.0; }
         const double rd = rsqrt(d);
-        L[c][c] = d * rd;
-        rdiag[c] = rd;
+        if (lane == c) { row[c] = d * rd; rdiag[c] = rd; }
+        else if (lane > c) row[c] *= rd;
 #pragma unroll
-        for (int r = c + 1; r < NB; ++r) L[r][c] *= rd;
-#pragma unroll
-        for (int r = c + 1; r < NB; ++r)
-#pragma unroll
-            for (int q = c + 1; q <= r; ++q) L[r][q] -= L[r][c] * L[q][c];
-    }
-#pragma unroll
-    for (int r = 0; r < NB; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) {
-            dblk[r * PP + c] = L[r][c];
-            if (r < nb) A[tri(k0 + r, k0 + c)] = L[r][c];
+        for (int q = c + 1; q < NB; ++q) {
+            const double lqc = __shfl_sync(0xffffffffu, row[c], q);   // L[q][c]
+            if (lane >= q) row[q] -= row[c] * lqc;
         }
+    }
+    if (lane < NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+            if (c <= lane) {
+                dblk[lane * PP + c] = row[c];
+                if (lane < nb) A[AIDX(k0 + lane, k0 + c)] = row[c];
+            }
+    }
 }
 
 // Blocked right-looking factorisation (block width NB): per block column (1) the NB x NB diagonal block is
@@ -721,8 +725,8 @@ __device__ __noinline__ void factor_diag_block(double* A, int k0, int nb, double
 // from a shared copy of the panel.  u is carried as an extra matrix row p: the panel solve turns it into
 // z = L^-1 u and the trailing update leaves -z.z in entry (p, p), so there is no separate forward solve.
 // Four block barriers per block column instead of five per column.
-template <int NB>
-__global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_finish_kernel(CholArgs a) {
+template <int NB, bool PACKED>
+__global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 2) chol_finish_kernel(CholArgs a) {
     extern __shared__ double smem[];
     __shared__ double scratch[kCholThreads / 32];
     __shared__ int sFail;
@@ -736,10 +740,11 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
     double* dblk = z + pp;                        // [NB][PP] diagonal block
     double* rdiag = dblk + NB * PP;               // [NB]   1 / L_cc of the current block
     double* panel = rdiag + NB;                   // [p + 1][PP] rows below the diagonal block
-    const size_t n_tri = (size_t)(p + 1) * (p + 2) / 2;
-    double* A;                                    // row-packed lower triangle of rows 0..p (row p = u^T), see tri()
-    if (a.use_smem) A = panel + (size_t)(p + 1) * PP;
-    else A = a.Sq + (size_t)b * n_tri;            // large rank: factorise in the L2-resident global scratch
+    // matrix rows 0..p (row p = u^T): row-packed lower triangle in shared memory (PACKED), pitched rows in the
+    // L2-resident global scratch of the large ranks
+    const int lda = pp + 1;
+    const size_t n_tri = PACKED ? (size_t)(p + 1) * (p + 2) / 2 : (size_t)(p + 1) * lda;
+    double* A = PACKED ? panel + (size_t)(p + 1) * PP : a.Sq + (size_t)b * n_tri;
     // ---- Sigma: unpack the packed lower triangle t = r(r+1)/2 + c (dense path) or assemble it from the column sums
     //      through the pair table (structured path); split-K slabs are summed in slice order
     {
@@ -747,7 +752,7 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
         const long n_pairs = (long)p * (p + 1) / 2;
         double* sR = nullptr;
         if (a.table) {
-            sR = panel + (size_t)(p + 1) * PP + (a.use_smem ? n_tri : 0);   // last shared slot
+            sR = panel + (size_t)(p + 1) * PP + (PACKED ? n_tri : 0);   // last shared slot
             const double* gR = a.R + (size_t)b * a.ld_r;
             for (int i = tid; i < a.n_r; i += nt) {
                 double v = gR[i];
@@ -769,7 +774,7 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
                 v = gA[t];
                 for (int zz = 1; zz < a.ksplit; ++zz) v += gA[(size_t)zz * a.split_stride_sig + t];
             }
-            A[tri(r, c)] = v;
+            A[AIDX(r, c)] = v;
             c += nt;
             while (c > r) { c -= r + 1; ++r; }
         }
@@ -778,10 +783,10 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
         for (int i = tid; i < p; i += nt) {
             double v = gU[(size_t)b * ldu + i];
             for (int zz = 1; zz < a.ksplit; ++zz) v += gU[(size_t)zz * su + (size_t)b * ldu + i];
-            A[tri(p, i)] = v;
+            A[AIDX(p, i)] = v;
         }
     }
-    if (tid == 0) { sFail = 0; A[tri(p, p)] = 0.0; }
+    if (tid == 0) { sFail = 0; A[AIDX(p, p)] = 0.0; }
 
     // ---- Phi^-1 for this walker
     const double* P = a.Pext + (size_t)b * a.row;
@@ -806,7 +811,7 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
     double lphi = 0.0;
     for (int i = tid; i < p; i += nt) {
         lphi += log(phi[i]);
-        A[tri(i, i)] += phi[i];
+        A[AIDX(i, i)] += phi[i];
     }
     const double logdetPhi = -block_sum(lphi, scratch);
     __syncthreads();
@@ -817,13 +822,11 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
         const int nb = min(NB, p - k0), k1 = k0 + nb;
         // (1) diagonal block
         if constexpr (NB <= 8) {
-            // one thread factorises the NB x NB block entirely in registers (a dependent chain either way; this
-            // avoids NB rounds of warp barriers and shared-memory round trips); rows >= nb are identity padding
-            if (tid == 0) factor_diag_block<NB>(A, k0, nb, dblk, rdiag, &sFail);
+            if (tid < 32) factor_diag_block_warp<NB, PACKED>(A, lda, k0, nb, dblk, rdiag, &sFail);
         } else {
             for (int e = tid; e < nb * nb; e += nt) {
                 const int r = e / nb, c = e - r * nb;
-                if (c <= r) dblk[r * PP + c] = A[tri(k0 + r, k0 + c)];
+                if (c <= r) dblk[r * PP + c] = A[AIDX(k0 + r, k0 + c)];
             }
             __syncthreads();
             if (tid < 32) {
@@ -848,7 +851,7 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
                 }
                 for (int e = tid; e < nb * nb; e += 32) {
                     const int r = e / nb, c = e - r * nb;
-                    if (c <= r) A[tri(k0 + r, k0 + c)] = dblk[r * PP + c];
+                    if (c <= r) A[AIDX(k0 + r, k0 + c)] = dblk[r * PP + c];
                 }
             }
         }
@@ -856,7 +859,7 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
         // (2) panel: rows k1 .. p (row p is u^T) times L_kk^-T, one thread per row
         for (int i = k1 + tid; i < n1; i += nt) {
             double x[NB];
-            double* row = A + tri(i, k0);
+            double* row = A + AIDX(i, k0);
 #pragma unroll
             for (int c = 0; c < NB; ++c) x[c] = c < nb ? row[c] : 0.0;
 #pragma unroll
@@ -897,11 +900,11 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
                         s00 += li0[c] * lj0; s01 += li0[c] * lj1;
                         s10 += li1[c] * lj0; s11 += li1[c] * lj1;
                     }
-                    if (j0 <= i0) A[tri(k1 + i0, k1 + j0)] -= s00;
-                    if (j1 <= i0 && j1 < m) A[tri(k1 + i0, k1 + j1)] -= s01;
+                    if (j0 <= i0) A[AIDX(k1 + i0, k1 + j0)] -= s00;
+                    if (j1 <= i0 && j1 < m) A[AIDX(k1 + i0, k1 + j1)] -= s01;
                     if (i1 < m) {
-                        if (j0 <= i1) A[tri(k1 + i1, k1 + j0)] -= s10;
-                        if (j1 <= i1 && j1 < m) A[tri(k1 + i1, k1 + j1)] -= s11;
+                        if (j0 <= i1) A[AIDX(k1 + i1, k1 + j0)] -= s10;
+                        if (j1 <= i1 && j1 < m) A[AIDX(k1 + i1, k1 + j1)] -= s11;
                     }
                 }
             }
@@ -910,10 +913,10 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
     }
 
     double ld = 0.0;
-    for (int i = tid; i < p; i += nt) ld += log(A[tri(i, i)]);
+    for (int i = tid; i < p; i += nt) ld += log(A[AIDX(i, i)]);
     const double logdetSig = 2 * block_sum(ld, scratch);
     if (tid == 0) {
-        const double zz = -A[tri(p, p)];
+        const double zz = -A[AIDX(p, p)];
         double yNy = 0.0, logdetN = 0.0;
         for (int t = 0; t < a.n_tiles; ++t) {
             yNy += a.partial[((size_t)t * a.B + b) * 2];
@@ -926,13 +929,13 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
     if (!a.ahat) return;
     // ---- conditional mean of the marginalised amplitudes: L^T ahat = z, i.e. ahat = Sigma u
     // (pyvela/pyvela/spnta.py:376-394: cho_solve((Sigmainv_cf, False), MT_Ninv_y)) and the upper factor L^T
-    for (int i = tid; i < p; i += nt) z[i] = A[tri(p, i)];
+    for (int i = tid; i < p; i += nt) z[i] = A[AIDX(p, i)];
     for (int k = p - 1; k >= 0; --k) {
         __syncthreads();
-        if (tid == 0) z[k] /= A[tri(k, k)];
+        if (tid == 0) z[k] /= A[AIDX(k, k)];
         __syncthreads();
         const double zk = z[k];
-        for (int i = tid; i < k; i += nt) z[i] -= A[tri(k, i)] * zk;
+        for (int i = tid; i < k; i += nt) z[i] -= A[AIDX(k, i)] * zk;
     }
     __syncthreads();
     const double bad = sFail ? CUDART_NAN : 0.0;
@@ -941,12 +944,14 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 3) chol_fini
         double* dst = a.cf + (size_t)b * p * p;
         for (int idx = tid; idx < p * p; idx += nt) {
             const int i = idx / p, j = idx - i * p;
-            dst[idx] = j >= i ? A[tri(j, i)] + bad : 0.0;
+            dst[idx] = j >= i ? A[AIDX(j, i)] + bad : 0.0;
         }
     }
 }
-template __global__ void chol_finish_kernel<8>(CholArgs);
-template __global__ void chol_finish_kernel<16>(CholArgs);
+#undef AIDX
+template __global__ void chol_finish_kernel<8, true>(CholArgs);
+template __global__ void chol_finish_kernel<16, true>(CholArgs);
+template __global__ void chol_finish_kernel<16, false>(CholArgs);
 
 // Phi^-1 only (vela_b200_noise_weights_inv): one block, walker 0
 __global__ void phiinv_kernel(CholArgs a, double* __restrict__ out) {

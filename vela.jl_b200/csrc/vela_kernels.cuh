@@ -117,7 +117,7 @@ struct CholArgs {
     double* Sig;               // packed lower triangle per walker
     long ld_sig;
     long ld_u;
-    double* Sq;                // [B][(p + 1)(p + 2) / 2] row-packed scratch, only when the matrix does not fit shared memory
+    double* Sq;                // [B][p + 1][pp + 1] scratch, only when the matrix does not fit shared memory
     int ksplit;                // number of split-K slabs to sum
     long split_stride_sig;
     long split_stride_u;
@@ -162,7 +162,7 @@ __global__ void finish_white_kernel(const double* partial, int n_tiles, long B, 
 template <int BK, int STAGES, int MT, int NT, int WARPS>
 __global__ void sigma_contract_kernel(SigmaArgs a);
 
-template <int NB>
+template <int NB, bool PACKED>
 __global__ void chol_finish_kernel(CholArgs a);
 constexpr int kCholSmallRank = 96;   // block width 8 up to this rank, 16 above
 inline size_t chol_smem_doubles(int p, int pp, int nb, bool matrix_in_smem, int n_r) {
