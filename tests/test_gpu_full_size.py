@@ -29,3 +29,20 @@ def test_full_size_config(name, nsub, vb, oracle):
     y, _ = psr.resids_and_Ninvdiag(ds.truth)
     yo, _ = oracle.residuals(md, ds.truth)
     assert np.max(np.abs(y - yo)[: len(ds.toas)]) < 1e-9
+
+
+def test_config5_full_toa_count(vb, oracle):
+    """BASELINE configs[4] at its full 100k TOAs and rank 300 (red + DM + chromatic GP); the walker count is cut to
+    512 (the full 65 536 are 8 GPUs' worth) and the oracle checks four of them."""
+    cfg = vb.synth.CONFIGS["config5_array"]
+    ds = vb.synth.make_dataset("config5_array", lambda m, t: vb.Pulsar(m, t))
+    assert len(ds.toas) == cfg["ntoa"] == 100000 and ds.info["rank"] == 300
+    psr = vb.Pulsar(ds.model, ds.toas)
+    assert psr.sigma_structured() and psr.chain_specialized()
+    W = ds.walkers(512, seed=5)
+    out = psr.lnlike_vectorized(W)
+    assert np.all(np.isfinite(out))
+    perm = np.random.default_rng(2).permutation(len(W))
+    np.testing.assert_array_equal(psr.lnlike_vectorized(W[perm]), out[perm])
+    md = vb.ModelDescriptor(ds.model, ds.toas)
+    np.testing.assert_allclose(out[:4], oracle.lnlike_batch(md, W[:4]), rtol=1e-9)
