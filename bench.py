@@ -299,36 +299,40 @@ def main():
         nrows_pad = (nrows + 63) // 64 * 64
         sigma_exec = 2.0 * n_cols * nrows_pad if structured else float(flops_sigma)
         tf = lambda fl, ms: (fl * B / (ms * 1e-3) / 1e12) if ms > 0 else None   # noqa: E731
+        # compute-bound kernels of this path run on the FP64 pipe; on B200 scalar DFMA and the DMMA tensor path share it
+        # (measured peaks 36.5 vs 37.1 TFLOP/s), so "tensor" with the matching measured peak is the applicable roofline
+        fp64_note = "FP64 pipe, scalar DFMA issue (shares the datapath of the FP64 tensor path on B200); peak = measured DFMA loop"
         kernels = [
             {"kernel": "toa_chain_kernel (per-model NVRTC build)" if psr.chain_specialized() else "toa_chain_kernel (generic)",
-             "bound": "fp64", "ms": chain_ms, "algorithmic_flops_per_launch": 330.0 * ntoa * B,
+             "bound": "tensor", "bound_detail": fp64_note, "ms": chain_ms, "algorithmic_flops_per_launch": 330.0 * ntoa * B,
              "achieved": tf(330.0 * ntoa, chain_ms), "peak": dfma_peak, "unit": "TFLOP/s"},
             {"kernel": "colsum_kernel (structured Sigma, FP64 DMMA m8n8k4)" if structured else "sigma_contract_kernel (FP64 DMMA m8n8k4)",
              "bound": "tensor", "ms": sigma_ms, "algorithmic_flops_per_launch": sigma_exec * B,
              "achieved": tf(sigma_exec, sigma_ms), "peak": dmma_peak, "unit": "TFLOP/s",
              "reference_equivalent_tflops": tf(float(flops_sigma), sigma_ms)},
-            {"kernel": "chol_finish_kernel", "bound": "fp64", "ms": chol_ms,
+            {"kernel": "chol_finish_kernel", "bound": "tensor", "bound_detail": fp64_note, "ms": chol_ms,
              "algorithmic_flops_per_launch": (p**3 / 3 + p * p + 10 * p) * B,
              "achieved": tf(p**3 / 3 + p * p + 10 * p, chol_ms), "peak": dfma_peak, "unit": "TFLOP/s"},
         ]
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-        # very step (profiles/r1_ncu_full_config3_v3.txt); only valid for the default workload and kernel variants
-        ncu_traffic = {"toa_chain_kernel (per-model NVRTC build)": 0.003848e9 + 1.257515e9,
-                       "colsum_kernel (structured Sigma, FP64 DMMA m8n8k4)": 1.360821e9 + 0.042892e9,
-                       "sigma_contract_kernel (FP64 DMMA m8n8k4)": 1.532375e9 + 0.116714e9,
-                       "chol_finish_kernel": 0.057261e9 + 0.000297e9}
+        # very step (profiles/r1_ncu_full_config3_v4_final.txt); only valid for the default workload and kernel variants
+        ncu_traffic = {"toa_chain_kernel (per-model NVRTC build)": 0.003827e9 + 1.256570e9,
+                       "colsum_kernel (structured Sigma, FP64 DMMA m8n8k4)": 1.347266e9 + 0.043589e9,
+                       "sigma_contract_kernel (FP64 DMMA m8n8k4)": 1.532375e9 + 0.116714e9,   # v2b_dense capture
+                       "chol_finish_kernel": 0.057262e9 + 0.000205e9}
         for k in kernels:
             k["traffic"] = ncu_traffic.get(k["kernel"]) if (ntoa, p, B) == (10000, 60, 8192) else None
             k["frac"] = (k["achieved"] / k["peak"]) if k["achieved"] and k["peak"] > 0 else None
             k["share_of_step"] = k["ms"] / float(stage_ms[4]) if stage_ms[4] > 0 else None
         dom = max(kernels, key=lambda k: k["ms"])
         roofline = {
-            "bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
+            "bound": dom["bound"], "bound_detail": dom.get("bound_detail", "FP64 tensor cores (mma.sync m8n8k4 f64 -> DMMA)"),
+            "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
             "unit": "TFLOP/s", "frac": dom["frac"], "traffic": dom["traffic"],
             "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                              "(profiles/r1_ncu_full_config3_v3.txt)",
-            "peak_source": "measured in this run: register-resident FP64 loops (vela_b200_fp64_peak_tflops: DFMA for "
-                           "'fp64' kernels, mma.sync.m8n8k4.f64 for 'tensor' kernels); MEASURED_PEAKS.json holds only "
+                              "(profiles/r1_ncu_full_config3_v4_final.txt)",
+            "peak_source": "measured in this run: register-resident FP64 loops (vela_b200_fp64_peak_tflops: DFMA for the "
+                           "scalar kernels, mma.sync.m8n8k4.f64 for the DMMA kernels); MEASURED_PEAKS.json holds only "
                            "HBM and bf16 peaks",
             "fp64_fma_peak_tflops": dfma_peak, "fp64_dmma_peak_tflops": dmma_peak,
             "algorithmic_flops_per_launch": dom["algorithmic_flops_per_launch"],
