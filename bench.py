@@ -75,6 +75,14 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
 
 
+def host_threads() -> int:
+    """All host threads this process may use.  torchrun exports OMP_NUM_THREADS=1, so the OpenMP default is not it."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def algorithmic_flops(ntoa: int, nrows: int, p: int):
     """per-evaluation FLOPs; returns (total, sigma_contraction_only)."""
     chain = 330 * ntoa
@@ -95,7 +103,7 @@ def cpu_reference_arm(args, rank: int, world: int):
     from helpers import oracle_eval_factory
     ds = vb.synth.make_dataset(WORKLOAD, oracle_eval_factory(vb, O))
     md = vb.ModelDescriptor(ds.model, ds.toas)
-    cores = O.max_threads()
+    cores = host_threads()
     probe = ds.walkers(4 * cores, seed=99)
     t0 = time.perf_counter()
     O.lnlike_batch(md, probe, nthreads=cores)
@@ -362,7 +370,7 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle as O
             md = vb.ModelDescriptor(ds.model, ds.toas)
-            cores = O.max_threads()
+            cores = host_threads()
             probe = host_sets[0][: 4 * cores]
             t0 = time.perf_counter()
             O.lnlike_batch(md, probe, nthreads=cores)
