@@ -16,10 +16,11 @@ for _ in range(4):
     out = psr.lnlike_vectorized(W); st = psr.last_stage_ms(); best = min(best, st[1])
 print(f"chain {best:.3f} ms spec {psr.chain_specialized()} sum {out.sum():.10e}")
 '''
-open('/tmp/_cprobe.py', 'w').write(code)
+os.makedirs('gpurun_out', exist_ok=True)
+open('gpurun_out/_cprobe.py', 'w').write(code)
 cases = [("config3_gp", 10000, 8192), ("config2_ell1", 5000, 4096), ("config4_dd_wb", 20000, 4096), ("extra_ddk_wb", 5000, 2048), ("extra_ell1h_fd_wavex", 5000, 2048)]
 for name, ntoa, B in cases:
     for mb in (2, 3, 4):
         env = dict(os.environ, VELA_B200_JIT_MINBLOCKS=str(mb))
-        r = subprocess.run([sys.executable, '/tmp/_cprobe.py', name, str(ntoa), str(B)], env=env, capture_output=True, text=True, timeout=600)
+        r = subprocess.run([sys.executable, 'gpurun_out/_cprobe.py', name, str(ntoa), str(B)], env=env, capture_output=True, text=True, timeout=600)
         print(name, ntoa, B, 'minblocks', mb, r.stdout.strip() or r.stderr[-300:], flush=True)

@@ -17,7 +17,8 @@ for _ in range(4):
 p = ds.info["rank"]; nr = ntoa * (2 if ds.info["wideband"] else 1)
 print(f"sigma {best:.3f} ms chol {bc:.3f} all {ba:.3f}  {(nr*p*(p+1)+3*nr*p)*B/(best*1e-3)/1e12:.2f} TF  finite {np.isfinite(out).mean():.2f} sum {out.sum():.10e}")
 '''
-open('/tmp/_probe.py', 'w').write(code)
+os.makedirs('gpurun_out', exist_ok=True)
+open('gpurun_out/_probe.py', 'w').write(code)
 cases = [("config3_gp", 10000, 8192), ("config3_gp", 10000, 64), ("config3_gp", 10000, 1024), ("config4_dd_wb", 20000, 4096), ("config5_array", 20000, 2048)]
 plans = [(0, 0)] if len(sys.argv) > 1 and sys.argv[1] == "auto" else [(0, 0), (4, 1), (4, 2), (4, 3)]
 for name, ntoa, B in cases:
@@ -26,5 +27,5 @@ for name, ntoa, B in cases:
         if mt:
             env["VELA_B200_SIGMA_MT"] = str(mt)
             env["VELA_B200_SIGMA_KSPLIT"] = str(ks)
-        r = subprocess.run([sys.executable, '/tmp/_probe.py', name, str(ntoa), str(B)], env=env, capture_output=True, text=True, timeout=600)
+        r = subprocess.run([sys.executable, 'gpurun_out/_probe.py', name, str(ntoa), str(B)], env=env, capture_output=True, text=True, timeout=600)
         print(name, ntoa, B, 'mt', mt, 'ks', ks, r.stdout.strip() or r.stderr[-300:], flush=True)

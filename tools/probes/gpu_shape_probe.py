@@ -17,9 +17,10 @@ for _ in range(3):
 p = ds.info["rank"]; nr = ntoa
 print(f"sigma {best:.3f} ms  {(nr*p*(p+1)+3*nr*p)*B/(best*1e-3)/1e12:.2f} TF  finite {np.isfinite(out).mean():.2f}")
 '''
-open('/tmp/_probe.py', 'w').write(code)
+os.makedirs('gpurun_out', exist_ok=True)
+open('gpurun_out/_probe.py', 'w').write(code)
 for name, ntoa, B in (("config3_gp", 10000, 8192), ("config5_array", 10000, 1024)):
     for shape in ([0, 1, 2, 3, 9, 10] if name == "config3_gp" else [5, 6, 7, 11]):
         env = dict(os.environ, VELA_B200_SIGMA_SHAPE=str(shape))
-        r = subprocess.run([sys.executable, '/tmp/_probe.py', name, str(ntoa), str(B)], env=env, capture_output=True, text=True, timeout=300)
+        r = subprocess.run([sys.executable, 'gpurun_out/_probe.py', name, str(ntoa), str(B)], env=env, capture_output=True, text=True, timeout=300)
         print(name, 'shape', shape, r.stdout.strip() or r.stderr[-300:])

@@ -210,7 +210,7 @@ const SigmaShape kSigmaShapes[] = {
 
 // K3 work quantisation.  A CTA is `warps` units of MT m8-tiles over 32 walkers and one CTA is resident per SM, so a
 // launch costs about  CTAs x t_cta / SMs + 0.8 t_cta  (throughput term + tail; the tail factor is fitted to the
-// measurements in tests/gpu_plan_probe.py).  Two knobs trade padding against the tail: the row-tile height MT (4 or 3
+// measurements in tools/probes/gpu_plan_probe.py).  Two knobs trade padding against the tail: the row-tile height MT (4 or 3
 // m8-tiles per warp) and split-K over gridDim.z (K4 sums the slabs in slice order, so the result stays deterministic
 // for a given batch size).  Small batches use the same model: few CTAs -> deep split.
 struct SigmaPlan { int mt, ksplit, n_pair_units, n_units; };
@@ -221,7 +221,7 @@ SigmaPlan plan_sigma(const VelaPulsar* h, const SigmaShape& sh, long sig_rows, l
     const long max_split = std::max<long>(1, std::min<long>({64, std::max<long>(1, n_ktiles / 4),
                                                               sig_rows / std::max<long>(round_up(B, kSigMaxSamples), 1)}));
     // Units: one k-tile of 64 TOAs for one m8 tile row of a CTA (2.4 us on a B200).  Measured at config 3 / 4
-    // (tests/gpu_plan_probe.py): the MT = 3 kernel runs ~12 % slower per DMMA (10 LDS per 12 DMMAs instead of 12 per
+    // (tools/probes/gpu_plan_probe.py): the MT = 3 kernel runs ~12 % slower per DMMA (10 LDS per 12 DMMAs instead of 12 per
     // 16), and every extra split-K slab costs K4 one more pass over the walkers' packed triangles.
     const double kFixed = 6.0;                         // pipeline fill + epilogue of one CTA
     const double tile = sh.bk / 64.0;
@@ -422,7 +422,7 @@ int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool w
         return wy ? (n_t + sh.uc - 1) / sh.uc + (n_u + sh.uc - 1) / sh.uc : (n_units + sh.uc - 1) / sh.uc;
     };
     // the shape that pads the unit count least; ties go to the deeper rings and, for many units, to wide CTAs
-    // (tests/gpu_colsum_probe.py)
+    // (tools/probes/gpu_colsum_probe.py)
     int si = n_units <= 8 ? 2 : 1;
     {
         long best = cta_cols(shapes[si]) * shapes[si].uc;
@@ -611,7 +611,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
             ch.split_stride_sig = sa.split_stride_sig; ch.split_stride_u = sa.split_stride_u;
         }
         ch.ahat = d_ahat; ch.cf = d_cf;
-        int chol_threads = kCholLaunchThreads;     // measured best across ranks 60..300 (tests/gpu_chol_probe.py)
+        int chol_threads = kCholLaunchThreads;     // measured best across ranks 60..300 (tools/probes/gpu_chol_probe.py)
         if (const char* e = getenv("VELA_B200_CHOL_THREADS")) chol_threads = std::max(32, std::min(kCholLaunchThreads, atoi(e) / 32 * 32));
         (h->p <= kCholSmallRank ? chol_finish_kernel<8, true> : (h->chol_smem ? chol_finish_kernel<16, true> : chol_finish_kernel<16, false>))<<<(unsigned)B, chol_threads, h->chol_smem_bytes, st>>>(ch);
         if (timing) cudaEventRecord(d.ev[4], st);
@@ -950,7 +950,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         if (!(e && atoi(e) == 0)) {
             cudaKernel_t k = nullptr;
             // three resident blocks per SM (80 registers): 3-8 % faster than two on every model probed, the few
-            // spilled bytes included (tests/gpu_chain_probe.py)
+            // spilled bytes included (tools/probes/gpu_chain_probe.py)
             int mb = 3;
             if (const char* force = getenv("VELA_B200_JIT_MINBLOCKS")) mb = std::max(1, std::min(4, atoi(force)));
             int rc_jit = jit_chain_kernel(spec_source(pg, mb), &k, h->jit_log);
