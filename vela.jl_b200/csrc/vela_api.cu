@@ -326,9 +326,31 @@ bool analyse_basis(const VelaModelDesc* desc, long n_rows, long n_rows_pad, int 
     for (int i = 0; i < ng; ++i) gslot[good[i]] = i;
     std::vector<int> baseC((size_t)ng * ng, -1), baseS((size_t)ng * ng, -1);
     long n_r = 0;
+    // group pairs whose scale products coincide row by row share their columns (red x chromatic and DM x DM both
+    // scale as (1400 MHz / nu)^4, for instance); "owner" marks the pair that fills them
+    std::vector<char> owner((size_t)ng * ng, 0);
     for (int a = 0; a < ng; ++a)
         for (int c = a; c < ng; ++c) {
-            const int K = groups[good[a]].kmax + groups[good[c]].kmax;
+            const Grp &Ga = groups[good[a]], &Gc = groups[good[c]];
+            const int K = Ga.kmax + Gc.kmax;
+            bool shared = false;
+            for (int a2 = 0; a2 <= a && !shared; ++a2)
+                for (int c2 = a2; c2 < ng && !shared; ++c2) {
+                    if (!owner[(size_t)a2 * ng + c2] || groups[good[a2]].kmax + groups[good[c2]].kmax < K) continue;
+                    const Grp &Ha = groups[good[a2]], &Hc = groups[good[c2]];
+                    bool same = true;
+                    for (long j = 0; j < n_rows && same; ++j) {
+                        const double u = Ga.s[j] * Gc.s[j], v = Ha.s[j] * Hc.s[j];
+                        same = std::fabs(u - v) <= 1e-14 * std::max(std::fabs(u), std::fabs(v));
+                    }
+                    if (same) {
+                        baseC[(size_t)a * ng + c] = baseC[(size_t)c * ng + a] = baseC[(size_t)a2 * ng + c2];
+                        baseS[(size_t)a * ng + c] = baseS[(size_t)c * ng + a] = baseS[(size_t)a2 * ng + c2];
+                        shared = true;
+                    }
+                }
+            if (shared) continue;
+            owner[(size_t)a * ng + c] = 1;
             baseC[(size_t)a * ng + c] = baseC[(size_t)c * ng + a] = (int)n_r; n_r += K + 1;
             baseS[(size_t)a * ng + c] = baseS[(size_t)c * ng + a] = (int)n_r - 1; n_r += K;   // S(m) at baseS + m, m >= 1
         }
@@ -376,6 +398,7 @@ bool analyse_basis(const VelaModelDesc* desc, long n_rows, long n_rows_pad, int 
                 }
             for (int a = 0; a < ng; ++a)
                 for (int c = a; c < ng; ++c) {
+                    if (!owner[(size_t)a * ng + c]) continue;
                     const Grp &Ga = groups[good[a]], &Gc = groups[good[c]];
                     const int K = Ga.kmax + Gc.kmax, bc = baseC[(size_t)a * ng + c], bs = baseS[(size_t)a * ng + c];
                     for (int m = 0; m <= K; ++m) {
