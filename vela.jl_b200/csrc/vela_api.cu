@@ -582,12 +582,15 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
     const bool ecorr = h->n_ecorr_groups > 0;
     ChainArgs ca;
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
-    ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = B; ca.group = h->chain_group;
+    // walkers per chain CTA: 32 at full size; emcee-sized batches use smaller groups so the grid still covers the SMs
+    int group = h->chain_group;
+    while (group > 4 && (long)h->n_tiles * ((B + group - 1) / group) < 3L * d.n_sm) group /= 2;
+    ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = B; ca.group = group;
     const bool wy = woodbury && h->sp.active && !ecorr;   // Y carries w.y for the structured contraction
     ca.emit = wy ? 3 : ((woodbury || ecorr) ? 1 : 0); ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     const int warps = h->chain_threads / 32;
-    size_t chain_smem = ((size_t)h->chain_group * pg.row + 2 * h->chain_group + (size_t)warps * h->chain_group * 3) * sizeof(double);
-    dim3 cgrid((unsigned)h->n_tiles, (unsigned)((B + h->chain_group - 1) / h->chain_group));
+    size_t chain_smem = ((size_t)group * pg.row + 2 * group + (size_t)warps * group * 3) * sizeof(double);
+    dim3 cgrid((unsigned)h->n_tiles, (unsigned)((B + group - 1) / group));
     launch_chain(h, cgrid, chain_smem, st, ca);
     h->launches += 2;
     if (ecorr) {
