@@ -124,6 +124,7 @@ struct VelaPulsar {
     bool have_priors = false;
     long max_chunk = 0;  // walkers per device per pass
     cudaKernel_t spec_chain = nullptr;   // NVRTC-specialised chain kernel (vela_jit.cu); null = generic kernel only
+    cudaKernel_t spec_prologue = nullptr;
     bool use_spec = false;
     std::string jit_log;
 };
@@ -159,7 +160,8 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
         CU(cudaMemsetAsync(b.W, 0, yw, d.stream));
     }
     if (h->p > 0 && h->sp.active) {
-        b.r_rows = std::max<long>(cap * 4, kSplitRows);
+        // room for deep split-K at small and medium batches: R rows are only n_cols doubles each
+        b.r_rows = std::max<long>(cap * 4, std::min<long>(65536, ((long)64 << 20) / ((long)h->sp.n_cols * 8)));
         CU(cudaMalloc((void**)&b.R, (size_t)b.r_rows * h->sp.n_cols * sizeof(double)));
         CU(cudaMemsetAsync(b.R, 0, (size_t)b.r_rows * h->sp.n_cols * sizeof(double), d.stream));
     }
@@ -462,11 +464,17 @@ int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool w
                                                               b.r_rows / std::max<long>(round_up(B, kSigMaxSamples), 1)}));
     long ks_best = 1;
     double best_cost = 1e300;
-    for (long ks = 1; ks <= max_split; ++ks) {     // same cost model as plan_sigma
+    // all CTAs of this kernel take the same time and one is resident per SM, so the launch runs in (nearly) whole
+    // waves: cost = waves x (k-tiles per CTA + fixed cost) with waves half-way between ceil(CTAs / SMs) and the
+    // fractional count; measured at config 3 (tools/probes/gpu_ks_probe.py): 288 CTAs (ks 3, 1.95 waves) 1.09 ms,
+    // 384 CTAs (ks 4) 1.19 ms, 480 / 576 CTAs 1.24 ms; at config 4 (112 CTAs per slice) ks 1 / 4 / 8: 6.48 / 6.13 / 6.07 ms
+    for (long ks = 1; ks <= max_split; ++ks) {
         const long kt = (n_ktiles + ks - 1) / ks, nz = (n_ktiles + kt - 1) / kt;
         if (nz != ks) continue;
-        const double t_cta = (double)kt * (sh.bk / 64.0) * 4 + 6.0;
-        const double cost = std::max((double)(ctas_xy * nz) / d.n_sm, 1.0) * t_cta + 0.8 * t_cta + 0.02 * t_cta * (double)(ks - 1) / ks;
+        const double t_cta = (double)kt * (sh.bk / 16.0) + 16.0;
+        const double frac = std::max((double)(ctas_xy * nz) / d.n_sm, 1.0);
+        const double waves = 0.5 * (std::ceil(frac) + frac);
+        const double cost = waves * t_cta * (1.0 + 0.002 * (double)(ks - 1));
         if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; ks_best = ks; }
     }
     if (const char* e = getenv("VELA_B200_SIGMA_KSPLIT")) ks_best = std::max<long>(1, std::min<long>(atoi(e), max_split));
@@ -555,6 +563,21 @@ int set_smem_attrs(int dev) {
     return 0;
 }
 
+// K0 launch (read_params + hoists + TZR phase), per-model build when available
+void launch_prologue(VelaPulsar* h, DeviceModel& d, const double* d_params, long B, cudaStream_t st) {
+    PrologueArgs pa;
+    pa.defaults = d.defaults; pa.free_idx = d.free_idx; pa.params = d_params; pa.B = B; pa.tzr_block = d.tzr_block;
+    pa.index_masks = d.index_masks; pa.bit_masks = d.bit_masks; pa.n_toas = h->n_toas; pa.Pext = d.buf.Pext; pa.tzr_phase = d.buf.tzr;
+    const int threads = B >= 4096 ? 128 : 32;    // small batches: spread the walkers over more SMs
+    const dim3 grid((unsigned)((B + threads - 1) / threads));
+    if (h->use_spec && h->spec_prologue) {
+        void* args[] = {&pa};
+        cudaLaunchKernel((const void*)h->spec_prologue, grid, dim3((unsigned)threads), args, 0, st);
+    } else {
+        sample_prologue_kernel<<<grid, threads, 0, st>>>(h->prog, pa);
+    }
+}
+
 // K1 launch: the NVRTC-specialised kernel of this model when it exists and is enabled, else the generic interpreter
 void launch_chain(VelaPulsar* h, dim3 grid, size_t smem, cudaStream_t st, ChainArgs& ca) {
     if (h->use_spec && h->spec_chain) {
@@ -574,9 +597,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
     Buffers& b = d.buf;
     const bool timing = h->stage_timing && (&d == &h->devs[0]);
     if (timing) cudaEventRecord(d.ev[0], st);
-    sample_prologue_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(pg, d.defaults, d.free_idx, d_params, B,
-                                                                         d.tzr_block, d.index_masks, d.bit_masks,
-                                                                         h->n_toas, b.Pext, b.tzr);
+    launch_prologue(h, d, d_params, B, st);
     if (timing) cudaEventRecord(d.ev[1], st);
     const bool woodbury = h->p > 0 && mode == 0;
     const bool ecorr = h->n_ecorr_groups > 0;
@@ -771,7 +792,9 @@ std::string spec_source(const ProgramDev& pg, int min_blocks = 2) {
     src += "}};\n}  // namespace vela\n"
            "extern \"C\" __global__ void __launch_bounds__(vela::kChainThreads, ";
     src += std::to_string(min_blocks);
-    src += ") vela_chain_spec(vela::ChainArgs a) {\n    vela::chain_body(vela::kSpecProg, a);\n}\n";
+    src += ") vela_chain_spec(vela::ChainArgs a) {\n    vela::chain_body(vela::kSpecProg, a);\n}\n"
+           "extern \"C\" __global__ void __launch_bounds__(128) vela_prologue_spec(vela::PrologueArgs a) {\n"
+           "    vela::prologue_body(vela::kSpecProg, a);\n}\n";
     return src;
 }
 
@@ -979,7 +1002,8 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
             // spilled bytes included (tools/probes/gpu_chain_probe.py)
             int mb = 3;
             if (const char* force = getenv("VELA_B200_JIT_MINBLOCKS")) mb = std::max(1, std::min(4, atoi(force)));
-            int rc_jit = jit_chain_kernel(spec_source(pg, mb), &k, h->jit_log);
+            cudaKernel_t kp = nullptr;
+            int rc_jit = jit_chain_kernel(spec_source(pg, mb), &k, &kp, h->jit_log);
             if (rc_jit == 0) {
                 bool ok = true;
                 for (auto& d : h->devs) {
@@ -992,7 +1016,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
                     }
                 }
                 cudaSetDevice(prev);
-                if (ok) { h->spec_chain = k; h->use_spec = true; }
+                if (ok) { h->spec_chain = k; h->spec_prologue = kp; h->use_spec = true; }
             }
         } else {
             h->jit_log = "disabled by VELA_B200_JIT=0";
@@ -1159,8 +1183,7 @@ static int run_single(VelaHandle h, const double* params, int64_t n_free, int mo
     cudaMalloc((void**)&dW, sizeof(double) * h->n_rows_pad);
     cudaMalloc((void**)&dF, sizeof(double) * h->n_rows_pad);
     cudaMemcpyAsync(b.params, params, sizeof(double) * std::max<long>(n_free, 1), cudaMemcpyHostToDevice, d.stream);
-    sample_prologue_kernel<<<1, 128, 0, d.stream>>>(h->prog, d.defaults, d.free_idx, b.params, 1, d.tzr_block,
-                                                    d.index_masks, d.bit_masks, h->n_toas, b.Pext, b.tzr);
+    launch_prologue(h, d, b.params, 1, d.stream);
     ChainArgs ca;
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = mode;
@@ -1205,8 +1228,7 @@ VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int
     if (rc) { cudaSetDevice(prev); return rc; }
     Buffers& b = d.buf;
     cudaMemcpyAsync(b.params, params, sizeof(double) * std::max<long>(n_free, 1), cudaMemcpyHostToDevice, d.stream);
-    sample_prologue_kernel<<<1, 128, 0, d.stream>>>(h->prog, d.defaults, d.free_idx, b.params, 1, d.tzr_block,
-                                                    d.index_masks, d.bit_masks, h->n_toas, b.Pext, b.tzr);
+    launch_prologue(h, d, b.params, 1, d.stream);
     CholArgs ch;
     memset(&ch, 0, sizeof ch);
     ch.Pext = b.Pext; ch.row = h->prog.row; ch.p = h->p; ch.pp = h->pp; ch.n_gp = h->n_gp; ch.gp = d.gp; ch.gp_data = d.gp_data;
@@ -1322,8 +1344,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     if (rc) { cudaSetDevice(prev); return rc; }
     Buffers& b = d.buf;
     cudaMemcpyAsync(b.params, params, sizeof(double) * std::max<long>(n_free, 1), cudaMemcpyHostToDevice, d.stream);
-    sample_prologue_kernel<<<1, 128, 0, d.stream>>>(h->prog, d.defaults, d.free_idx, b.params, 1, d.tzr_block,
-                                                    d.index_masks, d.bit_masks, h->n_toas, b.Pext, b.tzr);
+    launch_prologue(h, d, b.params, 1, d.stream);
     ChainArgs ca;
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
     const bool wy = h->sp.active && h->n_ecorr_groups == 0;

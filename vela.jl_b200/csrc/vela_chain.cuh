@@ -27,6 +27,47 @@ struct ChainArgs {
     double* partial;           // [tiles][B][2]
 };
 
+struct PrologueArgs {
+    const double* defaults;    // [np + n_aux]: default parameter values, then the components' constant tables
+    const int* free_idx;       // [nd] 0-based positions of the free parameters
+    const double* params;      // [B][nd] samples
+    long B;
+    const double* tzr_block;   // the TZR TOA as C_NCOL columns with stride 1
+    const uint32_t* index_masks;
+    const uint8_t* bit_masks;
+    long n_toas;
+    double* Pext;              // [B][row]
+    double* tzr_phase;         // [B][2]
+};
+
+// K0 body: read_params (parameter.jl:158-169) + per-walker hoists + calc_tzr_phase (residuals.jl:29-32); one thread
+// per walker.  Shared by the generic kernel and the per-model NVRTC build like chain_body below.
+__device__ __forceinline__ void prologue_body(const ProgramDev& prog, const PrologueArgs& a) {
+    long b = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    double* P = a.Pext + b * prog.row;
+    for (int i = 0; i < prog.n_params; ++i) P[i] = a.defaults[i];
+    for (int i = 0; i < prog.n_free; ++i) P[a.free_idx[i]] = a.params[b * prog.n_free + i];
+    double* D = P + prog.n_params;
+    const double* aux = a.defaults + prog.n_params;
+#ifdef VELA_SPEC_CALLS
+#define VELA_APPLY(i) fill_derived(prog.comp[i], P, D + prog.comp[i].der, aux);
+    VELA_SPEC_CALLS
+#undef VELA_APPLY
+#else
+    for (int ic = 0; ic < prog.n_comp; ++ic) fill_derived(prog.comp[ic], P, D + prog.comp[ic].der, aux);
+#endif
+    ChainEnv e;
+    e.toa_base = a.tzr_block; e.stride = 1; e.j = 0;
+    e.index_masks = a.index_masks; e.bit_masks = a.bit_masks; e.n_toas = a.n_toas;
+    e.tzr = true; e.wide = false;
+    // the TZR block is laid out column-after-column with stride 1 (C_NCOL doubles)
+    ToaRegs t = load_toa(a.tzr_block, 1, 0, false);
+    Corr k = run_chain(prog, P, t, e);
+    a.tzr_phase[2 * b] = k.bad ? CUDART_NAN : k.phase.hi;
+    a.tzr_phase[2 * b + 1] = k.phase.lo;
+}
+
 __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainArgs& a) {
     extern __shared__ double smem[];
     const int row = prog.row;

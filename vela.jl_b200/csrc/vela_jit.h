@@ -11,8 +11,8 @@ namespace vela {
 // Needs libnvrtc but no GPU.  Returns 0 on success; `log` holds the compiler log / the reason otherwise.
 int jit_compile_cubin(const std::string& src, std::vector<char>& cubin, std::string& log);
 
-// Compile (cached per process by source text), load and return the `vela_chain_spec` kernel.
-int jit_chain_kernel(const std::string& src, cudaKernel_t* out, std::string& log);
+// Compile (cached per process by source text), load and return the `vela_chain_spec` and `vela_prologue_spec` kernels.
+int jit_chain_kernel(const std::string& src, cudaKernel_t* out, cudaKernel_t* prologue, std::string& log);
 
 // True when the ptxas statistics in `log` (compiled with -v) report register spills.
 bool jit_log_spills(const std::string& log);

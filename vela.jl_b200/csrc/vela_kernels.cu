@@ -21,31 +21,8 @@ namespace vela {
 // K0  sample prologue
 // ------------------------------------------------------------------------------------------
 // read_params (parameter.jl:158-169) + hoists + calc_tzr_phase (residuals.jl:29-32)
-__global__ void __launch_bounds__(128) sample_prologue_kernel(const __grid_constant__ ProgramDev prog,
-                                                             const double* __restrict__ defaults,
-                                                             const int* __restrict__ free_idx,
-                                                             const double* __restrict__ params, long B,
-                                                             const double* __restrict__ tzr_block,
-                                                             const uint32_t* __restrict__ index_masks,
-                                                             const uint8_t* __restrict__ bit_masks, long n_toas,
-                                                             double* __restrict__ Pext, double* __restrict__ tzr_phase) {
-    long b = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    double* P = Pext + b * prog.row;
-    for (int i = 0; i < prog.n_params; ++i) P[i] = defaults[i];
-    for (int i = 0; i < prog.n_free; ++i) P[free_idx[i]] = params[b * prog.n_free + i];
-    double* D = P + prog.n_params;
-    for (int ic = 0; ic < prog.n_comp; ++ic) fill_derived(prog.comp[ic], P, D + prog.comp[ic].der, defaults + prog.n_params);
-
-    ChainEnv e;
-    e.toa_base = tzr_block; e.stride = 1; e.j = 0;
-    e.index_masks = index_masks; e.bit_masks = bit_masks; e.n_toas = n_toas;
-    e.tzr = true; e.wide = false;
-    // the TZR block is laid out column-after-column with stride 1 (C_NCOL doubles)
-    ToaRegs t = load_toa(tzr_block, 1, 0, false);
-    Corr k = run_chain(prog, P, t, e);
-    tzr_phase[2 * b] = k.bad ? CUDART_NAN : k.phase.hi;
-    tzr_phase[2 * b + 1] = k.phase.lo;
+__global__ void __launch_bounds__(128) sample_prologue_kernel(const __grid_constant__ ProgramDev prog, PrologueArgs a) {
+    prologue_body(prog, a);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -147,10 +147,7 @@ struct CholArgs {
     double* cf;                // optional [B][p][p] row-major upper Cholesky factor of Sigma^-1 (L^T)
 };
 
-__global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, const double* defaults, const int* free_idx,
-                                       const double* params, long B, const double* tzr_block,
-                                       const uint32_t* index_masks, const uint8_t* bit_masks, long n_toas,
-                                       double* Pext, double* tzr_phase);
+__global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, PrologueArgs a);
 __global__ void toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a);
 __global__ void prior_kernel(const PriorDev* priors, int nd, const double* params, long B, int mode, double* out);
 __global__ void ecorr_group_kernel(EcorrArgs a);
