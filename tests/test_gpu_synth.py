@@ -159,3 +159,14 @@ def test_structured_and_dense_sigma_paths_agree(name, ntoa, datasets, vb, oracle
     for B in (1, 3, 33):
         np.testing.assert_allclose(psr.lnlike_vectorized(W[:B]), a[:B], rtol=1e-12)
         np.testing.assert_allclose(dense.lnlike_vectorized(W[:B]), b[:B], rtol=1e-12)
+
+
+def test_wideband_model_dm_and_scaled_errors(datasets, oracle):
+    """spnta.py:605-645 mirrors on a wideband dataset: model DM = measured DM - DM residual, scaled DM errors."""
+    ds, psr, md = datasets("config4_dd_wb", 700)
+    n = len(ds.toas)
+    yo, wo = oracle.residuals(md, ds.truth)
+    np.testing.assert_allclose(psr.model_dm(ds.truth), (ds.toas.dm - yo[n:]) * 2.41e-16, rtol=1e-12)
+    np.testing.assert_allclose(psr.scaled_dm_uncertainties(ds.truth), 1 / np.sqrt(wo[n:]), rtol=1e-13)
+    with pytest.raises(NotImplementedError):
+        datasets("config3_gp", 1200)[1].model_dm(datasets("config3_gp", 1200)[0].truth)

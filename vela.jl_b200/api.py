@@ -237,6 +237,25 @@ class Pulsar:
     def scaled_toa_uncertainties(self, params) -> np.ndarray:
         return 1.0 / np.sqrt(self.resids_and_Ninvdiag(params)[1][: len(self.toas)])
 
+    def scaled_dm_uncertainties(self, params) -> np.ndarray:
+        """spnta.py:605-620 (wideband only)."""
+        if not self.toas.wideband:
+            raise AssertionError("This method is only defined for wideband datasets.")
+        return 1.0 / np.sqrt(self.resids_and_Ninvdiag(params)[1][len(self.toas):])
+
+    def model_dm(self, params) -> np.ndarray:
+        """spnta.py:622-645, in dmu.  Wideband: the model DM the chain accumulates (measured DM minus DM residual);
+        the narrowband variant re-runs the dispersion components on the host in the reference and is not mirrored."""
+        if not self.toas.wideband:
+            raise NotImplementedError("model_dm is mirrored for wideband TOAs only")
+        return (self.toas.dm - self.dm_residuals(params)) * 2.41e-16
+
+    def maxpost_params(self, x0=None) -> np.ndarray:
+        """spnta.py:647-655: Nelder-Mead on -lnpost from the default parameters."""
+        from scipy.optimize import minimize
+        start = self.model.read_param_values_to_vector() if x0 is None else np.asarray(x0, dtype=np.float64)
+        return minimize(lambda x: -self.lnpost(x), start, method="Nelder-Mead").x
+
     def whitened_time_residuals(self, params, rng=None) -> np.ndarray:
         """spnta.py:523-556: subtract one GP realisation, then the conditional mean of the ECORR jitter.  The
         ECORR design matrix is block-orthogonal, so its normal equations decouple into one scalar per group."""
