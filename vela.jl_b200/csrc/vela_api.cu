@@ -800,6 +800,41 @@ std::string spec_source(const ProgramDev& pg, int min_blocks = 2) {
     return src;
 }
 
+// Expansion points of shapiro_log() (vela_device.cuh): for every TOA, x0 = r - L0.r for the Sun and the five planets with
+// L0 the pulsar direction at the DEFAULT parameter values (evaluate_proper_motion, solarsystem.jl:45-56, plain libm: the
+// point only has to be close), 1 / x0 and log(x0 / AU).  Columns stay zero (= general branch on the device) when there
+// is no SolarSystem component or the geometry is degenerate.
+void fill_shapiro_columns(const VelaModelDesc* desc, double* cols, long stride, long j) {
+    const VelaComponentDesc* ss = nullptr;
+    for (int ic = 0; ic < desc->n_components; ++ic)
+        if (desc->components[ic].kind == VELA_COMP_SOLAR_SYSTEM) { ss = &desc->components[ic]; break; }
+    if (!ss) return;
+    const double* P = desc->default_values;
+    for (int k = 0; k < 6; ++k) if (ss->par[k] < 0) return;
+    const double lon = P[ss->par[0]], lat = P[ss->par[1]], pma = P[ss->par[2]], pmd = P[ss->par[3]], posepoch = P[ss->par[5]];
+    const double sa = std::sin(lon), ca = std::cos(lon), sd = std::sin(lat), cd = std::cos(lat);
+    auto at = [&](int c) { return cols[(size_t)c * stride + j]; };
+    const double dt = at(C_T_HI) - posepoch;
+    double L[3] = {ca * cd + (-sa * pma - ca * sd * pmd) * dt, sa * cd + (ca * pma - sa * sd * pmd) * dt, sd + cd * pmd * dt};
+    const double mag = std::sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+    for (double& v : L) v /= mag;
+    if (ss->flags & VELA_FLAG_ECLIPTIC) {
+        const double se = 0.397776969112606, ce = 0.9174821430652418;
+        const double y = L[1], z = L[2];
+        L[1] = ce * y - se * z;
+        L[2] = se * y + ce * z;
+    }
+    for (int b = 0; b < 6; ++b) {
+        const int c0 = b == 0 ? C_SUN : C_PLANET + 3 * (b - 1);
+        const double r = b == 0 ? at(C_RSUN) : at(C_RPLANET + b - 1);
+        const double x0 = r - (L[0] * at(c0) + L[1] * at(c0 + 1) + L[2] * at(c0 + 2));
+        if (!(x0 > 0.0) || !std::isfinite(x0)) continue;
+        cols[(size_t)(C_SHAP + 3 * b) * stride + j] = x0;
+        cols[(size_t)(C_SHAP + 3 * b + 1) * stride + j] = 1.0 / x0;
+        cols[(size_t)(C_SHAP + 3 * b + 2) * stride + j] = std::log(x0 / 499.00478383615643);
+    }
+}
+
 int validate(const VelaModelDesc* d) {
     if (!d) return fail(VELA_ERR_INVALID_ARG, "null descriptor");
     if (d->abi_version != VELA_B200_ABI_VERSION) return fail(VELA_ERR_INVALID_ARG, "ABI version %d, expected %d", d->abi_version, VELA_B200_ABI_VERSION);
@@ -964,10 +999,13 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     // SoA TOA table (+ TOA-only hoists) and the TZR block
     long stride = round_up(desc->n_toas, 32);
     std::vector<double> soa((size_t)C_NCOL * stride, 0.0);
-    for (long j = 0; j < desc->n_toas; ++j)
+    for (long j = 0; j < desc->n_toas; ++j) {
         fill_toa_columns((const double*)((const char*)desc->toas + j * (long)desc->toa_stride_bytes), desc->wideband, soa.data(), stride, j);
+        fill_shapiro_columns(desc, soa.data(), stride, j);
+    }
     std::vector<double> tzr(C_NCOL, 0.0);
     fill_toa_columns((const double*)desc->tzr_toa, 0, tzr.data(), 1, 0);
+    fill_shapiro_columns(desc, tzr.data(), 1, 0);
 
     std::vector<int> devices;
     if (desc->n_devices > 0 && desc->devices) devices.assign(desc->devices, desc->devices + desc->n_devices);
