@@ -14,7 +14,8 @@ Keys beyond the base contract: `roofline` (the kernel with the largest share of 
 peak of its pipe measured in this run; every kernel of the step is listed under `roofline.kernels`), `cpu_baseline` (the CPU oracle — a C/OpenMP restatement of
 the reference algorithm, NOT Julia — on a bounded sample of the same workload), `e2e` (host buffers
 through the public `Pulsar.lnpost_vectorized` call, H2D/D2H inside the timed region), `clocks`,
-`gpu_launches`, `parity` (max relative lnlike difference vs the oracle on the CPU sample).
+`gpu_launches`, `parity` (max relative lnlike difference vs the oracle on the CPU sample), `dense_sigma_path` (the same
+workload with the structured Sigma path switched off: the dense FP64 tensor-core contraction and its roofline).
 """
 from __future__ import annotations
 
@@ -366,6 +367,38 @@ def main():
             "flops_per_eval": flops_eval,
             "reference_equivalent_tflops_whole_step": flops_eval * B * world / (dev_ms / args.steps * 1e-3) / 1e12,
         }
+        if world == 1:
+            # the same workload with the structured Sigma path switched off: the dense packed-triangle contraction that
+            # an arbitrary (non-harmonic) basis gets, rated on the reference algorithm's own flop count
+            os.environ["VELA_B200_STRUCTURED"] = "0"
+            try:
+                dense = vb.Pulsar(ds.model, ds.toas, devices=[local_rank])
+                dense.set_priors(priors)
+            finally:
+                del os.environ["VELA_B200_STRUCTURED"]
+            nd_steps = max(3, min(args.steps, 20))
+            for i in range(3):
+                dense.lnpost_device(dev_sets[i % n_sets].data_ptr(), B, dev_lnpr[i % n_sets].data_ptr(), d_out.data_ptr(), stream)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(nd_steps):
+                dense.lnpost_device(dev_sets[i % n_sets].data_ptr(), B, dev_lnpr[i % n_sets].data_ptr(), d_out.data_ptr(), stream)
+            e1.record()
+            torch.cuda.synchronize()
+            dense_ms = e0.elapsed_time(e1) / nd_steps
+            dense.set_stage_timing(True)
+            dstage = np.zeros(5)
+            for i in range(3):
+                dense.lnpost_device(dev_sets[i % n_sets].data_ptr(), B, dev_lnpr[i % n_sets].data_ptr(), d_out.data_ptr(), stream)
+                torch.cuda.synchronize()
+                dstage += np.array(dense.last_stage_ms())
+            dstage /= 3
+            dtf = flops_sigma * B / (dstage[2] * 1e-3) / 1e12 if dstage[2] > 0 else None
+            line["dense_sigma_path"] = {
+                "value": B / (dense_ms * 1e-3), "unit": UNIT, "ms_per_step": dense_ms, "steps": nd_steps,
+                "kernel": "sigma_contract_kernel (FP64 DMMA m8n8k4, packed lower triangle)", "kernel_ms": float(dstage[2]),
+                "achieved": dtf, "peak": dmma_peak, "unit_roofline": "TFLOP/s", "frac": (dtf / dmma_peak) if dtf else None,
+                "note": "VELA_B200_STRUCTURED=0; what a basis without harmonic structure runs"}
         if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle as O
