@@ -216,3 +216,68 @@ def test_structured_sigma_rejects_unstructured_basis(vb, oracle):
                                  ds.model.components, bad, ds.model.param_handler, ds.model.tzr_toa, ds.model.priors)
     md = vb.ModelDescriptor(model, ds.toas)
     assert vb.lib.lib().vela_b200_debug_structured_sigma(md.byref(), None, None, None) == 0
+
+
+def test_structured_sigma_on_perturbed_bases(vb, oracle):
+    """The structure is verified on the numbers of M, never assumed: per-row scales (zero and negative ones
+    included), a group with its own phase, a noisy column and log-spaced harmonics must either be served exactly
+    through the table or leave the handle on the dense path."""
+    import ctypes as C
+    from helpers import oracle_eval_factory
+    M_ = vb.model
+    vb.synth.CONFIGS["_tmp_small_gp"] = dict(ntoa=400, span_d=3000.0, red=6, dmgp=5, chromgp=4, nback=2, walkers=16, seed=31)
+    try:
+        ds = vb.synth.make_dataset("_tmp_small_gp", oracle_eval_factory(vb, oracle))
+    finally:
+        del vb.synth.CONFIGS["_tmp_small_gp"]
+    k = ds.model.kernel
+    n, p = k.noise_basis.shape
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-np.pi, np.pi, n)
+    w = rng.uniform(0.5, 2.0, n) * 1e12
+    dp = C.POINTER(C.c_double)
+    L = vb.lib.lib()
+
+    def basis(scales, phase_shift=(0.0, 0.0, 0.0)):
+        cols = []
+        for (nh, s, ph) in zip((6, 5, 4), scales, phase_shift):
+            kk = np.arange(1, nh + 1)
+            cols += [s[:, None] * np.sin(np.outer(x + ph, kk)), s[:, None] * np.cos(np.outer(x + ph, kk))]
+        return np.concatenate(cols, axis=1)
+
+    def run(Mat, gps=None):
+        kern = M_.WoodburyKernel(k.inner_kernel, gps or k.gp_components, Mat)
+        model = M_.TimingModel(ds.model.pulsar_name, ds.model.ephem, ds.model.clock, ds.model.units, ds.model.epoch,
+                               ds.model.components, kern, ds.model.param_handler, ds.model.tzr_toa, ds.model.priors)
+        md = vb.ModelDescriptor(model, ds.toas)
+        out = np.zeros(p * (p + 1) // 2)
+        info = (C.c_int32 * 3)()
+        n_r = L.vela_b200_debug_structured_sigma(md.byref(), w.ctypes.data_as(dp), out.ctypes.data_as(dp), info)
+        if n_r > 0:
+            dense = Mat.T @ (Mat * w[:, None])
+            il = np.tril_indices(p)
+            scale = np.sqrt(np.outer(np.diag(dense), np.diag(dense)))[il] + 1e-300
+            assert np.max(np.abs(out - dense[il]) / scale) < 1e-12
+        return n_r, info[2]
+
+    s1 = np.ones(n)
+    s2 = rng.uniform(0.5, 8.0, n)
+    s2[::7] = 0.0                                   # rows where the second group vanishes
+    s3 = -s2 * s2                                   # a negative scale
+    n_r, groups = run(basis((s1, s2, s3)))
+    assert n_r > 0 and groups == 3
+    # second group on its own phase: it cannot share the table; whatever path is chosen must stay exact
+    n_r2, groups2 = run(basis((s1, s2, s3), phase_shift=(0.0, 0.3, 0.0)))
+    assert groups2 <= 2 and (n_r2 == 0 or n_r2 > n_r)
+    # one noisy column (1e-9 relative): its group is demoted
+    noisy = basis((s1, s2, s3))
+    noisy[:, 3] *= 1 + 1e-9 * rng.standard_normal(n)
+    n_r3, groups3 = run(noisy)
+    assert groups3 <= 2
+    # log-spaced harmonics (non-integer multiples of the fundamental) are generic columns
+    gps = (M_.PowerlawRedNoiseGP(4, 2, 2.0), k.gp_components[1], k.gp_components[2])
+    js = np.exp(np.asarray(gps[0].ln_js, dtype=np.float64))
+    red = np.concatenate([np.sin(np.outer(x, js)), np.cos(np.outer(x, js))], axis=1)
+    rest = basis((s1, s2, s3))[:, 12:]
+    n_r4, groups4 = run(np.concatenate([red, rest], axis=1), gps=gps)
+    assert n_r4 == 0 or groups4 >= 2
