@@ -697,11 +697,11 @@ __device__ __forceinline__ void factor_diag_block_warp(double* A, int lda, int k
 }
 
 // Blocked right-looking factorisation (block width NB): per block column (1) the NB x NB diagonal block is
-// factorised by one warp in a small shared tile, (2) one thread per row solves the panel below it against that
-// block, (3) all threads apply the rank-NB update to the trailing lower triangle in 2x2 register micro-tiles fed
-// from a shared copy of the panel.  u is carried as an extra matrix row p: the panel solve turns it into
-// z = L^-1 u and the trailing update leaves -z.z in entry (p, p), so there is no separate forward solve.
-// Four block barriers per block column instead of five per column.
+// factorised by one warp (in registers for NB = 8, in a small shared tile for NB = 16), (2) one thread per row
+// solves the panel below it against that block, (3) all threads apply the rank-NB update to the trailing lower
+// triangle in 2x2 register micro-tiles fed from a shared copy of the panel.  u is carried as an extra matrix row p:
+// the panel solve turns it into z = L^-1 u and the trailing update leaves -z.z in entry (p, p), so there is no
+// separate forward solve.  Three block barriers per block of 8 columns instead of five per column.
 template <int NB, bool PACKED>
 __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 2) chol_finish_kernel(CholArgs a) {
     extern __shared__ double smem[];
