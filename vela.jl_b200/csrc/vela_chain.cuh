@@ -68,6 +68,18 @@ __device__ __forceinline__ void prologue_body(const ProgramDev& prog, const Prol
     a.tzr_phase[2 * b + 1] = k.phase.lo;
 }
 
+// frexp for the log-det accumulation: normal positive inputs (every sane err^2) are split with three integer
+// operations; zero, subnormal, infinite and NaN inputs go through the library routine.
+__device__ __forceinline__ double split_mantissa(double v, int* ex) {
+    const long long bits = __double_as_longlong(v);
+    const int field = (int)((bits >> 52) & 0x7ff);
+    if (bits > 0 && field != 0 && field != 0x7ff) {
+        *ex = field - 1022;
+        return __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3fe0000000000000LL);   // mantissa in [1/2, 1)
+    }
+    return frexp(v, ex);
+}
+
 __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainArgs& a) {
     extern __shared__ double smem[];
     const int row = prog.row;
@@ -106,7 +118,7 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
         // logarithm is taken once per (tile, walker) in the block epilogue instead of once per (TOA, walker)
         double chi, w = 0.0;
         int lex;
-        double lman = frexp(err2, &lex);
+        double lman = split_mantissa(err2, &lex);
         if (a.emit) {  // Woodbury: y^T N^-1 y and log det N from Ninvdiag, gls_likelihood.jl:81-99
             w = 1.0 / err2;
             chi = tres * tres * w;
@@ -118,7 +130,7 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
             dmres = t.dm - k.model_dm;
             double dmerr2 = (t.dmerr2 + k.dmequad2) * k.dmefac * k.dmefac;
             int dex;
-            lman *= frexp(dmerr2, &dex);
+            lman *= split_mantissa(dmerr2, &dex);
             lex += dex;
             if (a.emit) {
                 wdm = 1.0 / dmerr2;
