@@ -47,3 +47,24 @@ def test_lnpost_uses_device_priors(vb, golden, oracle):
     assert post[7] == -np.inf
     ok = np.isfinite(want)
     np.testing.assert_allclose(post[ok], want[ok], rtol=1e-9)
+
+
+def test_reference_prior_literals_on_device(vb, golden):
+    """test/test_priors.jl:3-44 through the device twins: PHOFF, F0 (truncated Normal, lower = 0), F1."""
+    P = vb.priors
+    g = golden("NGC6440E")
+    psr = vb.Pulsar(g.model, g.toas)
+    nd = psr.ndim
+    priors = [P.SimplePrior("PHOFF", P.Uniform(-0.5, 0.5)), P.SimplePriorMulti("F", 1, P.TruncatedNormal(100.0, 1e-7, 0.0, np.inf)),
+              P.SimplePriorMulti("F", 2, P.Uniform(-1.01e-14, -0.9e-14))]
+    priors += [P.SimplePrior(f"x{k}", P.Uniform(-1e9, 1e9)) for k in range(nd - 3)]
+    assert psr.set_priors(priors)
+    pad = np.zeros(nd - 3)
+    good = np.concatenate([[0.1, 100.0, -1e-14], pad])
+    bad = np.concatenate([[1.1, -200.0, -2e-14], pad])
+    lp = psr.lnprior_vectorized(np.stack([good, bad]))
+    assert np.isfinite(lp[0]) and lp[1] == -np.inf
+    np.testing.assert_allclose(lp[0], P.lnprior(priors, good), rtol=1e-12)
+    cube = np.concatenate([[0.5, 0.5, 0.0], np.full(nd - 3, 0.5)])
+    got = psr.prior_transform_vectorized(cube[None, :])[0]
+    np.testing.assert_allclose(got[:3], [0.0, 100.0, -1.01e-14], rtol=1e-12, atol=1e-30)

@@ -281,3 +281,22 @@ def test_structured_sigma_on_perturbed_bases(vb, oracle):
     rest = basis((s1, s2, s3))[:, 12:]
     n_r4, groups4 = run(np.concatenate([red, rest], axis=1), gps=gps)
     assert n_r4 == 0 or groups4 >= 2
+
+
+def test_priors_reference_literals(vb):
+    """The literal cases of test/test_priors.jl:3-44 (SimplePrior on PHOFF, truncated Normal on F0, Uniform on F1)."""
+    P = vb.priors
+    priors = [P.SimplePrior("PHOFF", P.Uniform(-0.5, 0.5), P.USER_DEFINED_PRIOR),
+              P.SimplePriorMulti("F", 1, P.TruncatedNormal(100.0, 1e-7, 0.0, np.inf), P.USER_DEFINED_PRIOR),
+              P.SimplePriorMulti("F", 2, P.Uniform(-1.01e-14, -0.9e-14), P.USER_DEFINED_PRIOR)]
+    good, bad = np.array([0.1, 100.0, -1e-14]), np.array([1.1, -200.0, -2e-14])
+    assert np.isfinite(P.lnprior(priors, good)) and not np.isfinite(P.lnprior(priors, bad))
+    for k in range(3):
+        assert np.isfinite(priors[k].distribution.logpdf(good[k])) and not np.isfinite(priors[k].distribution.logpdf(bad[k]))
+    assert float(priors[0].distribution.quantile(0.5)) == 0.0
+    assert float(priors[1].distribution.quantile(0.5)) == pytest.approx(100.0)
+    assert float(priors[2].distribution.quantile(0.0)) == -1.01e-14
+    np.testing.assert_allclose(P.prior_transform(priors, [0.5, 0.5, 0.0]), [0.0, 100.0, -1.01e-14], rtol=1e-12, atol=1e-30)
+    d = vb.descriptor.prior_descriptors(priors)
+    assert d is not None and [d[k].kind for k in range(3)] == [vb.descriptor.PRIOR_UNIFORM, vb.descriptor.PRIOR_TRUNCATED_NORMAL,
+                                                             vb.descriptor.PRIOR_UNIFORM]
