@@ -585,7 +585,7 @@ void build_program(const VelaModelDesc* desc, ProgramDev& pg) {
 }
 
 // Translation unit of the per-model chain kernel: the program as a constant object + the shared kernel body.
-std::string spec_source(const ProgramDev& pg, int min_blocks = 2) {
+std::string spec_source(const ProgramDev& pg, int min_blocks = 2, int threads = kChainThreads) {
     std::string src;
     char buf[256];
     src += "#define VELA_SPEC_CALLS";
@@ -606,8 +606,8 @@ std::string spec_source(const ProgramDev& pg, int min_blocks = 2) {
         src += buf;
     }
     src += "}};\n}  // namespace vela\n"
-           "extern \"C\" __global__ void __launch_bounds__(vela::kChainThreads, ";
-    src += std::to_string(min_blocks);
+           "extern \"C\" __global__ void __launch_bounds__(";
+    src += std::to_string(threads) + ", " + std::to_string(min_blocks);
     src += ") vela_chain_spec(vela::ChainArgs a) {\n    vela::chain_body(vela::kSpecProg, a);\n}\n"
            "extern \"C\" __global__ void __launch_bounds__(128) vela_prologue_spec(vela::PrologueArgs a) {\n"
            "    vela::prologue_body(vela::kSpecProg, a);\n}\n";
@@ -730,7 +730,8 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     h->n_toas = desc->n_toas;
     h->n_rows = desc->wideband ? 2 * desc->n_toas : desc->n_toas;
     h->n_rows_pad = round_up(h->n_rows, 64);
-    h->chain_threads = desc->n_toas <= 64 ? 64 : (desc->n_toas <= 2048 ? 128 : 256);
+    h->chain_threads = desc->n_toas <= 64 ? 64 : 128;   // 128-thread blocks x 5 resident (tools/probes/gpu_chain_threads_probe.py)
+    if (const char* e = getenv("VELA_B200_CHAIN_THREADS")) h->chain_threads = std::max(32, std::min(256, atoi(e) / 32 * 32));
     h->n_tiles = (int)((desc->n_toas + h->chain_threads - 1) / h->chain_threads);
     h->chain_group = 32;
 
@@ -852,12 +853,12 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         const char* e = getenv("VELA_B200_JIT");
         if (!(e && atoi(e) == 0)) {
             cudaKernel_t k = nullptr;
-            // three resident blocks per SM (80 registers): 3-8 % faster than two on every model probed, the few
-            // spilled bytes included (tools/probes/gpu_chain_probe.py)
-            int mb = 3;
-            if (const char* force = getenv("VELA_B200_JIT_MINBLOCKS")) mb = std::max(1, std::min(4, atoi(force)));
+            // five resident 128-thread blocks per SM (<= 102 registers, 20 warps): measured best among 64..256 threads x
+            // 2..10 blocks on the models probed (tools/probes/gpu_chain_threads_probe.py)
+            int mb = 5;
+            if (const char* force = getenv("VELA_B200_JIT_MINBLOCKS")) mb = std::max(1, std::min(16, atoi(force)));
             cudaKernel_t kp = nullptr;
-            int rc_jit = jit_chain_kernel(spec_source(pg, mb), &k, &kp, h->jit_log);
+            int rc_jit = jit_chain_kernel(spec_source(pg, mb, std::max(h->chain_threads, 128)), &k, &kp, h->jit_log);
             if (rc_jit == 0) {
                 bool ok = true;
                 for (auto& d : h->devs) {
@@ -1348,9 +1349,9 @@ VELA_API int64_t vela_b200_debug_spec_compile(const VelaModelDesc* desc) {
     build_program(desc, pg);
     std::vector<char> cubin;
     std::string log;
-    int mb = 3;
-    if (const char* f = getenv("VELA_B200_JIT_MINBLOCKS")) mb = std::max(1, std::min(4, atoi(f)));
-    if (jit_compile_cubin(spec_source(pg, mb), cubin, log)) return fail(VELA_ERR_UNSUPPORTED, "%s", log.c_str());
+    int mb = 5;
+    if (const char* f = getenv("VELA_B200_JIT_MINBLOCKS")) mb = std::max(1, std::min(16, atoi(f)));
+    if (jit_compile_cubin(spec_source(pg, mb, 128), cubin, log)) return fail(VELA_ERR_UNSUPPORTED, "%s", log.c_str());
     g_last_error = log;   // ptxas statistics of the successful build, readable through vela_b200_last_error()
     return (int64_t)cubin.size();
 }
