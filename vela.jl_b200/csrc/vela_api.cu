@@ -734,6 +734,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     if (const char* e = getenv("VELA_B200_CHAIN_THREADS")) h->chain_threads = std::max(32, std::min(256, atoi(e) / 32 * 32));
     h->n_tiles = (int)((desc->n_toas + h->chain_threads - 1) / h->chain_threads);
     h->chain_group = 32;
+    if (const char* e = getenv("VELA_B200_CHAIN_GROUP")) h->chain_group = std::max(4, std::min(128, atoi(e)));
 
     std::vector<int3> egroups;
     std::vector<int> echunks;
