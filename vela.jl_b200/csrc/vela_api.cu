@@ -248,7 +248,9 @@ const ColsumShape kColsumShapes[] = {
 };
 const ColsumShape kColsumSplitShapes[] = {
     {8, 4, 16, 1, colsum_kernel<8, 4, 16, 1, true>}, {16, 4, 8, 2, colsum_kernel<16, 4, 8, 2, true>},
-    {16, 4, 4, 4, colsum_kernel<16, 4, 4, 4, true>}, {16, 4, 2, 8, colsum_kernel<16, 4, 2, 8, true>},
+    // (2, 8): two stages of 32 TOAs beat four of 16 (1.04 vs 1.10 ms at config 3); three of 32 do not fit
+    {16, 4, 4, 4, colsum_kernel<16, 4, 4, 4, true>}, {32, 2, 2, 8, colsum_kernel<32, 2, 2, 8, true>},
+    {16, 4, 2, 8, colsum_kernel<16, 4, 2, 8, true>},   // (2, 8) for small batches: twice the k-tiles to split over
 };
 
 // Launches K3s for B walkers; `wy`: the chain kernel stored w.y in Y (emit 3).  Returns the number of split-K slabs.
@@ -270,7 +272,9 @@ int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool w
             if (padded < best) { best = padded; si = i; }
         }
     }
-    if (const char* e = getenv("VELA_B200_COLSUM_SHAPE")) si = std::max(0, std::min(3, atoi(e)));
+    // emcee-sized batches need deep split-K to cover the SMs: the 16-TOA ring has twice the k-tiles to split over
+    if (wy && si == 3 && cta_cols(shapes[3]) * ((B + 255) / 256) * (h->n_rows_pad / 32 / 8) < 2L * d.n_sm) si = 4;
+    if (const char* e = getenv("VELA_B200_COLSUM_SHAPE")) si = std::max(0, std::min(wy ? 4 : 3, atoi(e)));
     const ColsumShape& sh = shapes[si];
     const long n_ktiles = h->n_rows_pad / sh.bk;
     const long ctas_xy = cta_cols(sh) * ((B + 32 * sh.wc - 1) / (32 * sh.wc));

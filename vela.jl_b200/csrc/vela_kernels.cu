@@ -636,6 +636,7 @@ template __global__ void colsum_kernel<8, 4, 16, 1, true>(ColsumArgs);
 template __global__ void colsum_kernel<16, 4, 8, 2, true>(ColsumArgs);
 template __global__ void colsum_kernel<16, 4, 4, 4, true>(ColsumArgs);
 template __global__ void colsum_kernel<16, 4, 2, 8, true>(ColsumArgs);
+template __global__ void colsum_kernel<32, 2, 2, 8, true>(ColsumArgs);
 
 // ------------------------------------------------------------------------------------------
 // K4  + Phi^-1, Cholesky, log-det, solve, ln L
