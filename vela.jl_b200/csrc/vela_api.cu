@@ -106,6 +106,7 @@ struct VelaPulsar {
     int n_eg = 0, n_rect = 0;        // WoodburyKernel{EcorrKernel}: active groups, 32x32 rectangles of the (p+1) triangle
     long eg_pad = 0, ldv = 0;
     bool chol_smem = true;
+    int chol_nb = 8;                 // block width of the Cholesky kernel
     size_t chol_smem_bytes = 0;
     std::vector<DeviceModel> devs;
     std::mutex mtx;
@@ -478,9 +479,9 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         ch.ahat = d_ahat; ch.cf = d_cf;
         // 96 threads per walker at full size (more resident walkers, fewer idle warps in the serial phases: 0.41 ->
         // 0.35 ms at rank 60), 128 for small batches and large ranks (tools/probes/gpu_chol_probe.py)
-        int chol_threads = (B >= 1024 && h->p <= kCholSmallRank) ? 96 : kCholLaunchThreads;
+        int chol_threads = (B >= 1024 && h->chol_nb == 8) ? 96 : kCholLaunchThreads;
         if (const char* e = getenv("VELA_B200_CHOL_THREADS")) chol_threads = std::max(32, std::min(kCholLaunchThreads, atoi(e) / 32 * 32));
-        (h->p <= kCholSmallRank ? chol_finish_kernel<8, true> : (h->chol_smem ? chol_finish_kernel<16, true> : chol_finish_kernel<16, false>))<<<(unsigned)B, chol_threads, h->chol_smem_bytes, st>>>(ch);
+        (h->chol_nb == 8 && h->chol_smem ? chol_finish_kernel<8, true> : (h->chol_smem ? chol_finish_kernel<16, true> : chol_finish_kernel<16, false>))<<<(unsigned)B, chol_threads, h->chol_smem_bytes, st>>>(ch);
         if (timing) cudaEventRecord(d.ev[4], st);
         h->launches += 2;
     }
@@ -809,11 +810,13 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
             col += s.kind == VELA_GP_MARGINALIZED_TM ? s.n : 2 * s.n;
             gps.push_back(gd);
         }
-        const int cnb = h->p <= kCholSmallRank ? 8 : 16;
+        h->chol_nb = h->p <= kCholSmallRank ? 8 : 16;
+        if (const char* e = getenv("VELA_B200_CHOL_NB")) h->chol_nb = atoi(e) == 16 ? 16 : 8;
         const int n_r = h->sp.active ? h->sp.n_r : 0;
-        size_t need = chol_smem_doubles(h->p, h->pp, cnb, true, n_r) * sizeof(double);
+        size_t need = chol_smem_doubles(h->p, h->pp, h->chol_nb, true, n_r) * sizeof(double);
         h->chol_smem = need <= 200 * 1024;
-        h->chol_smem_bytes = h->chol_smem ? need : chol_smem_doubles(h->p, h->pp, cnb, false, n_r) * sizeof(double);
+        if (!h->chol_smem) h->chol_nb = 16;   // the global-scratch variant exists for block width 16 only
+        h->chol_smem_bytes = h->chol_smem ? need : chol_smem_doubles(h->p, h->pp, h->chol_nb, false, n_r) * sizeof(double);
     }
 
     // SoA TOA table (+ TOA-only hoists) and the TZR block
