@@ -870,6 +870,14 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 4) chol_fini
                 }
                 for (int j0 = tx; j0 <= min(i1, m - 1); j0 += 32) {
                     const int j1 = j0 + 16;
+                    // the four matrix entries are fetched before the dot products so that their latency (L2 for the
+                    // global-scratch variant) overlaps the FMAs
+                    const bool w00 = j0 <= i0, w01 = j1 <= i0 && j1 < m, w10 = i1 < m && j0 <= i1, w11 = i1 < m && j1 <= i1 && j1 < m;
+                    double* q00 = A + AIDX(k1 + i0, k1 + j0);
+                    double* q01 = A + AIDX(k1 + i0, k1 + j1);
+                    double* q10 = A + AIDX(k1 + i1, k1 + j0);
+                    double* q11 = A + AIDX(k1 + i1, k1 + j1);
+                    const double a00 = w00 ? *q00 : 0.0, a01 = w01 ? *q01 : 0.0, a10 = w10 ? *q10 : 0.0, a11 = w11 ? *q11 : 0.0;
                     double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
 #pragma unroll
                     for (int c = 0; c < NB; ++c) {
@@ -878,12 +886,10 @@ __global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 4) chol_fini
                         s00 += li0[c] * lj0; s01 += li0[c] * lj1;
                         s10 += li1[c] * lj0; s11 += li1[c] * lj1;
                     }
-                    if (j0 <= i0) A[AIDX(k1 + i0, k1 + j0)] -= s00;
-                    if (j1 <= i0 && j1 < m) A[AIDX(k1 + i0, k1 + j1)] -= s01;
-                    if (i1 < m) {
-                        if (j0 <= i1) A[AIDX(k1 + i1, k1 + j0)] -= s10;
-                        if (j1 <= i1 && j1 < m) A[AIDX(k1 + i1, k1 + j1)] -= s11;
-                    }
+                    if (w00) *q00 = a00 - s00;
+                    if (w01) *q01 = a01 - s01;
+                    if (w10) *q10 = a10 - s10;
+                    if (w11) *q11 = a11 - s11;
                 }
             }
         }
