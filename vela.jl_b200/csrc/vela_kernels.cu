@@ -704,7 +704,7 @@ __device__ __forceinline__ void factor_diag_block_warp(double* A, int lda, int k
 // the panel solve turns it into z = L^-1 u and the trailing update leaves -z.z in entry (p, p), so there is no
 // separate forward solve.  Three block barriers per block of 8 columns instead of five per column.
 template <int NB, bool PACKED>
-__global__ void __launch_bounds__(kCholLaunchThreads, NB <= 8 ? 6 : 4) chol_finish_kernel(CholArgs a) {
+__global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, NB <= 8 ? 6 : 2) chol_finish_kernel(CholArgs a) {
     extern __shared__ double smem[];
     __shared__ double scratch[kCholThreads / 32];
     __shared__ int sFail;
