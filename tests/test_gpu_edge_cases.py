@@ -136,3 +136,17 @@ def test_api_function_mirrors(vb, golden):
     assert vb.calc_lnpost(psr, parv) == vb.calc_lnpost_vectorized(psr, paramss)[0]
     cube = np.full(len(parv), 0.5)
     assert np.isfinite(vb.calc_lnprior(psr, vb.prior_transform(psr, cube)))
+
+
+@pytest.mark.parametrize("name,ntoa", [("config3_gp", 800), ("extra_ecorr_gp", None), ("config2_ell1", 600)])
+def test_batches_larger_than_the_scratch_run_in_passes(name, ntoa, vb, monkeypatch):
+    """Host batches beyond the per-pass scratch budget are processed in passes (forced here with a 128-walker chunk)."""
+    ds = vb.synth.make_dataset(name, lambda m, t: vb.Pulsar(m, t), ntoa=ntoa)
+    W = ds.walkers(700, seed=12)
+    whole = vb.Pulsar(ds.model, ds.toas).lnlike_vectorized(W)
+    monkeypatch.setenv("VELA_B200_MAX_CHUNK", "128")
+    chunked = vb.Pulsar(ds.model, ds.toas)
+    monkeypatch.delenv("VELA_B200_MAX_CHUNK")
+    got = chunked.lnlike_vectorized(W)
+    assert np.all(np.isfinite(got))
+    np.testing.assert_allclose(got, whole, rtol=1e-12)

@@ -899,6 +899,8 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     } else {
         h->max_chunk = 1 << 20;
     }
+    if (const char* e = getenv("VELA_B200_MAX_CHUNK"))   // test hook: force the multi-pass path with a small chunk
+        h->max_chunk = std::max<long>(kSigMaxSamples, std::min<long>(h->max_chunk, round_up(atol(e), kSigMaxSamples)));
     *out = h;
     return VELA_OK;
 }
