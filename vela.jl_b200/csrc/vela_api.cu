@@ -315,9 +315,13 @@ void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t
     EcorrBasisArgs ba;
     ba.M = d.M; ba.ldM = d.ldM; ba.rank = h->p; ba.Pext = b.Pext; ba.row = h->prog.row; ba.par_ecorr = h->par_ecorr;
     ba.Y = b.Y; ba.W = b.W; ba.ld_yw = h->n_rows_pad; ba.B = B; ba.groups = d.ecorr_active; ba.n_groups = h->n_eg;
-    ba.groups_per_block = 16; ba.V = b.V; ba.g_pad = h->eg_pad; ba.ldv = h->ldv;
+    ba.groups_per_block = 32; ba.V = b.V; ba.g_pad = h->eg_pad; ba.ldv = h->ldv;
     dim3 grid((unsigned)((h->n_eg + ba.groups_per_block - 1) / ba.groups_per_block), (unsigned)((B + 31) / 32));
-    const size_t sm = ((size_t)32 * (h->p + 1) + 2 * 32 * 33) * sizeof(double);
+    int chunk = kEcorrChunk;
+    auto smem_for = [&](int ch) { return ((size_t)ch * (h->p + 1) + 2 * 32 * (ch + 1)) * sizeof(double); };
+    while (chunk > 8 && smem_for(chunk) > (size_t)200 * 1024) chunk /= 2;
+    ba.chunk = chunk;
+    const size_t sm = smem_for(chunk);
     const int nacc = (h->p + 7) / 8;
     if (nacc <= 8) ecorr_basis_kernel<8><<<grid, 256, sm, st>>>(ba);
     else if (nacc <= 16) ecorr_basis_kernel<16><<<grid, 256, sm, st>>>(ba);

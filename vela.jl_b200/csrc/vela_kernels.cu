@@ -173,63 +173,97 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, doub
 // K2b builds V_b[g] = sqrt(alpha_g) [P_g | r_g] for every walker b; K2c subtracts V_b^T V_b (a per-walker SYRK on the
 // FP64 tensor cores) from the Sigma / u that K3 produced for the white part.
 //
-// K2b: block = 32 walkers x 8 column slices; one pass = the TOAs of one ECORR group (<= 32 at a time) staged in
-// shared memory (M rows, w, y), accumulators in registers, NACC = ceil(columns / 8) per thread.
+// K2b: block = 32 walkers x 8 column slices.  One staging pass brings the TOAs of SEVERAL consecutive ECORR groups
+// (up to `chunk` TOAs: M rows, w, y) into shared memory, then every thread walks the groups of the pass with its
+// accumulators (NACC = ceil(columns / 8)) in registers and writes one V row per group: two block barriers per ~8
+// epochs instead of two per epoch, no padded staging.  A single group longer than the chunk is processed in pieces.
 template <int NACC>
-__global__ void __launch_bounds__(256) ecorr_basis_kernel(EcorrBasisArgs a) {
+__global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) ecorr_basis_kernel(EcorrBasisArgs a) {
     extern __shared__ double smem[];
+    const int CH = a.chunk;                       // TOAs per staging pass (64, or less when the rank is large)
     const int p = a.rank, pc = p + 1;            // smem row pitch (odd -> conflict-free)
-    double* sM = smem;                            // [32 TOAs][pc]
-    double* sW = sM + 32 * pc;                    // [32 walkers][33]
-    double* sY = sW + 32 * 33;
+    double* sM = smem;                            // [CH TOAs][pc]
+    double* sW = sM + CH * pc;                    // [32 walkers][CH + 1]
+    double* sY = sW + 32 * (CH + 1);
     const int tid = threadIdx.x, s = tid >> 3, c = tid & 7;
     const long b0 = (long)blockIdx.y * 32;
     const long b = b0 + s;
     const bool live = b < a.B;
     const int g_begin = blockIdx.x * a.groups_per_block, g_end = min(g_begin + a.groups_per_block, a.n_groups);
-    for (int g = g_begin; g < g_end; ++g) {
-        const int3 grp = a.groups[g];             // [first, last) TOA, ECORR index >= 1
-        double acc[NACC];
+
+    auto stage = [&](int t0, int nj) {            // TOAs [t0, t0 + nj) -> shared memory
+        __syncthreads();
+        for (int e = tid; e < p * CH; e += 256) {
+            const int col = e / CH, i = e - col * CH;
+            if (i < nj) sM[i * pc + col] = a.M[(size_t)col * a.ldM + t0 + i];
+        }
+        for (int e = tid; e < 32 * CH; e += 256) {
+            const int ss = e / CH, i = e - ss * CH;
+            if (i < nj) {
+                const bool ok = b0 + ss < a.B;
+                sW[ss * (CH + 1) + i] = ok ? a.W[(size_t)(b0 + ss) * a.ld_yw + t0 + i] : 0.0;
+                sY[ss * (CH + 1) + i] = ok ? a.Y[(size_t)(b0 + ss) * a.ld_yw + t0 + i] : 0.0;
+            }
+        }
+        __syncthreads();
+    };
+    double acc[NACC];
+    double Q, ru;
+    auto reset = [&]() {
 #pragma unroll
         for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-        double Q = 0.0, ru = 0.0;
-        for (int j0 = grp.x; j0 < grp.y; j0 += 32) {
-            const int nj = min(32, grp.y - j0);
-            __syncthreads();
-            for (int e = tid; e < p * 32; e += 256) {
-                int col = e >> 5, i = e & 31;
-                sM[i * pc + col] = i < nj ? a.M[(size_t)col * a.ldM + j0 + i] : 0.0;
-            }
-            for (int e = tid; e < 32 * 32; e += 256) {
-                int ss = e >> 5, i = e & 31;
-                bool ok = i < nj && b0 + ss < a.B;
-                sW[ss * 33 + i] = ok ? a.W[(size_t)(b0 + ss) * a.ld_yw + j0 + i] : 0.0;
-                sY[ss * 33 + i] = ok ? a.Y[(size_t)(b0 + ss) * a.ld_yw + j0 + i] : 0.0;
-            }
-            __syncthreads();
-            for (int i = 0; i < nj; ++i) {
-                const double w = sW[s * 33 + i];
-                Q += w;
-                ru += w * sY[s * 33 + i];
-#pragma unroll
-                for (int k = 0; k < NACC; ++k) {
-                    int col = c + 8 * k;
-                    if (col < p) acc[k] += sM[i * pc + col] * w;
-                }
-            }
-        }
-        if (live) {
-            const double ecorr = a.Pext[(size_t)b * a.row + a.par_ecorr + grp.z - 1];
-            const double wt = ecorr * ecorr;
-            const double sa = sqrt(wt / (1 + wt * Q));
-            double* v = a.V + ((size_t)b * a.g_pad + g) * a.ldv;
+        Q = 0.0; ru = 0.0;
+    };
+    auto accumulate = [&](int i0, int i1) {        // staged TOAs [i0, i1)
+        for (int i = i0; i < i1; ++i) {
+            const double w = sW[s * (CH + 1) + i];
+            Q += w;
+            ru += w * sY[s * (CH + 1) + i];
 #pragma unroll
             for (int k = 0; k < NACC; ++k) {
-                int col = c + 8 * k;
-                if (col < p) v[col] = sa * acc[k];
+                const int col = c + 8 * k;
+                if (col < p) acc[k] += sM[i * pc + col] * w;
             }
-            if (c == 0) v[p] = sa * ru;
         }
+    };
+    auto flush = [&](int g, int ecorr_index) {
+        if (!live) return;
+        const double ecorr = a.Pext[(size_t)b * a.row + a.par_ecorr + ecorr_index - 1];
+        const double wt = ecorr * ecorr;
+        const double sa = sqrt(wt / (1 + wt * Q));
+        double* v = a.V + ((size_t)b * a.g_pad + g) * a.ldv;
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+            const int col = c + 8 * k;
+            if (col < p) v[col] = sa * acc[k];
+        }
+        if (c == 0) v[p] = sa * ru;
+    };
+
+    int g = g_begin;
+    while (g < g_end) {
+        const int3 first = a.groups[g];            // [first, last) TOA, ECORR index >= 1
+        if (first.y - first.x > CH) {              // one long group: pieces of CH TOAs
+            reset();
+            for (int j0 = first.x; j0 < first.y; j0 += CH) {
+                const int nj = min(CH, first.y - j0);
+                stage(j0, nj);
+                accumulate(0, nj);
+            }
+            flush(g, first.z);
+            ++g;
+            continue;
+        }
+        int ge = g;                                // last group of this pass: the span first.x .. groups[ge].y fits
+        while (ge + 1 < g_end && a.groups[ge + 1].y - first.x <= CH) ++ge;
+        stage(first.x, a.groups[ge].y - first.x);
+        for (int gg = g; gg <= ge; ++gg) {
+            const int3 grp = a.groups[gg];
+            reset();
+            accumulate(grp.x - first.x, grp.y - first.x);
+            flush(gg, grp.z);
+        }
+        g = ge + 1;
     }
 }
 template __global__ void ecorr_basis_kernel<8>(EcorrBasisArgs);

@@ -8,6 +8,7 @@ namespace vela {
 constexpr int kSigMaxSamples = 64;  // walkers per CTA: 8 x (n-tiles per warp)
 constexpr int kSigMaxRank = 1024;
 
+constexpr int kEcorrChunk = 64;         // TOAs staged per pass of the ECORR basis kernel
 constexpr int kCholThreads = 256;        // sizing of the per-warp scratch
 constexpr int kCholLaunchThreads = 128;  // threads per walker CTA (measured best across ranks 60..300)
 
@@ -89,6 +90,7 @@ struct EcorrBasisArgs {
     const int3* groups;        // ECORR-active groups only (index >= 1)
     int n_groups;
     int groups_per_block;
+    int chunk;                 // TOAs staged per pass (kEcorrChunk unless the rank is too large for shared memory)
     double* V;                 // [B][g_pad][ldv]: sqrt(alpha_g) [P_g | r_g | 0...]
     long g_pad;
     long ldv;
