@@ -331,8 +331,12 @@ void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t
     sa.V = b.V; sa.g_pad = h->eg_pad; sa.ldv = h->ldv; sa.rank = h->p; sa.n_rect = h->n_rect; sa.B = B;
     sa.Sig = b.Sig; sa.ld_sig = h->ld_sig; sa.U = b.U; sa.ld_u = h->pp;
     if (h->sp.active) { sa.U = b.R + h->sp.n_r; sa.ld_u = h->sp.n_cols; }   // u lives behind the column sums
-    const long warps = B * h->n_rect;
-    ecorr_syrk_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(sa);
+    if (h->ldv == 64 && !getenv("VELA_B200_ECORR_SYRK_RECT")) {
+        ecorr_syrk64_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(sa);   // one warp per walker
+    } else {
+        const long warps = B * h->n_rect;
+        ecorr_syrk_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(sa);
+    }
     h->launches += 2;
 }
 

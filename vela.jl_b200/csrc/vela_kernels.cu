@@ -320,6 +320,47 @@ __global__ void __launch_bounds__(256) ecorr_syrk_kernel(EcorrSyrkArgs a) {
             }
 }
 
+// K2c for ranks up to 63: one warp = one walker holds the whole lower triangle of the 64 x 64 product (36 m8n8k4
+// tiles = 72 accumulators), so V is read exactly once and no diagonal rectangle computes its upper half; the A
+// fragment of tile row t and the B fragment of tile column t are the same registers, and the fragments of the next
+// four groups are fetched before the 36 DMMAs of the current four are issued.
+__global__ void __launch_bounds__(128) ecorr_syrk64_kernel(EcorrSyrkArgs a) {
+    const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    const long b = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= a.B) return;
+    const double* V = a.V + (size_t)b * a.g_pad * a.ldv + (size_t)tig * a.ldv + gid;
+    double acc[36][2];
+#pragma unroll
+    for (int t = 0; t < 36; ++t) acc[t][0] = acc[t][1] = 0.0;
+    double f[8], fn[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) f[t] = V[t * 8];
+    for (long g0 = 0; g0 < a.g_pad; g0 += 4) {
+        const double* nxt = V + (size_t)(g0 + 4 < a.g_pad ? g0 + 4 : g0) * a.ldv;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) fn[t] = nxt[t * 8];
+#pragma unroll
+        for (int tr = 0; tr < 8; ++tr)
+#pragma unroll
+            for (int tc = 0; tc <= tr; ++tc) dmma8x8x4(acc[tr * (tr + 1) / 2 + tc][0], acc[tr * (tr + 1) / 2 + tc][1], f[tr], f[tc]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) f[t] = fn[t];
+    }
+    const int p = a.rank;
+    double* sig = a.Sig + (size_t)b * a.ld_sig;
+    double* u = a.U + (size_t)b * a.ld_u;
+#pragma unroll
+    for (int tr = 0; tr < 8; ++tr)
+#pragma unroll
+        for (int tc = 0; tc <= tr; ++tc)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int pp = tr * 8 + gid, qq = tc * 8 + 2 * tig + r;
+                if (pp < p && qq <= pp) sig[(size_t)pp * (pp + 1) / 2 + qq] -= acc[tr * (tr + 1) / 2 + tc][r];
+                else if (pp == p && qq < p) u[qq] -= acc[tr * (tr + 1) / 2 + tc][r];
+            }
+}
+
 // ------------------------------------------------------------------------------------------
 // K3  Sigma^-1 contraction on the FP64 tensor cores
 // ------------------------------------------------------------------------------------------

@@ -156,6 +156,7 @@ __global__ void ecorr_group_kernel(EcorrArgs a);
 template <int NACC>
 __global__ void ecorr_basis_kernel(EcorrBasisArgs a);
 __global__ void ecorr_syrk_kernel(EcorrSyrkArgs a);
+__global__ void ecorr_syrk64_kernel(EcorrSyrkArgs a);   // ranks <= 63 (ldv == 64)
 __global__ void finish_white_kernel(const double* partial, int n_tiles, long B, int mode, const double* lnprior,
                                     int with_prior, double* out);
 template <int BK, int STAGES, int MT, int NT, int WARPS>
