@@ -173,6 +173,14 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, doub
 // K2b builds V_b[g] = sqrt(alpha_g) [P_g | r_g] for every walker b; K2c subtracts V_b^T V_b (a per-walker SYRK on the
 // FP64 tensor cores) from the Sigma / u that K3 produced for the white part.
 //
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 // K2b: block = 32 walkers x 8 column slices.  One staging pass brings the TOAs of SEVERAL consecutive ECORR groups
 // (up to `chunk` TOAs: M rows, w, y) into shared memory, then every thread walks the groups of the pass with its
 // accumulators (NACC = ceil(columns / 8)) in registers and writes one V row per group: two block barriers per ~8
@@ -193,18 +201,20 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
 
     auto stage = [&](int t0, int nj) {            // TOAs [t0, t0 + nj) -> shared memory
         __syncthreads();
+        // asynchronous 8-byte copies: every load of the pass is in flight at once and none occupies a register
         for (int e = tid; e < p * CH; e += 256) {
             const int col = e / CH, i = e - col * CH;
-            if (i < nj) sM[i * pc + col] = a.M[(size_t)col * a.ldM + t0 + i];
+            if (i < nj) cp_async8(&sM[i * pc + col], &a.M[(size_t)col * a.ldM + t0 + i]);
         }
         for (int e = tid; e < 32 * CH; e += 256) {
             const int ss = e / CH, i = e - ss * CH;
             if (i < nj) {
-                const bool ok = b0 + ss < a.B;
-                sW[ss * (CH + 1) + i] = ok ? a.W[(size_t)(b0 + ss) * a.ld_yw + t0 + i] : 0.0;
-                sY[ss * (CH + 1) + i] = ok ? a.Y[(size_t)(b0 + ss) * a.ld_yw + t0 + i] : 0.0;
+                const long br = min(b0 + ss, a.B - 1);    // rows past the batch repeat the last walker (never stored)
+                cp_async8(&sW[ss * (CH + 1) + i], &a.W[(size_t)br * a.ld_yw + t0 + i]);
+                cp_async8(&sY[ss * (CH + 1) + i], &a.Y[(size_t)br * a.ld_yw + t0 + i]);
             }
         }
+        cp_async_commit_wait_all();
         __syncthreads();
     };
     double acc[NACC];
