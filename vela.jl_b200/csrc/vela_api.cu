@@ -310,9 +310,10 @@ int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool w
 }
 
 // WoodburyKernel{EcorrKernel}: subtract the per-group Sherman-Morrison terms from slab 0 of Sigma / U (K2b + K2c).
-void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st) {
+void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool wy) {
     Buffers& b = d.buf;
     EcorrBasisArgs ba;
+    ba.y_is_wy = wy ? 1 : 0;
     ba.M = d.M; ba.ldM = d.ldM; ba.rank = h->p; ba.Pext = b.Pext; ba.row = h->prog.row; ba.par_ecorr = h->par_ecorr;
     ba.Y = b.Y; ba.W = b.W; ba.ld_yw = h->n_rows_pad; ba.B = B; ba.groups = d.ecorr_active; ba.n_groups = h->n_eg;
     ba.groups_per_block = 32; ba.V = b.V; ba.g_pad = h->eg_pad; ba.ldv = h->ldv;
@@ -434,7 +435,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
     int group = h->chain_group;
     while (group > 4 && (long)h->n_tiles * ((B + group - 1) / group) < 3L * d.n_sm) group /= 2;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = B; ca.group = group;
-    const bool wy = woodbury && h->sp.active && !ecorr;   // Y carries w.y for the structured contraction
+    const bool wy = woodbury && h->sp.active;   // Y carries w.y for the structured contraction (the ECORR kernels take it too)
     ca.emit = wy ? 3 : ((woodbury || ecorr) ? 1 : 0); ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     const int warps = h->chain_threads / 32;
     size_t chain_smem = ((size_t)group * pg.row + 2 * group + (size_t)warps * group * 3) * sizeof(double);
@@ -445,7 +446,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         EcorrArgs ea;
         ea.Pext = b.Pext; ea.row = pg.row; ea.Y = b.Y; ea.W = b.W; ea.ld_yw = h->n_rows_pad; ea.B = B;
         ea.groups = d.ecorr_groups; ea.chunk_start = d.ecorr_chunks; ea.par_ecorr = h->par_ecorr;
-        ea.first_row = h->n_tiles; ea.partial = b.partial;
+        ea.first_row = h->n_tiles; ea.partial = b.partial; ea.y_is_wy = wy ? 1 : 0;
         ecorr_group_kernel<<<dim3((unsigned)((B + 127) / 128), (unsigned)h->n_ecorr_chunks), 128, 0, st>>>(ea);
         h->launches += 1;
     }
@@ -464,11 +465,11 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
             ksplit = launch_colsum(h, d, B, st, wy, &cs);
             if (h->n_eg > 0) {   // the ECORR correction is accumulated into a zeroed packed triangle that K4 adds
                 cudaMemsetAsync(b.Sig, 0, (size_t)B * h->ld_sig * sizeof(double), st);
-                launch_ecorr_correction(h, d, B, st);
+                launch_ecorr_correction(h, d, B, st, wy);
             }
         } else {
             ksplit = launch_sigma(h, d, B, st, &sa);
-            if (h->n_eg > 0) launch_ecorr_correction(h, d, B, st);
+            if (h->n_eg > 0) launch_ecorr_correction(h, d, B, st, false);
         }
         if (timing) cudaEventRecord(d.ev[3], st);
         CholArgs ch;
@@ -1220,7 +1221,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     launch_prologue(h, d, b.params, 1, d.stream);
     ChainArgs ca;
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
-    const bool wy = h->sp.active && h->n_ecorr_groups == 0;
+    const bool wy = h->sp.active;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = wy ? 3 : 1;
     ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 3) * sizeof(double);
@@ -1232,7 +1233,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
         const int ksplit = launch_colsum(h, d, 1, d.stream, wy, &cs);
         if (h->n_eg > 0) {
             cudaMemsetAsync(b.Sig, 0, (size_t)h->ld_sig * sizeof(double), d.stream);
-            launch_ecorr_correction(h, d, 1, d.stream);
+            launch_ecorr_correction(h, d, 1, d.stream, wy);
             cudaMemcpyAsync(S.data(), b.Sig, sizeof(double) * S.size(), cudaMemcpyDeviceToHost, d.stream);
         }
         std::vector<double> R(h->sp.n_cols, 0.0), tR(h->sp.n_cols);
@@ -1251,7 +1252,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     } else {
         SigmaArgs sa;
         const int ksplit = launch_sigma(h, d, 1, d.stream, &sa);
-        if (h->n_eg > 0) launch_ecorr_correction(h, d, 1, d.stream);
+        if (h->n_eg > 0) launch_ecorr_correction(h, d, 1, d.stream, false);
         std::vector<double> tS((size_t)h->ld_sig), tU(h->pp);
         for (int z = 0; z < ksplit; ++z) {   // sum the split-K slabs in slice order, as K4 does
             cudaMemcpyAsync(tS.data(), b.Sig + (size_t)z * sa.split_stride_sig, sizeof(double) * tS.size(), cudaMemcpyDeviceToHost, d.stream);

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128) ecorr_group_kernel(EcorrArgs a) {
         double r_u = 0.0, u_u = 0.0;
         for (int j = grp.x; j < grp.y; ++j) {
             const double wj = w[j];
-            r_u += y[j] * wj;
+            r_u += a.y_is_wy ? y[j] : y[j] * wj;
             u_u += wj;
         }
         const double denom = 1 + wt * u_u;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
         for (int i = i0; i < i1; ++i) {
             const double w = sW[s * (CH + 1) + i];
             Q += w;
-            ru += w * sY[s * (CH + 1) + i];
+            ru += a.y_is_wy ? sY[s * (CH + 1) + i] : w * sY[s * (CH + 1) + i];
 #pragma unroll
             for (int k = 0; k < NACC; ++k) {
                 const int col = c + 8 * k;

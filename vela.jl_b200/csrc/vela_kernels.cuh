@@ -74,6 +74,7 @@ struct EcorrArgs {
     int par_ecorr;
     int first_row;             // first `partial` row owned by the ECORR corrections (= number of TOA tiles)
     double* partial;
+    int y_is_wy;               // the Y buffer holds w.y (ChainArgs::emit == 3)
 };
 
 struct EcorrBasisArgs {
@@ -91,6 +92,7 @@ struct EcorrBasisArgs {
     int n_groups;
     int groups_per_block;
     int chunk;                 // TOAs staged per pass (kEcorrChunk unless the rank is too large for shared memory)
+    int y_is_wy;               // the Y buffer holds w.y (ChainArgs::emit == 3)
     double* V;                 // [B][g_pad][ldv]: sqrt(alpha_g) [P_g | r_g | 0...]
     long g_pad;
     long ldv;
