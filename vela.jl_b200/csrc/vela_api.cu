@@ -140,7 +140,7 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
     CU(cudaMalloc((void**)&b.params, (size_t)cap * std::max(pg.n_free, 1) * sizeof(double)));
     CU(cudaMalloc((void**)&b.Pext, (size_t)cap * pg.row * sizeof(double)));
     CU(cudaMalloc((void**)&b.tzr, (size_t)cap * 2 * sizeof(double)));
-    CU(cudaMalloc((void**)&b.partial, (size_t)(h->n_tiles + h->n_ecorr_chunks) * cap * 2 * sizeof(double)));
+    CU(cudaMalloc((void**)&b.partial, (size_t)(h->n_tiles + std::max(h->n_ecorr_chunks, (h->n_eg + 31) / 32)) * cap * 2 * sizeof(double)));
     CU(cudaMalloc((void**)&b.out, (size_t)cap * sizeof(double)));
     CU(cudaMalloc((void**)&b.lnprior, (size_t)cap * sizeof(double)));
     if (h->kernel_kind != VELA_KERNEL_WHITE) {   // every kernel but the plain white one needs y, w
@@ -310,10 +310,13 @@ int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool w
 }
 
 // WoodburyKernel{EcorrKernel}: subtract the per-group Sherman-Morrison terms from slab 0 of Sigma / U (K2b + K2c).
-void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool wy) {
+// K2b also emits the scalar ECORR corrections (one `partial` row per group block, after the TOA tiles); returns the
+// number of those rows.
+int launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool wy) {
     Buffers& b = d.buf;
     EcorrBasisArgs ba;
     ba.y_is_wy = wy ? 1 : 0;
+    ba.partial = b.partial; ba.first_row = h->n_tiles;
     ba.M = d.M; ba.ldM = d.ldM; ba.rank = h->p; ba.Pext = b.Pext; ba.row = h->prog.row; ba.par_ecorr = h->par_ecorr;
     ba.Y = b.Y; ba.W = b.W; ba.ld_yw = h->n_rows_pad; ba.B = B; ba.groups = d.ecorr_active; ba.n_groups = h->n_eg;
     ba.groups_per_block = 32; ba.V = b.V; ba.g_pad = h->eg_pad; ba.ldv = h->ldv;
@@ -339,6 +342,7 @@ void launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t
         ecorr_syrk_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(sa);
     }
     h->launches += 2;
+    return (int)grid.x;
 }
 
 // Fills the launch arguments, plans (row-tile height, split-K) and launches K3; returns the split count K4 has to sum.
@@ -442,7 +446,9 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
     dim3 cgrid((unsigned)h->n_tiles, (unsigned)((B + group - 1) / group));
     launch_chain(h, cgrid, chain_smem, st, ca);
     h->launches += 2;
-    if (ecorr) {
+    // Woodbury + active ECORR groups: the basis kernel of the correction (K2b) produces the scalar terms as well
+    const bool scalars_from_k2b = woodbury && h->n_eg > 0;
+    if (ecorr && !scalars_from_k2b) {
         EcorrArgs ea;
         ea.Pext = b.Pext; ea.row = pg.row; ea.Y = b.Y; ea.W = b.W; ea.ld_yw = h->n_rows_pad; ea.B = B;
         ea.groups = d.ecorr_groups; ea.chunk_start = d.ecorr_chunks; ea.par_ecorr = h->par_ecorr;
@@ -451,7 +457,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         h->launches += 1;
     }
     if (timing) cudaEventRecord(d.ev[2], st);
-    const int n_rows_partial = h->n_tiles + h->n_ecorr_chunks;
+    int n_rows_partial = h->n_tiles + (scalars_from_k2b ? 0 : h->n_ecorr_chunks);
     if (!woodbury) {
         finish_white_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(b.partial, n_rows_partial, B, mode, d_lnprior,
                                                                          with_prior, d_out);
@@ -465,11 +471,11 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
             ksplit = launch_colsum(h, d, B, st, wy, &cs);
             if (h->n_eg > 0) {   // the ECORR correction is accumulated into a zeroed packed triangle that K4 adds
                 cudaMemsetAsync(b.Sig, 0, (size_t)B * h->ld_sig * sizeof(double), st);
-                launch_ecorr_correction(h, d, B, st, wy);
+                n_rows_partial += launch_ecorr_correction(h, d, B, st, wy);
             }
         } else {
             ksplit = launch_sigma(h, d, B, st, &sa);
-            if (h->n_eg > 0) launch_ecorr_correction(h, d, B, st, false);
+            if (h->n_eg > 0) n_rows_partial += launch_ecorr_correction(h, d, B, st, false);
         }
         if (timing) cudaEventRecord(d.ev[3], st);
         CholArgs ch;

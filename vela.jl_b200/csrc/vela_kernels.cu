@@ -236,11 +236,17 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
             }
         }
     };
+    double dchi = 0.0, dlg = 0.0;                  // scalar corrections of this block's groups (slice 0 only)
     auto flush = [&](int g, int ecorr_index) {
         if (!live) return;
         const double ecorr = a.Pext[(size_t)b * a.row + a.par_ecorr + ecorr_index - 1];
         const double wt = ecorr * ecorr;
         const double sa = sqrt(wt / (1 + wt * Q));
+        if (c == 0 && a.partial) {                 // ecorr_likelihood.jl:8-76 terms of this group
+            const double denom = 1 + wt * Q;
+            dchi -= wt * ru * ru / denom;
+            dlg += log(denom);
+        }
         double* v = a.V + ((size_t)b * a.g_pad + g) * a.ldv;
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
@@ -274,6 +280,11 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
             flush(gg, grp.z);
         }
         g = ge + 1;
+    }
+    if (c == 0 && live && a.partial) {
+        double* out = a.partial + ((size_t)(a.first_row + blockIdx.x) * a.B + b) * 2;
+        out[0] = dchi;
+        out[1] = dlg;
     }
 }
 template __global__ void ecorr_basis_kernel<8>(EcorrBasisArgs);

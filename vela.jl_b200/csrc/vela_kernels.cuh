@@ -93,6 +93,8 @@ struct EcorrBasisArgs {
     int groups_per_block;
     int chunk;                 // TOAs staged per pass (kEcorrChunk unless the rank is too large for shared memory)
     int y_is_wy;               // the Y buffer holds w.y (ChainArgs::emit == 3)
+    double* partial;           // when set: the scalar ECORR corrections (chi^2, log det) of this block's groups go to
+    int first_row;             //   partial[first_row + blockIdx.x][b][2] and ecorr_group_kernel is not needed
     double* V;                 // [B][g_pad][ldv]: sqrt(alpha_g) [P_g | r_g | 0...]
     long g_pad;
     long ldv;
