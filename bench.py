@@ -253,7 +253,7 @@ def main():
 
     # ---- end-to-end timing through the public host API (`e2e`)
     def step_e2e(i):
-        out = psr.lnpost_vectorized(host_sets[i % n_sets])     # host prior + pinned staging + H2D + kernels + D2H
+        out = psr.lnpost_vectorized(host_sets[i % n_sets])     # pinned staging (priors on the device when every family has a device twin, else host prior vector) + H2D + kernels + D2H
         if world > 1:
             dist.all_gather_into_tensor(gathered, torch.from_numpy(out).cuda())
         return out
@@ -360,7 +360,7 @@ def main():
             "config": {"workload": f"{WORKLOAD}: PowerlawRedNoiseGP Woodbury lnpost, 10k TOAs, rank 60, 8192 walkers/GPU",
                        "ntoa": ntoa, "rank": p, "nfree": nd, "walkers_per_gpu": B, "parallelism": f"walker-shard x{world}",
                        "l2": "working set (y, w: 1.3 GB per step) exceeds L2; 4 distinct walker batches rotated"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (nd + 1) * 8 * world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (nd + (0 if psr.device_priors else 1)) * 8 * world),
                     "d2h_bytes_per_step": int(B * 8 * world), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary(),
             "finite_fraction": finite_frac,

@@ -963,13 +963,18 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
             if ((rc = ensure_host_buffers(h, d, n))) break;
             if ((rc = ensure_device_buffers(h, d, n))) break;
             Buffers& b = d.buf;
-            if (rs == nf && cs == 1) memcpy(b.h_params, params + r0[i] * rs, sizeof(double) * n * nf);
-            else
-                for (long r = 0; r < n; ++r)
-                    for (long k = 0; k < nf; ++k) b.h_params[r * nf + k] = params[(r0[i] + r) * rs + k * cs];
             const bool timing = h->stage_timing && i == 0;
             if (timing) cudaEventRecord(d.ev[5], d.stream);
-            cudaMemcpyAsync(b.params, b.h_params, sizeof(double) * n * std::max<long>(nf, 1), cudaMemcpyHostToDevice, d.stream);
+            // staged through pinned memory in slices, so the copy engine works on slice k while the host packs k + 1
+            const long slice = std::max<long>(256, (256 * 1024) / (8 * std::max<long>(nf, 1)));
+            for (long s0 = 0; s0 < n; s0 += slice) {
+                const long m = std::min(slice, n - s0);
+                if (rs == nf && cs == 1) memcpy(b.h_params + s0 * nf, params + (r0[i] + s0) * rs, sizeof(double) * m * nf);
+                else
+                    for (long r = s0; r < s0 + m; ++r)
+                        for (long k = 0; k < nf; ++k) b.h_params[r * nf + k] = params[(r0[i] + r) * rs + k * cs];
+                if (nf > 0) cudaMemcpyAsync(b.params + s0 * nf, b.h_params + s0 * nf, sizeof(double) * m * nf, cudaMemcpyHostToDevice, d.stream);
+            }
             const double* d_lp = nullptr;
             if (with_prior && !lnprior && h->have_priors) {
                 prior_kernel<<<(unsigned)((n + 127) / 128), 128, 0, d.stream>>>(d.priors, (int)nf, b.params, n, 0, b.lnprior);
