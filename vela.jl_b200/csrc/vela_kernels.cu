@@ -188,7 +188,8 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 template <int NACC>
 __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) ecorr_basis_kernel(EcorrBasisArgs a) {
     extern __shared__ double smem[];
-    const int CH = a.chunk;                       // TOAs per staging pass (64, or less when the rank is large)
+    const int CH = a.chunk;                       // TOAs per staging pass: a power of two (64, or less when the rank is large)
+    const int lgCH = 31 - __clz(CH);
     const int p = a.rank, pc = p + 1;            // smem row pitch (odd -> conflict-free)
     double* sM = smem;                            // [CH TOAs][pc]
     double* sW = sM + CH * pc;                    // [32 walkers][CH + 1]
@@ -203,11 +204,11 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
         __syncthreads();
         // asynchronous 8-byte copies: every load of the pass is in flight at once and none occupies a register
         for (int e = tid; e < p * CH; e += 256) {
-            const int col = e / CH, i = e - col * CH;
+            const int col = e >> lgCH, i = e & (CH - 1);
             if (i < nj) cp_async8(&sM[i * pc + col], &a.M[(size_t)col * a.ldM + t0 + i]);
         }
         for (int e = tid; e < 32 * CH; e += 256) {
-            const int ss = e / CH, i = e - ss * CH;
+            const int ss = e >> lgCH, i = e & (CH - 1);
             if (i < nj) {
                 const long br = min(b0 + ss, a.B - 1);    // rows past the batch repeat the last walker (never stored)
                 cp_async8(&sW[ss * (CH + 1) + i], &a.W[(size_t)br * a.ld_yw + t0 + i]);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
 #pragma unroll
             for (int k = 0; k < NACC; ++k) {
                 const int col = c + 8 * k;
-                if (col < p) acc[k] += sM[i * pc + col] * w;
+                if (col < p) acc[k] = fma(sM[i * pc + col], w, acc[k]);   // explicit: the file is built with -fmad=false
             }
         }
     };
@@ -780,7 +781,7 @@ __device__ __forceinline__ void factor_diag_block_warp(double* A, int lda, int k
 #pragma unroll
         for (int q = c + 1; q < NB; ++q) {
             const double lqc = __shfl_sync(0xffffffffu, row[c], q);   // L[q][c]
-            if (lane >= q) row[q] -= row[c] * lqc;
+            if (lane >= q) row[q] = fma(-row[c], lqc, row[q]);
         }
     }
     if (lane < NB) {
@@ -799,6 +800,8 @@ __device__ __forceinline__ void factor_diag_block_warp(double* A, int lda, int k
 // triangle in 2x2 register micro-tiles fed from a shared copy of the panel.  u is carried as an extra matrix row p:
 // the panel solve turns it into z = L^-1 u and the trailing update leaves -z.z in entry (p, p), so there is no
 // separate forward solve.  Three block barriers per block of 8 columns instead of five per column.
+// The dot products are written with fma(): this file is compiled with -fmad=false for the double-double chain, and
+// the factorisation has no reference rounding order to mirror (LAPACK potrf uses fused multiply-adds as well).
 template <int NB, bool PACKED>
 __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, NB <= 8 ? 6 : 2) chol_finish_kernel(CholArgs a) {
     extern __shared__ double smem[];
@@ -842,7 +845,7 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
             if (a.table) {
                 const PairTerm pt = a.table[t];
                 v = pt.c1 * sR[pt.i1];
-                if (pt.c2 != 0.0) v += pt.c2 * sR[pt.i2];
+                if (pt.c2 != 0.0) v = fma(pt.c2, sR[pt.i2], v);
                 if (a.add_sig) v += gA[t];
             } else {
                 v = gA[t];
@@ -919,7 +922,7 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
                     const int m = nb - c - 1;     // trailing block of the tile: entries (r, q), c < q <= r < nb
                     for (int e = tid; e < m * m; e += 32) {
                         const int r = c + 1 + e / m, q = c + 1 + e % m;
-                        if (q <= r) dblk[r * PP + q] -= dblk[r * PP + c] * dblk[q * PP + c];
+                        if (q <= r) dblk[r * PP + q] = fma(-dblk[r * PP + c], dblk[q * PP + c], dblk[r * PP + q]);
                     }
                     __syncwarp();
                 }
@@ -941,7 +944,7 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
                 if (c < nb) {
                     double v = x[c];
 #pragma unroll
-                    for (int q = 0; q < c; ++q) v -= x[q] * dblk[c * PP + q];
+                    for (int q = 0; q < c; ++q) v = fma(-x[q], dblk[c * PP + q], v);
                     x[c] = v * rdiag[c];
                 }
             }
@@ -979,8 +982,8 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
                     for (int c = 0; c < NB; ++c) {
                         const double lj0 = panel[(size_t)j0 * PP + c];
                         const double lj1 = j1 < m ? panel[(size_t)j1 * PP + c] : 0.0;
-                        s00 += li0[c] * lj0; s01 += li0[c] * lj1;
-                        s10 += li1[c] * lj0; s11 += li1[c] * lj1;
+                        s00 = fma(li0[c], lj0, s00); s01 = fma(li0[c], lj1, s01);
+                        s10 = fma(li1[c], lj0, s10); s11 = fma(li1[c], lj1, s11);
                     }
                     if (w00) *q00 = a00 - s00;
                     if (w01) *q01 = a01 - s01;
@@ -1015,7 +1018,7 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
         if (tid == 0) z[k] /= A[AIDX(k, k)];
         __syncthreads();
         const double zk = z[k];
-        for (int i = tid; i < k; i += nt) z[i] -= A[AIDX(k, i)] * zk;
+        for (int i = tid; i < k; i += nt) z[i] = fma(-A[AIDX(k, i)], zk, z[i]);
     }
     __syncthreads();
     const double bad = sFail ? CUDART_NAN : 0.0;
