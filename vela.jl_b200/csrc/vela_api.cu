@@ -323,6 +323,11 @@ int launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t 
     dim3 grid((unsigned)((h->n_eg + ba.groups_per_block - 1) / ba.groups_per_block), (unsigned)((B + 31) / 32));
     int chunk = kEcorrChunk;
     auto smem_for = [&](int ch) { return ((size_t)ch * (h->p + 1) + 2 * 32 * (ch + 1)) * sizeof(double); };
+    // the staging buffer must leave room for the blocks per SM the kernel is compiled for (4 / 2 / 1 by rank): at
+    // rank 60 a 64-TOA pass (64.5 KB) would cap the SM at three blocks; 32 TOAs measured 5.00 vs 5.09 ms
+    const int blocks_per_sm = h->p <= 64 ? 4 : (h->p <= 128 ? 2 : 1);
+    while (chunk > 8 && smem_for(chunk) > (size_t)224 * 1024 / blocks_per_sm) chunk /= 2;
+    if (const char* e = getenv("VELA_B200_ECORR_CHUNK")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64 || v == 128) chunk = v; }
     while (chunk > 8 && smem_for(chunk) > (size_t)200 * 1024) chunk /= 2;
     ba.chunk = chunk;
     const size_t sm = smem_for(chunk);

@@ -237,16 +237,20 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
             }
         }
     };
-    double dchi = 0.0, dlg = 0.0;                  // scalar corrections of this block's groups (slice 0 only)
+    double dchi = 0.0, lman = 1.0;                 // scalar corrections of this block's groups (slice 0 only)
+    int lex = 0;
     auto flush = [&](int g, int ecorr_index) {
         if (!live) return;
         const double ecorr = a.Pext[(size_t)b * a.row + a.par_ecorr + ecorr_index - 1];
         const double wt = ecorr * ecorr;
-        const double sa = sqrt(wt / (1 + wt * Q));
+        const double denom = 1 + wt * Q;
+        const double sa = sqrt(wt / denom);
         if (c == 0 && a.partial) {                 // ecorr_likelihood.jl:8-76 terms of this group
-            const double denom = 1 + wt * Q;
-            dchi -= wt * ru * ru / denom;
-            dlg += log(denom);
+            const double sr = sa * ru;             // wt ru^2 / denom without a second division
+            dchi = fma(-sr, sr, dchi);
+            int ex;                                // log(denom) summed as mantissa product + exponent sum: one
+            lman *= split_mantissa(denom, &ex);    // logarithm per block (<= 32 groups: the product stays >= 2^-32)
+            lex += ex;
         }
         double* v = a.V + ((size_t)b * a.g_pad + g) * a.ldv;
 #pragma unroll
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
     if (c == 0 && live && a.partial) {
         double* out = a.partial + ((size_t)(a.first_row + blockIdx.x) * a.B + b) * 2;
         out[0] = dchi;
-        out[1] = dlg;
+        out[1] = log(lman) + lex * 0.6931471805599453;   // ln 2
     }
 }
 template __global__ void ecorr_basis_kernel<8>(EcorrBasisArgs);
@@ -354,19 +358,22 @@ __global__ void __launch_bounds__(128) ecorr_syrk64_kernel(EcorrSyrkArgs a) {
     double acc[36][2];
 #pragma unroll
     for (int t = 0; t < 36; ++t) acc[t][0] = acc[t][1] = 0.0;
-    double f[8], fn[8];
+    // fragments travel two steps ahead of the DMMAs (eight warps per SM: one step does not cover the HBM latency)
+    double f[8], f1[8], f2[8];
+    const long last = a.g_pad - 4;
+    const double* v1 = V + (size_t)(4 < a.g_pad ? 4 : last) * a.ldv;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) f[t] = V[t * 8];
+    for (int t = 0; t < 8; ++t) { f[t] = V[t * 8]; f1[t] = v1[t * 8]; }
     for (long g0 = 0; g0 < a.g_pad; g0 += 4) {
-        const double* nxt = V + (size_t)(g0 + 4 < a.g_pad ? g0 + 4 : g0) * a.ldv;
+        const double* nxt = V + (size_t)(g0 + 8 < a.g_pad ? g0 + 8 : last) * a.ldv;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) fn[t] = nxt[t * 8];
+        for (int t = 0; t < 8; ++t) f2[t] = nxt[t * 8];
 #pragma unroll
         for (int tr = 0; tr < 8; ++tr)
 #pragma unroll
             for (int tc = 0; tc <= tr; ++tc) dmma8x8x4(acc[tr * (tr + 1) / 2 + tc][0], acc[tr * (tr + 1) / 2 + tc][1], f[tr], f[tc]);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) f[t] = fn[t];
+        for (int t = 0; t < 8; ++t) { f[t] = f1[t]; f1[t] = f2[t]; }
     }
     const int p = a.rank;
     double* sig = a.Sig + (size_t)b * a.ld_sig;
