@@ -322,7 +322,9 @@ int launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t 
     ba.groups_per_block = 32; ba.V = b.V; ba.g_pad = h->eg_pad; ba.ldv = h->ldv;
     dim3 grid((unsigned)((h->n_eg + ba.groups_per_block - 1) / ba.groups_per_block), (unsigned)((B + 31) / 32));
     int chunk = kEcorrChunk;
-    auto smem_for = [&](int ch) { return ((size_t)ch * (h->p + 1) + 2 * 32 * (ch + 1)) * sizeof(double); };
+    const int nacc = (h->p + 7) / 8;
+    const int pitch = nacc <= 8 ? 65 : (nacc <= 16 ? 129 : h->p + 1);   // ecorr_basis_kernel: zero-padded rows up to rank 128
+    auto smem_for = [&](int ch) { return ((size_t)ch * pitch + 2 * 32 * (ch + 1)) * sizeof(double); };
     // the staging buffer must leave room for the blocks per SM the kernel is compiled for (4 / 2 / 1 by rank): at
     // rank 60 a 64-TOA pass (64.5 KB) would cap the SM at three blocks; 32 TOAs measured 5.00 vs 5.09 ms
     const int blocks_per_sm = h->p <= 64 ? 4 : (h->p <= 128 ? 2 : 1);
@@ -331,7 +333,6 @@ int launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t 
     while (chunk > 8 && smem_for(chunk) > (size_t)200 * 1024) chunk /= 2;
     ba.chunk = chunk;
     const size_t sm = smem_for(chunk);
-    const int nacc = (h->p + 7) / 8;
     if (nacc <= 8) ecorr_basis_kernel<8><<<grid, 256, sm, st>>>(ba);
     else if (nacc <= 16) ecorr_basis_kernel<16><<<grid, 256, sm, st>>>(ba);
     else if (nacc <= 40) ecorr_basis_kernel<40><<<grid, 256, sm, st>>>(ba);

@@ -190,7 +190,10 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
     extern __shared__ double smem[];
     const int CH = a.chunk;                       // TOAs per staging pass: a power of two (64, or less when the rank is large)
     const int lgCH = 31 - __clz(CH);
-    const int p = a.rank, pc = p + 1;            // smem row pitch (odd -> conflict-free)
+    // smem row pitch (odd -> conflict-free).  Up to rank 128 the rows are padded with zeros to the 8 * NACC columns the
+    // accumulators cover, so the inner loop carries no column predicate.
+    constexpr bool PADDED = NACC <= 16;
+    const int p = a.rank, pc = PADDED ? 8 * NACC + 1 : p + 1;
     double* sM = smem;                            // [CH TOAs][pc]
     double* sW = sM + CH * pc;                    // [32 walkers][CH + 1]
     double* sY = sW + 32 * (CH + 1);
@@ -218,6 +221,8 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
         cp_async_commit_wait_all();
         __syncthreads();
     };
+    if (PADDED)                                   // the pad columns stay zero: staging writes columns < rank only
+        for (int e = tid; e < CH * pc; e += 256) sM[e] = 0.0;
     double acc[NACC];
     double Q, ru;
     auto reset = [&]() {
@@ -225,16 +230,18 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
         for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
         Q = 0.0; ru = 0.0;
     };
+    const bool y_is_wy = a.y_is_wy != 0;
     auto accumulate = [&](int i0, int i1) {        // staged TOAs [i0, i1)
-        for (int i = i0; i < i1; ++i) {
-            const double w = sW[s * (CH + 1) + i];
+        const double* wrow = sW + s * (CH + 1);
+        const double* yrow = sY + s * (CH + 1);
+        const double* mrow = sM + (size_t)i0 * pc + c;
+        for (int i = i0; i < i1; ++i, mrow += pc) {
+            const double w = wrow[i];
             Q += w;
-            ru += a.y_is_wy ? sY[s * (CH + 1) + i] : w * sY[s * (CH + 1) + i];
+            ru += y_is_wy ? yrow[i] : w * yrow[i];
 #pragma unroll
-            for (int k = 0; k < NACC; ++k) {
-                const int col = c + 8 * k;
-                if (col < p) acc[k] = fma(sM[i * pc + col], w, acc[k]);   // explicit: the file is built with -fmad=false
-            }
+            for (int k = 0; k < NACC; ++k)        // explicit fma: the file is built with -fmad=false
+                if (PADDED || c + 8 * k < p) acc[k] = fma(mrow[8 * k], w, acc[k]);
         }
     };
     double dchi = 0.0, lman = 1.0;                 // scalar corrections of this block's groups (slice 0 only)
@@ -243,8 +250,8 @@ __global__ void __launch_bounds__(256, NACC <= 8 ? 4 : (NACC <= 16 ? 2 : 1)) eco
         if (!live) return;
         const double ecorr = a.Pext[(size_t)b * a.row + a.par_ecorr + ecorr_index - 1];
         const double wt = ecorr * ecorr;
-        const double denom = 1 + wt * Q;
-        const double sa = sqrt(wt / denom);
+        const double denom = fma(wt, Q, 1.0);
+        const double sa = fabs(ecorr) * rsqrt(denom);   // sqrt(wt / denom)
         if (c == 0 && a.partial) {                 // ecorr_likelihood.jl:8-76 terms of this group
             const double sr = sa * ru;             // wt ru^2 / denom without a second division
             dchi = fma(-sr, sr, dchi);
