@@ -852,22 +852,34 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
             }
             __syncthreads();
         }
-        int r = 0, c = tid;
-        while (c > r) { c -= r + 1; ++r; }
-        for (long t = tid; t < n_pairs; t += nt) {
-            double v;
-            if (a.table) {
+        if (PACKED && a.table) {
+            // the packed triangle is indexed by the pair number itself; four table entries in flight per thread
+#pragma unroll 4
+            for (long t = tid; t < n_pairs; t += nt) {
                 const PairTerm pt = a.table[t];
-                v = pt.c1 * sR[pt.i1];
+                double v = pt.c1 * sR[pt.i1];
                 if (pt.c2 != 0.0) v = fma(pt.c2, sR[pt.i2], v);
                 if (a.add_sig) v += gA[t];
-            } else {
-                v = gA[t];
-                for (int zz = 1; zz < a.ksplit; ++zz) v += gA[(size_t)zz * a.split_stride_sig + t];
+                A[t] = v;
             }
-            A[AIDX(r, c)] = v;
-            c += nt;
+        } else {
+            int r = 0, c = tid;
             while (c > r) { c -= r + 1; ++r; }
+            for (long t = tid; t < n_pairs; t += nt) {
+                double v;
+                if (a.table) {
+                    const PairTerm pt = a.table[t];
+                    v = pt.c1 * sR[pt.i1];
+                    if (pt.c2 != 0.0) v = fma(pt.c2, sR[pt.i2], v);
+                    if (a.add_sig) v += gA[t];
+                } else {
+                    v = gA[t];
+                    for (int zz = 1; zz < a.ksplit; ++zz) v += gA[(size_t)zz * a.split_stride_sig + t];
+                }
+                A[AIDX(r, c)] = v;
+                c += nt;
+                while (c > r) { c -= r + 1; ++r; }
+            }
         }
         const double* gU = a.table ? a.R + a.u_off : a.U;
         const long ldu = a.table ? a.ld_r : a.ld_u, su = a.table ? a.split_stride_r : a.split_stride_u;
@@ -1012,13 +1024,16 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
     double ld = 0.0;
     for (int i = tid; i < p; i += nt) ld += log(A[AIDX(i, i)]);
     const double logdetSig = 2 * block_sum(ld, scratch);
+    // y^T N^-1 y and log det N: partial rows of the chain tiles (and ECORR blocks), summed by the whole block
+    double py = 0.0, pl = 0.0;
+    for (int t = tid; t < a.n_tiles; t += nt) {
+        const double2 v = *reinterpret_cast<const double2*>(a.partial + ((size_t)t * a.B + b) * 2);
+        py += v.x;
+        pl += v.y;
+    }
+    const double yNy = block_sum(py, scratch), logdetN = block_sum(pl, scratch);
     if (tid == 0) {
         const double zz = -A[AIDX(p, p)];
-        double yNy = 0.0, logdetN = 0.0;
-        for (int t = 0; t < a.n_tiles; ++t) {
-            yNy += a.partial[((size_t)t * a.B + b) * 2];
-            logdetN += a.partial[((size_t)t * a.B + b) * 2 + 1];
-        }
         double lnl = -0.5 * (yNy - zz + logdetN + logdetPhi + logdetSig);
         if (sFail) lnl = -CUDART_INF;
         a.out[b] = combine_prior(lnl, a.lnprior, b, a.with_prior);
