@@ -13,7 +13,8 @@ CASES = [("config2_ell1", 1500, 96), ("config3_gp", 1200, 96), ("config4_dd_wb",
          ("extra_ell1_fbx", None, 64), ("extra_dd_fbx_wb", None, 64), ("extra_dmjump_bits_wb", None, 64),
          ("extra_ell1h_fd_wavex", None, 48), ("extra_ell1k_swx", None, 48), ("extra_ddk_wb", None, 48),
          ("extra_ddh", None, 48), ("extra_dds", None, 48), ("extra_ecorr", None, 64), ("extra_ecorr_gp", None, 64),
-         ("extra_free_gp", None, 48), ("extra_free_gp_wb", None, 48)]
+         ("extra_free_gp", None, 48), ("extra_free_gp_wb", None, 48), ("extra_ecorr_gp_r80", None, 40),
+         ("extra_ecorr_gp_r140", None, 40)]
 
 
 @pytest.fixture(scope="module")
@@ -48,7 +49,7 @@ def test_residuals_and_lnlike(name, ntoa, nw, datasets, oracle):
 
 
 @pytest.mark.parametrize("name,ntoa", [("config3_gp", 1200), ("config4_dd_wb", 700), ("config5_array", 900),
-                                       ("extra_ecorr_gp", None)])
+                                       ("extra_ecorr_gp", None), ("extra_ecorr_gp_r80", None), ("extra_ecorr_gp_r140", None)])
 def test_sigma_and_u_match_oracle(name, ntoa, datasets, oracle):
     """_calc_Σinv__and__MT_Ninv_y parity (the quantity test_woodbury_kernel.jl:66-76 checks)."""
     ds, psr, md = datasets(name, ntoa)

@@ -10,7 +10,8 @@ from helpers import oracle_eval_factory
                                        ("extra_dmjump_bits_wb", None), ("extra_ell1h_fd_wavex", None),
                                        ("extra_ell1k_swx", None), ("extra_ddk_wb", None), ("extra_ddh", None),
                                        ("extra_dds", None), ("extra_ecorr", None), ("extra_ecorr_gp", None),
-                                       ("extra_free_gp", None), ("extra_free_gp_wb", None)])
+                                       ("extra_free_gp", None), ("extra_free_gp_wb", None), ("extra_ecorr_gp_r80", None),
+                                       ("extra_ecorr_gp_r140", None)])
 def test_datasets_are_phase_connected_and_finite(name, ntoa, vb, oracle):
     ds = vb.synth.make_dataset(name, oracle_eval_factory(vb, oracle), ntoa=ntoa)
     assert ds.info["connect_rms_s"] < 1e-12          # Newton iterations converge far below 1 ns

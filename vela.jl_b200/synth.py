@@ -155,6 +155,9 @@ CONFIGS = {
     # ECORR kernels: epochs of 8 TOAs (one per observing frequency) form the ECORR groups
     "extra_ecorr": dict(ntoa=1600, span_d=3000.0, ecorr=True, nback=3, walkers=256, seed=19),
     "extra_ecorr_gp": dict(ntoa=1600, span_d=3000.0, ecorr=True, red=12, dmgp=10, nback=3, walkers=256, seed=20),
+    # ranks above 64 and above 128: the wider variants of the ECORR correction kernels
+    "extra_ecorr_gp_r80": dict(ntoa=1200, span_d=3000.0, ecorr=True, red=25, dmgp=15, nback=3, walkers=128, seed=23),
+    "extra_ecorr_gp_r140": dict(ntoa=1200, span_d=3000.0, ecorr=True, red=40, dmgp=30, nback=2, walkers=128, seed=24),
     # power-law GPs with free amplitudes as delay components (marginalize_gp_noise=False): (Nlin, Nlog) per GP
     "extra_free_gp": dict(ntoa=900, span_d=3000.0, ured=(6, 2), udm=(5, 0), uchrom=(4, 1), nback=2, walkers=128, seed=22),
     "extra_free_gp_wb": dict(ntoa=700, span_d=2500.0, wideband=True, udm=(6, 1), ured=(4, 0), binary="ELL1", nback=2,
