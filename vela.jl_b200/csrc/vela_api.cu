@@ -102,7 +102,7 @@ struct VelaPulsar {
     int sig_shape = 0;
     size_t sig_smem = 0;
     int chain_threads = 256, chain_group = 32, n_tiles = 0;
-    int n_ecorr_groups = 0, n_ecorr_chunks = 0, par_ecorr = -1;   // EcorrKernel: group corrections occupy partial rows n_tiles..
+    int n_ecorr_groups = 0, n_ecorr_chunks = 0, n_ecorr_rows = 0, par_ecorr = -1;   // EcorrKernel: group corrections occupy partial rows n_tiles..
     int n_eg = 0, n_rect = 0;        // WoodburyKernel{EcorrKernel}: active groups, 32x32 rectangles of the (p+1) triangle
     long eg_pad = 0, ldv = 0;
     bool chol_smem = true;
@@ -140,7 +140,7 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
     CU(cudaMalloc((void**)&b.params, (size_t)cap * std::max(pg.n_free, 1) * sizeof(double)));
     CU(cudaMalloc((void**)&b.Pext, (size_t)cap * pg.row * sizeof(double)));
     CU(cudaMalloc((void**)&b.tzr, (size_t)cap * 2 * sizeof(double)));
-    CU(cudaMalloc((void**)&b.partial, (size_t)(h->n_tiles + std::max(h->n_ecorr_chunks, (h->n_eg + 31) / 32)) * cap * 2 * sizeof(double)));
+    CU(cudaMalloc((void**)&b.partial, (size_t)(h->n_tiles + std::max(h->n_ecorr_rows, (h->n_eg + 31) / 32)) * cap * 2 * sizeof(double)));
     CU(cudaMalloc((void**)&b.out, (size_t)cap * sizeof(double)));
     CU(cudaMalloc((void**)&b.lnprior, (size_t)cap * sizeof(double)));
     if (h->kernel_kind != VELA_KERNEL_WHITE) {   // every kernel but the plain white one needs y, w
@@ -459,11 +459,12 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         ea.Pext = b.Pext; ea.row = pg.row; ea.Y = b.Y; ea.W = b.W; ea.ld_yw = h->n_rows_pad; ea.B = B;
         ea.groups = d.ecorr_groups; ea.chunk_start = d.ecorr_chunks; ea.par_ecorr = h->par_ecorr;
         ea.first_row = h->n_tiles; ea.partial = b.partial; ea.y_is_wy = wy ? 1 : 0;
-        ecorr_group_kernel<<<dim3((unsigned)((B + 127) / 128), (unsigned)h->n_ecorr_chunks), 128, 0, st>>>(ea);
+        ea.n_chunks = h->n_ecorr_chunks;
+        ecorr_group_kernel<<<dim3((unsigned)((B + 7) / 8), (unsigned)h->n_ecorr_rows), 256, 0, st>>>(ea);
         h->launches += 1;
     }
     if (timing) cudaEventRecord(d.ev[2], st);
-    int n_rows_partial = h->n_tiles + (scalars_from_k2b ? 0 : h->n_ecorr_chunks);
+    int n_rows_partial = h->n_tiles + (scalars_from_k2b ? 0 : h->n_ecorr_rows);
     if (!woodbury) {
         finish_white_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(b.partial, n_rows_partial, B, mode, d_lnprior,
                                                                          with_prior, d_out);
@@ -766,20 +767,20 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     std::vector<int> echunks;
     std::vector<int3> eactive;
     if (desc->kernel_kind == VELA_KERNEL_ECORR || desc->kernel_kind == VELA_KERNEL_WOODBURY_ECORR) {
-        // groups without ECORR (index 0) need no correction; the others are packed into chunks of ~64 TOAs per thread
+        // chunks of 32 consecutive groups (one lane per group in ecorr_group_kernel; groups without ECORR, index 0,
+        // need no correction and idle their lane); kEcorrChunksPerRow chunks share a `partial` row
         h->par_ecorr = desc->par_ecorr;
         echunks.push_back(0);
-        long in_chunk = 0;
         for (int g = 0; g < desc->n_ecorr_groups; ++g) {
             const uint64_t* e = desc->ecorr_groups + 3 * g;
             egroups.push_back(make_int3((int)(e[0] - 1), (int)e[1], (int)e[2]));
             if (e[2]) eactive.push_back(egroups.back());
-            in_chunk += e[2] ? (long)(e[1] - e[0] + 1) : 0;
-            if (in_chunk >= 64) { echunks.push_back(g + 1); in_chunk = 0; }
+            if (g + 1 - echunks.back() >= 32) echunks.push_back(g + 1);
         }
         if (echunks.back() != desc->n_ecorr_groups) echunks.push_back(desc->n_ecorr_groups);
         h->n_ecorr_groups = desc->n_ecorr_groups;
         h->n_ecorr_chunks = (int)echunks.size() - 1;
+        h->n_ecorr_rows = (h->n_ecorr_chunks + kEcorrChunksPerRow - 1) / kEcorrChunksPerRow;
     }
     std::vector<GPDev> gps;
     std::vector<double> gp_data;

@@ -132,33 +132,70 @@ __global__ void finish_white_kernel(const double* __restrict__ partial, int n_ti
 // _ecorr_lnlike_group / _ecorr_chi2_group (ecorr_likelihood.jl:8-38, ecorr_chi2.jl:6-30): with r_u = sum_g y w,
 // u_u = sum_g w over the TOAs of an ECORR group and W = ECORR^2, the block-diagonal covariance adds
 //   chi^2   -= W r_u^2 / (1 + W u_u),      log det += log(1 + W u_u)
-// to the white-noise sums the chain kernel already produced.  One thread = one walker x one chunk of consecutive
-// groups; the two corrections are written as extra rows of `partial`, so the finishing kernels need no change.
-__global__ void __launch_bounds__(128) ecorr_group_kernel(EcorrArgs a) {
-    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
-    const int c = blockIdx.y;
+// to the white-noise sums the chain kernel already produced.  One warp = one walker x kEcorrChunksPerRow consecutive
+// chunks (a chunk = 32 consecutive groups): the lanes read the walker's w / y rows in coalesced 64-TOA passes
+// into a per-warp shared buffer, lane g then sums the TOAs of group g of the chunk; the group terms are reduced over
+// the warp (log(1 + W u_u) as a mantissa product and an exponent sum: one logarithm per row) and written as one
+// extra row of `partial`, so the finishing kernels need no change.  (The first version, one thread per walker
+// walking its row alone, read w / y with a stride of one row per lane: 0.6 ms at 10k TOAs x 8192 walkers.)
+__global__ void __launch_bounds__(256) ecorr_group_kernel(EcorrArgs a) {
+    __shared__ double sY[8][64], sW[8][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long b = (long)blockIdx.x * 8 + warp;
+    if (b >= a.B) return;                        // whole warps leave; the kernel uses no block barrier
     const double* P = a.Pext + (size_t)b * a.row;
     const double* y = a.Y + (size_t)b * a.ld_yw;
     const double* w = a.W + (size_t)b * a.ld_yw;
-    double dchi = 0.0, dlg = 0.0;
-    for (int g = a.chunk_start[c]; g < a.chunk_start[c + 1]; ++g) {
-        const int3 grp = a.groups[g];          // first TOA (0-based), one-past-last TOA, ECORR index (0 = none)
-        if (grp.z == 0) continue;
-        const double ecorr = P[a.par_ecorr + grp.z - 1];
-        const double wt = ecorr * ecorr;
-        double r_u = 0.0, u_u = 0.0;
-        for (int j = grp.x; j < grp.y; ++j) {
-            const double wj = w[j];
-            r_u += a.y_is_wy ? y[j] : y[j] * wj;
-            u_u += wj;
+    const bool y_is_wy = a.y_is_wy != 0;
+    double dchi = 0.0, lman = 1.0;
+    int lex = 0;
+    const int c_end = min((int)(blockIdx.y + 1) * kEcorrChunksPerRow, a.n_chunks);
+    for (int c = blockIdx.y * kEcorrChunksPerRow; c < c_end; ++c) {
+        const int g0 = a.chunk_start[c], g1 = a.chunk_start[c + 1];      // g1 - g0 <= 32 (create())
+        int3 grp = make_int3(0x7fffffff, 0, 0);
+        if (g0 + lane < g1) grp = a.groups[g0 + lane];   // first TOA (0-based), one-past-last TOA, ECORR index (0 = none)
+        if (grp.z == 0) grp = make_int3(0x7fffffff, 0, 0);
+        int t0 = grp.x, t1 = grp.y;                      // TOA span of the chunk's active groups
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            t0 = min(t0, __shfl_xor_sync(0xffffffffu, t0, off));
+            t1 = max(t1, __shfl_xor_sync(0xffffffffu, t1, off));
         }
-        const double denom = 1 + wt * u_u;
-        dchi -= wt * r_u * r_u / denom;
-        dlg += log(denom);
+        double r_u = 0.0, u_u = 0.0;
+        for (int p0 = t0; p0 < t1; p0 += 64) {
+            __syncwarp();
+#pragma unroll
+            for (int i = lane; i < 64; i += 32)
+                if (p0 + i < t1) { sY[warp][i] = y[p0 + i]; sW[warp][i] = w[p0 + i]; }
+            __syncwarp();
+            const int lo = max(grp.x, p0), hi = min(grp.y, p0 + 64);
+            for (int j = lo; j < hi; ++j) {
+                const double wj = sW[warp][j - p0];
+                r_u += y_is_wy ? sY[warp][j - p0] : sY[warp][j - p0] * wj;
+                u_u += wj;
+            }
+        }
+        if (grp.z) {
+            const double ecorr = P[a.par_ecorr + grp.z - 1];
+            const double wt = ecorr * ecorr;
+            const double denom = 1 + wt * u_u;
+            dchi -= wt * r_u * r_u / denom;
+            int ex;
+            lman *= split_mantissa(denom, &ex);          // <= kEcorrChunksPerRow mantissas in [1/2, 1) per lane
+            lex += ex;
+        }
     }
-    a.partial[((size_t)(a.first_row + c) * a.B + b) * 2] = dchi;
-    a.partial[((size_t)(a.first_row + c) * a.B + b) * 2 + 1] = dlg;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        dchi += __shfl_xor_sync(0xffffffffu, dchi, off);
+        lman *= __shfl_xor_sync(0xffffffffu, lman, off);
+        lex += __shfl_xor_sync(0xffffffffu, lex, off);
+    }
+    if (lane == 0) {
+        double* out = a.partial + ((size_t)(a.first_row + blockIdx.y) * a.B + b) * 2;
+        out[0] = dchi;
+        out[1] = log(lman) + lex * 0.6931471805599453;   // ln 2
+    }
 }
 
 __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {

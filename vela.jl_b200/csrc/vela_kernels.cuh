@@ -62,6 +62,7 @@ struct PairTerm {
     double c1, c2;
 };
 
+constexpr int kEcorrChunksPerRow = 8;   // chunks one warp of ecorr_group_kernel walks = chunks per `partial` row
 struct EcorrArgs {
     const double* Pext;
     int row;
@@ -70,7 +71,8 @@ struct EcorrArgs {
     long ld_yw;
     long B;
     const int3* groups;        // [n_groups] (first TOA 0-based, one past last, ECORR index)
-    const int* chunk_start;    // [n_chunks + 1] group ranges handled by one thread
+    const int* chunk_start;    // [n_chunks + 1] group ranges (at most 32 groups each)
+    int n_chunks;
     int par_ecorr;
     int first_row;             // first `partial` row owned by the ECORR corrections (= number of TOA tiles)
     double* partial;
