@@ -274,7 +274,10 @@ int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool w
         }
     }
     // emcee-sized batches need deep split-K to cover the SMs: the 16-TOA ring has twice the k-tiles to split over
-    if (wy && si == 3 && cta_cols(shapes[3]) * ((B + 255) / 256) * (h->n_rows_pad / 32 / 8) < 2L * d.n_sm) si = 4;
+    // (config 3, column sums alone: 39 us for any B <= 256, against 54 us with the 32-TOA ring).  Up to 128 walkers the
+    // (8, 2) shape is faster still (21 us): a (2, 8) CTA stages the w rows of 256 walkers whatever the batch holds, and
+    // at these sizes the kernel is bound by that L2 traffic (tools/probes/gpu_small_batch_probe.py)
+    if (wy && si == 3 && cta_cols(shapes[3]) * ((B + 255) / 256) * (h->n_rows_pad / 32 / 8) < 2L * d.n_sm) si = B <= 128 ? 1 : 4;
     if (const char* e = getenv("VELA_B200_COLSUM_SHAPE")) si = std::max(0, std::min(wy ? 4 : 3, atoi(e)));
     const ColsumShape& sh = shapes[si];
     const long n_ktiles = h->n_rows_pad / sh.bk;
