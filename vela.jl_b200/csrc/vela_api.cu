@@ -505,7 +505,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         // 96 threads per walker at full size (more resident walkers, fewer idle warps in the serial phases: 0.41 ->
         // 0.35 ms at rank 60), 128 for small batches and large ranks (tools/probes/gpu_chol_probe.py)
         int chol_threads = (B >= 1024 && h->chol_nb == 8) ? 96 : kCholLaunchThreads;
-        if (const char* e = getenv("VELA_B200_CHOL_THREADS")) chol_threads = std::max(32, std::min(h->chol_nb == 8 ? kCholLaunchThreads : kCholThreads, atoi(e) / 32 * 32));
+        if (const char* e = getenv("VELA_B200_CHOL_THREADS")) chol_threads = std::max(h->chol_nb == 8 ? 64 : 32, std::min(h->chol_nb == 8 ? kCholLaunchThreads : kCholThreads, atoi(e) / 32 * 32));
         (h->chol_nb == 8 && h->chol_smem ? chol_finish_kernel<8, true> : (h->chol_smem ? chol_finish_kernel<16, true> : chol_finish_kernel<16, false>))<<<(unsigned)B, chol_threads, h->chol_smem_bytes, st>>>(ch);
         if (timing) cudaEventRecord(d.ev[4], st);
         h->launches += 2;

@@ -805,6 +805,22 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     return s;
 }
 
+// Sum of one entry over the split-K slabs.  Small batches run the column sums with up to 64 slabs and a single CTA then
+// adds ~16k values: four accumulators and an unrolled body keep 16 L2 loads in flight per thread (the plain loop had 4).
+__device__ __forceinline__ double slab_sum(const double* g, long stride, int n) {
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    int z = 0;
+#pragma unroll 4
+    for (; z + 4 <= n; z += 4) {
+        v0 += g[(size_t)z * stride];
+        v1 += g[(size_t)(z + 1) * stride];
+        v2 += g[(size_t)(z + 2) * stride];
+        v3 += g[(size_t)(z + 3) * stride];
+    }
+    for (; z < n; ++z) v0 += g[(size_t)z * stride];
+    return (v0 + v1) + (v2 + v3);
+}
+
 // Row-packed lower triangle: entry (r, c <= r) of the walker's matrix (rows 0..p, row p = u^T and -z.z)
 __device__ __forceinline__ size_t tri(int r, int c) { return (size_t)r * (r + 1) / 2 + c; }
 
@@ -882,11 +898,7 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
         if (a.table) {
             sR = panel + (size_t)(p + 1) * PP + (PACKED ? n_tri : 0);   // last shared slot
             const double* gR = a.R + (size_t)b * a.ld_r;
-            for (int i = tid; i < a.n_r; i += nt) {
-                double v = gR[i];
-                for (int zz = 1; zz < a.ksplit; ++zz) v += gR[(size_t)zz * a.split_stride_r + i];
-                sR[i] = v;
-            }
+            for (int i = tid; i < a.n_r; i += nt) sR[i] = slab_sum(gR + i, a.split_stride_r, a.ksplit);
             __syncthreads();
         }
         if (PACKED && a.table) {
@@ -910,8 +922,7 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
                     if (pt.c2 != 0.0) v = fma(pt.c2, sR[pt.i2], v);
                     if (a.add_sig) v += gA[t];
                 } else {
-                    v = gA[t];
-                    for (int zz = 1; zz < a.ksplit; ++zz) v += gA[(size_t)zz * a.split_stride_sig + t];
+                    v = slab_sum(gA + t, a.split_stride_sig, a.ksplit);
                 }
                 A[AIDX(r, c)] = v;
                 c += nt;
@@ -920,11 +931,7 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
         }
         const double* gU = a.table ? a.R + a.u_off : a.U;
         const long ldu = a.table ? a.ld_r : a.ld_u, su = a.table ? a.split_stride_r : a.split_stride_u;
-        for (int i = tid; i < p; i += nt) {
-            double v = gU[(size_t)b * ldu + i];
-            for (int zz = 1; zz < a.ksplit; ++zz) v += gU[(size_t)zz * su + (size_t)b * ldu + i];
-            A[AIDX(p, i)] = v;
-        }
+        for (int i = tid; i < p; i += nt) A[AIDX(p, i)] = slab_sum(gU + (size_t)b * ldu + i, su, a.ksplit);
     }
     if (tid == 0) { sFail = 0; A[AIDX(p, p)] = 0.0; }
 
@@ -958,12 +965,17 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
 
     // ---- Cholesky A = L L^T (isposdef + cholesky!, gls_likelihood.jl:211-217) and z = L^-1 u (ldiv!, :220)
     const int n1 = p + 1;                         // matrix rows including the u row
+    // NB <= 8: look-ahead.  Warp 0 factorises the NEXT diagonal block during the trailing update (it first brings that
+    // block up to date itself) while the other warps update the rest, so nobody waits for the serial factorisation and
+    // a block step has two barriers instead of three; only the first block is factorised up front.
+    if constexpr (NB <= 8) {
+        if (tid < 32 && p > 0) factor_diag_block_warp<NB, PACKED>(A, lda, 0, min(NB, p), dblk, rdiag, &sFail);
+        __syncthreads();
+    }
     for (int k0 = 0; k0 < p; k0 += NB) {
         const int nb = min(NB, p - k0), k1 = k0 + nb;
         // (1) diagonal block
-        if constexpr (NB <= 8) {
-            if (tid < 32) factor_diag_block_warp<NB, PACKED>(A, lda, k0, nb, dblk, rdiag, &sFail);
-        } else {
+        if constexpr (NB > 8) {
             for (int e = tid; e < nb * nb; e += nt) {
                 const int r = e / nb, c = e - r * nb;
                 if (c <= r) dblk[r * PP + c] = A[AIDX(k0 + r, k0 + c)];
@@ -994,8 +1006,8 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
                     if (c <= r) A[AIDX(k0 + r, k0 + c)] = dblk[r * PP + c];
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
         // (2) panel: rows k1 .. p (row p is u^T) times L_kk^-T, one thread per row
         for (int i = k1 + tid; i < n1; i += nt) {
             double x[NB];
@@ -1019,10 +1031,24 @@ __global__ void __launch_bounds__(NB <= 8 ? kCholLaunchThreads : kCholThreads, N
         }
         __syncthreads();
         // (3) trailing update A[i][j] -= sum_c L[i][k0+c] L[j][k0+c] for k1 <= j <= i <= p, 2x2 micro-tiles
-        {
-            const int tx = tid & 15, ty = tid >> 4, ny = nt >> 4;
+        const int nbn = NB <= 8 ? max(0, min(NB, p - k1)) : 0;   // rows of the next diagonal block (look-ahead)
+        if (NB <= 8 && tid < 32) {
+            for (int e = tid; e < nbn * (nbn + 1) / 2; e += 32) {
+                int i = 0;
+                while ((i + 1) * (i + 2) / 2 <= e) ++i;
+                const int j = e - i * (i + 1) / 2;
+                double sacc = 0.0;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) sacc = fma(panel[(size_t)i * PP + c], panel[(size_t)j * PP + c], sacc);
+                A[AIDX(k1 + i, k1 + j)] -= sacc;
+            }
+            __syncwarp();
+            if (nbn > 0) factor_diag_block_warp<NB, PACKED>(A, lda, k1, nbn, dblk, rdiag, &sFail);
+        } else {
+            const int wt = NB <= 8 ? tid - 32 : tid, wn = NB <= 8 ? nt - 32 : nt;   // worker index / count
+            const int tx = wt & 15, ty = wt >> 4, ny = wn >> 4;
             const int m = n1 - k1;                // trailing size (rows k1..p)
-            for (int i0 = ty; i0 < m; i0 += 2 * ny) {
+            for (int i0 = nbn + ty; i0 < m; i0 += 2 * ny) {
                 const int i1 = i0 + ny;
                 double li0[NB], li1[NB];
 #pragma unroll
