@@ -150,3 +150,18 @@ def test_batches_larger_than_the_scratch_run_in_passes(name, ntoa, vb, monkeypat
     got = chunked.lnlike_vectorized(W)
     assert np.all(np.isfinite(got))
     np.testing.assert_allclose(got, whole, rtol=1e-12)
+
+
+@pytest.mark.parametrize("chunk", ["4", "8", "64"])
+def test_ecorr_correction_staging_sizes(chunk, vb, monkeypatch):
+    """The ECORR basis kernel stages TOAs in passes: several groups per pass, one group per pass, and (4 TOAs per pass
+    against 8-TOA epochs) groups cut into pieces must all give the same correction."""
+    ds = vb.synth.make_dataset("extra_ecorr_gp", lambda m, t: vb.Pulsar(m, t))
+    psr = vb.Pulsar(ds.model, ds.toas)
+    W = ds.walkers(70, seed=5)
+    ref = psr.lnlike_vectorized(W)
+    monkeypatch.setenv("VELA_B200_ECORR_CHUNK", chunk)
+    got = psr.lnlike_vectorized(W)
+    monkeypatch.delenv("VELA_B200_ECORR_CHUNK")
+    assert np.all(np.isfinite(ref))
+    np.testing.assert_allclose(got, ref, rtol=1e-11)

@@ -332,7 +332,7 @@ int launch_ecorr_correction(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t 
     // rank 60 a 64-TOA pass (64.5 KB) would cap the SM at three blocks; 32 TOAs measured 5.00 vs 5.09 ms
     const int blocks_per_sm = h->p <= 64 ? 4 : (h->p <= 128 ? 2 : 1);
     while (chunk > 8 && smem_for(chunk) > (size_t)224 * 1024 / blocks_per_sm) chunk /= 2;
-    if (const char* e = getenv("VELA_B200_ECORR_CHUNK")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64 || v == 128) chunk = v; }
+    if (const char* e = getenv("VELA_B200_ECORR_CHUNK")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32 || v == 64 || v == 128) chunk = v; }
     while (chunk > 8 && smem_for(chunk) > (size_t)200 * 1024) chunk /= 2;
     ba.chunk = chunk;
     const size_t sm = smem_for(chunk);
