@@ -324,11 +324,11 @@ def main():
              "achieved": tf(p**3 / 3 + p * p + 10 * p, chol_ms), "peak": dfma_peak, "unit": "TFLOP/s"},
         ]
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-        # very step (profiles/r1_ncu_full_config3_v8_final.txt); only valid for the default workload and kernel variants
-        ncu_traffic = {"toa_chain_kernel (per-model NVRTC build)": 0.004255e9 + 1.261794e9,
-                       "colsum_kernel (structured Sigma, FP64 DMMA m8n8k4)": 1.345202e9 + 0.023757e9,
+        # very step (profiles/r1_ncu_full_config3_v9_final.txt); only valid for the default workload and kernel variants
+        ncu_traffic = {"toa_chain_kernel (per-model NVRTC build)": 0.004324e9 + 1.261522e9,
+                       "colsum_kernel (structured Sigma, FP64 DMMA m8n8k4)": 1.344508e9 + 0.026701e9,
                        "sigma_contract_kernel (FP64 DMMA m8n8k4)": 1.532375e9 + 0.116714e9,   # v2b_dense capture
-                       "chol_finish_kernel": 0.049790e9 + 0.000009e9}
+                       "chol_finish_kernel": 0.049809e9 + 0.000072e9}
         for k in kernels:
             k["traffic"] = ncu_traffic.get(k["kernel"]) if (ntoa, p, B) == (10000, 60, 8192) else None
             k["frac"] = (k["achieved"] / k["peak"]) if k["achieved"] and k["peak"] > 0 else None
@@ -339,7 +339,7 @@ def main():
             "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
             "unit": "TFLOP/s", "frac": dom["frac"], "traffic": dom["traffic"],
             "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                              "(profiles/r1_ncu_full_config3_v8_final.txt)",
+                              "(profiles/r1_ncu_full_config3_v9_final.txt)",
             "peak_source": "measured in this run: register-resident FP64 loops (vela_b200_fp64_peak_tflops: DFMA for the "
                            "scalar kernels, mma.sync.m8n8k4.f64 for the DMMA kernels); MEASURED_PEAKS.json holds only "
                            "HBM and bf16 peaks",
