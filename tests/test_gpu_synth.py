@@ -14,7 +14,7 @@ CASES = [("config2_ell1", 1500, 96), ("config3_gp", 1200, 96), ("config4_dd_wb",
          ("extra_ell1h_fd_wavex", None, 48), ("extra_ell1k_swx", None, 48), ("extra_ddk_wb", None, 48),
          ("extra_ddh", None, 48), ("extra_dds", None, 48), ("extra_ecorr", None, 64), ("extra_ecorr_gp", None, 64),
          ("extra_free_gp", None, 48), ("extra_free_gp_wb", None, 48), ("extra_ecorr_gp_r80", None, 40),
-         ("extra_ecorr_gp_r140", None, 40)]
+         ("extra_ecorr_gp_r140", None, 40), ("extra_mtm_only", None, 48)]
 
 
 @pytest.fixture(scope="module")

@@ -11,7 +11,7 @@ from helpers import oracle_eval_factory
                                        ("extra_ell1k_swx", None), ("extra_ddk_wb", None), ("extra_ddh", None),
                                        ("extra_dds", None), ("extra_ecorr", None), ("extra_ecorr_gp", None),
                                        ("extra_free_gp", None), ("extra_free_gp_wb", None), ("extra_ecorr_gp_r80", None),
-                                       ("extra_ecorr_gp_r140", None)])
+                                       ("extra_ecorr_gp_r140", None), ("extra_mtm_only", None)])
 def test_datasets_are_phase_connected_and_finite(name, ntoa, vb, oracle):
     ds = vb.synth.make_dataset(name, oracle_eval_factory(vb, oracle), ntoa=ntoa)
     assert ds.info["connect_rms_s"] < 1e-12          # Newton iterations converge far below 1 ns

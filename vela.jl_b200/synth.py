@@ -155,6 +155,8 @@ CONFIGS = {
     # ECORR kernels: epochs of 8 TOAs (one per observing frequency) form the ECORR groups
     "extra_ecorr": dict(ntoa=1600, span_d=3000.0, ecorr=True, nback=3, walkers=256, seed=19),
     "extra_ecorr_gp": dict(ntoa=1600, span_d=3000.0, ecorr=True, red=12, dmgp=10, nback=3, walkers=256, seed=20),
+    # rank 4 (MarginalizedTimingModel alone): a single, partial block column in the Cholesky finish
+    "extra_mtm_only": dict(ntoa=700, span_d=2500.0, mtm=True, nback=2, walkers=128, seed=25),
     # ranks above 64 and above 128: the wider variants of the ECORR correction kernels
     "extra_ecorr_gp_r80": dict(ntoa=1200, span_d=3000.0, ecorr=True, red=25, dmgp=15, nback=3, walkers=128, seed=23),
     "extra_ecorr_gp_r140": dict(ntoa=1200, span_d=3000.0, ecorr=True, red=40, dmgp=30, nback=2, walkers=128, seed=24),
