@@ -329,8 +329,14 @@ def main():
                        "colsum_kernel (structured Sigma, FP64 DMMA m8n8k4)": 1.344508e9 + 0.026701e9,
                        "sigma_contract_kernel (FP64 DMMA m8n8k4)": 1.532375e9 + 0.116714e9,   # v2b_dense capture
                        "chol_finish_kernel": 0.049809e9 + 0.000072e9}
+        # busy fraction of the bounding pipe from the same capture (sm__pipe_fp64_cycles_active / sm__pipe_tensor_cycles_active,
+        # pct_of_peak_sustained_active): what the hardware counters say next to the algorithmic-FLOP fraction
+        ncu_pipe = {"toa_chain_kernel (per-model NVRTC build)": 0.638,
+                    "colsum_kernel (structured Sigma, FP64 DMMA m8n8k4)": 0.843,
+                    "chol_finish_kernel": 0.202}
         for k in kernels:
             k["traffic"] = ncu_traffic.get(k["kernel"]) if (ntoa, p, B) == (10000, 60, 8192) else None
+            k["pipe_active_ncu"] = ncu_pipe.get(k["kernel"]) if (ntoa, p, B) == (10000, 60, 8192) else None
             k["frac"] = (k["achieved"] / k["peak"]) if k["achieved"] and k["peak"] > 0 else None
             k["share_of_step"] = k["ms"] / float(stage_ms[4]) if stage_ms[4] > 0 else None
         dom = max(kernels, key=lambda k: k["ms"])
