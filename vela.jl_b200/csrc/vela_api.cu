@@ -2,6 +2,7 @@
 // orchestration (streams, pinned staging, walker sharding across devices) and the C ABI of
 // include/vela_b200.h.  There is no CPU compute path in this library.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -9,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "vela_jit.h"
@@ -110,7 +112,7 @@ struct VelaPulsar {
     size_t chol_smem_bytes = 0;
     std::vector<DeviceModel> devs;
     std::mutex mtx;
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};   // several feeder threads when the handle spans several devices
     bool stage_timing = false;
     bool have_priors = false;
     long max_chunk = 0;  // walkers per device per pass
@@ -943,7 +945,7 @@ VELA_API int vela_b200_destroy(VelaHandle h) {
 VELA_API int vela_b200_n_free(VelaHandle h) { return h ? h->prog.n_free : -1; }
 VELA_API int64_t vela_b200_n_rows(VelaHandle h) { return h ? h->n_rows : -1; }
 VELA_API int64_t vela_b200_n_basis(VelaHandle h) { return h ? h->p : -1; }
-VELA_API int64_t vela_b200_launch_count(VelaHandle h) { return h ? h->launches : -1; }
+VELA_API int64_t vela_b200_launch_count(VelaHandle h) { return h ? (int64_t)h->launches.load() : -1; }
 
 static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free, int64_t rs, int64_t cs,
                           const double* lnprior, int with_prior, int mode, double* out) {
@@ -965,13 +967,16 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
         long per = (pass + nd - 1) / nd;
         std::vector<long> r0(nd), r1(nd);
         for (int i = 0; i < nd; ++i) { r0[i] = done + std::min<long>(pass, i * per); r1[i] = done + std::min<long>(pass, (i + 1) * per); }
-        for (int i = 0; i < nd && !rc; ++i) {
+        // one device: this thread; several: one host thread per device, so the pinned staging copies (1.3 MB per device
+        // at config 3, ~0.1 ms each) run side by side instead of delaying device i by i copies
+        auto feed = [&](int i) -> int {
+            int rc = 0;
             DeviceModel& d = h->devs[i];
             long n = r1[i] - r0[i];
-            if (n <= 0) continue;
+            if (n <= 0) return 0;
             cudaSetDevice(d.dev);
-            if ((rc = ensure_host_buffers(h, d, n))) break;
-            if ((rc = ensure_device_buffers(h, d, n))) break;
+            if ((rc = ensure_host_buffers(h, d, n))) return rc;
+            if ((rc = ensure_device_buffers(h, d, n))) return rc;
             Buffers& b = d.buf;
             const bool timing = h->stage_timing && i == 0;
             if (timing) cudaEventRecord(d.ev[5], d.stream);
@@ -997,6 +1002,19 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
             }
             rc = enqueue_batch(h, d, b.params, n, mode, with_prior, d_lp, b.out, d.stream);
             cudaMemcpyAsync(b.h_out, b.out, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
+            return rc;
+        };
+        if (nd == 1) {
+            rc = feed(0);
+        } else {
+            std::vector<int> rcs(nd, 0);
+            std::vector<std::string> msgs(nd);
+            std::vector<std::thread> workers;
+            for (int i = 0; i < nd; ++i)
+                workers.emplace_back([&, i] { rcs[i] = feed(i); if (rcs[i]) msgs[i] = g_last_error; });   // the message is thread-local
+            for (auto& w : workers) w.join();
+            for (int i = 0; i < nd && !rc; ++i)
+                if (rcs[i]) { rc = rcs[i]; g_last_error = msgs[i]; }
         }
         for (int i = 0; i < nd; ++i) {
             DeviceModel& d = h->devs[i];
