@@ -1,0 +1,76 @@
+// emul.cpp - host-side arithmetic check of the chain kernel (TEST INFRASTRUCTURE ONLY).
+//
+// Compiles the product's own device headers (vela_device.cuh, vela_chain.cuh) and host preparation (vela_host_prep.h)
+// with g++ through cuda_shim.h, and runs, one "thread" at a time, exactly what the CUDA kernels run per walker
+// (prologue_body) and per (TOA, walker) (run_chain + residual_terms).  What it cannot cover is the kernel's
+// parallel plumbing (shared memory, shuffles, grid mapping) - the `-m gpu` tests do that.  Nothing in the product
+// links or loads this file.
+#define VELA_HOST_EMUL 1
+#include "../../vela.jl_b200/csrc/vela_chain.cuh"
+#include "../../vela.jl_b200/csrc/vela_host_prep.h"
+
+#include <vector>
+
+using namespace vela;
+
+extern "C" __attribute__((visibility("default")))
+int emul_chain(const VelaModelDesc* desc, const double* params, long B, int emit, double* Y, double* W, double* F,
+               double* chi2, double* logdetN) {
+    ProgramDev pg;
+    build_program(desc, pg);
+    const long nt = desc->n_toas, stride = (nt + 31) / 32 * 32;
+    const long n_rows = desc->wideband ? 2 * nt : nt;
+    std::vector<double> soa((size_t)C_NCOL * stride, 0.0), tzr(C_NCOL, 0.0);
+    for (long j = 0; j < nt; ++j) {
+        fill_toa_columns((const double*)((const char*)desc->toas + j * (long)desc->toa_stride_bytes), desc->wideband,
+                         soa.data(), stride, j);
+        fill_shapiro_columns(desc, soa.data(), stride, j);
+    }
+    fill_toa_columns((const double*)desc->tzr_toa, 0, tzr.data(), 1, 0);
+    fill_shapiro_columns(desc, tzr.data(), 1, 0);
+    std::vector<double> defaults(desc->default_values, desc->default_values + desc->n_params);
+    if (desc->n_aux > 0) defaults.insert(defaults.end(), desc->aux_values, desc->aux_values + desc->n_aux);
+    std::vector<int> free_idx(desc->free_indices, desc->free_indices + desc->n_free);
+    std::vector<double> Pext((size_t)B * pg.row, 0.0), tzr_phase((size_t)B * 2, 0.0);
+
+    PrologueArgs pa;
+    pa.defaults = defaults.data(); pa.free_idx = free_idx.data(); pa.params = params; pa.B = B;
+    pa.tzr_block = tzr.data(); pa.index_masks = desc->index_masks; pa.bit_masks = desc->bit_masks; pa.n_toas = nt;
+    pa.Pext = Pext.data(); pa.tzr_phase = tzr_phase.data();
+    blockIdx = {0, 0, 0}; blockDim = {1, 1, 1};
+    for (long b = 0; b < B; ++b) {
+        threadIdx = {(unsigned)b, 0, 0};
+        prologue_body(pg, pa);
+    }
+    for (long b = 0; b < B; ++b) {
+        const double* P = Pext.data() + (size_t)b * pg.row;
+        double chi = 0.0, lg = 0.0;
+        for (long j = 0; j < nt; ++j) {
+            ToaRegs t = load_toa(soa.data(), stride, j, false);
+            ChainEnv e;
+            e.toa_base = soa.data(); e.stride = stride; e.j = j;
+            e.index_masks = desc->index_masks; e.bit_masks = desc->bit_masks; e.n_toas = nt;
+            e.tzr = false; e.wide = desc->wideband != 0;
+            Corr k = run_chain(pg, P, t, e);
+            ResidTerms r = residual_terms(k, t, e.wide, tzr_phase[2 * b], tzr_phase[2 * b + 1], emit);
+            chi += r.chi;
+            lg += std::log(r.lman) + r.lex * 0.6931471805599453;
+            const size_t o = (size_t)b * n_rows + j;
+            if (emit == 2) {
+                if (Y) Y[o] = r.dphase.hi;
+                if (W) W[o] = r.dphase.lo;
+                if (F) F[o] = r.f;
+            } else {
+                if (Y) Y[o] = r.tres;
+                if (W) W[o] = emit ? r.w : 0.0;
+                if (e.wide) {
+                    if (Y) Y[o + nt] = r.dmres;
+                    if (W) W[o + nt] = emit ? r.wdm : 0.0;
+                }
+            }
+        }
+        if (chi2) chi2[b] = chi;
+        if (logdetN) logdetN[b] = lg;
+    }
+    return 0;
+}

@@ -1,0 +1,57 @@
+"""The chain kernel's arithmetic, compiled for the CPU, against the oracle (`-m "not gpu"`).
+
+tests/host_emul builds vela_device.cuh / vela_chain.cuh (the product's device source) with g++ behind a shim of the
+CUDA builtins and runs, thread by thread, what the kernels run per walker and per (TOA, walker).  The oracle follows
+the reference's operation order in full Double64; the kernel source takes documented shortcuts (small phase terms in
+FP64, error-free leading-word subtraction, shared reciprocal) - this test bounds what they cost, without a GPU:
+residuals within 1e-15 s (the parity budget is 1e-9 s), white-noise ln L within 1e-12 relative (budget 1e-9).
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES
+from helpers import emul_chain, oracle_eval_factory
+
+SYNTH = ["config2_ell1", "config3_gp", "config4_dd_wb", "extra_ell1_fbx", "extra_dd_fbx_wb", "extra_dmjump_bits_wb",
+         "extra_ell1h_fd_wavex", "extra_ell1k_swx", "extra_ddk_wb", "extra_ddh", "extra_dds", "extra_ecorr",
+         "extra_free_gp", "extra_free_gp_wb", "extra_mtm_only"]
+
+
+def _check(vb, oracle, md, walkers, white):
+    y, w, chi, lg = emul_chain(md, walkers, emit=1)
+    for b in range(len(walkers)):
+        yo, wo = oracle.residuals(md, walkers[b])
+        nt = len(md.toas)
+        assert np.max(np.abs(y[b, :nt] - yo[:nt])) < 1e-15, np.max(np.abs(y[b, :nt] - yo[:nt]))
+        np.testing.assert_allclose(w[b], wo, rtol=4e-16)
+        if md.n_rows > nt:   # wideband DM residuals [Hz-scaled DM units]
+            np.testing.assert_allclose(y[b, nt:], yo[nt:], rtol=1e-12, atol=1e-12 * np.max(np.abs(yo[nt:])))
+    if white:
+        y0, w0, chi0, lg0 = emul_chain(md, walkers, emit=0)
+        want = oracle.lnlike_batch(md, walkers)
+        np.testing.assert_allclose(-(chi0 + lg0) / 2, want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_reference_fixtures(name, vb, oracle, golden):
+    g = golden(name)
+    white = g.md.desc.kernel_kind == 0
+    _check(vb, oracle, g.md, g.walkers[:6], white)
+
+
+@pytest.mark.parametrize("name", SYNTH)
+def test_synthetic_cases(name, vb, oracle):
+    cfg = vb.synth.CONFIGS[name]
+    ds = vb.synth.make_dataset(name, oracle_eval_factory(vb, oracle), ntoa=min(cfg["ntoa"], 600))
+    md = vb.ModelDescriptor(ds.model, ds.toas)
+    _check(vb, oracle, md, ds.walkers(4, seed=3), md.desc.kernel_kind == 0)
+
+
+def test_phase_mode_matches_oracle(vb, oracle, golden):
+    g = golden("NGC6440E")
+    hi, lo, f, _, _ = emul_chain(g.md, g.x0[None, :], emit=2)
+    ohi, olo, of, _, _ = oracle.phases(g.md, g.x0)
+    nt = len(g.md.toas)
+    # Double64 phase residual: hi + lo agree to 1e-13 cycle (phase_small joins in FP64)
+    assert np.max(np.abs((hi[0, :nt] - ohi) + (lo[0, :nt] - olo))) < 1e-13
+    np.testing.assert_allclose(f[0, :nt], of, rtol=1e-15)

@@ -13,6 +13,7 @@
 #include <thread>
 #include <vector>
 
+#include "vela_host_prep.h"
 #include "vela_jit.h"
 #include "vela_kernels.cuh"
 #include "vela_structured.h"
@@ -453,7 +454,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
     const bool wy = woodbury && h->sp.active;   // Y carries w.y for the structured contraction (the ECORR kernels take it too)
     ca.emit = wy ? 3 : ((woodbury || ecorr) ? 1 : 0); ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
     const int warps = h->chain_threads / 32;
-    size_t chain_smem = ((size_t)group * pg.row + 2 * group + (size_t)warps * group * 3) * sizeof(double);
+    size_t chain_smem = chain_smem_doubles(group, pg.row, warps) * sizeof(double);
     dim3 cgrid((unsigned)h->n_tiles, (unsigned)((B + group - 1) / group));
     launch_chain(h, cgrid, chain_smem, st, ca);
     h->launches += 2;
@@ -572,54 +573,15 @@ void destroy_device(DeviceModel& d) {
     if (d.stream) cudaStreamDestroy(d.stream);
 }
 
-// TOA record (Julia isbits layout) -> SoA columns with the TOA-only hoists
-void fill_toa_columns(const double* rec, int wideband, double* cols, long stride, long j) {
-    auto put = [&](int c, double v) { cols[(size_t)c * stride + j] = v; };
-    put(C_T_HI, rec[0]); put(C_T_LO, rec[1]);
-    put(C_ERR2, rec[2] * rec[2]);  // toa.error * toa.error, toa.jl:123
-    put(C_FREQ, rec[3]); put(C_PN_HI, rec[4]); put(C_PN_LO, rec[5]);
-    for (int i = 0; i < 3; ++i) { put(C_POS + i, rec[6 + i]); put(C_VEL + i, rec[9 + i]); put(C_SUN + i, rec[12 + i]); }
-    const double* s = rec + 12;
-    const double* R = rec + 6;
-    put(C_RSUN, std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]));
-    put(C_R2, R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
-    put(C_DM, wideband ? rec[31] : 0.0);
-    put(C_DMERR2, wideband ? rec[32] * rec[32] : 0.0);
-    for (int b = 0; b < 5; ++b) {
-        const double* r = rec + 15 + 3 * b;
-        for (int i = 0; i < 3; ++i) put(C_PLANET + 3 * b + i, r[i]);
-        put(C_RPLANET + b, std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]));
-    }
-}
-
-// Component program of a validated descriptor (offsets of the hoisted per-sample values included).
-void build_program(const VelaModelDesc* desc, ProgramDev& pg) {
-    memset(&pg, 0, sizeof pg);
-    pg.n_comp = desc->n_components;
-    pg.n_params = desc->n_params;
-    pg.n_free = desc->n_free;
-    pg.wideband = desc->wideband;
-    int nder = 0;
-    for (int ic = 0; ic < desc->n_components; ++ic) {
-        const VelaComponentDesc& c = desc->components[ic];
-        CompDev& cd = pg.comp[ic];
-        cd.kind = c.kind; cd.flags = c.flags;
-        memcpy(cd.par, c.par, sizeof cd.par);
-        memcpy(cd.len, c.len, sizeof cd.len);
-        memcpy(cd.mask, c.mask, sizeof cd.mask);
-        memcpy(cd.dval, c.dval, sizeof cd.dval);
-        cd.der = nder;
-        nder += derived_count(c.kind, c.len);
-    }
-    pg.n_derived = nder;
-    pg.row = pg.n_params + nder;
-    if ((pg.row & 1) == 0) pg.row += 1;  // odd pitch: conflict-free column reads across rows
-}
-
 // Translation unit of the per-model chain kernel: the program as a constant object + the shared kernel body.
 std::string spec_source(const ProgramDev& pg, int min_blocks = 2, int threads = kChainThreads) {
     std::string src;
     char buf[256];
+    // walkers in flight per thread (unroll factor of the walker loop; more instruction-level parallelism for more registers)
+    if (const char* e = getenv("VELA_B200_JIT_UNROLL")) {
+        snprintf(buf, sizeof buf, "#define VELA_CHAIN_UNROLL %d\n", std::max(1, std::min(4, atoi(e))));
+        src += buf;
+    }
     src += "#define VELA_SPEC_CALLS";
     for (int ic = 0; ic < pg.n_comp; ++ic) { snprintf(buf, sizeof buf, " VELA_APPLY(%d)", ic); src += buf; }
     src += "\n#include \"vela_chain.cuh\"\nnamespace vela {\n";
@@ -644,41 +606,6 @@ std::string spec_source(const ProgramDev& pg, int min_blocks = 2, int threads = 
            "extern \"C\" __global__ void __launch_bounds__(128) vela_prologue_spec(vela::PrologueArgs a) {\n"
            "    vela::prologue_body(vela::kSpecProg, a);\n}\n";
     return src;
-}
-
-// Expansion points of shapiro_log() (vela_device.cuh): for every TOA, x0 = r - L0.r for the Sun and the five planets with
-// L0 the pulsar direction at the DEFAULT parameter values (evaluate_proper_motion, solarsystem.jl:45-56, plain libm: the
-// point only has to be close), 1 / x0 and log(x0 / AU).  Columns stay zero (= general branch on the device) when there
-// is no SolarSystem component or the geometry is degenerate.
-void fill_shapiro_columns(const VelaModelDesc* desc, double* cols, long stride, long j) {
-    const VelaComponentDesc* ss = nullptr;
-    for (int ic = 0; ic < desc->n_components; ++ic)
-        if (desc->components[ic].kind == VELA_COMP_SOLAR_SYSTEM) { ss = &desc->components[ic]; break; }
-    if (!ss) return;
-    const double* P = desc->default_values;
-    for (int k = 0; k < 6; ++k) if (ss->par[k] < 0) return;
-    const double lon = P[ss->par[0]], lat = P[ss->par[1]], pma = P[ss->par[2]], pmd = P[ss->par[3]], posepoch = P[ss->par[5]];
-    const double sa = std::sin(lon), ca = std::cos(lon), sd = std::sin(lat), cd = std::cos(lat);
-    auto at = [&](int c) { return cols[(size_t)c * stride + j]; };
-    const double dt = at(C_T_HI) - posepoch;
-    double L[3] = {ca * cd + (-sa * pma - ca * sd * pmd) * dt, sa * cd + (ca * pma - sa * sd * pmd) * dt, sd + cd * pmd * dt};
-    const double mag = std::sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
-    for (double& v : L) v /= mag;
-    if (ss->flags & VELA_FLAG_ECLIPTIC) {
-        const double se = 0.397776969112606, ce = 0.9174821430652418;
-        const double y = L[1], z = L[2];
-        L[1] = ce * y - se * z;
-        L[2] = se * y + ce * z;
-    }
-    for (int b = 0; b < 6; ++b) {
-        const int c0 = b == 0 ? C_SUN : C_PLANET + 3 * (b - 1);
-        const double r = b == 0 ? at(C_RSUN) : at(C_RPLANET + b - 1);
-        const double x0 = r - (L[0] * at(c0) + L[1] * at(c0 + 1) + L[2] * at(c0 + 2));
-        if (!(x0 > 0.0) || !std::isfinite(x0)) continue;
-        cols[(size_t)(C_SHAP + 3 * b) * stride + j] = x0;
-        cols[(size_t)(C_SHAP + 3 * b + 1) * stride + j] = 1.0 / x0;
-        cols[(size_t)(C_SHAP + 3 * b + 2) * stride + j] = std::log(x0 / 499.00478383615643);
-    }
 }
 
 int validate(const VelaModelDesc* d) {
@@ -1101,7 +1028,7 @@ static int run_single(VelaHandle h, const double* params, int64_t n_free, int mo
     ca.Pext = b.Pext; ca.tzr_phase = b.tzr; ca.toa = d.toa; ca.toa_stride = d.toa_stride; ca.n_toas = h->n_toas;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = mode;
     ca.Y = dY; ca.W = dW; ca.F = dF; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
-    size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 3) * sizeof(double);
+    size_t chain_smem = chain_smem_doubles(h->chain_group, h->prog.row, h->chain_threads / 32) * sizeof(double);
     launch_chain(h, dim3((unsigned)h->n_tiles, 1), chain_smem, d.stream, ca);
     h->launches += 2;
     const long n = mode == 1 ? h->n_rows : h->n_toas;
@@ -1263,7 +1190,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     const bool wy = h->sp.active;
     ca.index_masks = d.index_masks; ca.bit_masks = d.bit_masks; ca.B = 1; ca.group = h->chain_group; ca.emit = wy ? 3 : 1;
     ca.Y = b.Y; ca.W = b.W; ca.F = nullptr; ca.ld_yw = h->n_rows_pad; ca.partial = b.partial;
-    size_t chain_smem = ((size_t)h->chain_group * h->prog.row + 2 * h->chain_group + (size_t)(h->chain_threads / 32) * h->chain_group * 3) * sizeof(double);
+    size_t chain_smem = chain_smem_doubles(h->chain_group, h->prog.row, h->chain_threads / 32) * sizeof(double);
     launch_chain(h, dim3((unsigned)h->n_tiles, 1), chain_smem, d.stream, ca);
     std::vector<double> S((size_t)h->ld_sig, 0.0), U(h->pp, 0.0);
     h->launches += 3;

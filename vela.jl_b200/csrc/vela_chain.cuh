@@ -64,8 +64,9 @@ __device__ __forceinline__ void prologue_body(const ProgramDev& prog, const Prol
     // the TZR block is laid out column-after-column with stride 1 (C_NCOL doubles)
     ToaRegs t = load_toa(a.tzr_block, 1, 0, false);
     Corr k = run_chain(prog, P, t, e);
-    a.tzr_phase[2 * b] = k.bad ? CUDART_NAN : k.phase.hi;
-    a.tzr_phase[2 * b + 1] = k.phase.lo;
+    const dd ph = dd_add_d(k.phase, k.phase_small);
+    a.tzr_phase[2 * b] = k.bad ? CUDART_NAN : ph.hi;
+    a.tzr_phase[2 * b + 1] = ph.lo;
 }
 
 // frexp for the log-det accumulation: normal positive inputs (every sane err^2) are split with three integer
@@ -80,16 +81,131 @@ __device__ __forceinline__ double split_mantissa(double v, int* ex) {
     return frexp(v, ex);
 }
 
+// What one (TOA, walker) pair contributes: form_residual (residuals.jl:8-12, wideband_residuals.jl:6-17), the scaled
+// errors (toa.jl:122-123, wideband_toa.jl:68-69) and the terms of chi^2 / log det N.  Shared by the chain kernel and
+// the host-side arithmetic check (tests/host_emul).
+struct ResidTerms {
+    double tres, w, dmres, wdm;   // residual [s], 1 / sigma^2 (emit != 0 only), DM residual and its weight (wideband)
+    double chi;                   // r^2 / sigma^2 (+ DM term); NaN for a failed chain
+    double lman; int lex;         // prod sigma^2 = lman 2^lex
+    dd dphase;                    // phase mode (emit == 2) only
+    double f;                     // doppler-shifted spin frequency
+};
+
+__device__ __forceinline__ ResidTerms residual_terms(const Corr& k, const ToaRegs& t, bool wide, double tzr_hi, double tzr_lo,
+                                                     int emit) {
+    ResidTerms r;
+    // Float64((phase - pulse_number) - tzrphase) / (f (1 + doppler)).
+    // phase and tzrphase are ~1e10 cycles and differ by the pulse number to within a fraction of a cycle: their
+    // leading words are subtracted error-free, the pulse number (an integer) then cancels exactly, and what is
+    // left - trailing words and the small phase terms - is of the size of the residual itself, so plain FP64
+    // keeps it to 1e-16 relative.  12 operations where the Double64 route takes 40.
+    double tres_phase;
+    r.dphase = dd{0.0, 0.0};
+    if (emit == 2) {   // phase mode wants the Double64 value itself
+        dd dphase = dd_add_d(k.phase, k.phase_small);
+        dphase = t.pn_lo == 0.0 ? dd_add_d(dphase, -t.pn_hi) : dd_sub(dphase, dd{t.pn_hi, t.pn_lo});
+        dphase = dd_sub(dphase, dd{tzr_hi, tzr_lo});
+        r.dphase = dphase;
+        tres_phase = dphase.hi;
+    } else {
+        const dd lead = two_sum(k.phase.hi, -tzr_hi);
+        const double tail = ((k.phase.lo - tzr_lo) + lead.lo) + (k.phase_small - t.pn_lo);
+        tres_phase = (lead.hi - t.pn_hi) + tail;
+    }
+    r.f = k.spin_frequency * (1 + k.doppler);
+    r.tres = tres_phase / r.f;
+    const double err2 = (t.err2 + k.equad2) * k.efac * k.efac;  // scaled_toa_error_sqr toa.jl:122-123
+    // log det N = sum_j log(err2_j) is accumulated as a PRODUCT of mantissas and a sum of binary exponents, so the
+    // logarithm is taken once per (tile, walker) in the block epilogue instead of once per (TOA, walker)
+    r.w = 0.0;
+    r.lman = split_mantissa(err2, &r.lex);
+    if (emit) {  // Woodbury: y^T N^-1 y and log det N from Ninvdiag, gls_likelihood.jl:81-99
+        r.w = 1.0 / err2;
+        r.chi = r.tres * r.tres * r.w;
+    } else {
+        r.chi = r.tres * r.tres / err2;
+    }
+    r.dmres = 0.0; r.wdm = 0.0;
+    if (wide) {  // wideband_residuals.jl:6-17, wideband_toa.jl:68-69
+        r.dmres = t.dm - k.model_dm;
+        const double dmerr2 = (t.dmerr2 + k.dmequad2) * k.dmefac * k.dmefac;
+        int dex;
+        r.lman *= split_mantissa(dmerr2, &dex);
+        r.lex += dex;
+        if (emit) {
+            r.wdm = 1.0 / dmerr2;
+            r.chi += r.dmres * r.dmres * r.wdm;
+        } else {
+            r.chi += r.dmres * r.dmres / dmerr2;
+        }
+    }
+    if (k.bad || k.spin_frequency == 0.0) r.chi = CUDART_NAN;
+    return r;
+}
+
+#ifndef VELA_HOST_EMUL   // the kernel body proper: warp shuffles and shared memory have no host stand-in
+// Walkers whose (chi^2, mantissa product, exponent sum) terms wait in the per-warp ring before one pass reduces them
+// over the 32 TOAs of the warp.
+constexpr int kRedRing = 8;
+constexpr int kRedPitch = 33;   // doubles / ints per ring row: conflict-free for the column-wise pass
+// shared doubles one warp needs for its ring: two double rows and one int row per slot
+constexpr int kRedRingDoubles = kRedRing * kRedPitch * 2 + (kRedRing * kRedPitch + 1) / 2;
+
+__host__ __device__ inline size_t chain_smem_doubles(int group, int row, int warps) {
+    return (size_t)group * row + 2 * (size_t)group + (size_t)warps * group * 3 + (size_t)warps * kRedRingDoubles;
+}
+
+// Reduce `cnt` ring slots (walkers s0 .. s0 + cnt - 1 of the block's group) over the warp's 32 TOAs.  Lane l sums
+// eight consecutive TOAs of slot l & 7; two shuffle steps join the four parts; the lanes of part 0 store the warp's
+// partial for their walker.  25 shuffles + 10 FP64 operations per walker in the butterfly this replaces; here 1.25 + 2.25.
+__device__ __forceinline__ void ring_reduce(const double* rChi, const double* rMan, const int* rExp, int cnt, int lane,
+                                            double* out, int s0) {
+    __syncwarp();
+    const int slot = lane & (kRedRing - 1), part = lane >> 3;
+    double chi = 0.0, man = 1.0;
+    int ex = 0;
+    if (slot < cnt) {
+        const double* pc = rChi + slot * kRedPitch + part * 8;
+        const double* pm = rMan + slot * kRedPitch + part * 8;
+        const int* pe = rExp + slot * kRedPitch + part * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { chi += pc[i]; man *= pm[i]; ex += pe[i]; }   // 8 mantissas in [1/2, 1): >= 2^-8
+    }
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+        chi += __shfl_xor_sync(0xffffffffu, chi, off);
+        man *= __shfl_xor_sync(0xffffffffu, man, off);    // 32 mantissas: >= 2^-32, no underflow
+        ex += __shfl_xor_sync(0xffffffffu, ex, off);
+    }
+    if (part == 0 && slot < cnt) {
+        double* r = out + (size_t)(s0 + slot) * 3;
+        r[0] = chi; r[1] = man; r[2] = (double)ex;
+    }
+    __syncwarp();
+}
+
+#ifndef VELA_CHAIN_UNROLL
+#define VELA_CHAIN_UNROLL 1
+#endif
+constexpr int kChainUnroll = VELA_CHAIN_UNROLL;   // walkers in flight per thread (per-model build: VELA_B200_JIT_UNROLL)
+
 __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainArgs& a) {
     extern __shared__ double smem[];
     const int row = prog.row;
+    const int nwarps = blockDim.x >> 5;
     double* sP = smem;                                  // [group][row]
     double* sTzr = sP + (size_t)a.group * row;          // [group][2]
     double* sRed = sTzr + 2 * a.group;                  // [warps][group][3]: chi^2, mantissa product, exponent sum
+    double* sRing = sRed + (size_t)nwarps * a.group * 3;   // [warps][kRedRingDoubles]
 
     const long b0 = (long)blockIdx.y * a.group;
     const int nb = (int)min((long)a.group, a.B - b0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* rChi = sRing + (size_t)warp * kRedRingDoubles;
+    double* rMan = rChi + kRedRing * kRedPitch;
+    int* rExp = reinterpret_cast<int*>(rMan + kRedRing * kRedPitch);
+    double* wRed = sRed + (size_t)warp * a.group * 3;
 
     for (int i = tid; i < nb * row; i += blockDim.x) sP[i] = a.Pext[b0 * row + i];
     for (int i = tid; i < 2 * nb; i += blockDim.x) sTzr[i] = a.tzr_phase[2 * b0 + i];
@@ -104,70 +220,34 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
     e.tzr = false; e.wide = prog.wideband != 0;
     __syncthreads();
 
+#pragma unroll kChainUnroll
     for (int s = 0; s < nb; ++s) {
         const double* P = sP + (size_t)s * row;
         Corr k = run_chain(prog, P, t, e);
-        // form_residual residuals.jl:8-12: Float64((phase - pulse_number) - tzrphase) / (f (1 + doppler))
-        // (pulse numbers are integers below 2^53, so pn_lo is normally 0: dd - double is the same bits for 11 adds less)
-        dd dphase = t.pn_lo == 0.0 ? dd_add_d(k.phase, -t.pn_hi) : dd_sub(k.phase, dd{t.pn_hi, t.pn_lo});
-        dphase = dd_sub(dphase, dd{sTzr[2 * s], sTzr[2 * s + 1]});
-        double f = k.spin_frequency * (1 + k.doppler);
-        double tres = dphase.hi / f;
-        double err2 = (t.err2 + k.equad2) * k.efac * k.efac;  // scaled_toa_error_sqr toa.jl:122-123
-        // log det N = sum_j log(err2_j) is accumulated as a PRODUCT of mantissas and a sum of binary exponents, so the
-        // logarithm is taken once per (tile, walker) in the block epilogue instead of once per (TOA, walker)
-        double chi, w = 0.0;
-        int lex;
-        double lman = split_mantissa(err2, &lex);
-        if (a.emit) {  // Woodbury: y^T N^-1 y and log det N from Ninvdiag, gls_likelihood.jl:81-99
-            w = 1.0 / err2;
-            chi = tres * tres * w;
-        } else {
-            chi = tres * tres / err2;
-        }
-        double dmres = 0.0, wdm = 0.0;
-        if (e.wide) {  // wideband_residuals.jl:6-17, wideband_toa.jl:68-69
-            dmres = t.dm - k.model_dm;
-            double dmerr2 = (t.dmerr2 + k.dmequad2) * k.dmefac * k.dmefac;
-            int dex;
-            lman *= split_mantissa(dmerr2, &dex);
-            lex += dex;
-            if (a.emit) {
-                wdm = 1.0 / dmerr2;
-                chi += dmres * dmres * wdm;
-            } else {
-                chi += dmres * dmres / dmerr2;
-            }
-        }
-        if (k.bad || k.spin_frequency == 0.0) chi = CUDART_NAN;
-        if (!active) { chi = 0.0; lman = 1.0; lex = 0; }
+        const ResidTerms r = residual_terms(k, t, e.wide, sTzr[2 * s], sTzr[2 * s + 1], a.emit);
         if (a.emit == 2 && active) {  // phase mode: Double64 phase residual and doppler-shifted spin frequency
             const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
-            a.Y[o] = dphase.hi;
-            a.W[o] = dphase.lo;
-            a.F[o] = f;
+            a.Y[o] = r.dphase.hi;
+            a.W[o] = r.dphase.lo;
+            a.F[o] = r.f;
         } else if (a.emit && active) {
             const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
-            a.Y[o] = a.emit == 3 ? w * tres : tres;       // emit 3: the structured contraction wants w.y
-            a.W[o] = w;
+            a.Y[o] = a.emit == 3 ? r.w * r.tres : r.tres;       // emit 3: the structured contraction wants w.y
+            a.W[o] = r.w;
             if (e.wide) {
-                a.Y[o + a.n_toas] = a.emit == 3 ? wdm * dmres : dmres;
-                a.W[o + a.n_toas] = wdm;
+                a.Y[o + a.n_toas] = a.emit == 3 ? r.wdm * r.dmres : r.dmres;
+                a.W[o + a.n_toas] = r.wdm;
             }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            chi += __shfl_xor_sync(0xffffffffu, chi, off);
-            lman *= __shfl_xor_sync(0xffffffffu, lman, off);    // 32 mantissas in [1/4, 1): no underflow
-            lex += __shfl_xor_sync(0xffffffffu, lex, off);
-        }
-        if (lane == 0) {
-            double* r = sRed + ((size_t)warp * a.group + s) * 3;
-            r[0] = chi; r[1] = lman; r[2] = (double)lex;
-        }
+        // this walker's terms wait in the warp's ring; every kRedRing walkers one pass reduces them over the TOAs
+        const int slot = s & (kRedRing - 1);
+        rChi[slot * kRedPitch + lane] = active ? r.chi : 0.0;
+        rMan[slot * kRedPitch + lane] = active ? r.lman : 1.0;   // wideband: a product of two mantissas, >= 1/4
+        rExp[slot * kRedPitch + lane] = active ? r.lex : 0;
+        if (slot == kRedRing - 1) ring_reduce(rChi, rMan, rExp, kRedRing, lane, wRed, s - (kRedRing - 1));
     }
+    if (nb & (kRedRing - 1)) ring_reduce(rChi, rMan, rExp, nb & (kRedRing - 1), lane, wRed, nb & ~(kRedRing - 1));
     __syncthreads();
-    const int nwarps = blockDim.x >> 5;
     for (int i = tid; i < nb; i += blockDim.x) {
         double chi = 0.0, man = 1.0, ex = 0.0;
         for (int w = 0; w < nwarps; ++w) {
@@ -179,5 +259,7 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
         out[1] = log(man) + ex * 0.6931471805599453;   // ln 2
     }
 }
+
+#endif  // !VELA_HOST_EMUL
 
 }  // namespace vela

@@ -1,0 +1,91 @@
+// vela_host_prep.h - host-side preparation of the device inputs, shared by vela_api.cu (create()) and by the host-side
+// arithmetic check under tests/host_emul: the SoA TOA table with its TOA-only hoists, the component program, and the
+// expansion points of the Shapiro-delay logarithms.
+#pragma once
+#include <cmath>
+#include <cstring>
+
+#include "vela_device.cuh"
+
+namespace vela {
+
+// TOA record (Julia isbits layout) -> SoA columns with the TOA-only hoists
+inline void fill_toa_columns(const double* rec, int wideband, double* cols, long stride, long j) {
+    auto put = [&](int c, double v) { cols[(size_t)c * stride + j] = v; };
+    put(C_T_HI, rec[0]); put(C_T_LO, rec[1]);
+    put(C_ERR2, rec[2] * rec[2]);  // toa.error * toa.error, toa.jl:123
+    put(C_FREQ, rec[3]); put(C_PN_HI, rec[4]); put(C_PN_LO, rec[5]);
+    for (int i = 0; i < 3; ++i) { put(C_POS + i, rec[6 + i]); put(C_VEL + i, rec[9 + i]); put(C_SUN + i, rec[12 + i]); }
+    const double* s = rec + 12;
+    const double* R = rec + 6;
+    put(C_RSUN, std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]));
+    put(C_R2, R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
+    put(C_DM, wideband ? rec[31] : 0.0);
+    put(C_DMERR2, wideband ? rec[32] * rec[32] : 0.0);
+    for (int b = 0; b < 5; ++b) {
+        const double* r = rec + 15 + 3 * b;
+        for (int i = 0; i < 3; ++i) put(C_PLANET + 3 * b + i, r[i]);
+        put(C_RPLANET + b, std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]));
+    }
+}
+
+// Component program of a validated descriptor (offsets of the hoisted per-sample values included).
+inline void build_program(const VelaModelDesc* desc, ProgramDev& pg) {
+    memset(&pg, 0, sizeof pg);
+    pg.n_comp = desc->n_components;
+    pg.n_params = desc->n_params;
+    pg.n_free = desc->n_free;
+    pg.wideband = desc->wideband;
+    int nder = 0;
+    for (int ic = 0; ic < desc->n_components; ++ic) {
+        const VelaComponentDesc& c = desc->components[ic];
+        CompDev& cd = pg.comp[ic];
+        cd.kind = c.kind; cd.flags = c.flags;
+        memcpy(cd.par, c.par, sizeof cd.par);
+        memcpy(cd.len, c.len, sizeof cd.len);
+        memcpy(cd.mask, c.mask, sizeof cd.mask);
+        memcpy(cd.dval, c.dval, sizeof cd.dval);
+        cd.der = nder;
+        nder += derived_count(c.kind, c.len);
+    }
+    pg.n_derived = nder;
+    pg.row = pg.n_params + nder;
+    if ((pg.row & 1) == 0) pg.row += 1;  // odd pitch: conflict-free column reads across rows
+}
+
+// Expansion points of shapiro_log() (vela_device.cuh): for every TOA, x0 = r - L0.r for the Sun and the five planets with
+// L0 the pulsar direction at the DEFAULT parameter values (evaluate_proper_motion, solarsystem.jl:45-56, plain libm: the
+// point only has to be close), 1 / x0 and log(x0 / AU).  Columns stay zero (= general branch on the device) when there
+// is no SolarSystem component or the geometry is degenerate.
+inline void fill_shapiro_columns(const VelaModelDesc* desc, double* cols, long stride, long j) {
+    const VelaComponentDesc* ss = nullptr;
+    for (int ic = 0; ic < desc->n_components; ++ic)
+        if (desc->components[ic].kind == VELA_COMP_SOLAR_SYSTEM) { ss = &desc->components[ic]; break; }
+    if (!ss) return;
+    const double* P = desc->default_values;
+    for (int k = 0; k < 6; ++k) if (ss->par[k] < 0) return;
+    const double lon = P[ss->par[0]], lat = P[ss->par[1]], pma = P[ss->par[2]], pmd = P[ss->par[3]], posepoch = P[ss->par[5]];
+    const double sa = std::sin(lon), ca = std::cos(lon), sd = std::sin(lat), cd = std::cos(lat);
+    auto at = [&](int c) { return cols[(size_t)c * stride + j]; };
+    const double dt = at(C_T_HI) - posepoch;
+    double L[3] = {ca * cd + (-sa * pma - ca * sd * pmd) * dt, sa * cd + (ca * pma - sa * sd * pmd) * dt, sd + cd * pmd * dt};
+    const double mag = std::sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+    for (double& v : L) v /= mag;
+    if (ss->flags & VELA_FLAG_ECLIPTIC) {
+        const double se = 0.397776969112606, ce = 0.9174821430652418;
+        const double y = L[1], z = L[2];
+        L[1] = ce * y - se * z;
+        L[2] = se * y + ce * z;
+    }
+    for (int b = 0; b < 6; ++b) {
+        const int c0 = b == 0 ? C_SUN : C_PLANET + 3 * (b - 1);
+        const double r = b == 0 ? at(C_RSUN) : at(C_RPLANET + b - 1);
+        const double x0 = r - (L[0] * at(c0) + L[1] * at(c0 + 1) + L[2] * at(c0 + 2));
+        if (!(x0 > 0.0) || !std::isfinite(x0)) continue;
+        cols[(size_t)(C_SHAP + 3 * b) * stride + j] = x0;
+        cols[(size_t)(C_SHAP + 3 * b + 1) * stride + j] = 1.0 / x0;
+        cols[(size_t)(C_SHAP + 3 * b + 2) * stride + j] = std::log(x0 / 499.00478383615643);
+    }
+}
+
+}  // namespace vela
