@@ -297,7 +297,10 @@ VELA_API int vela_b200_lnlike_batch(VelaHandle h, const double* params, int64_t 
 /*
  * ln posterior = lnprior[b] + ln L_b, with the reference's short-circuit: when
  * lnprior[b] is not finite the result is lnprior[b] itself (posterior.jl:9-12).
- * lnprior == NULL means a flat (zero) prior.
+ * lnprior == NULL means a flat (zero) prior (or the device-side priors, once vela_b200_set_priors has been called).
+ * A sample whose likelihood evaluates to NaN (an assertion of the reference would have thrown: orbit.jl:26,
+ * toa.jl:95-99) is reported as -Inf, never as NaN and never as an error of the call - a deliberate difference from the
+ * reference, whose exception would abort the whole batch.
  */
 VELA_API int vela_b200_lnpost_batch(VelaHandle h, const double* params, int64_t B, int64_t n_free,
                            int64_t row_stride, int64_t col_stride, const double* lnprior,
@@ -410,12 +413,17 @@ VELA_API int vela_b200_marginalized_mean_batch(VelaHandle h, const double* param
  * the samples on the GPU: `d_params` is a row-major (B x n_free) DEVICE buffer on
  * device `devices[0]`, `d_out` a DEVICE buffer of B doubles.  Work is enqueued on
  * `stream` (a cudaStream_t passed as void*; NULL = the handle's own stream) and
- * the call returns without synchronising.
+ * the call returns without synchronising.  The handle's scratch is one set per device:
+ * every call (this one, the host-buffer batches, residuals, ...) orders itself after the
+ * previous call's work with an event, whatever streams the two used, so calls on one
+ * handle may be issued back to back on different streams; d_params / d_out / d_lnprior
+ * are the caller's and must stay valid until the stream has run the work.
  */
 VELA_API int vela_b200_lnlike_batch_device(VelaHandle h, const double* d_params, int64_t B,
                                   double* d_out, void* stream);
 
-/* Same, for the log-posterior: d_lnprior is a DEVICE buffer of B doubles (NULL = flat prior). */
+/* Same, for the log-posterior (with_prior != 0): d_lnprior is a DEVICE buffer of B doubles.  d_lnprior == NULL: the
+ * priors set with vela_b200_set_priors are evaluated on the device; without them NULL means a flat (zero) prior. */
 VELA_API int vela_b200_lnpost_batch_device(VelaHandle h, const double* d_params, int64_t B, const double* d_lnprior,
                                            int with_prior, double* d_out, void* stream);
 
@@ -432,6 +440,10 @@ VELA_API double vela_b200_last_stage_ms(VelaHandle h, int stage);
 /* FP64 micro-benchmarks used for the roofline denominators (TFLOP/s):
  * kind 0 = register-resident DFMA loop, kind 1 = mma.sync m8n8k4 f64 (DMMA) loop. */
 VELA_API double vela_b200_fp64_peak_tflops(int device, int kind);
+
+/* Test hook: quotients of the shared-reciprocal division (proper-motion normalisation) that differ from IEEE division
+ * over n pseudo-random operand sets; 0 expected. */
+VELA_API int64_t vela_b200_debug_div3(int64_t n, uint64_t seed);
 
 /* Test hook: the correctly rounded sin/cos (double-double Taylor) used for the sky-position unit vector. */
 VELA_API int vela_b200_debug_sincos(const double* x, int n, double* s, double* c);

@@ -28,10 +28,41 @@ def build(force: bool = False) -> str:
     return so
 
 
-def lib():
+def build_native() -> str:
+    """The same source built `-O3 -march=native` (SURVEY 8d's CPU-baseline flags) ON the machine that runs it; contraction
+    stays off, so the results are the standard build's bit for bit.  Used by bench.py's CPU legs only."""
+    out_dir = os.path.join(_HERE, "_native")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libvela_oracle_native.so")
+    src = os.path.join(_HERE, "vela_oracle.c")
+    cc = "/usr/bin/gcc" if os.access("/usr/bin/gcc", os.X_OK) else "gcc"
+    subprocess.run([cc, "-O3", "-march=native", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fno-fast-math",
+                    "-fvisibility=hidden", "-shared", "-o", so, src, "-lm"], check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    return so
+
+
+_NATIVE = False
+
+
+def use_native() -> bool:
+    """Switch this module to the -O3 -march=native build (compiled now, on this host).  Returns False (and keeps the
+    standard build) when the compile fails."""
+    global _LIB, _NATIVE
+    try:
+        so = build_native()
+    except Exception:
+        return False
+    _LIB = None
+    _NATIVE = True
+    lib(so)
+    return True
+
+
+def lib(path: str = None):
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build())
+        L = C.CDLL(path or build())
         dp = C.POINTER(C.c_double)
         L.oracle_lnlike_batch.argtypes = [C.c_void_p, dp, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int, C.c_int]
         L.oracle_lnlike_batch.restype = C.c_int

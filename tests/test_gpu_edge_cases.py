@@ -165,3 +165,9 @@ def test_ecorr_correction_staging_sizes(chunk, vb, monkeypatch):
     monkeypatch.delenv("VELA_B200_ECORR_CHUNK")
     assert np.all(np.isfinite(ref))
     np.testing.assert_allclose(got, ref, rtol=1e-11)
+
+
+def test_shared_reciprocal_division_is_ieee(vb):
+    """div3_by (three quotients from one reciprocal refinement, the proper-motion normalisation of solarsystem.jl:45-64)
+    must give the IEEE-rounded quotient bit for bit: 3 x 2^26 quotients, none may differ."""
+    assert vb.lib.lib().vela_b200_debug_div3(1 << 26, 12345) == 0

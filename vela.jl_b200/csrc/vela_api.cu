@@ -7,8 +7,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <mutex>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -91,7 +94,58 @@ struct DeviceModel {
     Buffers buf;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[5] = {0, 0, 0, 0, 0};
+    // The per-batch scratch (Pext, Y/W, R, ...) is one set per device.  Calls may enqueue on different streams (the
+    // handle's own, or a caller's through the *_device entry points) and return before the work has run, so the last
+    // user records `busy` on its stream and the next one makes its stream wait for it before touching the scratch.
+    cudaEvent_t busy = nullptr;
+    bool busy_valid = false;
 };
+
+// One host thread per device of a multi-device handle, alive for the life of the handle: it stages its device's block
+// through pinned memory and enqueues the kernels, so the devices start side by side (run_host_batch).
+struct Feeder {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, stop = false;
+    void start() {
+        th = std::thread([this] {
+            std::unique_lock<std::mutex> lk(m);
+            for (;;) {
+                cv.wait(lk, [this] { return has_job || stop; });
+                if (stop) return;
+                lk.unlock();
+                job();
+                lk.lock();
+                has_job = false;
+                cv.notify_all();
+            }
+        });
+    }
+    void post(std::function<void()> f) {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(f);
+        has_job = true;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return !has_job; });
+    }
+    void shutdown() {
+        if (!th.joinable()) return;
+        { std::lock_guard<std::mutex> lk(m); stop = true; cv.notify_all(); }
+        th.join();
+    }
+};
+
+void scratch_acquire(DeviceModel& d, cudaStream_t st) {
+    if (d.busy_valid) cudaStreamWaitEvent(st, d.busy, 0);
+}
+void scratch_release(DeviceModel& d, cudaStream_t st) {
+    if (d.busy && cudaEventRecord(d.busy, st) == cudaSuccess) d.busy_valid = true;
+}
 
 }  // namespace
 
@@ -112,6 +166,7 @@ struct VelaPulsar {
     int chol_nb = 8;                 // block width of the Cholesky kernel
     size_t chol_smem_bytes = 0;
     std::vector<DeviceModel> devs;
+    std::vector<std::unique_ptr<Feeder>> feeders;   // one per device when the handle spans several
     std::mutex mtx;
     std::atomic<int64_t> launches{0};   // several feeder threads when the handle spans several devices
     bool stage_timing = false;
@@ -187,6 +242,8 @@ int ensure_host_buffers(VelaPulsar* h, DeviceModel& d, long B) {
     if (b.h_params) cudaFreeHost(b.h_params);
     if (b.h_out) cudaFreeHost(b.h_out);
     if (b.h_lnprior) cudaFreeHost(b.h_lnprior);
+    b.h_params = b.h_out = b.h_lnprior = nullptr;   // a failed allocation below must not leave stale pointers behind
+    b.h_cap = 0;
     long cap = std::max<long>(B, 64);
     CU(cudaMallocHost((void**)&b.h_params, (size_t)cap * std::max(h->prog.n_free, 1) * sizeof(double)));
     CU(cudaMallocHost((void**)&b.h_out, (size_t)cap * sizeof(double)));
@@ -399,6 +456,8 @@ int set_smem_attrs(int dev) {
     // variant keeps the default split (its matrix traffic wants the L1)
     for (auto k : {chol_finish_kernel<8, true>, chol_finish_kernel<16, true>})
         CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(chol_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(cudaFuncSetAttribute(chol_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
@@ -505,11 +564,19 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
             ch.split_stride_sig = sa.split_stride_sig; ch.split_stride_u = sa.split_stride_u;
         }
         ch.ahat = d_ahat; ch.cf = d_cf;
+        // ranks up to 63: one warp per walker (chol_warp_kernel); the conditional-mean outputs and larger ranks keep the
+        // CTA-per-walker kernel.  VELA_B200_CHOL_WARP=0 forces the latter (A/B measurements).
+        static const bool warp_off = getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 0;
+        if (h->p + 1 <= 64 && !d_ahat && !warp_off) {
+            const int n_ru = (h->sp.active ? h->sp.n_r : 0) + h->p;
+            chol_warp_kernel<<<(unsigned)B, 32, chol_warp_smem_bytes(h->p, n_ru), st>>>(ch);
+        } else {
         // 96 threads per walker at full size (more resident walkers, fewer idle warps in the serial phases: 0.41 ->
         // 0.35 ms at rank 60), 128 for small batches and large ranks (tools/probes/gpu_chol_probe.py)
         int chol_threads = (B >= 1024 && h->chol_nb == 8) ? 96 : kCholLaunchThreads;
         if (const char* e = getenv("VELA_B200_CHOL_THREADS")) chol_threads = std::max(h->chol_nb == 8 ? 64 : 32, std::min(h->chol_nb == 8 ? kCholLaunchThreads : kCholThreads, atoi(e) / 32 * 32));
         (h->chol_nb == 8 && h->chol_smem ? chol_finish_kernel<8, true> : (h->chol_smem ? chol_finish_kernel<16, true> : chol_finish_kernel<16, false>))<<<(unsigned)B, chol_threads, h->chol_smem_bytes, st>>>(ch);
+        }
         if (timing) cudaEventRecord(d.ev[4], st);
         h->launches += 2;
     }
@@ -526,6 +593,7 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
     CU(cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, d.dev));
     CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     for (auto& e : d.ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&d.busy, cudaEventDisableTiming));
     if (upload(&d.toa, toa_soa.data(), toa_soa.size())) return VELA_ERR_CUDA;
     if (upload(&d.tzr_block, tzr_block.data(), tzr_block.size())) return VELA_ERR_CUDA;
     if (upload(&d.index_masks, desc->index_masks, (size_t)desc->n_index_masks * desc->n_toas)) return VELA_ERR_CUDA;
@@ -570,6 +638,7 @@ void destroy_device(DeviceModel& d) {
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
     cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active); cudaFree(d.priors);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
+    if (d.busy) cudaEventDestroy(d.busy);
     if (d.stream) cudaStreamDestroy(d.stream);
 }
 
@@ -808,6 +877,8 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         }
     }
     cudaSetDevice(prev);
+    if (h->devs.size() > 1)
+        for (size_t i = 0; i < h->devs.size(); ++i) { h->feeders.emplace_back(new Feeder()); h->feeders.back()->start(); }
     std::vector<double>().swap(h->sp.T);   // the device copies are authoritative from here on
 
     // per-model chain kernel (vela_jit.cu); any failure leaves the generic kernel in charge
@@ -834,6 +905,13 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
                 }
                 cudaSetDevice(prev);
                 if (ok) { h->spec_chain = k; h->spec_prologue = kp; h->use_spec = true; }
+            }
+            if (!h->use_spec && !getenv("VELA_B200_QUIET")) {
+                static std::atomic<bool> warned{false};
+                if (!warned.exchange(true))
+                    fprintf(stderr, "vela_b200: no per-model chain kernel (%s); the generic interpreting kernel runs instead, "
+                                    "~2.8x slower on the chain stage (vela_b200_jit_log has the details)\n",
+                            h->jit_log.substr(0, 200).c_str());
             }
         } else {
             h->jit_log = "disabled by VELA_B200_JIT=0";
@@ -863,6 +941,7 @@ VELA_API int vela_b200_destroy(VelaHandle h) {
     if (!h) return VELA_OK;
     int prev = 0;
     cudaGetDevice(&prev);
+    for (auto& f : h->feeders) f->shutdown();
     for (auto& d : h->devs) destroy_device(d);
     cudaSetDevice(prev);
     delete h;
@@ -906,7 +985,12 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
             if ((rc = ensure_device_buffers(h, d, n))) return rc;
             Buffers& b = d.buf;
             const bool timing = h->stage_timing && i == 0;
+            scratch_acquire(d, d.stream);
             if (timing) cudaEventRecord(d.ev[5], d.stream);
+            cudaError_t ce = cudaSuccess;
+            auto copy = [&](void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, bytes, kind, d.stream);
+            };
             // staged through pinned memory in slices, so the copy engine works on slice k while the host packs k + 1
             const long slice = std::max<long>(256, (256 * 1024) / (8 * std::max<long>(nf, 1)));
             for (long s0 = 0; s0 < n; s0 += slice) {
@@ -915,7 +999,7 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
                 else
                     for (long r = s0; r < s0 + m; ++r)
                         for (long k = 0; k < nf; ++k) b.h_params[r * nf + k] = params[(r0[i] + r) * rs + k * cs];
-                if (nf > 0) cudaMemcpyAsync(b.params + s0 * nf, b.h_params + s0 * nf, sizeof(double) * m * nf, cudaMemcpyHostToDevice, d.stream);
+                if (nf > 0) copy(b.params + s0 * nf, b.h_params + s0 * nf, sizeof(double) * m * nf, cudaMemcpyHostToDevice);
             }
             const double* d_lp = nullptr;
             if (with_prior && !lnprior && h->have_priors) {
@@ -924,22 +1008,25 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
                 d_lp = b.lnprior;
             } else if (with_prior && lnprior) {
                 memcpy(b.h_lnprior, lnprior + r0[i], sizeof(double) * n);
-                cudaMemcpyAsync(b.lnprior, b.h_lnprior, sizeof(double) * n, cudaMemcpyHostToDevice, d.stream);
+                copy(b.lnprior, b.h_lnprior, sizeof(double) * n, cudaMemcpyHostToDevice);
                 d_lp = b.lnprior;
             }
             rc = enqueue_batch(h, d, b.params, n, mode, with_prior, d_lp, b.out, d.stream);
-            cudaMemcpyAsync(b.h_out, b.out, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
+            copy(b.h_out, b.out, sizeof(double) * n, cudaMemcpyDeviceToHost);
+            scratch_release(d, d.stream);
+            if (ce != cudaSuccess && !rc) rc = fail(VELA_ERR_CUDA, "device %d: staging copy failed: %s", d.dev, cudaGetErrorString(ce));
             return rc;
         };
         if (nd == 1) {
             rc = feed(0);
         } else {
+            // the handle's per-device feeder threads (alive since create()): staging copies and launches of all devices
+            // proceed side by side instead of delaying device i by i copies
             std::vector<int> rcs(nd, 0);
             std::vector<std::string> msgs(nd);
-            std::vector<std::thread> workers;
             for (int i = 0; i < nd; ++i)
-                workers.emplace_back([&, i] { rcs[i] = feed(i); if (rcs[i]) msgs[i] = g_last_error; });   // the message is thread-local
-            for (auto& w : workers) w.join();
+                h->feeders[i]->post([&, i] { rcs[i] = feed(i); if (rcs[i]) msgs[i] = g_last_error; });   // the message is thread-local
+            for (int i = 0; i < nd; ++i) h->feeders[i]->wait();
             for (int i = 0; i < nd && !rc; ++i)
                 if (rcs[i]) { rc = rcs[i]; g_last_error = msgs[i]; }
         }
@@ -991,12 +1078,14 @@ VELA_API int vela_b200_lnpost_batch_device(VelaHandle h, const double* d_params,
     int rc = ensure_device_buffers(h, d, B);
     cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
     if (!rc && st != d.stream && d.buf.cap_B != cap_before) cudaStreamSynchronize(d.stream);  // scratch zero-fills ran on the handle's stream
+    if (!rc) scratch_acquire(d, st);   // earlier work on another stream may still be reading / writing the scratch
     if (!rc && with_prior && !d_lnprior && h->have_priors) {   // device-side priors
         prior_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(d.priors, h->prog.n_free, d_params, B, 0, d.buf.lnprior);
         h->launches += 1;
         d_lnprior = d.buf.lnprior;
     }
     if (!rc) rc = enqueue_batch(h, d, d_params, B, 0, with_prior, d_lnprior, d_out, st);
+    if (!rc) scratch_release(d, st);
     cudaSetDevice(prev);
     return rc;
 }
@@ -1018,6 +1107,7 @@ static int run_single(VelaHandle h, const double* params, int64_t n_free, int mo
     int rc = ensure_device_buffers(h, d, 1);
     if (rc) { cudaSetDevice(prev); return rc; }
     Buffers& b = d.buf;
+    scratch_acquire(d, d.stream);
     double *dY = nullptr, *dW = nullptr, *dF = nullptr;
     cudaMalloc((void**)&dY, sizeof(double) * h->n_rows_pad);
     cudaMalloc((void**)&dW, sizeof(double) * h->n_rows_pad);
@@ -1067,6 +1157,7 @@ VELA_API int vela_b200_noise_weights_inv(VelaHandle h, const double* params, int
     int rc = ensure_device_buffers(h, d, 1);
     if (rc) { cudaSetDevice(prev); return rc; }
     Buffers& b = d.buf;
+    scratch_acquire(d, d.stream);
     cudaMemcpyAsync(b.params, params, sizeof(double) * std::max<long>(n_free, 1), cudaMemcpyHostToDevice, d.stream);
     launch_prologue(h, d, b.params, 1, d.stream);
     CholArgs ch;
@@ -1183,6 +1274,7 @@ VELA_API int vela_b200_sigma_and_u(VelaHandle h, const double* params, int64_t n
     int rc = ensure_device_buffers(h, d, 1);
     if (rc) { cudaSetDevice(prev); return rc; }
     Buffers& b = d.buf;
+    scratch_acquire(d, d.stream);
     cudaMemcpyAsync(b.params, params, sizeof(double) * std::max<long>(n_free, 1), cudaMemcpyHostToDevice, d.stream);
     launch_prologue(h, d, b.params, 1, d.stream);
     ChainArgs ca;
@@ -1272,6 +1364,7 @@ VELA_API int vela_b200_marginalized_mean_batch(VelaHandle h, const double* param
         if ((rc = ensure_host_buffers(h, d, n))) break;
         if ((rc = ensure_device_buffers(h, d, n))) break;
         Buffers& b = d.buf;
+        scratch_acquire(d, d.stream);
         for (long r = 0; r < n; ++r)
             for (long k = 0; k < nf; ++k) b.h_params[r * nf + k] = params[(done + r) * rs + k * cs];
         cudaMemcpyAsync(b.params, b.h_params, sizeof(double) * n * std::max<long>(nf, 1), cudaMemcpyHostToDevice, d.stream);
@@ -1388,6 +1481,21 @@ VELA_API int vela_b200_debug_sincos(const double* x, int n, double* s, double* c
     CU(cudaMemcpy(c, dc, sizeof(double) * n, cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(ds); cudaFree(dc);
     return VELA_OK;
+}
+
+// test hook: compares the shared-reciprocal quotients of the proper-motion normalisation (div3_by) with the IEEE
+// divisions on n pseudo-random operand sets; returns the number of quotients that differ (0 expected), < 0 on error
+VELA_API int64_t vela_b200_debug_div3(int64_t n, uint64_t seed) {
+    if (vela_b200_device_count() <= 0) return fail(VELA_ERR_NO_DEVICE, "no CUDA device");
+    unsigned long long* d = nullptr;
+    unsigned long long hval = 0;
+    if (cudaMalloc((void**)&d, 8) != cudaSuccess) return VELA_ERR_CUDA;
+    cudaMemset(d, 0, 8);
+    div3_check_kernel<<<(unsigned)((n + 255) / 256), 256>>>(seed, n, d);
+    cudaError_t e = cudaMemcpy(&hval, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "div3 check: %s", cudaGetErrorString(e));
+    return (int64_t)hval;
 }
 
 // kind: 0 DFMA, 1 DMMA at full occupancy; 100 + w: DMMA with w warps per SM (one block of 32 w threads per SM)

@@ -55,13 +55,15 @@ inline void build_program(const VelaModelDesc* desc, ProgramDev& pg) {
 
 // Expansion points of shapiro_log() (vela_device.cuh): for every TOA, x0 = r - L0.r for the Sun and the five planets with
 // L0 the pulsar direction at the DEFAULT parameter values (evaluate_proper_motion, solarsystem.jl:45-56, plain libm: the
-// point only has to be close), 1 / x0 and log(x0 / AU).  Columns stay zero (= general branch on the device) when there
-// is no SolarSystem component or the geometry is degenerate.
+// point only has to be close), 1 / x0 and log(x0 / AU).  Where the geometry is degenerate (x0 not positive or not
+// finite) or the component lacks parameters, 1 / x0 is NaN, which sends the device down the general branch.
 inline void fill_shapiro_columns(const VelaModelDesc* desc, double* cols, long stride, long j) {
     const VelaComponentDesc* ss = nullptr;
     for (int ic = 0; ic < desc->n_components; ++ic)
         if (desc->components[ic].kind == VELA_COMP_SOLAR_SYSTEM) { ss = &desc->components[ic]; break; }
     if (!ss) return;
+    // 1 / x0 = NaN marks "no expansion point": d = (x - x0) * NaN fails |d| < 1e-4 and the device takes log(x / AU)
+    for (int b = 0; b < 6; ++b) cols[(size_t)(C_SHAP + 3 * b + 1) * stride + j] = std::nan("");
     const double* P = desc->default_values;
     for (int k = 0; k < 6; ++k) if (ss->par[k] < 0) return;
     const double lon = P[ss->par[0]], lat = P[ss->par[1]], pma = P[ss->par[2]], pmd = P[ss->par[3]], posepoch = P[ss->par[5]];

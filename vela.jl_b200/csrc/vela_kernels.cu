@@ -1128,6 +1128,216 @@ template __global__ void chol_finish_kernel<8, true>(CholArgs);
 template __global__ void chol_finish_kernel<16, true>(CholArgs);
 template __global__ void chol_finish_kernel<16, false>(CholArgs);
 
+// ------------------------------------------------------------------------------------------
+// K4w  Cholesky finish, one WARP per walker (ranks up to 63)
+// ------------------------------------------------------------------------------------------
+// Same quantities as chol_finish_kernel, for matrices of at most 64 rows (p + 1 <= 64, row p = u^T): the whole
+// factorisation runs inside one warp, so there is no block barrier anywhere (the CTA-per-walker kernel waits on its
+// barriers a third of the time at rank 60) and every walker occupies 32 threads and ~19 KB of shared memory instead of
+// 96-128 threads.
+//   * lane l owns matrix rows l and l + 32; the lower triangle sits in shared memory column by column, column k
+//     holding rows (k & ~3) .. NR-1 (NR = 32 or 64), so the four columns of a block share one row range, the own-row
+//     reads of a warp are one contiguous 256-byte row and the four entries L[j0..j0+3][k] every lane needs are two
+//     aligned 16-byte broadcasts;
+//   * left-looking, four columns at a time: the block's entries of the lane's two rows are 8 accumulators; for every
+//     earlier column k: acc[s][c] -= L[row_s][k] L[j0 + c][k] (4 shared-memory wavefronts for the own rows, 2
+//     broadcasts, 8 DFMA); then the 4 x 4 diagonal block is factorised in place in the accumulators, pivots and
+//     multipliers travelling by shuffle - no separate panel solve and no shared-memory round trip in the dependent
+//     chain; the columns are stored once, finished;
+//   * u rides along as row p (column p takes no pivot): its row ends as z = L^-1 u and entry (p, p) as -z.z;
+//   * log det Sigma^-1 = sum log(pivot) and log det Phi are mantissa products with exponent sums: two logarithms per
+//     walker instead of 2 p.
+constexpr int kCholWarpMaxRows = 64;
+__device__ __forceinline__ int cw_col_base(int m, int NR) { return 4 * m * NR - 8 * m * (m - 1); }   // first entry of column block m
+
+template <bool LOW, bool TWO>
+__device__ __forceinline__ void cw_block_step(double* A, int NR, int jb, int n1, int p, int lane, int& fail, double& lman,
+                                              int& lex) {
+    const int j0 = 4 * jb;
+    const int lenj = NR - j0;
+    double* cj = A + cw_col_base(jb, NR) - j0;            // cj[c * lenj + row] = entry (row, j0 + c)
+    double acc0[4], acc1[4];
+    const bool own0 = LOW && lane >= j0, own1 = TWO && lane + 32 >= j0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        acc0[c] = own0 ? cj[c * lenj + lane] : 0.0;
+        acc1[c] = own1 ? cj[c * lenj + lane + 32] : 0.0;
+    }
+    for (int m = 0; m < jb; ++m) {
+        const int len = NR - 4 * m;
+        const double* cb = A + cw_col_base(m, NR) - 4 * m;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double* cp = cb + r * len;
+            const double2 b01 = *reinterpret_cast<const double2*>(cp + j0);
+            const double2 b23 = *reinterpret_cast<const double2*>(cp + j0 + 2);
+            if (LOW) {
+                const double a0 = cp[lane];   // rows above j0 read finished entries (or a neighbouring column): never stored
+                acc0[0] = fma(-a0, b01.x, acc0[0]); acc0[1] = fma(-a0, b01.y, acc0[1]);
+                acc0[2] = fma(-a0, b23.x, acc0[2]); acc0[3] = fma(-a0, b23.y, acc0[3]);
+            }
+            if (TWO) {
+                const double a1 = cp[lane + 32];
+                acc1[0] = fma(-a1, b01.x, acc1[0]); acc1[1] = fma(-a1, b01.y, acc1[1]);
+                acc1[2] = fma(-a1, b23.x, acc1[2]); acc1[3] = fma(-a1, b23.y, acc1[3]);
+            }
+        }
+    }
+    // 4 x 4 diagonal block + panel, in the accumulators: the rows j0 .. j0 + 3 belong to lanes (j0 & 31) .. + 3
+    const int dl = j0 & 31;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int col = j0 + c;
+        if (col >= p) break;                               // column p (u) takes no pivot; columns past it do not exist
+        double d = __shfl_sync(0xffffffffu, LOW ? acc0[c] : acc1[c], dl + c);
+        if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
+        int ex;
+        lman *= split_mantissa(d, &ex);
+        lex += ex;
+        const double rd = rsqrt(d);
+        if (LOW) acc0[c] *= rd;
+        if (TWO) acc1[c] *= rd;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 4; ++c2) {
+            const double lv = __shfl_sync(0xffffffffu, LOW ? acc0[c] : acc1[c], dl + c2);   // L[j0 + c2][col]
+            if (LOW) acc0[c2] = fma(-acc0[c], lv, acc0[c2]);
+            if (TWO) acc1[c2] = fma(-acc1[c], lv, acc1[c2]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (own0) cj[c * lenj + lane] = acc0[c];
+        if (own1) cj[c * lenj + lane + 32] = acc1[c];
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) chol_warp_kernel(CholArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const long b = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int p = a.p, n1 = p + 1;
+    const int NR = n1 <= 32 ? 32 : 64, nblk = (n1 + 3) / 4;
+    const int nA = 4 * nblk * NR - 8 * nblk * (nblk - 1);
+    double* A = smem;
+    double* sR = A + nA;                                   // column sums (structured path), then u
+    for (int i = lane; i < nA; i += 32) A[i] = 0.0;
+    // entry (row, col <= row)
+    auto at = [&](int row, int col) -> double& { return A[cw_col_base(col >> 2, NR) + (col & 3) * (NR - (col & ~3)) + row - (col & ~3)]; };
+
+    // ---- u and, on the structured path, the column sums; split-K slabs are summed in slice order
+    const int n_r = a.table ? a.n_r : 0;
+    {
+        if (a.table) {
+            const double* gR = a.R + (size_t)b * a.ld_r;
+            for (int i = lane; i < n_r; i += 32) sR[i] = slab_sum(gR + i, a.split_stride_r, a.ksplit);
+        }
+        const double* gU = a.table ? a.R + a.u_off : a.U;
+        const long ldu = a.table ? a.ld_r : a.ld_u, su = a.table ? a.split_stride_r : a.split_stride_u;
+        for (int i = lane; i < p; i += 32) sR[n_r + i] = slab_sum(gU + (size_t)b * ldu + i, su, a.ksplit);
+    }
+    __syncwarp();
+    // ---- Sigma (packed pairs t = r (r + 1) / 2 + c): from the pair table or from the dense contraction's slabs
+    {
+        const double* gA = a.Sig + (size_t)b * a.ld_sig;
+        const long n_pairs = (long)p * (p + 1) / 2;
+        int r = 0, c = lane;
+        while (c > r) { c -= r + 1; ++r; }
+#pragma unroll 2
+        for (long t = lane; t < n_pairs; t += 32) {
+            double v;
+            if (a.table) {
+                const PairTerm pt = a.table[t];
+                v = pt.c1 * sR[pt.i1];
+                if (pt.c2 != 0.0) v = fma(pt.c2, sR[pt.i2], v);
+                if (a.add_sig) v += gA[t];
+            } else {
+                v = slab_sum(gA + t, a.split_stride_sig, a.ksplit);
+            }
+            at(r, c) = v;
+            c += 32;
+            while (c > r) { c -= r + 1; ++r; }
+        }
+        for (int i = lane; i < p; i += 32) at(p, i) = sR[n_r + i];
+    }
+    __syncwarp();
+    // ---- + Phi^-1 on the diagonal (calc_noise_weights_inv); log det Phi as a mantissa product
+    const double* P = a.Pext + (size_t)b * a.row;
+    double pman = 1.0;
+    int pex = 0;
+    for (int g = 0; g < a.n_gp; ++g) {
+        const GPDev gp = a.gp[g];
+        if (gp.kind == VELA_GP_MARGINALIZED_TM) {
+            for (int i = lane; i < gp.n; i += 32) {
+                const double v = a.gp_data[gp.data0 + i];
+                at(gp.col0 + i, gp.col0 + i) += v;
+                int ex;
+                pman *= split_mantissa(v, &ex);
+                pex += ex;
+            }
+        } else {
+            // powerlaw(A, gamma, f1, f1) gp_noise.jl:12-16 with A = exp10(log10_A)
+            const double fyr = 1.0 / 3600 / 24 / 365.25;
+            const double denom = 12 * (CUDART_PI * CUDART_PI) * fyr * fyr * fyr;
+            const double amp = exp10(P[gp.par_log10_amp]), gamma = P[gp.par_gamma], f1 = P[gp.par_f1];
+            const double P1 = amp * amp / denom * pow(fyr / f1, gamma) * f1;
+            for (int i = lane; i < gp.n; i += 32) {
+                const double v = 1 / (P1 * exp(-gamma * a.gp_data[gp.data0 + i]));
+                at(gp.col0 + i, gp.col0 + i) += v;
+                at(gp.col0 + gp.n + i, gp.col0 + gp.n + i) += v;
+                int ex;
+                const double mv = split_mantissa(v, &ex);   // the weight serves the sine and the cosine column
+                pman *= mv * mv;
+                pex += 2 * ex;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {               // <= 32 lanes x a few mantissas each: far from underflow
+        pman *= __shfl_xor_sync(0xffffffffu, pman, off);
+        pex += __shfl_xor_sync(0xffffffffu, pex, off);
+    }
+    const double logdetPhi = -(log(pman) + pex * 0.6931471805599453);   // log det Phi = -sum log Phi^-1
+    __syncwarp();
+
+    // ---- Cholesky (isposdef + cholesky!, gls_likelihood.jl:211-217) with z = L^-1 u riding along (ldiv!, :220)
+    int fail = 0, lex = 0;
+    double lman = 1.0;
+    const bool two = NR == 64;
+    for (int jb = 0; jb < nblk; ++jb) {
+        if (4 * jb < 32) {
+            if (two) cw_block_step<true, true>(A, NR, jb, n1, p, lane, fail, lman, lex);
+            else cw_block_step<true, false>(A, NR, jb, n1, p, lane, fail, lman, lex);
+        } else {
+            cw_block_step<false, true>(A, NR, jb, n1, p, lane, fail, lman, lex);
+        }
+        if ((jb & 7) == 7) {                               // 32 pivots: fold the mantissa product into the exponent sum
+            int ex;
+            lman = split_mantissa(lman, &ex);
+            lex += ex;
+        }
+    }
+    const double logdetSig = log(lman) + lex * 0.6931471805599453;     // sum log(pivot) = 2 sum log L_cc
+    // y^T N^-1 y and log det N: partial rows of the chain tiles (and ECORR blocks)
+    double py = 0.0, pl = 0.0;
+    for (int t = lane; t < a.n_tiles; t += 32) {
+        const double2 v = *reinterpret_cast<const double2*>(a.partial + ((size_t)t * a.B + b) * 2);
+        py += v.x;
+        pl += v.y;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        py += __shfl_xor_sync(0xffffffffu, py, off);
+        pl += __shfl_xor_sync(0xffffffffu, pl, off);
+    }
+    if (lane == 0) {
+        const double zz = -at(p, p);
+        double lnl = -0.5 * (py - zz + pl + logdetPhi + logdetSig);
+        if (fail) lnl = -CUDART_INF;
+        a.out[b] = combine_prior(lnl, a.lnprior, b, a.with_prior);
+    }
+}
+
 // Phi^-1 only (vela_b200_noise_weights_inv): one block, walker 0
 __global__ void phiinv_kernel(CholArgs a, double* __restrict__ out) {
     const double* P = a.Pext;
@@ -1147,6 +1357,32 @@ __global__ void phiinv_kernel(CholArgs a, double* __restrict__ out) {
             }
         }
     }
+}
+
+// test hook for div3_by: counts quotients that differ from the IEEE division in any bit
+__global__ void div3_check_kernel(unsigned long long seed, long n, unsigned long long* mismatches) {
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long st = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(i + 1);
+    auto next = [&]() {   // splitmix64
+        st += 0x9E3779B97F4A7C15ULL;
+        unsigned long long z = st;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    };
+    auto unit = [&]() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); };
+    // a unit vector plus a proper-motion-sized offset, as evaluate_proper_motion sees it; every 4th sample a wide range
+    double a[3], b;
+    const bool wide = (i & 3) == 3;
+    for (int k = 0; k < 3; ++k) a[k] = 2.0 * unit() - 1.0;
+    if (wide) b = 0.26 + 3.7 * unit();
+    else b = sqrt(1.0 + 1e-6 * (2.0 * unit() - 1.0));
+    double q[3];
+    div3_by(a[0], a[1], a[2], b, q);
+    unsigned long long bad = 0;
+    for (int k = 0; k < 3; ++k) bad += __double_as_longlong(q[k]) != __double_as_longlong(a[k] / b);
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // test hook for sincos_cr

@@ -175,7 +175,14 @@ inline size_t chol_smem_doubles(int p, int pp, int nb, bool matrix_in_smem, int 
     return (size_t)2 * pp + (size_t)nb * (nb + 1) + nb + (size_t)(p + 1) * (nb + 1) +
            (matrix_in_smem ? (size_t)(p + 1) * (p + 2) / 2 : 0) + (size_t)n_r;   // n_r: column sums of the structured path
 }
+// K4w: one warp per walker, ranks up to 63 (vela_kernels.cu)
+__global__ void chol_warp_kernel(CholArgs a);
+inline size_t chol_warp_smem_bytes(int p, int n_ru) {   // matrix (column blocks of 4, rows padded to 32 / 64) + column sums / u
+    const int n1 = p + 1, NR = n1 <= 32 ? 32 : 64, nblk = (n1 + 3) / 4;
+    return ((size_t)(4 * nblk * NR - 8 * nblk * (nblk - 1)) + (size_t)((n_ru + 1) & ~1)) * sizeof(double);
+}
 __global__ void phiinv_kernel(CholArgs a, double* out);
+__global__ void div3_check_kernel(unsigned long long seed, long n, unsigned long long* mismatches);
 __global__ void sincos_cr_kernel(const double* x, int n, double* s, double* c);
 __global__ void dfma_peak_kernel(double* out, int iters);
 __global__ void dmma_peak_kernel(double* out, int iters);

@@ -369,11 +369,13 @@ function batch(sym::Symbol, psr::B200Pulsar, paramss::AbstractMatrix, extra...)
     A = paramss isa StridedMatrix{Float64} ? paramss : Matrix{Float64}(paramss)
     rs, cs = strides(A)                      # Julia Matrix: (1, B); a PyArray from numpy: (nd, 1)
     out = Vector{Float64}(undef, B)
-    GC.@preserve A out begin
+    # the host-side lnprior vector (when there is one) is rooted for the duration of the call like A and out
+    lnpr = (sym === :lnpost && !(extra[1] isa Ptr)) ? convert(Vector{Float64}, extra[1]) : nothing
+    GC.@preserve A out lnpr begin
         rc = if sym === :lnpost
             ccall((:vela_b200_lnpost_batch, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
-                psr.handle, pointer(A), B, nd, rs, cs, extra[1] isa Ptr ? extra[1] : pointer(extra[1]), pointer(out))
+                psr.handle, pointer(A), B, nd, rs, cs, lnpr === nothing ? extra[1] : pointer(lnpr), pointer(out))
         else
             ccall((:vela_b200_lnlike_batch, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}),

@@ -140,6 +140,18 @@ def _distribution(js: JLStruct):
         return P.LogNormal(float(f["mu"]), float(f["sigma"]))
     if n == "PXPriorDistribution":
         return P.PXPriorDistribution(float(f["Rmax"]))
+    if n == "Truncated":
+        # Distributions.truncated(Normal(mu, sigma), lower, upper): what pyvela writes for bounded user priors
+        # (pyvela/pyvela/priors.py:245-256); a missing bound (`nothing`) is infinite
+        base = f["untruncated"]
+        if not (isinstance(base, JLStruct) and base.typename == "Normal"):
+            raise NotImplementedError(f"truncated {getattr(base, 'typename', base)} prior")
+
+        def bound(v, default):
+            return default if v is None or isinstance(v, JLStruct) else float(v)
+
+        return P.TruncatedNormal(float(base.fields["mu"]), float(base.fields["sigma"]),
+                                 bound(f.get("lower"), -np.inf), bound(f.get("upper"), np.inf))
     if hasattr(P, n):
         return getattr(P, n)()
     raise NotImplementedError(f"prior distribution {n}")
@@ -193,17 +205,20 @@ _MASK_FIELDS = {
     "ExclusivePhaseJump": ["jump_mask"], "DispersionJump": ["jump_mask"],
     "ExclusiveDispersionJump": ["jump_mask"], "MeasurementNoise": ["efac_index_mask", "equad_index_mask"],
     "DispersionMeasurementNoise": ["dmefac_index_mask", "dmequad_index_mask"],
+    "FrequencyDependentJump": ["jump_mask", "exponents"], "SolarWindDispersionPiecewise": ["swx_mask"],
+    "DispersionOffset": ["jump_mask"], "ExclusiveDispersionOffset": ["jump_mask"],
 }
 
 
 def _dist_spec(d) -> dict:
     spec = {"type": type(d).__name__}
-    spec.update({k: float(v) for k, v in vars(d).items() if isinstance(v, (int, float))})
+    spec.update({k: (float(v) if np.isfinite(v) else ("inf" if v > 0 else "-inf")) for k, v in vars(d).items()
+                 if isinstance(v, (int, float))})
     return spec
 
 
 def _dist_from(spec: dict):
-    kw = {k: v for k, v in spec.items() if k != "type"}
+    kw = {k: (float(v) if isinstance(v, str) else v) for k, v in spec.items() if k != "type"}   # "inf" / "-inf": open bounds
     kw.pop("lb", None), kw.pop("ub", None)
     return getattr(P, spec["type"])(**kw)
 
@@ -236,6 +251,8 @@ def save_pulsar_npz(path: str, model: M.TimingModel, toas: M.TOAs, extra: dict =
                 arrays[f"gp{i}_ln_js"] = g.ln_js
                 gps.append({"type": type(g).__name__})
         arrays["noise_basis"] = np.asarray(k.noise_basis)
+        if isinstance(k.inner_kernel, M.EcorrKernel):
+            arrays["ecorr_groups"] = k.inner_kernel.ecorr_groups
         kspec = {"type": "WoodburyKernel", "inner": type(k.inner_kernel).__name__, "gp": gps}
     elif isinstance(k, M.EcorrKernel):
         arrays["ecorr_groups"] = k.ecorr_groups
@@ -281,7 +298,8 @@ def load_pulsar_npz(path: str):
                 gps.append(M.MarginalizedTimingModel(prior_weights_inv=z[f"gp{i}_weights_inv"], pnames=g["names"]))
             else:
                 gps.append(getattr(M, g["type"])(ln_js=z[f"gp{i}_ln_js"]))
-        kernel = M.WoodburyKernel(getattr(M, ks["inner"])(), gps, z["noise_basis"])
+        inner = M.EcorrKernel(z["ecorr_groups"]) if ks["inner"] == "EcorrKernel" else getattr(M, ks["inner"])()
+        kernel = M.WoodburyKernel(inner, gps, z["noise_basis"])
     elif ks["type"] == "EcorrKernel":
         kernel = M.EcorrKernel(z["ecorr_groups"])
     else:
