@@ -441,6 +441,10 @@ VELA_API double vela_b200_last_stage_ms(VelaHandle h, int stage);
  * kind 0 = register-resident DFMA loop, kind 1 = mma.sync m8n8k4 f64 (DMMA) loop. */
 VELA_API double vela_b200_fp64_peak_tflops(int device, int kind);
 
+/* Probe: do scalar FP64 (DFMA) and the FP64 tensor path (DMMA) issue side by side?  tflops[0] DFMA in half the warps
+ * alone, [1] DMMA in the other half alone, [2] / [3] the two parts when both halves run in one launch. */
+VELA_API int vela_b200_debug_fp64_coissue(int device, double* tflops);
+
 /* Test hook: quotients of the shared-reciprocal division (proper-motion normalisation) that differ from IEEE division
  * over n pseudo-random operand sets; 0 expected. */
 VELA_API int64_t vela_b200_debug_div3(int64_t n, uint64_t seed);

@@ -27,6 +27,7 @@ static inline T __ldg(const T* p) { return *p; }
 static inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &v, 8); return r; }
 static inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
 static inline int __double2hiint(double v) { return (int)(__double_as_longlong(v) >> 32); }
+static inline int __double2loint(double v) { return (int)(__double_as_longlong(v) & 0xffffffffLL); }
 static inline double __hiloint2double(int hi, int lo) {
     return __longlong_as_double(((long long)hi << 32) | (unsigned int)lo);
 }

@@ -168,6 +168,7 @@ def test_ecorr_correction_staging_sizes(chunk, vb, monkeypatch):
 
 
 def test_shared_reciprocal_division_is_ieee(vb):
-    """div3_by (three quotients from one reciprocal refinement, the proper-motion normalisation of solarsystem.jl:45-64)
-    must give the IEEE-rounded quotient bit for bit: 3 x 2^26 quotients, none may differ."""
+    """div3_by (three quotients from one reciprocal refinement, the proper-motion normalisation of solarsystem.jl:45-64),
+    div_fast and rcp_fast (the division sequence without its special-case scaffolding, operands 2^-130 .. 2^130) must give
+    the IEEE-rounded result bit for bit: 5 x 2^26 quotients, none may differ."""
     assert vb.lib.lib().vela_b200_debug_div3(1 << 26, 12345) == 0

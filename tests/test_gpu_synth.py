@@ -77,7 +77,9 @@ def test_marginalized_mean_and_factor(name, ntoa, datasets, oracle):
     ds, psr, md = datasets(name, ntoa)
     W = ds.walkers(5, seed=3)
     ahat, cf, lnl = psr.marginalized_offset_mean_vectorized(W, with_cf=True, with_lnlike=True)
-    np.testing.assert_array_equal(lnl, psr.lnlike_vectorized(W))
+    # the conditional-mean outputs come from the CTA-per-walker factorisation, ln L of small ranks from the warp-per-walker
+    # one: same Sigma^-1, another operation order
+    np.testing.assert_allclose(lnl, psr.lnlike_vectorized(W), rtol=1e-13)
     for b in range(len(W)):
         So, uo = oracle.sigma(md, W[b])
         scale = np.sqrt(np.outer(np.diag(So), np.diag(So)))

@@ -1,0 +1,398 @@
+"""A second, independent pin of the oracle for the components the reference's JLSO fixtures do not exercise.
+
+Each component below is restated in mpmath (40 digits) directly from the reference's Julia source - one compact function
+per `correct_toa` method, written without looking at oracle/vela_oracle.c - and evaluated on the literal TOA of the
+reference's own tests (test/runtests.jl:13-59: the ephemeris vectors, 2.5 GHz, MJD 53470 epoch) with the parameter
+tuples of test/test_ell1.jl, test_dd.jl, test_solarwind.jl ... (where the reference only asserts `isfinite`), plus the
+same TOA shifted over +-1000 days so that every trigonometric term is exercised.  The oracle must agree with these
+restatements to 2e-11 s in delay (Float64 orbital-phase rounding of the reference arithmetic itself; 5e-13 s without a
+binary) and 1e-15 absolute in the Doppler factor (|doppler| ~ 1e-4); the kernels are tied to the oracle by the
+`-m gpu` parity tests and by tests/test_device_math_host.py.
+
+What stays unpinned without Julia: third-party conventions (GeometricUnits taylor_horner, Distributions logpdf) - both
+restated from their published definitions - and libm-level rounding.
+"""
+import mpmath as mp
+import numpy as np
+import pytest
+
+mp.mp.dps = 40
+DAY = 86400.0
+EPOCH_MJD = 53470.0
+# test/runtests.jl:13-20
+EPHEM = dict(
+    ssb_obs_pos=(18.0354099, 450.01472245, 195.05827732),
+    ssb_obs_vel=(-9.96231954e-05, 3.31555854e-06, 1.12968547e-06),
+    obs_sun_pos=(-15.89483533, -450.17185232, -195.18212616),
+    obs_jupiter_pos=(-1610.1796849, -1706.87348483, -681.22381513),
+    obs_saturn_pos=(-2392.85651431, 3109.13626083, 1405.71912274),
+    obs_venus_pos=(140.85922773, -217.65571843, -74.64804201),
+    obs_uranus_pos=(9936.62957939, -3089.07377113, -1486.17339104),
+    obs_neptune_pos=(11518.60924426, -9405.0693235, -4126.91030657),
+)
+OBL = mp.mpf("0.4090926006005829")
+AU = mp.mpf("499.00478383615643")
+M_SUN = mp.mpf("4.92549094830932e-06")
+M_PLANETS = [mp.mpf(v) for v in ("4.702819050227708e-09", "1.408128810019423e-09", "1.205680558494223e-11",
+                                 "2.1505895513637613e-10", "2.5373119991867603e-10")]
+# the literal TOA (MJD 53470 -> t = 0), test_dd.jl's (MJD 53471) and shifted copies
+T_TOAS = [0.0, 1.0 * DAY, -977.3 * DAY, -411.17 * DAY, 123.456 * DAY, 640.02 * DAY, 1000.9 * DAY]
+
+
+# ------------------------------------------------------------------------------------------------ model scaffolding
+def mini_model(vb, comps, single, multi, wideband_dm=None, ephems=None):
+    """A TimingModel with the given components (+ Spindown) over the literal TOAs; all parameters frozen except F0."""
+    M = vb.model
+    eph = M.SolarSystemEphemeris(*[EPHEM[k] for k in ("ssb_obs_pos", "ssb_obs_vel", "obs_sun_pos", "obs_jupiter_pos",
+                                                      "obs_saturn_pos", "obs_venus_pos", "obs_uranus_pos", "obs_neptune_pos")])
+    toas = []
+    for i, t in enumerate(T_TOAS):
+        e = ephems[i] if ephems is not None else eph
+        toa = M.TOA((t, 0.0), 1e-6, 2.5e9, (0.0, 0.0), e, i + 1)
+        toas.append(M.WidebandTOA(toa, M.DMInfo(*wideband_dm[i])) if wideband_dm is not None else toa)
+    sp = [M.Parameter(k, float(v), 0, True) for k, v in single.items()] + [M.Parameter("F_", 100.0, -1, True)]
+    mps = [M.MultiParameter(k, [M.Parameter(f"{k}{i}", float(v), 0, True) for i, v in enumerate(vs)]) for k, vs in multi.items()]
+    mps.append(M.MultiParameter("F", [M.Parameter("F0", 0.0, -1, False), M.Parameter("F1", -1e-15, -2, True)]))
+    ph = M.ParamHandler(sp, mps)
+    tzr = M.make_tzr_toa(((53475.0 - EPOCH_MJD) * DAY, 0.0), 2.5e9, eph)
+    model = M.TimingModel("TEST", "DE440", "TT(BIPM2021)", "TDB", EPOCH_MJD * DAY, tuple(comps) + (M.Spindown(),),
+                          M.WhiteNoiseKernel(), ph, tzr)
+    return model, M.TOAs.from_list(toas)
+
+
+def oracle_delay_doppler(vb, oracle, model, toas):
+    md = vb.ModelDescriptor(model, toas)
+    x = model.read_param_values_to_vector()
+    hi, lo, f, dly, _ = oracle.phases(md, x)
+    # doppler-shifted spin frequency = f_spin (1 + doppler), toa.jl:131-134; f_spin = F_ + F0 + F1 (t - delay)
+    fspin = 100.0 + (-1e-15) * (np.asarray(T_TOAS) - dly)
+    return dly, f / fspin - 1.0, md, x
+
+
+# ------------------------------------------------------------------------------------------------ restatements
+def taylor_horner(x, cs):              # GeometricUnits: sum c_n x^n / n!
+    return sum(mp.mpf(c) * x**n / mp.factorial(n) for n, c in enumerate(cs))
+
+
+def taylor_horner_integral(x, cs):     # sum c_n x^(n+1) / (n+1)!
+    return sum(mp.mpf(c) * x ** (n + 1) / mp.factorial(n + 1) for n, c in enumerate(cs))
+
+
+def orbit(dt, p, fbx):                 # binary/orbit.jl:3-12
+    if fbx:
+        return 2 * mp.pi * taylor_horner_integral(dt, p["FB"]), 2 * mp.pi * taylor_horner(dt, p["FB"])
+    x = dt / p["PB"]
+    return 2 * mp.pi * (x - mp.mpf(0.5) * p["PBDOT"] * x * x), 2 * mp.pi / (p["PB"] + p["PBDOT"] * dt)
+
+
+def mikkola(l, e):                     # binary/orbit.jl:21-74 (the algorithm itself, in high precision)
+    if e == 0 or l == 0:
+        return l
+    sgn = mp.sign(l)
+    l = l * sgn
+    ncyc = mp.floor(l / (2 * mp.pi))
+    l = l - 2 * mp.pi * ncyc
+    flag = l > mp.pi
+    if flag:
+        l = 2 * mp.pi - l
+    al = (1 - e) / (4 * e + mp.mpf(0.5))
+    be = (l / 2) / (4 * e + mp.mpf(0.5))
+    root = mp.sqrt(al**3 + be**2)
+    z = mp.cbrt(be + root) if be > 0 else -mp.cbrt(-(be - root))
+    s = z - al / z
+    w = s - mp.mpf("0.078") * s**5 / (1 + e)
+    E0 = l + e * (3 * w - 4 * w**3)
+    su, cu = mp.sin(E0), mp.cos(E0)
+    fu, f1, f2, f3, f4 = E0 - e * su - l, 1 - e * cu, e * su, e * cu, -e * su
+    u1 = -fu / f1
+    u2 = -fu / (f1 + f2 * u1 / 2)
+    u3 = -fu / (f1 + f2 * u2 / 2 + f3 * u2**2 / 6)
+    u4 = -fu / (f1 + f2 * u3 / 2 + f3 * u3**2 / 6 + f4 * u3**3 / 24)
+    xi = E0 + u4
+    return sgn * ((2 * mp.pi - xi if flag else xi) + ncyc * 2 * mp.pi)
+
+
+def ell1(dt, p, kind, fbx):
+    """binary_ell1_base.jl:36-180, binary_ell1h.jl, binary_ell1k.jl -> (delay, doppler).  The Roemer series is written
+    in its complex-exponential form, R = a1 Im[...] - an algebraically different route to the same truncated series."""
+    a1 = p["A1"] + dt * p["A1DOT"]
+    if kind == "ELL1k":                                   # binary_ell1k.jl:17-49
+        wd, led = p["OMDOT"], p["LNEDOT"]
+        e1 = (1 + led * dt) * (p["EPS1"] * mp.cos(wd * dt) + p["EPS2"] * mp.sin(wd * dt))
+        e2 = (1 + led * dt) * (p["EPS2"] * mp.cos(wd * dt) - p["EPS1"] * mp.sin(wd * dt))
+    else:
+        e1, e2 = p["EPS1"] + dt * p["EPS1DOT"], p["EPS2"] + dt * p["EPS2DOT"]
+    Phi, n = orbit(dt, p, fbx)
+    s = [None] + [mp.sin(k * Phi) for k in range(1, 5)]
+    c = [None] + [mp.cos(k * Phi) for k in range(1, 5)]
+
+    def series(d):   # d-th derivative w.r.t. Phi of the Lange+ 2001 series to O(e^3), term by term
+        def S(k):    # d^d/dPhi^d sin(k Phi)
+            return k**d * [s[k], c[k], -s[k], -c[k]][d % 4]
+
+        def C(k):
+            return k**d * [c[k], -s[k], -c[k], s[k]][d % 4]
+
+        return a1 * (S(1) + mp.mpf(0.5) * (e2 * S(2) - e1 * C(2))
+                     - (mp.mpf(1) / 8) * ((5 * e2**2 + 3 * e1**2) * S(1) - 2 * e2 * e1 * C(1)
+                                          + (-3 * e2**2 + 3 * e1**2) * S(3) + 6 * e2 * e1 * C(3))
+                     - (mp.mpf(1) / 12) * ((5 * e2**3 + 3 * e1**2 * e2) * S(2) + (-6 * e1 * e2**2 - 4 * e1**3) * C(2)
+                                           + (-4 * e2**3 + 12 * e1**2 * e2) * S(4) + (12 * e1 * e2**2 - 4 * e1**3) * C(4)))
+
+    dR, dRp, dRp2 = series(0), series(1), series(2)
+    if kind == "ELL1k":
+        dR = dR - mp.mpf(1.5) * a1 * e1                   # binary_ell1k.jl: constant term kept by ELL1k
+    if kind == "ELL1H":                                   # binary_ell1h.jl:22-46
+        h3, st = p["H3"], p["STIGMA"]
+        m2, sini = h3 / st**3, 2 * st / (1 + st**2)
+    else:
+        m2, sini = p["M2"], p["SINI"]
+    dRinv = dR * (1 - n * dRp + n * n * dRp * dRp + mp.mpf(0.5) * n * n * dR * dRp2)
+    dS = -2 * m2 * mp.log(1 - sini * s[1])
+    if kind == "ELL1H":
+        cbar = mp.sqrt(1 - sini**2)
+        sg = sini / (1 + cbar)
+        dS = dS - (-2 * m2 * (-mp.log(1 + sg**2) - 2 * sg * s[1] + sg**2 * c[2]))
+    return dRinv + dS, -dRp * n
+
+
+def dd(dt, p, kind, fbx, Lhat=None, R=None, ecl=False):
+    """binary_dd_base.jl:36-162, binary_ddh.jl, binary_dds.jl, binary_ddk.jl:20-120 -> (delay, doppler)."""
+    l, n = orbit(dt, p, fbx)
+    et = p["ECC"] + dt * p["EDOT"]
+    er, ephi = et * (1 + p["DR"]), et * (1 + p["DTH"])
+    u = mikkola(l, et)
+    su, cu = mp.sin(u), mp.cos(u)
+    eta = mp.sqrt(1 - ephi**2)
+    bphi = (1 - eta) / ephi
+    v = 2 * mp.atan2(bphi * su, 1 - bphi * cu) + u
+    a1 = p["A1"] + dt * p["A1DOT"]
+    dom = 0
+    if kind == "DDH":
+        m2, sini = p["H3"] / p["STIGMA"] ** 3, 2 * p["STIGMA"] / (1 + p["STIGMA"] ** 2)
+    elif kind == "DDS":
+        m2, sini = p["M2"], 1 - mp.exp(-p["SHAPMAX"])
+    elif kind == "DDK":
+        mua, mud = (p["PMELONG"], p["PMELAT"]) if ecl else (p["PMRA"], p["PMDEC"])
+        kin, kom, px = p["KIN"], p["KOM"], p["PX"]
+        cot, csc = mp.cos(kin) / mp.sin(kin), 1 / mp.sin(kin)
+        dkin = (-mua * mp.sin(kom) + mud * mp.cos(kom)) * dt
+        sd = Lhat[2]
+        cd = mp.sqrt(1 - sd * sd)
+        ca, sa = Lhat[0] / cd, Lhat[1] / cd
+        I0, J0 = (-sa, ca, 0), (-ca * sd, -sa * sd, cd)
+        dI, dJ = sum(r * i for r, i in zip(R, I0)), sum(r * j for r, j in zip(R, J0))
+        dx = a1 * cot * dkin + a1 * cot * px * (dI * mp.sin(kom) - dJ * mp.cos(kom))
+        dom = csc * (mua * mp.cos(kom) + mud * mp.sin(kom)) * dt - csc * px * (dI * mp.cos(kom) + dJ * mp.sin(kom))
+        a1 = a1 + dx
+        m2, sini = p["M2"], mp.sin(kin + dkin)
+    else:
+        m2, sini = p["M2"], p["SINI"]
+    om = p["OM"] + (p["OMDOT"] / n) * v + dom
+    al, be, ga = a1 * mp.sin(om), a1 * eta * mp.cos(om), p["GAMMA"]
+    dRE = al * (cu - er) + (be + ga) * su
+    dREp = -al * su + (be + ga) * cu
+    dREp2 = -al * cu - (be + ga) * su
+    nhat = n / (1 - et * cu)
+    dREinv = dRE * (1 - nhat * dREp + nhat**2 * dREp**2 + mp.mpf(0.5) * nhat**2 * dRE * dREp2
+                    - mp.mpf(0.5) * et * su / (1 - et * cu) * nhat**2 * dRE * dREp)
+    dS = -2 * m2 * mp.log(1 - et * cu - (sini / a1) * (al * (cu - er) + be * su))
+    return dREinv + dS, dREp * nhat
+
+
+def solar_system(t, p, ecl, planets, eph=EPHEM):
+    """solarsystem.jl:31-134 -> (delay, doppler, Lhat)."""
+    lon, lat = (p["ELONG"], p["ELAT"]) if ecl else (p["RAJ"], p["DECJ"])
+    pml, pmb = (p["PMELONG"], p["PMELAT"]) if ecl else (p["PMRA"], p["PMDEC"])
+    dt = t - p["POSEPOCH"]
+    x0 = [mp.cos(lon) * mp.cos(lat), mp.sin(lon) * mp.cos(lat), mp.sin(lat)]
+    xd = [-mp.sin(lon) * pml - mp.cos(lon) * mp.sin(lat) * pmb, mp.cos(lon) * pml - mp.sin(lon) * mp.sin(lat) * pmb,
+          mp.cos(lat) * pmb]
+    x1 = [a + b * dt for a, b in zip(x0, xd)]
+    mag = mp.sqrt(sum(a * a for a in x1))
+    L = [a / mag for a in x1]
+    if ecl:
+        L = [L[0], mp.cos(OBL) * L[1] - mp.sin(OBL) * L[2], mp.sin(OBL) * L[1] + mp.cos(OBL) * L[2]]
+    R = [mp.mpf(v) for v in eph["ssb_obs_pos"]]
+    LR = sum(a * b for a, b in zip(L, R))
+    delay = -LR
+    if p["PX"] != 0:
+        delay += mp.mpf(0.5) * p["PX"] * (sum(r * r for r in R) - LR * LR)
+
+    def shapiro(Mobj, key):
+        rv = [mp.mpf(v) for v in eph[key]]
+        return -2 * Mobj * mp.log((mp.sqrt(sum(a * a for a in rv)) - sum(a * b for a, b in zip(L, rv))) / AU)
+
+    delay += shapiro(M_SUN, "obs_sun_pos")
+    if planets:
+        for Mobj, key in zip(M_PLANETS, ("obs_jupiter_pos", "obs_saturn_pos", "obs_venus_pos", "obs_uranus_pos", "obs_neptune_pos")):
+            delay += shapiro(Mobj, key)
+    dop = sum(a * mp.mpf(b) for a, b in zip(L, eph["ssb_obs_vel"]))
+    return delay, dop, L
+
+
+def P(d):
+    return {k: (tuple(mp.mpf(x) for x in v) if isinstance(v, (tuple, list)) else mp.mpf(v)) for k, v in d.items()}
+
+
+# ------------------------------------------------------------------------------------------------ parameter tuples
+ELL1 = dict(TASC=(53470.0 - EPOCH_MJD) * DAY, PB=8e4, PBDOT=1e-10, A1=5.0, A1DOT=0.0, EPS1=1e-5, EPS2=-2e-5,
+            EPS1DOT=0.0, EPS2DOT=0.0, M2=5e-9, SINI=0.5)                                   # test/test_ell1.jl:9-23
+FB = (1.25e-5, -1.5625e-20)
+DD = dict(T0=(53470.0 - EPOCH_MJD) * DAY, PB=8e4, PBDOT=1e-10, A1=5.0, A1DOT=0.0, ECC=0.5, EDOT=0.0, OM=0.1, OMDOT=0.0,
+          DR=0.0, DTH=0.0, GAMMA=0.0, M2=5e-9, SINI=0.5)                                    # test/test_dd.jl:24-41
+SS_EQ = dict(POSEPOCH=(53470.0 - EPOCH_MJD) * DAY, PX=3e-12, RAJ=1.2, DECJ=0.5, PMRA=-7e-16, PMDEC=-4e-16)
+SS_ECL = dict(POSEPOCH=(53470.0 - EPOCH_MJD) * DAY, PX=3e-12, ELONG=1.2, ELAT=0.5, PMELONG=-7e-16, PMELAT=-4e-16)
+
+
+def _split(d, fbx):
+    single = {k: v for k, v in d.items() if not (fbx and k in ("PB", "PBDOT"))}
+    multi = {"FB": FB} if fbx else {}
+    return single, multi
+
+
+def _check(dly, dop, want, tol_d=2e-11, tol_dop=1e-15):
+    """delay to 2e-11 s: the reference's (and the oracle's) Float64 orbital phase after ~1000 orbits carries ~1e-12 rad,
+    i.e. a few 1e-12 s on a 5 lt-s orbit, against the exact evaluation here - a wrong term or sign shows up 3+ orders above
+    that.  The Doppler factor is read back as f_shifted / f_spin - 1, i.e. to a few ulp of 1."""
+    for j, (wd, wdop) in enumerate(want):
+        assert abs(float(mp.mpf(dly[j]) - wd)) < tol_d, (j, dly[j], float(wd))
+        assert abs(float(mp.mpf(dop[j]) - wdop)) < tol_dop, (j, dop[j], float(wdop))
+
+
+@pytest.mark.parametrize("kind", ["ELL1", "ELL1H", "ELL1k"])
+@pytest.mark.parametrize("fbx", [False, True])
+def test_ell1_family(kind, fbx, vb, oracle):
+    d = dict(ELL1)
+    # nonzero rates so every branch carries weight (the reference's tuples keep them at zero)
+    d.update(A1DOT=1e-14, EPS1DOT=2e-17, EPS2DOT=-1e-17)
+    if kind == "ELL1H":
+        d.pop("M2"), d.pop("SINI")
+        d.update(H3=1e-9, STIGMA=0.02)                       # test/test_ell1.jl:51-52
+        d["STIGMA"] = 0.4
+    if kind == "ELL1k":
+        d.pop("EPS1DOT"), d.pop("EPS2DOT")
+        d.update(OMDOT=3e-9, LNEDOT=1e-12)
+    single, multi = _split(d, fbx)
+    comp = {"ELL1": vb.model.BinaryELL1, "ELL1H": vb.model.BinaryELL1H, "ELL1k": vb.model.BinaryELL1k}[kind](fbx)
+    model, toas = mini_model(vb, [comp], single, multi)
+    dly, dop, _, _ = oracle_delay_doppler(vb, oracle, model, toas)
+    p = P(dict(d, FB=FB))
+    _check(dly, dop, [ell1(mp.mpf(t) - p["TASC"], p, kind, fbx) for t in T_TOAS])
+
+
+@pytest.mark.parametrize("kind", ["DD", "DDH", "DDS"])
+@pytest.mark.parametrize("fbx", [False, True])
+def test_dd_family(kind, fbx, vb, oracle):
+    d = dict(DD)
+    d.update(A1DOT=1e-14, EDOT=1e-16, OMDOT=2e-10, DR=1e-6, DTH=2e-6, GAMMA=1e-4)
+    if kind == "DDH":
+        d.pop("M2"), d.pop("SINI")
+        d.update(H3=1e-7, STIGMA=0.3)
+    if kind == "DDS":
+        d.pop("SINI")
+        d.update(SHAPMAX=3.0)
+    single, multi = _split(d, fbx)
+    comp = {"DD": vb.model.BinaryDD, "DDH": vb.model.BinaryDDH, "DDS": vb.model.BinaryDDS}[kind](fbx)
+    model, toas = mini_model(vb, [comp], single, multi)
+    dly, dop, _, _ = oracle_delay_doppler(vb, oracle, model, toas)
+    p = P(dict(d, FB=FB))
+    _check(dly, dop, [dd(mp.mpf(t) - p["T0"], p, kind, fbx) for t in T_TOAS])
+
+
+def test_dd_reference_tuple_as_written(vb, oracle):
+    """test/test_dd.jl:24-41 verbatim (all rates zero), PB and FBX forms."""
+    for fbx in (False, True):
+        single, multi = _split(DD, fbx)
+        model, toas = mini_model(vb, [vb.model.BinaryDD(fbx)], single, multi)
+        dly, dop, _, _ = oracle_delay_doppler(vb, oracle, model, toas)
+        p = P(dict(DD, FB=FB))
+        _check(dly, dop, [dd(mp.mpf(t) - p["T0"], p, "DD", fbx) for t in T_TOAS])
+
+
+def test_mikkola_solves_kepler(oracle):
+    """test/test_dd.jl:2-11 on a finer grid, against the high-precision evaluation of the same algorithm and against
+    Kepler's equation itself."""
+    for e in (0.0, 1e-6, 0.1, 0.3, 0.5, 0.9, 0.97):
+        for u in np.linspace(-7.0, 9.0, 41):
+            l = u - e * np.sin(u)
+            got = oracle.mikkola(l, e)
+            assert abs(got - float(mikkola(mp.mpf(l), mp.mpf(e)))) < 3e-15 * max(1.0, abs(u))
+            assert abs(got - e * np.sin(got) - l) < 1e-14 * max(1.0, abs(l))
+
+
+@pytest.mark.parametrize("ecl", [False, True])
+@pytest.mark.parametrize("planets", [False, True])
+def test_solar_system(ecl, planets, vb, oracle):
+    ss = SS_ECL if ecl else SS_EQ
+    model, toas = mini_model(vb, [vb.model.SolarSystem(ecl, planets)], ss, {})
+    dly, dop, _, _ = oracle_delay_doppler(vb, oracle, model, toas)
+    p = P(ss)
+    _check(dly, dop, [solar_system(mp.mpf(t), p, ecl, planets)[:2] for t in T_TOAS], tol_d=5e-13)
+
+
+@pytest.mark.parametrize("ecl", [False, True])
+def test_ddk_after_solar_system(ecl, vb, oracle):
+    """binary_ddk.jl:20-120: Kopeikin terms read the pulsar direction the SolarSystem component left behind."""
+    ss = SS_ECL if ecl else SS_EQ
+    d = dict(DD)
+    d.pop("SINI")
+    d.update(A1DOT=1e-14, OMDOT=2e-10, GAMMA=1e-4, KIN=1.1, KOM=0.7)
+    model, toas = mini_model(vb, [vb.model.SolarSystem(ecl, False), vb.model.BinaryDDK(False, ecl)], dict(ss, **d), {})
+    dly, dop, _, _ = oracle_delay_doppler(vb, oracle, model, toas)
+    p = P(dict(ss, **d))
+    want = []
+    for t in T_TOAS:
+        d_ss, dop_ss, L = solar_system(mp.mpf(t), p, ecl, False)
+        d_b, dop_b = dd((mp.mpf(t) - d_ss) - p["T0"], p, "DDK", False, Lhat=L, R=[mp.mpf(v) for v in EPHEM["ssb_obs_pos"]], ecl=ecl)
+        want.append((d_ss + d_b, dop_ss + dop_b))
+    _check(dly, dop, want)
+
+
+def test_solar_wind_and_dispersion(vb, oracle):
+    """solarwind.jl:10-51 + dispersion.jl:15-26 + component.jl:70-79 after an ecliptic SolarSystem with planets."""
+    ss = SS_ECL
+    extra = dict(SWEPOCH=100.0 * DAY, DMEPOCH=-50.0 * DAY)
+    multi = dict(NE_SW=(3.3e8, 1e-1), DM=(6.2e16, 3e7, -1e-2))
+    model, toas = mini_model(vb, [vb.model.SolarSystem(True, True), vb.model.SolarWindDispersion(), vb.model.DispersionTaylor()],
+                             dict(ss, **extra), multi)
+    dly, dop, _, _ = oracle_delay_doppler(vb, oracle, model, toas)
+    p = P(dict(ss, **extra))
+    want = []
+    for t in T_TOAS:
+        t = mp.mpf(t)
+        d0, dop0, L = solar_system(t, p, True, True)
+        rv = [mp.mpf(v) for v in EPHEM["obs_sun_pos"]]
+        r = mp.sqrt(sum(a * a for a in rv))
+        rho = mp.acos(-sum(a * b for a, b in zip(L, rv)) / r)
+        ne = taylor_horner((t - d0) - p["SWEPOCH"], multi["NE_SW"])
+        nu = mp.mpf(2.5e9) * (1 - dop0)
+        d1 = d0 + (ne * AU * AU * rho / (r * mp.sin(rho))) / nu**2
+        dm = taylor_horner((t - d1) - p["DMEPOCH"], multi["DM"])
+        want.append((d1 + dm / nu**2, dop0))
+    _check(dly, dop, want, tol_d=5e-12)
+
+
+def test_wideband_dm_residuals(vb, oracle):
+    """wideband_residuals.jl:6-17, wideband_model.jl:16-27, dmjump.jl, dispersion_measurement_noise.jl:19-46: the DM
+    residual is dm_measured - (sum of dispersion slopes - DMJUMP) and its variance (dmerr^2 + DMEQUAD^2) DMEFAC^2."""
+    M = vb.model
+    n = len(T_TOAS)
+    dms = [(1e16 + 3e11 * i, 1e11 * (1 + 0.1 * i)) for i in range(n)]                      # test/runtests.jl:55-58 scale
+    jm = np.array([1, 0, 1, 2, 2, 0, 1], dtype=np.uint32)
+    multi = dict(DM=(1.0002e16, 2e6), DMJUMP=(4e11, -2e11), DMEFAC=(1.3,), DMEQUAD=(5e10,))
+    comps = [M.SolarSystem(False, False), M.DispersionTaylor(), M.ExclusiveDispersionJump(jm),
+             M.DispersionMeasurementNoise(np.ones(n, dtype=np.uint32), np.ones(n, dtype=np.uint32))]
+    model, toas = mini_model(vb, comps, dict(SS_EQ, DMEPOCH=0.0), multi, wideband_dm=dms)
+    md = vb.ModelDescriptor(model, toas)
+    y, w = oracle.residuals(md, model.read_param_values_to_vector())
+    p = P(dict(SS_EQ, DMEPOCH=0.0))
+    for j, t in enumerate(T_TOAS):
+        d0, _, _ = solar_system(mp.mpf(t), p, False, False)
+        dm_model = taylor_horner((mp.mpf(t) - d0) - p["DMEPOCH"], multi["DM"])
+        if jm[j]:
+            dm_model -= mp.mpf(multi["DMJUMP"][jm[j] - 1])
+        want = mp.mpf(dms[j][0]) - dm_model
+        assert abs(float(mp.mpf(y[n + j]) - want)) < 1e-12 * abs(float(want)) + 1e-3, (j, y[n + j], float(want))
+        var = (mp.mpf(dms[j][1]) ** 2 + mp.mpf(5e10) ** 2) * mp.mpf(1.3) ** 2
+        assert abs(float(mp.mpf(w[n + j]) * var - 1)) < 1e-14

@@ -85,6 +85,7 @@ struct DeviceModel {
     long ldM = 0;
     double* T = nullptr;            // structured path: [n_rows_pad x n_cols] table (device copy of StructPlan::T)
     PairTerm* table = nullptr;
+    unsigned* ltab = nullptr;       // chol_warp_kernel layout table (ranks <= 63 on the structured path)
     GPDev* gp = nullptr;
     double* gp_data = nullptr;
     int3* ecorr_groups = nullptr;
@@ -163,6 +164,7 @@ struct VelaPulsar {
     int n_eg = 0, n_rect = 0;        // WoodburyKernel{EcorrKernel}: active groups, 32x32 rectangles of the (p+1) triangle
     long eg_pad = 0, ldv = 0;
     bool chol_smem = true;
+    std::vector<unsigned> ltab;      // layout table of chol_warp_kernel; empty = that kernel is not used
     int chol_nb = 8;                 // block width of the Cholesky kernel
     size_t chol_smem_bytes = 0;
     std::vector<DeviceModel> devs;
@@ -174,6 +176,7 @@ struct VelaPulsar {
     long max_chunk = 0;  // walkers per device per pass
     cudaKernel_t spec_chain = nullptr;   // NVRTC-specialised chain kernel (vela_jit.cu); null = generic kernel only
     cudaKernel_t spec_prologue = nullptr;
+    int spec_emit = -1;                  // ChainArgs::emit the specialised chain kernel was built for
     bool use_spec = false;
     std::string jit_log;
 };
@@ -483,7 +486,7 @@ void launch_prologue(VelaPulsar* h, DeviceModel& d, const double* d_params, long
 
 // K1 launch: the NVRTC-specialised kernel of this model when it exists and is enabled, else the generic interpreter
 void launch_chain(VelaPulsar* h, dim3 grid, size_t smem, cudaStream_t st, ChainArgs& ca) {
-    if (h->use_spec && h->spec_chain) {
+    if (h->use_spec && h->spec_chain && ca.emit == h->spec_emit) {   // other modes (single-sample residuals / phases): generic kernel
         void* args[] = {&ca};
         cudaLaunchKernel((const void*)h->spec_chain, grid, dim3((unsigned)h->chain_threads), args, smem, st);
     } else {
@@ -564,11 +567,12 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
             ch.split_stride_sig = sa.split_stride_sig; ch.split_stride_u = sa.split_stride_u;
         }
         ch.ahat = d_ahat; ch.cf = d_cf;
-        // ranks up to 63: one warp per walker (chol_warp_kernel); the conditional-mean outputs and larger ranks keep the
-        // CTA-per-walker kernel.  VELA_B200_CHOL_WARP=0 forces the latter (A/B measurements).
+        // ranks up to 63 on the structured path: one warp per walker (chol_warp_kernel); the conditional-mean outputs, the
+        // ECORR correction, dense bases and larger ranks keep the CTA-per-walker kernel.  VELA_B200_CHOL_WARP=0 forces the latter (A/B measurements).
         static const bool warp_off = getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 0;
-        if (h->p + 1 <= 64 && !d_ahat && !warp_off) {
-            const int n_ru = (h->sp.active ? h->sp.n_r : 0) + h->p;
+        ch.ltab = d.ltab;
+        if (d.ltab && !d_ahat && !warp_off && h->n_eg == 0) {
+            const int n_ru = h->sp.n_r + h->p;
             chol_warp_kernel<<<(unsigned)B, 32, chol_warp_smem_bytes(h->p, n_ru), st>>>(ch);
         } else {
         // 96 threads per walker at full size (more resident walkers, fewer idle warps in the serial phases: 0.41 ->
@@ -621,6 +625,7 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
         if (h->sp.active) {
             if (upload(&d.T, h->sp.T.data(), h->sp.T.size())) return VELA_ERR_CUDA;
             if (upload(&d.table, h->sp.table.data(), h->sp.table.size())) return VELA_ERR_CUDA;
+            if (!h->ltab.empty() && upload(&d.ltab, h->ltab.data(), h->ltab.size())) return VELA_ERR_CUDA;
         }
     }
     if (set_smem_attrs(d.dev)) return VELA_ERR_CUDA;
@@ -634,7 +639,7 @@ void destroy_device(DeviceModel& d) {
     if (d.buf.h_params) cudaFreeHost(d.buf.h_params);
     if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
     if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
-    cudaFree(d.T); cudaFree(d.table);
+    cudaFree(d.T); cudaFree(d.table); cudaFree(d.ltab);
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
     cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active); cudaFree(d.priors);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -643,12 +648,16 @@ void destroy_device(DeviceModel& d) {
 }
 
 // Translation unit of the per-model chain kernel: the program as a constant object + the shared kernel body.
-std::string spec_source(const ProgramDev& pg, int min_blocks = 2, int threads = kChainThreads) {
+std::string spec_source(const ProgramDev& pg, int min_blocks = 2, int threads = kChainThreads, int emit = -1) {
     std::string src;
     char buf[256];
     // walkers in flight per thread (unroll factor of the walker loop; more instruction-level parallelism for more registers)
     if (const char* e = getenv("VELA_B200_JIT_UNROLL")) {
         snprintf(buf, sizeof buf, "#define VELA_CHAIN_UNROLL %d\n", std::max(1, std::min(4, atoi(e))));
+        src += buf;
+    }
+    if (emit >= 0) {   // the emit mode of the handle's batches, folded into the kernel (launch_chain checks it)
+        snprintf(buf, sizeof buf, "#define VELA_SPEC_EMIT %d\n", emit);
         src += buf;
     }
     src += "#define VELA_SPEC_CALLS";
@@ -840,6 +849,24 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         h->chol_smem = need <= 200 * 1024;
         if (!h->chol_smem) h->chol_nb = 16;   // the global-scratch variant exists for block width 16 only
         h->chol_smem_bytes = h->chol_smem ? need : chol_smem_doubles(h->p, h->pp, h->chol_nb, false, n_r) * sizeof(double);
+        // ranks up to 63 on the structured path: layout table of the warp-per-walker Cholesky kernel - for every
+        // shared-memory slot of its column-blocked matrix the recipe that fills it (zero | c1 R[i1] + c2 R[i2] | u_i)
+        if (h->sp.active && h->p + 1 <= kCholWarpMaxRows && h->sp.n_cols <= kCholWarpMaxCols) {
+            const int n1 = h->p + 1, NR = (n1 + 1) & ~1, nblk = (n1 + 3) / 4;
+            h->ltab.assign((size_t)cw_col_base(nblk, NR), 0u);
+            bool ok = true;
+            for (int r = 0; r < h->p && ok; ++r)
+                for (int c = 0; c <= r; ++c) {
+                    const PairTerm& pt = h->sp.table[(size_t)r * (r + 1) / 2 + c];
+                    const bool c1_one = pt.c1 == 1.0, c1_half = pt.c1 == 0.5;
+                    const int c2 = pt.c2 == 0.0 ? 0 : (pt.c2 == 0.5 ? 1 : (pt.c2 == -0.5 ? 2 : -1));
+                    if (!(c1_one || c1_half) || c2 < 0) { ok = false; break; }   // a coefficient the 4-byte code cannot carry
+                    h->ltab[cw_slot(r, c, NR)] = (1u << 29) | ((unsigned)c2 << 27) | ((c1_one ? 1u : 0u) << 26) |
+                                                 ((unsigned)(c2 ? pt.i2 : 0) << 13) | (unsigned)pt.i1;
+                }
+            for (int i = 0; i < h->p; ++i) h->ltab[cw_slot(h->p, i, NR)] = (2u << 29) | (unsigned)(h->sp.n_r + i);
+            if (!ok) h->ltab.clear();
+        }
     }
 
     // SoA TOA table (+ TOA-only hoists) and the TZR block
@@ -891,7 +918,10 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
             int mb = 5;
             if (const char* force = getenv("VELA_B200_JIT_MINBLOCKS")) mb = std::max(1, std::min(16, atoi(force)));
             cudaKernel_t kp = nullptr;
-            int rc_jit = jit_chain_kernel(spec_source(pg, mb, std::max(h->chain_threads, 128)), &k, &kp, h->jit_log);
+            // batches of this handle always run one emit mode: w.y / w for the structured contraction, y / w for the dense
+            // one and the ECORR kernel, nothing for the white kernel
+            h->spec_emit = (h->p > 0 && h->sp.active) ? 3 : ((h->p > 0 || h->n_ecorr_groups > 0) ? 1 : 0);
+            int rc_jit = jit_chain_kernel(spec_source(pg, mb, std::max(h->chain_threads, 128), h->spec_emit), &k, &kp, h->jit_log);
             if (rc_jit == 0) {
                 bool ok = true;
                 for (auto& d : h->devs) {
@@ -1496,6 +1526,46 @@ VELA_API int64_t vela_b200_debug_div3(int64_t n, uint64_t seed) {
     cudaFree(d);
     if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "div3 check: %s", cudaGetErrorString(e));
     return (int64_t)hval;
+}
+
+// FP64 co-issue probe (fp64_coissue_kernel): tflops[0] = DFMA in the even warps alone, [1] = DMMA in the odd warps alone,
+// [2] = DFMA part and [3] = DMMA part when both run at once (same launch, so both are rated on the same elapsed time)
+VELA_API int vela_b200_debug_fp64_coissue(int device, double* tflops) {
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) return fail(VELA_ERR_NO_DEVICE, "no such device");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 16384;
+    double* dout = nullptr;
+    cudaMalloc((void**)&dout, sizeof(double) * blocks * threads);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const double fl_dfma = (double)blocks * (threads / 2) * iters * 16 * 2;
+    const double fl_dmma = (double)blocks * (threads / 64) * iters * 16 * (8.0 * 8 * 4 * 2);
+    double best[4] = {0, 0, 0, 0};
+    for (int mode = 1; mode <= 3; ++mode)
+        for (int rep = 0; rep < 8; ++rep) {
+            cudaEventRecord(e0);
+            fp64_coissue_kernel<<<blocks, threads>>>(dout, iters, mode);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (ms <= 0 || rep < 2) continue;
+            const double t = ms * 1e-3;
+            if (mode == 1) best[0] = std::max(best[0], fl_dfma / t / 1e12);
+            else if (mode == 2) best[1] = std::max(best[1], fl_dmma / t / 1e12);
+            else if (fl_dfma / t / 1e12 > best[2]) { best[2] = fl_dfma / t / 1e12; best[3] = fl_dmma / t / 1e12; }
+        }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(dout);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return fail(VELA_ERR_CUDA, "co-issue probe: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 4; ++i) tflops[i] = best[i];
+    return VELA_OK;
 }
 
 // kind: 0 DFMA, 1 DMMA at full occupancy; 100 + w: DMMA with w warps per SM (one block of 32 w threads per SM)

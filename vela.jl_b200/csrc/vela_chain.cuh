@@ -72,11 +72,11 @@ __device__ __forceinline__ void prologue_body(const ProgramDev& prog, const Prol
 // frexp for the log-det accumulation: normal positive inputs (every sane err^2) are split with three integer
 // operations; zero, subnormal, infinite and NaN inputs go through the library routine.
 __device__ __forceinline__ double split_mantissa(double v, int* ex) {
-    const long long bits = __double_as_longlong(v);
-    const int field = (int)((bits >> 52) & 0x7ff);
-    if (bits > 0 && field != 0 && field != 0x7ff) {
-        *ex = field - 1022;
-        return __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3fe0000000000000LL);   // mantissa in [1/2, 1)
+    const int hi = __double2hiint(v);
+    // positive and normal <=> sign 0 and exponent field in 1 .. 0x7fe: one unsigned compare on the high word
+    if ((unsigned)(hi - 0x00100000) < 0x7fe00000u) {
+        *ex = (hi >> 20) - 1022;
+        return __hiloint2double((hi & 0x000fffff) | 0x3fe00000, __double2loint(v));   // mantissa in [1/2, 1)
     }
     return frexp(v, ex);
 }
@@ -114,17 +114,17 @@ __device__ __forceinline__ ResidTerms residual_terms(const Corr& k, const ToaReg
         tres_phase = (lead.hi - t.pn_hi) + tail;
     }
     r.f = k.spin_frequency * (1 + k.doppler);
-    r.tres = tres_phase / r.f;
+    r.tres = div_fast(tres_phase, r.f);
     const double err2 = (t.err2 + k.equad2) * k.efac * k.efac;  // scaled_toa_error_sqr toa.jl:122-123
     // log det N = sum_j log(err2_j) is accumulated as a PRODUCT of mantissas and a sum of binary exponents, so the
     // logarithm is taken once per (tile, walker) in the block epilogue instead of once per (TOA, walker)
     r.w = 0.0;
     r.lman = split_mantissa(err2, &r.lex);
     if (emit) {  // Woodbury: y^T N^-1 y and log det N from Ninvdiag, gls_likelihood.jl:81-99
-        r.w = 1.0 / err2;
+        r.w = rcp_fast(err2);
         r.chi = r.tres * r.tres * r.w;
     } else {
-        r.chi = r.tres * r.tres / err2;
+        r.chi = div_fast(r.tres * r.tres, err2);
     }
     r.dmres = 0.0; r.wdm = 0.0;
     if (wide) {  // wideband_residuals.jl:6-17, wideband_toa.jl:68-69
@@ -134,10 +134,10 @@ __device__ __forceinline__ ResidTerms residual_terms(const Corr& k, const ToaReg
         r.lman *= split_mantissa(dmerr2, &dex);
         r.lex += dex;
         if (emit) {
-            r.wdm = 1.0 / dmerr2;
+            r.wdm = rcp_fast(dmerr2);
             r.chi += r.dmres * r.dmres * r.wdm;
         } else {
-            r.chi += r.dmres * r.dmres / dmerr2;
+            r.chi += div_fast(r.dmres * r.dmres, dmerr2);
         }
     }
     if (k.bad || k.spin_frequency == 0.0) r.chi = CUDART_NAN;
@@ -220,30 +220,45 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
     e.tzr = false; e.wide = prog.wideband != 0;
     __syncthreads();
 
+    // the launch's emit mode; the per-model build knows it at compile time (VELA_SPEC_EMIT), so the mode tests fold away
+#ifdef VELA_SPEC_EMIT
+    constexpr int emit = VELA_SPEC_EMIT;
+#else
+    const int emit = a.emit;
+#endif
+    // running pointers instead of per-walker index arithmetic (64-bit multiplies in the innermost loop otherwise)
+    const double* P = sP;
+    const double* tz = sTzr;
+    double* yp = a.Y + (size_t)b0 * a.ld_yw + j;
+    double* wp = a.W + (size_t)b0 * a.ld_yw + j;
+    double* fp = emit == 2 ? a.F + (size_t)b0 * a.ld_yw + j : nullptr;
+    double* rc = rChi + lane;
+    double* rm = rMan + lane;
+    int* re = rExp + lane;
 #pragma unroll kChainUnroll
-    for (int s = 0; s < nb; ++s) {
-        const double* P = sP + (size_t)s * row;
+    for (int s = 0; s < nb; ++s, P += row, tz += 2, yp += a.ld_yw, wp += a.ld_yw) {
         Corr k = run_chain(prog, P, t, e);
-        const ResidTerms r = residual_terms(k, t, e.wide, sTzr[2 * s], sTzr[2 * s + 1], a.emit);
-        if (a.emit == 2 && active) {  // phase mode: Double64 phase residual and doppler-shifted spin frequency
-            const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
-            a.Y[o] = r.dphase.hi;
-            a.W[o] = r.dphase.lo;
-            a.F[o] = r.f;
-        } else if (a.emit && active) {
-            const size_t o = (size_t)(b0 + s) * a.ld_yw + j;
-            a.Y[o] = a.emit == 3 ? r.w * r.tres : r.tres;       // emit 3: the structured contraction wants w.y
-            a.W[o] = r.w;
+        const ResidTerms r = residual_terms(k, t, e.wide, tz[0], tz[1], emit);
+        if (emit == 2) {  // phase mode: Double64 phase residual and doppler-shifted spin frequency
+            if (active) {
+                *yp = r.dphase.hi;
+                *wp = r.dphase.lo;
+                *fp = r.f;
+            }
+            fp += a.ld_yw;
+        } else if (emit && active) {
+            *yp = emit == 3 ? r.w * r.tres : r.tres;       // emit 3: the structured contraction wants w.y
+            *wp = r.w;
             if (e.wide) {
-                a.Y[o + a.n_toas] = a.emit == 3 ? r.wdm * r.dmres : r.dmres;
-                a.W[o + a.n_toas] = r.wdm;
+                yp[a.n_toas] = emit == 3 ? r.wdm * r.dmres : r.dmres;
+                wp[a.n_toas] = r.wdm;
             }
         }
         // this walker's terms wait in the warp's ring; every kRedRing walkers one pass reduces them over the TOAs
         const int slot = s & (kRedRing - 1);
-        rChi[slot * kRedPitch + lane] = active ? r.chi : 0.0;
-        rMan[slot * kRedPitch + lane] = active ? r.lman : 1.0;   // wideband: a product of two mantissas, >= 1/4
-        rExp[slot * kRedPitch + lane] = active ? r.lex : 0;
+        rc[slot * kRedPitch] = active ? r.chi : 0.0;
+        rm[slot * kRedPitch] = active ? r.lman : 1.0;   // wideband: a product of two mantissas, >= 1/4
+        re[slot * kRedPitch] = active ? r.lex : 0;
         if (slot == kRedRing - 1) ring_reduce(rChi, rMan, rExp, kRedRing, lane, wRed, s - (kRedRing - 1));
     }
     if (nb & (kRedRing - 1)) ring_reduce(rChi, rMan, rExp, nb & (kRedRing - 1), lane, wRed, nb & ~(kRedRing - 1));

@@ -1129,58 +1129,63 @@ template __global__ void chol_finish_kernel<16, true>(CholArgs);
 template __global__ void chol_finish_kernel<16, false>(CholArgs);
 
 // ------------------------------------------------------------------------------------------
-// K4w  Cholesky finish, one WARP per walker (ranks up to 63)
+// K4w  Cholesky finish, one WARP per walker (ranks up to 63, structured Sigma path)
 // ------------------------------------------------------------------------------------------
 // Same quantities as chol_finish_kernel, for matrices of at most 64 rows (p + 1 <= 64, row p = u^T): the whole
 // factorisation runs inside one warp, so there is no block barrier anywhere (the CTA-per-walker kernel waits on its
-// barriers a third of the time at rank 60) and every walker occupies 32 threads and ~19 KB of shared memory instead of
-// 96-128 threads.
+// barriers a third of the time at rank 60) and a walker occupies 32 threads and ~18 KB of shared memory.
 //   * lane l owns matrix rows l and l + 32; the lower triangle sits in shared memory column by column, column k
-//     holding rows (k & ~3) .. NR-1 (NR = 32 or 64), so the four columns of a block share one row range, the own-row
-//     reads of a warp are one contiguous 256-byte row and the four entries L[j0..j0+3][k] every lane needs are two
-//     aligned 16-byte broadcasts;
+//     holding rows (k & ~3) .. NR-1 (NR = p + 1 rounded up to even), so the four columns of a block share one row
+//     range, the own-row reads of a warp are one contiguous row segment and the four entries L[j0..j0+3][k] every lane
+//     needs are two aligned 16-byte broadcasts (layout: cw_col_base / chol_warp_layout, vela_kernels.cuh);
+//   * assembly through a LAYOUT table built at create(): one 4-byte code per shared-memory slot (zero | c1 R[i1] +
+//     c2 R[i2] | copy of u_i), so the loop that fills the matrix is a coalesced table read, two shared loads and one
+//     store per slot, with no index arithmetic and no separate zero fill;
 //   * left-looking, four columns at a time: the block's entries of the lane's two rows are 8 accumulators; for every
-//     earlier column k: acc[s][c] -= L[row_s][k] L[j0 + c][k] (4 shared-memory wavefronts for the own rows, 2
-//     broadcasts, 8 DFMA); then the 4 x 4 diagonal block is factorised in place in the accumulators, pivots and
-//     multipliers travelling by shuffle - no separate panel solve and no shared-memory round trip in the dependent
-//     chain; the columns are stored once, finished;
+//     earlier column k: acc[s][c] -= L[row_s][k] L[j0 + c][k] (own rows: 2 LDS.64, the block's rows: 2 broadcast
+//     LDS.128, 8 DFMA; column pointers advance by additions only); then the 4 x 4 diagonal block is factorised in
+//     place in the accumulators, pivots and multipliers travelling by shuffle - no separate panel solve and no
+//     shared-memory round trip in the dependent chain; the columns are stored once, finished;
 //   * u rides along as row p (column p takes no pivot): its row ends as z = L^-1 u and entry (p, p) as -z.z;
 //   * log det Sigma^-1 = sum log(pivot) and log det Phi are mantissa products with exponent sums: two logarithms per
 //     walker instead of 2 p.
-constexpr int kCholWarpMaxRows = 64;
-__device__ __forceinline__ int cw_col_base(int m, int NR) { return 4 * m * NR - 8 * m * (m - 1); }   // first entry of column block m
-
 template <bool LOW, bool TWO>
-__device__ __forceinline__ void cw_block_step(double* A, int NR, int jb, int n1, int p, int lane, int& fail, double& lman,
-                                              int& lex) {
+__device__ __forceinline__ void cw_block_step(double* A, int NR, int jb, int p, int lane, int& fail, double& lman, int& lex) {
     const int j0 = 4 * jb;
     const int lenj = NR - j0;
     double* cj = A + cw_col_base(jb, NR) - j0;            // cj[c * lenj + row] = entry (row, j0 + c)
     double acc0[4], acc1[4];
-    const bool own0 = LOW && lane >= j0, own1 = TWO && lane + 32 >= j0;
+    const bool own0 = LOW && lane >= j0 && lane < NR, own1 = TWO && lane + 32 >= j0 && lane + 32 < NR;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         acc0[c] = own0 ? cj[c * lenj + lane] : 0.0;
         acc1[c] = own1 ? cj[c * lenj + lane + 32] : 0.0;
     }
-    for (int m = 0; m < jb; ++m) {
-        const int len = NR - 4 * m;
-        const double* cb = A + cw_col_base(m, NR) - 4 * m;
+    {
+        // cp[row] = entry (row, 4 m) of the earlier column block m; the next column is `len` doubles further, the
+        // next block 4 len - 4
+        const double* cp = A;
+        int len = NR;
+#pragma unroll 2
+        for (int m = 0; m < jb; ++m) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const double* cp = cb + r * len;
-            const double2 b01 = *reinterpret_cast<const double2*>(cp + j0);
-            const double2 b23 = *reinterpret_cast<const double2*>(cp + j0 + 2);
-            if (LOW) {
-                const double a0 = cp[lane];   // rows above j0 read finished entries (or a neighbouring column): never stored
-                acc0[0] = fma(-a0, b01.x, acc0[0]); acc0[1] = fma(-a0, b01.y, acc0[1]);
-                acc0[2] = fma(-a0, b23.x, acc0[2]); acc0[3] = fma(-a0, b23.y, acc0[3]);
+            for (int r = 0; r < 4; ++r) {
+                const double* cc = cp + r * len;
+                const double2 b01 = *reinterpret_cast<const double2*>(cc + j0);
+                const double2 b23 = *reinterpret_cast<const double2*>(cc + j0 + 2);
+                if (LOW) {
+                    const double a0 = cc[lane];   // rows above j0 read finished entries (or a neighbouring column): never stored
+                    acc0[0] = fma(-a0, b01.x, acc0[0]); acc0[1] = fma(-a0, b01.y, acc0[1]);
+                    acc0[2] = fma(-a0, b23.x, acc0[2]); acc0[3] = fma(-a0, b23.y, acc0[3]);
+                }
+                if (TWO) {
+                    const double a1 = cc[lane + 32];
+                    acc1[0] = fma(-a1, b01.x, acc1[0]); acc1[1] = fma(-a1, b01.y, acc1[1]);
+                    acc1[2] = fma(-a1, b23.x, acc1[2]); acc1[3] = fma(-a1, b23.y, acc1[3]);
+                }
             }
-            if (TWO) {
-                const double a1 = cp[lane + 32];
-                acc1[0] = fma(-a1, b01.x, acc1[0]); acc1[1] = fma(-a1, b01.y, acc1[1]);
-                acc1[2] = fma(-a1, b23.x, acc1[2]); acc1[3] = fma(-a1, b23.y, acc1[3]);
-            }
+            cp += 4 * len - 4;
+            len -= 4;
         }
     }
     // 4 x 4 diagonal block + panel, in the accumulators: the rows j0 .. j0 + 3 belong to lanes (j0 & 31) .. + 3
@@ -1217,49 +1222,43 @@ __global__ void __launch_bounds__(32) chol_warp_kernel(CholArgs a) {
     const long b = blockIdx.x;
     const int lane = threadIdx.x;
     const int p = a.p, n1 = p + 1;
-    const int NR = n1 <= 32 ? 32 : 64, nblk = (n1 + 3) / 4;
-    const int nA = 4 * nblk * NR - 8 * nblk * (nblk - 1);
+    const int NR = (n1 + 1) & ~1, nblk = (n1 + 3) / 4;
+    const int nA = cw_col_base(nblk, NR);
     double* A = smem;
-    double* sR = A + nA;                                   // column sums (structured path), then u
-    for (int i = lane; i < nA; i += 32) A[i] = 0.0;
+    double* sR = A + nA + kCholWarpSlack;                  // column sums, then u
     // entry (row, col <= row)
     auto at = [&](int row, int col) -> double& { return A[cw_col_base(col >> 2, NR) + (col & 3) * (NR - (col & ~3)) + row - (col & ~3)]; };
 
-    // ---- u and, on the structured path, the column sums; split-K slabs are summed in slice order
-    const int n_r = a.table ? a.n_r : 0;
+    // ---- the column sums and u; split-K slabs are summed in slice order
     {
-        if (a.table) {
-            const double* gR = a.R + (size_t)b * a.ld_r;
-            for (int i = lane; i < n_r; i += 32) sR[i] = slab_sum(gR + i, a.split_stride_r, a.ksplit);
+        const double* gR = a.R + (size_t)b * a.ld_r;
+        const int n_ru = a.n_r + p;
+        if (a.ksplit == 1) {
+            for (int i = lane; i < a.n_r; i += 32) sR[i] = gR[i];
+            for (int i = lane; i < p; i += 32) sR[a.n_r + i] = gR[a.u_off + i];
+        } else {
+            for (int i = lane; i < a.n_r; i += 32) sR[i] = slab_sum(gR + i, a.split_stride_r, a.ksplit);
+            for (int i = lane; i < p; i += 32) sR[a.n_r + i] = slab_sum(gR + a.u_off + i, a.split_stride_r, a.ksplit);
         }
-        const double* gU = a.table ? a.R + a.u_off : a.U;
-        const long ldu = a.table ? a.ld_r : a.ld_u, su = a.table ? a.split_stride_r : a.split_stride_u;
-        for (int i = lane; i < p; i += 32) sR[n_r + i] = slab_sum(gU + (size_t)b * ldu + i, su, a.ksplit);
+        (void)n_ru;
     }
     __syncwarp();
-    // ---- Sigma (packed pairs t = r (r + 1) / 2 + c): from the pair table or from the dense contraction's slabs
-    {
-        const double* gA = a.Sig + (size_t)b * a.ld_sig;
-        const long n_pairs = (long)p * (p + 1) / 2;
-        int r = 0, c = lane;
-        while (c > r) { c -= r + 1; ++r; }
-#pragma unroll 2
-        for (long t = lane; t < n_pairs; t += 32) {
-            double v;
-            if (a.table) {
-                const PairTerm pt = a.table[t];
-                v = pt.c1 * sR[pt.i1];
-                if (pt.c2 != 0.0) v = fma(pt.c2, sR[pt.i2], v);
-                if (a.add_sig) v += gA[t];
-            } else {
-                v = slab_sum(gA + t, a.split_stride_sig, a.ksplit);
-            }
-            at(r, c) = v;
-            c += 32;
-            while (c > r) { c -= r + 1; ++r; }
+    // ---- Sigma and the u row through the layout table: one code per shared-memory slot
+#pragma unroll 4
+    for (int i = lane; i < nA; i += 32) {
+        const unsigned e = a.ltab[i];
+        const unsigned kind = e >> 29;
+        double v = 0.0;
+        if (kind == 1) {
+            v = ((e >> 26) & 1 ? 1.0 : 0.5) * sR[e & 0x1fff];
+            const unsigned c2 = (e >> 27) & 3;
+            if (c2) v = fma(c2 == 1 ? 0.5 : -0.5, sR[(e >> 13) & 0x1fff], v);
+        } else if (kind == 2) {
+            v = sR[e & 0x1fff];
         }
-        for (int i = lane; i < p; i += 32) at(p, i) = sR[n_r + i];
+        A[i] = v;
     }
+    for (int i = lane; i < kCholWarpSlack; i += 32) A[nA + i] = 0.0;
     __syncwarp();
     // ---- + Phi^-1 on the diagonal (calc_noise_weights_inv); log det Phi as a mantissa product
     const double* P = a.Pext + (size_t)b * a.row;
@@ -1303,13 +1302,13 @@ __global__ void __launch_bounds__(32) chol_warp_kernel(CholArgs a) {
     // ---- Cholesky (isposdef + cholesky!, gls_likelihood.jl:211-217) with z = L^-1 u riding along (ldiv!, :220)
     int fail = 0, lex = 0;
     double lman = 1.0;
-    const bool two = NR == 64;
+    const bool two = NR > 32;
     for (int jb = 0; jb < nblk; ++jb) {
         if (4 * jb < 32) {
-            if (two) cw_block_step<true, true>(A, NR, jb, n1, p, lane, fail, lman, lex);
-            else cw_block_step<true, false>(A, NR, jb, n1, p, lane, fail, lman, lex);
+            if (two) cw_block_step<true, true>(A, NR, jb, p, lane, fail, lman, lex);
+            else cw_block_step<true, false>(A, NR, jb, p, lane, fail, lman, lex);
         } else {
-            cw_block_step<false, true>(A, NR, jb, n1, p, lane, fail, lman, lex);
+            cw_block_step<false, true>(A, NR, jb, p, lane, fail, lman, lex);
         }
         if ((jb & 7) == 7) {                               // 32 pivots: fold the mantissa product into the exponent sum
             int ex;
@@ -1359,7 +1358,7 @@ __global__ void phiinv_kernel(CholArgs a, double* __restrict__ out) {
     }
 }
 
-// test hook for div3_by: counts quotients that differ from the IEEE division in any bit
+// test hook for div3_by / div_fast / rcp_fast: counts quotients that differ from the IEEE division in any bit
 __global__ void div3_check_kernel(unsigned long long seed, long n, unsigned long long* mismatches) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1382,6 +1381,11 @@ __global__ void div3_check_kernel(unsigned long long seed, long n, unsigned long
     div3_by(a[0], a[1], a[2], b, q);
     unsigned long long bad = 0;
     for (int k = 0; k < 3; ++k) bad += __double_as_longlong(q[k]) != __double_as_longlong(a[k] / b);
+    // div_fast / rcp_fast over the range the chain kernel's operands live in (and well beyond): 2^-130 .. 2^130
+    const double num = (1.0 + unit()) * exp2((double)((int)(next() % 261) - 130)) * ((next() & 1) ? 1.0 : -1.0);
+    const double den = (1.0 + unit()) * exp2((double)((int)(next() % 261) - 130)) * ((next() & 1) ? 1.0 : -1.0);
+    bad += __double_as_longlong(div_fast(num, den)) != __double_as_longlong(num / den);
+    bad += __double_as_longlong(rcp_fast(den)) != __double_as_longlong(1.0 / den);
     if (bad) atomicAdd(mismatches, bad);
 }
 
@@ -1421,6 +1425,41 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Co-issue probe: the even warps of every block run the register-resident DFMA loop (mode & 1), the odd warps the DMMA
+// loop (mode & 2).  If scalar FP64 and the FP64 tensor path were separate pipes, mode 3 would deliver the sum of modes 1
+// and 2; on B200 it delivers what either delivers alone (profiles/r2_fp64_coissue.txt), i.e. one shared datapath - which
+// is why the chain kernel and the column-sum kernel are not fused into one warp-specialised kernel.
+__global__ void __launch_bounds__(256) fp64_coissue_kernel(double* out, int iters, int mode) {
+    const bool dfma_warp = ((threadIdx.x >> 5) & 1) == 0;
+    double s = 0.0;
+    if (dfma_warp) {
+        if (mode & 1) {
+            double x[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+            const double a = 1.0000001, c = 1e-7;
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = fma(x[i], a, c);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s += x[i];
+        }
+    } else if (mode & 2) {
+        double acc[16][2];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+        const double af = 1.0 + 1e-9 * threadIdx.x, bf = 1.0 - 1e-9 * threadIdx.x;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dmma8x8x4(acc[i][0], acc[i][1], af, bf);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+    }
     if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 

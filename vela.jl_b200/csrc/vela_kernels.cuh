@@ -151,6 +151,7 @@ struct CholArgs {
     long split_stride_r;
     int n_r, u_off;
     int add_sig;               // add Sig[t] (ECORR correction) to the assembled entry
+    const unsigned* ltab;      // chol_warp_kernel: layout table (one code per shared-memory slot), null = not available
     double* ahat;              // optional [B][p]: conditional mean of the marginalised amplitudes, Sigma u
     double* cf;                // optional [B][p][p] row-major upper Cholesky factor of Sigma^-1 (L^T)
 };
@@ -175,18 +176,27 @@ inline size_t chol_smem_doubles(int p, int pp, int nb, bool matrix_in_smem, int 
     return (size_t)2 * pp + (size_t)nb * (nb + 1) + nb + (size_t)(p + 1) * (nb + 1) +
            (matrix_in_smem ? (size_t)(p + 1) * (p + 2) / 2 : 0) + (size_t)n_r;   // n_r: column sums of the structured path
 }
-// K4w: one warp per walker, ranks up to 63 (vela_kernels.cu)
-__global__ void chol_warp_kernel(CholArgs a);
-inline size_t chol_warp_smem_bytes(int p, int n_ru) {   // matrix (column blocks of 4, rows padded to 32 / 64) + column sums / u
-    const int n1 = p + 1, NR = n1 <= 32 ? 32 : 64, nblk = (n1 + 3) / 4;
-    return ((size_t)(4 * nblk * NR - 8 * nblk * (nblk - 1)) + (size_t)((n_ru + 1) & ~1)) * sizeof(double);
+// K4w: one warp per walker, ranks up to 63 (vela_kernels.cu).  Shared-memory layout of the walker's matrix (rows 0..p,
+// row p = u^T): columns in blocks of four, column k holding rows (k & ~3) .. NR-1, NR = p + 1 rounded up to even.
+constexpr int kCholWarpMaxRows = 64;
+constexpr int kCholWarpSlack = 64;       // zeroed doubles behind the matrix: lanes past the last row read them
+__host__ __device__ inline int cw_col_base(int m, int NR) { return 4 * m * NR - 8 * m * (m - 1); }   // first entry of column block m
+inline int cw_slot(int row, int col, int NR) { return cw_col_base(col >> 2, NR) + (col & 3) * (NR - (col & ~3)) + row - (col & ~3); }
+inline size_t chol_warp_smem_bytes(int p, int n_ru) {
+    const int n1 = p + 1, NR = (n1 + 1) & ~1, nblk = (n1 + 3) / 4;
+    return ((size_t)cw_col_base(nblk, NR) + kCholWarpSlack + (size_t)((n_ru + 1) & ~1)) * sizeof(double);
 }
+// layout-table codes (one per shared-memory slot): [12:0] i1, [25:13] i2, [26] c1 is 1.0 (else 0.5), [28:27] c2
+// (0 none, 1 +0.5, 2 -0.5), [31:29] kind (0 zero, 1 c1 R[i1] + c2 R[i2], 2 copy R[i1])
+constexpr int kCholWarpMaxCols = 8191;
+__global__ void chol_warp_kernel(CholArgs a);
 __global__ void phiinv_kernel(CholArgs a, double* out);
 __global__ void div3_check_kernel(unsigned long long seed, long n, unsigned long long* mismatches);
 __global__ void sincos_cr_kernel(const double* x, int n, double* s, double* c);
 __global__ void dfma_peak_kernel(double* out, int iters);
 __global__ void dmma_peak_kernel(double* out, int iters);
 __global__ void dmma_mix_kernel(double* out, int iters, int nmul, int nlds);
+__global__ void fp64_coissue_kernel(double* out, int iters, int mode);
 
 template <int BK, int STAGES, int UC, int WC, bool SPLIT>
 __global__ void colsum_kernel(ColsumArgs a);
