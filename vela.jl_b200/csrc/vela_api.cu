@@ -10,10 +10,12 @@
 #include <condition_variable>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <memory>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include "vela_host_prep.h"
@@ -57,6 +59,7 @@ int upload(T** dst, const T* src, size_t n) {
 
 inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
 constexpr long kSplitRows = 2048;   // walker rows reserved for split-K slabs of small batches
+constexpr long kGraphMaxBatch = 2048; // host batches up to this size replay a captured CUDA graph
 constexpr long kMaxBigSplit = 4;    // split-K slabs kept for full-size batches (wave quantisation), memory permitting
 
 struct Buffers {  // per-device, per-batch scratch (grown on demand)
@@ -68,7 +71,18 @@ struct Buffers {  // per-device, per-batch scratch (grown on demand)
     long r_rows = 0;
     double *h_params = nullptr, *h_out = nullptr, *h_lnprior = nullptr;  // pinned
     long h_cap = 0;
+    // Small host batches (emcee-sized) replay a captured CUDA graph: staging copy in, every kernel of the step, result
+    // copy out - one launch instead of eight.  Keyed by (walkers, mode, prior source); the graphs hold the addresses of
+    // the buffers above, so they are dropped whenever a buffer is reallocated.
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int launches = 0; };
+    std::map<std::tuple<long, int, int, int>, GraphEntry> graphs;
 };
+
+void drop_graphs(Buffers& b) {
+    for (auto& kv : b.graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    b.graphs.clear();
+}
 
 struct DeviceModel {
     int dev = 0;
@@ -172,6 +186,7 @@ struct VelaPulsar {
     std::mutex mtx;
     std::atomic<int64_t> launches{0};   // several feeder threads when the handle spans several devices
     bool stage_timing = false;
+    bool graphs_ok = true;               // cleared when a capture fails (the plain launch path always works)
     bool have_priors = false;
     long max_chunk = 0;  // walkers per device per pass
     cudaKernel_t spec_chain = nullptr;   // NVRTC-specialised chain kernel (vela_jit.cu); null = generic kernel only
@@ -184,6 +199,7 @@ struct VelaPulsar {
 namespace {
 
 void free_buffers(Buffers& b) {
+    drop_graphs(b);
     cudaFree(b.params); cudaFree(b.Pext); cudaFree(b.tzr); cudaFree(b.partial); cudaFree(b.Y); cudaFree(b.W);
     cudaFree(b.Sig); cudaFree(b.U); cudaFree(b.Sq); cudaFree(b.V); cudaFree(b.out); cudaFree(b.lnprior); cudaFree(b.R);
     b.params = b.Pext = b.tzr = b.partial = b.Y = b.W = b.Sig = b.U = b.Sq = b.V = b.out = b.lnprior = b.R = nullptr;
@@ -245,6 +261,7 @@ int ensure_host_buffers(VelaPulsar* h, DeviceModel& d, long B) {
     if (b.h_params) cudaFreeHost(b.h_params);
     if (b.h_out) cudaFreeHost(b.h_out);
     if (b.h_lnprior) cudaFreeHost(b.h_lnprior);
+    drop_graphs(b);
     b.h_params = b.h_out = b.h_lnprior = nullptr;   // a failed allocation below must not leave stale pointers behind
     b.h_cap = 0;
     long cap = std::max<long>(B, 64);
@@ -544,6 +561,15 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         int ksplit;
         if (h->sp.active) {
             ksplit = launch_colsum(h, d, B, st, wy, &cs);
+            if (ksplit > 4) {
+                // emcee-sized batches split K deeply to fill the SMs; summing 16 - 64 slabs per entry is then the longest
+                // serial stretch of the finishing kernel (one warp or CTA per walker), so a wide kernel does it first, in
+                // slice order like the finishing kernels would
+                const long n = B * (long)h->sp.n_cols;
+                slab_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.R, cs.split_stride_r, ksplit, n);
+                h->launches += 1;
+                ksplit = 1;
+            }
             if (h->n_eg > 0) {   // the ECORR correction is accumulated into a zeroed packed triangle that K4 adds
                 cudaMemsetAsync(b.Sig, 0, (size_t)B * h->ld_sig * sizeof(double), st);
                 n_rows_partial += launch_ecorr_correction(h, d, B, st, wy);
@@ -1015,6 +1041,58 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
             if ((rc = ensure_device_buffers(h, d, n))) return rc;
             Buffers& b = d.buf;
             const bool timing = h->stage_timing && i == 0;
+            static const bool graphs_off = getenv("VELA_B200_GRAPHS") && atoi(getenv("VELA_B200_GRAPHS")) == 0;
+            if (nd == 1 && n <= kGraphMaxBatch && !timing && h->graphs_ok && !graphs_off) {
+                // ---- small batch: pack, then replay the captured graph of the whole step
+                if (rs == nf && cs == 1) memcpy(b.h_params, params + r0[i] * rs, sizeof(double) * n * nf);
+                else
+                    for (long r = 0; r < n; ++r)
+                        for (long k = 0; k < nf; ++k) b.h_params[r * nf + k] = params[(r0[i] + r) * rs + k * cs];
+                const int prior_src = !with_prior ? 0 : (lnprior ? 1 : (h->have_priors ? 2 : 3));
+                if (prior_src == 1) memcpy(b.h_lnprior, lnprior + r0[i], sizeof(double) * n);
+                auto key = std::make_tuple(n, mode, with_prior, prior_src);
+                auto it = b.graphs.find(key);
+                if (it == b.graphs.end()) {
+                    Buffers::GraphEntry ge;
+                    const int64_t l0 = h->launches.load();
+                    cudaGraph_t graph = nullptr;
+                    cudaError_t ge_rc = cudaStreamBeginCapture(d.stream, cudaStreamCaptureModeThreadLocal);
+                    int erc = 0;
+                    if (ge_rc == cudaSuccess) {
+                        if (nf > 0) cudaMemcpyAsync(b.params, b.h_params, sizeof(double) * n * nf, cudaMemcpyHostToDevice, d.stream);
+                        const double* g_lp = nullptr;
+                        if (prior_src == 2) {
+                            prior_kernel<<<(unsigned)((n + 127) / 128), 128, 0, d.stream>>>(d.priors, (int)nf, b.params, n, 0, b.lnprior);
+                            h->launches += 1;
+                            g_lp = b.lnprior;
+                        } else if (prior_src == 1) {
+                            cudaMemcpyAsync(b.lnprior, b.h_lnprior, sizeof(double) * n, cudaMemcpyHostToDevice, d.stream);
+                            g_lp = b.lnprior;
+                        }
+                        erc = enqueue_batch(h, d, b.params, n, mode, with_prior, g_lp, b.out, d.stream);
+                        cudaMemcpyAsync(b.h_out, b.out, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream);
+                        ge_rc = cudaStreamEndCapture(d.stream, &graph);
+                    }
+                    if (ge_rc == cudaSuccess && !erc && graph) ge_rc = cudaGraphInstantiate(&ge.exec, graph, 0);
+                    if (graph) cudaGraphDestroy(graph);
+                    ge.launches = (int)(h->launches.load() - l0);
+                    h->launches -= ge.launches;              // counted per replay below
+                    if (ge_rc != cudaSuccess || erc || !ge.exec) {
+                        cudaGetLastError();
+                        h->graphs_ok = false;                // the plain path below takes over, for good
+                    } else {
+                        it = b.graphs.emplace(key, ge).first;
+                    }
+                }
+                if (it != b.graphs.end()) {
+                    scratch_acquire(d, d.stream);
+                    cudaError_t le = cudaGraphLaunch(it->second.exec, d.stream);
+                    scratch_release(d, d.stream);
+                    h->launches += it->second.launches;
+                    if (le != cudaSuccess) return fail(VELA_ERR_CUDA, "device %d: graph launch failed: %s", d.dev, cudaGetErrorString(le));
+                    return 0;
+                }
+            }
             scratch_acquire(d, d.stream);
             if (timing) cudaEventRecord(d.ev[5], d.stream);
             cudaError_t ce = cudaSuccess;

@@ -821,6 +821,13 @@ __device__ __forceinline__ double slab_sum(const double* g, long stride, int n) 
     return (v0 + v1) + (v2 + v3);
 }
 
+// R[i] <- sum over the split-K slabs of R[z * stride + i], in slice order (deterministic); one thread per entry of the
+// first slab.  Used when a small batch split K deeply (see enqueue_batch).
+__global__ void slab_reduce_kernel(double* R, long stride, int n_slabs, long n) {
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) R[i] = slab_sum(R + i, stride, n_slabs);
+}
+
 // Row-packed lower triangle: entry (r, c <= r) of the walker's matrix (rows 0..p, row p = u^T and -z.z)
 __device__ __forceinline__ size_t tri(int r, int c) { return (size_t)r * (r + 1) / 2 + c; }
 
@@ -1233,10 +1240,14 @@ __global__ void __launch_bounds__(32) chol_warp_kernel(CholArgs a) {
     {
         const double* gR = a.R + (size_t)b * a.ld_r;
         const int n_ru = a.n_r + p;
+        // every load of the walker's row is independent: unrolled so that they are all in flight together (one warp
+        // has nobody to hide a global-memory round trip behind)
         if (a.ksplit == 1) {
+#pragma unroll 8
             for (int i = lane; i < a.n_r; i += 32) sR[i] = gR[i];
             for (int i = lane; i < p; i += 32) sR[a.n_r + i] = gR[a.u_off + i];
         } else {
+#pragma unroll 4
             for (int i = lane; i < a.n_r; i += 32) sR[i] = slab_sum(gR + i, a.split_stride_r, a.ksplit);
             for (int i = lane; i < p; i += 32) sR[a.n_r + i] = slab_sum(gR + a.u_off + i, a.split_stride_r, a.ksplit);
         }
@@ -1244,9 +1255,9 @@ __global__ void __launch_bounds__(32) chol_warp_kernel(CholArgs a) {
     }
     __syncwarp();
     // ---- Sigma and the u row through the layout table: one code per shared-memory slot
-#pragma unroll 4
+#pragma unroll 8
     for (int i = lane; i < nA; i += 32) {
-        const unsigned e = a.ltab[i];
+        const unsigned e = __ldg(a.ltab + i);              // the same 8 KB for every walker: read-only path, L1-resident
         const unsigned kind = e >> 29;
         double v = 0.0;
         if (kind == 1) {

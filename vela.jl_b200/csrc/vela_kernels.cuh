@@ -190,6 +190,7 @@ inline size_t chol_warp_smem_bytes(int p, int n_ru) {
 // (0 none, 1 +0.5, 2 -0.5), [31:29] kind (0 zero, 1 c1 R[i1] + c2 R[i2], 2 copy R[i1])
 constexpr int kCholWarpMaxCols = 8191;
 __global__ void chol_warp_kernel(CholArgs a);
+__global__ void slab_reduce_kernel(double* R, long stride, int n_slabs, long n);
 __global__ void phiinv_kernel(CholArgs a, double* out);
 __global__ void div3_check_kernel(unsigned long long seed, long n, unsigned long long* mismatches);
 __global__ void sincos_cr_kernel(const double* x, int n, double* s, double* c);
