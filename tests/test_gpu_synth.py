@@ -173,3 +173,23 @@ def test_wideband_model_dm_and_scaled_errors(datasets, oracle):
     np.testing.assert_allclose(psr.scaled_dm_uncertainties(ds.truth), 1 / np.sqrt(wo[n:]), rtol=1e-13)
     with pytest.raises(NotImplementedError):
         datasets("config3_gp", 1200)[1].model_dm(datasets("config3_gp", 1200)[0].truth)
+
+
+def test_warp_per_walker_cholesky_matches_cta_kernel(vb, monkeypatch):
+    """chol_warp_kernel (opt-in: VELA_B200_CHOL_WARP=1; one warp per walker, layout-table assembly) against the default
+    CTA-per-walker kernel on the same walkers, small and large batches (the small ones also take the wide slab reduction),
+    and a rank that leaves the second row slot partly empty."""
+    for name, ntoa in (("config3_gp", 1500), ("extra_dmjump_bits_wb", None)):
+        ds = vb.synth.make_dataset(name, lambda m, t: vb.Pulsar(m, t), ntoa=ntoa)
+        psr = vb.Pulsar(ds.model, ds.toas)
+        if not psr.sigma_structured():
+            continue
+        for B in (3, 70, 1500):
+            W = ds.walkers(B, seed=11)
+            monkeypatch.delenv("VELA_B200_CHOL_WARP", raising=False)
+            ref = psr.lnlike_vectorized(W)
+            monkeypatch.setenv("VELA_B200_CHOL_WARP", "1")
+            got = psr.lnlike_vectorized(W)
+            monkeypatch.delenv("VELA_B200_CHOL_WARP", raising=False)
+            assert np.all(np.isfinite(ref))
+            np.testing.assert_allclose(got, ref, rtol=1e-13)

@@ -7,7 +7,7 @@ import sys
 name, ntoa, B = sys.argv[1], sys.argv[2], sys.argv[3]
 VARIANTS = [
     ("default", {}),
-    ("chol_cta", {"VELA_B200_CHOL_WARP": "0"}),
+    ("chol_warp", {"VELA_B200_CHOL_WARP": "1"}),
     ("mb4", {"VELA_B200_JIT_MINBLOCKS": "4"}),
     ("mb6", {"VELA_B200_JIT_MINBLOCKS": "6"}),
     ("unroll2_mb5", {"VELA_B200_JIT_UNROLL": "2"}),

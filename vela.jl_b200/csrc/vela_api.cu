@@ -561,10 +561,11 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         int ksplit;
         if (h->sp.active) {
             ksplit = launch_colsum(h, d, B, st, wy, &cs);
-            if (ksplit > 4) {
-                // emcee-sized batches split K deeply to fill the SMs; summing 16 - 64 slabs per entry is then the longest
-                // serial stretch of the finishing kernel (one warp or CTA per walker), so a wide kernel does it first, in
-                // slice order like the finishing kernels would
+            const bool warp_on = getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 1;
+            if (ksplit > 4 && warp_on && d.ltab && !d_ahat && h->n_eg == 0) {
+                // emcee-sized batches split K deeply to fill the SMs; summing 16 - 64 slabs per entry would be the longest
+                // serial stretch of the warp-per-walker finishing kernel, so a wide kernel does it first, in slice order
+                // (the CTA-per-walker kernel sums its slabs itself: 128 threads, cheaper than one more launch)
                 const long n = B * (long)h->sp.n_cols;
                 slab_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.R, cs.split_stride_r, ksplit, n);
                 h->launches += 1;
@@ -593,10 +594,13 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
             ch.split_stride_sig = sa.split_stride_sig; ch.split_stride_u = sa.split_stride_u;
         }
         ch.ahat = d_ahat; ch.cf = d_cf;
-        // ranks up to 63 on the structured path: one warp per walker (chol_warp_kernel); the conditional-mean outputs, the
-        // ECORR correction, dense bases and larger ranks keep the CTA-per-walker kernel.  VELA_B200_CHOL_WARP=0 forces the latter (A/B measurements).
-        static const bool warp_off = getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 0;
-        ch.ltab = d.ltab;
+        // ranks up to 63 on the structured path can run one warp per walker (chol_warp_kernel) instead of one CTA.
+        // Measured on B200 at rank 60 (profiles/r2_chol_variants.md): 8192 walkers 0.30 ms either way (both are bound by
+        // the dependent chain of a 60-column factorisation: 12 resident warps per SM at 36 % issue utilisation for the
+        // warp kernel, 18 at 3.4 barrier stalls per issue for the CTA kernel); a lone walker 49 us (warp) against 35 us
+        // (CTA, four warps share the assembly and the trailing updates).  The CTA kernel therefore stays the default and
+        // VELA_B200_CHOL_WARP=1 selects the warp kernel (A/B measurements, tests).
+        const bool warp_off = !(getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 1);
         if (d.ltab && !d_ahat && !warp_off && h->n_eg == 0) {
             const int n_ru = h->sp.n_r + h->p;
             chol_warp_kernel<<<(unsigned)B, 32, chol_warp_smem_bytes(h->p, n_ru), st>>>(ch);
