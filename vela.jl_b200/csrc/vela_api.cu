@@ -1054,7 +1054,9 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
                         for (long k = 0; k < nf; ++k) b.h_params[r * nf + k] = params[(r0[i] + r) * rs + k * cs];
                 const int prior_src = !with_prior ? 0 : (lnprior ? 1 : (h->have_priors ? 2 : 3));
                 if (prior_src == 1) memcpy(b.h_lnprior, lnprior + r0[i], sizeof(double) * n);
-                auto key = std::make_tuple(n, mode, with_prior, prior_src);
+                // the kernel-variant switch read at enqueue time is part of the key (A/B tests flip it between calls)
+                const int variant = (getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 1) ? 16 : 0;
+                auto key = std::make_tuple(n, mode, with_prior, prior_src | variant);
                 auto it = b.graphs.find(key);
                 if (it == b.graphs.end()) {
                     Buffers::GraphEntry ge;
