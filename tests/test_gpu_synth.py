@@ -193,3 +193,23 @@ def test_warp_per_walker_cholesky_matches_cta_kernel(vb, monkeypatch):
             monkeypatch.delenv("VELA_B200_CHOL_WARP", raising=False)
             assert np.all(np.isfinite(ref))
             np.testing.assert_allclose(got, ref, rtol=1e-13)
+
+
+@pytest.mark.parametrize("name,ntoa", [("config3_gp", 1500), ("extra_ecorr_gp_r140", None), ("config4_dd_wb", 900)])
+def test_panel_cholesky_matches_shared_memory_kernel(name, ntoa, vb, oracle, monkeypatch):
+    """chol_panel_kernel (large ranks: 32-column panels + DMMA trailing updates on the global scratch) forced onto small
+    ranks with VELA_B200_CHOL_SMEM=0, against the shared-memory kernel and the older global-scratch kernel."""
+    ds = vb.synth.make_dataset(name, lambda m, t: vb.Pulsar(m, t), ntoa=ntoa)
+    W = ds.walkers(67, seed=4)
+    ref = vb.Pulsar(ds.model, ds.toas).lnlike_vectorized(W)
+    monkeypatch.setenv("VELA_B200_CHOL_SMEM", "0")
+    big = vb.Pulsar(ds.model, ds.toas)
+    monkeypatch.delenv("VELA_B200_CHOL_SMEM")
+    got = big.lnlike_vectorized(W)
+    monkeypatch.setenv("VELA_B200_CHOL_PANEL", "0")
+    old = big.lnlike_vectorized(W[:66])          # another batch size: not the cached graph of the panel kernel
+    monkeypatch.delenv("VELA_B200_CHOL_PANEL")
+    np.testing.assert_allclose(got, ref, rtol=1e-12)
+    np.testing.assert_allclose(old, ref[:66], rtol=1e-12)
+    md = vb.ModelDescriptor(ds.model, ds.toas)
+    np.testing.assert_allclose(got[:4], oracle.lnlike_batch(md, W[:4]), rtol=1e-9)

@@ -234,7 +234,7 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
         CU(cudaMemsetAsync(b.R, 0, (size_t)b.r_rows * h->sp.n_cols * sizeof(double), d.stream));
     }
     if (h->p > 0 && h->sp.active && h->n_eg == 0) {
-        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * (h->p + 1) * (h->pp + 1) * sizeof(double)));
+        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * chol_panel_scratch_doubles(h->p, h->pp) * sizeof(double)));
     } else if (h->p > 0) {
         // Sigma / U scratch: at least `cap` walker rows, and never fewer than kSplitRows so that small batches can
         // hold several split-K slabs
@@ -244,7 +244,7 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
         CU(cudaMalloc((void**)&b.U, (size_t)b.sig_rows * h->pp * sizeof(double)));
         CU(cudaMemsetAsync(b.Sig, 0, (size_t)b.sig_rows * h->ld_sig * sizeof(double), d.stream));
         CU(cudaMemsetAsync(b.U, 0, (size_t)b.sig_rows * h->pp * sizeof(double), d.stream));
-        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * (h->p + 1) * (h->pp + 1) * sizeof(double)));
+        if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * chol_panel_scratch_doubles(h->p, h->pp) * sizeof(double)));
         if (h->n_eg > 0) {
             size_t vb = (size_t)cap * h->eg_pad * h->ldv * sizeof(double);
             CU(cudaMalloc((void**)&b.V, vb));
@@ -476,6 +476,7 @@ int set_smem_attrs(int dev) {
     // variant keeps the default split (its matrix traffic wants the L1)
     for (auto k : {chol_finish_kernel<8, true>, chol_finish_kernel<16, true>})
         CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
     CU(cudaFuncSetAttribute(chol_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CU(cudaFuncSetAttribute(chol_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ecorr_basis_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
@@ -601,9 +602,14 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         // (CTA, four warps share the assembly and the trailing updates).  The CTA kernel therefore stays the default and
         // VELA_B200_CHOL_WARP=1 selects the warp kernel (A/B measurements, tests).
         const bool warp_off = !(getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 1);
+        ch.ltab = d.ltab;
         if (d.ltab && !d_ahat && !warp_off && h->n_eg == 0) {
             const int n_ru = h->sp.n_r + h->p;
             chol_warp_kernel<<<(unsigned)B, 32, chol_warp_smem_bytes(h->p, n_ru), st>>>(ch);
+        } else if (!h->chol_smem && !d_ahat && !(getenv("VELA_B200_CHOL_PANEL") && atoi(getenv("VELA_B200_CHOL_PANEL")) == 0)) {
+            // large ranks: 32-column panels in shared memory, trailing updates on DMMA (chol_panel_kernel)
+            const int n_ru = h->sp.active ? h->sp.n_r : 0;
+            chol_panel_kernel<<<(unsigned)B, kPanelThreadsHost, chol_panel_smem_bytes(h->p, h->pp, n_ru), st>>>(ch);
         } else {
         // 96 threads per walker at full size (more resident walkers, fewer idle warps in the serial phases: 0.41 ->
         // 0.35 ms at rank 60), 128 for small batches and large ranks (tools/probes/gpu_chol_probe.py)
@@ -877,6 +883,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         const int n_r = h->sp.active ? h->sp.n_r : 0;
         size_t need = chol_smem_doubles(h->p, h->pp, h->chol_nb, true, n_r) * sizeof(double);
         h->chol_smem = need <= 200 * 1024;
+        if (const char* e = getenv("VELA_B200_CHOL_SMEM")) { if (atoi(e) == 0) h->chol_smem = false; }   // tests: force the global-scratch kernels
         if (!h->chol_smem) h->chol_nb = 16;   // the global-scratch variant exists for block width 16 only
         h->chol_smem_bytes = h->chol_smem ? need : chol_smem_doubles(h->p, h->pp, h->chol_nb, false, n_r) * sizeof(double);
         // ranks up to 63 on the structured path: layout table of the warp-per-walker Cholesky kernel - for every
@@ -980,7 +987,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
 
     // walkers per device per pass: bound the y/w/Sigma scratch to ~1/4 of the device memory
     if (h->kernel_kind != VELA_KERNEL_WHITE) {
-        size_t per = (size_t)2 * h->n_rows_pad * 8 + (h->sp.active ? (size_t)h->sp.n_cols * 32 + (h->n_eg ? (size_t)h->ld_sig * 8 : 0) : (size_t)h->ld_sig * 8) + (size_t)h->pp * 8 + (h->chol_smem ? 0 : (size_t)(h->p + 1) * (h->pp + 1) * 8) + (size_t)h->eg_pad * h->ldv * 8;
+        size_t per = (size_t)2 * h->n_rows_pad * 8 + (h->sp.active ? (size_t)h->sp.n_cols * 32 + (h->n_eg ? (size_t)h->ld_sig * 8 : 0) : (size_t)h->ld_sig * 8) + (size_t)h->pp * 8 + (h->chol_smem ? 0 : chol_panel_scratch_doubles(h->p, h->pp) * 8) + (size_t)h->eg_pad * h->ldv * 8;
         size_t free_b = 0, total_b = 0;
         cudaSetDevice(devices[0]);
         cudaMemGetInfo(&free_b, &total_b);

@@ -1136,6 +1136,259 @@ template __global__ void chol_finish_kernel<16, true>(CholArgs);
 template __global__ void chol_finish_kernel<16, false>(CholArgs);
 
 // ------------------------------------------------------------------------------------------
+// K4p  Cholesky finish for large ranks: 32-column panels in shared memory, trailing updates on the FP64 tensor cores
+// ------------------------------------------------------------------------------------------
+// Ranks whose triangle does not fit shared memory (p >~ 220; the 100k-TOA array pulsar has p = 300) keep the matrix
+// (rows 0..p, row p = u^T, pitched rows) in an L2-resident global scratch.  chol_finish_kernel<16, false> updates that
+// scratch with 2 x 2 register tiles 16 columns at a time: 16 FMAs per read-modify-write of the triangle, latency-bound on
+// L2 (ncu: FP64 pipe 26 % active, 8.7 GB of DRAM traffic per 2048 walkers).  Here a block column is 32 wide, lives in
+// shared memory while it is factorised, and the trailing update A22 -= L21 L21^T runs on DMMA (m8n8k4) straight from
+// that shared panel: 32 FMAs per read-modify-write, half the passes over the triangle, and the FP64 pipe does the work.
+//   per panel (k0 .. k0+31), one CTA of 8 warps per walker:
+//     1. rows k0..p of the panel: global -> shared (P[row - k0][0..31], pitch 36: conflict-free DMMA fragment reads)
+//     2. factorise it in place, 8 columns at a time: warp 0 factorises the 8 x 8 diagonal block in registers
+//        (factor_panel_diag), one thread per row solves against it, then lane = column / warp = row strip apply the
+//        rank-8 update to the panel's remaining columns (the lane keeps its column's 8 multipliers in registers)
+//     3. the finished columns go back to global (they are L)
+//     4. trailing update: 32 x 32 tiles of the lower triangle of rows k1..p, one warp per tile, 4 x 4 m8n8k4
+//        accumulators, 8 k-steps; the C tile is fetched before the k-loop and written once
+// u rides along as row p (z = L^-1 u, entry (p, p) = -z.z) exactly as in the other finishing kernels.
+constexpr int kPanelW = 32;
+constexpr int kPanelPitch = kPanelW + 4;
+constexpr int kPanelThreads = 256;
+
+// 8 x 8 diagonal block at rows / columns c0 .. c0+7 of the shared panel, by one warp in registers (lane r owns row r)
+__device__ __forceinline__ void factor_panel_diag(double* P, int c0, int nbb, double* dblk, double* rdiag, int* fail) {
+    const int lane = threadIdx.x & 31;
+    double row[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        row[c] = (lane < nbb && c <= lane) ? P[(c0 + lane) * kPanelPitch + c0 + c] : ((lane == c) ? 1.0 : 0.0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        double d = __shfl_sync(0xffffffffu, row[c], c);
+        if (c < nbb && (!(d > 0.0) || !isfinite(d))) { if (lane == 0) *fail = 1; d = 1.0; }
+        const double rd = rsqrt(d);
+        if (lane == c) { row[c] = d * rd; rdiag[c] = rd; }
+        else if (lane > c) row[c] *= rd;
+#pragma unroll
+        for (int q = c + 1; q < 8; ++q) {
+            const double lqc = __shfl_sync(0xffffffffu, row[c], q);
+            if (lane >= q) row[q] = fma(-row[c], lqc, row[q]);
+        }
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c <= lane) {
+                dblk[lane * 9 + c] = row[c];
+                if (lane < nbb) P[(c0 + lane) * kPanelPitch + c0 + c] = row[c];
+            }
+    }
+}
+
+__global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double scratch[kPanelThreads / 32];
+    __shared__ int sFail;
+    const long b = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int p = a.p, pp = a.pp, n1 = p + 1;
+    const int lda = pp + 2;                                // even pitch of the global matrix rows
+    const int prow = ((n1 + 31) & ~31) + 32;               // panel rows incl. zero padding for the last tiles
+    double* phi = smem;                                    // [pp]
+    double* dblk = phi + pp;                               // [8][9]
+    double* rdiag = dblk + 72;                             // [8]
+    double* P = rdiag + 8;                                 // [prow][kPanelPitch]; the column sums / u alias it during assembly
+    double* sR = P;
+    double* A = a.Sq + (size_t)b * n1 * lda;
+    if (tid == 0) sFail = 0;
+
+    // ---- Sigma (lower triangle, rows 0..p-1) and u (row p) into the global scratch
+    {
+        const long n_pairs = (long)p * (p + 1) / 2;
+        const double* gA = a.Sig + (size_t)b * a.ld_sig;
+        if (a.table) {
+            const double* gR = a.R + (size_t)b * a.ld_r;
+            for (int i = tid; i < a.n_r; i += nt) sR[i] = slab_sum(gR + i, a.split_stride_r, a.ksplit);
+            __syncthreads();
+        }
+        int r = 0, c = tid;
+        while (c > r) { c -= r + 1; ++r; }
+#pragma unroll 2
+        for (long t = tid; t < n_pairs; t += nt) {
+            double v;
+            if (a.table) {
+                const PairTerm pt = a.table[t];
+                v = pt.c1 * sR[pt.i1];
+                if (pt.c2 != 0.0) v = fma(pt.c2, sR[pt.i2], v);
+                if (a.add_sig) v += gA[t];
+            } else {
+                v = slab_sum(gA + t, a.split_stride_sig, a.ksplit);
+            }
+            A[(size_t)r * lda + c] = v;
+            c += nt;
+            while (c > r) { c -= r + 1; ++r; }
+        }
+        const double* gU = a.table ? a.R + a.u_off : a.U;
+        const long ldu = a.table ? a.ld_r : a.ld_u, su = a.table ? a.split_stride_r : a.split_stride_u;
+        for (int i = tid; i < p; i += nt) A[(size_t)p * lda + i] = slab_sum(gU + (size_t)b * ldu + i, su, a.ksplit);
+        if (tid == 0) A[(size_t)p * lda + p] = 0.0;
+    }
+    // ---- Phi^-1
+    const double* Pw = a.Pext + (size_t)b * a.row;
+    for (int g = 0; g < a.n_gp; ++g) {
+        GPDev gp = a.gp[g];
+        if (gp.kind == VELA_GP_MARGINALIZED_TM) {
+            for (int i = tid; i < gp.n; i += nt) phi[gp.col0 + i] = a.gp_data[gp.data0 + i];
+        } else {
+            const double fyr = 1.0 / 3600 / 24 / 365.25;
+            const double denom = 12 * (CUDART_PI * CUDART_PI) * fyr * fyr * fyr;
+            double amp = exp10(Pw[gp.par_log10_amp]), gamma = Pw[gp.par_gamma], f1 = Pw[gp.par_f1];
+            double P1 = amp * amp / denom * pow(fyr / f1, gamma) * f1;
+            for (int i = tid; i < gp.n; i += nt) {
+                double v = 1 / (P1 * exp(-gamma * a.gp_data[gp.data0 + i]));
+                phi[gp.col0 + i] = v;
+                phi[gp.col0 + gp.n + i] = v;
+            }
+        }
+    }
+    __syncthreads();                                       // phi complete; the triangle in global is complete (same block)
+    double lphi = 0.0;
+    for (int i = tid; i < p; i += nt) {
+        lphi += log(phi[i]);
+        A[(size_t)i * lda + i] += phi[i];
+    }
+    const double logdetPhi = -block_sum(lphi, scratch);
+    __syncthreads();
+
+    // ---- blocked factorisation
+    const int gid = lane >> 2, tig = lane & 3;
+    double ldsum = 0.0;                                    // sum of log L_cc over the columns this thread finalises
+    for (int k0 = 0; k0 < p; k0 += kPanelW) {
+        const int nb = min(kPanelW, p - k0), k1 = k0 + nb;
+        const int m = n1 - k0;                             // panel rows: global rows k0 .. p
+        // 1. panel -> shared (zero-padded to 32 columns and to `mpad` rows)
+        const int mpad = min(prow, ((m + 31) & ~31) + 32);
+        for (int e = tid; e < mpad * kPanelW; e += nt) {
+            const int i = e >> 5, c = e & 31;
+            double v = 0.0;
+            if (i < m && c < nb && k0 + c <= k0 + i) v = A[(size_t)(k0 + i) * lda + k0 + c];
+            P[i * kPanelPitch + c] = v;
+        }
+        __syncthreads();
+        // 2. factorise the panel, 8 columns at a time
+        for (int c0 = 0; c0 < nb; c0 += 8) {
+            const int nbb = min(8, nb - c0);
+            if (warp == 0) factor_panel_diag(P, c0, nbb, dblk, rdiag, &sFail);
+            __syncthreads();
+            for (int i = c0 + nbb + tid; i < m; i += nt) {           // rows below the diagonal block: x L_kk^T = row
+                double x[8];
+                double* row = P + i * kPanelPitch + c0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) x[c] = c < nbb ? row[c] : 0.0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < nbb) {
+                        double v = x[c];
+#pragma unroll
+                        for (int q = 0; q < c; ++q) v = fma(-x[q], dblk[c * 9 + q], v);
+                        x[c] = v * rdiag[c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < nbb) row[c] = x[c];
+            }
+            __syncthreads();
+            // rank-nbb update of the panel's remaining columns: lane = column, warp = row strip
+            const int c2 = c0 + 8 + lane;
+            if (c2 < nb) {
+                double lj[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) lj[c] = P[c2 * kPanelPitch + c0 + c];
+                for (int i = c2 + ((warp - c2) % nwarps + nwarps) % nwarps; i < m; i += nwarps) {   // rows i >= c2, i = warp (mod nwarps)
+                    const double* li = P + i * kPanelPitch + c0;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc = fma(li[c], lj[c], acc);
+                    P[i * kPanelPitch + c2] -= acc;
+                }
+            }
+            __syncthreads();
+        }
+        // 3. the finished columns back to global; log L_cc of the pivots
+        for (int e = tid; e < m * kPanelW; e += nt) {
+            const int i = e >> 5, c = e & 31;
+            if (c < nb && c <= i) A[(size_t)(k0 + i) * lda + k0 + c] = P[i * kPanelPitch + c];
+        }
+        for (int c = tid; c < nb; c += nt) ldsum += log(P[c * kPanelPitch + c]);
+        // 4. trailing update on DMMA: rows / columns k1 .. p, 32 x 32 tiles of the lower triangle, one warp each
+        const int m2 = n1 - k1;
+        const int T = (m2 + 31) >> 5;
+        const double* P2 = P + nb * kPanelPitch;           // panel rows below the diagonal block: L21
+        for (int tile = warp; tile < T * (T + 1) / 2; tile += nwarps) {
+            int ti = 0;
+            while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+            const int tj = tile - ti * (ti + 1) / 2;
+            double acc[4][4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            const double* pa = P2 + (ti * 32 + gid) * kPanelPitch + tig;
+            const double* pb = P2 + (tj * 32 + gid) * kPanelPitch + tig;
+#pragma unroll
+            for (int kk = 0; kk < kPanelW / 4; ++kk) {
+                double fa[4], fb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    fa[i] = pa[i * 8 * kPanelPitch + kk * 4];
+                    fb[i] = pb[i * 8 * kPanelPitch + kk * 4];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = ti * 32 + i * 8 + gid, cc = tj * 32 + j * 8 + 2 * tig;
+                    if (rr < m2) {
+                        double* dst = A + (size_t)(k1 + rr) * lda + k1 + cc;
+                        if (cc + 1 <= rr) {                // both entries in the lower triangle: one 16-byte access
+                            double2 v = *reinterpret_cast<double2*>(dst);
+                            v.x -= acc[i][j][0];
+                            v.y -= acc[i][j][1];
+                            *reinterpret_cast<double2*>(dst) = v;
+                        } else if (cc <= rr) {
+                            dst[0] -= acc[i][j][0];
+                        }
+                    }
+                }
+        }
+        __syncthreads();                                   // the panel buffer is reused; global updates are block-local
+    }
+
+    const double logdetSig = 2 * block_sum(ldsum, scratch);
+    double py = 0.0, pl = 0.0;
+    for (int t = tid; t < a.n_tiles; t += nt) {
+        const double2 v = *reinterpret_cast<const double2*>(a.partial + ((size_t)t * a.B + b) * 2);
+        py += v.x;
+        pl += v.y;
+    }
+    const double yNy = block_sum(py, scratch), logdetN = block_sum(pl, scratch);
+    if (tid == 0) {
+        const double zz = -A[(size_t)p * lda + p];
+        double lnl = -0.5 * (yNy - zz + logdetN + logdetPhi + logdetSig);
+        if (sFail) lnl = -CUDART_INF;
+        a.out[b] = combine_prior(lnl, a.lnprior, b, a.with_prior);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K4w  Cholesky finish, one WARP per walker (ranks up to 63, structured Sigma path)
 // ------------------------------------------------------------------------------------------
 // Same quantities as chol_finish_kernel, for matrices of at most 64 rows (p + 1 <= 64, row p = u^T): the whole

@@ -176,6 +176,16 @@ inline size_t chol_smem_doubles(int p, int pp, int nb, bool matrix_in_smem, int 
     return (size_t)2 * pp + (size_t)nb * (nb + 1) + nb + (size_t)(p + 1) * (nb + 1) +
            (matrix_in_smem ? (size_t)(p + 1) * (p + 2) / 2 : 0) + (size_t)n_r;   // n_r: column sums of the structured path
 }
+// K4p: large ranks, 32-column panels in shared memory + DMMA trailing updates on the global scratch (vela_kernels.cu)
+__global__ void chol_panel_kernel(CholArgs a);
+constexpr int kPanelThreadsHost = 256;   // = kPanelThreads in vela_kernels.cu
+inline size_t chol_panel_smem_bytes(int p, int pp, int n_ru) {
+    const int n1 = p + 1, prow = ((n1 + 31) & ~31) + 32;
+    const size_t panel = (size_t)prow * 36;                // kPanelPitch
+    return ((size_t)pp + 72 + 8 + (panel > (size_t)n_ru ? panel : (size_t)n_ru)) * sizeof(double);
+}
+inline size_t chol_panel_scratch_doubles(int p, int pp) { return (size_t)(p + 1) * (pp + 2); }   // per walker
+
 // K4w: one warp per walker, ranks up to 63 (vela_kernels.cu).  Shared-memory layout of the walker's matrix (rows 0..p,
 // row p = u^T): columns in blocks of four, column k holding rows (k & ~3) .. NR-1, NR = p + 1 rounded up to even.
 constexpr int kCholWarpMaxRows = 64;
