@@ -100,6 +100,7 @@ struct DeviceModel {
     double* T = nullptr;            // structured path: [n_rows_pad x n_cols] table (device copy of StructPlan::T)
     PairTerm* table = nullptr;
     unsigned* ltab = nullptr;       // chol_warp_kernel layout table (ranks <= 63 on the structured path)
+    unsigned* ctab = nullptr;       // compact pair table (4 bytes per pair) of the structured path
     GPDev* gp = nullptr;
     double* gp_data = nullptr;
     int3* ecorr_groups = nullptr;
@@ -179,6 +180,7 @@ struct VelaPulsar {
     long eg_pad = 0, ldv = 0;
     bool chol_smem = true;
     std::vector<unsigned> ltab;      // layout table of chol_warp_kernel; empty = that kernel is not used
+    std::vector<unsigned> ctab;      // compact pair table; empty = some coefficient / index does not fit the 4-byte code
     int chol_nb = 8;                 // block width of the Cholesky kernel
     size_t chol_smem_bytes = 0;
     std::vector<DeviceModel> devs;
@@ -603,6 +605,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         // VELA_B200_CHOL_WARP=1 selects the warp kernel (A/B measurements, tests).
         const bool warp_off = !(getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 1);
         ch.ltab = d.ltab;
+        ch.ctab = d.ctab;
         if (d.ltab && !d_ahat && !warp_off && h->n_eg == 0) {
             const int n_ru = h->sp.n_r + h->p;
             chol_warp_kernel<<<(unsigned)B, 32, chol_warp_smem_bytes(h->p, n_ru), st>>>(ch);
@@ -662,6 +665,7 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
             if (upload(&d.T, h->sp.T.data(), h->sp.T.size())) return VELA_ERR_CUDA;
             if (upload(&d.table, h->sp.table.data(), h->sp.table.size())) return VELA_ERR_CUDA;
             if (!h->ltab.empty() && upload(&d.ltab, h->ltab.data(), h->ltab.size())) return VELA_ERR_CUDA;
+            if (!h->ctab.empty() && upload(&d.ctab, h->ctab.data(), h->ctab.size())) return VELA_ERR_CUDA;
         }
     }
     if (set_smem_attrs(d.dev)) return VELA_ERR_CUDA;
@@ -675,7 +679,7 @@ void destroy_device(DeviceModel& d) {
     if (d.buf.h_params) cudaFreeHost(d.buf.h_params);
     if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
     if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
-    cudaFree(d.T); cudaFree(d.table); cudaFree(d.ltab);
+    cudaFree(d.T); cudaFree(d.table); cudaFree(d.ltab); cudaFree(d.ctab);
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
     cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active); cudaFree(d.priors);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -886,6 +890,18 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         if (const char* e = getenv("VELA_B200_CHOL_SMEM")) { if (atoi(e) == 0) h->chol_smem = false; }   // tests: force the global-scratch kernels
         if (!h->chol_smem) h->chol_nb = 16;   // the global-scratch variant exists for block width 16 only
         h->chol_smem_bytes = h->chol_smem ? need : chol_smem_doubles(h->p, h->pp, h->chol_nb, false, n_r) * sizeof(double);
+        // structured path: the pair table again as 4-byte codes (13-bit column indices, coefficients 1 | 1/2 and 0 | +-1/2),
+        // 1/6 of the bytes the finishing kernel pulls through L2 per walker (rank 300: 45 150 pairs)
+        if (h->sp.active && h->sp.n_cols <= kCholWarpMaxCols) {
+            h->ctab.resize(h->sp.table.size());
+            for (size_t t = 0; t < h->sp.table.size(); ++t) {
+                const PairTerm& pt = h->sp.table[t];
+                const bool c1_one = pt.c1 == 1.0, c1_half = pt.c1 == 0.5;
+                const int c2 = pt.c2 == 0.0 ? 0 : (pt.c2 == 0.5 ? 1 : (pt.c2 == -0.5 ? 2 : -1));
+                if (!(c1_one || c1_half) || c2 < 0) { h->ctab.clear(); break; }
+                h->ctab[t] = (1u << 29) | ((unsigned)c2 << 27) | ((c1_one ? 1u : 0u) << 26) | ((unsigned)(c2 ? pt.i2 : 0) << 13) | (unsigned)pt.i1;
+            }
+        }
         // ranks up to 63 on the structured path: layout table of the warp-per-walker Cholesky kernel - for every
         // shared-memory slot of its column-blocked matrix the recipe that fills it (zero | c1 R[i1] + c2 R[i2] | u_i)
         if (h->sp.active && h->p + 1 <= kCholWarpMaxRows && h->sp.n_cols <= kCholWarpMaxCols) {

@@ -1215,10 +1215,16 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
         }
         int r = 0, c = tid;
         while (c > r) { c -= r + 1; ++r; }
-#pragma unroll 2
+#pragma unroll 4
         for (long t = tid; t < n_pairs; t += nt) {
             double v;
-            if (a.table) {
+            if (a.ctab) {                                  // 4-byte recipe per pair (same code as the layout table)
+                const unsigned e = __ldg(a.ctab + t);
+                v = ((e >> 26) & 1 ? 1.0 : 0.5) * sR[e & 0x1fff];
+                const unsigned c2 = (e >> 27) & 3;
+                if (c2) v = fma(c2 == 1 ? 0.5 : -0.5, sR[(e >> 13) & 0x1fff], v);
+                if (a.add_sig) v += gA[t];
+            } else if (a.table) {
                 const PairTerm pt = a.table[t];
                 v = pt.c1 * sR[pt.i1];
                 if (pt.c2 != 0.0) v = fma(pt.c2, sR[pt.i2], v);
@@ -1301,18 +1307,32 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
                     if (c < nbb) row[c] = x[c];
             }
             __syncthreads();
-            // rank-nbb update of the panel's remaining columns: lane = column, warp = row strip
-            const int c2 = c0 + 8 + lane;
-            if (c2 < nb) {
-                double lj[8];
+            // rank-8 update of the panel's remaining columns (c0+8 .. 31) on DMMA: C[i][c2] -= sum_c P[i][c0+c] P[c2][c0+c]
+            // for the row tiles below the diagonal block; one warp per 8-row tile, up to three 8-column tiles each.  (The
+            // first version gave every lane one column and every warp a row strip: one FMA per shared load, 123 k of the
+            // kernel's 424 k instructions per walker.)  Entries above the panel's diagonal are computed too and never read.
+            const int n_nt = (nb - (c0 + 8) + 7) >> 3;     // 8-column tiles right of this block column (<= 3)
+            if (n_nt > 0) {
+                double fb[3][2];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) lj[c] = P[c2 * kPanelPitch + c0 + c];
-                for (int i = c2 + ((warp - c2) % nwarps + nwarps) % nwarps; i < m; i += nwarps) {   // rows i >= c2, i = warp (mod nwarps)
-                    const double* li = P + i * kPanelPitch + c0;
-                    double acc = 0.0;
+                for (int j = 0; j < 3; ++j)
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) acc = fma(li[c], lj[c], acc);
-                    P[i * kPanelPitch + c2] -= acc;
+                    for (int kk = 0; kk < 2; ++kk)
+                        fb[j][kk] = c0 + 8 + j * 8 + gid < nb ? P[(c0 + 8 + j * 8 + gid) * kPanelPitch + c0 + kk * 4 + tig] : 0.0;   // columns past the panel stay zero
+                // (reads touch columns c0 .. c0+7 only, writes columns >= c0+8: no barrier needed in between)
+                for (int r0 = c0 + 8 + warp * 8; r0 < m; r0 += nwarps * 8) {
+                    const double* arow = P + (r0 + gid) * kPanelPitch + c0 + tig;
+                    const double fa0 = -arow[0], fa1 = -arow[4];
+                    double* crow = P + (r0 + gid) * kPanelPitch + c0 + 8 + 2 * tig;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        if (j < n_nt) {
+                            double2 cv = *reinterpret_cast<double2*>(crow + j * 8);
+                            dmma8x8x4(cv.x, cv.y, fa0, fb[j][0]);
+                            dmma8x8x4(cv.x, cv.y, fa1, fb[j][1]);
+                            *reinterpret_cast<double2*>(crow + j * 8) = cv;
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -1331,11 +1351,26 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
             int ti = 0;
             while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
             const int tj = tile - ti * (ti + 1) / 2;
+            // the C tile is the accumulators' initial value (A enters negated): its global loads are in flight while the
+            // fragments come from shared memory, and no second register tile is needed
             double acc[4][4][2];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = ti * 32 + i * 8 + gid, cc = tj * 32 + j * 8 + 2 * tig;
+                    acc[i][j][0] = acc[i][j][1] = 0.0;
+                    if (rr < m2) {
+                        const double* src = A + (size_t)(k1 + rr) * lda + k1 + cc;
+                        if (cc + 1 <= rr) {
+                            const double2 v = *reinterpret_cast<const double2*>(src);
+                            acc[i][j][0] = v.x;
+                            acc[i][j][1] = v.y;
+                        } else if (cc <= rr) {
+                            acc[i][j][0] = src[0];
+                        }
+                    }
+                }
             const double* pa = P2 + (ti * 32 + gid) * kPanelPitch + tig;
             const double* pb = P2 + (tj * 32 + gid) * kPanelPitch + tig;
 #pragma unroll
@@ -1343,7 +1378,7 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
                 double fa[4], fb[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    fa[i] = pa[i * 8 * kPanelPitch + kk * 4];
+                    fa[i] = -pa[i * 8 * kPanelPitch + kk * 4];
                     fb[i] = pb[i * 8 * kPanelPitch + kk * 4];
                 }
 #pragma unroll
@@ -1358,14 +1393,8 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
                     const int rr = ti * 32 + i * 8 + gid, cc = tj * 32 + j * 8 + 2 * tig;
                     if (rr < m2) {
                         double* dst = A + (size_t)(k1 + rr) * lda + k1 + cc;
-                        if (cc + 1 <= rr) {                // both entries in the lower triangle: one 16-byte access
-                            double2 v = *reinterpret_cast<double2*>(dst);
-                            v.x -= acc[i][j][0];
-                            v.y -= acc[i][j][1];
-                            *reinterpret_cast<double2*>(dst) = v;
-                        } else if (cc <= rr) {
-                            dst[0] -= acc[i][j][0];
-                        }
+                        if (cc + 1 <= rr) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+                        else if (cc <= rr) dst[0] = acc[i][j][0];
                     }
                 }
         }

@@ -151,6 +151,7 @@ struct CholArgs {
     long split_stride_r;
     int n_r, u_off;
     int add_sig;               // add Sig[t] (ECORR correction) to the assembled entry
+    const unsigned* ctab;      // compact pair table: one 4-byte recipe per packed pair (codes as in ltab), null = use `table`
     const unsigned* ltab;      // chol_warp_kernel: layout table (one code per shared-memory slot), null = not available
     double* ahat;              // optional [B][p]: conditional mean of the marginalised amplitudes, Sigma u
     double* cf;                // optional [B][p][p] row-major upper Cholesky factor of Sigma^-1 (L^T)
