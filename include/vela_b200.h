@@ -400,6 +400,9 @@ VELA_API int vela_b200_chain_specialized(VelaHandle h, int on);
 VELA_API int64_t vela_b200_debug_structured_sigma(const VelaModelDesc* desc, const double* w, double* sigma_packed, int32_t* info);
 /* 1 if this handle assembles Sigma from column sums (structured path), 0 if it runs the dense pair contraction. */
 VELA_API int vela_b200_sigma_structured(VelaHandle h);
+/* Host-only check of the two-stage column sums (cell moments + stage-2 matrices) against the direct ones, see vela_api.cu. */
+VELA_API int64_t vela_b200_debug_two_stage(const VelaModelDesc* desc, const double* w, const double* wy, double* R_direct,
+                                           double* R_two, int64_t* info);
 VELA_API const char* vela_b200_jit_log(VelaHandle h);
 VELA_API int64_t vela_b200_debug_spec_source(const VelaModelDesc* desc, char* buf, int64_t cap);
 VELA_API int64_t vela_b200_debug_spec_compile(const VelaModelDesc* desc);

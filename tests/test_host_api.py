@@ -300,3 +300,32 @@ def test_priors_reference_literals(vb):
     d = vb.descriptor.prior_descriptors(priors)
     assert d is not None and [d[k].kind for k in range(3)] == [vb.descriptor.PRIOR_UNIFORM, vb.descriptor.PRIOR_TRUNCATED_NORMAL,
                                                              vb.descriptor.PRIOR_UNIFORM]
+
+
+@pytest.mark.parametrize("name,ntoa", [("config3_gp", 6000), ("config4_dd_wb", 14000), ("config5_array", 6000), ("config3_gp_ecorr", 6000)])
+def test_two_stage_column_sums_match_direct_sums(name, ntoa, vb, oracle):
+    """The two-stage evaluation of the structured path's column sums (cell moments with 32 Chebyshev columns per scale
+    function, then constant stage-2 matrices: Jacobi-Anger expansion of exp(i m x) around each cell's centre) against
+    the direct sums over the table T, on the host (vela_b200_debug_two_stage): agreement to ~1e-14 of the largest sum."""
+    import ctypes as C
+    from helpers import oracle_eval_factory
+    ds = vb.synth.make_dataset(name, oracle_eval_factory(vb, oracle), ntoa=ntoa)
+    md = vb.ModelDescriptor(ds.model, ds.toas)
+    L = vb.lib.lib()
+    dp = C.POINTER(C.c_double)
+    info = (C.c_int64 * 8)()
+    nc = int(L.vela_b200_debug_two_stage(md.byref(), None, None, None, None, info))
+    assert nc > 0 and info[1] == 1, list(info)
+    y, w = oracle.residuals(md, ds.truth)
+    wy = w * y
+    Rd, Rt = np.zeros(nc), np.zeros(nc)
+    L.vela_b200_debug_two_stage(md.byref(), w.ctypes.data_as(dp), wy.ctypes.data_as(dp), Rd.ctypes.data_as(dp),
+                                Rt.ctypes.data_as(dp), info)
+    n_u = (md.n_basis + 31) // 32 * 32
+    nr = nc - n_u
+    assert np.max(np.abs(Rd[:nr] - Rt[:nr])) <= 5e-14 * np.max(np.abs(Rd[:nr]))
+    # u = M^T (w y) sums terms of both signs: bound every column by its sum of magnitudes, not by the cancelled result
+    Mb = np.asarray(ds.model.kernel.noise_basis)
+    bound = np.abs(Mb).T @ np.abs(wy)
+    assert np.all(np.abs(Rd[nr:nr + md.n_basis] - Rt[nr:nr + md.n_basis]) <= 2e-14 * bound)
+    assert info[4] * 32 < 0.75 * nc      # fewer stage-1 columns than table columns: that is the point

@@ -59,6 +59,7 @@ int upload(T** dst, const T* src, size_t n) {
 
 inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
 constexpr long kSplitRows = 2048;   // walker rows reserved for split-K slabs of small batches
+constexpr long kTwoStageMinBatch = 1024; // batches from this size on take the two-stage column sums (cell moments)
 constexpr long kGraphMaxBatch = 2048; // host batches up to this size replay a captured CUDA graph
 constexpr long kMaxBigSplit = 4;    // split-K slabs kept for full-size batches (wave quantisation), memory permitting
 
@@ -69,6 +70,8 @@ struct Buffers {  // per-device, per-batch scratch (grown on demand)
     double *Sig = nullptr, *U = nullptr, *Sq = nullptr, *V = nullptr, *out = nullptr, *lnprior = nullptr;
     double* R = nullptr;   // structured path: column sums [r_rows][n_cols]
     long r_rows = 0;
+    double* mu = nullptr;  // two-stage column sums: cell moments [n_blocks][cap_B][k2_pad]
+    long mu_rows = 0;
     double *h_params = nullptr, *h_out = nullptr, *h_lnprior = nullptr;  // pinned
     long h_cap = 0;
     // Small host batches (emcee-sized) replay a captured CUDA graph: staging copy in, every kernel of the step, result
@@ -99,6 +102,8 @@ struct DeviceModel {
     long ldM = 0;
     double* T = nullptr;            // structured path: [n_rows_pad x n_cols] table (device copy of StructPlan::T)
     PairTerm* table = nullptr;
+    double* A1 = nullptr;           // two-stage column sums: stage-1 Chebyshev columns [n_rows_pad x 32 n_blocks]
+    double* T2 = nullptr;           //                        stage-2 matrices (StructPlan::jobs)
     unsigned* ltab = nullptr;       // chol_warp_kernel layout table (ranks <= 63 on the structured path)
     unsigned* ctab = nullptr;       // compact pair table (4 bytes per pair) of the structured path
     GPDev* gp = nullptr;
@@ -203,7 +208,8 @@ namespace {
 void free_buffers(Buffers& b) {
     drop_graphs(b);
     cudaFree(b.params); cudaFree(b.Pext); cudaFree(b.tzr); cudaFree(b.partial); cudaFree(b.Y); cudaFree(b.W);
-    cudaFree(b.Sig); cudaFree(b.U); cudaFree(b.Sq); cudaFree(b.V); cudaFree(b.out); cudaFree(b.lnprior); cudaFree(b.R);
+    cudaFree(b.Sig); cudaFree(b.U); cudaFree(b.Sq); cudaFree(b.V); cudaFree(b.out); cudaFree(b.lnprior); cudaFree(b.R); cudaFree(b.mu);
+    b.mu = nullptr; b.mu_rows = 0;
     b.params = b.Pext = b.tzr = b.partial = b.Y = b.W = b.Sig = b.U = b.Sq = b.V = b.out = b.lnprior = b.R = nullptr;
     b.r_rows = 0;
     b.cap_B = 0;
@@ -234,6 +240,12 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
         b.r_rows = std::max<long>(cap * 4, std::min<long>(65536, ((long)64 << 20) / ((long)h->sp.n_cols * 8)));
         CU(cudaMalloc((void**)&b.R, (size_t)b.r_rows * h->sp.n_cols * sizeof(double)));
         CU(cudaMemsetAsync(b.R, 0, (size_t)b.r_rows * h->sp.n_cols * sizeof(double), d.stream));
+        if (h->sp.two_stage && cap >= kTwoStageMinBatch) {
+            b.mu_rows = round_up(cap, 512);
+            const size_t nb = (size_t)h->sp.n_blocks * b.mu_rows * h->sp.k2_pad * sizeof(double);
+            CU(cudaMalloc((void**)&b.mu, nb));
+            CU(cudaMemsetAsync(b.mu, 0, nb, d.stream));   // the padding behind the last cell stays zero
+        }
     }
     if (h->p > 0 && h->sp.active && h->n_eg == 0) {
         if (!h->chol_smem) CU(cudaMalloc((void**)&b.Sq, (size_t)cap * chol_panel_scratch_doubles(h->p, h->pp) * sizeof(double)));
@@ -383,6 +395,7 @@ int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool w
     }
     if (const char* e = getenv("VELA_B200_SIGMA_KSPLIT")) ks_best = std::max<long>(1, std::min<long>(atoi(e), max_split));
     ColsumArgs ca;
+    ca.plane_stride = 0; ca.n_valid = 0;
     ca.T = d.T; ca.ldT = h->n_rows_pad; ca.n_cols = h->sp.n_cols; ca.n_w_units = n_t; ca.n_rows_pad = h->n_rows_pad;
     ca.W = b.W; ca.Y = b.Y; ca.ld_yw = h->n_rows_pad; ca.B = B; ca.R = b.R; ca.ld_r = h->sp.n_cols;
     ca.kt_per_split = (int)((n_ktiles + ks_best - 1) / ks_best);
@@ -392,6 +405,52 @@ int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool w
     sh.kernel<<<grid, 512, colsum_smem_bytes(sh.bk, sh.stages, sh.uc, sh.wc, wy), st>>>(ca);
     if (out_args) *out_args = ca;
     return nz;
+}
+
+// Two-stage column sums (vela_structured.h): stage 1 contracts w / w.y with the Chebyshev columns cell by cell (one
+// launch, split-K slices = cells, moments stored walker-major per block), stage 2 maps the moments to the column sums
+// with one small GEMM per run of output columns.  Same kernel both times.  Writes slab 0 of R; returns 1 (slab).
+int launch_two_stage(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, ColsumArgs* out_args) {
+    Buffers& b = d.buf;
+    const StructPlan& sp = h->sp;
+    const long plane = b.mu_rows * sp.k2_pad;
+    ColsumArgs ca;
+    // ---- stage 1
+    ca.T = d.A1; ca.ldT = h->n_rows_pad; ca.n_cols = sp.n_blocks * 32; ca.n_w_units = sp.n_w_blocks; ca.n_rows_pad = h->n_rows_pad;
+    ca.W = b.W; ca.Y = b.Y; ca.ld_yw = h->n_rows_pad; ca.B = B; ca.R = b.mu; ca.ld_r = sp.k2_pad;
+    ca.kt_per_split = sp.cp / 16; ca.split_stride_r = 0; ca.plane_stride = plane; ca.n_valid = 0;
+    {
+        dim3 grid((unsigned)sp.n_blocks, (unsigned)((B + 511) / 512), (unsigned)sp.n_cells);
+        colsum_kernel<16, 2, 1, 16, true><<<grid, 512, colsum_smem_bytes(16, 2, 1, 16, true), st>>>(ca);
+    }
+    // ---- stage 2: every job is a dense [n_out x k2_pad] x [k2_pad x B] product on the block's moments
+    for (const StructPlan::Stage2Job& job : sp.jobs) {
+        ColsumArgs c2;
+        const int n_units = (job.n_out + 31) / 32;
+        c2.T = d.T2 + job.t2_off; c2.ldT = sp.k2_pad; c2.n_cols = n_units * 32; c2.n_w_units = n_units; c2.n_rows_pad = sp.k2_pad;
+        c2.W = b.mu + (size_t)job.block * plane; c2.Y = c2.W; c2.ld_yw = sp.k2_pad; c2.B = B;
+        c2.R = b.R + job.r_off; c2.ld_r = sp.n_cols; c2.split_stride_r = 0; c2.plane_stride = 0; c2.n_valid = job.n_out;
+        // shape by the number of 32-column units of the run; all of the (short) K axis in one slice
+        if (n_units >= 3) {
+            c2.kt_per_split = (int)(sp.k2_pad / 16);
+            dim3 grid((unsigned)((n_units + 3) / 4), (unsigned)((B + 127) / 128), 1);
+            colsum_kernel<16, 4, 4, 4, true><<<grid, 512, colsum_smem_bytes(16, 4, 4, 4, true), st>>>(c2);
+        } else if (n_units == 2) {
+            c2.kt_per_split = (int)(sp.k2_pad / 32);
+            dim3 grid(1, (unsigned)((B + 255) / 256), 1);
+            colsum_kernel<32, 2, 2, 8, true><<<grid, 512, colsum_smem_bytes(32, 2, 2, 8, true), st>>>(c2);
+        } else {
+            c2.kt_per_split = (int)(sp.k2_pad / 16);
+            dim3 grid(1, (unsigned)((B + 511) / 512), 1);
+            colsum_kernel<16, 2, 1, 16, true><<<grid, 512, colsum_smem_bytes(16, 2, 1, 16, true), st>>>(c2);
+        }
+    }
+    h->launches += 1 + (int64_t)sp.jobs.size();
+    if (out_args) {
+        ca.R = b.R; ca.ld_r = sp.n_cols; ca.split_stride_r = round_up(B, kSigMaxSamples) * (long)sp.n_cols;
+        *out_args = ca;
+    }
+    return 1;
 }
 
 // WoodburyKernel{EcorrKernel}: subtract the per-group Sherman-Morrison terms from slab 0 of Sigma / U (K2b + K2c).
@@ -472,6 +531,7 @@ int set_smem_attrs(int dev) {
         CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     for (const ColsumShape& sh : kColsumSplitShapes)
         CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(colsum_kernel<16, 2, 1, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     for (auto k : {chol_finish_kernel<8, true>, chol_finish_kernel<16, true>, chol_finish_kernel<16, false>})
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
     // shared-memory matrices: many small walker CTAs per SM, so ask for the largest shared carve-out; the global-scratch
@@ -563,7 +623,13 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         ColsumArgs cs;
         int ksplit;
         if (h->sp.active) {
-            ksplit = launch_colsum(h, d, B, st, wy, &cs);
+            const bool two_off = getenv("VELA_B200_TWO_STAGE") && atoi(getenv("VELA_B200_TWO_STAGE")) == 0;
+            if (h->sp.two_stage && wy && b.mu && B >= kTwoStageMinBatch && B <= b.mu_rows && !two_off) {
+                ksplit = launch_two_stage(h, d, B, st, &cs);
+                h->launches -= 1;                            // (the caller counts one launch for this stage below)
+            } else {
+                ksplit = launch_colsum(h, d, B, st, wy, &cs);
+            }
             const bool warp_on = getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 1;
             if (ksplit > 4 && warp_on && d.ltab && !d_ahat && h->n_eg == 0) {
                 // emcee-sized batches split K deeply to fill the SMs; summing 16 - 64 slabs per entry would be the longest
@@ -664,6 +730,10 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
         if (h->sp.active) {
             if (upload(&d.T, h->sp.T.data(), h->sp.T.size())) return VELA_ERR_CUDA;
             if (upload(&d.table, h->sp.table.data(), h->sp.table.size())) return VELA_ERR_CUDA;
+            if (h->sp.two_stage) {
+                if (upload(&d.A1, h->sp.A1.data(), h->sp.A1.size())) return VELA_ERR_CUDA;
+                if (upload(&d.T2, h->sp.T2.data(), h->sp.T2.size())) return VELA_ERR_CUDA;
+            }
             if (!h->ltab.empty() && upload(&d.ltab, h->ltab.data(), h->ltab.size())) return VELA_ERR_CUDA;
             if (!h->ctab.empty() && upload(&d.ctab, h->ctab.data(), h->ctab.size())) return VELA_ERR_CUDA;
         }
@@ -679,7 +749,7 @@ void destroy_device(DeviceModel& d) {
     if (d.buf.h_params) cudaFreeHost(d.buf.h_params);
     if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
     if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
-    cudaFree(d.T); cudaFree(d.table); cudaFree(d.ltab); cudaFree(d.ctab);
+    cudaFree(d.T); cudaFree(d.table); cudaFree(d.A1); cudaFree(d.T2); cudaFree(d.ltab); cudaFree(d.ctab);
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
     cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active); cudaFree(d.priors);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -960,6 +1030,8 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     if (h->devs.size() > 1)
         for (size_t i = 0; i < h->devs.size(); ++i) { h->feeders.emplace_back(new Feeder()); h->feeders.back()->start(); }
     std::vector<double>().swap(h->sp.T);   // the device copies are authoritative from here on
+    std::vector<double>().swap(h->sp.A1);
+    std::vector<double>().swap(h->sp.T2);
 
     // per-model chain kernel (vela_jit.cu); any failure leaves the generic kernel in charge
     {
@@ -1003,7 +1075,8 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
 
     // walkers per device per pass: bound the y/w/Sigma scratch to ~1/4 of the device memory
     if (h->kernel_kind != VELA_KERNEL_WHITE) {
-        size_t per = (size_t)2 * h->n_rows_pad * 8 + (h->sp.active ? (size_t)h->sp.n_cols * 32 + (h->n_eg ? (size_t)h->ld_sig * 8 : 0) : (size_t)h->ld_sig * 8) + (size_t)h->pp * 8 + (h->chol_smem ? 0 : chol_panel_scratch_doubles(h->p, h->pp) * 8) + (size_t)h->eg_pad * h->ldv * 8;
+        size_t per = (size_t)2 * h->n_rows_pad * 8 + (h->sp.active ? (size_t)h->sp.n_cols * 32 + (h->n_eg ? (size_t)h->ld_sig * 8 : 0) : (size_t)h->ld_sig * 8) + (size_t)h->pp * 8 + (h->chol_smem ? 0 : chol_panel_scratch_doubles(h->p, h->pp) * 8) + (size_t)h->eg_pad * h->ldv * 8 +
+                     (h->sp.two_stage ? (size_t)h->sp.n_blocks * h->sp.k2_pad * 8 : 0);
         size_t free_b = 0, total_b = 0;
         cudaSetDevice(devices[0]);
         cudaMemGetInfo(&free_b, &total_b);
@@ -1536,7 +1609,8 @@ VELA_API const char* vela_b200_jit_log(VelaHandle h) { return h ? h->jit_log.c_s
 VELA_API int64_t vela_b200_debug_structured_sigma(const VelaModelDesc* desc, const double* w, double* sigma_packed, int32_t* info) {
     if (int rc = validate(desc)) return rc;
     if (desc->kernel_kind != VELA_KERNEL_WOODBURY_WHITE && desc->kernel_kind != VELA_KERNEL_WOODBURY_ECORR) return 0;
-    const long n_rows = desc->wideband ? 2 * desc->n_toas : desc->n_toas, n_rows_pad = round_up(n_rows, 64);
+    const long n_rows = desc->wideband ? 2 * desc->n_toas : desc->n_toas;
+    long n_rows_pad = round_up(n_rows, 64);
     const int p = (int)desc->basis_cols;
     StructPlan sp;
     if (!analyse_basis(desc, n_rows, n_rows_pad, p, sp)) return 0;
@@ -1555,6 +1629,63 @@ VELA_API int64_t vela_b200_debug_structured_sigma(const VelaModelDesc* desc, con
         }
     }
     return sp.n_r;
+}
+
+// test / tooling hook (no device needed): the column sums R (n_cols values: table columns against w, then the basis
+// columns against wy) evaluated on the host twice - directly from the table T, and through the two-stage plan (cell
+// moments with the Chebyshev columns A1, then the stage-2 matrices T2) - so the expansion can be checked against the
+// direct sums without a GPU.  info = {n_cols, two_stage, cp, n_cells, n_blocks, n_w_blocks, n_jobs, n_rows_pad}.
+// Returns n_cols (0 = the basis stays on the dense path).
+VELA_API int64_t vela_b200_debug_two_stage(const VelaModelDesc* desc, const double* w, const double* wy, double* R_direct,
+                                           double* R_two, int64_t* info) {
+    if (int rc = validate(desc)) return rc;
+    if (desc->kernel_kind != VELA_KERNEL_WOODBURY_WHITE && desc->kernel_kind != VELA_KERNEL_WOODBURY_ECORR) return 0;
+    const long n_rows = desc->wideband ? 2 * desc->n_toas : desc->n_toas;
+    long n_rows_pad = round_up(n_rows, 64);
+    const int p = (int)desc->basis_cols;
+    StructPlan sp;
+    if (!analyse_basis(desc, n_rows, n_rows_pad, p, sp)) return 0;
+    if (info) {
+        info[0] = sp.n_cols; info[1] = sp.two_stage ? 1 : 0; info[2] = sp.cp; info[3] = sp.n_cells; info[4] = sp.n_blocks;
+        info[5] = sp.n_w_blocks; info[6] = (int64_t)sp.jobs.size(); info[7] = n_rows_pad;
+    }
+    if (w && wy && R_direct) {
+        for (int c = 0; c < sp.n_cols; ++c) {
+            const double* t = sp.T.data() + (size_t)c * n_rows_pad;
+            const double* v = c < sp.n_r ? w : wy;
+            double acc = 0.0;
+            for (long j = 0; j < n_rows; ++j) acc += t[j] * v[j];
+            R_direct[c] = acc;
+        }
+    }
+    if (w && wy && R_two && sp.two_stage) {
+        for (int c = 0; c < sp.n_cols; ++c) R_two[c] = 0.0;
+        // stage 1: mu[block][cell * 32 + q]
+        std::vector<double> mu((size_t)sp.n_blocks * sp.k2_pad, 0.0);
+        for (int b = 0; b < sp.n_blocks; ++b) {
+            const double* v = b < sp.n_w_blocks ? w : wy;
+            for (int q = 0; q < 32; ++q) {
+                const double* a1 = sp.A1.data() + ((size_t)b * 32 + q) * n_rows_pad;
+                for (int c = 0; c < sp.n_cells; ++c) {
+                    double acc = 0.0;
+                    const long j1 = std::min<long>(n_rows, (long)(c + 1) * sp.cp);
+                    for (long j = (long)c * sp.cp; j < j1; ++j) acc += a1[j] * v[j];
+                    mu[(size_t)b * sp.k2_pad + (size_t)c * 32 + q] = acc;
+                }
+            }
+        }
+        // stage 2
+        for (const StructPlan::Stage2Job& job : sp.jobs) {
+            const double* m = mu.data() + (size_t)job.block * sp.k2_pad;
+            for (int oc = 0; oc < job.n_out; ++oc) {
+                const double* t2 = sp.T2.data() + job.t2_off + (size_t)oc * sp.k2_pad;
+                double acc = 0.0;
+                for (long k = 0; k < sp.k2_pad; ++k) acc += t2[k] * m[k];
+                R_two[job.r_off + oc] = acc;
+            }
+        }
+    }
+    return sp.n_cols;
 }
 
 // test / tooling hook: compile the translation unit below with NVRTC (no device needed); returns the cubin size

@@ -766,12 +766,16 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
         const int col = u * 32 + i * 8 + gid;
+        if (a.n_valid && col >= a.n_valid) continue;
+        // normal mode: one slab per split-K slice; moment mode: walker-major planes per 32-column block, slice = cell
+        double* dst = a.plane_stride ? a.R + (size_t)u * a.plane_stride + (size_t)blockIdx.z * 32 + (i * 8 + gid)
+                                     : a.R + (size_t)blockIdx.z * a.split_stride_r + col;
 #pragma unroll
         for (int n = 0; n < NT; ++n)
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 long b = b0 + wc * 32 + n * 8 + 2 * tig + r;
-                if (b < a.B) a.R[(size_t)blockIdx.z * a.split_stride_r + (size_t)b * a.ld_r + col] = acc[i][n][r];
+                if (b < a.B) dst[(size_t)b * a.ld_r] = acc[i][n][r];
             }
     }
 }
@@ -785,6 +789,7 @@ template __global__ void colsum_kernel<16, 4, 8, 2, true>(ColsumArgs);
 template __global__ void colsum_kernel<16, 4, 4, 4, true>(ColsumArgs);
 template __global__ void colsum_kernel<16, 4, 2, 8, true>(ColsumArgs);
 template __global__ void colsum_kernel<32, 2, 2, 8, true>(ColsumArgs);
+template __global__ void colsum_kernel<16, 2, 1, 16, true>(ColsumArgs);   // one column unit x 512 walkers: stage 1 of the two-stage sums
 
 // ------------------------------------------------------------------------------------------
 // K4  + Phi^-1, Cholesky, log-det, solve, ln L

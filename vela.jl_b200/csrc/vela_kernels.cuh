@@ -54,6 +54,11 @@ struct ColsumArgs {
     long ld_r;
     int kt_per_split;
     long split_stride_r;       // doubles between the slabs of consecutive split-K slices
+    // two-stage evaluation (vela_structured.h): stage 1 stores the cell moments walker-major per 32-column block,
+    //   R[(col / 32) * plane_stride + b * ld_r + slice * 32 + col % 32]      (plane_stride > 0; slice = cell)
+    // and stage 2 stores only its first n_valid columns (0 = all): its output runs are not multiples of 32
+    long plane_stride;
+    int n_valid;
 };
 
 // Sigma[p][q] = c1 R[i1] + c2 R[i2]  (c2 == 0: single term) for the packed pair t = p(p+1)/2 + q
