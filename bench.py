@@ -452,14 +452,10 @@ def main():
                 "reference_equivalent_tflops_per_gpu": flops_eval * Bc / (ms_max / steps * 1e-3) / 1e12,
                 "fp64_fma_peak_tflops": dfma}
         if case.p and case.psr.sigma_structured():
-            import ctypes as C
-            tab = (C.c_int32 * 3)()
-            L.vela_b200_debug_structured_sigma(vb.ModelDescriptor(case.ds.model, case.ds.toas).byref(), None, None, tab)
-            nrp = (case.nrows + 63) // 64 * 64
-            info["sigma_columns"] = {"column_sums": int(tab[0]), "with_u_columns_padded": int(tab[1]),
-                                     "packed_pairs_of_dense_path": case.p * (case.p + 1) // 2}
+            si = case.psr.sigma_info(Bc)
+            info["sigma_plan"] = dict(si, packed_pairs_of_dense_path=case.p * (case.p + 1) // 2)
             if st[2] > 0:
-                info["sigma_executed_tflops"] = 2.0 * tab[1] * nrp * Bc / (st[2] * 1e-3) / 1e12
+                info["sigma_executed_tflops"] = si["executed_flops_per_walker"] * Bc / (st[2] * 1e-3) / 1e12
         del case
         import gc
         gc.collect()
@@ -519,15 +515,10 @@ def main():
         # launch; the structured Sigma path executes FEWER flops than the reference algorithm's contraction (it is an
         # algebraic identity on harmonic bases), so its entry is rated on the flops it executes and the
         # reference-equivalent rate is given separately.
-        n_cols = None
-        if structured:
-            import ctypes as C
-            info = (C.c_int32 * 3)()
-            md0 = vb.ModelDescriptor(c3.ds.model, c3.ds.toas)
-            L.vela_b200_debug_structured_sigma(md0.byref(), None, None, info)
-            n_cols = int(info[1])
-        nrows_pad = (nrows + 63) // 64 * 64
-        sigma_exec = 2.0 * n_cols * nrows_pad if structured else float(flops_sigma)
+        # executed flops of the Sigma stage, from the handle itself (vela_b200_sigma_info): the direct column sums
+        # (2 n_cols rows_pad) or, for large batches, the two-stage evaluation (stage-1 Chebyshev columns + stage-2 matrices)
+        sig_info = psr.sigma_info(B) if structured else None
+        sigma_exec = sig_info["executed_flops_per_walker"] if structured else float(flops_sigma)
         tf = lambda fl, ms: (fl * B / (ms * 1e-3) / 1e12) if ms > 0 else None   # noqa: E731
         # compute-bound kernels of this path run on the FP64 pipe; on B200 scalar DFMA and the DMMA tensor path share it
         # (measured peaks 36.5 vs 37.1 TFLOP/s), so "tensor" with the matching measured peak is the applicable roofline
@@ -542,7 +533,7 @@ def main():
             {"kernel": sigma_name, "ncu_name": "colsum_kernel" if structured else "sigma_contract_kernel",
              "bound": "tensor", "ms": sigma_ms, "algorithmic_flops_per_launch": sigma_exec * B,
              "achieved": tf(sigma_exec, sigma_ms), "peak": dmma_peak, "unit": "TFLOP/s",
-             "reference_equivalent_tflops": tf(float(flops_sigma), sigma_ms)},
+             "reference_equivalent_tflops": tf(float(flops_sigma), sigma_ms), "plan": sig_info},
             {"kernel": chol_name, "ncu_name": chol_name, "bound": "tensor", "bound_detail": fp64_note, "ms": chol_ms,
              "algorithmic_flops_per_launch": (p**3 / 3 + p * p + 10 * p) * B,
              "achieved": tf(p**3 / 3 + p * p + 10 * p, chol_ms), "peak": dfma_peak, "unit": "TFLOP/s"},

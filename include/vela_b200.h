@@ -400,6 +400,10 @@ VELA_API int vela_b200_chain_specialized(VelaHandle h, int on);
 VELA_API int64_t vela_b200_debug_structured_sigma(const VelaModelDesc* desc, const double* w, double* sigma_packed, int32_t* info);
 /* 1 if this handle assembles Sigma from column sums (structured path), 0 if it runs the dense pair contraction. */
 VELA_API int vela_b200_sigma_structured(VelaHandle h);
+/* What the Sigma stage executes for a batch of B walkers: returns the FP64 operations per walker of the column-sum launches
+ * (0 on the dense path); info[8] = {structured, two-stage taken, table columns, padded rows, stage-1 columns, stage-2
+ * columns as launched, moments per block and walker, cells}.  Measurement bookkeeping only. */
+VELA_API double vela_b200_sigma_info(VelaHandle h, int64_t B, int64_t* info);
 /* Host-only check of the two-stage column sums (cell moments + stage-2 matrices) against the direct ones, see vela_api.cu. */
 VELA_API int64_t vela_b200_debug_two_stage(const VelaModelDesc* desc, const double* w, const double* wy, double* R_direct,
                                            double* R_two, int64_t* info);

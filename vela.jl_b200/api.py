@@ -304,6 +304,16 @@ class Pulsar:
         """True when Sigma^-1 is assembled from trigonometric column sums (harmonic Fourier basis detected)."""
         return bool(self._lib.vela_b200_sigma_structured(self._h))
 
+    def sigma_info(self, B: int) -> dict:
+        """What the Sigma stage executes for a batch of B walkers (measurement bookkeeping): path taken and executed flops."""
+        import ctypes as C
+        info = (C.c_int64 * 8)()
+        fl = float(self._lib.vela_b200_sigma_info(self._h, int(B), info))
+        keys = ("structured", "two_stage", "table_columns", "rows_padded", "stage1_columns", "stage2_columns", "moments_per_block", "cells")
+        d = dict(zip(keys, (int(v) for v in info)))
+        d["executed_flops_per_walker"] = fl
+        return d
+
     def jit_log(self) -> str:
         return (self._lib.vela_b200_jit_log(self._h) or b"").decode(errors="replace")
 

@@ -104,6 +104,8 @@ struct DeviceModel {
     PairTerm* table = nullptr;
     double* A1 = nullptr;           // two-stage column sums: stage-1 Chebyshev columns [n_rows_pad x 32 n_blocks]
     double* T2 = nullptr;           //                        stage-2 matrices (StructPlan::jobs)
+    ColsumUnit* units2 = nullptr;   //                        stage-2 CTA columns (64 output columns each), n_units2 of them
+    int n_units2 = 0;
     unsigned* ltab = nullptr;       // chol_warp_kernel layout table (ranks <= 63 on the structured path)
     unsigned* ctab = nullptr;       // compact pair table (4 bytes per pair) of the structured path
     GPDev* gp = nullptr;
@@ -216,6 +218,16 @@ void free_buffers(Buffers& b) {
     b.sig_rows = 0;
 }
 
+// Batches from kTwoStageMinBatch walkers on take the two-stage column sums when the basis has a plan
+// (VELA_B200_TWO_STAGE=0 switches them off, VELA_B200_TWO_STAGE_MIN moves the threshold: A/B measurements).
+bool two_stage_taken(const VelaPulsar* h, long B) {
+    if (!h->sp.two_stage) return false;
+    if (const char* e = getenv("VELA_B200_TWO_STAGE")) if (atoi(e) == 0) return false;
+    long min_b = kTwoStageMinBatch;
+    if (const char* e = getenv("VELA_B200_TWO_STAGE_MIN")) min_b = std::max(1, atoi(e));
+    return B >= min_b;
+}
+
 int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
     Buffers& b = d.buf;
     if (B <= b.cap_B) return 0;
@@ -240,7 +252,7 @@ int ensure_device_buffers(VelaPulsar* h, DeviceModel& d, long B) {
         b.r_rows = std::max<long>(cap * 4, std::min<long>(65536, ((long)64 << 20) / ((long)h->sp.n_cols * 8)));
         CU(cudaMalloc((void**)&b.R, (size_t)b.r_rows * h->sp.n_cols * sizeof(double)));
         CU(cudaMemsetAsync(b.R, 0, (size_t)b.r_rows * h->sp.n_cols * sizeof(double), d.stream));
-        if (h->sp.two_stage && cap >= kTwoStageMinBatch) {
+        if (h->sp.two_stage && two_stage_taken(h, cap)) {
             b.mu_rows = round_up(cap, 512);
             const size_t nb = (size_t)h->sp.n_blocks * b.mu_rows * h->sp.k2_pad * sizeof(double);
             CU(cudaMalloc((void**)&b.mu, nb));
@@ -409,7 +421,8 @@ int launch_colsum(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, bool w
 
 // Two-stage column sums (vela_structured.h): stage 1 contracts w / w.y with the Chebyshev columns cell by cell (one
 // launch, split-K slices = cells, moments stored walker-major per block), stage 2 maps the moments to the column sums
-// with one small GEMM per run of output columns.  Same kernel both times.  Writes slab 0 of R; returns 1 (slab).
+// with small constant matrices, one run of output columns per block.  Same kernel both times.  Returns the number of
+// split-K slabs of R that stage 2 wrote.
 int launch_two_stage(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, ColsumArgs* out_args) {
     Buffers& b = d.buf;
     const StructPlan& sp = h->sp;
@@ -423,34 +436,38 @@ int launch_two_stage(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, Col
         dim3 grid((unsigned)sp.n_blocks, (unsigned)((B + 511) / 512), (unsigned)sp.n_cells);
         colsum_kernel<16, 2, 1, 16, true><<<grid, 512, colsum_smem_bytes(16, 2, 1, 16, true), st>>>(ca);
     }
-    // ---- stage 2: every job is a dense [n_out x k2_pad] x [k2_pad x B] product on the block's moments
-    for (const StructPlan::Stage2Job& job : sp.jobs) {
-        ColsumArgs c2;
-        const int n_units = (job.n_out + 31) / 32;
-        c2.T = d.T2 + job.t2_off; c2.ldT = sp.k2_pad; c2.n_cols = n_units * 32; c2.n_w_units = n_units; c2.n_rows_pad = sp.k2_pad;
-        c2.W = b.mu + (size_t)job.block * plane; c2.Y = c2.W; c2.ld_yw = sp.k2_pad; c2.B = B;
-        c2.R = b.R + job.r_off; c2.ld_r = sp.n_cols; c2.split_stride_r = 0; c2.plane_stride = 0; c2.n_valid = job.n_out;
-        // shape by the number of 32-column units of the run; all of the (short) K axis in one slice
-        if (n_units >= 3) {
-            c2.kt_per_split = (int)(sp.k2_pad / 16);
-            dim3 grid((unsigned)((n_units + 3) / 4), (unsigned)((B + 127) / 128), 1);
-            colsum_kernel<16, 4, 4, 4, true><<<grid, 512, colsum_smem_bytes(16, 4, 4, 4, true), st>>>(c2);
-        } else if (n_units == 2) {
-            c2.kt_per_split = (int)(sp.k2_pad / 32);
-            dim3 grid(1, (unsigned)((B + 255) / 256), 1);
-            colsum_kernel<32, 2, 2, 8, true><<<grid, 512, colsum_smem_bytes(32, 2, 2, 8, true), st>>>(c2);
-        } else {
-            c2.kt_per_split = (int)(sp.k2_pad / 16);
-            dim3 grid(1, (unsigned)((B + 511) / 512), 1);
-            colsum_kernel<16, 2, 1, 16, true><<<grid, 512, colsum_smem_bytes(16, 2, 1, 16, true), st>>>(c2);
-        }
+    // ---- stage 2: every job is a dense [n_out x k2_pad] x [k2_pad x B] product on its block's moments.  All jobs go in
+    // ONE launch: blockIdx.x walks the table of 64-column CTA columns built at create() (d.units2), so the grid is
+    // (CTA columns of all jobs) x (256-walker tiles) x (split-K slices) however short the single runs are - one launch
+    // per job left 32 - 64 CTAs on 148 SMs (0.17 + 0.17 ms at config 3).  Split-K by the same wave model as launch_colsum.
+    ColsumArgs c2;
+    c2.T = d.T2; c2.ldT = sp.k2_pad; c2.n_cols = 64; c2.n_w_units = 2; c2.n_rows_pad = sp.k2_pad;
+    c2.W = b.mu; c2.Y = b.mu; c2.ld_yw = sp.k2_pad; c2.B = B; c2.w_plane = plane;
+    c2.R = b.R; c2.ld_r = sp.n_cols; c2.plane_stride = 0; c2.n_valid = 0; c2.units = d.units2;
+    c2.split_stride_r = round_up(B, kSigMaxSamples) * (long)sp.n_cols;
+    const long n_ktiles = sp.k2_pad / 16;
+    const long ctas_xy = (long)d.n_units2 * ((B + 255) / 256);
+    const long max_split = std::max<long>(1, std::min<long>({kMaxBigSplit, std::max<long>(1, n_ktiles / 8),
+                                                              b.r_rows / std::max<long>(round_up(B, kSigMaxSamples), 1)}));
+    long ks_best = 1;
+    double best_cost = 1e300;
+    for (long ks = 1; ks <= max_split; ++ks) {
+        const long kt = (n_ktiles + ks - 1) / ks, nz = (n_ktiles + kt - 1) / kt;
+        if (nz != ks) continue;
+        const double frac = std::max((double)(ctas_xy * nz) / d.n_sm, 1.0);
+        const double cost = 0.5 * (std::ceil(frac) + frac) * ((double)kt + 16.0) * (1.0 + 0.002 * (double)(ks - 1));
+        if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; ks_best = ks; }
     }
-    h->launches += 1 + (int64_t)sp.jobs.size();
-    if (out_args) {
-        ca.R = b.R; ca.ld_r = sp.n_cols; ca.split_stride_r = round_up(B, kSigMaxSamples) * (long)sp.n_cols;
-        *out_args = ca;
+    if (const char* e = getenv("VELA_B200_STAGE2_KSPLIT")) ks_best = std::max<long>(1, std::min<long>(atoi(e), max_split));
+    c2.kt_per_split = (int)((n_ktiles + ks_best - 1) / ks_best);
+    const int nz = (int)((n_ktiles + c2.kt_per_split - 1) / c2.kt_per_split);
+    {
+        dim3 grid((unsigned)d.n_units2, (unsigned)((B + 255) / 256), (unsigned)nz);
+        colsum_kernel<16, 4, 2, 8, true><<<grid, 512, colsum_smem_bytes(16, 4, 2, 8, true), st>>>(c2);
     }
-    return 1;
+    h->launches += 2;
+    if (out_args) *out_args = c2;
+    return nz;
 }
 
 // WoodburyKernel{EcorrKernel}: subtract the per-group Sherman-Morrison terms from slab 0 of Sigma / U (K2b + K2c).
@@ -623,8 +640,7 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         ColsumArgs cs;
         int ksplit;
         if (h->sp.active) {
-            const bool two_off = getenv("VELA_B200_TWO_STAGE") && atoi(getenv("VELA_B200_TWO_STAGE")) == 0;
-            if (h->sp.two_stage && wy && b.mu && B >= kTwoStageMinBatch && B <= b.mu_rows && !two_off) {
+            if (wy && b.mu && B <= b.mu_rows && two_stage_taken(h, B)) {
                 ksplit = launch_two_stage(h, d, B, st, &cs);
                 h->launches -= 1;                            // (the caller counts one launch for this stage below)
             } else {
@@ -733,6 +749,13 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
             if (h->sp.two_stage) {
                 if (upload(&d.A1, h->sp.A1.data(), h->sp.A1.size())) return VELA_ERR_CUDA;
                 if (upload(&d.T2, h->sp.T2.data(), h->sp.T2.size())) return VELA_ERR_CUDA;
+                std::vector<ColsumUnit> units;
+                for (const StructPlan::Stage2Job& job : h->sp.jobs)
+                    for (int c = 0; c < job.n_out; c += 64)
+                        units.push_back(ColsumUnit{job.t2_off + (long)c * h->sp.k2_pad, (long)job.block, job.r_off + c,
+                                                   std::min(64, job.n_out - c)});
+                d.n_units2 = (int)units.size();
+                if (upload(&d.units2, units.data(), units.size())) return VELA_ERR_CUDA;
             }
             if (!h->ltab.empty() && upload(&d.ltab, h->ltab.data(), h->ltab.size())) return VELA_ERR_CUDA;
             if (!h->ctab.empty() && upload(&d.ctab, h->ctab.data(), h->ctab.size())) return VELA_ERR_CUDA;
@@ -749,7 +772,7 @@ void destroy_device(DeviceModel& d) {
     if (d.buf.h_params) cudaFreeHost(d.buf.h_params);
     if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
     if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
-    cudaFree(d.T); cudaFree(d.table); cudaFree(d.A1); cudaFree(d.T2); cudaFree(d.ltab); cudaFree(d.ctab);
+    cudaFree(d.T); cudaFree(d.table); cudaFree(d.A1); cudaFree(d.T2); cudaFree(d.units2); cudaFree(d.ltab); cudaFree(d.ctab);
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
     cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active); cudaFree(d.priors);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -1599,6 +1622,23 @@ VELA_API int vela_b200_chain_specialized(VelaHandle h, int on) {
 }
 
 VELA_API int vela_b200_sigma_structured(VelaHandle h) { return h ? (h->sp.active ? 1 : 0) : VELA_ERR_INVALID_ARG; }
+
+// What the Sigma stage of this handle executes for a batch of B walkers (measurement bookkeeping, bench.py):
+// info = {structured, two_stage (taken at this batch size), table columns n_cols, padded rows, stage-1 columns
+// (32 per block), stage-2 output columns as launched (64 per CTA column), moments per block and walker (k2_pad),
+// cells}.  Returns the FP64 operations per walker (2 per multiply-add) of the column-sum launches; 0 on the dense path.
+VELA_API double vela_b200_sigma_info(VelaHandle h, int64_t B, int64_t* info) {
+    if (!h) return 0.0;
+    const StructPlan& sp = h->sp;
+    const bool two = sp.active && two_stage_taken(h, B);
+    if (info) {
+        info[0] = sp.active ? 1 : 0; info[1] = two ? 1 : 0; info[2] = sp.n_cols; info[3] = h->n_rows_pad;
+        info[4] = (int64_t)sp.n_blocks * 32; info[5] = (int64_t)h->devs[0].n_units2 * 64; info[6] = sp.k2_pad; info[7] = sp.n_cells;
+    }
+    if (!sp.active) return 0.0;
+    if (!two) return 2.0 * (double)sp.n_cols * (double)h->n_rows_pad;
+    return 2.0 * (32.0 * sp.n_blocks * (double)h->n_rows_pad + 64.0 * h->devs[0].n_units2 * (double)sp.k2_pad);
+}
 
 // Compiler log / reason the specialised kernel is absent (empty when it compiled cleanly).
 VELA_API const char* vela_b200_jit_log(VelaHandle h) { return h ? h->jit_log.c_str() : ""; }

@@ -689,7 +689,14 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
         u_end = n_units;
         use_y = false;
     }
-    const int c0 = u_first * 32;
+    int c0 = u_first * 32, col_clamp = a.n_cols - 1, out_col0 = 0, n_valid = a.n_valid;
+    const double* Tbase = a.T;
+    const double* walker_src = (SPLIT && use_y) ? a.Y : a.W;
+    if (a.units) {   // stage-2 job table: this CTA column's own matrix, moment plane and output run
+        const ColsumUnit cu = a.units[blockIdx.x];
+        u_first = 0; u_end = (cu.n_valid + 31) / 32; c0 = 0; col_clamp = u_end * 32 - 1;
+        Tbase = a.T + cu.t_off; walker_src = a.W + (size_t)cu.w_off * a.w_plane; out_col0 = cu.r_col; n_valid = cu.n_valid;
+    }
 
     if (tid == 0) {
 #pragma unroll
@@ -700,7 +707,6 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
 
     const int kt0 = blockIdx.z * a.kt_per_split;
     const int n_ktiles = min(a.kt_per_split, (int)(a.n_rows_pad / BK) - kt0);
-    const double* walker_src = (SPLIT && use_y) ? a.Y : a.W;
     auto issue = [&](int t) {
         const int s = t % STAGES;
         double* base = smem + (size_t)s * stage_doubles;
@@ -708,7 +714,7 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
         for (int c = tid; c < total_chunks; c += kThreads) {
             int r = c / kChunks, ch = c - r * kChunks;
             const double* src;
-            if (r < NCOL) src = a.T + (size_t)min(c0 + r, a.n_cols - 1) * a.ldT + j0 + ch * 2;
+            if (r < NCOL) src = Tbase + (size_t)min(c0 + r, col_clamp) * a.ldT + j0 + ch * 2;
             else if (r < NCOL + NS) src = walker_src + (size_t)min(b0 + (r - NCOL), a.B - 1) * a.ld_yw + j0 + ch * 2;
             else src = a.Y + (size_t)min(b0 + (r - NCOL - NS), a.B - 1) * a.ld_yw + j0 + ch * 2;
             cp_async16(base + (size_t)r * PITCH + ch * 2, src);
@@ -765,8 +771,8 @@ __global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
     if (!have_unit) return;
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
-        const int col = u * 32 + i * 8 + gid;
-        if (a.n_valid && col >= a.n_valid) continue;
+        const int col = out_col0 + u * 32 + i * 8 + gid;
+        if (n_valid && col - out_col0 >= n_valid) continue;
         // normal mode: one slab per split-K slice; moment mode: walker-major planes per 32-column block, slice = cell
         double* dst = a.plane_stride ? a.R + (size_t)u * a.plane_stride + (size_t)blockIdx.z * 32 + (i * 8 + gid)
                                      : a.R + (size_t)blockIdx.z * a.split_stride_r + col;

@@ -39,6 +39,15 @@ struct SigmaArgs {
     long split_stride_u;
 };
 
+// One CTA column of a stage-2 launch of the two-stage column sums (ColsumArgs::units): up to 32 UC output columns fed by
+// one block's cell moments.
+struct ColsumUnit {
+    long t_off;                // first of its columns inside ColsumArgs::T (doubles)
+    long w_off;                // its stage-1 block: the moments start at ColsumArgs::W + w_off * ColsumArgs::w_plane
+    int r_col;                 // first output column in R
+    int n_valid;               // output columns of this CTA column (<= 32 UC); the rest of the tile is padding
+};
+
 // K3s: column sums  R[b, c] = sum_j T[j, c] * (c < n_w_cols ? w[b, j] : w[b, j] y[b, j])  (structured Sigma path)
 struct ColsumArgs {
     const double* T;           // column-major [n_rows_pad x n_cols], leading dimension ldT; n_cols multiple of 32
@@ -57,8 +66,11 @@ struct ColsumArgs {
     // two-stage evaluation (vela_structured.h): stage 1 stores the cell moments walker-major per 32-column block,
     //   R[(col / 32) * plane_stride + b * ld_r + slice * 32 + col % 32]      (plane_stride > 0; slice = cell)
     // and stage 2 stores only its first n_valid columns (0 = all): its output runs are not multiples of 32
-    long plane_stride;
-    int n_valid;
+    long plane_stride = 0;
+    int n_valid = 0;
+    // stage 2 as ONE launch: blockIdx.x indexes this table instead of the 32 UC-column units of T (nullptr otherwise)
+    const ColsumUnit* units = nullptr;
+    long w_plane = 0;          // doubles between the moment planes of consecutive blocks
 };
 
 // Sigma[p][q] = c1 R[i1] + c2 R[i2]  (c2 == 0: single term) for the packed pair t = p(p+1)/2 + q

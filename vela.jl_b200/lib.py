@@ -24,6 +24,7 @@ EXPORTS = [
     "vela_b200_marginalized_mean_batch", "vela_b200_chain_specialized", "vela_b200_jit_log",
     "vela_b200_debug_spec_source", "vela_b200_debug_spec_compile", "vela_b200_debug_structured_sigma",
     "vela_b200_sigma_structured", "vela_b200_debug_div3", "vela_b200_debug_fp64_coissue", "vela_b200_debug_two_stage",
+    "vela_b200_sigma_info",
 ]
 
 
@@ -96,6 +97,8 @@ def lib():
     L.vela_b200_debug_fp64_coissue.argtypes = [C.c_int, dp]
     L.vela_b200_debug_two_stage.argtypes = [vp, dp, dp, dp, dp, C.POINTER(C.c_int64)]
     L.vela_b200_debug_two_stage.restype = i64
+    L.vela_b200_sigma_info.argtypes = [vp, i64, C.POINTER(C.c_int64)]
+    L.vela_b200_sigma_info.restype = C.c_double
     L.vela_b200_fp64_peak_tflops.argtypes = [C.c_int, C.c_int]
     L.vela_b200_fp64_peak_tflops.restype = C.c_double
     _LIB = L
