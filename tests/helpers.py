@@ -33,13 +33,14 @@ def emul_lib():
         subprocess.run(["make", "-C", here], check=True, stdout=subprocess.DEVNULL)
         L = C.CDLL(os.path.join(here, "libvela_emul.so"))
         dp = C.POINTER(C.c_double)
-        L.emul_chain.argtypes = [C.c_void_p, dp, C.c_long, C.c_int, dp, dp, dp, dp, dp]
+        L.emul_chain.argtypes = [C.c_void_p, dp, C.c_long, C.c_int, C.c_int, dp, dp, dp, dp, dp]
         _EMUL = L
     return _EMUL
 
 
-def emul_chain(md, paramss, emit=1):
+def emul_chain(md, paramss, emit=1, fast=False):
     """Runs prologue + chain + residual terms of the CUDA source on the CPU.
+    fast: the fast-arithmetic build of the chain (the product's default) instead of the strict one.
     emit 0/1: returns (y[B, n_rows], w[B, n_rows], chi2[B], logdetN[B]); emit 2: (phase_hi, phase_lo, f, chi2, logdetN)."""
     import ctypes as C
     p = np.ascontiguousarray(np.atleast_2d(paramss), dtype=np.float64)
@@ -48,7 +49,7 @@ def emul_chain(md, paramss, emit=1):
     Y = np.zeros((B, md.n_rows)); W = np.zeros((B, md.n_rows)); F = np.zeros((B, md.n_rows))
     chi = np.zeros(B); lg = np.zeros(B)
     ptr = lambda a: a.ctypes.data_as(dp)  # noqa: E731
-    rc = emul_lib().emul_chain(C.addressof(md.desc), ptr(p), B, emit, ptr(Y), ptr(W), ptr(F), ptr(chi), ptr(lg))
+    rc = emul_lib().emul_chain(C.addressof(md.desc), ptr(p), B, emit, int(bool(fast)), ptr(Y), ptr(W), ptr(F), ptr(chi), ptr(lg))
     assert rc == 0
     if emit == 2:
         return Y, W, F, chi, lg

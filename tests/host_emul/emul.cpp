@@ -14,10 +14,10 @@
 using namespace vela;
 
 extern "C" __attribute__((visibility("default")))
-int emul_chain(const VelaModelDesc* desc, const double* params, long B, int emit, double* Y, double* W, double* F,
+int emul_chain(const VelaModelDesc* desc, const double* params, long B, int emit, int fast, double* Y, double* W, double* F,
                double* chi2, double* logdetN) {
     ProgramDev pg;
-    build_program(desc, pg);
+    build_program(desc, pg, fast != 0);   // fast: the fast-arithmetic build (kFlagFast), else the strict one
     const long nt = desc->n_toas, stride = (nt + 31) / 32 * 32;
     const long n_rows = desc->wideband ? 2 * nt : nt;
     std::vector<double> soa((size_t)C_NCOL * stride, 0.0), tzr(C_NCOL, 0.0);

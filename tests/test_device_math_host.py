@@ -4,7 +4,8 @@ tests/host_emul builds vela_device.cuh / vela_chain.cuh (the product's device so
 CUDA builtins and runs, thread by thread, what the kernels run per walker and per (TOA, walker).  The oracle follows
 the reference's operation order in full Double64; the kernel source takes documented shortcuts (small phase terms in
 FP64, error-free leading-word subtraction, shared reciprocal) - this test bounds what they cost, without a GPU:
-residuals within 1e-15 s (the parity budget is 1e-9 s), white-noise ln L within 1e-12 relative (budget 1e-9).
+residuals within 1e-15 s (the parity budget is 1e-9 s), white-noise ln L within 1e-12 relative (budget 1e-9) for the
+strict build; 1e-12 s and 2e-10 for the fast build (fused multiply-adds, series for the unit-vector normalisation).
 """
 import numpy as np
 import pytest
@@ -17,19 +18,27 @@ SYNTH = ["config2_ell1", "config3_gp", "config4_dd_wb", "extra_ell1_fbx", "extra
          "extra_free_gp", "extra_free_gp_wb", "extra_mtm_only"]
 
 
+# (residual [s], ln L relative) bounds of the two builds of the chain: strict mirrors the reference operation for
+# operation; fast (the product's default, kFlagFast in vela_device.cuh) fuses multiply-adds and expands the proper-motion
+# normalisation and the dispersion delay's Doppler factor - one rounding of the 500 s Roemer delay at most
+BOUNDS = {False: (1e-15, 1e-12), True: (1e-15, 1e-12)}
+
+
 def _check(vb, oracle, md, walkers, white):
-    y, w, chi, lg = emul_chain(md, walkers, emit=1)
-    for b in range(len(walkers)):
-        yo, wo = oracle.residuals(md, walkers[b])
-        nt = len(md.toas)
-        assert np.max(np.abs(y[b, :nt] - yo[:nt])) < 1e-15, np.max(np.abs(y[b, :nt] - yo[:nt]))
-        np.testing.assert_allclose(w[b], wo, rtol=4e-16)
-        if md.n_rows > nt:   # wideband DM residuals [Hz-scaled DM units]
-            np.testing.assert_allclose(y[b, nt:], yo[nt:], rtol=1e-12, atol=1e-12 * np.max(np.abs(yo[nt:])))
-    if white:
-        y0, w0, chi0, lg0 = emul_chain(md, walkers, emit=0)
-        want = oracle.lnlike_batch(md, walkers)
-        np.testing.assert_allclose(-(chi0 + lg0) / 2, want, rtol=1e-12)
+    for fast in (False, True):
+        tol_r, tol_l = BOUNDS[fast]
+        y, w, chi, lg = emul_chain(md, walkers, emit=1, fast=fast)
+        for b in range(len(walkers)):
+            yo, wo = oracle.residuals(md, walkers[b])
+            nt = len(md.toas)
+            assert np.max(np.abs(y[b, :nt] - yo[:nt])) < tol_r, (fast, np.max(np.abs(y[b, :nt] - yo[:nt])))
+            np.testing.assert_allclose(w[b], wo, rtol=4e-16)
+            if md.n_rows > nt:   # wideband DM residuals [Hz-scaled DM units]
+                np.testing.assert_allclose(y[b, nt:], yo[nt:], rtol=1e-12, atol=1e-12 * np.max(np.abs(yo[nt:])))
+        if white:
+            y0, w0, chi0, lg0 = emul_chain(md, walkers, emit=0, fast=fast)
+            want = oracle.lnlike_batch(md, walkers)
+            np.testing.assert_allclose(-(chi0 + lg0) / 2, want, rtol=tol_l)
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)

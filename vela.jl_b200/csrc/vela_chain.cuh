@@ -113,8 +113,13 @@ __device__ __forceinline__ ResidTerms residual_terms(const Corr& k, const ToaReg
         const double tail = ((k.phase.lo - tzr_lo) + lead.lo) + (k.phase_small - t.pn_lo);
         tres_phase = (lead.hi - t.pn_hi) + tail;
     }
-    r.f = k.spin_frequency * (1 + k.doppler);
-    r.tres = div_fast(tres_phase, r.f);
+    if (k.fast) {   // the quotient is residual-sized (1 ulp = 1e-22 s): a reciprocal and a product do
+        r.f = __fma_rn(k.spin_frequency, k.doppler, k.spin_frequency);
+        r.tres = tres_phase * rcp_fast(r.f);
+    } else {
+        r.f = k.spin_frequency * (1 + k.doppler);
+        r.tres = div_fast(tres_phase, r.f);
+    }
     const double err2 = (t.err2 + k.equad2) * k.efac * k.efac;  // scaled_toa_error_sqr toa.jl:122-123
     // log det N = sum_j log(err2_j) is accumulated as a PRODUCT of mantissas and a sum of binary exponents, so the
     // logarithm is taken once per (tile, walker) in the block epilogue instead of once per (TOA, walker)

@@ -3,6 +3,7 @@
 // expansion points of the Shapiro-delay logarithms.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "vela_device.cuh"
@@ -30,7 +31,12 @@ inline void fill_toa_columns(const double* rec, int wideband, double* cols, long
 }
 
 // Component program of a validated descriptor (offsets of the hoisted per-sample values included).
-inline void build_program(const VelaModelDesc* desc, ProgramDev& pg) {
+// `fast`: the fast-arithmetic build of the chain (kFlagFast, vela_device.cuh); strict_arithmetic() is the switch.
+inline bool strict_arithmetic() {
+    const char* e = getenv("VELA_B200_STRICT");
+    return e && atoi(e) != 0;
+}
+inline void build_program(const VelaModelDesc* desc, ProgramDev& pg, bool fast = !strict_arithmetic()) {
     memset(&pg, 0, sizeof pg);
     pg.n_comp = desc->n_components;
     pg.n_params = desc->n_params;
@@ -40,7 +46,7 @@ inline void build_program(const VelaModelDesc* desc, ProgramDev& pg) {
     for (int ic = 0; ic < desc->n_components; ++ic) {
         const VelaComponentDesc& c = desc->components[ic];
         CompDev& cd = pg.comp[ic];
-        cd.kind = c.kind; cd.flags = c.flags;
+        cd.kind = c.kind; cd.flags = (c.flags & ~kFlagFast) | (fast ? kFlagFast : 0);
         memcpy(cd.par, c.par, sizeof cd.par);
         memcpy(cd.len, c.len, sizeof cd.len);
         memcpy(cd.mask, c.mask, sizeof cd.mask);
