@@ -195,6 +195,38 @@ def test_warp_per_walker_cholesky_matches_cta_kernel(vb, monkeypatch):
             np.testing.assert_allclose(got, ref, rtol=1e-13)
 
 
+@pytest.mark.parametrize("name,ntoa", [("config3_gp", 1500), ("config4_dd_wb", 900), ("extra_mtm_only", None),
+                                       ("extra_dmjump_bits_wb", None)])
+def test_tensor_core_cholesky_matches_cta_kernel(name, ntoa, vb, oracle, monkeypatch):
+    """chol_dmma_kernel (default for ranks <= 64 on the structured path: one warp per walker, 8 x 8 blocks in DMMA
+    fragment registers) against the CTA-per-walker kernel (VELA_B200_CHOL_DMMA=0) on the same walkers, at batch sizes
+    that take the graph replay, the deep split-K and the two-stage column sums, and against the oracle."""
+    if name not in vb.synth.CONFIGS:
+        pytest.skip("no such synthetic case")
+    ds = vb.synth.make_dataset(name, lambda m, t: vb.Pulsar(m, t), ntoa=ntoa)
+    psr = vb.Pulsar(ds.model, ds.toas)
+    if not psr.sigma_structured():
+        pytest.skip("dense Sigma path: the CTA kernel is the only one")
+    for B in (1, 5, 70, 1500):
+        W = ds.walkers(B, seed=13)
+        got = psr.lnlike_vectorized(W)
+        monkeypatch.setenv("VELA_B200_CHOL_DMMA", "0")
+        ref = psr.lnlike_vectorized(W)
+        monkeypatch.delenv("VELA_B200_CHOL_DMMA")
+        assert np.all(np.isfinite(ref))
+        np.testing.assert_allclose(got, ref, rtol=1e-12)
+    md = vb.ModelDescriptor(ds.model, ds.toas)
+    np.testing.assert_allclose(got[:4], oracle.lnlike_batch(md, W[:4]), rtol=1e-9)
+    # a walker whose Sigma^-1 is not positive definite (NaN amplitude) must come out as -Inf from this kernel too
+    bad = W[:3].copy()
+    names = list(ds.info["free_names"])
+    amp = [i for i, n in enumerate(names) if "AMP" in n.upper()]
+    if amp:
+        bad[1, amp[0]] = np.nan
+        out = psr.lnlike_vectorized(bad)
+        assert np.isfinite(out[0]) and out[1] == -np.inf and np.isfinite(out[2])
+
+
 @pytest.mark.parametrize("name,ntoa", [("config3_gp", 1500), ("extra_ecorr_gp_r140", None), ("config4_dd_wb", 900)])
 def test_panel_cholesky_matches_shared_memory_kernel(name, ntoa, vb, oracle, monkeypatch):
     """chol_panel_kernel (large ranks: 32-column panels + DMMA trailing updates on the global scratch) forced onto small

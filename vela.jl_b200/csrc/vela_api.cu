@@ -107,6 +107,7 @@ struct DeviceModel {
     ColsumUnit* units2 = nullptr;   //                        stage-2 CTA columns (64 output columns each), n_units2 of them
     int n_units2 = 0;
     unsigned* ltab = nullptr;       // chol_warp_kernel layout table (ranks <= 63 on the structured path)
+    unsigned* ftab = nullptr;       // chol_dmma_kernel fragment table (ranks <= 64 on the structured path)
     unsigned* ctab = nullptr;       // compact pair table (4 bytes per pair) of the structured path
     GPDev* gp = nullptr;
     double* gp_data = nullptr;
@@ -187,6 +188,7 @@ struct VelaPulsar {
     long eg_pad = 0, ldv = 0;
     bool chol_smem = true;
     std::vector<unsigned> ltab;      // layout table of chol_warp_kernel; empty = that kernel is not used
+    std::vector<unsigned> ftab;      // fragment table of chol_dmma_kernel; empty = not available
     std::vector<unsigned> ctab;      // compact pair table; empty = some coefficient / index does not fit the 4-byte code
     int chol_nb = 8;                 // block width of the Cholesky kernel
     size_t chol_smem_bytes = 0;
@@ -647,10 +649,11 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
                 ksplit = launch_colsum(h, d, B, st, wy, &cs);
             }
             const bool warp_on = getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 1;
-            if (ksplit > 4 && warp_on && d.ltab && !d_ahat && h->n_eg == 0) {
+            const bool dmma_on = d.ftab && !(getenv("VELA_B200_CHOL_DMMA") && atoi(getenv("VELA_B200_CHOL_DMMA")) == 0);
+            if (ksplit > 4 && ((warp_on && d.ltab) || (dmma_on && !warp_on)) && !d_ahat && h->n_eg == 0) {
                 // emcee-sized batches split K deeply to fill the SMs; summing 16 - 64 slabs per entry would be the longest
-                // serial stretch of the warp-per-walker finishing kernel, so a wide kernel does it first, in slice order
-                // (the CTA-per-walker kernel sums its slabs itself: 128 threads, cheaper than one more launch)
+                // serial stretch of the warp-per-walker finishing kernels (chol_dmma_kernel, chol_warp_kernel), so a wide
+                // kernel does it first, in slice order (the CTA-per-walker kernel sums its slabs itself: 128 threads)
                 const long n = B * (long)h->sp.n_cols;
                 slab_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.R, cs.split_stride_r, ksplit, n);
                 h->launches += 1;
@@ -688,6 +691,16 @@ int enqueue_batch(VelaPulsar* h, DeviceModel& d, const double* d_params, long B,
         const bool warp_off = !(getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 1);
         ch.ltab = d.ltab;
         ch.ctab = d.ctab;
+        ch.ftab = d.ftab;
+        // ranks up to 64 on the structured path: the tensor-core kernel with the matrix in registers (chol_dmma_kernel),
+        // unless the conditional mean is wanted or an ECORR correction has to be added; VELA_B200_CHOL_DMMA=0 switches it off
+        const bool dmma_off = getenv("VELA_B200_CHOL_DMMA") && atoi(getenv("VELA_B200_CHOL_DMMA")) == 0;
+        if (d.ftab && !d_ahat && h->n_eg == 0 && !dmma_off && warp_off) {
+            const int nbk = chol_dmma_nbk(h->p);
+            const size_t sm = chol_dmma_smem_bytes(nbk, h->sp.n_r + h->p);
+            (nbk == 2 ? chol_dmma_kernel<2> : nbk == 4 ? chol_dmma_kernel<4> : nbk == 6 ? chol_dmma_kernel<6> : chol_dmma_kernel<8>)
+                <<<(unsigned)B, 32, sm, st>>>(ch);
+        } else
         if (d.ltab && !d_ahat && !warp_off && h->n_eg == 0) {
             const int n_ru = h->sp.n_r + h->p;
             chol_warp_kernel<<<(unsigned)B, 32, chol_warp_smem_bytes(h->p, n_ru), st>>>(ch);
@@ -758,6 +771,7 @@ int build_device(VelaPulsar* h, DeviceModel& d, const VelaModelDesc* desc, const
                 if (upload(&d.units2, units.data(), units.size())) return VELA_ERR_CUDA;
             }
             if (!h->ltab.empty() && upload(&d.ltab, h->ltab.data(), h->ltab.size())) return VELA_ERR_CUDA;
+            if (!h->ftab.empty() && upload(&d.ftab, h->ftab.data(), h->ftab.size())) return VELA_ERR_CUDA;
             if (!h->ctab.empty() && upload(&d.ctab, h->ctab.data(), h->ctab.size())) return VELA_ERR_CUDA;
         }
     }
@@ -772,7 +786,7 @@ void destroy_device(DeviceModel& d) {
     if (d.buf.h_params) cudaFreeHost(d.buf.h_params);
     if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
     if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
-    cudaFree(d.T); cudaFree(d.table); cudaFree(d.A1); cudaFree(d.T2); cudaFree(d.units2); cudaFree(d.ltab); cudaFree(d.ctab);
+    cudaFree(d.T); cudaFree(d.table); cudaFree(d.A1); cudaFree(d.T2); cudaFree(d.units2); cudaFree(d.ltab); cudaFree(d.ftab); cudaFree(d.ctab);
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
     cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active); cudaFree(d.priors);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -1013,6 +1027,46 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
             for (int i = 0; i < h->p; ++i) h->ltab[cw_slot(h->p, i, NR)] = (2u << 29) | (unsigned)(h->sp.n_r + i);
             if (!ok) h->ltab.clear();
         }
+        // ranks up to 64 on the structured path: fragment table of the tensor-core Cholesky kernel - for every block
+        // (36 of Sigma at 8 block rows, then the u row's 8), register and lane, two 16-bit indices (i1 | i2 << 16) into
+        // the walker's pre-scaled sums S = {-R/2, -u/2 | +R/2, +u/2 | 0 | -1/2}: the (negated) entry is S[i1] + S[i2].
+        // lane l = 4 r + t, register e  <->  row pi(r), column 4 e + t of the block (chol_dmma_kernel, vela_kernels.cu);
+        // entries are grouped in fours per lane (one 16-byte load): word 4 g + q of lane l sits at (g * 32 + l) * 4 + q.
+        if (h->sp.active && h->p <= kCholDmmaMaxRank && 2 * (h->sp.n_r + h->p) + 2 <= 65535) {
+            const int nbk = chol_dmma_nbk(h->p), nt0 = nbk * (nbk + 1) / 2, nt = nt0 + nbk;
+            const unsigned n_ru = (unsigned)(h->sp.n_r + h->p), zero = 2 * n_ru, half_one = 2 * n_ru + 1;
+            h->ftab.assign((size_t)((2 * nt + 3) / 4) * 128, zero | (zero << 16));
+            bool ok = true;
+            for (int I = 0; I <= nbk && ok; ++I)
+                for (int J = 0; J <= (I < nbk ? I : nbk - 1) && ok; ++J) {
+                    const int blk = I < nbk ? I * (I + 1) / 2 + J : nt0 + J;
+                    for (int e = 0; e < 2 && ok; ++e)
+                        for (int l = 0; l < 32; ++l) {
+                            const int rr = cd_pi(l >> 2), cc = 4 * e + (l & 3);
+                            unsigned i1 = zero, i2 = zero;
+                            if (I < nbk) {
+                                const int row = 8 * I + rr, col = 8 * J + cc;
+                                if (row < h->p && col < h->p) {
+                                    const int hi = std::max(row, col), lo = std::min(row, col);
+                                    const PairTerm& pt = h->sp.table[(size_t)hi * (hi + 1) / 2 + lo];
+                                    i1 = (unsigned)pt.i1;
+                                    if (pt.c1 == 1.0 && pt.c2 == 0.0) i2 = i1;                     // R1 = (R1 + R1) / 2
+                                    else if (pt.c1 == 0.5 && pt.c2 == 0.0) i2 = zero;
+                                    else if (pt.c1 == 0.5 && pt.c2 == 0.5) i2 = (unsigned)pt.i2;
+                                    else if (pt.c1 == 0.5 && pt.c2 == -0.5) i2 = n_ru + (unsigned)pt.i2;
+                                    else { ok = false; break; }                                    // a coefficient this form cannot carry
+                                } else if (row == col) {
+                                    i1 = i2 = half_one;                                            // identity padding past the rank
+                                }
+                            } else if (rr == 0 && 8 * J + cc < h->p) {
+                                i1 = i2 = (unsigned)(h->sp.n_r + 8 * J + cc);                      // u^T: row 0 of the last block row
+                            }
+                            const int word = blk * 2 + e;
+                            h->ftab[(size_t)((word >> 2) * 32 + l) * 4 + (word & 3)] = i1 | (i2 << 16);
+                        }
+                }
+            if (!ok) h->ftab.clear();
+        }
     }
 
     // SoA TOA table (+ TOA-only hoists) and the TZR block
@@ -1174,7 +1228,10 @@ static int run_host_batch(VelaHandle h, const double* params, int64_t B, int64_t
                 const int prior_src = !with_prior ? 0 : (lnprior ? 1 : (h->have_priors ? 2 : 3));
                 if (prior_src == 1) memcpy(b.h_lnprior, lnprior + r0[i], sizeof(double) * n);
                 // the kernel-variant switch read at enqueue time is part of the key (A/B tests flip it between calls)
-                const int variant = (getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 1) ? 16 : 0;
+                const int variant = ((getenv("VELA_B200_CHOL_WARP") && atoi(getenv("VELA_B200_CHOL_WARP")) == 1) ? 16 : 0) |
+                                    ((getenv("VELA_B200_CHOL_DMMA") && atoi(getenv("VELA_B200_CHOL_DMMA")) == 0) ? 32 : 0) |
+                                    ((getenv("VELA_B200_CHOL_PANEL") && atoi(getenv("VELA_B200_CHOL_PANEL")) == 0) ? 64 : 0) |
+                                    (two_stage_taken(h, n) ? 128 : 0);
                 auto key = std::make_tuple(n, mode, with_prior, prior_src | variant);
                 auto it = b.graphs.find(key);
                 if (it == b.graphs.end()) {

@@ -1641,6 +1641,256 @@ __global__ void __launch_bounds__(32) chol_warp_kernel(CholArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K4d  Cholesky finish on the FP64 tensor cores, one WARP per walker, matrix in registers (ranks up to 64)
+// ------------------------------------------------------------------------------------------
+// Same quantities as chol_finish_kernel.  Sigma^-1 is cut into 8 x 8 blocks (NBK block rows, identity padding past
+// rank p) and u^T is one more block row; every block lives in two registers per lane, in the operand layout of
+// mma.sync.m8n8k4.f64 with rows AND columns permuted by pi(n) = 4 (n & 1) + (n >> 1):
+//     lane l = 4 r + t, register e  holds  X[pi(r)][4 e + t].
+// In that layout the two registers of a block ARE its A fragments (k-halves e = 0, 1) and its B fragments, and a
+// product A.B^T of two such blocks comes out of the DMMA in the same layout again, so the blocked right-looking
+// factorisation needs no data movement between its steps:
+//   * diagonal block (k, k): its rows are gathered by shuffle (lane & 7 = row, four replicas), factorised in registers
+//     as in factor_diag_block_warp, and the inverse W of the 8 x 8 factor is formed column by column (lane = column;
+//     the factor's entries are broadcast shared-memory reads);
+//   * panel: L(I, k) = A(I, k) W^T - two DMMAs per block, W^T read from shared memory in B layout;
+//   * trailing update: A(I, J) -= L(I, k) L(J, k)^T - two DMMAs per block, operands = the panel registers.
+// All blocks are stored NEGATED, so the panel product yields -L and the update adds (-L)(-L)^T: no negations anywhere.
+// The u row rides along as block row NBK: its panel blocks end as -z^T (z = L^-1 u), z.z is accumulated from them.
+// Per walker: ~6 k warp instructions against ~21 k of the CTA-per-walker kernel, and a dependent chain of 8 block
+// steps with no barrier and no shared-memory matrix traffic.  The blocks are filled through a fragment table built at
+// create(): per lane and register two 16-bit indices into the walker's pre-scaled column sums (entry = S[i1] + S[i2]).
+// The factorisation of the diagonal block and its inverse are ONE copy of code inside a rolled loop over the block
+// steps (the first version unrolled everything: 64 KB of straight-line code, and the warps waited for instructions
+// more than for anything else); only the DMMA steps are unrolled, selected by a switch.
+// Step K of the blocked factorisation on the register blocks: panel products against W^T (wf0 / wf1: its two k-halves
+// in B layout) and the trailing update.  Every block index is a compile-time constant.
+template <int NBK, int K>
+__device__ __forceinline__ void cd_step(double (&m)[NBK * (NBK + 1) / 2 + NBK][2], double wf0, double wf1, double& zz) {
+    constexpr int NT0 = NBK * (NBK + 1) / 2;
+    // panel: -L(I, K) = (-A(I, K)) W^T; the u row's blocks end as -z^T
+#pragma unroll
+    for (int I = K + 1; I <= NBK; ++I) {
+        const int blk = I < NBK ? I * (I + 1) / 2 + K : NT0 + K;
+        double x0 = 0.0, x1 = 0.0;
+        dmma8x8x4(x0, x1, m[blk][0], wf0);
+        dmma8x8x4(x0, x1, m[blk][1], wf1);
+        m[blk][0] = x0; m[blk][1] = x1;
+        if (I == NBK) zz = fma(x0, x0, fma(x1, x1, zz));
+    }
+    // trailing update: (-A(I, J)) += (-L(I, K)) (-L(J, K))^T
+#pragma unroll
+    for (int I = K + 1; I <= NBK; ++I) {
+        const int bi = I < NBK ? I * (I + 1) / 2 + K : NT0 + K;
+#pragma unroll
+        for (int J = K + 1; J <= (I < NBK ? I : NBK - 1); ++J) {
+            const int bj = J * (J + 1) / 2 + K;
+            const int bij = I < NBK ? I * (I + 1) / 2 + J : NT0 + J;
+            dmma8x8x4(m[bij][0], m[bij][1], m[bi][0], m[bj][0]);
+            dmma8x8x4(m[bij][0], m[bij][1], m[bi][1], m[bj][1]);
+        }
+    }
+}
+
+template <int NBK>
+__global__ void __launch_bounds__(32) chol_dmma_kernel(CholArgs a) {
+    constexpr int NT0 = NBK * (NBK + 1) / 2, NT = NT0 + NBK;
+    constexpr unsigned kFull = 0xffffffffu;
+    extern __shared__ __align__(16) double smem[];
+    const long b = blockIdx.x;
+    const int lane = threadIdx.x, r = lane >> 2, t = lane & 3;
+    const int p = a.p, n_ru = a.n_r + p;
+    double* sW = smem;                 // [64] inverse of the current diagonal factor, row-major
+    double* sL = sW + 64;              // [64] the current diagonal factor, row-major, reciprocal pivots on the diagonal
+    double* sPhi = sL + 72;            // [8 NBK] Phi^-1 (zero past p)
+    double* sS = sPhi + 8 * NBK;       // [2 n_ru + 2]: -R / 2, -u / 2 | +R / 2, +u / 2 | 0 | -1 / 2
+
+    // ---- the column sums and u (split-K slabs summed in slice order), pre-scaled for the assembly below; u follows the
+    //      column sums both in R (u_off == n_r rounded to 32: read through a second index) and in S
+    {
+        const double* gR = a.R + (size_t)b * a.ld_r;
+#pragma unroll 4
+        for (int i = lane; i < n_ru; i += 32) {
+            const double* g = gR + (i < a.n_r ? i : a.u_off + (i - a.n_r));
+            // (one to four slabs at full size: plain loads, all in flight; emcee-sized batches split K up to 64 ways)
+            double v = a.ksplit <= 4 ? g[0] : slab_sum(g, a.split_stride_r, a.ksplit);
+            if (a.ksplit <= 4) {
+                const double v1 = a.ksplit > 1 ? g[a.split_stride_r] : 0.0, v2 = a.ksplit > 2 ? g[2 * a.split_stride_r] : 0.0,
+                             v3 = a.ksplit > 3 ? g[3 * a.split_stride_r] : 0.0;
+                v = ((v + v1) + v2) + v3;
+            }
+            v *= 0.5;
+            sS[i] = -v; sS[n_ru + i] = v;
+        }
+        if (lane == 0) { sS[2 * n_ru] = 0.0; sS[2 * n_ru + 1] = -0.5; }
+    }
+    // ---- Phi^-1 (calc_noise_weights_inv); log det Phi as a mantissa product
+    for (int i = lane; i < 8 * NBK; i += 32) sPhi[i] = 0.0;
+    __syncwarp();
+    const double* P = a.Pext + (size_t)b * a.row;
+    double pman = 1.0;
+    int pex = 0;
+    for (int g = 0; g < a.n_gp; ++g) {
+        const GPDev gp = a.gp[g];
+        if (gp.kind == VELA_GP_MARGINALIZED_TM) {
+            for (int i = lane; i < gp.n; i += 32) {
+                const double v = a.gp_data[gp.data0 + i];
+                sPhi[gp.col0 + i] = v;
+                int ex;
+                pman *= split_mantissa(v, &ex);
+                pex += ex;
+            }
+        } else {
+            // powerlaw(A, gamma, f1, f1) gp_noise.jl:12-16 with A = exp10(log10_A)
+            const double fyr = 1.0 / 3600 / 24 / 365.25;
+            const double denom = 12 * (CUDART_PI * CUDART_PI) * fyr * fyr * fyr;
+            const double amp = exp10(P[gp.par_log10_amp]), gamma = P[gp.par_gamma], f1 = P[gp.par_f1];
+            const double P1 = amp * amp / denom * pow(fyr / f1, gamma) * f1;
+            for (int i = lane; i < gp.n; i += 32) {
+                const double v = 1 / (P1 * exp(-gamma * a.gp_data[gp.data0 + i]));
+                sPhi[gp.col0 + i] = v;
+                sPhi[gp.col0 + gp.n + i] = v;
+                int ex;
+                const double mv = split_mantissa(v, &ex);   // the weight serves the sine and the cosine column
+                pman *= mv * mv;
+                pex += 2 * ex;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        pman *= __shfl_xor_sync(kFull, pman, off);
+        pex += __shfl_xor_sync(kFull, pex, off);
+    }
+    const double logdetPhi = -(log(pman) + pex * 0.6931471805599453);   // log det Phi = -sum log Phi^-1
+    __syncwarp();
+
+    // ---- the blocks, negated: entry = S[i1] + S[i2] with the two 16-bit indices of the fragment table (four entries
+    //      per 16-byte load; 0.5 (R1 +- R2), R1 = 0.5 (R1 + R1), the identity padding and zero all take this one form)
+    double m[NT][2];
+    {
+        const uint4* ft = reinterpret_cast<const uint4*>(a.ftab) + lane;
+#pragma unroll
+        for (int g = 0; g < (2 * NT + 3) / 4; ++g) {
+            const uint4 c4 = __ldg(ft + g * 32);
+            const unsigned cs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * g + q < 2 * NT) m[(4 * g + q) >> 1][(4 * g + q) & 1] = sS[cs[q] & 0xffffu] + sS[cs[q] >> 16];
+        }
+    }
+    if (t == (r >> 1)) {   // this lane holds a diagonal entry of every diagonal block: row pi(r), register r & 1
+#pragma unroll
+        for (int I = 0; I < NBK; ++I) {
+            const double ph = sPhi[8 * I + cd_pi(r)];
+            if (r & 1) m[I * (I + 1) / 2 + I][1] -= ph;
+            else m[I * (I + 1) / 2 + I][0] -= ph;
+        }
+    }
+
+    // ---- blocked Cholesky (isposdef + cholesky!, gls_likelihood.jl:211-217) with z = L^-1 u riding along (ldiv!, :220).
+    // A pivot that is not positive and finite turns into NaN under rsqrt and poisons everything after it, ln L included:
+    // no test inside the dependent chain (combine_prior maps NaN to -Inf).
+    int lex = 0;
+    double lman = 1.0, zz = 0.0;
+    const int i8 = lane & 7;
+    const int src0 = 4 * (2 * (i8 & 3) + (i8 >> 2));   // lanes holding row i8 of a block: 4 pi^-1(i8) + (column & 3)
+#pragma unroll 1
+    for (int k = 0; k < NBK; ++k) {
+        double d0, d1;
+        switch (k) {   // the diagonal block's registers (every case a compile-time index)
+            case 0: d0 = m[0][0]; d1 = m[0][1]; break;
+            case 1: d0 = m[NBK > 1 ? 2 : 0][0]; d1 = m[NBK > 1 ? 2 : 0][1]; break;
+            case 2: d0 = m[NBK > 2 ? 5 : 0][0]; d1 = m[NBK > 2 ? 5 : 0][1]; break;
+            case 3: d0 = m[NBK > 3 ? 9 : 0][0]; d1 = m[NBK > 3 ? 9 : 0][1]; break;
+            case 4: d0 = m[NBK > 4 ? 14 : 0][0]; d1 = m[NBK > 4 ? 14 : 0][1]; break;
+            case 5: d0 = m[NBK > 5 ? 20 : 0][0]; d1 = m[NBK > 5 ? 20 : 0][1]; break;
+            case 6: d0 = m[NBK > 6 ? 27 : 0][0]; d1 = m[NBK > 6 ? 27 : 0][1]; break;
+            default: d0 = m[NBK > 7 ? 35 : 0][0]; d1 = m[NBK > 7 ? 35 : 0][1]; break;
+        }
+        {   // (1) diagonal block: gather rows (lane & 7 = row, four replicas), factorise in registers
+            double row[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) row[c] = -__shfl_sync(kFull, c < 4 ? d0 : d1, src0 + (c & 3));
+            double prod = 1.0, myrd = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double d = __shfl_sync(kFull, row[c], c);      // pivot, held by the lanes of row c
+                prod *= d;
+                const double rd = rsqrt(d);
+                // No predicates: the lanes of rows above c scale / update entries of the block's upper triangle, which
+                // nobody reads (pivots and multipliers come from the lower triangle of the lanes that own them), and for
+                // the pivot's own lane row[c] == d, so row[c] * rd is d * rd = L[c][c].
+                row[c] *= rd;
+                myrd = (i8 == c) ? rd : myrd;      // the reciprocal pivot of this lane's own row: stored on the diagonal below
+#pragma unroll
+                for (int q = c + 1; q < 8; ++q) {
+                    const double lqc = __shfl_sync(kFull, row[c], q);   // L[q][c]
+                    row[q] = fma(-row[c], lqc, row[q]);
+                }
+            }
+            int ex;                                                  // 8 pivots of ~1e14 at most: no overflow
+            lman *= split_mantissa(prod, &ex);
+            lex += ex;
+            if (lane < 8) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) sL[lane * 8 + c] = (c == lane) ? myrd : row[c];   // diagonal: 1 / L[c][c], all the inverse needs
+            }
+        }
+        __syncwarp();
+        {   // (2) W = L_kk^-1, lane & 7 = column: w[rr] = (delta - sum_q L[rr][q] w[q]) / L[rr][rr]
+            double w[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                double acc = (rr == i8) ? 1.0 : 0.0;
+#pragma unroll
+                for (int q = 0; q < rr; ++q) acc = fma(-sL[rr * 8 + q], w[q], acc);
+                w[rr] = acc * sL[rr * 9];
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) sW[rr * 8 + lane] = w[rr];
+            }
+        }
+        __syncwarp();
+        const double wf0 = sW[cd_pi(r) * 8 + t], wf1 = sW[cd_pi(r) * 8 + 4 + t];   // W^T as the B operand, columns permuted
+        __syncwarp();
+        switch (k) {   // (3) + (4) panel products and trailing update of this step
+            case 0: cd_step<NBK, 0>(m, wf0, wf1, zz); break;
+            case 1: cd_step<NBK, (NBK > 1 ? 1 : 0)>(m, wf0, wf1, zz); break;
+            case 2: cd_step<NBK, (NBK > 2 ? 2 : 0)>(m, wf0, wf1, zz); break;
+            case 3: cd_step<NBK, (NBK > 3 ? 3 : 0)>(m, wf0, wf1, zz); break;
+            case 4: cd_step<NBK, (NBK > 4 ? 4 : 0)>(m, wf0, wf1, zz); break;
+            case 5: cd_step<NBK, (NBK > 5 ? 5 : 0)>(m, wf0, wf1, zz); break;
+            case 6: cd_step<NBK, (NBK > 6 ? 6 : 0)>(m, wf0, wf1, zz); break;
+            default: cd_step<NBK, (NBK > 7 ? 7 : 0)>(m, wf0, wf1, zz); break;
+        }
+    }
+    const double logdetSig = log(lman) + lex * 0.6931471805599453;     // sum log(pivot) = 2 sum log L_cc
+    // y^T N^-1 y and log det N: partial rows of the chain tiles (and ECORR blocks)
+    double py = 0.0, pl = 0.0;
+    for (int tt = lane; tt < a.n_tiles; tt += 32) {
+        const double2 v = *reinterpret_cast<const double2*>(a.partial + ((size_t)tt * a.B + b) * 2);
+        py += v.x;
+        pl += v.y;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        py += __shfl_xor_sync(kFull, py, off);
+        pl += __shfl_xor_sync(kFull, pl, off);
+        zz += __shfl_xor_sync(kFull, zz, off);
+    }
+    if (lane == 0) {
+        const double lnl = -0.5 * (py - zz + pl + logdetPhi + logdetSig);   // NaN (failed factorisation) -> -Inf below
+        a.out[b] = combine_prior(lnl, a.lnprior, b, a.with_prior);
+    }
+}
+template __global__ void chol_dmma_kernel<2>(CholArgs);
+template __global__ void chol_dmma_kernel<4>(CholArgs);
+template __global__ void chol_dmma_kernel<6>(CholArgs);
+template __global__ void chol_dmma_kernel<8>(CholArgs);
+
 // Phi^-1 only (vela_b200_noise_weights_inv): one block, walker 0
 __global__ void phiinv_kernel(CholArgs a, double* __restrict__ out) {
     const double* P = a.Pext;

@@ -170,6 +170,7 @@ struct CholArgs {
     int add_sig;               // add Sig[t] (ECORR correction) to the assembled entry
     const unsigned* ctab;      // compact pair table: one 4-byte recipe per packed pair (codes as in ltab), null = use `table`
     const unsigned* ltab;      // chol_warp_kernel: layout table (one code per shared-memory slot), null = not available
+    const unsigned* ftab;      // chol_dmma_kernel: fragment table (one code per block register and lane), null = not available
     double* ahat;              // optional [B][p]: conditional mean of the marginalised amplitudes, Sigma u
     double* cf;                // optional [B][p][p] row-major upper Cholesky factor of Sigma^-1 (L^T)
 };
@@ -218,6 +219,13 @@ inline size_t chol_warp_smem_bytes(int p, int n_ru) {
 // (0 none, 1 +0.5, 2 -0.5), [31:29] kind (0 zero, 1 c1 R[i1] + c2 R[i2], 2 copy R[i1])
 constexpr int kCholWarpMaxCols = 8191;
 __global__ void chol_warp_kernel(CholArgs a);
+// K4d (vela_kernels.cu): tensor-core Cholesky finish, one warp per walker, ranks up to kCholDmmaMaxRank
+constexpr int kCholDmmaMaxRank = 64;
+__host__ __device__ constexpr int cd_pi(int n) { return 4 * (n & 1) + (n >> 1); }   // row / column permutation of its block layout
+template <int NBK>
+__global__ void chol_dmma_kernel(CholArgs a);
+inline int chol_dmma_nbk(int p) { const int n = ((p + 7) / 8 + 1) & ~1; return n < 2 ? 2 : n; }   // block rows: 2, 4, 6 or 8
+inline size_t chol_dmma_smem_bytes(int nbk, int n_ru) { return (size_t)(64 + 72 + 8 * nbk + 2 * n_ru + 2) * sizeof(double); }
 __global__ void slab_reduce_kernel(double* R, long stride, int n_slabs, long n);
 __global__ void phiinv_kernel(CholArgs a, double* out);
 __global__ void div3_check_kernel(unsigned long long seed, long n, unsigned long long* mismatches);
