@@ -525,7 +525,9 @@ def main():
         fp64_note = "FP64 pipe, scalar DFMA issue (shares the datapath of the FP64 tensor path on B200); peak = measured DFMA loop"
         chain_name = "toa_chain_kernel (per-model NVRTC build)" if psr.chain_specialized() else "toa_chain_kernel (generic)"
         sigma_name = "colsum_kernel (structured Sigma, FP64 DMMA m8n8k4)" if structured else "sigma_contract_kernel (FP64 DMMA m8n8k4)"
-        chol_name = "chol_warp_kernel" if p + 1 <= 64 and os.environ.get("VELA_B200_CHOL_WARP", "0") == "1" else "chol_finish_kernel"
+        chol_name = ("chol_warp_kernel" if p + 1 <= 64 and os.environ.get("VELA_B200_CHOL_WARP", "0") == "1" else
+                     "chol_dmma_kernel" if structured and p <= 64 and os.environ.get("VELA_B200_CHOL_DMMA", "1") != "0" else
+                     "chol_finish_kernel")
         kernels = [
             {"kernel": chain_name, "ncu_name": "vela_chain_spec",
              "bound": "tensor", "bound_detail": fp64_note, "ms": chain_ms, "algorithmic_flops_per_launch": 330.0 * ntoa * B,

@@ -39,10 +39,18 @@ for r in rows[2:]:
     fp64 = float(d.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", 0) or 0)
     tens = float(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0) or 0)
     dur = float(d["gpu__time_duration.sum"]) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")], 1.0)
-    kernels[short] = {"dram_bytes": rd + wr, "pipe_active": max(fp64, tens) / 100.0, "pipe": "tensor (DMMA)" if tens > fp64 else "fp64",
-                      "ncu_duration_ms": dur, "warps_active_pct": float(d.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0) or 0),
-                      "issue_active_pct": float(d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0) or 0),
-                      "inst_executed": float(d.get("smsp__inst_executed.sum", 0) or 0)}
+    ent = {"dram_bytes": rd + wr, "pipe_active": max(fp64, tens) / 100.0, "pipe": "tensor (DMMA)" if tens > fp64 else "fp64",
+           "ncu_duration_ms": dur, "warps_active_pct": float(d.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0) or 0),
+           "issue_active_pct": float(d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0) or 0),
+           "inst_executed": float(d.get("smsp__inst_executed.sum", 0) or 0), "launches": 1}
+    if short in kernels:   # several launches of one kernel in the step (the two stages of the column sums): bytes, time and
+        old = kernels[short]   # instructions add up, the percentages are duration-weighted
+        tot = old["ncu_duration_ms"] + dur
+        for k in ("pipe_active", "warps_active_pct", "issue_active_pct"):
+            ent[k] = (old[k] * old["ncu_duration_ms"] + ent[k] * dur) / tot
+        for k in ("dram_bytes", "ncu_duration_ms", "inst_executed", "launches"):
+            ent[k] += old[k]
+    kernels[short] = ent
 open(txt_out, "w").write("\n".join(out) + "\n")
 if json_out:
     json.dump({"source": txt_out, "command": "ncu --profile-from-start off --set full --import-source on --clock-control none "
