@@ -340,21 +340,25 @@ def main():
     stage_ms = c3.stage_ms(args.steps)
     finite_frac = float(torch.isfinite(c3.d_out).double().mean().item())
 
-    # ---- end-to-end timing through the public host API (`e2e`): host numpy in, host numpy out; with several ranks the
-    #      per-rank result is staged back from pinned memory for the NCCL gather and the gathered vector read back
-    pin_out = torch.empty(B, dtype=torch.float64).pin_memory() if world > 1 else None
+    # ---- end-to-end timing (`e2e`).  One GPU: the public host call, host numpy in, host numpy out (pinned staging + H2D +
+    #      device priors + kernels + D2H inside the call).  Several ranks: every step copies this rank's walkers from PINNED
+    #      host memory to the device, runs the public device entry point (priors evaluated on the device), gathers the
+    #      per-rank results over NCCL from the device buffer and reads the gathered vector back to pinned host memory -
+    #      the result never bounces through the host before the collective.
+    pin_in = [torch.from_numpy(w).pin_memory() for w in c3.host_sets] if world > 1 else None
+    d_in = torch.empty((B, nd), dtype=torch.float64, device="cuda") if world > 1 else None
     pin_all = torch.empty(B * world, dtype=torch.float64).pin_memory() if world > 1 else None
 
     def step_e2e(case, i, n=None):
         n = n or case.B
-        out = case.psr.lnpost_vectorized(case.host_sets[i % n_sets][:n])   # pinned staging + H2D + device priors + kernels + D2H
-        if world > 1:
-            pin_out[:n].copy_(torch.from_numpy(out))
-            case.d_out[:n].copy_(pin_out[:n], non_blocking=True)
-            dist.all_gather_into_tensor(case.gathered[: n * world], case.d_out[:n])
-            pin_all[: n * world].copy_(case.gathered[: n * world], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return out
+        if world == 1:
+            return case.psr.lnpost_vectorized(case.host_sets[i % n_sets][:n])
+        d_in[:n].copy_(pin_in[i % n_sets][:n], non_blocking=True)
+        case.psr.lnpost_device(d_in.data_ptr(), n, 0, case.d_out.data_ptr(), stream)
+        dist.all_gather_into_tensor(case.gathered[: n * world], case.d_out[:n])
+        pin_all[: n * world].copy_(case.gathered[: n * world], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pin_all
 
     def time_e2e(case, steps, warmup, n=None):
         for i in range(warmup):
@@ -575,7 +579,10 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": headline_config(world, ntoa, p, nd, B),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (nd + (0 if psr.device_priors else 1)) * 8 * world),
-                    "d2h_bytes_per_step": int(B * 8 * world), "ms_per_step": e2e_ms / args.steps},
+                    # one rank reads its B results; with several ranks every rank reads the gathered B x world vector
+                    "d2h_bytes_per_step": int(B * 8 * (world * world if world > 1 else 1)), "ms_per_step": e2e_ms / args.steps,
+                    "path": "Pulsar.lnpost_vectorized (host numpy in / out)" if world == 1 else
+                            "pinned H2D -> Pulsar.lnpost_device (device priors) -> NCCL all_gather -> pinned D2H of the gathered vector"},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary(),
             "finite_fraction": finite_frac,
             "flops_per_eval": flops_eval,

@@ -23,6 +23,9 @@ import oracle as O  # noqa: E402
 
 REF = "/root/reference/test/datafiles"
 FIXTURES = ["NGC6440E", "sim_sw.wb", "sim3.gp", "sim_dmgp_wb", "sim2"]
+# walkers per fixture: BASELINE.json configs[0] names a batch of 1024 samples for NGC6440E; the others keep 64 (their
+# oracle evaluations are the slow part of the CPU suite)
+N_WALKERS = {"NGC6440E": 1024}
 
 
 def walkers(model, n, seed):
@@ -49,7 +52,7 @@ def main():
         md = vb.ModelDescriptor(model, toas)
         x0 = model.read_param_values_to_vector()
         y, w = O.residuals(md, x0)
-        W = walkers(model, 64, seed=20260101)
+        W = walkers(model, N_WALKERS.get(name, 64), seed=20260101)
         extra = {
             "source": f"test/datafiles/{name}.jlso",
             "lnlike_default": O.lnlike(md, x0),

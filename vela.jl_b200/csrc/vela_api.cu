@@ -435,8 +435,25 @@ int launch_two_stage(VelaPulsar* h, DeviceModel& d, long B, cudaStream_t st, Col
     ca.W = b.W; ca.Y = b.Y; ca.ld_yw = h->n_rows_pad; ca.B = B; ca.R = b.mu; ca.ld_r = sp.k2_pad;
     ca.kt_per_split = sp.cp / 16; ca.split_stride_r = 0; ca.plane_stride = plane; ca.n_valid = 0;
     {
-        dim3 grid((unsigned)sp.n_blocks, (unsigned)((B + 511) / 512), (unsigned)sp.n_cells);
-        colsum_kernel<16, 2, 1, 16, true><<<grid, 512, colsum_smem_bytes(16, 2, 1, 16, true), st>>>(ca);
+        // CTA shape, measured on B200 (stage 1 + stage 2, ms; config 3 / config 5 at 8192 walkers): 512 walkers x 2 stages
+        // of 16 rows 0.544 / 17.43; 512 x 4 stages of 8 rows 0.523 / 18.16; 256 walkers x 2 stages, TWO CTAs per SM
+        // 0.488 / 15.35 (default: the second CTA computes while the first waits for its tile); 256 x 4 stages 0.519 / 15.78
+        int shape = 2;
+        if (const char* e = getenv("VELA_B200_STAGE1_SHAPE")) shape = std::max(0, std::min(3, atoi(e)));
+        if (shape == 1) {
+            ca.kt_per_split = sp.cp / 8;
+            dim3 grid((unsigned)sp.n_blocks, (unsigned)((B + 511) / 512), (unsigned)sp.n_cells);
+            colsum_kernel<8, 4, 1, 16, true><<<grid, 512, colsum_smem_bytes(8, 4, 1, 16, true), st>>>(ca);
+        } else if (shape == 2) {
+            dim3 grid((unsigned)sp.n_blocks, (unsigned)((B + 255) / 256), (unsigned)sp.n_cells);
+            colsum_kernel<16, 2, 1, 8, true><<<grid, 256, colsum_smem_bytes(16, 2, 1, 8, true), st>>>(ca);
+        } else if (shape == 3) {
+            dim3 grid((unsigned)sp.n_blocks, (unsigned)((B + 255) / 256), (unsigned)sp.n_cells);
+            colsum_kernel<16, 4, 1, 8, true><<<grid, 256, colsum_smem_bytes(16, 4, 1, 8, true), st>>>(ca);
+        } else {
+            dim3 grid((unsigned)sp.n_blocks, (unsigned)((B + 511) / 512), (unsigned)sp.n_cells);
+            colsum_kernel<16, 2, 1, 16, true><<<grid, 512, colsum_smem_bytes(16, 2, 1, 16, true), st>>>(ca);
+        }
     }
     // ---- stage 2: every job is a dense [n_out x k2_pad] x [k2_pad x B] product on its block's moments.  All jobs go in
     // ONE launch: blockIdx.x walks the table of 64-column CTA columns built at create() (d.units2), so the grid is
@@ -551,6 +568,9 @@ int set_smem_attrs(int dev) {
     for (const ColsumShape& sh : kColsumSplitShapes)
         CU(cudaFuncSetAttribute(sh.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     CU(cudaFuncSetAttribute(colsum_kernel<16, 2, 1, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(colsum_kernel<8, 4, 1, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(colsum_kernel<16, 2, 1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CU(cudaFuncSetAttribute(colsum_kernel<16, 4, 1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     for (auto k : {chol_finish_kernel<8, true>, chol_finish_kernel<16, true>, chol_finish_kernel<16, false>})
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
     // shared-memory matrices: many small walker CTAs per SM, so ask for the largest shared carve-out; the global-scratch

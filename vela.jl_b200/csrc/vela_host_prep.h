@@ -23,6 +23,12 @@ inline void fill_toa_columns(const double* rec, int wideband, double* cols, long
     put(C_R2, R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
     put(C_DM, wideband ? rec[31] : 0.0);
     put(C_DMERR2, wideband ? rec[32] * rec[32] : 0.0);
+    {   // fast build: chromatic powers and FD logarithms start from ln(frequency), kept to ~1e-19 in two words
+        const long double lf = logl((long double)rec[3]);
+        const double hi = (double)lf;
+        put(C_LOG_FREQ, hi);
+        put(C_LOG_FREQ + 1, std::isfinite(hi) ? (double)(lf - (long double)hi) : 0.0);
+    }
     for (int b = 0; b < 5; ++b) {
         const double* r = rec + 15 + 3 * b;
         for (int i = 0; i < 3; ++i) put(C_PLANET + 3 * b + i, r[i]);

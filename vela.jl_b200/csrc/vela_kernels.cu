@@ -660,7 +660,7 @@ VELA_SIGMA_INST(8, 2, 3, 4, 16)
 // homogeneous - either 32 UC table columns against W or 32 UC columns of M against w.y - so a stage holds one walker
 // operand instead of two and the two kinds of units pad separately.
 template <int BK, int STAGES, int UC, int WC, bool SPLIT>
-__global__ void __launch_bounds__(UC * WC * 32, 1) colsum_kernel(ColsumArgs a) {
+__global__ void __launch_bounds__(UC * WC * 32, (UC * WC <= 8) ? 2 : 1) colsum_kernel(ColsumArgs a) {
     constexpr int WARPS = UC * WC, kThreads = WARPS * 32, MT = 4, NT = 4;
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
@@ -796,6 +796,9 @@ template __global__ void colsum_kernel<16, 4, 4, 4, true>(ColsumArgs);
 template __global__ void colsum_kernel<16, 4, 2, 8, true>(ColsumArgs);
 template __global__ void colsum_kernel<32, 2, 2, 8, true>(ColsumArgs);
 template __global__ void colsum_kernel<16, 2, 1, 16, true>(ColsumArgs);   // one column unit x 512 walkers: stage 1 of the two-stage sums
+template __global__ void colsum_kernel<8, 4, 1, 16, true>(ColsumArgs);    // stage-1 variants (VELA_B200_STAGE1_SHAPE): deeper ring of 8-row tiles,
+template __global__ void colsum_kernel<16, 2, 1, 8, true>(ColsumArgs);    // 256-walker CTAs, two resident per SM,
+template __global__ void colsum_kernel<16, 4, 1, 8, true>(ColsumArgs);    // 256-walker CTAs with a four-stage ring
 
 // ------------------------------------------------------------------------------------------
 // K4  + Phi^-1, Cholesky, log-det, solve, ln L
