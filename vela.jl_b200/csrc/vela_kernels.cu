@@ -1227,18 +1227,31 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
             for (int i = tid; i < a.n_r; i += nt) sR[i] = slab_sum(gR + i, a.split_stride_r, a.ksplit);
             __syncthreads();
         }
+        if (a.ctab) {
+            // 4-byte recipe per pair (same code as the layout table), row by row: warp = row, lanes along the row, so the
+            // recipe loads and the stores are coalesced and no thread tracks (row, column) through the packed order (the
+            // pair-ordered loop below spent 62 thread-instructions per pair on that bookkeeping: 20 % of the kernel)
+            for (int r = warp; r < p; r += nwarps) {
+                const size_t t0 = (size_t)r * (r + 1) / 2;
+                const unsigned* ct = a.ctab + t0;
+                double* dst = A + (size_t)r * lda;
+#pragma unroll 4
+                for (int c = lane; c <= r; c += 32) {
+                    const unsigned e = __ldg(ct + c);
+                    double v = ((e >> 26) & 1 ? 1.0 : 0.5) * sR[e & 0x1fff];
+                    const unsigned c2 = (e >> 27) & 3;
+                    if (c2) v = fma(c2 == 1 ? 0.5 : -0.5, sR[(e >> 13) & 0x1fff], v);
+                    if (a.add_sig) v += gA[t0 + c];
+                    dst[c] = v;
+                }
+            }
+        } else {
         int r = 0, c = tid;
         while (c > r) { c -= r + 1; ++r; }
 #pragma unroll 4
         for (long t = tid; t < n_pairs; t += nt) {
             double v;
-            if (a.ctab) {                                  // 4-byte recipe per pair (same code as the layout table)
-                const unsigned e = __ldg(a.ctab + t);
-                v = ((e >> 26) & 1 ? 1.0 : 0.5) * sR[e & 0x1fff];
-                const unsigned c2 = (e >> 27) & 3;
-                if (c2) v = fma(c2 == 1 ? 0.5 : -0.5, sR[(e >> 13) & 0x1fff], v);
-                if (a.add_sig) v += gA[t];
-            } else if (a.table) {
+            if (a.table) {
                 const PairTerm pt = a.table[t];
                 v = pt.c1 * sR[pt.i1];
                 if (pt.c2 != 0.0) v = fma(pt.c2, sR[pt.i2], v);
@@ -1249,6 +1262,7 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
             A[(size_t)r * lda + c] = v;
             c += nt;
             while (c > r) { c -= r + 1; ++r; }
+        }
         }
         const double* gU = a.table ? a.R + a.u_off : a.U;
         const long ldu = a.table ? a.ld_r : a.ld_u, su = a.table ? a.split_stride_r : a.split_stride_u;
@@ -1290,11 +1304,16 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
         const int m = n1 - k0;                             // panel rows: global rows k0 .. p
         // 1. panel -> shared (zero-padded to 32 columns and to `mpad` rows)
         const int mpad = min(prow, ((m + 31) & ~31) + 32);
-        for (int e = tid; e < mpad * kPanelW; e += nt) {
-            const int i = e >> 5, c = e & 31;
-            double v = 0.0;
-            if (i < m && c < nb && k0 + c <= k0 + i) v = A[(size_t)(k0 + i) * lda + k0 + c];
-            P[i * kPanelPitch + c] = v;
+        // (two columns per thread: 16-byte loads and stores, four rows in flight; lda and k0 are even, so the pairs are aligned)
+#pragma unroll 4
+        for (int e = tid; e < mpad * (kPanelW / 2); e += nt) {
+            const int i = e >> 4, c = (e & 15) * 2;
+            double2 v = make_double2(0.0, 0.0);
+            if (i < m && c < nb && c <= i) {
+                v = *reinterpret_cast<const double2*>(A + (size_t)(k0 + i) * lda + k0 + c);
+                if (c + 1 >= nb || c + 1 > i) v.y = 0.0;
+            }
+            *reinterpret_cast<double2*>(P + i * kPanelPitch + c) = v;
         }
         __syncthreads();
         // 2. factorise the panel, 8 columns at a time
@@ -1352,9 +1371,15 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
             __syncthreads();
         }
         // 3. the finished columns back to global; log L_cc of the pivots
-        for (int e = tid; e < m * kPanelW; e += nt) {
-            const int i = e >> 5, c = e & 31;
-            if (c < nb && c <= i) A[(size_t)(k0 + i) * lda + k0 + c] = P[i * kPanelPitch + c];
+#pragma unroll 4
+        for (int e = tid; e < m * (kPanelW / 2); e += nt) {
+            const int i = e >> 4, c = (e & 15) * 2;
+            if (c < nb && c <= i) {
+                const double2 v = *reinterpret_cast<const double2*>(P + i * kPanelPitch + c);
+                double* dst = A + (size_t)(k0 + i) * lda + k0 + c;
+                if (c + 1 < nb && c + 1 <= i) *reinterpret_cast<double2*>(dst) = v;
+                else dst[0] = v.x;
+            }
         }
         for (int c = tid; c < nb; c += nt) ldsum += log(P[c * kPanelPitch + c]);
         // 4. trailing update on DMMA: rows / columns k1 .. p, 32 x 32 tiles of the lower triangle, one warp each
