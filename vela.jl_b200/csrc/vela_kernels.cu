@@ -1201,6 +1201,24 @@ __device__ __forceinline__ void factor_panel_diag(double* P, int c0, int nbb, do
     }
 }
 
+// W = L_kk^-1 of the block factor_panel_diag left in dblk (pitch 9; rdiag = reciprocal pivots), by the same warp: lane & 7
+// = column, forward substitution down the rows; identity padding inverts to itself.  sW is row-major [8][8].
+__device__ __forceinline__ void invert_panel_diag(const double* dblk, const double* rdiag, double* sW) {
+    const int col = threadIdx.x & 7;
+    double w[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+        double acc = (rr == col) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < rr; ++q) acc = fma(-dblk[rr * 9 + q], w[q], acc);
+        w[rr] = acc * rdiag[rr];
+    }
+    if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) sW[rr * 8 + col] = w[rr];
+    }
+}
+
 __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double scratch[kPanelThreads / 32];
@@ -1213,7 +1231,8 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
     double* phi = smem;                                    // [pp]
     double* dblk = phi + pp;                               // [8][9]
     double* rdiag = dblk + 72;                             // [8]
-    double* P = rdiag + 8;                                 // [prow][kPanelPitch]; the column sums / u alias it during assembly
+    double* sW = rdiag + 8;                                // [8][8] inverse of the current diagonal factor
+    double* P = sW + 64;                                   // [prow][kPanelPitch]; the column sums / u alias it during assembly
     double* sR = P;
     double* A = a.Sq + (size_t)b * n1 * lda;
     if (tid == 0) sFail = 0;
@@ -1319,25 +1338,27 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
         // 2. factorise the panel, 8 columns at a time
         for (int c0 = 0; c0 < nb; c0 += 8) {
             const int nbb = min(8, nb - c0);
-            if (warp == 0) factor_panel_diag(P, c0, nbb, dblk, rdiag, &sFail);
-            __syncthreads();
-            for (int i = c0 + nbb + tid; i < m; i += nt) {           // rows below the diagonal block: x L_kk^T = row
-                double x[8];
-                double* row = P + i * kPanelPitch + c0;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) x[c] = c < nbb ? row[c] : 0.0;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c < nbb) {
-                        double v = x[c];
-#pragma unroll
-                        for (int q = 0; q < c; ++q) v = fma(-x[q], dblk[c * 9 + q], v);
-                        x[c] = v * rdiag[c];
-                    }
+            if (c0 == 0) {   // later blocks of the panel were factorised by the look-ahead below
+                if (warp == 0) {
+                    factor_panel_diag(P, c0, nbb, dblk, rdiag, &sFail);
+                    __syncwarp();
+                    invert_panel_diag(dblk, rdiag, sW);
                 }
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (c < nbb) row[c] = x[c];
+                __syncthreads();
+            }
+            // rows below the diagonal block: X = R L_kk^-T as a product with W = L_kk^-1 on DMMA (two per 8-row tile; the
+            // thread-per-row substitution this replaces was a 36-deep dependent FMA chain fed by 4-way conflicting loads:
+            // 18 % of the kernel).  Identity padding of a short last block leaves the zero columns zero.
+            {
+                const double wf0 = sW[gid * 8 + tig], wf1 = sW[gid * 8 + 4 + tig];   // B[k][n] = W[n][k]
+                for (int r0 = c0 + nbb + warp * 8; r0 < m; r0 += nwarps * 8) {
+                    double* row = P + (r0 + gid) * kPanelPitch + c0;
+                    double x0 = 0.0, x1 = 0.0;
+                    dmma8x8x4(x0, x1, row[tig], wf0);
+                    dmma8x8x4(x0, x1, row[4 + tig], wf1);
+                    __syncwarp();                                      // every lane has read the tile before it is overwritten
+                    *reinterpret_cast<double2*>(row + 2 * tig) = make_double2(x0, x1);
+                }
             }
             __syncthreads();
             // rank-8 update of the panel's remaining columns (c0+8 .. 31) on DMMA: C[i][c2] -= sum_c P[i][c0+c] P[c2][c0+c]
@@ -1365,6 +1386,15 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
                             dmma8x8x4(cv.x, cv.y, fa1, fb[j][1]);
                             *reinterpret_cast<double2*>(crow + j * 8) = cv;
                         }
+                    }
+                    // look-ahead: warp 0's first tile holds the next diagonal block, now up to date; it factorises and
+                    // inverts it while the other warps apply the rest of the update (dblk / rdiag / sW were last read
+                    // before the barrier above), so a block step has two block barriers instead of three
+                    if (warp == 0 && r0 == c0 + 8) {
+                        __syncwarp();
+                        factor_panel_diag(P, c0 + 8, min(8, nb - c0 - 8), dblk, rdiag, &sFail);
+                        __syncwarp();
+                        invert_panel_diag(dblk, rdiag, sW);
                     }
                 }
             }

@@ -201,7 +201,7 @@ constexpr int kPanelThreadsHost = 256;   // = kPanelThreads in vela_kernels.cu
 inline size_t chol_panel_smem_bytes(int p, int pp, int n_ru) {
     const int n1 = p + 1, prow = ((n1 + 31) & ~31) + 32;
     const size_t panel = (size_t)prow * 36;                // kPanelPitch
-    return ((size_t)pp + 72 + 8 + (panel > (size_t)n_ru ? panel : (size_t)n_ru)) * sizeof(double);
+    return ((size_t)pp + 72 + 8 + 64 + (panel > (size_t)n_ru ? panel : (size_t)n_ru)) * sizeof(double);
 }
 inline size_t chol_panel_scratch_doubles(int p, int pp) { return (size_t)(p + 1) * (pp + 2); }   // per walker
 
