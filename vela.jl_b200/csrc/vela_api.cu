@@ -1017,16 +1017,22 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
         if (const char* e = getenv("VELA_B200_CHOL_SMEM")) { if (atoi(e) == 0) h->chol_smem = false; }   // tests: force the global-scratch kernels
         if (!h->chol_smem) h->chol_nb = 16;   // the global-scratch variant exists for block width 16 only
         h->chol_smem_bytes = h->chol_smem ? need : chol_smem_doubles(h->p, h->pp, h->chol_nb, false, n_r) * sizeof(double);
-        // structured path: the pair table again as 4-byte codes (13-bit column indices, coefficients 1 | 1/2 and 0 | +-1/2),
-        // 1/6 of the bytes the finishing kernel pulls through L2 per walker (rank 300: 45 150 pairs)
-        if (h->sp.active && h->sp.n_cols <= kCholWarpMaxCols) {
+        // structured path, large ranks (chol_panel_kernel): the pair table again as 4 bytes per pair - two 16-bit indices
+        // (i1 | i2 << 16) into the walker's pre-scaled sums S = {+R/2 | -R/2 | 0}: the entry is S[i1] + S[i2] (R1 = R1/2 +
+        // R1/2, R1/2 = R1/2 + 0, (R1 +- R2)/2), bit for bit the value c1 R1 + c2 R2 of the 24-byte table, for 1/6 of the
+        // bytes the finishing kernel pulls through L2 per walker (rank 300: 45 150 pairs) and one add per entry
+        if (h->sp.active && 2 * (long)h->sp.n_r + 1 <= 65535) {
+            const unsigned n_r = (unsigned)h->sp.n_r, zero = 2 * n_r;
             h->ctab.resize(h->sp.table.size());
             for (size_t t = 0; t < h->sp.table.size(); ++t) {
                 const PairTerm& pt = h->sp.table[t];
-                const bool c1_one = pt.c1 == 1.0, c1_half = pt.c1 == 0.5;
-                const int c2 = pt.c2 == 0.0 ? 0 : (pt.c2 == 0.5 ? 1 : (pt.c2 == -0.5 ? 2 : -1));
-                if (!(c1_one || c1_half) || c2 < 0) { h->ctab.clear(); break; }
-                h->ctab[t] = (1u << 29) | ((unsigned)c2 << 27) | ((c1_one ? 1u : 0u) << 26) | ((unsigned)(c2 ? pt.i2 : 0) << 13) | (unsigned)pt.i1;
+                unsigned i2;
+                if (pt.c1 == 1.0 && pt.c2 == 0.0) i2 = (unsigned)pt.i1;
+                else if (pt.c1 == 0.5 && pt.c2 == 0.0) i2 = zero;
+                else if (pt.c1 == 0.5 && pt.c2 == 0.5) i2 = (unsigned)pt.i2;
+                else if (pt.c1 == 0.5 && pt.c2 == -0.5) i2 = n_r + (unsigned)pt.i2;
+                else { h->ctab.clear(); break; }                    // a coefficient this form cannot carry
+                h->ctab[t] = (unsigned)pt.i1 | (i2 << 16);
             }
         }
         // ranks up to 63 on the structured path: layout table of the warp-per-walker Cholesky kernel - for every

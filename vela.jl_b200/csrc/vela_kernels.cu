@@ -1243,13 +1243,23 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
         const double* gA = a.Sig + (size_t)b * a.ld_sig;
         if (a.table) {
             const double* gR = a.R + (size_t)b * a.ld_r;
-            for (int i = tid; i < a.n_r; i += nt) sR[i] = slab_sum(gR + i, a.split_stride_r, a.ksplit);
+            if (a.ctab) {   // pre-scaled sums S = {+R/2 | -R/2 | 0} for the two-index codes
+                for (int i = tid; i < a.n_r; i += nt) {
+                    const double v = 0.5 * slab_sum(gR + i, a.split_stride_r, a.ksplit);
+                    sR[i] = v;
+                    sR[a.n_r + i] = -v;
+                }
+                if (tid == 0) sR[2 * a.n_r] = 0.0;
+            } else {
+                for (int i = tid; i < a.n_r; i += nt) sR[i] = slab_sum(gR + i, a.split_stride_r, a.ksplit);
+            }
             __syncthreads();
         }
         if (a.ctab) {
-            // 4-byte recipe per pair (same code as the layout table), row by row: warp = row, lanes along the row, so the
-            // recipe loads and the stores are coalesced and no thread tracks (row, column) through the packed order (the
-            // pair-ordered loop below spent 62 thread-instructions per pair on that bookkeeping: 20 % of the kernel)
+            // 4-byte recipe per pair (two 16-bit indices into S: entry = S[i1] + S[i2]), row by row: warp = row, lanes along
+            // the row, so the recipe loads and the stores are coalesced and no thread tracks (row, column) through the
+            // packed order (the pair-ordered loop below spent 62 thread-instructions per pair on bookkeeping and on
+            // decoding coefficient codes: 20 % of the kernel)
             for (int r = warp; r < p; r += nwarps) {
                 const size_t t0 = (size_t)r * (r + 1) / 2;
                 const unsigned* ct = a.ctab + t0;
@@ -1257,9 +1267,7 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
 #pragma unroll 4
                 for (int c = lane; c <= r; c += 32) {
                     const unsigned e = __ldg(ct + c);
-                    double v = ((e >> 26) & 1 ? 1.0 : 0.5) * sR[e & 0x1fff];
-                    const unsigned c2 = (e >> 27) & 3;
-                    if (c2) v = fma(c2 == 1 ? 0.5 : -0.5, sR[(e >> 13) & 0x1fff], v);
+                    double v = sR[e & 0xffffu] + sR[e >> 16];
                     if (a.add_sig) v += gA[t0 + c];
                     dst[c] = v;
                 }
@@ -1324,15 +1332,20 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
         // 1. panel -> shared (zero-padded to 32 columns and to `mpad` rows)
         const int mpad = min(prow, ((m + 31) & ~31) + 32);
         // (two columns per thread: 16-byte loads and stores, four rows in flight; lda and k0 are even, so the pairs are aligned)
+        {
+            const int c = (tid & 15) * 2;                  // this thread's column pair; rows tid / 16, + nt / 16, ...
+            const bool cin = c < nb, c1in = c + 1 < nb;
+            const double* src = A + (size_t)(k0 + (tid >> 4)) * lda + k0 + c;
+            double* dstp = P + (tid >> 4) * kPanelPitch + c;
 #pragma unroll 4
-        for (int e = tid; e < mpad * (kPanelW / 2); e += nt) {
-            const int i = e >> 4, c = (e & 15) * 2;
-            double2 v = make_double2(0.0, 0.0);
-            if (i < m && c < nb && c <= i) {
-                v = *reinterpret_cast<const double2*>(A + (size_t)(k0 + i) * lda + k0 + c);
-                if (c + 1 >= nb || c + 1 > i) v.y = 0.0;
+            for (int i = tid >> 4; i < mpad; i += nt >> 4, src += (size_t)(nt >> 4) * lda, dstp += (nt >> 4) * kPanelPitch) {
+                double2 v = make_double2(0.0, 0.0);
+                if (i < m && cin && c <= i) {
+                    v = *reinterpret_cast<const double2*>(src);
+                    if (!c1in || c + 1 > i) v.y = 0.0;
+                }
+                *reinterpret_cast<double2*>(dstp) = v;
             }
-            *reinterpret_cast<double2*>(P + i * kPanelPitch + c) = v;
         }
         __syncthreads();
         // 2. factorise the panel, 8 columns at a time
@@ -1401,14 +1414,18 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
             __syncthreads();
         }
         // 3. the finished columns back to global; log L_cc of the pivots
+        {
+            const int c = (tid & 15) * 2;
+            const bool cin = c < nb, c1in = c + 1 < nb;
+            double* dst = A + (size_t)(k0 + (tid >> 4)) * lda + k0 + c;
+            const double* srcp = P + (tid >> 4) * kPanelPitch + c;
 #pragma unroll 4
-        for (int e = tid; e < m * (kPanelW / 2); e += nt) {
-            const int i = e >> 4, c = (e & 15) * 2;
-            if (c < nb && c <= i) {
-                const double2 v = *reinterpret_cast<const double2*>(P + i * kPanelPitch + c);
-                double* dst = A + (size_t)(k0 + i) * lda + k0 + c;
-                if (c + 1 < nb && c + 1 <= i) *reinterpret_cast<double2*>(dst) = v;
-                else dst[0] = v.x;
+            for (int i = tid >> 4; i < m; i += nt >> 4, dst += (size_t)(nt >> 4) * lda, srcp += (nt >> 4) * kPanelPitch) {
+                if (cin && c <= i) {
+                    const double2 v = *reinterpret_cast<const double2*>(srcp);
+                    if (c1in && c + 1 <= i) *reinterpret_cast<double2*>(dst) = v;
+                    else dst[0] = v.x;
+                }
             }
         }
         for (int c = tid; c < nb; c += nt) ldsum += log(P[c * kPanelPitch + c]);
@@ -1423,6 +1440,19 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
             // the C tile is the accumulators' initial value (A enters negated): its global loads are in flight while the
             // fragments come from shared memory, and no second register tile is needed
             double acc[4][4][2];
+            // tiles strictly below the diagonal with all 32 rows inside the matrix (most of them) need no predicates
+            const bool interior = ti > tj && ti * 32 + 32 <= m2;
+            double* ctile = A + (size_t)(k1 + ti * 32 + gid) * lda + k1 + tj * 32 + 2 * tig;
+            if (interior) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double2 v = *reinterpret_cast<const double2*>(ctile + (size_t)(i * 8) * lda + j * 8);
+                        acc[i][j][0] = v.x;
+                        acc[i][j][1] = v.y;
+                    }
+            } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -1440,6 +1470,7 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
                         }
                     }
                 }
+            }
             const double* pa = P2 + (ti * 32 + gid) * kPanelPitch + tig;
             const double* pb = P2 + (tj * 32 + gid) * kPanelPitch + tig;
 #pragma unroll
@@ -1455,6 +1486,13 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
             }
+            if (interior) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<double2*>(ctile + (size_t)(i * 8) * lda + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+            } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -1466,6 +1504,7 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
                         else if (cc <= rr) dst[0] = acc[i][j][0];
                     }
                 }
+            }
         }
         __syncthreads();                                   // the panel buffer is reused; global updates are block-local
     }

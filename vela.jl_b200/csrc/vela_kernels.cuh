@@ -168,7 +168,7 @@ struct CholArgs {
     long split_stride_r;
     int n_r, u_off;
     int add_sig;               // add Sig[t] (ECORR correction) to the assembled entry
-    const unsigned* ctab;      // compact pair table: one 4-byte recipe per packed pair (codes as in ltab), null = use `table`
+    const unsigned* ctab;      // compact pair table (chol_panel_kernel): per packed pair i1 | i2 << 16 into S = {+R/2 | -R/2 | 0}, null = use `table`
     const unsigned* ltab;      // chol_warp_kernel: layout table (one code per shared-memory slot), null = not available
     const unsigned* ftab;      // chol_dmma_kernel: fragment table (one code per block register and lane), null = not available
     double* ahat;              // optional [B][p]: conditional mean of the marginalised amplitudes, Sigma u
@@ -201,7 +201,8 @@ constexpr int kPanelThreadsHost = 256;   // = kPanelThreads in vela_kernels.cu
 inline size_t chol_panel_smem_bytes(int p, int pp, int n_ru) {
     const int n1 = p + 1, prow = ((n1 + 31) & ~31) + 32;
     const size_t panel = (size_t)prow * 36;                // kPanelPitch
-    return ((size_t)pp + 72 + 8 + 64 + (panel > (size_t)n_ru ? panel : (size_t)n_ru)) * sizeof(double);
+    const size_t sums = 2 * (size_t)n_ru + 2;              // S = {+R/2 | -R/2 | 0} aliases the panel during assembly
+    return ((size_t)pp + 72 + 8 + 64 + (panel > sums ? panel : sums)) * sizeof(double);
 }
 inline size_t chol_panel_scratch_doubles(int p, int pp) { return (size_t)(p + 1) * (pp + 2); }   // per walker
 
