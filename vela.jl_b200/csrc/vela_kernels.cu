@@ -1219,20 +1219,96 @@ __device__ __forceinline__ void invert_panel_diag(const double* dblk, const doub
     }
 }
 
+// 1 / sqrt(d) from the hardware seed (rsqrt.approx.f64: ~22 bits) and one third-order step: e = 1 - d y^2,
+// y <- y + y e (1/2 + 3/8 e), good to ~1e-18 relative - four dependent FP64 operations where the library routine's
+// special-case scaffolding sits on the factorisation's critical path.  d <= 0, Inf or NaN gives NaN (0 . Inf, Inf . 0).
+__device__ __forceinline__ double rsqrt_fast(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-(d * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+// Cholesky of the panel's top block (nbt <= 32 rows / columns, lower triangle in Tb, pitch kPanelPitch, zero elsewhere) by
+// ONE warp, in registers: lane r owns row r (32 doubles, statically indexed after unrolling; lanes past nbt hold identity
+// rows).  Column by column: every lane publishes its (unscaled) entry u_r of column c in a shared column buffer, reads the
+// pivot d = u_c from it, and updates row[q] -= (u_r / d) u_q with the u_q as broadcast shared loads; L_rc = u_r / sqrt(d) is
+// formed off the critical path.  No shuffles (a shuffled double is two SHFLs plus, inside a function, a convergence
+// collective around each: the shuffle version ran 10 k instructions) and no predicates: entries of the upper triangle are
+// updated with junk that nobody reads.  A pivot that is not positive and finite turns into NaN under rsqrt and poisons the
+// walker's ln L (mapped to -Inf at the end), so there is no test in the dependent chain.  Then the four 8 x 8 diagonal
+// factors are inverted at once (lane = 8 block + column) into sW[block], and L goes back to Tb.  This runs while the other
+// warps do the trailing update, so its length decides how many of them end up waiting (the first version - 8 columns at
+// a time: diagonal block, inverse, solve and update on DMMA through shared memory - took 22 k cycles).
+// colbuf: 64 + 32 doubles (two column buffers, then the reciprocal pivots).  Returns this lane's log L_rr (0 past nbt).
+__device__ __noinline__ double factor_top_block(double* Tb, int nbt, double* colbuf, double* sW) {
+    const int lane = threadIdx.x & 31;
+    double* rdiag = colbuf + 64;
+    double row[32];
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(Tb + lane * kPanelPitch + c);
+        row[c] = v.x;
+        row[c + 1] = v.y;
+    }
+    if (lane >= nbt) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) row[c] = (c == lane) ? 1.0 : 0.0;
+    }
+    double myrd = 1.0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        double* cb = colbuf + (c & 1) * 32;        // two buffers: a fast lane's next column cannot overtake a slow lane's reads
+        cb[lane] = row[c];
+        __syncwarp();
+        const double d = cb[c];
+        const double t = row[c] * rcp_fast(d);
+        const double rd = rsqrt_fast(d);
+        row[c] *= rd;                              // lane c: d / sqrt(d) = L_cc; lanes below: L_rc
+        myrd = (lane == c) ? rd : myrd;
+#pragma unroll
+        for (int q = c + 1; q < 32; ++q) row[q] = fma(-t, cb[q], row[q]);
+    }
+    rdiag[lane] = myrd;
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+        // (lower triangle only: the junk above the diagonal must not reach the fragment reads of the solve)
+        const double2 v = make_double2(c <= lane ? row[c] : 0.0, c + 1 <= lane ? row[c + 1] : 0.0);
+        *reinterpret_cast<double2*>(Tb + lane * kPanelPitch + c) = v;
+    }
+    __syncwarp();
+    {   // W = L_bb^-1 for the four diagonal blocks at once: lane = 8 b + column, forward substitution down the rows
+        const int blk = lane >> 3, col = lane & 7;
+        const double* L = Tb + (blk * 8) * kPanelPitch + blk * 8;
+        double w[8];
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            double acc = (rr == col) ? 1.0 : 0.0;
+#pragma unroll
+            for (int q = 0; q < rr; ++q) acc = fma(-L[rr * kPanelPitch + q], w[q], acc);
+            w[rr] = acc * rdiag[blk * 8 + rr];
+        }
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) sW[blk * 64 + rr * 8 + col] = w[rr];
+    }
+    __syncwarp();
+    return lane < nbt ? log(Tb[lane * kPanelPitch + lane]) : 0.0;
+}
+
 __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double scratch[kPanelThreads / 32];
-    __shared__ int sFail;
+    __shared__ int sFail, sTile;
     const long b = blockIdx.x;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int p = a.p, pp = a.pp, n1 = p + 1;
     const int lda = pp + 2;                                // even pitch of the global matrix rows
-    const int prow = ((n1 + 31) & ~31) + 32;               // panel rows incl. zero padding for the last tiles
     double* phi = smem;                                    // [pp]
-    double* dblk = phi + pp;                               // [8][9]
-    double* rdiag = dblk + 72;                             // [8]
-    double* sW = rdiag + 8;                                // [8][8] inverse of the current diagonal factor
-    double* P = sW + 64;                                   // [prow][kPanelPitch]; the column sums / u alias it during assembly
+    double* dblk = phi + pp;                               // [96] factor_top_block: two column buffers, reciprocal pivots
+    double* rdiag = dblk + 96;                             // [8] (unused)
+    double* sW = rdiag + 8;                                // [4][8][8] inverses of the top block's diagonal factors
+    double* Tb = sW + 256;                                 // [32][kPanelPitch] the panel's top block (L_kk)
+    double* P = Tb + kPanelW * kPanelPitch;                // [prow][kPanelPitch] rows below it (L21); the column sums alias it during assembly
     double* sR = P;
     double* A = a.Sq + (size_t)b * n1 * lda;
     if (tid == 0) sFail = 0;
@@ -1326,114 +1402,103 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
     // ---- blocked factorisation
     const int gid = lane >> 2, tig = lane & 3;
     double ldsum = 0.0;                                    // sum of log L_cc over the columns this thread finalises
+    // top block of the first panel: nobody has anything else to do yet
+    if (warp == 0) {
+        const int nb0 = min(kPanelW, p);
+        for (int e = lane; e < kPanelW * (kPanelW / 2); e += 32) {
+            const int i = e >> 4, c = (e & 15) * 2;
+            double2 v = make_double2(0.0, 0.0);
+            if (i < nb0 && c <= i) {
+                v = *reinterpret_cast<const double2*>(A + (size_t)i * lda + c);
+                if (c + 1 > i) v.y = 0.0;
+            }
+            *reinterpret_cast<double2*>(Tb + i * kPanelPitch + c) = v;
+        }
+        __syncwarp();
+        ldsum += factor_top_block(Tb, nb0, dblk, sW);
+        for (int e = lane; e < nb0 * (kPanelW / 2); e += 32) {
+            const int i = e >> 4, c = (e & 15) * 2;
+            if (c <= i) {
+                const double2 v = *reinterpret_cast<const double2*>(Tb + i * kPanelPitch + c);
+                double* dst = A + (size_t)i * lda + c;
+                if (c + 1 <= i) *reinterpret_cast<double2*>(dst) = v;
+                else dst[0] = v.x;
+            }
+        }
+    }
     for (int k0 = 0; k0 < p; k0 += kPanelW) {
         const int nb = min(kPanelW, p - k0), k1 = k0 + nb;
-        const int m = n1 - k0;                             // panel rows: global rows k0 .. p
-        // 1. panel -> shared (zero-padded to 32 columns and to `mpad` rows)
-        const int mpad = min(prow, ((m + 31) & ~31) + 32);
-        // (two columns per thread: 16-byte loads and stores, four rows in flight; lda and k0 are even, so the pairs are aligned)
-        {
-            const int c = (tid & 15) * 2;                  // this thread's column pair; rows tid / 16, + nt / 16, ...
-            const bool cin = c < nb, c1in = c + 1 < nb;
-            const double* src = A + (size_t)(k0 + (tid >> 4)) * lda + k0 + c;
-            double* dstp = P + (tid >> 4) * kPanelPitch + c;
-#pragma unroll 4
-            for (int i = tid >> 4; i < mpad; i += nt >> 4, src += (size_t)(nt >> 4) * lda, dstp += (nt >> 4) * kPanelPitch) {
+        const int m2 = n1 - k1;                            // rows below the top block: global rows k1 .. p (row p = u^T)
+        const int T = (m2 + 31) >> 5;                      // 32-row tiles of the trailing matrix
+        const int nsb = (nb + 7) >> 3;                     // 8-column blocks of this panel
+        __syncthreads();                                   // Tb / sW of this panel are complete (first panel: above; later: look-ahead)
+        if (tid == 0) sTile = 1;                           // trailing tiles are handed out dynamically; tile 0 is warp 0's
+        // 1. rows below the top block, one warp per 8-row tile, no block barrier: R -> shared, then the blocked forward
+        //    substitution X_s = (R_s - sum_{s' < s} X_s' L_ss'^T) W_s^T on DMMA (W_s = inverse of the s-th 8 x 8 diagonal
+        //    factor), X -> shared (L21 for the trailing update) and -> global (it is L).  Rows are independent of each other,
+        //    so the whole panel is solved between two block barriers (the first version went 8 columns at a time with
+        //    three barriers each and every warp waiting for warp 0's diagonal block: 29 % of the kernel).
+        for (int r0 = warp * 8; r0 < T * 32; r0 += nwarps * 8) {
+            double* tile = P + r0 * kPanelPitch;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                  // 8 rows x 16 column pairs, 4 per lane; a row is one 256-byte run
+                const int i = q * 2 + (lane >> 4), c = (lane & 15) * 2;
                 double2 v = make_double2(0.0, 0.0);
-                if (i < m && cin && c <= i) {
-                    v = *reinterpret_cast<const double2*>(src);
-                    if (!c1in || c + 1 > i) v.y = 0.0;
+                if (r0 + i < m2 && c < nb) {
+                    v = *reinterpret_cast<const double2*>(A + (size_t)(k1 + r0 + i) * lda + k0 + c);
+                    if (c + 1 >= nb) v.y = 0.0;
                 }
-                *reinterpret_cast<double2*>(dstp) = v;
+                *reinterpret_cast<double2*>(tile + i * kPanelPitch + c) = v;
             }
-        }
-        __syncthreads();
-        // 2. factorise the panel, 8 columns at a time
-        for (int c0 = 0; c0 < nb; c0 += 8) {
-            const int nbb = min(8, nb - c0);
-            if (c0 == 0) {   // later blocks of the panel were factorised by the look-ahead below
-                if (warp == 0) {
-                    factor_panel_diag(P, c0, nbb, dblk, rdiag, &sFail);
-                    __syncwarp();
-                    invert_panel_diag(dblk, rdiag, sW);
+            __syncwarp();
+            if (r0 >= m2) continue;                        // zero padding below the matrix
+            double* xrow = tile + gid * kPanelPitch;
+            for (int sb = 0; sb < nsb; ++sb) {
+                double2 acc = *reinterpret_cast<const double2*>(xrow + sb * 8 + 2 * tig);
+                for (int sp = 0; sp < sb; ++sp) {
+                    const double* lrow = Tb + (sb * 8 + gid) * kPanelPitch + sp * 8 + tig;
+                    dmma8x8x4(acc.x, acc.y, -xrow[sp * 8 + tig], lrow[0]);
+                    dmma8x8x4(acc.x, acc.y, -xrow[sp * 8 + 4 + tig], lrow[4]);
                 }
-                __syncthreads();
+                __syncwarp();                              // the tile's block sb has been read by every lane
+                *reinterpret_cast<double2*>(xrow + sb * 8 + 2 * tig) = acc;
+                __syncwarp();
+                const double* w = sW + sb * 64 + gid * 8 + tig;
+                double x0 = 0.0, x1 = 0.0;
+                dmma8x8x4(x0, x1, xrow[sb * 8 + tig], w[0]);
+                dmma8x8x4(x0, x1, xrow[sb * 8 + 4 + tig], w[4]);
+                __syncwarp();
+                *reinterpret_cast<double2*>(xrow + sb * 8 + 2 * tig) = make_double2(x0, x1);
+                __syncwarp();
             }
-            // rows below the diagonal block: X = R L_kk^-T as a product with W = L_kk^-1 on DMMA (two per 8-row tile; the
-            // thread-per-row substitution this replaces was a 36-deep dependent FMA chain fed by 4-way conflicting loads:
-            // 18 % of the kernel).  Identity padding of a short last block leaves the zero columns zero.
-            {
-                const double wf0 = sW[gid * 8 + tig], wf1 = sW[gid * 8 + 4 + tig];   // B[k][n] = W[n][k]
-                for (int r0 = c0 + nbb + warp * 8; r0 < m; r0 += nwarps * 8) {
-                    double* row = P + (r0 + gid) * kPanelPitch + c0;
-                    double x0 = 0.0, x1 = 0.0;
-                    dmma8x8x4(x0, x1, row[tig], wf0);
-                    dmma8x8x4(x0, x1, row[4 + tig], wf1);
-                    __syncwarp();                                      // every lane has read the tile before it is overwritten
-                    *reinterpret_cast<double2*>(row + 2 * tig) = make_double2(x0, x1);
-                }
-            }
-            __syncthreads();
-            // rank-8 update of the panel's remaining columns (c0+8 .. 31) on DMMA: C[i][c2] -= sum_c P[i][c0+c] P[c2][c0+c]
-            // for the row tiles below the diagonal block; one warp per 8-row tile, up to three 8-column tiles each.  (The
-            // first version gave every lane one column and every warp a row strip: one FMA per shared load, 123 k of the
-            // kernel's 424 k instructions per walker.)  Entries above the panel's diagonal are computed too and never read.
-            const int n_nt = (nb - (c0 + 8) + 7) >> 3;     // 8-column tiles right of this block column (<= 3)
-            if (n_nt > 0) {
-                double fb[3][2];
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-                        fb[j][kk] = c0 + 8 + j * 8 + gid < nb ? P[(c0 + 8 + j * 8 + gid) * kPanelPitch + c0 + kk * 4 + tig] : 0.0;   // columns past the panel stay zero
-                // (reads touch columns c0 .. c0+7 only, writes columns >= c0+8: no barrier needed in between)
-                for (int r0 = c0 + 8 + warp * 8; r0 < m; r0 += nwarps * 8) {
-                    const double* arow = P + (r0 + gid) * kPanelPitch + c0 + tig;
-                    const double fa0 = -arow[0], fa1 = -arow[4];
-                    double* crow = P + (r0 + gid) * kPanelPitch + c0 + 8 + 2 * tig;
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        if (j < n_nt) {
-                            double2 cv = *reinterpret_cast<double2*>(crow + j * 8);
-                            dmma8x8x4(cv.x, cv.y, fa0, fb[j][0]);
-                            dmma8x8x4(cv.x, cv.y, fa1, fb[j][1]);
-                            *reinterpret_cast<double2*>(crow + j * 8) = cv;
-                        }
-                    }
-                    // look-ahead: warp 0's first tile holds the next diagonal block, now up to date; it factorises and
-                    // inverts it while the other warps apply the rest of the update (dblk / rdiag / sW were last read
-                    // before the barrier above), so a block step has two block barriers instead of three
-                    if (warp == 0 && r0 == c0 + 8) {
-                        __syncwarp();
-                        factor_panel_diag(P, c0 + 8, min(8, nb - c0 - 8), dblk, rdiag, &sFail);
-                        __syncwarp();
-                        invert_panel_diag(dblk, rdiag, sW);
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        // 3. the finished columns back to global; log L_cc of the pivots
-        {
-            const int c = (tid & 15) * 2;
-            const bool cin = c < nb, c1in = c + 1 < nb;
-            double* dst = A + (size_t)(k0 + (tid >> 4)) * lda + k0 + c;
-            const double* srcp = P + (tid >> 4) * kPanelPitch + c;
-#pragma unroll 4
-            for (int i = tid >> 4; i < m; i += nt >> 4, dst += (size_t)(nt >> 4) * lda, srcp += (nt >> 4) * kPanelPitch) {
-                if (cin && c <= i) {
-                    const double2 v = *reinterpret_cast<const double2*>(srcp);
-                    if (c1in && c + 1 <= i) *reinterpret_cast<double2*>(dst) = v;
+            for (int q = 0; q < 4; ++q) {
+                const int i = q * 2 + (lane >> 4), c = (lane & 15) * 2;
+                if (r0 + i < m2 && c < nb) {
+                    const double2 v = *reinterpret_cast<const double2*>(tile + i * kPanelPitch + c);
+                    double* dst = A + (size_t)(k1 + r0 + i) * lda + k0 + c;
+                    if (c + 1 < nb) *reinterpret_cast<double2*>(dst) = v;
                     else dst[0] = v.x;
                 }
             }
         }
-        for (int c = tid; c < nb; c += nt) ldsum += log(P[c * kPanelPitch + c]);
-        // 4. trailing update on DMMA: rows / columns k1 .. p, 32 x 32 tiles of the lower triangle, one warp each
-        const int m2 = n1 - k1;
-        const int T = (m2 + 31) >> 5;
-        const double* P2 = P + nb * kPanelPitch;           // panel rows below the diagonal block: L21
-        for (int tile = warp; tile < T * (T + 1) / 2; tile += nwarps) {
+        __syncthreads();                                   // L21 complete in shared memory
+        // 2. trailing update on DMMA: rows / columns k1 .. p, 32 x 32 tiles of the lower triangle, one warp each.  Warp 0
+        //    takes tile (0, 0) - it holds the next panel's top block - copies the result into Tb and factorises it while the
+        //    other warps work through the remaining tiles (look-ahead across panels: the serial diagonal work is hidden
+        //    behind the trailing update whenever that has more than a few tiles).
+        const int n_tiles = T * (T + 1) / 2;
+        const int nb_next = min(kPanelW, p - k1);
+        bool first = warp == 0;
+        for (;;) {
+            int tile;
+            if (first) tile = 0;
+            else {
+                tile = 0;
+                if (lane == 0) tile = atomicAdd(&sTile, 1);
+                tile = __shfl_sync(0xffffffffu, tile, 0);
+            }
+            if (tile >= n_tiles) break;
             int ti = 0;
             while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
             const int tj = tile - ti * (ti + 1) / 2;
@@ -1454,25 +1519,25 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
                     }
             } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rr = ti * 32 + i * 8 + gid, cc = tj * 32 + j * 8 + 2 * tig;
-                    acc[i][j][0] = acc[i][j][1] = 0.0;
-                    if (rr < m2) {
-                        const double* src = A + (size_t)(k1 + rr) * lda + k1 + cc;
-                        if (cc + 1 <= rr) {
-                            const double2 v = *reinterpret_cast<const double2*>(src);
-                            acc[i][j][0] = v.x;
-                            acc[i][j][1] = v.y;
-                        } else if (cc <= rr) {
-                            acc[i][j][0] = src[0];
+                    for (int j = 0; j < 4; ++j) {
+                        const int rr = ti * 32 + i * 8 + gid, cc = tj * 32 + j * 8 + 2 * tig;
+                        acc[i][j][0] = acc[i][j][1] = 0.0;
+                        if (rr < m2) {
+                            const double* src = A + (size_t)(k1 + rr) * lda + k1 + cc;
+                            if (cc + 1 <= rr) {
+                                const double2 v = *reinterpret_cast<const double2*>(src);
+                                acc[i][j][0] = v.x;
+                                acc[i][j][1] = v.y;
+                            } else if (cc <= rr) {
+                                acc[i][j][0] = src[0];
+                            }
                         }
                     }
-                }
             }
-            const double* pa = P2 + (ti * 32 + gid) * kPanelPitch + tig;
-            const double* pb = P2 + (tj * 32 + gid) * kPanelPitch + tig;
+            const double* pa = P + (ti * 32 + gid) * kPanelPitch + tig;
+            const double* pb = P + (tj * 32 + gid) * kPanelPitch + tig;
 #pragma unroll
             for (int kk = 0; kk < kPanelW / 4; ++kk) {
                 double fa[4], fb[4];
@@ -1494,20 +1559,50 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
                         *reinterpret_cast<double2*>(ctile + (size_t)(i * 8) * lda + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
             } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rr = ti * 32 + i * 8 + gid, cc = tj * 32 + j * 8 + 2 * tig;
-                    if (rr < m2) {
-                        double* dst = A + (size_t)(k1 + rr) * lda + k1 + cc;
-                        if (cc + 1 <= rr) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
-                        else if (cc <= rr) dst[0] = acc[i][j][0];
+                    for (int j = 0; j < 4; ++j) {
+                        const int rr = ti * 32 + i * 8 + gid, cc = tj * 32 + j * 8 + 2 * tig;
+                        if (rr < m2) {
+                            double* dst = A + (size_t)(k1 + rr) * lda + k1 + cc;
+                            if (cc + 1 <= rr) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+                            else if (cc <= rr) dst[0] = acc[i][j][0];
+                        }
+                    }
+            }
+            if (first) {
+                first = false;
+                if (nb_next > 0) {
+                    // the next top block (rows / columns k1 .. k1 + nb_next - 1): lower triangle into Tb, zero elsewhere.
+                    // Tb and sW of the current panel were last read before the barrier above.
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int rr = i * 8 + gid, cc = j * 8 + 2 * tig;
+                            double2 v = make_double2(0.0, 0.0);
+                            if (rr < nb_next) {
+                                if (cc <= rr) v.x = acc[i][j][0];
+                                if (cc + 1 <= rr) v.y = acc[i][j][1];
+                            }
+                            *reinterpret_cast<double2*>(Tb + rr * kPanelPitch + cc) = v;
+                        }
+                    __syncwarp();
+                    ldsum += factor_top_block(Tb, nb_next, dblk, sW);
+                    for (int e = lane; e < nb_next * (kPanelW / 2); e += 32) {
+                        const int i = e >> 4, c = (e & 15) * 2;
+                        if (c <= i) {
+                            const double2 v = *reinterpret_cast<const double2*>(Tb + i * kPanelPitch + c);
+                            double* dst = A + (size_t)(k1 + i) * lda + k1 + c;
+                            if (c + 1 <= i) *reinterpret_cast<double2*>(dst) = v;
+                            else dst[0] = v.x;
+                        }
                     }
                 }
             }
         }
-        __syncthreads();                                   // the panel buffer is reused; global updates are block-local
     }
+    __syncthreads();
 
     const double logdetSig = 2 * block_sum(ldsum, scratch);
     double py = 0.0, pl = 0.0;

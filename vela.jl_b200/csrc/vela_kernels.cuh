@@ -199,10 +199,12 @@ inline size_t chol_smem_doubles(int p, int pp, int nb, bool matrix_in_smem, int 
 __global__ void chol_panel_kernel(CholArgs a);
 constexpr int kPanelThreadsHost = 256;   // = kPanelThreads in vela_kernels.cu
 inline size_t chol_panel_smem_bytes(int p, int pp, int n_ru) {
-    const int n1 = p + 1, prow = ((n1 + 31) & ~31) + 32;
+    // phi[pp] | column buffers[96] | [8] | sW[4][64] | Tb[32][36] | P[prow][36]: prow = rows below the first panel's top block,
+    // rounded up to the 32-row tiles of the trailing update
+    const int n1 = p + 1, prow = (n1 - (p < 32 ? p : 32) + 31) & ~31;
     const size_t panel = (size_t)prow * 36;                // kPanelPitch
     const size_t sums = 2 * (size_t)n_ru + 2;              // S = {+R/2 | -R/2 | 0} aliases the panel during assembly
-    return ((size_t)pp + 72 + 8 + 64 + (panel > sums ? panel : sums)) * sizeof(double);
+    return ((size_t)pp + 96 + 8 + 256 + 32 * 36 + (panel > sums ? panel : sums)) * sizeof(double);
 }
 inline size_t chol_panel_scratch_doubles(int p, int pp) { return (size_t)(p + 1) * (pp + 2); }   // per walker
 
