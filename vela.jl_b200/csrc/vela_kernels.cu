@@ -1336,16 +1336,29 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
             // the row, so the recipe loads and the stores are coalesced and no thread tracks (row, column) through the
             // packed order (the pair-ordered loop below spent 62 thread-instructions per pair on bookkeeping and on
             // decoding coefficient codes: 20 % of the kernel)
+            // (eight codes in flight per lane: the loop is a chain of dependent L2 / shared / global accesses per entry and
+            // the CTA has eight warps to hide it with)
+            const unsigned zero_code = (unsigned)(2 * a.n_r) * 0x10001u;      // S[zero] + S[zero]
+            const bool add_sig = a.add_sig != 0;
             for (int r = warp; r < p; r += nwarps) {
                 const size_t t0 = (size_t)r * (r + 1) / 2;
                 const unsigned* ct = a.ctab + t0;
                 double* dst = A + (size_t)r * lda;
-#pragma unroll 4
-                for (int c = lane; c <= r; c += 32) {
-                    const unsigned e = __ldg(ct + c);
-                    double v = sR[e & 0xffffu] + sR[e >> 16];
-                    if (a.add_sig) v += gA[t0 + c];
-                    dst[c] = v;
+                for (int c0 = lane; c0 <= r; c0 += 256) {
+                    unsigned e[8];
+                    double g[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const bool in = c0 + 32 * u <= r;
+                        e[u] = in ? __ldg(ct + c0 + 32 * u) : zero_code;
+                        g[u] = (in && add_sig) ? gA[t0 + c0 + 32 * u] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        double v = sR[e[u] & 0xffffu] + sR[e[u] >> 16];
+                        if (add_sig) v += g[u];
+                        if (c0 + 32 * u <= r) dst[c0 + 32 * u] = v;
+                    }
                 }
             }
         } else {
@@ -1453,8 +1466,11 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
             __syncwarp();
             if (r0 >= m2) continue;                        // zero padding below the matrix
             double* xrow = tile + gid * kPanelPitch;
-            for (int sb = 0; sb < nsb; ++sb) {
+#pragma unroll
+            for (int sb = 0; sb < kPanelW / 8; ++sb) {
+                if (sb >= nsb) break;
                 double2 acc = *reinterpret_cast<const double2*>(xrow + sb * 8 + 2 * tig);
+#pragma unroll
                 for (int sp = 0; sp < sb; ++sp) {
                     const double* lrow = Tb + (sb * 8 + gid) * kPanelPitch + sp * 8 + tig;
                     dmma8x8x4(acc.x, acc.y, -xrow[sp * 8 + tig], lrow[0]);
