@@ -1158,66 +1158,24 @@ template __global__ void chol_finish_kernel<16, false>(CholArgs);
 // L2 (ncu: FP64 pipe 26 % active, 8.7 GB of DRAM traffic per 2048 walkers).  Here a block column is 32 wide, lives in
 // shared memory while it is factorised, and the trailing update A22 -= L21 L21^T runs on DMMA (m8n8k4) straight from
 // that shared panel: 32 FMAs per read-modify-write, half the passes over the triangle, and the FP64 pipe does the work.
-//   per panel (k0 .. k0+31), one CTA of 8 warps per walker:
-//     1. rows k0..p of the panel: global -> shared (P[row - k0][0..31], pitch 36: conflict-free DMMA fragment reads)
-//     2. factorise it in place, 8 columns at a time: warp 0 factorises the 8 x 8 diagonal block in registers
-//        (factor_panel_diag), one thread per row solves against it, then lane = column / warp = row strip apply the
-//        rank-8 update to the panel's remaining columns (the lane keeps its column's 8 multipliers in registers)
-//     3. the finished columns go back to global (they are L)
-//     4. trailing update: 32 x 32 tiles of the lower triangle of rows k1..p, one warp per tile, 4 x 4 m8n8k4
-//        accumulators, 8 k-steps; the C tile is fetched before the k-loop and written once
+//   one CTA of 8 warps per walker; per panel (columns k0 .. k0+31):
+//     1. the panel's 32 x 32 top block L_kk (shared, Tb) and the inverses W_s of its four 8 x 8 diagonal factors (sW) are
+//        ready when the panel starts: warp 0 made them during the previous panel's trailing update (look-ahead; first
+//        panel: up front) with a register Cholesky, lane = row (factor_top_block)
+//     2. rows below the top block, one warp per 8-row tile and no block barrier in between: global -> shared, blocked
+//        forward substitution X_s = (R_s - sum_{s' < s} X_s' L_ss'^T) W_s^T on DMMA, X -> shared (L21) and -> global (L)
+//     3. trailing update A22 -= L21 L21^T: 32 x 32 tiles of the lower triangle of rows k1..p handed out through a shared
+//        counter, 4 x 4 m8n8k4 accumulators, 8 k-steps; the C tile is fetched before the k-loop and written once.  Warp 0
+//        takes tile (0, 0) first - the next panel's top block - and factorises it while the others do the rest.
+//   Two block barriers per panel.  The first version factorised the panel 8 columns at a time (diagonal block by warp 0,
+//   thread-per-row substitution, rank-8 update: three barriers per 8 columns, ten per panel) and assembled Sigma in pair
+//   order: 12.6 ms at 8192 walkers; this one 8.0 ms (tensor pipe 21 -> 34 % busy).  What is left is the look-ahead itself:
+//   its scalar FP64 chain shares the FP64 pipe with the other warps' DMMAs and runs ~5 x slower than alone, so the
+//   trailing tiles still wait for it on the later, smaller panels (profiles/r2_ncu_chol_panel_rank300.txt).
 // u rides along as row p (z = L^-1 u, entry (p, p) = -z.z) exactly as in the other finishing kernels.
 constexpr int kPanelW = 32;
 constexpr int kPanelPitch = kPanelW + 4;
 constexpr int kPanelThreads = 256;
-
-// 8 x 8 diagonal block at rows / columns c0 .. c0+7 of the shared panel, by one warp in registers (lane r owns row r)
-__device__ __forceinline__ void factor_panel_diag(double* P, int c0, int nbb, double* dblk, double* rdiag, int* fail) {
-    const int lane = threadIdx.x & 31;
-    double row[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        row[c] = (lane < nbb && c <= lane) ? P[(c0 + lane) * kPanelPitch + c0 + c] : ((lane == c) ? 1.0 : 0.0);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        double d = __shfl_sync(0xffffffffu, row[c], c);
-        if (c < nbb && (!(d > 0.0) || !isfinite(d))) { if (lane == 0) *fail = 1; d = 1.0; }
-        const double rd = rsqrt(d);
-        if (lane == c) { row[c] = d * rd; rdiag[c] = rd; }
-        else if (lane > c) row[c] *= rd;
-#pragma unroll
-        for (int q = c + 1; q < 8; ++q) {
-            const double lqc = __shfl_sync(0xffffffffu, row[c], q);
-            if (lane >= q) row[q] = fma(-row[c], lqc, row[q]);
-        }
-    }
-    if (lane < 8) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            if (c <= lane) {
-                dblk[lane * 9 + c] = row[c];
-                if (lane < nbb) P[(c0 + lane) * kPanelPitch + c0 + c] = row[c];
-            }
-    }
-}
-
-// W = L_kk^-1 of the block factor_panel_diag left in dblk (pitch 9; rdiag = reciprocal pivots), by the same warp: lane & 7
-// = column, forward substitution down the rows; identity padding inverts to itself.  sW is row-major [8][8].
-__device__ __forceinline__ void invert_panel_diag(const double* dblk, const double* rdiag, double* sW) {
-    const int col = threadIdx.x & 7;
-    double w[8];
-#pragma unroll
-    for (int rr = 0; rr < 8; ++rr) {
-        double acc = (rr == col) ? 1.0 : 0.0;
-#pragma unroll
-        for (int q = 0; q < rr; ++q) acc = fma(-dblk[rr * 9 + q], w[q], acc);
-        w[rr] = acc * rdiag[rr];
-    }
-    if ((threadIdx.x & 31) < 8) {
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) sW[rr * 8 + col] = w[rr];
-    }
-}
 
 // 1 / sqrt(d) from the hardware seed (rsqrt.approx.f64: ~22 bits) and one third-order step: e = 1 - d y^2,
 // y <- y + y e (1/2 + 3/8 e), good to ~1e-18 relative - four dependent FP64 operations where the library routine's
@@ -1304,9 +1262,8 @@ __global__ void __launch_bounds__(kPanelThreads, 2) chol_panel_kernel(CholArgs a
     const int p = a.p, pp = a.pp, n1 = p + 1;
     const int lda = pp + 2;                                // even pitch of the global matrix rows
     double* phi = smem;                                    // [pp]
-    double* dblk = phi + pp;                               // [96] factor_top_block: two column buffers, reciprocal pivots
-    double* rdiag = dblk + 96;                             // [8] (unused)
-    double* sW = rdiag + 8;                                // [4][8][8] inverses of the top block's diagonal factors
+    double* dblk = phi + pp;                               // [96 + 8] factor_top_block: two column buffers, reciprocal pivots
+    double* sW = dblk + 104;                               // [4][8][8] inverses of the top block's diagonal factors
     double* Tb = sW + 256;                                 // [32][kPanelPitch] the panel's top block (L_kk)
     double* P = Tb + kPanelW * kPanelPitch;                // [prow][kPanelPitch] rows below it (L21); the column sums alias it during assembly
     double* sR = P;
