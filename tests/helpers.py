@@ -34,6 +34,7 @@ def emul_lib():
         L = C.CDLL(os.path.join(here, "libvela_emul.so"))
         dp = C.POINTER(C.c_double)
         L.emul_chain.argtypes = [C.c_void_p, dp, C.c_long, C.c_int, C.c_int, dp, dp, dp, dp, dp]
+        L.emul_spec_check.argtypes = [C.c_void_p, dp, C.c_long, C.c_int, C.POINTER(C.c_long)]
         _EMUL = L
     return _EMUL
 
@@ -54,3 +55,14 @@ def emul_chain(md, paramss, emit=1, fast=False):
     if emit == 2:
         return Y, W, F, chi, lg
     return Y, W, chi, lg
+
+
+def emul_spec_check(md, paramss, emit=1):
+    """Speculative vs branching evaluation of the fast chain build on the CPU (tests/host_emul/emul.cpp):
+    returns (pairs, pairs that raised `redo`, pairs without `redo` whose outputs differ in any bit)."""
+    import ctypes as C
+    p = np.ascontiguousarray(np.atleast_2d(paramss), dtype=np.float64)
+    counts = (C.c_long * 3)()
+    rc = emul_lib().emul_spec_check(C.addressof(md.desc), p.ctypes.data_as(C.POINTER(C.c_double)), p.shape[0], emit, counts)
+    assert rc == 0
+    return tuple(counts)

@@ -74,3 +74,57 @@ int emul_chain(const VelaModelDesc* desc, const double* params, long B, int emit
     }
     return 0;
 }
+
+// Speculative evaluation (Corr::spec, the per-model fast build's hot loop) against the branching evaluation of the same
+// (TOA, walker) pairs: wherever the speculative pass raises no `redo`, every output must be the same bits; where it does,
+// the kernel evaluates again with branches, so nothing is to be compared.  counts = {pairs, redo raised, mismatches}.
+extern "C" __attribute__((visibility("default")))
+int emul_spec_check(const VelaModelDesc* desc, const double* params, long B, int emit, long* counts) {
+    ProgramDev pg;
+    build_program(desc, pg, true);
+    const long nt = desc->n_toas, stride = (nt + 31) / 32 * 32;
+    std::vector<double> soa((size_t)C_NCOL * stride, 0.0), tzr(C_NCOL, 0.0);
+    for (long j = 0; j < nt; ++j) {
+        fill_toa_columns((const double*)((const char*)desc->toas + j * (long)desc->toa_stride_bytes), desc->wideband,
+                         soa.data(), stride, j);
+        fill_shapiro_columns(desc, soa.data(), stride, j);
+    }
+    fill_toa_columns((const double*)desc->tzr_toa, 0, tzr.data(), 1, 0);
+    fill_shapiro_columns(desc, tzr.data(), 1, 0);
+    std::vector<double> defaults(desc->default_values, desc->default_values + desc->n_params);
+    if (desc->n_aux > 0) defaults.insert(defaults.end(), desc->aux_values, desc->aux_values + desc->n_aux);
+    std::vector<int> free_idx(desc->free_indices, desc->free_indices + desc->n_free);
+    std::vector<double> Pext((size_t)B * pg.row, 0.0), tzr_phase((size_t)B * 2, 0.0);
+    PrologueArgs pa;
+    pa.defaults = defaults.data(); pa.free_idx = free_idx.data(); pa.params = params; pa.B = B;
+    pa.tzr_block = tzr.data(); pa.index_masks = desc->index_masks; pa.bit_masks = desc->bit_masks; pa.n_toas = nt;
+    pa.Pext = Pext.data(); pa.tzr_phase = tzr_phase.data();
+    blockIdx = {0, 0, 0}; blockDim = {1, 1, 1};
+    for (long b = 0; b < B; ++b) {
+        threadIdx = {(unsigned)b, 0, 0};
+        prologue_body(pg, pa);
+    }
+    counts[0] = counts[1] = counts[2] = 0;
+    auto same = [](double x, double y) { return memcmp(&x, &y, 8) == 0 || (x != x && y != y); };
+    for (long b = 0; b < B; ++b) {
+        const double* P = Pext.data() + (size_t)b * pg.row;
+        for (long j = 0; j < nt; ++j) {
+            ToaRegs t = load_toa(soa.data(), stride, j, false);
+            ChainEnv e;
+            e.toa_base = soa.data(); e.stride = stride; e.j = j;
+            e.index_masks = desc->index_masks; e.bit_masks = desc->bit_masks; e.n_toas = nt;
+            e.tzr = false; e.wide = desc->wideband != 0;
+            Corr ks = run_chain(pg, P, t, e, true);
+            ResidTerms rs = residual_terms(ks, t, e.wide, tzr_phase[2 * b], tzr_phase[2 * b + 1], emit);
+            Corr kb = run_chain(pg, P, t, e, false);
+            ResidTerms rb = residual_terms(kb, t, e.wide, tzr_phase[2 * b], tzr_phase[2 * b + 1], emit);
+            ++counts[0];
+            if (rs.redo) { ++counts[1]; continue; }
+            if (!(same(rs.tres, rb.tres) && same(rs.w, rb.w) && same(rs.chi, rb.chi) && same(rs.lman, rb.lman) && rs.lex == rb.lex &&
+                  same(rs.dmres, rb.dmres) && same(rs.wdm, rb.wdm) && same(rs.f, rb.f) && same(rs.dphase.hi, rb.dphase.hi) &&
+                  same(rs.dphase.lo, rb.dphase.lo)))
+                ++counts[2];
+        }
+    }
+    return 0;
+}

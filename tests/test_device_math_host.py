@@ -68,3 +68,23 @@ def test_phase_mode_matches_oracle(vb, oracle, golden):
     # Double64 phase residual: hi + lo agree to 1e-13 cycle (phase_small joins in FP64)
     assert np.max(np.abs((hi[0, :nt] - ohi) + (lo[0, :nt] - olo))) < 1e-13
     np.testing.assert_allclose(f[0, :nt], of, rtol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["config3_gp", "config4_dd_wb", "config5_array", "extra_ell1h_fd_wavex", "extra_free_gp_wb"])
+def test_speculative_evaluation_is_the_branching_one(name, vb, oracle):
+    """The per-model fast build evaluates every gated shortcut unconditionally and defers the gates to a `redo` flag
+    (Corr::spec); wherever the flag stays down the outputs must be the branching evaluation's, bit for bit, and walkers
+    near the truth must practically never raise it.  A walker far from the default sky position must raise it."""
+    from helpers import emul_spec_check
+    cfg = vb.synth.CONFIGS[name]
+    ds = vb.synth.make_dataset(name, oracle_eval_factory(vb, oracle), ntoa=min(cfg["ntoa"], 400))
+    md = vb.ModelDescriptor(ds.model, ds.toas)
+    for emit in (0, 1, 3):
+        pairs, redo, bad = emul_spec_check(md, ds.walkers(6, seed=11), emit=emit)
+        assert bad == 0 and redo <= 0.01 * pairs, (emit, pairs, redo, bad)
+    sky = [i for i, n in enumerate(ds.info["free_names"]) if n in ("RAJ", "DECJ", "ELONG", "ELAT")]
+    assert sky, ds.info["free_names"]
+    far = ds.walkers(1, seed=2).copy()
+    far[0, sky[0]] += 1e-3          # 200 arcsec off: the Shapiro expansion point is out of reach
+    pairs, redo, bad = emul_spec_check(md, far, emit=1)
+    assert bad == 0 and redo > 0

@@ -823,6 +823,9 @@ std::string spec_source(const ProgramDev& pg, int min_blocks = 2, int threads = 
         snprintf(buf, sizeof buf, "#define VELA_CHAIN_UNROLL %d\n", std::max(1, std::min(4, atoi(e))));
         src += buf;
     }
+    // fast-arithmetic build: speculative straight-line evaluation with a warp-uniform re-evaluation (Corr::spec)
+    if ((pg.comp[0].flags & kFlagFast) && !(getenv("VELA_B200_JIT_SPECULATE") && atoi(getenv("VELA_B200_JIT_SPECULATE")) == 0))
+        src += "#define VELA_SPEC_SPECULATE 1\n";
     if (emit >= 0) {   // the emit mode of the handle's batches, folded into the kernel (launch_chain checks it)
         snprintf(buf, sizeof buf, "#define VELA_SPEC_EMIT %d\n", emit);
         src += buf;
@@ -938,7 +941,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     if (const char* e = getenv("VELA_B200_CHAIN_THREADS")) h->chain_threads = std::max(32, std::min(256, atoi(e) / 32 * 32));
     h->n_tiles = (int)((desc->n_toas + h->chain_threads - 1) / h->chain_threads);
     h->chain_group = 32;
-    if (const char* e = getenv("VELA_B200_CHAIN_GROUP")) h->chain_group = std::max(4, std::min(128, atoi(e)));
+    if (const char* e = getenv("VELA_B200_CHAIN_GROUP")) h->chain_group = std::max(4, std::min(64, atoi(e)));   // <= 64: the speculative build keeps one redo bit per walker of the group
 
     std::vector<int3> egroups;
     std::vector<int> echunks;

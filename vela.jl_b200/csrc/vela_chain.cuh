@@ -71,14 +71,23 @@ __device__ __forceinline__ void prologue_body(const ProgramDev& prog, const Prol
 
 // frexp for the log-det accumulation: normal positive inputs (every sane err^2) are split with three integer
 // operations; zero, subnormal, infinite and NaN inputs go through the library routine.
-__device__ __forceinline__ double split_mantissa(double v, int* ex) {
+__device__ __forceinline__ double split_mantissa(double v, int* ex, bool spec, bool& redo) {
     const int hi = __double2hiint(v);
+    if (spec) {   // speculative evaluation (Corr::spec): the integer split unconditionally, the range test deferred
+        redo |= !((unsigned)(hi - 0x00100000) < 0x7fe00000u);
+        *ex = (hi >> 20) - 1022;
+        return __hiloint2double((hi & 0x000fffff) | 0x3fe00000, __double2loint(v));
+    }
     // positive and normal <=> sign 0 and exponent field in 1 .. 0x7fe: one unsigned compare on the high word
     if ((unsigned)(hi - 0x00100000) < 0x7fe00000u) {
         *ex = (hi >> 20) - 1022;
         return __hiloint2double((hi & 0x000fffff) | 0x3fe00000, __double2loint(v));   // mantissa in [1/2, 1)
     }
     return frexp(v, ex);
+}
+__device__ __forceinline__ double split_mantissa(double v, int* ex) {
+    bool unused = false;
+    return split_mantissa(v, ex, false, unused);
 }
 
 // What one (TOA, walker) pair contributes: form_residual (residuals.jl:8-12, wideband_residuals.jl:6-17), the scaled
@@ -90,6 +99,7 @@ struct ResidTerms {
     double lman; int lex;         // prod sigma^2 = lman 2^lex
     dd dphase;                    // phase mode (emit == 2) only
     double f;                     // doppler-shifted spin frequency
+    bool redo;                    // speculative evaluation: a gate failed (in the chain or here), evaluate again with branches
 };
 
 __device__ __forceinline__ ResidTerms residual_terms(const Corr& k, const ToaRegs& t, bool wide, double tzr_hi, double tzr_lo,
@@ -124,7 +134,8 @@ __device__ __forceinline__ ResidTerms residual_terms(const Corr& k, const ToaReg
     // log det N = sum_j log(err2_j) is accumulated as a PRODUCT of mantissas and a sum of binary exponents, so the
     // logarithm is taken once per (tile, walker) in the block epilogue instead of once per (TOA, walker)
     r.w = 0.0;
-    r.lman = split_mantissa(err2, &r.lex);
+    r.redo = k.redo;
+    r.lman = split_mantissa(err2, &r.lex, k.spec, r.redo);
     if (emit) {  // Woodbury: y^T N^-1 y and log det N from Ninvdiag, gls_likelihood.jl:81-99
         r.w = rcp_fast(err2);
         r.chi = r.tres * r.tres * r.w;
@@ -136,7 +147,7 @@ __device__ __forceinline__ ResidTerms residual_terms(const Corr& k, const ToaReg
         r.dmres = t.dm - k.model_dm;
         const double dmerr2 = (t.dmerr2 + k.dmequad2) * k.dmefac * k.dmefac;
         int dex;
-        r.lman *= split_mantissa(dmerr2, &dex);
+        r.lman *= split_mantissa(dmerr2, &dex, k.spec, r.redo);
         r.lex += dex;
         if (emit) {
             r.wdm = rcp_fast(dmerr2);
@@ -234,23 +245,19 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
     // running pointers instead of per-walker index arithmetic (64-bit multiplies in the innermost loop otherwise)
     const double* P = sP;
     const double* tz = sTzr;
-    double* yp = a.Y + (size_t)b0 * a.ld_yw + j;
-    double* wp = a.W + (size_t)b0 * a.ld_yw + j;
-    double* fp = emit == 2 ? a.F + (size_t)b0 * a.ld_yw + j : nullptr;
     double* rc = rChi + lane;
     double* rm = rMan + lane;
     int* re = rExp + lane;
-#pragma unroll kChainUnroll
-    for (int s = 0; s < nb; ++s, P += row, tz += 2, yp += a.ld_yw, wp += a.ld_yw) {
-        Corr k = run_chain(prog, P, t, e);
-        const ResidTerms r = residual_terms(k, t, e.wide, tz[0], tz[1], emit);
+    // what one evaluated (TOA, walker) pair leaves behind: its rows of Y / W (/ F) and its terms in ring slot `slot`
+    auto deposit = [&](const ResidTerms& r, size_t off, int slot) {   // off: (b0 + s) ld_yw + j
+        double* yp = a.Y + off;
+        double* wp = a.W + off;
         if (emit == 2) {  // phase mode: Double64 phase residual and doppler-shifted spin frequency
             if (active) {
                 *yp = r.dphase.hi;
                 *wp = r.dphase.lo;
-                *fp = r.f;
+                a.F[off] = r.f;
             }
-            fp += a.ld_yw;
         } else if (emit && active) {
             *yp = emit == 3 ? r.w * r.tres : r.tres;       // emit 3: the structured contraction wants w.y
             *wp = r.w;
@@ -259,14 +266,44 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
                 wp[a.n_toas] = r.wdm;
             }
         }
-        // this walker's terms wait in the warp's ring; every kRedRing walkers one pass reduces them over the TOAs
-        const int slot = s & (kRedRing - 1);
         rc[slot * kRedPitch] = active ? r.chi : 0.0;
         rm[slot * kRedPitch] = active ? r.lman : 1.0;   // wideband: a product of two mantissas, >= 1/4
         re[slot * kRedPitch] = active ? r.lex : 0;
+    };
+#ifdef VELA_SPEC_SPECULATE
+    // Per-model fast build: every walker is first evaluated straight-line (Corr::spec); walkers for which some lane of the
+    // warp fell outside a gate are noted in a warp-uniform mask and evaluated again, through the branching code, in a
+    // second loop after this one (rare: prior draws far from the default sky position, barycentred TOAs).  The hot loop
+    // holds no trace of the branching code: it is one basic block plus the ring pass.
+    unsigned long long redo_mask = 0;
+#endif
+    size_t off = (size_t)b0 * a.ld_yw + j;   // running offset instead of per-walker index arithmetic (64-bit multiplies otherwise)
+#pragma unroll kChainUnroll
+    for (int s = 0; s < nb; ++s, P += row, tz += 2, off += a.ld_yw) {
+#ifdef VELA_SPEC_SPECULATE
+        const Corr k = run_chain(prog, P, t, e, true);
+        const ResidTerms r = residual_terms(k, t, e.wide, tz[0], tz[1], emit);
+        if (__any_sync(0xffffffffu, r.redo)) redo_mask |= 1ULL << s;
+#else
+        const Corr k = run_chain(prog, P, t, e);
+        const ResidTerms r = residual_terms(k, t, e.wide, tz[0], tz[1], emit);
+#endif
+        // this walker's terms wait in the warp's ring; every kRedRing walkers one pass reduces them over the TOAs
+        const int slot = s & (kRedRing - 1);
+        deposit(r, off, slot);
         if (slot == kRedRing - 1) ring_reduce(rChi, rMan, rExp, kRedRing, lane, wRed, s - (kRedRing - 1));
     }
     if (nb & (kRedRing - 1)) ring_reduce(rChi, rMan, rExp, nb & (kRedRing - 1), lane, wRed, nb & ~(kRedRing - 1));
+#ifdef VELA_SPEC_SPECULATE
+    while (redo_mask) {
+        const int s = __ffsll((long long)redo_mask) - 1;
+        redo_mask &= redo_mask - 1;
+        const Corr k = run_chain(prog, sP + (size_t)s * row, t, e, false);
+        const ResidTerms r = residual_terms(k, t, e.wide, sTzr[2 * s], sTzr[2 * s + 1], emit);
+        deposit(r, (size_t)(b0 + s) * a.ld_yw + j, 0);
+        ring_reduce(rChi, rMan, rExp, 1, lane, wRed, s);
+    }
+#endif
     __syncthreads();
     for (int i = tid; i < nb; i += blockDim.x) {
         double chi = 0.0, man = 1.0, ex = 0.0;
