@@ -36,7 +36,7 @@ int emul_chain(const VelaModelDesc* desc, const double* params, long B, int emit
     PrologueArgs pa;
     pa.defaults = defaults.data(); pa.free_idx = free_idx.data(); pa.params = params; pa.B = B;
     pa.tzr_block = tzr.data(); pa.index_masks = desc->index_masks; pa.bit_masks = desc->bit_masks; pa.n_toas = nt;
-    pa.Pext = Pext.data(); pa.tzr_phase = tzr_phase.data();
+    pa.Pext = Pext.data(); pa.tzr_phase = tzr_phase.data(); pa.rows_in_smem = 0;
     blockIdx = {0, 0, 0}; blockDim = {1, 1, 1};
     for (long b = 0; b < B; ++b) {
         threadIdx = {(unsigned)b, 0, 0};
@@ -98,7 +98,7 @@ int emul_spec_check(const VelaModelDesc* desc, const double* params, long B, int
     PrologueArgs pa;
     pa.defaults = defaults.data(); pa.free_idx = free_idx.data(); pa.params = params; pa.B = B;
     pa.tzr_block = tzr.data(); pa.index_masks = desc->index_masks; pa.bit_masks = desc->bit_masks; pa.n_toas = nt;
-    pa.Pext = Pext.data(); pa.tzr_phase = tzr_phase.data();
+    pa.Pext = Pext.data(); pa.tzr_phase = tzr_phase.data(); pa.rows_in_smem = 0;
     blockIdx = {0, 0, 0}; blockDim = {1, 1, 1};
     for (long b = 0; b < B; ++b) {
         threadIdx = {(unsigned)b, 0, 0};

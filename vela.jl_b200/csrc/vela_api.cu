@@ -593,13 +593,20 @@ void launch_prologue(VelaPulsar* h, DeviceModel& d, const double* d_params, long
     PrologueArgs pa;
     pa.defaults = d.defaults; pa.free_idx = d.free_idx; pa.params = d_params; pa.B = B; pa.tzr_block = d.tzr_block;
     pa.index_masks = d.index_masks; pa.bit_masks = d.bit_masks; pa.n_toas = h->n_toas; pa.Pext = d.buf.Pext; pa.tzr_phase = d.buf.tzr;
-    const int threads = B >= 4096 ? 128 : 32;    // small batches: spread the walkers over more SMs
+    int threads = B >= 4096 ? 128 : 32;          // small batches: spread the walkers over more SMs
+    // working rows in shared memory while they fit the default 48 KB (config 3: 45 doubles per row); longer rows (free-
+    // amplitude GPs with hundreds of hoisted factors) take narrower blocks, or the global row
+    const size_t row_bytes = (size_t)h->prog.row * sizeof(double);
+    if (threads * row_bytes > 48 * 1024) threads = 32;
+    size_t smem = threads * row_bytes;
+    if (smem > 48 * 1024 || (getenv("VELA_B200_PROLOGUE_SMEM") && atoi(getenv("VELA_B200_PROLOGUE_SMEM")) == 0)) smem = 0;
+    pa.rows_in_smem = smem ? 1 : 0;
     const dim3 grid((unsigned)((B + threads - 1) / threads));
     if (h->use_spec && h->spec_prologue) {
         void* args[] = {&pa};
-        cudaLaunchKernel((const void*)h->spec_prologue, grid, dim3((unsigned)threads), args, 0, st);
+        cudaLaunchKernel((const void*)h->spec_prologue, grid, dim3((unsigned)threads), args, smem, st);
     } else {
-        sample_prologue_kernel<<<grid, threads, 0, st>>>(h->prog, pa);
+        sample_prologue_kernel<<<grid, threads, smem, st>>>(h->prog, pa);
     }
 }
 

@@ -38,14 +38,34 @@ struct PrologueArgs {
     long n_toas;
     double* Pext;              // [B][row]
     double* tzr_phase;         // [B][2]
+    int rows_in_smem;          // 1: the launch carries blockDim.x * row doubles of dynamic shared memory for the working rows
 };
 
 // K0 body: read_params (parameter.jl:158-169) + per-walker hoists + calc_tzr_phase (residuals.jl:29-32); one thread
 // per walker.  Shared by the generic kernel and the per-model NVRTC build like chain_body below.
+__device__ __forceinline__ void prologue_row(const ProgramDev& prog, const PrologueArgs& a, long b, double* P);
 __device__ __forceinline__ void prologue_body(const ProgramDev& prog, const PrologueArgs& a) {
     long b = blockIdx.x * (long)blockDim.x + threadIdx.x;
+#ifndef VELA_HOST_EMUL
+    // The walker's extended row is written and then read back dozens of times along one dependent chain (derived values,
+    // the TZR fold); in global memory every one of those reads is an L2 round trip (stores do not allocate in L1): the
+    // kernel waited on them 8 cycles out of 9.  The working row lives in shared memory (odd pitch: conflict-free) and
+    // goes out in one coalesced pass at the end.
+    extern __shared__ double sRows[];
+    if (a.rows_in_smem) {
+        const long b0 = blockIdx.x * (long)blockDim.x;
+        const int nrow = (int)min((long)blockDim.x, a.B - b0);
+        if (b < a.B) prologue_row(prog, a, b, sRows + (size_t)threadIdx.x * prog.row);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nrow * prog.row; i += blockDim.x) a.Pext[b0 * prog.row + i] = sRows[i];
+        return;
+    }
+#endif
     if (b >= a.B) return;
-    double* P = a.Pext + b * prog.row;
+    prologue_row(prog, a, b, a.Pext + b * prog.row);
+}
+
+__device__ __forceinline__ void prologue_row(const ProgramDev& prog, const PrologueArgs& a, long b, double* P) {
     for (int i = 0; i < prog.n_params; ++i) P[i] = a.defaults[i];
     for (int i = 0; i < prog.n_free; ++i) P[a.free_idx[i]] = a.params[b * prog.n_free + i];
     double* D = P + prog.n_params;
