@@ -396,3 +396,150 @@ def test_wideband_dm_residuals(vb, oracle):
         assert abs(float(mp.mpf(y[n + j]) - want)) < 1e-12 * abs(float(want)) + 1e-3, (j, y[n + j], float(want))
         var = (mp.mpf(dms[j][1]) ** 2 + mp.mpf(5e10) ** 2) * mp.mpf(1.3) ** 2
         assert abs(float(mp.mpf(w[n + j]) * var - 1)) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------ the remaining delay components
+def test_wavex_family_and_chromatic_taylor(vb, oracle):
+    """wavex.jl:20-106 (WaveX, DMWaveX, CMWaveX: sum a sin(2 pi f (t - epoch)) + b cos(...)), chromatic.jl:10-34 (delay =
+    slope (1 MHz / nu)^TNCHROMIDX), component.jl:70-79 (DM delay = slope / nu^2), nu the doppler-corrected frequency; every
+    component sees the TOA corrected by the delays before it (timing_model.jl:85-109)."""
+    M = vb.model
+    single = dict(SS_EQ, WXEPOCH=10.0 * DAY, DMWXEPOCH=-20.0 * DAY, CMWXEPOCH=35.0 * DAY, CMEPOCH=5.0 * DAY, TNCHROMIDX=3.7)
+    multi = dict(WXSIN_=(3e-6, -1e-6), WXCOS_=(-2e-6, 4e-7), WXFREQ_=(1.0 / (400 * DAY), 1.0 / (173 * DAY)),
+                 DMWXSIN_=(2e12, 5e11), DMWXCOS_=(-1e12, 3e11), DMWXFREQ_=(1.0 / (500 * DAY), 1.0 / (91 * DAY)),
+                 CMWXSIN_=(4e5, -2e5), CMWXCOS_=(1e5, 3e5), CMWXFREQ_=(1.0 / (350 * DAY), 1.0 / (120 * DAY)),
+                 CM=(2e6, 3e-3, -1e-10))
+    comps = [M.SolarSystem(False, False), M.WaveX(), M.DMWaveX(), M.CMWaveX(), M.ChromaticTaylor()]
+    model, toas = mini_model(vb, comps, single, multi)
+    dly, dop, _, _ = oracle_delay_doppler(vb, oracle, model, toas)
+    p = P(single)
+    two_pi = 2 * mp.pi
+
+    def series(t, pre, epoch):
+        k = two_pi * (t - epoch)
+        return sum(mp.mpf(a) * mp.sin(k * mp.mpf(f)) + mp.mpf(b) * mp.cos(k * mp.mpf(f))
+                   for a, b, f in zip(multi[pre + "SIN_"], multi[pre + "COS_"], multi[pre + "FREQ_"]))
+
+    want = []
+    for t in T_TOAS:
+        t = mp.mpf(t)
+        d, dop0, _ = solar_system(t, p, False, False)
+        nu = mp.mpf(2.5e9) * (1 - dop0)
+        d += series(t - d, "WX", p["WXEPOCH"])
+        d += series(t - d, "DMWX", p["DMWXEPOCH"]) / nu**2
+        d += series(t - d, "CMWX", p["CMWXEPOCH"]) * (mp.mpf(1e6) / nu) ** p["TNCHROMIDX"]
+        d += taylor_horner((t - d) - p["CMEPOCH"], multi["CM"]) * (mp.mpf(1e6) / nu) ** p["TNCHROMIDX"]
+        want.append((d, dop0))
+    _check(dly, dop, want, tol_d=5e-13)
+
+
+def test_fd_fdjump_dmx_cmx_swx(vb, oracle):
+    """frequency_dependent.jl:22-81 (sum FD_p log(nu / 1 GHz)^p, FDJUMPs with a BitMatrix and per-jump exponents),
+    dispersion.jl:43-54 (DMX), chromatic.jl:46-57 (CMX), solarwind.jl:72-91 (SWX: DM scaled between the opposition and
+    conjunction geometries)."""
+    M = vb.model
+    n = len(T_TOAS)
+    single = dict(SS_ECL, TNCHROMIDX=4.4)
+    multi = dict(FD=(1e-5, -3e-6, 2e-7), FDJUMP=(4e-6, -2e-6, 1e-6), DMX_=(3e13, -2e13), CMX_=(5e6, -1e6, 2e6), SWXDM_=(7e12, 4e12))
+    fdmask = np.array([[1, 0, 1, 1, 0, 0, 1], [0, 1, 1, 0, 0, 1, 0], [1, 1, 0, 0, 1, 0, 0]], dtype=bool)
+    fdexp = np.array([1, 2, 3], dtype=np.uint64)
+    dmx = np.array([1, 2, 0, 1, 2, 0, 1], dtype=np.uint32)
+    cmx = np.array([0, 3, 2, 1, 0, 2, 3], dtype=np.uint32)
+    swx = np.array([2, 0, 1, 1, 2, 0, 1], dtype=np.uint32)
+    conj, opp = 37.5, 0.0021
+    comps = [M.SolarSystem(True, True), M.FrequencyDependent(), M.FrequencyDependentJump(fdmask, fdexp), M.DispersionPiecewise(dmx),
+             M.ChromaticPiecewise(cmx), M.SolarWindDispersionPiecewise(swx, conj, opp)]
+    model, toas = mini_model(vb, comps, single, multi)
+    dly, dop, _, _ = oracle_delay_doppler(vb, oracle, model, toas)
+    p = P(single)
+    rv = [mp.mpf(v) for v in EPHEM["obs_sun_pos"]]
+    r = mp.sqrt(sum(a * a for a in rv))
+    want = []
+    for j, t in enumerate(T_TOAS):
+        t = mp.mpf(t)
+        d, dop0, L = solar_system(t, p, True, True)
+        nu = mp.mpf(2.5e9) * (1 - dop0)
+        lam = mp.log(nu / mp.mpf(1e9))
+        d += sum(mp.mpf(fd) * lam ** (q + 1) for q, fd in enumerate(multi["FD"]))
+        d += sum(mp.mpf(fj) * lam ** int(e) for fj, e, m in zip(multi["FDJUMP"], fdexp, fdmask[:, j]) if m)
+        if dmx[j]:
+            d += mp.mpf(multi["DMX_"][dmx[j] - 1]) / nu**2
+        if cmx[j]:
+            d += mp.mpf(multi["CMX_"][cmx[j] - 1]) * (mp.mpf(1e6) / nu) ** p["TNCHROMIDX"]
+        if swx[j]:
+            rho = mp.acos(-sum(a * b for a, b in zip(L, rv)) / r)
+            geometry = AU * AU * rho / (r * mp.sin(rho))
+            d += mp.mpf(multi["SWXDM_"][swx[j] - 1]) * (geometry - mp.mpf(opp)) / (mp.mpf(conj) - mp.mpf(opp)) / nu**2
+        want.append((d, dop0))
+    _check(dly, dop, want, tol_d=5e-13)
+
+
+def test_exponential_dips(vb, oracle):
+    """expdip.jl:11-31: -A (f / fref)^gamma (tau / eps)^(eps / tau) (tau / (tau - eps))^((tau - eps) / tau)
+    exp(-dt / tau) / (1 + exp(-dt / eps)), summed over the dips, f the doppler-corrected frequency."""
+    M = vb.model
+    single = dict(SS_EQ, EXPDIPFREF=1.4e9, EXPDIPEPS=0.7 * DAY)
+    multi = dict(EXPDIPEP_=(-500.0 * DAY, 100.0 * DAY), EXPDIPAMP_=(3e-6, 8e-7), EXPDIPIDX_=(-2.0, -4.1), EXPDIPTAU_=(60.0 * DAY, 25.0 * DAY))
+    model, toas = mini_model(vb, [M.SolarSystem(False, False), M.ChromaticExponentialDip()], single, multi)
+    dly, dop, _, _ = oracle_delay_doppler(vb, oracle, model, toas)
+    p = P(single)
+    want = []
+    for t in T_TOAS:
+        t = mp.mpf(t)
+        d, dop0, _ = solar_system(t, p, False, False)
+        f = mp.mpf(2.5e9) * (1 - dop0)
+        eps = p["EXPDIPEPS"]
+        tot = mp.mpf(0)
+        for T, A, g, tau in zip(*(multi[k] for k in ("EXPDIPEP_", "EXPDIPAMP_", "EXPDIPIDX_", "EXPDIPTAU_"))):
+            T, A, g, tau = mp.mpf(T), mp.mpf(A), mp.mpf(g), mp.mpf(tau)
+            dt = (t - d) - T
+            tot += -A * (f / p["EXPDIPFREF"]) ** g * (tau / eps) ** (eps / tau) * (tau / (tau - eps)) ** ((tau - eps) / tau) \
+                * mp.exp(-dt / tau) / (1 + mp.exp(-dt / eps))
+        want.append((d + tot, dop0))
+    _check(dly, dop, want, tol_d=5e-13)
+
+
+# ------------------------------------------------------------------------------------------------ phase components
+def test_glitch_offset_and_jumps_in_phase(vb, oracle):
+    """glitch.jl:14-38, phase_offset.jl:12-13, jump.jl:14-45.  The phase components are read off as the DIFFERENCE of the
+    oracle's Double64 phase residuals with and without them (same delays, same spin-down), so the comparison is at the
+    1e-12-cycle level although the phases themselves are ~1e10 cycles.  The TZR TOA (5 d after the epoch) lies before both
+    glitches and is exempt from PHOFF and JUMPs by definition, so its phase is common to both evaluations."""
+    M = vb.model
+    n = len(T_TOAS)
+    ex = np.array([1, 0, 2, 2, 0, 1, 0], dtype=np.uint32)
+    bits = np.array([[1, 1, 0, 0, 1, 0, 1], [0, 1, 1, 0, 0, 0, 1]], dtype=bool)
+    gl = dict(GLEP_=(30.0 * DAY, 400.5 * DAY), GLPH_=(0.013, -0.2), GLF0_=(2e-7, -5e-8), GLF1_=(-3e-15, 1e-15),
+              GLF2_=(1e-23, 0.0), GLF0D_=(4e-8, 1e-8), GLTD_=(20.0 * DAY, 150.0 * DAY))
+
+    def phases(with_terms):
+        z = 1.0 if with_terms else 0.0
+        single = dict(SS_EQ, PHOFF=0.123456 * z)
+        multi = dict({k: (tuple(np.array(v) * z) if k not in ("GLEP_", "GLTD_") else v) for k, v in gl.items()},
+                     JUMP=(3e-6 * z, -7e-6 * z))
+        # (one JUMP vector of two entries serves both jump components of this test model: index mask and 2-row BitMatrix)
+        comps = [M.SolarSystem(False, False), M.Glitch(), M.PhaseOffset(), M.ExclusivePhaseJump(ex), M.PhaseJump(bits[:, :n])]
+        model, toas = mini_model(vb, comps, single, multi)
+        md = vb.ModelDescriptor(model, toas)
+        hi, lo, f, dly, _ = oracle.phases(md, model.read_param_values_to_vector())
+        return np.asarray(hi), np.asarray(lo), np.asarray(dly)
+
+    h1, l1, d1 = phases(True)
+    h0, l0, d0 = phases(False)
+    np.testing.assert_array_equal(d1, d0)                       # phase components leave the delay alone
+    got = (h1 - h0) + (l1 - l0)
+    F0tot = mp.mpf(100.0)                                       # F_ + F0 of mini_model
+    jump = [mp.mpf(v) for v in (3e-6, -7e-6)]
+    for j, t in enumerate(T_TOAS):
+        tc = mp.mpf(t) - mp.mpf(float(d1[j]))
+        want = mp.mpf(0)
+        for tg, ph, f0, f1, f2, fd, td in zip(*(gl[k] for k in ("GLEP_", "GLPH_", "GLF0_", "GLF1_", "GLF2_", "GLF0D_", "GLTD_"))):
+            tg, ph, f0, f1, f2, fd, td = (mp.mpf(v) for v in (tg, ph, f0, f1, f2, fd, td))
+            if not tc < tg:
+                dt = tc - tg
+                want += ph + dt * (f0 + dt * f1 / 2 + dt * dt * f2 / 6) + fd * td * (1 - mp.exp(-dt / td))
+        want += -mp.mpf(0.123456)
+        if ex[j]:
+            want += jump[ex[j] - 1] * F0tot
+        want += sum(jump[g] for g in range(2) if bits[g, j]) * F0tot
+        assert abs(float(mp.mpf(float(got[j])) - want)) < 2e-12 + 1e-13 * abs(float(want)), (j, got[j], float(want))

@@ -129,10 +129,13 @@ class ModelDescriptor:
             index_masks.append(mask)
             return len(index_masks) - 1
 
-        def add_bit_mask(mask) -> int:
+        def add_bit_mask(mask, n_amplitudes=None) -> int:
             mask = np.asarray(mask).astype(np.uint8)
             if mask.ndim != 2 or mask.shape[1] != ntoa:
                 raise ValueError(f"bit mask has shape {mask.shape}, expected (njump, {ntoa})")
+            # the reference contracts the amplitude vector with a mask column (jump.jl:14-22: dot of equal lengths)
+            if n_amplitudes is not None and mask.shape[0] != n_amplitudes:
+                raise ValueError(f"bit mask has {mask.shape[0]} rows for {n_amplitudes} amplitudes")
             first = len(bit_rows)
             bit_rows.extend(list(mask))
             return first
@@ -273,7 +276,7 @@ class ModelDescriptor:
                 excl = isinstance(comp, M.ExclusiveDispersionOffset)
                 c = new(COMP_DM_OFFSET_EXCLUSIVE if excl else COMP_DM_OFFSET)
                 setp(c, 0, "FDJUMPDM", 0)
-                c.mask[0] = add_index_mask(comp.jump_mask) if excl else add_bit_mask(comp.jump_mask)
+                c.mask[0] = add_index_mask(comp.jump_mask) if excl else add_bit_mask(comp.jump_mask, c.len[0])
             elif isinstance(comp, M.Glitch):
                 c = new(COMP_GLITCH)
                 for s, nme in enumerate(("GLEP_", "GLPH_", "GLF0_", "GLF1_", "GLF2_", "GLF0D_", "GLTD_")):
@@ -297,7 +300,7 @@ class ModelDescriptor:
                 setp(c, 0, "JUMP", 0)
                 setp(c, 1, "F_")
                 setp(c, 2, "F")
-                c.mask[0] = add_index_mask(comp.jump_mask) if excl else add_bit_mask(comp.jump_mask)
+                c.mask[0] = add_index_mask(comp.jump_mask) if excl else add_bit_mask(comp.jump_mask, c.len[0])
             elif isinstance(comp, M.MeasurementNoise):
                 c = new(COMP_MEASUREMENT_NOISE)
                 setp(c, 0, "EFAC", 0, required=False)
@@ -308,7 +311,7 @@ class ModelDescriptor:
                 excl = isinstance(comp, M.ExclusiveDispersionJump)
                 c = new(COMP_DM_JUMP_EXCLUSIVE if excl else COMP_DM_JUMP)
                 setp(c, 0, "DMJUMP", 0)
-                c.mask[0] = add_index_mask(comp.jump_mask) if excl else add_bit_mask(comp.jump_mask)
+                c.mask[0] = add_index_mask(comp.jump_mask) if excl else add_bit_mask(comp.jump_mask, c.len[0])
             elif isinstance(comp, M.DispersionMeasurementNoise):
                 c = new(COMP_DM_MEASUREMENT_NOISE)
                 setp(c, 0, "DMEFAC", 0, required=False)
