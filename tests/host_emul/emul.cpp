@@ -13,6 +13,31 @@
 
 using namespace vela;
 
+// kFlagDelta (vela_device.cuh): fills the C_DELTA columns of the SoA table and the TZR spin phase at the default parameters
+// the way create() does on the device - prologue for the default vector, then default_phase_point per TOA.
+static bool prepare_delta(const VelaModelDesc* desc, const ProgramDev& pg, std::vector<double>& soa, long stride,
+                          const std::vector<double>& tzr, const std::vector<double>& defaults, const std::vector<int>& free_idx,
+                          double* tzr0) {
+    bool want = false;
+    for (int ic = 0; ic < pg.n_comp; ++ic) want = want || (pg.comp[ic].flags & kFlagDelta);
+    if (!want) return false;
+    const long nt = desc->n_toas;
+    std::vector<double> x0((size_t)std::max(desc->n_free, 1), 0.0), P0((size_t)pg.row, 0.0), tz(2, 0.0);
+    for (int i = 0; i < desc->n_free; ++i) x0[i] = desc->default_values[desc->free_indices[i]];
+    PrologueArgs pa;
+    pa.defaults = defaults.data(); pa.free_idx = free_idx.data(); pa.params = x0.data(); pa.B = 1;
+    pa.tzr_block = tzr.data(); pa.index_masks = desc->index_masks; pa.bit_masks = desc->bit_masks; pa.n_toas = nt;
+    pa.Pext = P0.data(); pa.tzr_phase = tz.data(); pa.rows_in_smem = 0; pa.tzr0 = nullptr;
+    blockIdx = {0, 0, 0}; blockDim = {1, 1, 1}; threadIdx = {0, 0, 0};
+    prologue_body(pg, pa);
+    for (long j = 0; j < nt; ++j) {
+        double out3[3];
+        default_phase_point(pg, P0.data(), soa.data(), stride, j, tzr.data(), desc->index_masks, desc->bit_masks, nt, out3, tzr0);
+        for (int c = 0; c < 3; ++c) soa[(size_t)(C_DELTA + c) * stride + j] = out3[c];
+    }
+    return true;
+}
+
 extern "C" __attribute__((visibility("default")))
 int emul_chain(const VelaModelDesc* desc, const double* params, long B, int emit, int fast, double* Y, double* W, double* F,
                double* chi2, double* logdetN) {
@@ -32,11 +57,13 @@ int emul_chain(const VelaModelDesc* desc, const double* params, long B, int emit
     if (desc->n_aux > 0) defaults.insert(defaults.end(), desc->aux_values, desc->aux_values + desc->n_aux);
     std::vector<int> free_idx(desc->free_indices, desc->free_indices + desc->n_free);
     std::vector<double> Pext((size_t)B * pg.row, 0.0), tzr_phase((size_t)B * 2, 0.0);
+    double tzr0[2] = {0.0, 0.0};
+    const bool delta = prepare_delta(desc, pg, soa, stride, tzr, defaults, free_idx, tzr0);
 
     PrologueArgs pa;
     pa.defaults = defaults.data(); pa.free_idx = free_idx.data(); pa.params = params; pa.B = B;
     pa.tzr_block = tzr.data(); pa.index_masks = desc->index_masks; pa.bit_masks = desc->bit_masks; pa.n_toas = nt;
-    pa.Pext = Pext.data(); pa.tzr_phase = tzr_phase.data(); pa.rows_in_smem = 0;
+    pa.Pext = Pext.data(); pa.tzr_phase = tzr_phase.data(); pa.rows_in_smem = 0; pa.tzr0 = delta ? tzr0 : nullptr;
     blockIdx = {0, 0, 0}; blockDim = {1, 1, 1};
     for (long b = 0; b < B; ++b) {
         threadIdx = {(unsigned)b, 0, 0};
@@ -50,7 +77,8 @@ int emul_chain(const VelaModelDesc* desc, const double* params, long B, int emit
             ChainEnv e;
             e.toa_base = soa.data(); e.stride = stride; e.j = j;
             e.index_masks = desc->index_masks; e.bit_masks = desc->bit_masks; e.n_toas = nt;
-            e.tzr = false; e.wide = desc->wideband != 0;
+            e.tzr = false; e.wide = desc->wideband != 0; e.delta = delta && emit != 2;
+            for (int c = 0; c < 3; ++c) e.d0[c] = e.delta ? soa[(size_t)(C_DELTA + c) * stride + j] : 0.0;
             Corr k = run_chain(pg, P, t, e);
             ResidTerms r = residual_terms(k, t, e.wide, tzr_phase[2 * b], tzr_phase[2 * b + 1], emit);
             chi += r.chi;
@@ -95,10 +123,12 @@ int emul_spec_check(const VelaModelDesc* desc, const double* params, long B, int
     if (desc->n_aux > 0) defaults.insert(defaults.end(), desc->aux_values, desc->aux_values + desc->n_aux);
     std::vector<int> free_idx(desc->free_indices, desc->free_indices + desc->n_free);
     std::vector<double> Pext((size_t)B * pg.row, 0.0), tzr_phase((size_t)B * 2, 0.0);
+    double tzr0[2] = {0.0, 0.0};
+    const bool delta = prepare_delta(desc, pg, soa, stride, tzr, defaults, free_idx, tzr0);
     PrologueArgs pa;
     pa.defaults = defaults.data(); pa.free_idx = free_idx.data(); pa.params = params; pa.B = B;
     pa.tzr_block = tzr.data(); pa.index_masks = desc->index_masks; pa.bit_masks = desc->bit_masks; pa.n_toas = nt;
-    pa.Pext = Pext.data(); pa.tzr_phase = tzr_phase.data(); pa.rows_in_smem = 0;
+    pa.Pext = Pext.data(); pa.tzr_phase = tzr_phase.data(); pa.rows_in_smem = 0; pa.tzr0 = delta ? tzr0 : nullptr;
     blockIdx = {0, 0, 0}; blockDim = {1, 1, 1};
     for (long b = 0; b < B; ++b) {
         threadIdx = {(unsigned)b, 0, 0};
@@ -113,7 +143,8 @@ int emul_spec_check(const VelaModelDesc* desc, const double* params, long B, int
             ChainEnv e;
             e.toa_base = soa.data(); e.stride = stride; e.j = j;
             e.index_masks = desc->index_masks; e.bit_masks = desc->bit_masks; e.n_toas = nt;
-            e.tzr = false; e.wide = desc->wideband != 0;
+            e.tzr = false; e.wide = desc->wideband != 0; e.delta = delta && emit != 2;
+            for (int c = 0; c < 3; ++c) e.d0[c] = e.delta ? soa[(size_t)(C_DELTA + c) * stride + j] : 0.0;
             Corr ks = run_chain(pg, P, t, e, true);
             ResidTerms rs = residual_terms(ks, t, e.wide, tzr_phase[2 * b], tzr_phase[2 * b + 1], emit);
             Corr kb = run_chain(pg, P, t, e, false);

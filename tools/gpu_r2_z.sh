@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, GPU call Z: speculative straight-line chain (default) vs branching chain, all configs; full GPU suite.
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_jit.py tests/test_gpu_synth.py tests/test_gpu_fixtures.py -m gpu -q --maxfail=15 > gpurun_out/z_tests.log 2>&1; echo "tests rc $?" >> gpurun_out/z_tests.log
+timeout 1200 python -m pytest tests -m gpu -q --maxfail=15 > gpurun_out/z_tests.log 2>&1; echo "tests rc $?" >> gpurun_out/z_tests.log
 tail -4 gpurun_out/z_tests.log
 run() { tag=$1; cfg=$2; shift 2; env "$@" timeout 300 python tools/probes/gpu_stage_probe.py $cfg 2>&1 | tail -1 | cut -c1-150 | sed "s/^/[$tag] /"; }
 {

@@ -109,6 +109,7 @@ struct DeviceModel {
     unsigned* ltab = nullptr;       // chol_warp_kernel layout table (ranks <= 63 on the structured path)
     unsigned* ftab = nullptr;       // chol_dmma_kernel fragment table (ranks <= 64 on the structured path)
     unsigned* ctab = nullptr;       // compact pair table (4 bytes per pair) of the structured path
+    double* tzr0 = nullptr;         // kFlagDelta: Double64 spin phase of the TZR TOA at the default parameters (2 doubles)
     GPDev* gp = nullptr;
     double* gp_data = nullptr;
     int3* ecorr_groups = nullptr;
@@ -190,6 +191,7 @@ struct VelaPulsar {
     std::vector<unsigned> ltab;      // layout table of chol_warp_kernel; empty = that kernel is not used
     std::vector<unsigned> ftab;      // fragment table of chol_dmma_kernel; empty = not available
     std::vector<unsigned> ctab;      // compact pair table; empty = some coefficient / index does not fit the 4-byte code
+    bool delta_ready = false;        // the C_DELTA columns of every device's TOA table are filled (kFlagDelta in use)
     int chol_nb = 8;                 // block width of the Cholesky kernel
     size_t chol_smem_bytes = 0;
     std::vector<DeviceModel> devs;
@@ -593,6 +595,7 @@ void launch_prologue(VelaPulsar* h, DeviceModel& d, const double* d_params, long
     PrologueArgs pa;
     pa.defaults = d.defaults; pa.free_idx = d.free_idx; pa.params = d_params; pa.B = B; pa.tzr_block = d.tzr_block;
     pa.index_masks = d.index_masks; pa.bit_masks = d.bit_masks; pa.n_toas = h->n_toas; pa.Pext = d.buf.Pext; pa.tzr_phase = d.buf.tzr;
+    pa.tzr0 = h->delta_ready ? d.tzr0 : nullptr;
     int threads = B >= 4096 ? 128 : 32;          // small batches: spread the walkers over more SMs
     // working rows in shared memory while they fit the default 48 KB (config 3: 45 doubles per row); longer rows (free-
     // amplitude GPs with hundreds of hoisted factors) take narrower blocks, or the global row
@@ -612,6 +615,7 @@ void launch_prologue(VelaPulsar* h, DeviceModel& d, const double* d_params, long
 
 // K1 launch: the NVRTC-specialised kernel of this model when it exists and is enabled, else the generic interpreter
 void launch_chain(VelaPulsar* h, dim3 grid, size_t smem, cudaStream_t st, ChainArgs& ca) {
+    ca.delta = (h->delta_ready && ca.emit != 2) ? 1 : 0;   // phase mode returns Double64 itself
     if (h->use_spec && h->spec_chain && ca.emit == h->spec_emit) {   // other modes (single-sample residuals / phases): generic kernel
         void* args[] = {&ca};
         cudaLaunchKernel((const void*)h->spec_chain, grid, dim3((unsigned)h->chain_threads), args, smem, st);
@@ -813,7 +817,7 @@ void destroy_device(DeviceModel& d) {
     if (d.buf.h_params) cudaFreeHost(d.buf.h_params);
     if (d.buf.h_out) cudaFreeHost(d.buf.h_out);
     if (d.buf.h_lnprior) cudaFreeHost(d.buf.h_lnprior);
-    cudaFree(d.T); cudaFree(d.table); cudaFree(d.A1); cudaFree(d.T2); cudaFree(d.units2); cudaFree(d.ltab); cudaFree(d.ftab); cudaFree(d.ctab);
+    cudaFree(d.T); cudaFree(d.table); cudaFree(d.A1); cudaFree(d.T2); cudaFree(d.units2); cudaFree(d.ltab); cudaFree(d.ftab); cudaFree(d.ctab); cudaFree(d.tzr0);
     cudaFree(d.toa); cudaFree(d.tzr_block); cudaFree(d.index_masks); cudaFree(d.bit_masks); cudaFree(d.defaults);
     cudaFree(d.free_idx); cudaFree(d.M); cudaFree(d.gp); cudaFree(d.gp_data); cudaFree(d.ecorr_groups); cudaFree(d.ecorr_chunks); cudaFree(d.ecorr_active); cudaFree(d.priors);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -833,6 +837,11 @@ std::string spec_source(const ProgramDev& pg, int min_blocks = 2, int threads = 
     // fast-arithmetic build: speculative straight-line evaluation with a warp-uniform re-evaluation (Corr::spec)
     if ((pg.comp[0].flags & kFlagFast) && !(getenv("VELA_B200_JIT_SPECULATE") && atoi(getenv("VELA_B200_JIT_SPECULATE")) == 0))
         src += "#define VELA_SPEC_SPECULATE 1\n";
+    {   // kFlagDelta in the program <=> create() filled the C_DELTA columns; residual-emitting batches then always take the route
+        bool delta = false;
+        for (int ic = 0; ic < pg.n_comp; ++ic) delta = delta || (pg.comp[ic].flags & kFlagDelta);
+        src += (delta && emit >= 0 && emit != 2) ? "#define VELA_SPEC_DELTA 1\n" : "#define VELA_SPEC_DELTA 0\n";
+    }
     if (emit >= 0) {   // the emit mode of the handle's batches, folded into the kernel (launch_chain checks it)
         snprintf(buf, sizeof buf, "#define VELA_SPEC_EMIT %d\n", emit);
         src += buf;
@@ -1145,6 +1154,29 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
     std::vector<double>().swap(h->sp.T);   // the device copies are authoritative from here on
     std::vector<double>().swap(h->sp.A1);
     std::vector<double>().swap(h->sp.T2);
+
+    // kFlagDelta: the chain at the default parameters fills the C_DELTA columns of every device's TOA table
+    {
+        bool want = false;
+        for (int ic = 0; ic < pg.n_comp; ++ic) want = want || (pg.comp[ic].flags & kFlagDelta);
+        bool ok = want;
+        std::vector<double> x0((size_t)std::max(desc->n_free, 1), 0.0);
+        for (int i = 0; i < desc->n_free; ++i) x0[i] = desc->default_values[desc->free_indices[i]];
+        for (size_t i = 0; ok && i < h->devs.size(); ++i) {
+            DeviceModel& d = h->devs[i];
+            cudaSetDevice(d.dev);
+            ok = ensure_device_buffers(h, d, 1) == 0 && cudaMalloc((void**)&d.tzr0, 2 * sizeof(double)) == cudaSuccess;
+            if (!ok) break;
+            cudaMemcpyAsync(d.buf.params, x0.data(), sizeof(double) * x0.size(), cudaMemcpyHostToDevice, d.stream);
+            launch_prologue(h, d, d.buf.params, 1, d.stream);      // (delta_ready is still false: plain rows)
+            default_phase_kernel<<<(unsigned)((h->n_toas + 127) / 128), 128, 0, d.stream>>>(
+                h->prog, d.buf.Pext, d.toa, d.toa_stride, h->n_toas, d.tzr_block, d.index_masks, d.bit_masks, d.tzr0);
+            ok = cudaStreamSynchronize(d.stream) == cudaSuccess;
+        }
+        cudaSetDevice(prev);
+        if (want && !ok) { cudaGetLastError(); for (int ic = 0; ic < pg.n_comp; ++ic) h->prog.comp[ic].flags &= ~kFlagDelta; }
+        h->delta_ready = want && ok;
+    }
 
     // per-model chain kernel (vela_jit.cu); any failure leaves the generic kernel in charge
     {
@@ -1830,7 +1862,9 @@ VELA_API int64_t vela_b200_debug_spec_compile(const VelaModelDesc* desc) {
     std::string log;
     int mb = 5;
     if (const char* f = getenv("VELA_B200_JIT_MINBLOCKS")) mb = std::max(1, std::min(16, atoi(f)));
-    if (jit_compile_cubin(spec_source(pg, mb, 128), cubin, log)) return fail(VELA_ERR_UNSUPPORTED, "%s", log.c_str());
+    // tooling: VELA_B200_DEBUG_EMIT=<mode> compiles the build create() makes for a handle of that emit mode
+    const int emit = getenv("VELA_B200_DEBUG_EMIT") ? atoi(getenv("VELA_B200_DEBUG_EMIT")) : -1;
+    if (jit_compile_cubin(spec_source(pg, mb, 128, emit), cubin, log)) return fail(VELA_ERR_UNSUPPORTED, "%s", log.c_str());
     g_last_error = log;   // ptxas statistics of the successful build, readable through vela_b200_last_error()
     return (int64_t)cubin.size();
 }

@@ -25,6 +25,7 @@ struct ChainArgs {
     double* F;                 // emit == 2 only
     long ld_yw;
     double* partial;           // [tiles][B][2]
+    int delta;                 // the C_DELTA columns of the TOA table are filled and the launch wants residuals (emit != 2)
 };
 
 struct PrologueArgs {
@@ -39,11 +40,25 @@ struct PrologueArgs {
     double* Pext;              // [B][row]
     double* tzr_phase;         // [B][2]
     int rows_in_smem;          // 1: the launch carries blockDim.x * row doubles of dynamic shared memory for the working rows
+    const double* tzr0;        // Double64 spin phase of the TZR TOA at the default parameters (kFlagDelta), or null
 };
 
 // K0 body: read_params (parameter.jl:158-169) + per-walker hoists + calc_tzr_phase (residuals.jl:29-32); one thread
 // per walker.  Shared by the generic kernel and the per-model NVRTC build like chain_body below.
 __device__ __forceinline__ void prologue_row(const ProgramDev& prog, const PrologueArgs& a, long b, double* P);
+// Spindown with kFlagDelta: derived slots 2 (TZR phase minus its default-parameter value) and 3.. (dF_n); a no-op for every
+// other component (folded away in the per-model build).
+__device__ __forceinline__ void fill_delta_slots(const CompDev& c, const double* P, double* Ds, const double* defaults,
+                                                 const double* tzr0, dd ph, bool bad) {
+    if (c.kind != VELA_COMP_SPINDOWN || !(c.flags & kFlagDelta)) return;
+    const int nf = c.len[0];
+    const dd s0 = two_sum(defaults[c.par[0]], nf > 0 ? defaults[c.par[1]] : 0.0);
+    const dd ds = dd_sub(dd{Ds[0], Ds[1]}, s0);
+    Ds[3] = ds.hi + ds.lo;
+    for (int n = 1; n < nf; ++n) Ds[3 + n] = P[c.par[1] + n] - defaults[c.par[1] + n];
+    const dd dz = tzr0 ? dd_sub(ph, dd{tzr0[0], tzr0[1]}) : dd{CUDART_NAN, 0.0};
+    Ds[2] = bad ? CUDART_NAN : dz.hi + dz.lo;
+}
 __device__ __forceinline__ void prologue_body(const ProgramDev& prog, const PrologueArgs& a) {
     long b = blockIdx.x * (long)blockDim.x + threadIdx.x;
 #ifndef VELA_HOST_EMUL
@@ -80,13 +95,21 @@ __device__ __forceinline__ void prologue_row(const ProgramDev& prog, const Prolo
     ChainEnv e;
     e.toa_base = a.tzr_block; e.stride = 1; e.j = 0;
     e.index_masks = a.index_masks; e.bit_masks = a.bit_masks; e.n_toas = a.n_toas;
-    e.tzr = true; e.wide = false;
+    e.tzr = true; e.wide = false; e.delta = false; e.d0[0] = e.d0[1] = e.d0[2] = 0.0;
     // the TZR block is laid out column-after-column with stride 1 (C_NCOL doubles)
     ToaRegs t = load_toa(a.tzr_block, 1, 0, false);
     Corr k = run_chain(prog, P, t, e);
     const dd ph = dd_add_d(k.phase, k.phase_small);
     a.tzr_phase[2 * b] = k.bad ? CUDART_NAN : ph.hi;
     a.tzr_phase[2 * b + 1] = ph.lo;
+    // kFlagDelta: this walker's spin parameters and TZR phase as differences from the default-parameter values
+#ifdef VELA_SPEC_CALLS
+#define VELA_APPLY(i) fill_delta_slots(prog.comp[i], P, D + prog.comp[i].der, a.defaults, a.tzr0, ph, k.bad);
+    VELA_SPEC_CALLS
+#undef VELA_APPLY
+#else
+    for (int ic = 0; ic < prog.n_comp; ++ic) fill_delta_slots(prog.comp[ic], P, D + prog.comp[ic].der, a.defaults, a.tzr0, ph, k.bad);
+#endif
 }
 
 // frexp for the log-det accumulation: normal positive inputs (every sane err^2) are split with three integer
@@ -138,6 +161,8 @@ __device__ __forceinline__ ResidTerms residual_terms(const Corr& k, const ToaReg
         dphase = dd_sub(dphase, dd{tzr_hi, tzr_lo});
         r.dphase = dphase;
         tres_phase = dphase.hi;
+    } else if (k.delta) {   // kFlagDelta: (phase - pulse number) - TZR phase arrived as one residual-sized double
+        tres_phase = k.dph + k.phase_small;
     } else {
         const dd lead = two_sum(k.phase.hi, -tzr_hi);
         const double tail = ((k.phase.lo - tzr_lo) + lead.lo) + (k.phase_small - t.pn_lo);
@@ -178,6 +203,30 @@ __device__ __forceinline__ ResidTerms residual_terms(const Corr& k, const ToaReg
     }
     if (k.bad || k.spin_frequency == 0.0) r.chi = CUDART_NAN;
     return r;
+}
+
+// create(): the C_DELTA columns of one TOA (kFlagDelta) from the chain at the DEFAULT parameters - P is the extended row
+// the prologue made of them.  tzr0: Double64 spin phase of the TZR TOA at those parameters (every thread computes it;
+// the caller keeps one copy for the prologue).  Same code as the per-walker evaluation, so delay0 is the very double a
+// walker sitting at the defaults would carry.
+__device__ inline void default_phase_point(const ProgramDev& prog, const double* P, const double* toa, long stride, long j,
+                                           const double* tzr_block, const uint32_t* index_masks, const uint8_t* bit_masks,
+                                           long n_toas, double* out3, double* tzr0) {
+    ChainEnv e;
+    e.index_masks = index_masks; e.bit_masks = bit_masks; e.n_toas = n_toas; e.wide = false; e.delta = false;
+    e.d0[0] = e.d0[1] = e.d0[2] = 0.0;
+    e.toa_base = tzr_block; e.stride = 1; e.j = 0; e.tzr = true;
+    const Corr kz = run_chain(prog, P, load_toa(tzr_block, 1, 0, false), e);
+    tzr0[0] = kz.phase.hi; tzr0[1] = kz.phase.lo;
+    e.toa_base = toa; e.stride = stride; e.j = j; e.tzr = false; e.wide = prog.wideband != 0;
+    const ToaRegs t = load_toa(toa, stride, j, false);
+    const Corr k = run_chain(prog, P, t, e);
+    const dd dt0 = dd_add_d(dd{t.t_hi, t.t_lo}, -k.delay);
+    const dd r0 = dd_sub(dd_sub(k.phase, dd{t.pn_hi, t.pn_lo}), kz.phase);
+    const bool bad = k.bad || kz.bad;
+    out3[0] = bad ? CUDART_NAN : k.delay;
+    out3[1] = dt0.hi;
+    out3[2] = r0.hi + r0.lo;
 }
 
 #ifndef VELA_HOST_EMUL   // the kernel body proper: warp shuffles and shared memory have no host stand-in
@@ -254,6 +303,15 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
     e.toa_base = a.toa; e.stride = a.toa_stride; e.j = jj;
     e.index_masks = a.index_masks; e.bit_masks = a.bit_masks; e.n_toas = a.n_toas;
     e.tzr = false; e.wide = prog.wideband != 0;
+#ifdef VELA_SPEC_DELTA   // per-model build: whether the handle's C_DELTA columns are filled and this emit mode takes residuals is a
+    e.delta = VELA_SPEC_DELTA != 0;   // compile-time fact
+#else
+    e.delta = a.delta != 0;
+#endif
+    // the three C_DELTA words ride in registers through the walker loop (as loads inside it they missed L1 - five CTAs'
+    // parameter rows leave it ~40 KB - and sat on the critical path: 0.95 ms against 0.87 without the route)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) e.d0[c] = e.delta ? __ldg(a.toa + (size_t)(C_DELTA + c) * a.toa_stride + jj) : 0.0;
     __syncthreads();
 
     // the launch's emit mode; the per-model build knows it at compile time (VELA_SPEC_EMIT), so the mode tests fold away
@@ -318,8 +376,14 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
     while (redo_mask) {
         const int s = __ffsll((long long)redo_mask) - 1;
         redo_mask &= redo_mask - 1;
-        const Corr k = run_chain(prog, sP + (size_t)s * row, t, e, false);
-        const ResidTerms r = residual_terms(k, t, e.wide, sTzr[2 * s], sTzr[2 * s + 1], emit);
+        ToaRegs tr = t;
+#if defined(VELA_SPEC_DELTA) && VELA_SPEC_DELTA   // the hot loop no longer reads the words of the double-double route: fetched here, they cost it no register
+        tr.t_lo = __ldg(a.toa + (size_t)C_T_LO * a.toa_stride + jj);
+        tr.pn_hi = __ldg(a.toa + (size_t)C_PN_HI * a.toa_stride + jj);
+        tr.pn_lo = __ldg(a.toa + (size_t)C_PN_LO * a.toa_stride + jj);
+#endif
+        const Corr k = run_chain(prog, sP + (size_t)s * row, tr, e, false);
+        const ResidTerms r = residual_terms(k, tr, e.wide, sTzr[2 * s], sTzr[2 * s + 1], emit);
         deposit(r, (size_t)(b0 + s) * a.ld_yw + j, 0);
         ring_reduce(rChi, rMan, rExp, 1, lane, wRed, s);
     }

@@ -60,6 +60,20 @@ inline void build_program(const VelaModelDesc* desc, ProgramDev& pg, bool fast =
         cd.der = nder;
         nder += derived_count(c.kind, c.len);
     }
+    // kFlagDelta (vela_device.cuh): spin phase as a difference from the default parameters - when Spindown is the model's
+    // only spin-phase component and nothing after it touches the delay
+    if (fast && !(getenv("VELA_B200_DELTA") && atoi(getenv("VELA_B200_DELTA")) == 0)) {
+        int isp = -1, nsp = 0;
+        for (int ic = 0; ic < pg.n_comp; ++ic) if (pg.comp[ic].kind == VELA_COMP_SPINDOWN) { isp = ic; ++nsp; }
+        bool ok = nsp == 1;
+        for (int ic = isp + 1; ok && ic < pg.n_comp; ++ic) {
+            const int kd = pg.comp[ic].kind;
+            ok = kd == VELA_COMP_PHASE_OFFSET || kd == VELA_COMP_PHASE_JUMP || kd == VELA_COMP_PHASE_JUMP_EXCLUSIVE ||
+                 kd == VELA_COMP_GLITCH || kd == VELA_COMP_MEASUREMENT_NOISE || kd == VELA_COMP_DM_MEASUREMENT_NOISE ||
+                 kd == VELA_COMP_DM_JUMP || kd == VELA_COMP_DM_JUMP_EXCLUSIVE;
+        }
+        if (ok) pg.comp[isp].flags |= kFlagDelta;
+    }
     pg.n_derived = nder;
     pg.row = pg.n_params + nder;
     if ((pg.row & 1) == 0) pg.row += 1;  // odd pitch: conflict-free column reads across rows

@@ -103,6 +103,19 @@ __global__ void __launch_bounds__(kChainThreads, 2) toa_chain_kernel(const __gri
     chain_body(prog, a);
 }
 
+// create(): one thread per TOA evaluates the chain at the default parameters (P: their extended row) and fills the C_DELTA
+// columns; thread 0 also stores the TZR TOA's spin phase (default_phase_point, vela_chain.cuh)
+__global__ void default_phase_kernel(const __grid_constant__ ProgramDev prog, const double* P, double* toa, long stride, long n_toas,
+                                     const double* tzr_block, const uint32_t* index_masks, const uint8_t* bit_masks, double* tzr0) {
+    const long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (j >= n_toas) return;
+    double out3[3], z[2];
+    default_phase_point(prog, P, toa, stride, j, tzr_block, index_masks, bit_masks, n_toas, out3, z);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) toa[(size_t)(C_DELTA + c) * stride + j] = out3[c];
+    if (j == 0) { tzr0[0] = z[0]; tzr0[1] = z[1]; }
+}
+
 // ------------------------------------------------------------------------------------------
 // K1b  white-noise finish: -sum/2 (wls_likelihood.jl:49-56) or chi^2 (wls_chi2.jl:44-51), + prior
 // ------------------------------------------------------------------------------------------

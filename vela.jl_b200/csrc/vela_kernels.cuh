@@ -177,6 +177,9 @@ struct CholArgs {
 
 __global__ void sample_prologue_kernel(const __grid_constant__ ProgramDev prog, PrologueArgs a);
 __global__ void toa_chain_kernel(const __grid_constant__ ProgramDev prog, ChainArgs a);
+// create(): C_DELTA columns of the TOA table and the TZR spin phase at the default parameters (kFlagDelta)
+__global__ void default_phase_kernel(const __grid_constant__ ProgramDev prog, const double* P, double* toa, long stride, long n_toas,
+                                     const double* tzr_block, const uint32_t* index_masks, const uint8_t* bit_masks, double* tzr0);
 __global__ void prior_kernel(const PriorDev* priors, int nd, const double* params, long B, int mode, double* out);
 __global__ void ecorr_group_kernel(EcorrArgs a);
 template <int NACC>
