@@ -565,6 +565,12 @@ def main():
                            "HBM and bf16 peaks",
             "fp64_fma_peak_tflops": dfma_peak, "fp64_dmma_peak_tflops": dmma_peak,
             "algorithmic_flops_per_launch": dom["algorithmic_flops_per_launch"],
+            "frac_note": "achieved = SURVEY 8(d)'s algorithmic count (330 FLOP-equivalents per TOA and walker for the chain) / "
+                         "measured kernel time; the chain kernel executes fewer FP64 operations than that count assumes "
+                         "(~102 FP64 instructions per pair: logarithms, square root, divisions and the double-double phase "
+                         "are replaced by expansions around the default parameters), so `frac` can approach 1 while the "
+                         "pipe itself is `pipe_active_ncu` busy (committed ncu capture) - the kernel is latency-bound",
+            "pipe_active_ncu": dom.get("pipe_active_ncu"),
             "kernel_ms": dom["ms"], "sigma_path": "structured (column sums)" if structured else "dense (pair contraction)",
             "kernels": kernels,
             "stage_ms": {"prologue": float(stage_ms[0]), "chain": chain_ms, "sigma_contract": sigma_ms,
