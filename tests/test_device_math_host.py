@@ -88,3 +88,30 @@ def test_speculative_evaluation_is_the_branching_one(name, vb, oracle):
     far[0, sky[0]] += 1e-3          # 200 arcsec off: the Shapiro expansion point is out of reach
     pairs, redo, bad = emul_spec_check(md, far, emit=1)
     assert bad == 0 and redo > 0
+
+
+@pytest.mark.parametrize("name", ["config3_gp", "config2_ell1", "extra_ell1k_swx"])
+def test_spin_phase_difference_route_and_its_gate(name, vb, oracle, monkeypatch):
+    """kFlagDelta (fast build): the spin phase as a difference from its default-parameter value agrees with the oracle's
+    Double64 phase to the same 1e-15 s as the double-double route, and a walker whose spin frequency is 7e-4 Hz off - 1e5
+    cycles over the span, beyond the route's gate on most TOAs - falls back to the double-double code: still the oracle's
+    residuals (hundreds of seconds) to 1e-12 s."""
+    from helpers import emul_spec_check
+    ds = vb.synth.make_dataset(name, oracle_eval_factory(vb, oracle), ntoa=500)
+    md = vb.ModelDescriptor(ds.model, ds.toas)
+    names = list(ds.info["free_names"])
+    spin = [i for i, n in enumerate(names) if n in ("F0", "F1")]
+    W = ds.walkers(3, seed=6)
+    W[1, spin[0]] += 7e-4
+    nt = len(md.toas)
+    y, w, chi, lg = emul_chain(md, W, emit=1, fast=True)
+    monkeypatch.setenv("VELA_B200_DELTA", "0")
+    ydd, _, _, _ = emul_chain(md, W, emit=1, fast=True)
+    monkeypatch.delenv("VELA_B200_DELTA")
+    assert np.any(y[0, :nt] != ydd[0, :nt])                      # the route is in use ...
+    for b in range(3):
+        yo, _ = oracle.residuals(md, W[b])
+        tol = 1e-12 if b == 1 else 1e-15
+        assert np.max(np.abs(y[b, :nt] - yo[:nt])) < tol, (b, np.max(np.abs(y[b, :nt] - yo[:nt])))
+    pairs, redo, bad = emul_spec_check(md, W, emit=1)
+    assert bad == 0 and 0.2 * nt < redo <= nt                    # ... and its gate trips for the walker that is far off

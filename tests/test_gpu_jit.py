@@ -66,3 +66,39 @@ def test_speculative_chain_redoes_walkers_outside_the_gates(name, ntoa, vb):
     np.testing.assert_array_equal(l1, l0)
     np.testing.assert_array_equal(y1, y0)
     np.testing.assert_array_equal(w1, w0)
+
+
+@pytest.mark.parametrize("name,ntoa", [("config3_gp", 900), ("config2_ell1", 700), ("extra_ell1_fbx", None)])
+def test_spin_phase_difference_route(name, ntoa, vb, oracle, monkeypatch):
+    """kFlagDelta (fast build): the spin phase as a difference from its default-parameter value, against the double-double
+    route (VELA_B200_DELTA=0) and the oracle - also for walkers whose spin frequency is so far off that |phase - phase0|
+    exceeds the route's 1e4-cycle gate and the double-double code takes over (in line / through the redo loop)."""
+    ds = vb.synth.make_dataset(name, lambda m, t: vb.Pulsar(m, t), ntoa=ntoa)
+    W = ds.walkers(40, seed=6)
+    names = list(ds.info["free_names"])
+    spin = [i for i, n in enumerate(names) if n in ("F0", "F1")]      # the first element of the F vector, whatever it is called
+    assert spin, names
+    far = [3, 17, 31]
+    W[far, spin[0]] += 7e-4                                             # ~1e5 cycles over the data span
+    psr = vb.Pulsar(ds.model, ds.toas)
+    l1 = psr.lnlike_vectorized(W)
+    y1, w1 = psr.resids_and_Ninvdiag(W[0])
+    yf, _ = psr.resids_and_Ninvdiag(W[far[0]])
+    monkeypatch.setenv("VELA_B200_DELTA", "0")
+    ref = vb.Pulsar(ds.model, ds.toas)
+    monkeypatch.delenv("VELA_B200_DELTA")
+    l0 = ref.lnlike_vectorized(W)
+    y0, w0 = ref.resids_and_Ninvdiag(W[0])
+    yf0, _ = ref.resids_and_Ninvdiag(W[far[0]])
+    nt = len(ds.toas)
+    assert np.max(np.abs(y1[:nt] - y0[:nt])) < 1e-15
+    np.testing.assert_array_equal(w1, w0)
+    # beyond the gate (most TOAs of these walkers) both handles run the double-double code; residuals of hundreds of seconds
+    assert np.max(np.abs(yf[:nt])) > 1.0 and np.max(np.abs(yf[:nt] - yf0[:nt])) < 1e-12
+    np.testing.assert_allclose(l1, l0, rtol=1e-11)
+    yfo, _ = oracle.residuals(vb.ModelDescriptor(ds.model, ds.toas), W[far[0]])
+    assert np.max(np.abs(yf[:nt] - yfo[:nt])) < 1e-9
+    md = vb.ModelDescriptor(ds.model, ds.toas)
+    yo, _ = oracle.residuals(md, W[0])
+    assert np.max(np.abs(y1[:nt] - yo[:nt])) < 1e-12
+    np.testing.assert_allclose(l1[:6], oracle.lnlike_batch(md, W[:6]), rtol=1e-9)
