@@ -90,6 +90,7 @@ inline void fill_shapiro_columns(const VelaModelDesc* desc, double* cols, long s
     if (!ss) return;
     // 1 / x0 = NaN marks "no expansion point": d = (x - x0) * NaN fails |d| < 1e-4 and the device takes log(x / AU)
     for (int b = 0; b < 6; ++b) cols[(size_t)(C_SHAP + 3 * b + 1) * stride + j] = std::nan("");
+    cols[(size_t)(C_SWG + 1) * stride + j] = std::nan("");   // solar_wind_geometry(): no expansion point either
     const double* P = desc->default_values;
     for (int k = 0; k < 6; ++k) if (ss->par[k] < 0) return;
     const double lon = P[ss->par[0]], lat = P[ss->par[1]], pma = P[ss->par[2]], pmd = P[ss->par[3]], posepoch = P[ss->par[5]];
@@ -104,6 +105,20 @@ inline void fill_shapiro_columns(const VelaModelDesc* desc, double* cols, long s
         const double y = L[1], z = L[2];
         L[1] = ce * y - se * z;
         L[2] = se * y + ce * z;
+    }
+    {   // solar-wind geometry AU^2 rho / (r sin rho) as a quadratic in cos(rho) around the default sky position
+        const double r = at(C_RSUN);
+        const double c0 = -(L[0] * at(C_SUN) + L[1] * at(C_SUN + 1) + L[2] * at(C_SUN + 2)) / r;
+        const long double c = c0, w = 1.0L - c * c;
+        if (r > 0.0 && std::isfinite(c0) && w > 1e-12L) {
+            const long double au2_r = 499.00478383615643L * 499.00478383615643L / (long double)r;
+            const long double g = acosl(c) / sqrtl(w), g1 = (c * g - 1.0L) / w, g2 = (g + 3.0L * c * g1) / w;
+            cols[(size_t)(C_SWG + 0) * stride + j] = c0;
+            cols[(size_t)(C_SWG + 1) * stride + j] = (double)w;
+            cols[(size_t)(C_SWG + 2) * stride + j] = (double)(au2_r * g);
+            cols[(size_t)(C_SWG + 3) * stride + j] = (double)(au2_r * g1);
+            cols[(size_t)(C_SWG + 4) * stride + j] = (double)(au2_r * g2 / 2);
+        }
     }
     for (int b = 0; b < 6; ++b) {
         const int c0 = b == 0 ? C_SUN : C_PLANET + 3 * (b - 1);
