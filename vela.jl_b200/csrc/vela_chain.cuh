@@ -292,7 +292,16 @@ __device__ __forceinline__ void chain_body(const ProgramDev& prog, const ChainAr
     int* rExp = reinterpret_cast<int*>(rMan + kRedRing * kRedPitch);
     double* wRed = sRed + (size_t)warp * a.group * 3;
 
-    for (int i = tid; i < nb * row; i += blockDim.x) sP[i] = a.Pext[b0 * row + i];
+    {   // the group's parameter rows -> shared memory, 16 bytes per load and eight loads in flight per thread (one element per
+        // iteration left the block waiting on a dozen dependent round trips: 9 % of the kernel's stall samples); b0 is a
+        // multiple of the group size, so b0 * row doubles is a multiple of 16 bytes
+        const int n = nb * row, n2 = n >> 1;
+        const double2* src = reinterpret_cast<const double2*>(a.Pext + b0 * row);
+        double2* dst = reinterpret_cast<double2*>(sP);
+#pragma unroll 8
+        for (int i = tid; i < n2; i += blockDim.x) dst[i] = src[i];
+        if ((n & 1) && tid == 0) sP[n - 1] = a.Pext[b0 * row + n - 1];
+    }
     for (int i = tid; i < 2 * nb; i += blockDim.x) sTzr[i] = a.tzr_phase[2 * b0 + i];
 
     const long j = (long)blockIdx.x * blockDim.x + tid;
