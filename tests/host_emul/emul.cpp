@@ -77,7 +77,7 @@ int emul_chain(const VelaModelDesc* desc, const double* params, long B, int emit
             ChainEnv e;
             e.toa_base = soa.data(); e.stride = stride; e.j = j;
             e.index_masks = desc->index_masks; e.bit_masks = desc->bit_masks; e.n_toas = nt;
-            e.tzr = false; e.wide = desc->wideband != 0; e.delta = delta && emit != 2;
+            e.tzr = false; e.wide = desc->wideband != 0; e.delta = delta && emit != 2; e.sun_regs = false;
             for (int c = 0; c < 3; ++c) e.d0[c] = e.delta ? soa[(size_t)(C_DELTA + c) * stride + j] : 0.0;
             Corr k = run_chain(pg, P, t, e);
             ResidTerms r = residual_terms(k, t, e.wide, tzr_phase[2 * b], tzr_phase[2 * b + 1], emit);
@@ -143,7 +143,7 @@ int emul_spec_check(const VelaModelDesc* desc, const double* params, long B, int
             ChainEnv e;
             e.toa_base = soa.data(); e.stride = stride; e.j = j;
             e.index_masks = desc->index_masks; e.bit_masks = desc->bit_masks; e.n_toas = nt;
-            e.tzr = false; e.wide = desc->wideband != 0; e.delta = delta && emit != 2;
+            e.tzr = false; e.wide = desc->wideband != 0; e.delta = delta && emit != 2; e.sun_regs = false;
             for (int c = 0; c < 3; ++c) e.d0[c] = e.delta ? soa[(size_t)(C_DELTA + c) * stride + j] : 0.0;
             Corr ks = run_chain(pg, P, t, e, true);
             ResidTerms rs = residual_terms(ks, t, e.wide, tzr_phase[2 * b], tzr_phase[2 * b + 1], emit);

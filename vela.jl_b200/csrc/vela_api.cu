@@ -192,6 +192,7 @@ struct VelaPulsar {
     std::vector<unsigned> ftab;      // fragment table of chol_dmma_kernel; empty = not available
     std::vector<unsigned> ctab;      // compact pair table; empty = some coefficient / index does not fit the 4-byte code
     bool delta_ready = false;        // the C_DELTA columns of every device's TOA table are filled (kFlagDelta in use)
+    int n_index_masks = 0;
     int chol_nb = 8;                 // block width of the Cholesky kernel
     size_t chol_smem_bytes = 0;
     std::vector<DeviceModel> devs;
@@ -616,6 +617,7 @@ void launch_prologue(VelaPulsar* h, DeviceModel& d, const double* d_params, long
 // K1 launch: the NVRTC-specialised kernel of this model when it exists and is enabled, else the generic interpreter
 void launch_chain(VelaPulsar* h, dim3 grid, size_t smem, cudaStream_t st, ChainArgs& ca) {
     ca.delta = (h->delta_ready && ca.emit != 2) ? 1 : 0;   // phase mode returns Double64 itself
+    ca.n_index_masks = h->n_index_masks;
     if (h->use_spec && h->spec_chain && ca.emit == h->spec_emit) {   // other modes (single-sample residuals / phases): generic kernel
         void* args[] = {&ca};
         cudaLaunchKernel((const void*)h->spec_chain, grid, dim3((unsigned)h->chain_threads), args, smem, st);
@@ -951,6 +953,7 @@ VELA_API int vela_b200_create(const VelaModelDesc* desc, VelaHandle* out) {
 
     h->kernel_kind = desc->kernel_kind;
     h->n_toas = desc->n_toas;
+    h->n_index_masks = desc->n_index_masks;
     h->n_rows = desc->wideband ? 2 * desc->n_toas : desc->n_toas;
     h->n_rows_pad = round_up(h->n_rows, 64);
     h->chain_threads = desc->n_toas <= 64 ? 64 : 128;   // 128-thread blocks x 5 resident (tools/probes/gpu_chain_threads_probe.py)
